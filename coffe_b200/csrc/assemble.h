@@ -1,0 +1,218 @@
+// Host-side assembly of the uploaded knots (coffe_b200_tables, include/coffe_b200.h) into one flat
+// arena of doubles plus a `Tables` view onto it.  The same arena is either copied to HBM (engine.cu)
+// or viewed in place by the CPU debugging harness (tests/hostsim).
+#pragma once
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/coffe_b200.h"
+#include "table_build.h"
+#include "tables.cuh"
+
+namespace coffe {
+
+struct Arena {
+    std::vector<double> buf;
+    /* offsets are multiples of 4 doubles so every double4 stays 32-byte aligned */
+    size_t alloc(const size_t n)
+    {
+        const size_t off = buf.size();
+        buf.resize(off + ((n + 3) / 4) * 4, 0.0);
+        return off;
+    }
+    size_t put(const double *p, const size_t n)
+    {
+        const size_t off = alloc(n);
+        if (n) std::memcpy(buf.data() + off, p, n * sizeof(double));
+        return off;
+    }
+    size_t put(const std::vector<build::Coef> &k) { return put(reinterpret_cast<const double *>(k.data()), 4 * k.size()); }
+};
+
+struct SplineOff { size_t x = 0, k = 0; int n = 0; };
+
+struct Layout {
+    size_t bg_z = 0; int bg_n = 0; double bg_inv_dz = 0;
+    size_t bg_a = 0, bg_Hc = 0, bg_D1 = 0, bg_f = 0, bg_G1 = 0, bg_G2 = 0, bg_chi = 0;
+    SplineOff z_of_chi, bias[8], i40, ren0, flat_i1[3], flat_half[4];
+    size_t ifam_x = 0, ifam_k = 0; int ifam_n = 0, ifam_n_small = 0; double ifam_r0 = 1, ifam_inv_dln = 0;
+    size_t ren2d_x = 0, ren2d_node = 0; int ren2d_n = 0; double ren2d_x0 = 0, ren2d_inv_dx = 0;
+    size_t los = 0; int los_n = 0; double los_h = 0;
+    int has_divergent = 0, has_flat_i1 = 0, has_flat_half = 0;
+    double chi_max_table = 0;     /* largest chi of the background table */
+    double r_max_table = 0;       /* largest r of the I^n_l family */
+};
+
+inline SplineView view_of(const SplineOff &s, const double *base)
+{
+    SplineView v;
+    v.x = base + s.x;
+    v.k = reinterpret_cast<const double4 *>(base + s.k);
+    v.n = s.n;
+    return v;
+}
+
+inline Tables make_view(const Layout &L, const double *base)
+{
+    Tables t;
+    std::memset(&t, 0, sizeof(t));
+    t.bg.z = base + L.bg_z; t.bg.n = L.bg_n; t.bg.inv_dz = L.bg_inv_dz;
+    t.bg.a = reinterpret_cast<const double4 *>(base + L.bg_a);
+    t.bg.Hc = reinterpret_cast<const double4 *>(base + L.bg_Hc);
+    t.bg.D1 = reinterpret_cast<const double4 *>(base + L.bg_D1);
+    t.bg.f = reinterpret_cast<const double4 *>(base + L.bg_f);
+    t.bg.G1 = reinterpret_cast<const double4 *>(base + L.bg_G1);
+    t.bg.G2 = reinterpret_cast<const double4 *>(base + L.bg_G2);
+    t.bg.chi = reinterpret_cast<const double4 *>(base + L.bg_chi);
+    t.bg.z_of_chi = view_of(L.z_of_chi, base);
+    for (int i = 0; i < 8; ++i) t.bias[i] = view_of(L.bias[i], base);
+    t.ifam.x = base + L.ifam_x;
+    t.ifam.k = reinterpret_cast<const double4 *>(base + L.ifam_k);
+    t.ifam.n = L.ifam_n; t.ifam.n_small = L.ifam_n_small; t.ifam.r0 = L.ifam_r0; t.ifam.inv_dln = L.ifam_inv_dln;
+    t.i40 = view_of(L.i40, base);
+    t.ren0 = view_of(L.ren0, base);
+    t.ren2d.x = base + L.ren2d_x;
+    t.ren2d.node = reinterpret_cast<const double4 *>(base + L.ren2d_node);
+    t.ren2d.n = L.ren2d_n; t.ren2d.x0 = L.ren2d_x0; t.ren2d.inv_dx = L.ren2d_inv_dx;
+    t.los.v = reinterpret_cast<const double4 *>(base + L.los);
+    t.los.n = L.los_n; t.los.h = L.los_h; t.los.inv_h = L.los_h > 0 ? 1.0 / L.los_h : 0.0;
+    for (int i = 0; i < 3; ++i) t.flat_i1[i] = view_of(L.flat_i1[i], base);
+    for (int i = 0; i < 4; ++i) t.flat_half[i] = view_of(L.flat_half[i], base);
+    t.has_divergent = L.has_divergent; t.has_flat_i1 = L.has_flat_i1; t.has_flat_half = L.has_flat_half;
+    return t;
+}
+
+inline bool put_spline(Arena &A, const coffe_b200_spline &s, const int kind, SplineOff &out, std::string &err, const char *what)
+{
+    if (!s.x || !s.y || s.n < 2) { err = std::string("missing table: ") + what; return false; }
+    for (int i = 0; i + 1 < s.n; ++i)
+        if (!(s.x[i + 1] > s.x[i])) { err = std::string("knots not strictly increasing in table: ") + what; return false; }
+    std::vector<build::Coef> k;
+    if (!build::spline_coefs(kind, s.x, s.y, s.n, k)) { err = std::string("unsupported interpolation type or too few knots for table: ") + what; return false; }
+    out.x = A.put(s.x, s.n);
+    out.k = A.put(k);
+    out.n = s.n;
+    return true;
+}
+
+static const int kFamilyN[N_ITAB] = {0, 0, 0, 1, 1, 2, 2, 3};
+static const int kFamilyL[N_ITAB] = {0, 2, 4, 1, 3, 0, 2, 1};
+
+inline const coffe_b200_integral *find_integral(const coffe_b200_tables &T, const int n, const int l, const int half)
+{
+    for (int i = 0; i < T.n_integrals; ++i)
+        if (T.integrals[i].n == n && T.integrals[i].l == l && (T.integrals[i].half_integer != 0) == (half != 0)) return &T.integrals[i];
+    return nullptr;
+}
+
+/* number of uniformly spaced lambda samples of the line-of-sight table */
+static const int kLosSamples = 2048;
+
+inline bool assemble(const coffe_b200_tables &T, Arena &A, Layout &L, std::string &err)
+{
+    const int kind = T.interp_method;
+    /* ---- background ---- */
+    const coffe_b200_spline &chi = T.background[COFFE_B200_BG_COMOVING_DISTANCE];
+    if (!chi.x || chi.n < 5) { err = "missing background tables"; return false; }
+    const int n = chi.n;
+    L.bg_n = n;
+    L.bg_z = A.put(chi.x, n);
+    L.bg_inv_dz = (n - 1) / (chi.x[n - 1] - chi.x[0]);
+    if (chi.x[0] != 0.0) { err = "background z grid must start at 0"; return false; }
+    struct { int idx; size_t *off; const char *name; } fz[] = {
+        {COFFE_B200_BG_A, &L.bg_a, "a"}, {COFFE_B200_BG_CONFORMAL_HZ, &L.bg_Hc, "conformal_Hz"},
+        {COFFE_B200_BG_D1, &L.bg_D1, "D1"}, {COFFE_B200_BG_F, &L.bg_f, "f"}, {COFFE_B200_BG_G1, &L.bg_G1, "G1"},
+        {COFFE_B200_BG_G2, &L.bg_G2, "G2"}, {COFFE_B200_BG_COMOVING_DISTANCE, &L.bg_chi, "comoving_distance"}};
+    for (auto &e : fz) {
+        const coffe_b200_spline &s = T.background[e.idx];
+        if (!s.x || !s.y || s.n != n) { err = std::string("background table missing or of different size: ") + e.name; return false; }
+        for (int i = 0; i < n; ++i)
+            if (s.x[i] != chi.x[i]) { err = std::string("background tables must share their z knots: ") + e.name; return false; }
+        std::vector<build::Coef> k;
+        if (!build::spline_coefs(kind, s.x, s.y, n, k)) { err = "unsupported interpolation type for the background"; return false; }
+        *e.off = A.put(k);
+    }
+    if (!put_spline(A, T.background[COFFE_B200_BG_Z_AS_CHI], kind, L.z_of_chi, err, "z_as_chi")) return false;
+    L.chi_max_table = T.background[COFFE_B200_BG_Z_AS_CHI].x[T.background[COFFE_B200_BG_Z_AS_CHI].n - 1];
+    static const char *bias_names[8] = {"galaxy_bias1", "galaxy_bias2", "galaxy_bias3", "galaxy_bias4",
+                                        "magnification_bias1", "magnification_bias2", "evolution_bias1", "evolution_bias2"};
+    for (int i = 0; i < 8; ++i) {
+        /* galaxy_bias3/4 only matter for the covariance; tolerate their absence */
+        if ((i == 2 || i == 3) && !T.bias[i].x) { L.bias[i] = SplineOff(); continue; }
+        if (!put_spline(A, T.bias[i], kind, L.bias[i], err, bias_names[i])) return false;
+    }
+    /* ---- I^n_l family on shared knots ---- */
+    const coffe_b200_integral *fam[N_ITAB];
+    for (int t = 0; t < N_ITAB; ++t) {
+        fam[t] = find_integral(T, kFamilyN[t], kFamilyL[t], 0);
+        if (!fam[t]) { err = "missing I^n_l table (need (0,0),(0,2),(0,4),(1,1),(1,3),(2,0),(2,2),(3,1))"; return false; }
+        if (fam[t]->result.n != fam[0]->result.n) { err = "I^n_l tables must share their knots"; return false; }
+    }
+    const int m = fam[0]->result.n;
+    const double *fx = fam[0]->result.x;
+    for (int t = 1; t < N_ITAB; ++t)
+        for (int i = 0; i < m; ++i)
+            if (fam[t]->result.x[i] != fx[i]) { err = "I^n_l tables must share their knots"; return false; }
+    {
+        std::vector<build::Coef> inter((size_t)(m - 1) * N_ITAB);
+        for (int t = 0; t < N_ITAB; ++t) {
+            std::vector<build::Coef> k;
+            if (!build::spline_coefs(kind, fx, fam[t]->result.y, m, k)) { err = "unsupported interpolation type for I^n_l"; return false; }
+            for (int i = 0; i < m - 1; ++i) inter[(size_t)i * N_ITAB + t] = k[i];
+        }
+        L.ifam_x = A.put(fx, m);
+        L.ifam_k = A.put(inter);
+        L.ifam_n = m;
+        L.r_max_table = fx[m - 1];
+        /* longest geometric suffix: x[i] = r0 * q^(i - n_small) */
+        int ns = m - 2;
+        const double lq = std::log(fx[m - 1] / fx[m - 2]);
+        while (ns > 0 && fx[ns - 1] > 0.0 && std::fabs(std::log(fx[ns] / fx[ns - 1]) - lq) < 1e-7 * lq) --ns;
+        if (m - ns < 16) { ns = m - 1; L.ifam_r0 = fx[m - 1]; L.ifam_inv_dln = 0.0; }   /* not log-spaced: always search */
+        else { L.ifam_r0 = fx[ns]; L.ifam_inv_dln = (m - 1 - ns) / std::log(fx[m - 1] / fx[ns]); }
+        L.ifam_n_small = ns;
+    }
+    /* ---- divergent extras ---- */
+    L.has_divergent = 0;
+    if (T.n_renorm > 0) {
+        const coffe_b200_integral *i40 = find_integral(T, 4, 0, 0);
+        if (!i40 || !T.renorm_chi || !T.renorm_z) { err = "renormalisation grid given without I^4_0"; return false; }
+        if (!put_spline(A, i40->result, kind, L.i40, err, "I^4_0")) return false;
+        if (!put_spline(A, T.renorm_zero_separation, kind, L.ren0, err, "renormalization_zero_separation")) return false;
+        const int nr = T.n_renorm;
+        if (nr < 4) { err = "renormalisation grid too small"; return false; }
+        const std::vector<build::Coef> node = build::bicubic_nodes(T.renorm_chi, T.renorm_chi, T.renorm_z, nr, nr);
+        L.ren2d_x = A.put(T.renorm_chi, nr);
+        L.ren2d_node = A.put(node);
+        L.ren2d_n = nr;
+        L.ren2d_x0 = T.renorm_chi[0];
+        L.ren2d_inv_dx = (nr - 1) / (T.renorm_chi[nr - 1] - T.renorm_chi[0]);
+        L.has_divergent = 1;
+    }
+    /* ---- flat-sky closed-form tables (optional) ---- */
+    L.has_flat_i1 = 1;
+    for (int i = 0; i < 3; ++i) {
+        const coffe_b200_integral *t = find_integral(T, 1, 2 * i, 0);
+        if (!t) { L.has_flat_i1 = 0; break; }
+        if (!put_spline(A, t->result, kind, L.flat_i1[i], err, "I^1_l")) return false;
+    }
+    L.has_flat_half = 1;
+    {
+        /* I^{(l-2k+3)/2}_{(l-2k+1)/2}, stored by the reference with n = l-2k+3, l = l-2k+1, i.e.
+           (n, l) = (3,1), (5,3), (7,5) plus (1,-1)          src/functions.c:4210-4230, src/integrals.c:916-1083 */
+        static const int hn[4] = {1, 3, 5, 7}, hl[4] = {-1, 1, 3, 5};
+        for (int i = 0; i < 4; ++i) {
+            const coffe_b200_integral *t = find_integral(T, hn[i], hl[i], 1);
+            if (!t) { L.has_flat_half = 0; break; }
+            if (!put_spline(A, t->result, kind, L.flat_half[i], err, "half-integer I^n_l")) return false;
+        }
+    }
+    /* ---- line-of-sight table (filled later by evaluating the splines above) ---- */
+    L.los_n = kLosSamples;
+    L.los_h = L.chi_max_table / (kLosSamples - 1);
+    L.los = A.alloc((size_t)4 * kLosSamples);
+    return true;
+}
+
+}  // namespace coffe

@@ -1,0 +1,15 @@
+// Host/device portability macros.  Every numerical routine of the hot path is written once as a
+// `COFFE_HD` inline function so that nvcc compiles it into the sm_100a kernels; the same headers also
+// compile under plain g++ for the CPU-only debugging harness in tests/hostsim (test infrastructure:
+// the product library never executes these on the host).
+#pragma once
+#if defined(__CUDACC__)
+#define COFFE_HD __host__ __device__ __forceinline__
+#define COFFE_D __device__ __forceinline__
+#else
+#define COFFE_HD inline
+#define COFFE_D inline
+#include <cmath>
+struct alignas(16) double2 { double x, y; };
+struct alignas(16) double4 { double x, y, z, w; };
+#endif

@@ -1,0 +1,98 @@
+// Per-work-item integration: one (z_mean, separation, mu) point -> the three pieces the reference's
+// dispatcher returns (coffe_integrate, src/signal.c:472-771): local x local (closed form),
+// local x integrated (1-D line-of-sight integral per half) and integrated x integrated (2-D).
+//
+// Written as lane-strided partial sums: a caller with `nlanes` cooperating lanes passes its lane id and
+// reduces the returned partials (warp shuffle on the device; nlanes = 1 in the CPU debugging harness),
+// so the device kernels and the harness execute the same arithmetic on the same nodes.
+#pragma once
+#include "physics.cuh"
+#include "quadrature.cuh"
+
+namespace coffe {
+
+struct Rules {
+    const double *gl_x, *gl_w;      /* bank of Gauss-Legendre rules on [0,1] (quadrature.cuh: rule_offset) */
+    int n_panel_si, n_panel_di;
+    int n_outer;                    /* 0 = auto_n_outer(sep) */
+    double panel_w_mpc, panel_du, eps_min, tail_ratio;
+};
+
+/* integral over lambda in [0, hi] of f(lambda), with a ridge (closest approach) at `center` of width
+   eps.  Lane-strided partial sum. */
+template <class F>
+COFFE_HD double ridge_integrate(const F &f, const double hi, const double center, const double eps,
+                                const Rules &q, const int n_panel, const int lane, const int nlanes)
+{
+    const double *panel_x = q.gl_x + rule_offset(n_panel), *panel_w = q.gl_w + rule_offset(n_panel);
+    const PanelPlan plan = panel_plan(eps, q.eps_min, q.panel_w_mpc, q.panel_du, q.tail_ratio);
+    /* negative side: |d| in [a_neg, b_neg]; positive side: |d| in [0, b_pos] (center >= 0 always) */
+    const double b_neg = center;
+    const double a_neg = center > hi ? center - hi : 0.0;
+    const double b_pos = hi - center;
+    const int k_neg = panel_count(plan, b_neg);
+    const int k_pos = b_pos > 0.0 ? panel_count(plan, b_pos) : 0;
+    const int total = (k_neg + k_pos) * n_panel;
+    double acc = 0.0;
+    for (int idx = lane; idx < total; idx += nlanes) {
+        const int p = idx / n_panel, j = idx - p * n_panel;
+        const bool neg = p < k_neg;
+        const int k = neg ? p : p - k_neg;
+        double lo = panel_break(plan, k), up = panel_break(plan, k + 1);
+        const double a = neg ? a_neg : 0.0, b = neg ? b_neg : b_pos;
+        if (lo < a) lo = a;
+        if (up > b) up = b;
+        const double width = up - lo;
+        if (width <= 0.0) continue;
+        const double d = lo + width * panel_x[j];
+        const double lambda = neg ? center - d : center + d;
+        acc += width * panel_w[j] * f(lambda);
+    }
+    return acc;
+}
+
+struct SIFunctor {
+    const Tables *t; const SIHalf *h; const Geometry *g; const double4 *los; int los_n; double los_inv_h;
+    COFFE_HD double operator()(const double lambda) const
+    {
+        return si_half_eval(*t, *h, *g, lambda, los_eval(los, los_n, los_inv_h, lambda));
+    }
+};
+
+/* one half of the local x integrated piece, per unit x (the reference integrates x in [0,1], src/signal.c:584-606) */
+COFFE_HD double si_half_partial(const Tables &t, const Rules &q, const Geometry &g, const SIHalf &h,
+                                const double4 *los, const int lane, const int nlanes)
+{
+    SIFunctor f{&t, &h, &g, los, t.los.n, t.los.inv_h};
+    const double center = h.cs * g.c;
+    const double eps = h.cs * sqrt(g.s2);
+    return ridge_integrate(f, h.co, center, eps, q, q.n_panel_si, lane, nlanes) / h.co;
+}
+
+struct DIFunctor {
+    const Tables *t; const DIConst *k; const Geometry *g; const double4 *los; int los_n; double los_inv_h;
+    double l1; double4 los1;
+    COFFE_HD double operator()(const double l2) const
+    {
+        return di_eval(*t, *k, *g, l1, l2, los1, los_eval(los, los_n, los_inv_h, l2));
+    }
+};
+
+/* integrated x integrated piece per unit (x1, x2): outer nodes strided over `ngroups` groups of
+   `nlanes` lanes (warps of a CTA on the device) */
+COFFE_HD double di_partial(const Tables &t, const Rules &q, const Geometry &g, const DIConst &k, const double4 *los,
+                           const int group, const int ngroups, const int lane, const int nlanes)
+{
+    double acc = 0.0;
+    const double sth = sqrt(g.s2);
+    const int n_outer = q.n_outer > 0 ? q.n_outer : auto_n_outer(g.sep);
+    const double *outer_x = q.gl_x + rule_offset(n_outer), *outer_w = q.gl_w + rule_offset(n_outer);
+    for (int io = group; io < n_outer; io += ngroups) {
+        const double l1 = g.chi1 * outer_x[io];
+        DIFunctor f{&t, &k, &g, los, t.los.n, t.los.inv_h, l1, los_eval(los, t.los.n, t.los.inv_h, l1)};
+        acc += outer_w[io] * ridge_integrate(f, g.chi2, l1 * g.c, l1 * sth, q, q.n_panel_di, lane, nlanes);
+    }
+    return acc / g.chi2;
+}
+
+}  // namespace coffe

@@ -1,0 +1,454 @@
+// Integrands of the relativistic 2-point function: every auto/cross term of
+// {den, rsd, d1, d2, g1, g2, g3} (local) and {len, g4, g5} (line-of-sight integrated).
+//
+// What is computed follows the reference term by term (src/functions.c):
+//   local x local        functions_nonintegrated      src/functions.c:89-1484
+//   local x integrated   functions_single_integrated  src/functions.c:1486-3457
+//   integrated^2         functions_double_integrated  src/functions.c:3460-4016
+// but it is organised for a GPU inner loop instead of as 55 independent branches:
+//   * each term is (amplitude that depends only on the two end points) x (geometric bracket of
+//     I^n_l(r) values), so the amplitudes are folded once per (z, r, mu) work item into a handful of
+//     coefficients and the per-node work is one interleaved table record plus polynomial brackets;
+//   * the three potential terms g1, g2, g3 enter every formula only through
+//     Phi_i = [g1](1+G_i) + [g2](5 s_i - 2) + [g3](f_i - 1), so their 6 autos/crosses and 12 crosses
+//     with den/rsd/d1/d2/len/g4/g5 collapse to bilinear forms in Phi_1, Phi_2;
+//   * the two halves of every local x integrated term are the same function with the roles of the two
+//     galaxies swapped, so one evaluator (si_half_eval) serves both, each half on its own nodes.
+// Reference quirks reproduced on purpose: d1-len second half uses bg.G1 and s2
+// (functions.c:2776-2779), den-g5 multiplies by a(z) (functions.c:3178-3187), g5-len uses Hc(Hc-1)
+// (functions.c:3930-3959), rsd-len switches its I^0_4 bracket at |mu| >= 0.999 (functions.c:2199),
+// len-len falls back to 4 + 24 l1 l2 I^1_1(0)/15 for r^2 <= 1e-20 (functions.c:3814-3833).
+#pragma once
+#include "tables.cuh"
+
+namespace coffe {
+
+struct Options {
+    int den, rsd, len, d1, d2, g1, g2, g3, g4, g5;
+    int only_cross;
+    int flatsky_local, flatsky_local_nonlocal, flatsky_nonlocal;
+    int divergent;
+    double Om;     /* Omega0_cdm + Omega0_baryon */
+    double H0h;    /* COFFE_H0 * h  [1/Mpc] */
+};
+
+COFFE_HD bool opt_has_ni(const Options &o) { return o.den || o.rsd || o.d1 || o.d2 || o.g1 || o.g2 || o.g3; }
+COFFE_HD bool opt_has_integrated(const Options &o) { return o.len || o.g4 || o.g5; }
+COFFE_HD bool opt_has_si(const Options &o) { return opt_has_ni(o) && opt_has_integrated(o); }
+
+/* everything the formulas need at one end point (galaxy i = 1 or 2 at comoving distance chi) */
+struct EndVals {
+    double chi, z;
+    double a, Hc, D1, f;
+    double G;      /* bg.G1 for end 1, bg.G2 for end 2 */
+    double G1raw;  /* bg.G1 regardless of the end (needed by the d1-len quirk) */
+    double b, s, fevo;
+    double phi;    /* [g1](1+G) + [g2](5s-2) + [g3](f-1) */
+    double phi_auto[3];
+};
+
+COFFE_HD EndVals end_eval(const Options &o, const Tables &t, const double chi, const int which /* 1 or 2 */)
+{
+    EndVals e;
+    e.chi = chi;
+    e.z = spline_eval(t.bg.z_of_chi, chi);
+    const BackgroundAtZ b = bg_eval_all(t.bg, e.z);
+    e.a = b.a; e.Hc = b.Hc; e.D1 = b.D1; e.f = b.f;
+    e.G = (which == 1) ? b.G1 : b.G2;
+    e.G1raw = b.G1;
+    e.b = spline_eval(t.bias[which == 1 ? B_GAL1 : B_GAL2], e.z);
+    e.s = spline_eval(t.bias[which == 1 ? B_MAG1 : B_MAG2], e.z);
+    e.fevo = spline_eval(t.bias[which == 1 ? B_EVO1 : B_EVO2], e.z);
+    e.phi_auto[0] = o.g1 ? (1.0 + e.G) : 0.0;
+    e.phi_auto[1] = o.g2 ? (5.0 * e.s - 2.0) : 0.0;
+    e.phi_auto[2] = o.g3 ? (e.f - 1.0) : 0.0;
+    e.phi = e.phi_auto[0] + e.phi_auto[1] + e.phi_auto[2];
+    return e;
+}
+
+struct Geometry {
+    double chi_mean, sep, mu;
+    double chi1, chi2;
+    double c;      /* cos(theta)            src/functions.c:101-103 */
+    double omc;    /* 1 - cos(theta), evaluated without cancellation */
+    double s2;     /* 1 - cos^2(theta) */
+};
+
+COFFE_HD Geometry geometry(const double chi_mean, const double sep, const double mu)
+{
+    Geometry g;
+    g.chi_mean = chi_mean; g.sep = sep; g.mu = mu;
+    g.chi1 = chi_mean - sep * mu / 2.;
+    g.chi2 = chi_mean + sep * mu / 2.;
+    const double den = 2. * chi_mean * chi_mean - mu * mu * sep * sep / 2.;
+    g.c = (2. * chi_mean * chi_mean - sep * sep + mu * mu * sep * sep / 2.) / den;
+    g.omc = sep * sep * (1.0 - mu * mu) / den;
+    g.s2 = g.omc * (1.0 + g.c);
+    return g;
+}
+
+/* ---- values at the separation / mean redshift, constant over mu ------------------------------ */
+struct SepConst {
+    double i[N_ITAB];   /* I^n_l(sep) */
+    double i40;         /* I^4_0(sep) */
+    /* mean-redshift values (flat-sky branches and the final growth factor) */
+    double z_mean, chi_mean, fm, Hm, bm1, bm2, Gm1, Gm2, D1m, sm1, sm2;
+};
+
+COFFE_HD void ifam_eval_all(const IntegralFamilyView &t, const double r, double out[N_ITAB])
+{
+    const int i = ifam_index(t, r);
+    const double dx = r - t.x[i];
+    const double4 *k = t.k + (size_t)i * N_ITAB;
+#pragma unroll
+    for (int j = 0; j < N_ITAB; ++j) out[j] = cubic_eval(k[j], dx);
+}
+
+COFFE_HD SepConst sep_const(const Options &o, const Tables &t, const double z_mean, const double sep)
+{
+    SepConst s;
+    ifam_eval_all(t.ifam, sep, s.i);
+    s.i40 = o.divergent ? spline_eval(t.i40, sep) : 0.0;
+    s.z_mean = z_mean;
+    s.chi_mean = bg_chi(t.bg, z_mean);
+    const BackgroundAtZ b = bg_eval_all(t.bg, z_mean);
+    s.fm = b.f; s.Hm = b.Hc; s.Gm1 = b.G1; s.Gm2 = b.G2; s.D1m = b.D1;
+    s.bm1 = spline_eval(t.bias[B_GAL1], z_mean);
+    s.bm2 = spline_eval(t.bias[B_GAL2], z_mean);
+    s.sm1 = spline_eval(t.bias[B_MAG1], z_mean);
+    s.sm2 = spline_eval(t.bias[B_MAG2], z_mean);
+    return s;
+}
+
+COFFE_HD double legendre_p(const int l, const double x)
+{
+    if (l == 0) return 1.0;
+    double p0 = 1.0, p1 = x;
+    for (int k = 1; k < l; ++k) {
+        const double p2 = ((2.0 * k + 1.0) * x * p1 - k * p0) / (k + 1.0);
+        p0 = p1; p1 = p2;
+    }
+    return p1;
+}
+
+/* ---- local x local ------------------------------------------------------------------------------ */
+COFFE_HD double ni_eval(const Options &o, const Tables &t, const SepConst &sc, const Geometry &g,
+                        const EndVals &e1, const EndVals &e2)
+{
+    const double c = g.c, c2 = c * c, s2 = g.s2;
+    const double chi1 = g.chi1, chi2 = g.chi2, r = g.sep, r2 = r * r, mu = g.mu;
+    const double Om = o.Om, h2 = o.H0h * o.H0h, h4 = h2 * h2;
+    const double f1 = e1.f, f2 = e2.f, H1 = e1.Hc, H2 = e2.Hc, b1 = e1.b, b2 = e2.b;
+    const double G1 = e1.G, G2 = e2.G, a1 = e1.a, a2 = e2.a;
+    const double q1 = 3.0 - e1.fevo, q2 = 3.0 - e2.fevo;
+    const double *I = sc.i;
+    const bool autos = !o.only_cross;
+    double res = 0.0;
+
+    /* divergent bracket I^4_0(r) - renormalisation(chi1, chi2)   src/functions.c:574-597 */
+    double ren = 0.0;
+    if (o.divergent && (o.d2 || o.g1 || o.g2 || o.g3))
+        ren = sc.i40 - renorm2d_eval(t.ren2d, chi1, chi2);
+
+    if (o.flatsky_local) {
+        const double p2 = 0.5 * (3.0 * mu * mu - 1.0);
+        const double fm = sc.fm, Hm = sc.Hm;
+        if (o.den && autos) res += sc.bm1 * sc.bm2 * I[I00];                                  /* :133-199 */
+        if (o.rsd && autos)                                                                    /* :236-297 */
+            res += fm * fm * I[I00] / 5. - 4 * fm * fm * I[I02] / 7. * p2 + 8 * fm * fm * I[I04] / 35. * legendre_p(4, mu);
+        if (o.d1 && autos)                                                                     /* :369-440 */
+            res += Hm * Hm * fm * fm * sc.Gm1 * sc.Gm2 * I[I20] / 3.
+                 + 2 * Hm * Hm * fm * fm * sc.Gm1 * sc.Gm2 * r2 * I[I22] * p2 / 3.;
+        if (o.den && o.rsd)                                                                    /* :676-738 */
+            res += (sc.bm1 * fm / 3. + sc.bm2 * fm / 3.) * I[I00] - (2 * sc.bm1 * fm / 3. + 2 * sc.bm2 * fm / 3.) * I[I02] * p2;
+        if (o.den && o.d1)                                                                     /* :789-809 */
+            res += (sc.bm1 * fm * Hm * sc.Gm2 * mu + sc.bm2 * fm * Hm * sc.Gm1 * (-mu)) * r * I[I11];
+        if (o.rsd && o.d1)                                                                     /* :893-931 */
+            res += (-3. / 5. * (fm * fm * Hm * sc.Gm2 * (-mu) + fm * fm * Hm * sc.Gm1 * mu) * I[I11] * r
+                    + (fm * fm * Hm * sc.Gm2 * 2. / 5. * legendre_p(3, -mu) + fm * fm * Hm * sc.Gm1 * 2. / 5. * legendre_p(3, mu)) * I[I13] * r);
+    }
+    else {
+        if (o.den && autos) res += b1 * b2 * I[I00];                                          /* :200-228 */
+        if (o.rsd && autos) {                                                                  /* :299-360 */
+            /* The reference's I^0_4 coefficient
+                   [4(3c^2-1)(chi1^4+chi2^4) + chi1 chi2 (3+c^2)(3(3+c^2) chi1 chi2 - 8(chi1^2+chi2^2) c)] / (35 r^4)
+               cancels from O((chi/r)^4) to O(1) (rounding noise ~1e-6 at r = 15 Mpc in the reference).  With
+               c = (chi1^2+chi2^2-r^2)/(2 chi1 chi2) and chi2^2-chi1^2 = 2 chi_mean r mu it is identically
+                   [560 X^2 mu^4 - 240 X mu^2 S + 12 S^2 + 24 X mu^2 r^2 + 4 r^2 S + 3 r^4] / (16 chi1^2 chi2^2 35),
+               X = chi_mean^2, S = chi1^2 + chi2^2, which has no cancellation. */
+            const double X = g.chi_mean * g.chi_mean, S = chi1 * chi1 + chi2 * chi2, m2 = mu * mu;
+            const double k4 = (560 * X * X * m2 * m2 - 240 * X * m2 * S + 12 * S * S + 24 * X * m2 * r2 + 4 * r2 * S + 3 * r2 * r2)
+                            / (16. * chi1 * chi1 * chi2 * chi2 * 35.);
+            res += f1 * f2 * (1 + 2 * c2) / 15 * I[I00]
+                 - f1 * f2 / 21. * ((1 + 11. * c2) - 18 * c * s2 * chi1 * chi2 / r2) * I[I02]
+                 + f1 * f2 * k4 * I[I04];
+        }
+        if (o.d1 && autos)                                                                     /* :441-571 */
+            res += H1 * H2 * f1 * f2 * G1 * G2 * (c * I[I20] / 3. - ((chi2 - chi1 * c) * (chi1 - chi2 * c) + r2 * c / 3.) * I[I22]);
+        if (o.den && o.rsd)                                                                    /* :739-786 */
+            res += (b1 * f2 / 3. + b2 * f1 / 3.) * I[I00]
+                 - (b1 * f2 * (2. / 3. - s2 * (chi1 / r) * (chi1 / r)) + b2 * f1 * (2. / 3. - s2 * (chi2 / r) * (chi2 / r))) * I[I02];
+        if (o.den && o.d1)                                                                     /* :810-827 */
+            res += -(b1 * f2 * H2 * G2 * (chi1 * c - chi2) + b2 * f1 * H1 * G1 * (chi2 * c - chi1)) * I[I11];
+        if (o.rsd && o.d1) {                                                                   /* :932-1022 */
+            const double pa = (1. - 3 * c2) * chi2 * chi2 * chi2 + c * (5. + c2) * chi2 * chi2 * chi1
+                            - 2 * (2. + c2) * chi2 * chi1 * chi1 + 2 * chi1 * chi1 * chi1 * c;
+            const double pb = (1. - 3 * c2) * chi1 * chi1 * chi1 + c * (5. + c2) * chi1 * chi1 * chi2
+                            - 2 * (2. + c2) * chi1 * chi2 * chi2 + 2 * chi2 * chi2 * chi2 * c;
+            res += (f1 * f2 * H2 * G2 * ((1. + 2 * c2) * chi2 - 3 * chi1 * c) / 5.
+                    + f2 * f1 * H1 * G1 * ((1. + 2 * c2) * chi1 - 3 * chi2 * c) / 5.) * I[I11]
+                 + (f1 * f2 * H2 * G2 * pa / 5 + f2 * f1 * H1 * G1 * pb / 5) * I[I13] / r2;
+        }
+    }
+    /* the remaining terms have no flat-sky variant in the reference */
+    if (o.d2 && autos) res += q1 * q2 * H1 * H1 * H2 * H2 * f1 * f2 * ren;                     /* :574-597 */
+    if (o.g1 || o.g2 || o.g3) {
+        /* g_i-g_j autos and crosses: 9 Om^2/(4 a1 a2) x bilinear form in Phi      :598-669, 1289-1368 */
+        double bil = e1.phi * e2.phi;
+        if (!autos) bil -= e1.phi_auto[0] * e2.phi_auto[0] + e1.phi_auto[1] * e2.phi_auto[1] + e1.phi_auto[2] * e2.phi_auto[2];
+        res += h4 * (9 * Om * Om / 4 / a1 / a2 * bil * ren);
+        if (o.den)                                                                             /* :840-881 */
+            res += h2 * (-(b1 * 3 * Om / 2 / a2 * e2.phi + b2 * 3 * Om / 2 / a1 * e1.phi) * I[I20]);
+        if (o.rsd) {                                                                           /* :1040-1095 */
+            const double T1 = 2. / 3 * r2 - s2 * chi1 * chi1, T2 = 2. / 3 * r2 - s2 * chi2 * chi2;
+            res += h2 * (-(Om / 2. / a2 * f1 * e2.phi + Om / 2. / a1 * f2 * e1.phi) * I[I20]
+                         + (3 * Om / 2. / a2 * f1 * e2.phi * T2 + 3 * Om / 2. / a1 * f2 * e1.phi * T1) * I[I22]);
+        }
+        if (o.d1)                                                                              /* :1110-1149 */
+            res += h2 * ((3 * Om / 2. / a2 * H1 * f1 * e2.phi * (chi2 * c - chi1)
+                          + 3 * Om / 2. / a1 * H2 * f2 * e1.phi * (chi1 * c - chi2)) * I[I31]);
+        if (o.d2)                                                                              /* :1150-1230 */
+            res += h2 * (-(3 * q1 * Om / 2. / a2 * H1 * H1 * f1 * e2.phi + 3 * q2 * Om / 2. / a1 * H2 * H2 * f2 * e1.phi) * ren);
+    }
+    if (o.den && o.d2) res += (q2 * b1 * f2 * H2 * H2 + q1 * b2 * f1 * H1 * H1) * I[I20];      /* :828-839 */
+    if (o.rsd && o.d2) {                                                                       /* :1023-1039 */
+        const double T1 = 2. / 3 * r2 - s2 * chi1 * chi1, T2 = 2. / 3 * r2 - s2 * chi2 * chi2;
+        res += (q2 / 3 * f1 * f2 * H2 * H2 + q1 / 3 * f2 * f1 * H1 * H1) * I[I20]
+             - (q2 * f1 * f2 * H2 * H2 * T2 + q1 * f2 * f1 * H1 * H1 * T1) * I[I22];
+    }
+    if (o.d1 && o.d2)                                                                          /* :1098-1109 */
+        res += -(q2 * H1 * H2 * H2 * f1 * f2 * (chi2 * c - chi1) + q1 * H2 * H1 * H1 * f2 * f1 * (chi1 * c - chi2)) * I[I31];
+
+    /* growth: D1(z_mean)^2 in flat-sky, D1(z1) D1(z2) otherwise            src/functions.c:1456-1467 */
+    return o.flatsky_local ? res * sc.D1m * sc.D1m : res * e1.D1 * e2.D1;
+}
+
+/* ---- local x integrated ------------------------------------------------------------------------
+   One half: the local effect sits at the "source" end (distance cs), the integrated effect runs along
+   the other line of sight, lambda in [0, co].  Amplitudes follow src/functions.c:1558-3423. */
+struct SIHalf {
+    double cs, co;
+    double a_denlen, a_rsdlen, a_d1len, a_pot;      /* x (co - lambda) W(lambda) x bracket */
+    double g4_i20, g4_rsd, g4_d1, g4_ren;           /* x W(lambda) x bracket */
+    double g5_i20, g5_rsd, g5_d1, g5_ren;           /* x V(lambda) x {Wa | W} x bracket (co, G_other folded in) */
+    int alt_i04;                                    /* |mu| >= 0.999 */
+    int any_lens, any_g4, any_g5, need_ren;
+};
+
+/* src = local end, oth = the end whose line of sight is integrated.  `first` selects the quirks of the
+   first (src = 1) or second (src = 2) summand. */
+COFFE_HD SIHalf si_half_setup(const Options &o, const Geometry &g, const EndVals &src, const EndVals &oth, const bool first)
+{
+    SIHalf h;
+    const double Om = o.Om, h2 = o.H0h * o.H0h, h4 = h2 * h2;
+    h.cs = src.chi; h.co = oth.chi;
+    const double m_oth = 2.0 - 5.0 * oth.s;      /* (2 - 5 s) of the lensed galaxy */
+    const double q = 3.0 - src.fevo;
+    h.a_denlen = (o.den && o.len && !o.flatsky_local_nonlocal) ? h2 * (-3 * Om / 2.) * src.b * m_oth * src.D1 : 0.0;
+    h.a_rsdlen = (o.rsd && o.len && !o.flatsky_local_nonlocal) ? h2 * (3 * Om / 2.) * src.f * m_oth * src.D1 : 0.0;
+    /* d1-len: both summands use bg.G1 and (2 - 5 s2)      src/functions.c:2490-2493, 2776-2779 */
+    {
+        const double m_quirk = first ? m_oth : (2.0 - 5.0 * src.s);
+        h.a_d1len = (o.d1 && o.len && !o.flatsky_local_nonlocal) ? h2 * (3 * Om / 2.) * src.Hc * src.f * src.G1raw * m_quirk * src.D1 : 0.0;
+    }
+    h.a_pot = 0.0;
+    if (o.len) {
+        if (o.d2) h.a_pot += h2 * (-3 * Om / 2.) * q * src.f * src.Hc * src.Hc * m_oth * src.D1;         /* :3000-3030 */
+        if (o.g1 || o.g2 || o.g3) h.a_pot += h4 * (9 * Om * Om / 4.) * src.phi * m_oth * src.D1;            /* :3031-3121 */
+    }
+    h.g4_i20 = h.g4_rsd = h.g4_d1 = h.g4_ren = 0.0;
+    if (o.g4) {
+        if (o.den) h.g4_i20 = h2 * (-3 * Om) * src.b * m_oth * src.D1;                                      /* :3122-3141 */
+        if (o.rsd) h.g4_rsd = h2 * (3 * Om) * src.f * m_oth * src.D1;                                       /* :3164-3191 */
+        if (o.d1) h.g4_d1 = h2 * (3 * Om) * src.Hc * src.f * m_oth * src.D1;                               /* :3222-3238 */
+        if (o.d2) h.g4_ren += h2 * (-3 * Om) * q * src.f * src.Hc * src.Hc * m_oth * src.D1;                /* :3260-3278 */
+        if (o.g1 || o.g2 || o.g3) h.g4_ren += h4 * (9 * Om * Om / 2.) * src.phi * m_oth * src.D1 / src.a;   /* :3300-3320 ... */
+    }
+    h.g5_i20 = h.g5_rsd = h.g5_d1 = h.g5_ren = 0.0;
+    if (o.g5) {
+        const double pre = oth.chi * oth.G;      /* chi_other x G_other(z_other) */
+        if (o.den) h.g5_i20 = h2 * (-3 * Om) * pre * src.b * src.D1;                                       /* :3142-3163 */
+        if (o.rsd) h.g5_rsd = h2 * (3 * Om) * pre * src.f * src.D1;                                        /* :3192-3221 */
+        if (o.d1) h.g5_d1 = h2 * (3 * Om) * pre * src.Hc * src.f * src.D1;                                /* :3239-3259 */
+        if (o.d2) h.g5_ren += h2 * (-3 * Om) * pre * q * src.f * src.Hc * src.Hc * src.D1;                  /* :3279-3299 */
+        if (o.g1 || o.g2 || o.g3) h.g5_ren += h4 * (9 * Om * Om / 2.) * pre * src.phi * src.D1 / src.a;     /* :3321-3423 */
+    }
+    h.alt_i04 = fabs(g.mu) >= 0.999;
+    h.any_lens = (h.a_denlen != 0.0) || (h.a_rsdlen != 0.0) || (h.a_d1len != 0.0) || (h.a_pot != 0.0);
+    h.any_g4 = o.g4 && opt_has_ni(o);
+    h.any_g5 = o.g5 && opt_has_ni(o);
+    h.need_ren = o.divergent && ((h.g4_ren != 0.0) || (h.g5_ren != 0.0));
+    return h;
+}
+
+/* integrand of one half at lambda (distance along the integrated line of sight), per unit x = lambda/co.
+   los = {W, V, U, Wa}(lambda). */
+COFFE_HD double si_half_eval(const Tables &t, const SIHalf &h, const Geometry &g, const double lambda, const double4 los)
+{
+    const double c = g.c, c2 = c * c, s2 = g.s2;
+    const double cs = h.cs, l = lambda;
+    /* r^2 = l^2 + cs^2 - 2 cs l cos(theta), written without the cancellation */
+    const double dl = l - cs;
+    double rr = dl * dl + 2.0 * cs * l * g.omc;
+    if (rr < 0) rr = 0;
+    const double R = sqrt(rr);
+    double I[N_ITAB];
+    ifam_eval_all(t.ifam, R, I);
+    const double W = los.x, V = los.y, Wa = los.w;
+    double res = 0.0;
+    if (h.any_lens) {
+        double br = 0.0;
+        if (rr != 0.0) {
+            const double irr = 1.0 / rr;
+            const double tc = 2 * c2 - 1;
+            if (h.a_denlen != 0.0)                                                                  /* :1592-1640 */
+                br += h.a_denlen * (2 * cs * c * I[I11] - cs * cs * l * s2 * I[I02] * irr);
+            if (h.a_rsdlen != 0.0) {                                                                /* :2059-2390 */
+                double b = (l - 6 * cs * c + 3 * l * tc) * I[I00] / 15.
+                         - (6 * cs * cs * cs * c - cs * cs * l * (9 * c2 + 11) + cs * l * l * c * (3 * tc + 19) - 2 * l * l * l * (3 * tc + 1)) * I[I02] * irr / 21.;
+                if (!h.alt_i04) {
+                    /* the reference's quintic (functions.c:2205-2214) cancels from O(chi^5) to O(chi r^4); the same
+                       polynomial expanded in the small quantities d = l - cs and w = 1 - cos(theta): */
+                    const double w = g.omc, d2 = dl * dl, cs2 = cs * cs, l2 = l * l;
+                    const double p5 = -4 * d2 * d2 * (2 * cs + dl)
+                                    + w * (4 * d2 * (12 * cs2 * cs + 23 * cs2 * dl + 15 * cs * d2 + 3 * d2 * dl)
+                                    + w * (-6 * l2 * (2 * cs2 * cs + 6 * cs2 * dl + 6 * cs * d2 + d2 * dl)
+                                    + w * (2 * cs * l2 * (2 * cs2 + 4 * cs * dl + 3 * d2)
+                                    + w * cs2 * l2 * l)));
+                    b += -p5 * I[I04] * irr * irr / 35.;
+                }
+                else b += 4. * (l + cs) * I[I04] / 35.;
+                br += h.a_rsdlen * b;
+            }
+            if (h.a_d1len != 0.0) {                                                                 /* :2490-2560 */
+                const double cs2 = cs * cs, l2 = l * l;
+                br += h.a_d1len * (2 * (c * (l2 - 2 * cs2) + cs * l * (2 * tc - 1)) * I[I11] / 15. + 2 * c * I[I20] / 3.
+                                   - (4 * cs2 * cs2 * c - cs2 * cs * l * (c2 + 9) + cs2 * l2 * c * (c2 + 5) - 2 * cs * l2 * l * (tc - 2) - 2 * l2 * l2 * c) * I[I13] * irr / 15.);
+            }
+            if (h.a_pot != 0.0)                                                                     /* :3000-3121 */
+                br += h.a_pot * (2 * cs * c * I[I31] - cs * cs * l * s2 * I[I22]);
+            res += (h.co - l) * W * br;
+        }
+        else {
+            /* r == 0 limits                                             src/functions.c:1641-1760, 2391-2480, 2631-2990 */
+            if (h.a_denlen != 0.0) br += h.a_denlen * 2 * cs * I[I11];
+            if (h.a_d1len != 0.0) br += h.a_d1len * 2 * I[I20] / 3.;
+            if (h.a_pot != 0.0) br += h.a_pot * (2 * cs * c * I[I31] - cs * cs * l * s2 * I[I22]);
+            res += (h.co - l) * W * br;
+            if (h.a_rsdlen != 0.0) res += h.a_rsdlen * (h.co - cs) * W * (-2 * cs * I[I00] / 15.);
+        }
+    }
+    if (h.any_g4 || h.any_g5) {
+        double ren = 0.0;
+        if (h.need_ren)                                                                             /* :1524-1556 */
+            ren = (rr == 0.0) ? spline_eval(t.ren0, l) : spline_eval(t.i40, R) - renorm2d_eval(t.ren2d, l, cs);
+        const double b_rsd = (2 * rr / 3. - s2 * l * l) * I[I22] - I[I20] / 3.;
+        const double b_d1 = (l * c - cs) * I[I31];
+        if (h.any_g4) res += W * (h.g4_i20 * I[I20] + h.g4_rsd * b_rsd + h.g4_d1 * b_d1 + h.g4_ren * ren);
+        if (h.any_g5) res += V * (h.g5_i20 * Wa * I[I20] + W * (h.g5_rsd * b_rsd + h.g5_d1 * b_d1 + h.g5_ren * ren));
+    }
+    return res;
+}
+
+/* ---- integrated x integrated ------------------------------------------------------------------- */
+struct DIConst {
+    double k_ll;              /* 9 Om^2 (2-5s1)(2-5s2)/4                        len-len  :3516-3836 */
+    double k_4l;              /* 9 Om^2 (2-5s1)(2-5s2)/2                        g4-len   :3876-3918 */
+    double k_5la, k_5lb;      /* 9 Om^2/2 (2-5s2) G1 chi1 ; (2-5s1) G2 chi2     g5-len   :3919-3965 */
+    double k_44;              /* 9 Om^2 (2-5s1)(2-5s2)                          g4-g4    :3837-3852 */
+    double k_55;              /* 9 Om^2 G1 G2 chi1 chi2                         g5-g5    :3853-3875 */
+    double k_45a, k_45b;      /* 9 Om^2 G2 (2-5s1) chi2 ; G1 (2-5s2) chi1       g4-g5    :3966-3988 */
+    double h4;
+    int any_ll, any_pl, any_ren;
+};
+
+COFFE_HD DIConst di_setup(const Options &o, const EndVals &e1, const EndVals &e2)
+{
+    DIConst k;
+    const double Om2 = o.Om * o.Om;
+    const double m1 = 2.0 - 5.0 * e1.s, m2 = 2.0 - 5.0 * e2.s;
+    const bool autos = !o.only_cross;
+    k.k_ll = (o.len && autos && !o.flatsky_nonlocal) ? 9. * Om2 * m1 * m2 / 4. : 0.0;
+    k.k_4l = (o.g4 && o.len) ? 9 * Om2 / 2. * m1 * m2 : 0.0;
+    k.k_5la = (o.g5 && o.len) ? 9 * Om2 / 2. * m2 * e1.G * e1.chi : 0.0;
+    k.k_5lb = (o.g5 && o.len) ? 9 * Om2 / 2. * m1 * e2.G * e2.chi : 0.0;
+    k.k_44 = (o.g4 && autos) ? 9 * Om2 * m1 * m2 : 0.0;
+    k.k_55 = (o.g5 && autos) ? 9 * Om2 * e1.G * e2.G * e1.chi * e2.chi : 0.0;
+    k.k_45a = (o.g4 && o.g5) ? 9 * Om2 * e2.G * m1 * e2.chi : 0.0;
+    k.k_45b = (o.g4 && o.g5) ? 9 * Om2 * e1.G * m2 * e1.chi : 0.0;
+    const double h2 = o.H0h * o.H0h;
+    k.h4 = h2 * h2;
+    k.any_ll = k.k_ll != 0.0;
+    k.any_pl = (k.k_4l != 0.0) || (k.k_5la != 0.0) || (k.k_5lb != 0.0);
+    k.any_ren = o.divergent && ((k.k_44 != 0.0) || (k.k_55 != 0.0) || (k.k_45a != 0.0) || (k.k_45b != 0.0));
+    return k;
+}
+
+/* integrand per unit (x1, x2) = (l1/chi1, l2/chi2); los_i = {W, V, U, Wa}(l_i) */
+COFFE_HD double di_eval(const Tables &t, const DIConst &k, const Geometry &g, const double l1, const double l2,
+                        const double4 los1, const double4 los2)
+{
+    const double c = g.c, c2 = c * c;
+    const double d = l1 - l2;
+    double r2 = d * d + 2.0 * l1 * l2 * g.omc;
+    if (r2 < 0) r2 = 0;
+    const double R = sqrt(r2);
+    double I[N_ITAB];
+    ifam_eval_all(t.ifam, R, I);
+    const double ll = l1 * l2;
+    const double WW = los1.x * los2.x;
+    const double e1 = g.chi1 - l1, e2 = g.chi2 - l2;    /* chi_i (1 - x_i) */
+    double res = 0.0;
+    if (k.any_ll) {
+        double br;
+        if (r2 > 1e-20) {
+            const double ir2 = 1.0 / r2;
+            const double cm = -g.s2;     /* cos^2(theta) - 1 */
+            br = 2 * cm * ll * I[I00] / 5.
+               + 4 * c * I[I20] / 3.
+               + 4 * c * (r2 + 6 * c * ll) * I[I11] / 15.
+               + 2 * cm * ll * (2 * r2 + 3 * c * ll) * I[I02] / 7. * ir2
+               + 2 * c * (2 * r2 * r2 + 12 * c * r2 * ll + 15 * cm * ll * ll) * I[I13] / 15. * ir2
+               + cm * ll * (6 * r2 * r2 + 30 * c * r2 * ll + 35 * cm * ll * ll) * I[I04] / 35. * ir2 * ir2;
+        }
+        else br = 4. + 24. * ll * I[I11] / 15.;
+        res += k.k_ll * e1 * e2 * WW * br;
+    }
+    if (k.any_pl) {
+        const double br = (r2 != 0.0) ? 2 * ll * c * I[I31] - ll * ll * g.s2 * I[I22] : 2 * ll * I[I31];
+        /* (1 - x2)/x2 = (chi2 - l2)/l2 */
+        const double w2 = e2 / l2, w1 = e1 / l1;
+        res += WW * br * (k.k_4l * (w2 + w1) + k.k_5la * los1.z * w2 + k.k_5lb * los2.z * w1);
+    }
+    if (k.any_ren) {
+        const double ren = (r2 <= 1e-12) ? spline_eval(t.ren0, l1) : spline_eval(t.i40, R) - renorm2d_eval(t.ren2d, l1, l2);
+        res += WW * ren * (k.k_44 + k.k_55 * los1.y * los2.y + k.k_45a * los2.y + k.k_45b * los1.y);
+    }
+    return res * k.h4;
+}
+
+/* line-of-sight functions at lambda through the reference's own two-level lookup (z = z(lambda), then
+   the background splines at z): {W = D1/a, V = Hc (f-1), U = Hc (Hc-1), Wa = D1 a} */
+COFFE_HD double4 los_point(const Tables &t, const double lambda)
+{
+    const double z = spline_eval(t.bg.z_of_chi, lambda);
+    const BackgroundAtZ b = bg_eval_all(t.bg, z);
+    double4 o;
+    o.x = b.D1 / b.a;
+    o.y = b.Hc * (b.f - 1.0);
+    o.z = b.Hc * (b.Hc - 1.0);
+    o.w = b.D1 * b.a;
+    return o;
+}
+
+}  // namespace coffe

@@ -1,0 +1,100 @@
+// Fixed-node quadrature that replaces the reference's adaptive integrators on this path
+// (Cuhre, src/common.c:1074-1118; QAG-61, src/common.c:1004-1040).
+//
+// The line-of-sight integrands are smooth functions of the integration variable multiplied by
+// I^n_l(sqrt(d^2 + eps^2)) brackets, where d is the distance along the line of sight from the point
+// of closest approach ("ridge") and eps the impact parameter: a cusp of width eps at d = 0, structure
+// on the BAO scale out to a few hundred Mpc and a slowly varying power-law tail beyond.  A tensor
+// Gauss-Legendre grid in (x1, x2) cannot resolve the cusp (this is why Cuhre exhausts its 750 000
+// evaluation budget); instead each inner integral is split at |d| = B_k,
+//     B_0 = 0, B_k = eps 2^(k-1)            while the panel width is below W   (geometric, resolves the cusp)
+//     then steps of W                       out to Du                           (uniform, resolves BAO-scale structure)
+//     then doubling again                   out to the end of the line of sight (power-law tail)
+// with an n-point Gauss-Legendre rule per panel.  On a geometric panel the nearest singularity of
+// f(sqrt(d^2+eps^2)) (at d = +-i eps) is at least one panel length away, so the rule converges like
+// rho^(-2n) with rho >= 3.7 independent of eps.
+#pragma once
+#include "hd.h"
+
+namespace coffe {
+
+struct PanelPlan {
+    double eps, W, ratio;
+    int J;          /* B_k = eps 2^(k-1) for 1 <= k <= J */
+    int M;          /* B_k = B_J + (k-J) W for J < k <= J+M */
+    double BJ, BJM;
+};
+
+COFFE_HD PanelPlan panel_plan(double eps, const double eps_min, const double W, const double Du, const double ratio)
+{
+    PanelPlan p;
+    if (eps < eps_min) eps = eps_min;
+    p.eps = eps; p.W = W; p.ratio = ratio;
+    int J = 0;
+    double b = 0.0;
+    if (eps < W) {          /* otherwise the cusp is wider than a uniform panel: uniform panels from d = 0 */
+        J = 1; b = eps;
+        while (b < W) { b *= 2.0; ++J; }
+    }
+    p.J = J; p.BJ = b;
+    int M = 0;
+    if (b < Du) M = (int)ceil((Du - b) / W);
+    p.M = M; p.BJM = b + M * W;
+    return p;
+}
+
+COFFE_HD double panel_break(const PanelPlan &p, const int k)
+{
+    if (k <= 0) return 0.0;
+    if (k <= p.J) return ldexp(p.eps, k - 1);
+    if (k <= p.J + p.M) return p.BJ + (k - p.J) * p.W;
+    return p.BJM * pow(p.ratio, (double)(k - p.J - p.M));
+}
+
+/* number of panels needed to cover [0, b] */
+COFFE_HD int panel_count(const PanelPlan &p, const double b)
+{
+    if (b <= 0.0) return 0;
+    int k = 1;
+    if (b > p.BJM) {
+        k = p.J + p.M;
+        int n = (int)ceil(log(b / p.BJM) / log(p.ratio));
+        if (n < 1) n = 1;
+        /* guard the rounding of the logarithm so that B_(k+n) >= b */
+        if (p.BJM * pow(p.ratio, (double)n) < b) ++n;
+        return k + n;
+    }
+    if (b > p.BJ || p.J == 0) return p.J + (int)ceil((b - p.BJ) / p.W);
+    double e = p.eps;
+    while (e < b) { e *= 2.0; ++k; }
+    return k;
+}
+
+/* runtime quadrature configuration (mirrors coffe_b200_quadrature, include/coffe_b200.h) */
+struct QuadConfig {
+    int n_mu_ni;            /* Gauss-Legendre nodes in mu for the local x local piece */
+    int n_mu_panel;         /* nodes per transverse-separation panel of the mu rule of the integrated pieces */
+    double mu_rho0, mu_panel_w, mu_du;     /* panel plan in r_perp = r sqrt(1-mu^2) [Mpc] */
+    int n_outer;            /* outer line-of-sight nodes of the integrated x integrated piece; 0 = by separation */
+    int n_panel_si, n_panel_di;            /* nodes per inner panel */
+    int n_z;                /* nodes of the redshift average */
+    double panel_w;         /* W  [Mpc] */
+    double panel_du;        /* Du [Mpc] */
+    double eps_min;         /* floor on eps [Mpc] */
+    double tail_ratio;      /* growth factor of the tail panels beyond Du */
+};
+
+/* bank of Gauss-Legendre rules on [0,1] for n = 1..kMaxRule, rule n stored at offset n(n-1)/2 */
+static const int kMaxRule = 128;
+COFFE_HD int rule_offset(const int n) { return n * (n - 1) / 2; }
+
+/* outer node count when QuadConfig::n_outer == 0: the inner integral as a function of lambda_1 carries
+   the structure of I(R) stretched by 1/sin(theta) ~ chi/r_perp, so wider separations need more nodes */
+COFFE_HD int auto_n_outer(const double sep)
+{
+    int n = 32 + (int)(sep / 12.0);
+    if (n > 80) n = 80;
+    return n & ~1;
+}
+
+}  // namespace coffe

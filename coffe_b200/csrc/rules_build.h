@@ -1,0 +1,103 @@
+// Host-side construction of the quadrature rule arrays described by QuadConfig (quadrature.cuh).
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "../../include/coffe_b200.h"
+#include "quadrature.cuh"
+#include "table_build.h"
+
+namespace coffe {
+
+/* |mu| at which the reference switches the rsd-len bracket (src/functions.c:2199) */
+static const double kMuSwitch = 0.999;
+
+inline QuadConfig default_quadrature()
+{
+    QuadConfig q;
+    q.n_mu_ni = 32;
+    q.n_mu_panel = 5; q.mu_rho0 = 4.0; q.mu_panel_w = 32.0; q.mu_du = 256.0;
+    q.n_outer = 0;
+    q.n_panel_si = 8; q.n_panel_di = 6;
+    q.n_z = 8;
+    q.panel_w = 16.0; q.panel_du = 320.0; q.eps_min = 1e-3; q.tail_ratio = 1.5;
+    return q;
+}
+
+inline QuadConfig merge_quadrature(const QuadConfig &base, const coffe_b200_quadrature &u)
+{
+    QuadConfig q = base;
+    if (u.n_mu_ni > 0) q.n_mu_ni = u.n_mu_ni;
+    if (u.n_mu_panel > 0) q.n_mu_panel = u.n_mu_panel;
+    if (u.mu_rho0 > 0) q.mu_rho0 = u.mu_rho0;
+    if (u.mu_panel_width > 0) q.mu_panel_w = u.mu_panel_width;
+    if (u.mu_uniform_extent > 0) q.mu_du = u.mu_uniform_extent;
+    if (u.n_outer > 0) q.n_outer = u.n_outer;
+    if (u.n_outer < 0) q.n_outer = 0;
+    if (u.n_panel_si > 0) q.n_panel_si = u.n_panel_si;
+    if (u.n_panel_di > 0) q.n_panel_di = u.n_panel_di;
+    if (u.n_z > 0) q.n_z = u.n_z;
+    if (u.panel_width > 0) q.panel_w = u.panel_width;
+    if (u.panel_uniform_extent > 0) q.panel_du = u.panel_uniform_extent;
+    if (u.eps_min > 0) q.eps_min = u.eps_min;
+    if (u.tail_ratio > 1.0) q.tail_ratio = u.tail_ratio;
+    return q;
+}
+
+inline bool quadrature_valid(const QuadConfig &q)
+{
+    return q.n_mu_ni >= 2 && q.n_mu_ni <= kMaxRule && q.n_mu_panel >= 2 && q.n_mu_panel <= kMaxRule &&
+           q.n_outer >= 0 && q.n_outer <= kMaxRule && q.n_panel_si >= 2 && q.n_panel_si <= kMaxRule &&
+           q.n_panel_di >= 2 && q.n_panel_di <= kMaxRule && q.n_z >= 1 && q.n_z <= kMaxRule &&
+           q.panel_w > 0 && q.panel_du >= 0 && q.eps_min > 0 && q.tail_ratio > 1.0 &&
+           q.mu_rho0 > 0 && q.mu_panel_w > 0 && q.mu_du >= 0;
+}
+
+/* bank of Gauss-Legendre rules on [0,1], rule n at offset n(n-1)/2 */
+inline void build_rule_bank(std::vector<double> &bx, std::vector<double> &bw)
+{
+    bx.assign(rule_offset(kMaxRule + 1), 0.0);
+    bw.assign(rule_offset(kMaxRule + 1), 0.0);
+    std::vector<double> x, w;
+    for (int n = 1; n <= kMaxRule; ++n) {
+        build::gauss_legendre_01(n, x, w);
+        std::copy(x.begin(), x.end(), bx.begin() + rule_offset(n));
+        std::copy(w.begin(), w.end(), bw.begin() + rule_offset(n));
+    }
+}
+
+/* mu rule of the integrated pieces for one separation: the integrands are functions of the transverse
+   separation r_perp = r sin(phi), mu = cos(phi), that peak sharply at r_perp -> 0 (|mu| -> 1) and carry
+   BAO-scale structure in r_perp.  Panels in phi with break points at r_perp = B_k (the same geometric /
+   uniform / geometric plan as the line-of-sight integrals) plus one at |mu| = 0.999 where the reference
+   switches formulas; n-point Gauss-Legendre per panel; mirrored to mu < 0.  Weights are for the measure
+   dmu/2, i.e. xi_l = (2l+1) sum_j w_j P_l(mu_j) xi(mu_j)      (src/signal.c:97-110, 541). */
+inline void build_mu_rule(const QuadConfig &q, const double sep, std::vector<double> &mu, std::vector<double> &w)
+{
+    mu.clear(); w.clear();
+    std::vector<double> bp;
+    bp.push_back(0.0);
+    double b = q.mu_rho0;
+    while (b < q.mu_panel_w && b < sep) { bp.push_back(b); b *= 2.0; }
+    while (b < q.mu_du && b < sep) { bp.push_back(b); b += q.mu_panel_w; }
+    while (b < sep) { bp.push_back(b); b *= q.tail_ratio; }
+    bp.push_back(sep);
+    bp.push_back(sep * std::sqrt(1.0 - kMuSwitch * kMuSwitch));
+    std::sort(bp.begin(), bp.end());
+    std::vector<double> x, wt;
+    build::gauss_legendre_01(q.n_mu_panel, x, wt);
+    for (size_t k = 0; k + 1 < bp.size(); ++k) {
+        const double a = std::asin(std::min(1.0, bp[k] / sep)), c = std::asin(std::min(1.0, bp[k + 1] / sep));
+        if (!(c - a > 1e-14)) continue;
+        for (int j = 0; j < q.n_mu_panel; ++j) {
+            const double phi = a + (c - a) * x[j];
+            mu.push_back(std::cos(phi));
+            w.push_back((c - a) * wt[j] * std::sin(phi) / 2.0);
+        }
+    }
+    const size_t n = mu.size();
+    for (size_t i = 0; i < n; ++i) { mu.push_back(-mu[i]); w.push_back(w[i]); }
+}
+
+}  // namespace coffe

@@ -1,0 +1,208 @@
+// Device-side table views and evaluators.
+//
+// Everything the reference looks up through GSL (`coffe_interp_spline`, src/common.c:704-719) is
+// flattened on upload into POD arrays of per-interval cubic coefficients {y, b, c, d} (one double4 per
+// interval) so that a lookup is: find interval, one 32-byte load, three FMAs.  The interval search is
+// specialised per table family:
+//   * background functions of z   -- uniform z grid (src/background.c:446), O(1) index + fix-up;
+//   * I^n_l(r) family             -- 43 irregular small-r knots + log-spaced FFTLog knots
+//                                    (src/integrals.c:111-126, 524-562), O(1) index from log(r);
+//                                    the eight (n,l) tables share knots and are interleaved per knot;
+//   * everything else (z(chi), biases, I^4_0, zero-separation renormalisation) -- binary search;
+//   * renormalisation(chi1,chi2)  -- uniform 201x201 grid (src/integrals.c:851-907), bicubic Hermite
+//                                    patch with node derivatives from natural cubic splines (GSL bicubic).
+#pragma once
+#include "hd.h"
+
+namespace coffe {
+
+COFFE_HD double cubic_eval(const double4 k, const double dx)
+{
+    return fma(dx, fma(dx, fma(dx, k.w, k.z), k.y), k.x);
+}
+
+/* index i with x[i] <= v < x[i+1], clamped to [0, n-2] (gsl_interp_bsearch semantics) */
+COFFE_HD int knot_search(const double *x, const int n, const double v)
+{
+    int lo = 0, hi = n - 1;
+    while (hi > lo + 1) {
+        const int mid = (hi + lo) >> 1;
+        if (x[mid] > v) hi = mid; else lo = mid;
+    }
+    return lo;
+}
+
+struct SplineView {
+    const double *x;
+    const double4 *k;
+    int n;
+};
+
+COFFE_HD double spline_eval(const SplineView s, const double v)
+{
+    const int i = knot_search(s.x, s.n, v);
+    return cubic_eval(s.k[i], v - s.x[i]);
+}
+
+/* spline on (nominally) uniform knots: O(1) guess, then fix-up against the real knots so that the
+   interval is exactly the one a binary search would return */
+struct UniformSplineView {
+    const double *x;
+    const double4 *k;
+    int n;
+    double x0, inv_dx;
+};
+
+COFFE_HD int uniform_index(const double *x, const int n, const double x0, const double inv_dx, const double v)
+{
+    int i = (int)((v - x0) * inv_dx);
+    if (i < 0) i = 0;
+    if (i > n - 2) i = n - 2;
+    if (v < x[i] && i > 0) --i;
+    else if (i < n - 2 && v >= x[i + 1]) ++i;
+    return i;
+}
+
+COFFE_HD double uspline_eval(const UniformSplineView s, const double v)
+{
+    const int i = uniform_index(s.x, s.n, s.x0, s.inv_dx, v);
+    return cubic_eval(s.k[i], v - s.x[i]);
+}
+
+/* background: all functions of z share the z knots */
+struct BackgroundView {
+    const double *z;          /* n knots, uniform on [0, 15] */
+    int n;
+    double inv_dz;
+    const double4 *a, *Hc, *D1, *f, *G1, *G2, *chi;   /* per-interval cubics, functions of z */
+    SplineView z_of_chi;      /* knots = chi(z_i) */
+};
+
+struct BackgroundAtZ { double a, Hc, D1, f, G1, G2; };
+
+COFFE_HD int bg_index(const BackgroundView &bg, const double z)
+{
+    return uniform_index(bg.z, bg.n, 0.0, bg.inv_dz, z);
+}
+
+COFFE_HD BackgroundAtZ bg_eval_all(const BackgroundView &bg, const double z)
+{
+    const int i = bg_index(bg, z);
+    const double dz = z - bg.z[i];
+    BackgroundAtZ o;
+    o.a = cubic_eval(bg.a[i], dz);
+    o.Hc = cubic_eval(bg.Hc[i], dz);
+    o.D1 = cubic_eval(bg.D1[i], dz);
+    o.f = cubic_eval(bg.f[i], dz);
+    o.G1 = cubic_eval(bg.G1[i], dz);
+    o.G2 = cubic_eval(bg.G2[i], dz);
+    return o;
+}
+
+COFFE_HD double bg_chi(const BackgroundView &bg, const double z)
+{
+    const int i = bg_index(bg, z);
+    return cubic_eval(bg.chi[i], z - bg.z[i]);
+}
+
+/* ---- I^n_l(r) family on shared knots ------------------------------------------------------- */
+enum { I00 = 0, I02, I04, I11, I13, I20, I22, I31, N_ITAB };
+
+struct IntegralFamilyView {
+    const double *x;        /* n knots: 0, small-r list, then r0*exp(i*dln) */
+    const double4 *k;       /* n-1 intervals x N_ITAB cubics, interleaved: k[i*N_ITAB + t] */
+    int n;
+    int n_small;            /* index of the first log-spaced knot (x[n_small] = r0) */
+    double r0, inv_dln;
+};
+
+COFFE_HD int ifam_index(const IntegralFamilyView &t, const double r)
+{
+    if (r < t.r0) return knot_search(t.x, t.n_small + 1, r);
+#if defined(__CUDA_ARCH__)
+    int i = t.n_small + (int)((double)__logf((float)(r / t.r0)) * t.inv_dln);
+#else
+    int i = t.n_small + (int)(log(r / t.r0) * t.inv_dln);
+#endif
+    if (i > t.n - 2) i = t.n - 2;
+    if (i < t.n_small) i = t.n_small;
+    /* the float log is good to ~1e-6 absolute, far below the knot spacing: at most one step off */
+    while (i > t.n_small && r < t.x[i]) --i;
+    while (i < t.n - 2 && r >= t.x[i + 1]) ++i;
+    return i;
+}
+
+/* ---- renormalisation(chi1, chi2), bicubic ---------------------------------------------------- */
+struct Renorm2DView {
+    const double *x;        /* n knots (same on both axes) */
+    const double4 *node;    /* n*n nodes {z, zx, zy, zxy}; index j*n + i with i <-> first argument */
+    int n;
+    double x0, inv_dx;
+};
+
+COFFE_HD double renorm2d_eval(const Renorm2DView &t, const double x, const double y)
+{
+    const int xi = uniform_index(t.x, t.n, t.x0, t.inv_dx, x);
+    const int yi = uniform_index(t.x, t.n, t.x0, t.inv_dx, y);
+    const double dx = t.x[xi + 1] - t.x[xi], dy = t.x[yi + 1] - t.x[yi];
+    const double tt = (x - t.x[xi]) / dx, u = (y - t.x[yi]) / dy;
+    const double4 n00 = t.node[yi * t.n + xi], n10 = t.node[yi * t.n + xi + 1];
+    const double4 n01 = t.node[(yi + 1) * t.n + xi], n11 = t.node[(yi + 1) * t.n + xi + 1];
+    const double t2 = tt * tt, t3 = t2 * tt, u2 = u * u, u3 = u2 * u;
+    const double h00t = 2 * t3 - 3 * t2 + 1, h10t = (t3 - 2 * t2 + tt) * dx, h01t = -2 * t3 + 3 * t2, h11t = (t3 - t2) * dx;
+    const double h00u = 2 * u3 - 3 * u2 + 1, h10u = (u3 - 2 * u2 + u) * dy, h01u = -2 * u3 + 3 * u2, h11u = (u3 - u2) * dy;
+    return h00t * (h00u * n00.x + h01u * n01.x + h10u * n00.z + h11u * n01.z)
+         + h01t * (h00u * n10.x + h01u * n11.x + h10u * n10.z + h11u * n11.z)
+         + h10t * (h00u * n00.y + h01u * n01.y + h10u * n00.w + h11u * n01.w)
+         + h11t * (h00u * n10.y + h01u * n11.y + h10u * n10.w + h11u * n11.w);
+}
+
+/* ---- line-of-sight functions resampled on a uniform lambda grid --------------------------------
+   W = D1/a, V = Hc (f-1), U = Hc (Hc-1), Wa = D1 a evaluated through the reference's own two-level
+   lookup z = z(lambda) -> spline(z) at n uniformly spaced lambda, read back by 4-point Lagrange
+   interpolation.  These are smooth on Gpc scales, so with spacing ~5 Mpc the resampling error is
+   ~1e-11 relative (tolerance budget). */
+struct LosView {
+    const double4 *v;   /* {W, V, U, Wa} per knot */
+    int n;
+    double h, inv_h;
+};
+
+COFFE_HD double4 los_eval(const double4 *v, const int n, const double inv_h, const double lambda)
+{
+    const double s = lambda * inv_h;
+    int j = (int)s;
+    if (j < 1) j = 1;
+    if (j > n - 3) j = n - 3;
+    const double p = s - j;             /* in [0,1) in the interior; may extrapolate slightly at the ends */
+    const double pm1 = p - 1.0, pm2 = p - 2.0, pp1 = p + 1.0;
+    const double w0 = -p * pm1 * pm2 * (1.0 / 6.0);
+    const double w1 = pp1 * pm1 * pm2 * 0.5;
+    const double w2 = -pp1 * p * pm2 * 0.5;
+    const double w3 = pp1 * p * pm1 * (1.0 / 6.0);
+    const double4 a = v[j - 1], b = v[j], c = v[j + 1], d = v[j + 2];
+    double4 o;
+    o.x = w0 * a.x + w1 * b.x + w2 * c.x + w3 * d.x;
+    o.y = w0 * a.y + w1 * b.y + w2 * c.y + w3 * d.y;
+    o.z = w0 * a.z + w1 * b.z + w2 * c.z + w3 * d.z;
+    o.w = w0 * a.w + w1 * b.w + w2 * c.w + w3 * d.w;
+    return o;
+}
+
+/* everything a kernel needs, passed by value */
+struct Tables {
+    BackgroundView bg;
+    SplineView bias[8];        /* galaxy_bias1..4, magnification_bias1,2, evolution_bias1,2 */
+    IntegralFamilyView ifam;
+    SplineView i40;            /* I^4_0(r) (divergent, renormalised) */
+    SplineView ren0;           /* renormalization_zero_separation */
+    Renorm2DView ren2d;
+    LosView los;
+    SplineView flat_i1[3];     /* I^1_l, l = 0, 2, 4 (flat-sky lensing-lensing multipoles) */
+    SplineView flat_half[4];   /* half-integer family for flat-sky density-lensing, see engine */
+    int has_divergent, has_flat_i1, has_flat_half;
+};
+
+enum { B_GAL1 = 0, B_GAL2, B_GAL3, B_GAL4, B_MAG1, B_MAG2, B_EVO1, B_EVO2 };
+
+}  // namespace coffe

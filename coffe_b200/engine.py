@@ -1,0 +1,105 @@
+"""Thin Python handle on libcoffe_b200.so (the C ABI in include/coffe_b200.h).
+
+`Engine` owns one `coffe_b200_ctx` (one GPU).  It does no arithmetic of its own: every number it returns
+was computed by the sm_100a kernels behind the C ABI, and it raises if the library or a GPU is missing.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+class CoffeB200Error(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"libcoffe_b200 error {capi.ERRORS.get(code, code)}: {message}")
+        self.code = code
+
+
+class Engine:
+    def __init__(self, device=0):
+        self.lib = capi.load()
+        h = C.c_void_p()
+        rc = self.lib.coffe_b200_create(C.c_int(device), C.byref(h))
+        if rc:
+            raise CoffeB200Error(rc, self.lib.coffe_b200_last_error(None).decode())
+        self._h = h
+        self._tables = None
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.coffe_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise CoffeB200Error(rc, self.lib.coffe_b200_last_error(self._h).decode())
+
+    # ---- state --------------------------------------------------------------------------------------
+    def upload_tables(self, tableset):
+        self._tables = tableset  # keep the host buffers alive during the call
+        self._check(self.lib.coffe_b200_upload_tables(self._h, C.byref(tableset.struct)))
+
+    def set_options(self, contributions, **flags):
+        o = capi.make_options(contributions, **flags)
+        self._check(self.lib.coffe_b200_set_options(self._h, C.byref(o)))
+
+    def set_quadrature(self, **kw):
+        q = capi.make_quadrature(**kw)
+        self._check(self.lib.coffe_b200_set_quadrature(self._h, C.byref(q)))
+
+    def get_quadrature(self):
+        q = capi.Quadrature()
+        self._check(self.lib.coffe_b200_get_quadrature(self._h, C.byref(q)))
+        return {name: getattr(q, name) for name, _ in q._fields_}
+
+    def last_timing(self):
+        ms, n = C.c_double(), C.c_int()
+        self._check(self.lib.coffe_b200_last_timing(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    # ---- signal -------------------------------------------------------------------------------------
+    def multipoles(self, z_mean, sep, l):
+        z, s, ls = capi.darr(z_mean), capi.darr(sep), capi.iarr(l)
+        out = np.empty((len(z), len(ls), len(s)))
+        self._check(self.lib.coffe_b200_multipoles(self._h, capi.ptr(z), C.c_int(len(z)), capi.ptr(s), C.c_int(len(s)),
+                                                   capi.iptr(ls), C.c_int(len(ls)), capi.ptr(out)))
+        return out
+
+    def multipoles_pieces(self, z_mean, sep, l):
+        """[3 pieces (NI, SI, DI), n_z, n_l, n_sep]"""
+        z, s, ls = capi.darr(z_mean), capi.darr(sep), capi.iarr(l)
+        out = np.empty((3, len(z), len(ls), len(s)))
+        self._check(self.lib.coffe_b200_multipoles_pieces(self._h, capi.ptr(z), C.c_int(len(z)), capi.ptr(s), C.c_int(len(s)),
+                                                          capi.iptr(ls), C.c_int(len(ls)), capi.ptr(out)))
+        return out
+
+    def multipoles_range(self, z_mean, sep, l, begin, end):
+        """[n_l, end-begin] for the flattened (iz, ir) items [begin, end)"""
+        z, s, ls = capi.darr(z_mean), capi.darr(sep), capi.iarr(l)
+        out = np.empty((len(ls), max(end - begin, 0)))
+        self._check(self.lib.coffe_b200_multipoles_range(self._h, capi.ptr(z), C.c_int(len(z)), capi.ptr(s), C.c_int(len(s)),
+                                                         capi.iptr(ls), C.c_int(len(ls)), C.c_long(begin), C.c_long(end), capi.ptr(out)))
+        return out
+
+    def corrfunc(self, z_mean, mu, sep):
+        z, m, s = capi.darr(z_mean), capi.darr(mu), capi.darr(sep)
+        out = np.empty((len(z), len(m), len(s)))
+        self._check(self.lib.coffe_b200_corrfunc(self._h, capi.ptr(z), C.c_int(len(z)), capi.ptr(m), C.c_int(len(m)),
+                                                 capi.ptr(s), C.c_int(len(s)), capi.ptr(out)))
+        return out
+
+    def average_multipoles(self, z_min, z_max, sep, l):
+        a, b, s, ls = capi.darr(z_min), capi.darr(z_max), capi.darr(sep), capi.iarr(l)
+        assert len(a) == len(b)
+        out = np.empty((len(a), len(ls), len(s)))
+        self._check(self.lib.coffe_b200_average_multipoles(self._h, capi.ptr(a), capi.ptr(b), C.c_int(len(a)), capi.ptr(s), C.c_int(len(s)),
+                                                           capi.iptr(ls), C.c_int(len(ls)), capi.ptr(out)))
+        return out

@@ -1,0 +1,142 @@
+/*
+ * libcoffe_b200 -- C ABI of the B200-native signal-evaluation path of COFFE.
+ *
+ * Plain C, no CUDA or torch types in any signature.  Every entry point returns 0 on success and a
+ * non-zero COFFE_B200_E* code on failure (never exits, never throws); coffe_b200_last_error() gives the
+ * message.  The reference's drivers call exit(EXIT_FAILURE) on non-finite integrands
+ * (src/functions.c:1470-1483); here that condition is reported as COFFE_B200_ENONFINITE instead.
+ *
+ * Which reference interface each entry point replaces (paths relative to the reference root):
+ *   coffe_b200_upload_tables      the state the drivers read through coffe_parameters_t /
+ *                                 coffe_background_t / coffe_integral_array_t
+ *                                 (src/common.h:340-550, src/background.h:23-45, src/integrals.h:25-52)
+ *   coffe_b200_multipoles         coffe_multipoles_init            src/multipoles.h:47, src/multipoles.c:50-133
+ *   coffe_b200_corrfunc           coffe_corrfunc_init              src/corrfunc.h:36,   src/corrfunc.c:56-139
+ *   coffe_b200_average_multipoles coffe_average_multipoles_init    src/average_multipoles.h:36, src/average_multipoles.c:72-156
+ *   coffe_b200_signal_pieces      coffe_integrate (per piece)      src/signal.h:17-29, src/signal.c:472-771
+ *   coffe_b200_covariance         coffe_covariance_init            src/covariance.h:48, src/covariance.c:477-1103
+ *   coffe_b200_integrals          coffe_integrals_init             src/integrals.h:84, src/integrals.c:580-1423
+ * Output buffers are caller-owned, dense, and in the reference's own loop order so that a patched
+ * driver can scatter them into its AoS result arrays.
+ */
+#ifndef COFFE_B200_H
+#define COFFE_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct coffe_b200_ctx coffe_b200_ctx;
+
+enum {
+    COFFE_B200_OK = 0,
+    COFFE_B200_EINVAL = 1,      /* bad argument / unsupported option */
+    COFFE_B200_ECUDA = 2,       /* CUDA runtime failure (no device, out of memory, launch error) */
+    COFFE_B200_ENOTABLES = 3,   /* compute call before coffe_b200_upload_tables */
+    COFFE_B200_ENONFINITE = 4,  /* a result is NaN/inf (argument outside a table's range) */
+    COFFE_B200_ERANGE = 5       /* a requested point lies outside the uploaded tables */
+};
+
+/* one 1-D table: knots of a reference spline (gsl_spline->x, ->y, ->size; python/coffe/coffe.pxd:20-23) */
+typedef struct coffe_b200_spline {
+    const double *x;
+    const double *y;
+    int n;
+} coffe_b200_spline;
+
+/* index into coffe_b200_tables.background[] -- the members of coffe_background_t (src/background.h:23-45) */
+enum {
+    COFFE_B200_BG_Z_AS_CHI = 0,     /* x = chi [Mpc], y = z */
+    COFFE_B200_BG_A, COFFE_B200_BG_HZ, COFFE_B200_BG_CONFORMAL_HZ, COFFE_B200_BG_CONFORMAL_HZ_PRIME,
+    COFFE_B200_BG_D1, COFFE_B200_BG_F, COFFE_B200_BG_G1, COFFE_B200_BG_G2,
+    COFFE_B200_BG_COMOVING_DISTANCE,  /* all of these: x = z, uniform knots (src/background.c:446) */
+    COFFE_B200_BG_COUNT
+};
+
+/* index into coffe_b200_tables.bias[] (src/common.h: galaxy_bias1..4, magnification_bias1,2, evolution_bias1,2) */
+enum {
+    COFFE_B200_BIAS_GALAXY1 = 0, COFFE_B200_BIAS_GALAXY2, COFFE_B200_BIAS_GALAXY3, COFFE_B200_BIAS_GALAXY4,
+    COFFE_B200_BIAS_MAGNIFICATION1, COFFE_B200_BIAS_MAGNIFICATION2,
+    COFFE_B200_BIAS_EVOLUTION1, COFFE_B200_BIAS_EVOLUTION2,
+    COFFE_B200_BIAS_COUNT
+};
+
+/* one coffe_integral_t (src/integrals.h:25-39): the stored quantity is r^(n-l) I^n_l(r) when n >= l */
+typedef struct coffe_b200_integral {
+    int n, l;
+    int half_integer;            /* COFFE_HALF_INTEGER family (flat-sky closed forms) */
+    coffe_b200_spline result;
+} coffe_b200_integral;
+
+typedef struct coffe_b200_tables {
+    coffe_b200_spline background[COFFE_B200_BG_COUNT];
+    coffe_b200_spline bias[COFFE_B200_BIAS_COUNT];
+    int interp_method;           /* enum coffe_interp1d_type (src/common.h:271-280); 5 = Akima */
+    const coffe_b200_integral *integrals;
+    int n_integrals;
+    /* divergent I^4_0 extras (src/integrals.c:773-914); n_renorm = 0 if par->divergent is off */
+    const double *renorm_chi;    /* n_renorm knots, same on both axes */
+    const double *renorm_z;      /* n_renorm^2 values, z[j*n + i] */
+    int n_renorm;
+    coffe_b200_spline renorm_zero_separation;
+    /* scalars of coffe_parameters_t */
+    double omega_matter;         /* Omega0_cdm + Omega0_baryon */
+    double h;
+} coffe_b200_tables;
+
+/* which terms to compute: coffe_correlation_contributions + the flat-sky / cross-correlation switches */
+typedef struct coffe_b200_options {
+    int den, rsd, len, d1, d2, g1, g2, g3, g4, g5;
+    int only_cross_correlations;
+    int flatsky_local, flatsky_local_nonlocal, flatsky_nonlocal;
+} coffe_b200_options;
+
+/* fixed-node quadrature sizes (0 = keep the library default); DESIGN.md holds the convergence evidence.
+   See coffe_b200/csrc/quadrature.cuh and rules_build.h for the meaning of each knob. */
+typedef struct coffe_b200_quadrature {
+    int n_mu_ni;                 /* Gauss-Legendre nodes in mu, local x local piece */
+    int n_mu_panel;              /* nodes per r_perp panel of the mu rule of the integrated pieces */
+    double mu_rho0, mu_panel_width, mu_uniform_extent;   /* r_perp panel plan [Mpc] */
+    int n_outer;                 /* outer line-of-sight nodes (integrated x integrated); -1 = by separation */
+    int n_panel_si, n_panel_di;  /* nodes per line-of-sight panel */
+    int n_z;                     /* nodes of the redshift average */
+    double panel_width, panel_uniform_extent, eps_min, tail_ratio;   /* line-of-sight panel plan [Mpc] */
+} coffe_b200_quadrature;
+
+/* ---- life cycle ---------------------------------------------------------------------------------- */
+int coffe_b200_create(int device, coffe_b200_ctx **out);
+void coffe_b200_destroy(coffe_b200_ctx *ctx);
+const char *coffe_b200_last_error(const coffe_b200_ctx *ctx);   /* ctx may be NULL: last create() error */
+int coffe_b200_upload_tables(coffe_b200_ctx *ctx, const coffe_b200_tables *tables);
+int coffe_b200_set_options(coffe_b200_ctx *ctx, const coffe_b200_options *opt);
+int coffe_b200_set_quadrature(coffe_b200_ctx *ctx, const coffe_b200_quadrature *q);
+int coffe_b200_get_quadrature(const coffe_b200_ctx *ctx, coffe_b200_quadrature *q);
+
+/* ---- signal -------------------------------------------------------------------------------------- */
+/* out[(iz*n_l + il)*n_sep + ir]   (order of src/multipoles.c:75-86) */
+int coffe_b200_multipoles(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double *sep, int n_sep,
+                          const int *l, int n_l, double *out);
+/* same grid, restricted to the flattened (iz, ir) work items [item_begin, item_end) (iz*n_sep + ir): the
+   unit of multi-GPU sharding.  out has n_l*(item_end-item_begin) entries: out[il*n_items + (item-item_begin)] */
+int coffe_b200_multipoles_range(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double *sep, int n_sep,
+                                const int *l, int n_l, long item_begin, long item_end, double *out);
+/* the three pieces coffe_integrate returns for flag_integral = NONINTEGRATED / SINGLE_INTEGRATED /
+   DOUBLE_INTEGRATED: out[((piece*n_z + iz)*n_l + il)*n_sep + ir] */
+int coffe_b200_multipoles_pieces(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double *sep, int n_sep,
+                                 const int *l, int n_l, double *out);
+/* out[(iz*n_mu + imu)*n_sep + ir]   (order of src/corrfunc.c:81-93) */
+int coffe_b200_corrfunc(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double *mu, int n_mu,
+                        const double *sep, int n_sep, double *out);
+/* out[(ibin*n_l + il)*n_sep + ir]   (order of src/average_multipoles.c:97-110) */
+int coffe_b200_average_multipoles(coffe_b200_ctx *ctx, const double *z_min, const double *z_max, int n_bins,
+                                  const double *sep, int n_sep, const int *l, int n_l, double *out);
+
+/* device time of the kernels of the last compute call [ms] and their launch count (bench / roofline) */
+int coffe_b200_last_timing(const coffe_b200_ctx *ctx, double *kernel_ms, int *n_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COFFE_B200_H */

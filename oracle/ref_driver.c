@@ -121,8 +121,10 @@ void ref_set_contributions(void *h, const int *c)
     s->par.correlation_contrib.g2 = c[6]; s->par.correlation_contrib.g3 = c[7];
     s->par.correlation_contrib.g4 = c[8]; s->par.correlation_contrib.g5 = c[9];
     /* coffe.pyx:1108-1109 (_check_contributions) */
+    const int old_divergent = s->par.divergent;
     if (c[4] || c[5] || c[6] || c[7] || c[8] || c[9]) s->par.divergent = 1;
-    coffe_integrals_free(&s->integral);
+    /* the I^n_l tables depend on the contributions only through `divergent` */
+    if (s->par.divergent != old_divergent) coffe_integrals_free(&s->integral);
     free_outputs(s);
 }
 

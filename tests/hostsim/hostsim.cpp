@@ -1,0 +1,164 @@
+// TEST INFRASTRUCTURE ONLY -- CPU debugging harness.
+//
+// Compiles the hot path's host/device headers (coffe_b200/csrc/*.cuh) with plain g++ so that the
+// physics transcription and the fixed-node quadrature can be checked against the oracle in the
+// GPU-less build container.  It is never linked into libcoffe_b200.so and nothing in the product
+// imports it; the `-m gpu` parity tests exercise the real sm_100a kernels through the C ABI.
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "../../coffe_b200/csrc/assemble.h"
+#include "../../coffe_b200/csrc/item.cuh"
+#include "../../coffe_b200/csrc/rules_build.h"
+
+using namespace coffe;
+
+struct HostSim {
+    Arena arena;
+    Layout layout;
+    Tables t;
+    Options o;
+    QuadConfig qc;
+    std::vector<double> bx, bw;
+    Rules q;
+    std::string err;
+};
+
+static void set_rules(HostSim *s)
+{
+    if (s->bx.empty()) build_rule_bank(s->bx, s->bw);
+    Rules &q = s->q;
+    q.gl_x = s->bx.data(); q.gl_w = s->bw.data();
+    q.n_panel_si = s->qc.n_panel_si; q.n_panel_di = s->qc.n_panel_di; q.n_outer = s->qc.n_outer;
+    q.panel_w_mpc = s->qc.panel_w; q.panel_du = s->qc.panel_du; q.eps_min = s->qc.eps_min; q.tail_ratio = s->qc.tail_ratio;
+}
+
+extern "C" {
+
+void *hs_create(const coffe_b200_tables *T, const coffe_b200_options *opt)
+{
+    HostSim *s = new HostSim();
+    if (!assemble(*T, s->arena, s->layout, s->err)) { fprintf(stderr, "hostsim: %s\n", s->err.c_str()); delete s; return nullptr; }
+    s->t = make_view(s->layout, s->arena.buf.data());
+    /* line-of-sight table */
+    double4 *los = reinterpret_cast<double4 *>(s->arena.buf.data() + s->layout.los);
+    for (int i = 0; i < s->layout.los_n; ++i) {
+        double lam = i * s->layout.los_h;
+        if (lam > s->layout.chi_max_table) lam = s->layout.chi_max_table;
+        los[i] = los_point(s->t, lam);
+    }
+    Options &o = s->o;
+    o.den = opt->den; o.rsd = opt->rsd; o.len = opt->len; o.d1 = opt->d1; o.d2 = opt->d2;
+    o.g1 = opt->g1; o.g2 = opt->g2; o.g3 = opt->g3; o.g4 = opt->g4; o.g5 = opt->g5;
+    o.only_cross = opt->only_cross_correlations;
+    o.flatsky_local = opt->flatsky_local; o.flatsky_local_nonlocal = opt->flatsky_local_nonlocal; o.flatsky_nonlocal = opt->flatsky_nonlocal;
+    o.divergent = s->layout.has_divergent;
+    o.Om = T->omega_matter; o.H0h = T->h / 2997.92458;
+    s->qc = default_quadrature();
+    set_rules(s);
+    return s;
+}
+
+void hs_destroy(void *h) { delete (HostSim *)h; }
+
+void hs_set_quadrature(void *h, const coffe_b200_quadrature *u)
+{
+    HostSim *s = (HostSim *)h;
+    s->qc = merge_quadrature(default_quadrature(), *u);
+    set_rules(s);
+}
+
+double hs_ni(void *h, double z, double mu, double sep)
+{
+    HostSim *s = (HostSim *)h;
+    const SepConst sc = sep_const(s->o, s->t, z, sep);
+    const Geometry g = geometry(sc.chi_mean, sep, mu);
+    const EndVals e1 = end_eval(s->o, s->t, g.chi1, 1), e2 = end_eval(s->o, s->t, g.chi2, 2);
+    return ni_eval(s->o, s->t, sc, g, e1, e2);
+}
+
+/* both halves at the same x, as functions_single_integrated evaluates them; exact LOS (no resampling)
+   when exact != 0 */
+double hs_si(void *h, double z, double mu, double sep, double x, int exact)
+{
+    HostSim *s = (HostSim *)h;
+    const double chi_mean = bg_chi(s->t.bg, z);
+    const Geometry g = geometry(chi_mean, sep, mu);
+    const EndVals e1 = end_eval(s->o, s->t, g.chi1, 1), e2 = end_eval(s->o, s->t, g.chi2, 2);
+    const SIHalf ha = si_half_setup(s->o, g, e1, e2, true), hb = si_half_setup(s->o, g, e2, e1, false);
+    const double la = g.chi2 * x, lb = g.chi1 * x;
+    const double4 losa = exact ? los_point(s->t, la) : los_eval(s->t.los.v, s->t.los.n, s->t.los.inv_h, la);
+    const double4 losb = exact ? los_point(s->t, lb) : los_eval(s->t.los.v, s->t.los.n, s->t.los.inv_h, lb);
+    return si_half_eval(s->t, ha, g, la, losa) + si_half_eval(s->t, hb, g, lb, losb);
+}
+
+double hs_di(void *h, double z, double mu, double sep, double x1, double x2, int exact)
+{
+    HostSim *s = (HostSim *)h;
+    const double chi_mean = bg_chi(s->t.bg, z);
+    const Geometry g = geometry(chi_mean, sep, mu);
+    const EndVals e1 = end_eval(s->o, s->t, g.chi1, 1), e2 = end_eval(s->o, s->t, g.chi2, 2);
+    const DIConst k = di_setup(s->o, e1, e2);
+    const double l1 = g.chi1 * x1, l2 = g.chi2 * x2;
+    const double4 los1 = exact ? los_point(s->t, l1) : los_eval(s->t.los.v, s->t.los.n, s->t.los.inv_h, l1);
+    const double4 los2 = exact ? los_point(s->t, l2) : los_eval(s->t.los.v, s->t.los.n, s->t.los.inv_h, l2);
+    return di_eval(s->t, k, g, l1, l2, los1, los2);
+}
+
+/* the three pieces at one (z, sep, mu) with the fixed-node rules: out[0..2] = NI, SI, DI */
+void hs_item(void *h, double z, double sep, double mu, double *out)
+{
+    HostSim *s = (HostSim *)h;
+    const Options &o = s->o;
+    const SepConst sc = sep_const(o, s->t, z, sep);
+    const Geometry g = geometry(sc.chi_mean, sep, mu);
+    const EndVals e1 = end_eval(o, s->t, g.chi1, 1), e2 = end_eval(o, s->t, g.chi2, 2);
+    out[0] = out[1] = out[2] = 0.0;
+    if (opt_has_ni(o)) out[0] = ni_eval(o, s->t, sc, g, e1, e2);
+    if (opt_has_si(o)) {
+        const SIHalf ha = si_half_setup(o, g, e1, e2, true), hb = si_half_setup(o, g, e2, e1, false);
+        out[1] = si_half_partial(s->t, s->q, g, ha, s->t.los.v, 0, 1) + si_half_partial(s->t, s->q, g, hb, s->t.los.v, 0, 1);
+    }
+    if (opt_has_integrated(o)) {
+        const DIConst k = di_setup(o, e1, e2);
+        out[2] = di_partial(s->t, s->q, g, k, s->t.los.v, 0, 1, 0, 1);
+    }
+}
+
+/* multipoles of the three pieces: out[piece*n_l + il]; same rules as the device path */
+void hs_multipoles(void *h, double z, double sep, const int *ls, int n_l, double *out)
+{
+    HostSim *s = (HostSim *)h;
+    std::vector<double> mu, w;
+    build_mu_rule(s->qc, sep, mu, w);
+    const int nm = (int)mu.size();
+    std::vector<double> v((size_t)3 * nm);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int im = 0; im < nm; ++im) hs_item(h, z, sep, mu[im], &v[(size_t)3 * im]);
+    for (int p = 1; p < 3; ++p)
+        for (int il = 0; il < n_l; ++il) {
+            double acc = 0.0;
+            for (int im = 0; im < nm; ++im) acc += w[im] * legendre_p(ls[il], mu[im]) * v[(size_t)3 * im + p];
+            out[p * n_l + il] = (2 * ls[il] + 1) * acc;
+        }
+    const int nn = s->qc.n_mu_ni;
+    const double *x = s->bx.data() + rule_offset(nn), *wn = s->bw.data() + rule_offset(nn);
+    for (int il = 0; il < n_l; ++il) {
+        double acc = 0.0;
+        if (opt_has_ni(s->o))
+            for (int j = 0; j < nn; ++j) acc += wn[j] * legendre_p(ls[il], 2 * x[j] - 1) * hs_ni(h, z, 2 * x[j] - 1, sep);
+        out[il] = (2 * ls[il] + 1) * acc;
+    }
+}
+
+int hs_n_mu(void *h, double sep)
+{
+    HostSim *s = (HostSim *)h;
+    std::vector<double> mu, w;
+    build_mu_rule(s->qc, sep, mu, w);
+    return (int)mu.size();
+}
+
+}  // extern "C"

@@ -1,0 +1,56 @@
+"""TEST INFRASTRUCTURE: ctypes bridge to tests/hostsim (the hot path's headers compiled for the CPU)."""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+from coffe_b200 import capi
+from oracle_tables import tableset_from_oracle
+
+LIB = Path(__file__).resolve().parent / "hostsim" / "_build" / "libhostsim.so"
+
+
+def available():
+    return LIB.exists()
+
+
+class HostSim:
+    def __init__(self, ref, contributions, tableset=None, **flags):
+        self.lib = C.CDLL(str(LIB))
+        self.lib.hs_create.restype = C.c_void_p
+        for f in ("hs_ni", "hs_si", "hs_di"):
+            getattr(self.lib, f).restype = C.c_double
+        self.ts = tableset if tableset is not None else tableset_from_oracle(ref)
+        o = capi.make_options(contributions, **flags)
+        self.h = C.c_void_p(self.lib.hs_create(C.byref(self.ts.struct), C.byref(o)))
+        assert self.h.value, "hostsim: table assembly failed"
+
+    def __del__(self):
+        try:
+            self.lib.hs_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_quadrature(self, **kw):
+        q = capi.make_quadrature(**kw)
+        self.lib.hs_set_quadrature(self.h, C.byref(q))
+
+    def ni(self, z, mu, sep):
+        return self.lib.hs_ni(self.h, C.c_double(z), C.c_double(mu), C.c_double(sep))
+
+    def si(self, z, mu, sep, x, exact=True):
+        return self.lib.hs_si(self.h, C.c_double(z), C.c_double(mu), C.c_double(sep), C.c_double(x), C.c_int(int(exact)))
+
+    def di(self, z, mu, sep, x1, x2, exact=True):
+        return self.lib.hs_di(self.h, C.c_double(z), C.c_double(mu), C.c_double(sep), C.c_double(x1), C.c_double(x2), C.c_int(int(exact)))
+
+    def item(self, z, sep, mu):
+        out = np.zeros(3)
+        self.lib.hs_item(self.h, C.c_double(z), C.c_double(sep), C.c_double(mu), capi.ptr(out))
+        return out
+
+    def multipoles(self, z, sep, ls):
+        ls = capi.iarr(ls)
+        out = np.zeros(3 * len(ls))
+        self.lib.hs_multipoles(self.h, C.c_double(z), C.c_double(sep), capi.iptr(ls), C.c_int(len(ls)), capi.ptr(out))
+        return out.reshape(3, len(ls))

@@ -1,0 +1,97 @@
+"""Host logic + physics transcription, on the CPU: the hot path's integrand code (the .cuh headers,
+compiled for the host by tests/hostsim) against the reference's integrands (oracle), term by term, and
+the fixed-node quadrature against an independent high-order rule over the REFERENCE's integrands
+(oracle/converged.py).  The GPU parity tests then only have to show kernels == this arithmetic."""
+import itertools
+
+import numpy as np
+import pytest
+
+import hostsim_bridge
+from conftest import ALL
+
+pytestmark = pytest.mark.skipif(not hostsim_bridge.available(), reason="tests/hostsim not built")
+
+POINTS = [(z, s, mu) for z in (0.5, 1.0, 2.0) for s in (15.0, 60.0, 224.0) for mu in (-0.95, -0.5, 0.0, 0.3, 0.8, 0.9995)]
+
+
+def _rel(a, b):
+    return abs(a - b) / abs(a) if a != 0 else abs(b)
+
+
+def _check_terms(ref, tableset, contrib, rng):
+    ref.set_contributions(contrib)
+    hs = hostsim_bridge.HostSim(ref, contrib, tableset=tableset)
+    worst = [0.0, 0.0, 0.0]
+    for (z, s, mu) in POINTS[::3]:
+        a = float(ref.f_nonintegrated(z, mu, s))
+        worst[0] = max(worst[0], _rel(a, hs.ni(z, mu, s)))
+        for x in rng.uniform(0.02, 0.98, 2):
+            a = float(ref.f_single(z, mu, s, x))
+            worst[1] = max(worst[1], _rel(a, hs.si(z, mu, s, x)))
+            x2 = rng.uniform(0.02, 0.98)
+            a = float(ref.f_double(z, mu, s, x, x2))
+            worst[2] = max(worst[2], _rel(a, hs.di(z, mu, s, x, x2)))
+    return worst
+
+
+def test_every_single_term_matches_reference_integrands(ref, tableset):
+    rng = np.random.default_rng(7)
+    for c in ALL:
+        w = _check_terms(ref, tableset, [c], rng)
+        # rsd-rsd: the reference's own I^0_4 coefficient carries ~(chi/r)^4 eps rounding noise (physics.cuh)
+        assert w[0] < (5e-5 if c == "rsd" else 1e-11), (c, w)
+        assert w[1] < 1e-9 and w[2] < 1e-9, (c, w)
+
+
+def test_every_cross_term_matches_reference_integrands(ref, tableset):
+    rng = np.random.default_rng(11)
+    for a, b in itertools.combinations(ALL, 2):
+        w = _check_terms(ref, tableset, [a, b], rng)
+        assert w[0] < (5e-5 if "rsd" in (a, b) else 1e-11), (a, b, w)
+        # rsd-len: the reference's quintic I^0_4 bracket cancels catastrophically near the ridge; ours is the
+        # cancellation-free expansion of the same polynomial (physics.cuh), so allow the reference's noise
+        assert w[1] < (1e-6 if {a, b} == {"rsd", "len"} else 1e-9), (a, b, w)
+        assert w[2] < 1e-9, (a, b, w)
+
+
+def test_all_effects_and_cross_only(ref, tableset):
+    rng = np.random.default_rng(3)
+    w = _check_terms(ref, tableset, list(ALL), rng)
+    assert w[0] < 5e-5 and w[1] < 1e-6 and w[2] < 1e-9, w
+
+
+def test_line_of_sight_resampling_error(ref, tableset):
+    """the resampled {D1/a, Hc(f-1), Hc(Hc-1), D1 a}(lambda) table vs the exact two-level lookup"""
+    ref.set_contributions(list(ALL))
+    hs = hostsim_bridge.HostSim(ref, list(ALL), tableset=tableset)
+    rng = np.random.default_rng(5)
+    for (z, s, mu) in POINTS[::4]:
+        for x in rng.uniform(0.01, 0.99, 3):
+            a, b = hs.si(z, mu, s, x, exact=True), hs.si(z, mu, s, x, exact=False)
+            assert _rel(a, b) < 2e-7
+            x2 = rng.uniform(0.01, 0.99)
+            a, b = hs.di(z, mu, s, x, x2, exact=True), hs.di(z, mu, s, x, x2, exact=False)
+            assert _rel(a, b) < 2e-7
+
+
+def test_fixed_node_rules_vs_converged_oracle_pointwise(ref, tableset):
+    """2PCF pieces at fixed mu: default rules (hot-path arithmetic) vs high-order rule over reference integrands"""
+    from oracle.converged import ConvergedOracle
+    ref.set_contributions(list(ALL))
+    hs = hostsim_bridge.HostSim(ref, list(ALL), tableset=tableset)
+    co = ConvergedOracle(ref)
+    for (z, s, mu) in [(1.0, 60.0, 0.5), (1.0, 448.0, 0.3), (1.0, 15.0, 0.97), (2.0, 150.0, -0.9), (0.5, 300.0, 0.9995)]:
+        want = co.corrfunc_pieces(z, s, mu)
+        got = hs.item(z, s, mu)
+        tot = abs(want.sum())
+        assert np.all(np.abs(got - want) / tot < 2e-6), (z, s, mu, np.abs(got - want) / tot)
+
+
+def test_panel_plan_covers_interval():
+    """the panel break points are increasing, start at 0 and the counted panels cover the extent"""
+    from oracle.converged import breakpoints
+    for eps in (1e-4, 0.3, 5.0, 40.0, 500.0):
+        for extent in (0.5, 30.0, 700.0, 5000.0):
+            b = breakpoints(extent, eps, 16.0, 320.0, 1.5)
+            assert b[0] == 0.0 and np.all(np.diff(b) > 0) and b[-1] >= extent
