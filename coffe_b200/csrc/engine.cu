@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kItemThreads) integrated_items_kernel(
     const __grid_constant__ Tables t, const __grid_constant__ Options o, const __grid_constant__ Rules q,
     const double *__restrict__ pz, const double *__restrict__ psep,
     const int *__restrict__ item_point, const double *__restrict__ item_mu, const int n_items,
-    const int los_stage_n, double *__restrict__ out_si, double *__restrict__ out_di)
+    const int los_stage_n, double *__restrict__ out_si, double *__restrict__ out_di, unsigned int *__restrict__ out_evals)
 {
     extern __shared__ double4 los_s[];
     __shared__ ItemShared sh;
@@ -144,6 +144,11 @@ __global__ void __launch_bounds__(kItemThreads) integrated_items_kernel(
     __syncthreads();
 
     double di = 0.0, si = 0.0;
+    if (out_evals && tid < 2) {
+        /* integrand evaluations of this item (roofline accounting): [2*item] = SI, [2*item+1] = DI */
+        out_evals[2 * item + tid] = tid == 0 ? (has_si ? si_eval_count(q, sh.g, sh.ha) + si_eval_count(q, sh.g, sh.hb) : 0u)
+                                             : (has_di ? di_eval_count(q, sh.g) : 0u);
+    }
     if (has_di) di = di_partial(t, q, sh.g, sh.k, los, warp, kItemWarps, lane, 32);
     if (has_si) {
         /* warps alternate between the two halves */
@@ -222,6 +227,17 @@ __global__ void average_reduce_kernel(const double *__restrict__ pm, const doubl
     double a = 0.0;
     for (int k = 0; k < n_z; ++k) a += pw[(size_t)g * n_z + k] * pm[((size_t)g * n_z + k) * 3 * n_l + rest];
     gm[i] = a;
+}
+
+/* FP64 FMA throughput probe: 8 independent chains per thread, `iters` x 8 DFMA each */
+__global__ void __launch_bounds__(256) dfma_probe_kernel(double *out, const int iters, const double a, const double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
 
 }  // namespace
@@ -319,6 +335,7 @@ struct Batch {
     int n_points = 0, n_items = 0;
     DevBuf<double> pz, psep, item_mu, item_w, si, di, ni, pm;
     DevBuf<int> item_point, point_begin;
+    DevBuf<unsigned int> evals;     /* optional: per-item integrand evaluation counts */
     double chi_max = 0;     /* largest chi2 over the batch: how much of the line-of-sight table to stage */
 };
 
@@ -336,7 +353,7 @@ int launch_integrated(coffe_b200_ctx *ctx, Batch &b)
     if (smem > 160 * 1024) { stage_n = 0; smem = 0; }     /* read the table through L1/L2 instead */
     CK(cudaFuncSetAttribute(integrated_items_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     integrated_items_kernel<<<b.n_items, kItemThreads, smem, ctx->stream>>>(
-        ctx->t, ctx->o, make_rules(ctx), b.pz.p, b.psep.p, b.item_point.p, b.item_mu.p, b.n_items, stage_n, b.si.p, b.di.p);
+        ctx->t, ctx->o, make_rules(ctx), b.pz.p, b.psep.p, b.item_point.p, b.item_mu.p, b.n_items, stage_n, b.si.p, b.di.p, b.evals.p);
     CK(cudaGetLastError());
     ctx->last_launches += 1;
     return COFFE_B200_OK;
@@ -354,10 +371,6 @@ LList make_llist(const int *l, const int n_l)
 int run_multipole_batch(coffe_b200_ctx *ctx, Batch &b, const LList &ls)
 {
     const bool has_ni = opt_has_ni(ctx->o);
-    CK(b.ni.alloc((size_t)b.n_points * ls.n));
-    CK(b.pm.alloc((size_t)b.n_points * 3 * ls.n));
-    CK(b.si.alloc(b.n_items));
-    CK(b.di.alloc(b.n_items));
     if (has_ni) {
         const int blocks = (b.n_points * 32 + 127) / 128;
         ni_multipoles_kernel<<<blocks, 128, 0, ctx->stream>>>(ctx->t, ctx->o, b.pz.p, b.psep.p, b.n_points, ctx->d_gl_x, ctx->d_gl_w,
@@ -419,45 +432,103 @@ int check_l(coffe_b200_ctx *ctx, const int *l, const int n_l)
     return COFFE_B200_OK;
 }
 
-/* shared body of multipoles / multipoles_range / multipoles_pieces: items [begin, end) of the (iz, ir) grid;
-   host result hm[(k*3 + piece)*n_l + il], k = item - begin */
-int multipoles_core(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double *sep, int n_sep, const int *l, int n_l,
-                    long begin, long end, std::vector<double> &hm)
+}  // namespace
+
+/* a prepared multipole computation: the (z, r) items [begin, end) with their mu rules resident in HBM */
+struct coffe_b200_plan {
+    coffe_b200_ctx *ctx = nullptr;
+    Batch b;
+    LList ls;
+    long n = 0;
+};
+
+namespace {
+
+int plan_build(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double *sep, int n_sep, const int *l, int n_l,
+               long begin, long end, coffe_b200_plan &pl)
 {
     if (!ctx->have_tables) { ctx->err = "no tables uploaded"; return COFFE_B200_ENOTABLES; }
-    if (!z_mean || !sep || n_z < 0 || n_sep < 0) { ctx->err = "bad grid arguments"; return COFFE_B200_EINVAL; }
+    if (n_z < 0 || n_sep < 0 || (n_z > 0 && !z_mean) || (n_sep > 0 && !sep)) { ctx->err = "bad grid arguments"; return COFFE_B200_EINVAL; }
     int rc = check_l(ctx, l, n_l);
     if (rc) return rc;
     const long total = (long)n_z * n_sep;
     if (begin < 0 || end > total || begin > end) { ctx->err = "item range outside the grid"; return COFFE_B200_EINVAL; }
-    ctx->last_ms = 0; ctx->last_launches = 0;
-    hm.assign((size_t)(end - begin) * 3 * n_l, 0.0);
+    const Options &o = ctx->o;
+    if ((o.flatsky_local_nonlocal && o.len && (o.den || o.rsd || o.d1)) || (o.flatsky_nonlocal && o.len)) {
+        ctx->err = "flat-sky closed forms for density-lensing / lensing-lensing multipoles are not available in this build";
+        return COFFE_B200_EINVAL;
+    }
+    pl.ctx = ctx; pl.n = end - begin; pl.ls = make_llist(l, n_l);
     if (end == begin) return COFFE_B200_OK;
     CK(cudaSetDevice(ctx->device));
     std::vector<double> pz, psep;
-    Batch b;
     const bool ren = needs_renorm(ctx->o);
     if (ren && !ctx->layout.has_divergent) { ctx->err = "d2/g1..g5 need the divergent I^4_0 tables (par->divergent)"; return COFFE_B200_EINVAL; }
+    pz.reserve(pl.n); psep.reserve(pl.n);
     for (long it = begin; it < end; ++it) {
         const double z = z_mean[it / n_sep], s = sep[it % n_sep];
         rc = check_point(ctx, z, s, ren && opt_has_ni(ctx->o));
         if (rc) return rc;
         pz.push_back(z); psep.push_back(s);
         const double chi2 = bg_chi(ctx->t_host.bg, z) + s / 2.;
-        if (chi2 > b.chi_max) b.chi_max = chi2;
+        if (chi2 > pl.b.chi_max) pl.b.chi_max = chi2;
     }
-    rc = build_multipole_batch(ctx, pz, psep, b, false);
+    rc = build_multipole_batch(ctx, pz, psep, pl.b, false);
     if (rc) return rc;
+    CK(pl.b.ni.alloc((size_t)pl.b.n_points * n_l));
+    CK(pl.b.pm.alloc((size_t)pl.b.n_points * 3 * n_l));
+    CK(pl.b.si.alloc(pl.b.n_items));
+    CK(pl.b.di.alloc(pl.b.n_items));
+    return COFFE_B200_OK;
+}
+
+int plan_run(coffe_b200_plan &pl)
+{
+    coffe_b200_ctx *ctx = pl.ctx;
+    ctx->last_ms = 0; ctx->last_launches = 0;
+    if (pl.n == 0) return COFFE_B200_OK;
+    CK(cudaSetDevice(ctx->device));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    rc = run_multipole_batch(ctx, b, make_llist(l, n_l));
+    const int rc = run_multipole_batch(ctx, pl.b, pl.ls);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
-    CK(cudaMemcpyAsync(hm.data(), b.pm.p, hm.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    return COFFE_B200_OK;
+}
+
+int plan_sync(coffe_b200_plan &pl)
+{
+    coffe_b200_ctx *ctx = pl.ctx;
+    if (pl.n == 0) return COFFE_B200_OK;
     CK(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_ms = ms;
+    return COFFE_B200_OK;
+}
+
+/* host result hm[(k*3 + piece)*n_l + il], k = item - begin */
+int plan_fetch(coffe_b200_plan &pl, std::vector<double> &hm)
+{
+    coffe_b200_ctx *ctx = pl.ctx;
+    hm.assign((size_t)pl.n * 3 * pl.ls.n, 0.0);
+    if (pl.n == 0) return COFFE_B200_OK;
+    CK(cudaMemcpyAsync(hm.data(), pl.b.pm.p, hm.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return check_finite(ctx, hm.data(), hm.size());
+}
+
+/* shared body of multipoles / multipoles_range / multipoles_pieces */
+int multipoles_core(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double *sep, int n_sep, const int *l, int n_l,
+                    long begin, long end, std::vector<double> &hm)
+{
+    coffe_b200_plan pl;
+    int rc = plan_build(ctx, z_mean, n_z, sep, n_sep, l, n_l, begin, end, pl);
+    if (rc) return rc;
+    rc = plan_run(pl);
+    if (rc) return rc;
+    rc = plan_fetch(pl, hm);          /* the copy is ordered after the kernels on the same stream */
+    if (rc) return rc;
+    return plan_sync(pl);
 }
 
 }  // namespace
@@ -730,6 +801,10 @@ int coffe_b200_average_multipoles(coffe_b200_ctx *ctx, const double *z_min, cons
     CK(gm.alloc((size_t)n_groups * 3 * n_l));
     rc = build_multipole_batch(ctx, pz_dummy, psep, b, true);
     if (rc) return rc;
+    CK(b.ni.alloc((size_t)b.n_points * n_l));
+    CK(b.pm.alloc((size_t)b.n_points * 3 * n_l));
+    CK(b.si.alloc(b.n_items));
+    CK(b.di.alloc(b.n_items));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     average_points_kernel<<<(n_points + 127) / 128, 128, 0, ctx->stream>>>(ctx->t, ctx->o.H0h, d_zmin.p, d_zmax.p, n_bins, d_sep.p, n_sep,
                                                                           ctx->d_gl_x, ctx->d_gl_w, nz, b.pz.p, b.psep.p, pw.p);
@@ -761,6 +836,106 @@ int coffe_b200_last_timing(const coffe_b200_ctx *ctx, double *kernel_ms, int *n_
     if (!ctx) return COFFE_B200_EINVAL;
     if (kernel_ms) *kernel_ms = ctx->last_ms;
     if (n_launches) *n_launches = ctx->last_launches;
+    return COFFE_B200_OK;
+}
+
+/* ---- prepared computations (bench: inputs resident in HBM before the timed region) ---------------- */
+int coffe_b200_plan_multipoles(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double *sep, int n_sep,
+                               const int *l, int n_l, long item_begin, long item_end, coffe_b200_plan **out)
+{
+    if (!ctx || !out) return COFFE_B200_EINVAL;
+    *out = nullptr;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    coffe_b200_plan *pl = new coffe_b200_plan();
+    const int rc = plan_build(ctx, z_mean, n_z, sep, n_sep, l, n_l, item_begin, item_end, *pl);
+    if (rc) { delete pl; return rc; }
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { delete pl; ctx->err = "upload failed"; return COFFE_B200_ECUDA; }
+    *out = pl;
+    return COFFE_B200_OK;
+}
+
+int coffe_b200_plan_execute(coffe_b200_plan *plan, double *kernel_ms)
+{
+    if (!plan) return COFFE_B200_EINVAL;
+    std::lock_guard<std::mutex> lock(plan->ctx->mu);
+    int rc = plan_run(*plan);
+    if (rc) return rc;
+    rc = plan_sync(*plan);
+    if (kernel_ms) *kernel_ms = plan->ctx->last_ms;
+    return rc;
+}
+
+int coffe_b200_plan_fetch(coffe_b200_plan *plan, double *out)
+{
+    if (!plan || !out) return COFFE_B200_EINVAL;
+    std::lock_guard<std::mutex> lock(plan->ctx->mu);
+    std::vector<double> hm;
+    const int rc = plan_fetch(*plan, hm);
+    if (rc) return rc;
+    const size_t n = (size_t)plan->n;
+    const int n_l = plan->ls.n;
+    for (size_t k = 0; k < n; ++k)
+        for (int il = 0; il < n_l; ++il)
+            out[(size_t)il * n + k] = hm[(k * 3 + 0) * n_l + il] + hm[(k * 3 + 1) * n_l + il] + hm[(k * 3 + 2) * n_l + il];
+    return COFFE_B200_OK;
+}
+
+int coffe_b200_plan_count(coffe_b200_plan *plan, double *n_items, double *n_ni_evals, double *n_si_evals, double *n_di_evals)
+{
+    if (!plan) return COFFE_B200_EINVAL;
+    coffe_b200_ctx *ctx = plan->ctx;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    Batch &b = plan->b;
+    double si = 0, di = 0;
+    if (b.n_items > 0 && opt_has_integrated(ctx->o)) {
+        CK(cudaSetDevice(ctx->device));
+        CK(b.evals.alloc((size_t)2 * b.n_items));
+        int rc = launch_integrated(ctx, b);
+        if (rc) return rc;
+        std::vector<unsigned int> h((size_t)2 * b.n_items);
+        CK(cudaMemcpyAsync(h.data(), b.evals.p, h.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(b.evals.p); b.evals.p = nullptr; b.evals.n = 0;
+        for (int i = 0; i < b.n_items; ++i) { si += h[2 * i]; di += h[2 * i + 1]; }
+    }
+    if (n_items) *n_items = b.n_items;
+    if (n_ni_evals) *n_ni_evals = opt_has_ni(ctx->o) ? (double)b.n_points * ctx->qc.n_mu_ni : 0.0;
+    if (n_si_evals) *n_si_evals = si;
+    if (n_di_evals) *n_di_evals = di;
+    return COFFE_B200_OK;
+}
+
+void coffe_b200_plan_destroy(coffe_b200_plan *plan)
+{
+    if (!plan) return;
+    cudaSetDevice(plan->ctx->device);
+    delete plan;
+}
+
+/* achievable FP64 FMA rate of this device [TFLOP/s]: the roofline denominator */
+int coffe_b200_fp64_peak(coffe_b200_ctx *ctx, double *tflops)
+{
+    if (!ctx || !tflops) return COFFE_B200_EINVAL;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, ctx->device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+    DevBuf<double> out;
+    CK(out.alloc((size_t)blocks * threads));
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        dfma_probe_kernel<<<blocks, threads, 0, ctx->stream>>>(out.p, iters, 0.999999, 1e-9);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        const double tf = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    *tflops = best;
     return COFFE_B200_OK;
 }
 

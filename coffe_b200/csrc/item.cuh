@@ -51,6 +51,27 @@ COFFE_HD double ridge_integrate(const F &f, const double hi, const double center
     return acc;
 }
 
+/* number of integrand evaluations ridge_integrate performs (empty clipped panels included: they cost
+   the index arithmetic but no evaluation, so they are not counted) */
+COFFE_HD unsigned int ridge_eval_count(const double hi, const double center, const double eps, const Rules &q, const int n_panel)
+{
+    const PanelPlan plan = panel_plan(eps, q.eps_min, q.panel_w_mpc, q.panel_du, q.tail_ratio);
+    const double b_neg = center, a_neg = center > hi ? center - hi : 0.0, b_pos = hi - center;
+    const int k_neg = panel_count(plan, b_neg);
+    const int k_pos = b_pos > 0.0 ? panel_count(plan, b_pos) : 0;
+    unsigned int n = 0;
+    for (int p = 0; p < k_neg + k_pos; ++p) {
+        const bool neg = p < k_neg;
+        const int k = neg ? p : p - k_neg;
+        double lo = panel_break(plan, k), up = panel_break(plan, k + 1);
+        const double a = neg ? a_neg : 0.0, b = neg ? b_neg : b_pos;
+        if (lo < a) lo = a;
+        if (up > b) up = b;
+        if (up - lo > 0.0) n += n_panel;
+    }
+    return n;
+}
+
 struct SIFunctor {
     const Tables *t; const SIHalf *h; const Geometry *g; const double4 *los; int los_n; double los_inv_h;
     COFFE_HD double operator()(const double lambda) const
@@ -67,6 +88,11 @@ COFFE_HD double si_half_partial(const Tables &t, const Rules &q, const Geometry 
     const double center = h.cs * g.c;
     const double eps = h.cs * sqrt(g.s2);
     return ridge_integrate(f, h.co, center, eps, q, q.n_panel_si, lane, nlanes) / h.co;
+}
+
+COFFE_HD unsigned int si_eval_count(const Rules &q, const Geometry &g, const SIHalf &h)
+{
+    return ridge_eval_count(h.co, h.cs * g.c, h.cs * sqrt(g.s2), q, q.n_panel_si);
 }
 
 struct DIFunctor {
@@ -93,6 +119,19 @@ COFFE_HD double di_partial(const Tables &t, const Rules &q, const Geometry &g, c
         acc += outer_w[io] * ridge_integrate(f, g.chi2, l1 * g.c, l1 * sth, q, q.n_panel_di, lane, nlanes);
     }
     return acc / g.chi2;
+}
+
+COFFE_HD unsigned int di_eval_count(const Rules &q, const Geometry &g)
+{
+    const double sth = sqrt(g.s2);
+    const int n_outer = q.n_outer > 0 ? q.n_outer : auto_n_outer(g.sep);
+    const double *outer_x = q.gl_x + rule_offset(n_outer);
+    unsigned int n = 0;
+    for (int io = 0; io < n_outer; ++io) {
+        const double l1 = g.chi1 * outer_x[io];
+        n += ridge_eval_count(g.chi2, l1 * g.c, l1 * sth, q, q.n_panel_di);
+    }
+    return n;
 }
 
 }  // namespace coffe

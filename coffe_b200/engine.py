@@ -103,3 +103,51 @@ class Engine:
         self._check(self.lib.coffe_b200_average_multipoles(self._h, capi.ptr(a), capi.ptr(b), C.c_int(len(a)), capi.ptr(s), C.c_int(len(s)),
                                                            capi.iptr(ls), C.c_int(len(ls)), capi.ptr(out)))
         return out
+
+    # ---- prepared computations (inputs resident in HBM) -----------------------------------------------
+    def plan_multipoles(self, z_mean, sep, l, begin=0, end=None):
+        z, s, ls = capi.darr(z_mean), capi.darr(sep), capi.iarr(l)
+        if end is None:
+            end = len(z) * len(s)
+        p = C.c_void_p()
+        self._check(self.lib.coffe_b200_plan_multipoles(self._h, capi.ptr(z), C.c_int(len(z)), capi.ptr(s), C.c_int(len(s)),
+                                                        capi.iptr(ls), C.c_int(len(ls)), C.c_long(begin), C.c_long(end), C.byref(p)))
+        return Plan(self, p, len(ls), end - begin)
+
+    def fp64_peak_tflops(self):
+        v = C.c_double()
+        self._check(self.lib.coffe_b200_fp64_peak(self._h, C.byref(v)))
+        return v.value
+
+
+class Plan:
+    def __init__(self, engine, handle, n_l, n_items):
+        self.engine, self._p, self.n_l, self.n = engine, handle, n_l, n_items
+
+    def execute(self):
+        """launch the kernels on the resident inputs; returns their device time in ms"""
+        ms = C.c_double()
+        self.engine._check(self.engine.lib.coffe_b200_plan_execute(self._p, C.byref(ms)))
+        return ms.value
+
+    def fetch(self):
+        out = np.empty((self.n_l, self.n))
+        self.engine._check(self.engine.lib.coffe_b200_plan_fetch(self._p, capi.ptr(out)))
+        return out
+
+    def count(self):
+        """(work items, NI evaluations, SI evaluations, DI evaluations)"""
+        v = [C.c_double() for _ in range(4)]
+        self.engine._check(self.engine.lib.coffe_b200_plan_count(self._p, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)
+
+    def close(self):
+        if self._p:
+            self.engine.lib.coffe_b200_plan_destroy(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -136,6 +136,23 @@ int coffe_b200_average_multipoles(coffe_b200_ctx *ctx, const double *z_min, cons
 /* device time of the kernels of the last compute call [ms] and their launch count (bench / roofline) */
 int coffe_b200_last_timing(const coffe_b200_ctx *ctx, double *kernel_ms, int *n_launches);
 
+/* ---- prepared computations ------------------------------------------------------------------------
+   coffe_b200_plan_multipoles uploads the grid and its quadrature items for the (iz, ir) items
+   [item_begin, item_end) once; coffe_b200_plan_execute then only launches kernels on inputs that are
+   already resident in HBM (what bench.py times as `value`); coffe_b200_plan_fetch copies the result
+   back in the layout of coffe_b200_multipoles_range.  coffe_b200_plan_count reports the number of
+   (point, mu) work items and of integrand evaluations per piece (roofline accounting). */
+typedef struct coffe_b200_plan coffe_b200_plan;
+int coffe_b200_plan_multipoles(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double *sep, int n_sep,
+                               const int *l, int n_l, long item_begin, long item_end, coffe_b200_plan **out);
+int coffe_b200_plan_execute(coffe_b200_plan *plan, double *kernel_ms);
+int coffe_b200_plan_fetch(coffe_b200_plan *plan, double *out);
+int coffe_b200_plan_count(coffe_b200_plan *plan, double *n_items, double *n_ni_evals, double *n_si_evals, double *n_di_evals);
+void coffe_b200_plan_destroy(coffe_b200_plan *plan);
+
+/* measured FP64 FMA throughput of the device [TFLOP/s] (dependent-chain-free DFMA probe kernel) */
+int coffe_b200_fp64_peak(coffe_b200_ctx *ctx, double *tflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,189 @@
+"""Parity of the sm_100a kernels (through the C ABI) with the reference: golden vectors, the reference's
+integrands under a converged rule, and size-independent properties on larger grids."""
+import numpy as np
+import pytest
+
+import hostsim_bridge
+from conftest import ALL, H
+
+pytestmark = pytest.mark.gpu
+
+SEP_H = np.array([10.0, 20.0, 40.0, 100.0, 150.0])
+GOLDEN_SETS = {
+    "den": ["den"], "rsd": ["rsd"], "d1": ["d1"], "d2": ["d2"], "g1": ["g1"], "g2": ["g2"], "g3": ["g3"],
+    "g4": ["g4"], "g5": ["g5"], "len": ["len"], "std": ["den", "rsd"], "std_len": ["den", "rsd", "len"],
+    "std_d1": ["den", "rsd", "d1"], "all": list(ALL),
+}
+# multipoles the reference's own suite does not check because they are ~0 (tests/test_multipoles.c:170-197)
+SKIP = {("den", 2), ("den", 4), ("d1", 4), ("d2", 2), ("d2", 4), ("g1", 2), ("g1", 4), ("g2", 2), ("g2", 4),
+        ("g3", 2), ("g3", 4)}
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_SETS))
+def test_multipoles_match_reference_golden_vectors(engine, golden, name):
+    """tolerance = the reference's own (5e-4, tests/test_coffe.py:303): the goldens for the lensing terms
+    carry the stock Cuhre truncation error"""
+    engine.set_options(GOLDEN_SETS[name])
+    got = engine.multipoles([1.0], SEP_H / H, [0, 2, 4])[0]
+    for il, l in enumerate((0, 2, 4)):
+        if (name, l) in SKIP:
+            continue
+        want = golden[f"{name}_multipoles{l}"][:, 1]
+        assert np.allclose(got[il], want, rtol=5e-4), (name, l, got[il] / want - 1)
+
+
+@pytest.mark.parametrize("name", ["den", "rsd", "std", "std_d1"])
+def test_local_multipoles_match_golden_tightly(engine, golden, name):
+    engine.set_options(GOLDEN_SETS[name])
+    got = engine.multipoles([1.0], SEP_H / H, [0, 2, 4])[0]
+    for il, l in enumerate((0, 2, 4)):
+        if (name, l) in SKIP:
+            continue
+        want = golden[f"{name}_multipoles{l}"][:, 1]
+        assert np.allclose(got[il], want, rtol=1e-5), (name, l, got[il] / want - 1)
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_SETS))
+def test_corrfunc_matches_reference_golden_vectors(engine, golden, name):
+    engine.set_options(GOLDEN_SETS[name])
+    mus = [0.0, 0.2, 0.5, 0.8, 0.95]
+    got = engine.corrfunc([1.0], mus, SEP_H / H)[0]
+    for im in range(5):
+        want = golden[f"{name}_corrfunc{im}"][:, 1]
+        assert np.allclose(got[im], want, rtol=5e-4, atol=5e-4 * np.abs(want).max() * 1e-3), (name, im, got[im] / want - 1)
+
+
+def test_kernels_reproduce_cpu_evaluation_of_the_same_rules(engine, ref, tableset):
+    """same nodes, same arithmetic, different processor: differences are summation-order rounding only"""
+    ref.set_contributions(list(ALL))
+    hs = hostsim_bridge.HostSim(ref, list(ALL), tableset=tableset)
+    engine.set_options(ALL)
+    for z, s in [(1.0, 30.0), (0.5, 150.0), (2.0, 300.0)]:
+        got = engine.multipoles_pieces([z], [s], [0, 2, 4])[:, 0, :, 0]
+        want = hs.multipoles(z, s, [0, 2, 4])
+        scale = np.abs(want.sum(0))
+        assert np.all(np.abs(got - want) / scale < 1e-9), (z, s, np.abs(got - want) / scale)
+
+
+def test_corrfunc_kernels_reproduce_cpu_evaluation(engine, ref, tableset):
+    ref.set_contributions(list(ALL))
+    hs = hostsim_bridge.HostSim(ref, list(ALL), tableset=tableset)
+    engine.set_options(ALL)
+    mus = [-0.9, 0.0, 0.3, 0.97, 0.9995]
+    got = engine.corrfunc([1.0], mus, [15.0, 224.0])[0]
+    for im, mu in enumerate(mus):
+        for ir, s in enumerate((15.0, 224.0)):
+            want = hs.item(1.0, s, mu).sum()
+            assert abs(got[im, ir] - want) < 1e-9 * abs(want), (mu, s, got[im, ir], want)
+
+
+@pytest.mark.parametrize("z,s", [(1.0, 60.0), (1.5, 224.0), (0.5, 15.0)])
+def test_multipoles_match_converged_oracle(engine, ref, z, s):
+    """the 1e-5 gate: kernels vs the REFERENCE's integrands under an independent high-order rule"""
+    from oracle.converged import ConvergedOracle
+    ref.set_contributions(list(ALL))
+    engine.set_options(ALL)
+    want = ConvergedOracle(ref, n_outer=64, n_panel=8, mu_kw=dict(n=6, W=24.0)).multipoles_pieces(z, s, [0, 2, 4])
+    got = engine.multipoles_pieces([z], [s], [0, 2, 4])[:, 0, :, 0]
+    total = want.sum(0)
+    err = np.abs(got.sum(0) - total) / np.abs(total)
+    assert np.all(err < 1e-5), (z, s, err, np.abs(got - want) / np.abs(total))
+
+
+def test_corrfunc_matches_converged_oracle(engine, ref):
+    from oracle.converged import ConvergedOracle
+    ref.set_contributions(list(ALL))
+    engine.set_options(ALL)
+    co = ConvergedOracle(ref)
+    mus = [-0.7, 0.2, 0.95]
+    seps = [40.0, 300.0]
+    got = engine.corrfunc([1.0], mus, seps)[0]
+    for im, mu in enumerate(mus):
+        for ir, s in enumerate(seps):
+            want = co.corrfunc_pieces(1.0, s, mu).sum()
+            assert abs(got[im, ir] / want - 1) < 1e-5, (mu, s, got[im, ir] / want - 1)
+
+
+def test_average_multipoles_match_golden(engine, golden):
+    """benchmark_avg_multipoles{0,2,4}.dat: den+rsd, z in [0.9, 1.1] (tests/test_coffe.py:327-352)"""
+    engine.set_options(["den", "rsd"])
+    got = engine.average_multipoles([0.9], [1.1], SEP_H / H, [0, 2, 4])[0]
+    for il, l in enumerate((0, 2, 4)):
+        want = golden[f"avg_multipoles{l}"][:, 1]
+        assert np.allclose(got[il], want, rtol=5e-4), (l, got[il] / want - 1)
+
+
+def test_average_multipoles_match_stock_reference(engine, ref):
+    """den+rsd+len averaged multipoles vs the reference's own 2/3/4-D Cuhre path at its tolerance"""
+    ref.set_contributions(["den", "rsd"])
+    ref.set_z_min([0.9]); ref.set_z_max([1.1]); ref.set_sep(np.array([20.0, 60.0]) / H)
+    want = ref.average_multipoles()[0]
+    ref.set_sep(SEP_H / H)
+    engine.set_options(["den", "rsd"])
+    got = engine.average_multipoles([0.9], [1.1], np.array([20.0, 60.0]) / H, [0, 2, 4])[0]
+    assert np.allclose(got, want, rtol=5e-4), got / want - 1
+
+
+# ---- size-independent properties on a larger grid ----------------------------------------------------
+def test_range_calls_tile_the_full_grid_bit_exactly(engine):
+    engine.set_options(ALL)
+    z = np.linspace(0.6, 1.9, 4)
+    s = np.linspace(20.0, 400.0, 9)
+    full = engine.multipoles(z, s, [0, 2, 4])
+    n = len(z) * len(s)
+    cuts = [0, 7, 8, 20, n]
+    parts = [engine.multipoles_range(z, s, [0, 2, 4], a, b) for a, b in zip(cuts[:-1], cuts[1:])]
+    tiled = np.concatenate(parts, axis=1).reshape(3, len(z), len(s)).transpose(1, 0, 2)
+    assert np.array_equal(tiled, full)
+    again = engine.multipoles(z, s, [0, 2, 4])
+    assert np.array_equal(again, full), "results must be deterministic run to run"
+
+
+def test_pieces_add_up_and_terms_are_bilinear(engine):
+    """xi(den+rsd) = xi(den) + xi(rsd) + cross, and the cross term alone is what only_cross keeps"""
+    z, s = [1.0, 1.7], np.linspace(15.0, 300.0, 6)
+    engine.set_options(["den", "rsd"]); both = engine.multipoles(z, s, [0, 2, 4])
+    engine.set_options(["den"]); den = engine.multipoles(z, s, [0, 2, 4])
+    engine.set_options(["rsd"]); rsd = engine.multipoles(z, s, [0, 2, 4])
+    engine.set_options(["den", "rsd"], only_cross=True); cross = engine.multipoles(z, s, [0, 2, 4])
+    assert np.allclose(both, den + rsd + cross, rtol=1e-12, atol=1e-18)
+    engine.set_options(ALL); pieces = engine.multipoles_pieces(z, s, [0, 2, 4]); tot = engine.multipoles(z, s, [0, 2, 4])
+    assert np.array_equal(pieces.sum(0), tot) or np.allclose(pieces.sum(0), tot, rtol=1e-15)
+
+
+def test_odd_multipoles_of_symmetric_terms_vanish(engine):
+    """odd multipoles of all effects with identical populations ~ 0 (tests/test_multipoles.c:505-557)"""
+    engine.set_options(ALL)
+    got = engine.multipoles([1.0], SEP_H / H, [0, 1, 3])[0]
+    assert np.all(np.abs(got[1]) < 1e-3 * np.abs(got[0]))
+    assert np.all(np.abs(got[2]) < 1e-3 * np.abs(got[0]))
+
+
+def test_quadrature_self_convergence_on_a_wide_grid(engine):
+    """default rules vs doubled rules across the bench grid's corners: the fixed-node error budget"""
+    engine.set_options(ALL)
+    z = [0.5, 2.0]
+    s = [15.0, 120.0, 448.0]
+    base = engine.multipoles(z, s, [0, 2, 4])
+    engine.set_quadrature(n_mu_panel=8, mu_panel_width=16.0, n_outer=96, n_panel_si=12, n_panel_di=10, panel_width=8.0,
+                          panel_uniform_extent=640.0, tail_ratio=1.3, n_mu_ni=64)
+    fine = engine.multipoles(z, s, [0, 2, 4])
+    engine.set_quadrature()
+    err = np.abs(base / fine - 1)
+    assert np.all(err < 1e-5), err
+
+
+def test_errors_are_reported_not_fatal(engine, tableset):
+    import coffe_b200
+    engine.set_options(ALL)
+    with pytest.raises(coffe_b200.CoffeB200Error) as e:
+        engine.multipoles([20.0], [50.0], [0])          # beyond the background table
+    assert e.value.code == 5
+    with pytest.raises(coffe_b200.CoffeB200Error) as e:
+        engine.multipoles([1.0], [50.0], list(range(9)))
+    assert e.value.code == 1
+    fresh = coffe_b200.Engine(0)
+    with pytest.raises(coffe_b200.CoffeB200Error) as e:
+        fresh.multipoles([1.0], [50.0], [0])
+    assert e.value.code == 3
+    assert engine.multipoles([1.0], [], [0]).shape == (1, 1, 0)      # empty grid is fine
