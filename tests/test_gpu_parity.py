@@ -19,17 +19,27 @@ SKIP = {("den", 2), ("den", 4), ("d1", 4), ("d2", 2), ("d2", 4), ("g1", 2), ("g1
         ("g3", 2), ("g3", 4)}
 
 
+INTEGRATED = {"len", "g4", "g5"}
+
+
+def golden_tolerance(name):
+    """5e-4 is the reference's own pytest tolerance (tests/test_coffe.py:303).  Golden vectors of sets with a
+    line-of-sight integrated effect were produced by the budget-truncated Cuhre path (750 009 evaluations, own
+    error estimate 1e-3..4e-2, SURVEY.md section 6) and deviate from the converged integral by up to ~1.5e-3;
+    for those the reference's C suite tolerance applies (5e-3, tests/test_multipoles.c:200).  The 1e-5 gate
+    for these terms is test_multipoles_match_converged_oracle."""
+    return 5e-3 if INTEGRATED & set(GOLDEN_SETS[name]) else 5e-4
+
+
 @pytest.mark.parametrize("name", list(GOLDEN_SETS))
 def test_multipoles_match_reference_golden_vectors(engine, golden, name):
-    """tolerance = the reference's own (5e-4, tests/test_coffe.py:303): the goldens for the lensing terms
-    carry the stock Cuhre truncation error"""
     engine.set_options(GOLDEN_SETS[name])
     got = engine.multipoles([1.0], SEP_H / H, [0, 2, 4])[0]
     for il, l in enumerate((0, 2, 4)):
         if (name, l) in SKIP:
             continue
         want = golden[f"{name}_multipoles{l}"][:, 1]
-        assert np.allclose(got[il], want, rtol=5e-4), (name, l, got[il] / want - 1)
+        assert np.allclose(got[il], want, rtol=golden_tolerance(name)), (name, l, got[il] / want - 1)
 
 
 @pytest.mark.parametrize("name", ["den", "rsd", "std", "std_d1"])
@@ -50,7 +60,8 @@ def test_corrfunc_matches_reference_golden_vectors(engine, golden, name):
     got = engine.corrfunc([1.0], mus, SEP_H / H)[0]
     for im in range(5):
         want = golden[f"{name}_corrfunc{im}"][:, 1]
-        assert np.allclose(got[im], want, rtol=5e-4, atol=5e-4 * np.abs(want).max() * 1e-3), (name, im, got[im] / want - 1)
+        tol = golden_tolerance(name)
+        assert np.allclose(got[im], want, rtol=tol, atol=tol * np.abs(want).max() * 1e-3), (name, im, got[im] / want - 1)
 
 
 def test_kernels_reproduce_cpu_evaluation_of_the_same_rules(engine, ref, tableset):
