@@ -146,10 +146,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
-        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+    import os
+    path = Path(os.environ.get("COFFE_B200_LIB", LIB_PATH))      # override: kernel-variant experiments only
+    if not path.exists():
+        raise RuntimeError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(coffe_b200 has no CPU fallback)")
-    lib = C.CDLL(str(LIB_PATH))
+    lib = C.CDLL(str(path))
     lib.coffe_b200_last_error.restype = C.c_char_p
     lib.coffe_b200_last_error.argtypes = [C.c_void_p]
     _lib = lib

@@ -31,13 +31,15 @@ struct Arena {
 };
 
 struct SplineOff { size_t x = 0, k = 0; int n = 0; };
+struct HintOff { size_t hint = 0; int n_hint = 0; double log_lo = 0, inv_dlog = 0; };
 
 struct Layout {
     size_t bg_z = 0; int bg_n = 0; double bg_inv_dz = 0;
     size_t bg_a = 0, bg_Hc = 0, bg_D1 = 0, bg_f = 0, bg_G1 = 0, bg_G2 = 0, bg_chi = 0;
     SplineOff z_of_chi, bias[8], i40, ren0, flat_i1[3], flat_half[4];
+    HintOff i40_hint;
     size_t ifam_x = 0, ifam_k = 0; int ifam_n = 0, ifam_n_small = 0; double ifam_r0 = 1, ifam_inv_dln = 0;
-    size_t ren2d_x = 0, ren2d_node = 0; int ren2d_n = 0; double ren2d_x0 = 0, ren2d_inv_dx = 0;
+    size_t ren2d_x = 0, ren2d_node = 0; int ren2d_n = 0; double ren2d_x0 = 0, ren2d_inv_dx = 0, ren2d_dx = 0;
     size_t los = 0; int los_n = 0; double los_h = 0;
     int has_divergent = 0, has_flat_i1 = 0, has_flat_half = 0;
     double chi_max_table = 0;     /* largest chi of the background table */
@@ -70,11 +72,16 @@ inline Tables make_view(const Layout &L, const double *base)
     t.ifam.x = base + L.ifam_x;
     t.ifam.k = reinterpret_cast<const double4 *>(base + L.ifam_k);
     t.ifam.n = L.ifam_n; t.ifam.n_small = L.ifam_n_small; t.ifam.r0 = L.ifam_r0; t.ifam.inv_dln = L.ifam_inv_dln;
-    t.i40 = view_of(L.i40, base);
+    {
+        const SplineView v = view_of(L.i40, base);
+        t.i40.x = v.x; t.i40.k = v.k; t.i40.n = v.n;
+        t.i40.hint = reinterpret_cast<const int *>(base + L.i40_hint.hint);
+        t.i40.n_hint = L.i40_hint.n_hint; t.i40.log_lo = L.i40_hint.log_lo; t.i40.inv_dlog = L.i40_hint.inv_dlog;
+    }
     t.ren0 = view_of(L.ren0, base);
     t.ren2d.x = base + L.ren2d_x;
     t.ren2d.node = reinterpret_cast<const double4 *>(base + L.ren2d_node);
-    t.ren2d.n = L.ren2d_n; t.ren2d.x0 = L.ren2d_x0; t.ren2d.inv_dx = L.ren2d_inv_dx;
+    t.ren2d.n = L.ren2d_n; t.ren2d.x0 = L.ren2d_x0; t.ren2d.inv_dx = L.ren2d_inv_dx; t.ren2d.dx = L.ren2d_dx;
     t.los.v = reinterpret_cast<const double4 *>(base + L.los);
     t.los.n = L.los_n; t.los.h = L.los_h; t.los.inv_h = L.los_h > 0 ? 1.0 / L.los_h : 0.0;
     for (int i = 0; i < 3; ++i) t.flat_i1[i] = view_of(L.flat_i1[i], base);
@@ -179,6 +186,23 @@ inline bool assemble(const coffe_b200_tables &T, Arena &A, Layout &L, std::strin
         const coffe_b200_integral *i40 = find_integral(T, 4, 0, 0);
         if (!i40 || !T.renorm_chi || !T.renorm_z) { err = "renormalisation grid given without I^4_0"; return false; }
         if (!put_spline(A, i40->result, kind, L.i40, err, "I^4_0")) return false;
+        {
+            /* bucket table in log(r) over [x_1, x_(n-1)] (x_0 may be tiny but is positive, src/integrals.c:76) */
+            const coffe_b200_spline &sp = i40->result;
+            if (!(sp.x[1] > 0.0)) { err = "I^4_0 knots must be positive"; return false; }
+            const int nb = 1024;
+            const double lo = std::log(sp.x[1]), hi = std::log(sp.x[sp.n - 1]);
+            std::vector<double> packed((nb + 1) / 2 + 1, 0.0);
+            int *hint = reinterpret_cast<int *>(packed.data());
+            int i = 0;
+            for (int b = 0; b < nb; ++b) {
+                const double edge = std::exp(lo + (hi - lo) * b / nb);
+                while (i < sp.n - 2 && sp.x[i + 1] <= edge) ++i;
+                hint[b] = i;
+            }
+            L.i40_hint.hint = A.put(packed.data(), packed.size());
+            L.i40_hint.n_hint = nb; L.i40_hint.log_lo = lo; L.i40_hint.inv_dlog = nb / (hi - lo);
+        }
         if (!put_spline(A, T.renorm_zero_separation, kind, L.ren0, err, "renormalization_zero_separation")) return false;
         const int nr = T.n_renorm;
         if (nr < 4) { err = "renormalisation grid too small"; return false; }
@@ -188,6 +212,9 @@ inline bool assemble(const coffe_b200_tables &T, Arena &A, Layout &L, std::strin
         L.ren2d_n = nr;
         L.ren2d_x0 = T.renorm_chi[0];
         L.ren2d_inv_dx = (nr - 1) / (T.renorm_chi[nr - 1] - T.renorm_chi[0]);
+        L.ren2d_dx = (T.renorm_chi[nr - 1] - T.renorm_chi[0]) / (nr - 1);
+        for (int i = 0; i < nr; ++i)
+            if (std::fabs(T.renorm_chi[i] - (L.ren2d_x0 + i * L.ren2d_dx)) > 1e-9 * L.ren2d_dx * nr) { err = "renormalisation grid must be uniform"; return false; }
         L.has_divergent = 1;
     }
     /* ---- flat-sky closed-form tables (optional) ---- */

@@ -108,9 +108,13 @@ struct ItemShared {
     SIHalf ha, hb;
     DIConst k;
     double red[kItemWarps][2];
+    double panels[kItemWarps][2 * kMaxPanels];      /* per-warp panel list of ridge_integrate */
 };
 
-__global__ void __launch_bounds__(kItemThreads) integrated_items_kernel(
+#ifndef COFFE_ITEM_MIN_BLOCKS
+#define COFFE_ITEM_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(kItemThreads, COFFE_ITEM_MIN_BLOCKS) integrated_items_kernel(
     const __grid_constant__ Tables t, const __grid_constant__ Options o, const __grid_constant__ Rules q,
     const double *__restrict__ pz, const double *__restrict__ psep,
     const int *__restrict__ item_point, const double *__restrict__ item_mu, const int n_items,
@@ -149,12 +153,9 @@ __global__ void __launch_bounds__(kItemThreads) integrated_items_kernel(
         out_evals[2 * item + tid] = tid == 0 ? (has_si ? si_eval_count(q, sh.g, sh.ha) + si_eval_count(q, sh.g, sh.hb) : 0u)
                                              : (has_di ? di_eval_count(q, sh.g) : 0u);
     }
-    if (has_di) di = di_partial(t, q, sh.g, sh.k, los, warp, kItemWarps, lane, 32);
-    if (has_si) {
-        /* warps alternate between the two halves */
-        if ((warp & 1) == 0) si = si_half_partial(t, q, sh.g, sh.ha, los, (warp >> 1) * 32 + lane, (kItemWarps / 2) * 32);
-        else si = si_half_partial(t, q, sh.g, sh.hb, los, (warp >> 1) * 32 + lane, (kItemWarps / 2) * 32);
-    }
+    /* local x integrated: one warp per half (1-D, ~3% of the work); the other warps go straight to the 2-D piece */
+    if (has_si && warp < 2) si = si_half_partial(t, q, sh.g, warp == 0 ? sh.ha : sh.hb, los, lane, 32, sh.panels[warp]);
+    if (has_di) di = di_partial(t, q, sh.g, sh.k, los, warp, kItemWarps, lane, 32, sh.panels[warp]);
     di = warp_sum(di);
     si = warp_sum(si);
     if (lane == 0) { sh.red[warp][0] = si; sh.red[warp][1] = di; }
@@ -635,7 +636,10 @@ int coffe_b200_set_quadrature(coffe_b200_ctx *ctx, const coffe_b200_quadrature *
     if (!ctx || !q) return COFFE_B200_EINVAL;
     std::lock_guard<std::mutex> lock(ctx->mu);
     const QuadConfig merged = merge_quadrature(default_quadrature(), *q);
-    if (!quadrature_valid(merged)) { ctx->err = "quadrature sizes out of range"; return COFFE_B200_EINVAL; }
+    if (!quadrature_valid(merged, kMaxPanels)) {
+        ctx->err = "quadrature sizes out of range (node counts 2..128; the line-of-sight panel plan must fit " + std::to_string(kMaxPanels) + " panels)";
+        return COFFE_B200_EINVAL;
+    }
     ctx->qc = merged;
     return COFFE_B200_OK;
 }

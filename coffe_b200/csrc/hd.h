@@ -6,7 +6,16 @@
 #if defined(__CUDACC__)
 #define COFFE_HD __host__ __device__ __forceinline__
 #define COFFE_D __device__ __forceinline__
+#if defined(__CUDA_ARCH__)
+#define COFFE_SYNC_LANES() __syncwarp()
+#define COFFE_RSQRT(x) rsqrt(x)
 #else
+#define COFFE_SYNC_LANES() ((void)0)
+#define COFFE_RSQRT(x) (1.0 / sqrt(x))
+#endif
+#else
+#define COFFE_SYNC_LANES() ((void)0)
+#define COFFE_RSQRT(x) (1.0 / std::sqrt(x))
 #define COFFE_HD inline
 #define COFFE_D inline
 #include <cmath>

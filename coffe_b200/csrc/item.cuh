@@ -18,11 +18,17 @@ struct Rules {
     double panel_w_mpc, panel_du, eps_min, tail_ratio;
 };
 
+/* panels one ridge_integrate call can hold in its scratch area (engine.cu checks the configured plan) */
+static const int kMaxPanels = 256;
+
 /* integral over lambda in [0, hi] of f(lambda), with a ridge (closest approach) at `center` of width
-   eps.  Lane-strided partial sum. */
+   eps.  Cooperative over `nlanes` lanes (one warp on the device; 1 in the CPU harness): first the lanes
+   fill `scratch` (2*kMaxPanels doubles shared by the lanes) with {start, signed width} of every clipped
+   panel, then each lane owns one Gauss-Legendre node index and strides over the panels.  Returns this
+   lane's partial sum. */
 template <class F>
 COFFE_HD double ridge_integrate(const F &f, const double hi, const double center, const double eps,
-                                const Rules &q, const int n_panel, const int lane, const int nlanes)
+                                const Rules &q, const int n_panel, const int lane, const int nlanes, double *scratch)
 {
     const double *panel_x = q.gl_x + rule_offset(n_panel), *panel_w = q.gl_w + rule_offset(n_panel);
     const PanelPlan plan = panel_plan(eps, q.eps_min, q.panel_w_mpc, q.panel_du, q.tail_ratio);
@@ -32,22 +38,41 @@ COFFE_HD double ridge_integrate(const F &f, const double hi, const double center
     const double b_pos = hi - center;
     const int k_neg = panel_count(plan, b_neg);
     const int k_pos = b_pos > 0.0 ? panel_count(plan, b_pos) : 0;
-    const int total = (k_neg + k_pos) * n_panel;
-    double acc = 0.0;
-    for (int idx = lane; idx < total; idx += nlanes) {
-        const int p = idx / n_panel, j = idx - p * n_panel;
+    int total = k_neg + k_pos;
+    if (total > kMaxPanels) total = kMaxPanels;
+    for (int p = lane; p < total; p += nlanes) {
         const bool neg = p < k_neg;
         const int k = neg ? p : p - k_neg;
         double lo = panel_break(plan, k), up = panel_break(plan, k + 1);
         const double a = neg ? a_neg : 0.0, b = neg ? b_neg : b_pos;
         if (lo < a) lo = a;
         if (up > b) up = b;
-        const double width = up - lo;
-        if (width <= 0.0) continue;
-        const double d = lo + width * panel_x[j];
-        const double lambda = neg ? center - d : center + d;
-        acc += width * panel_w[j] * f(lambda);
+        const double width = up > lo ? up - lo : 0.0;
+        scratch[2 * p] = neg ? center - lo : center + lo;
+        scratch[2 * p + 1] = neg ? -width : width;
     }
+    COFFE_SYNC_LANES();
+    double acc = 0.0;
+    if (nlanes >= n_panel) {
+        const int ppi = nlanes / n_panel;           /* panels in flight per sweep */
+        const int lp = lane / n_panel, j = lane - lp * n_panel;
+        if (lp < ppi) {
+            const double xj = panel_x[j], wj = panel_w[j];
+            for (int p = lp; p < total; p += ppi) {
+                const double a = scratch[2 * p], w = scratch[2 * p + 1];
+                if (w == 0.0) continue;
+                acc += fabs(w) * wj * f(a + w * xj);
+            }
+        }
+    }
+    else {
+        for (int p = 0; p < total; ++p) {
+            const double a = scratch[2 * p], w = scratch[2 * p + 1];
+            if (w == 0.0) continue;
+            for (int jj = lane; jj < n_panel; jj += nlanes) acc += fabs(w) * panel_w[jj] * f(a + w * panel_x[jj]);
+        }
+    }
+    COFFE_SYNC_LANES();
     return acc;
 }
 
@@ -82,12 +107,12 @@ struct SIFunctor {
 
 /* one half of the local x integrated piece, per unit x (the reference integrates x in [0,1], src/signal.c:584-606) */
 COFFE_HD double si_half_partial(const Tables &t, const Rules &q, const Geometry &g, const SIHalf &h,
-                                const double4 *los, const int lane, const int nlanes)
+                                const double4 *los, const int lane, const int nlanes, double *scratch)
 {
     SIFunctor f{&t, &h, &g, los, t.los.n, t.los.inv_h};
     const double center = h.cs * g.c;
     const double eps = h.cs * sqrt(g.s2);
-    return ridge_integrate(f, h.co, center, eps, q, q.n_panel_si, lane, nlanes) / h.co;
+    return ridge_integrate(f, h.co, center, eps, q, q.n_panel_si, lane, nlanes, scratch) / h.co;
 }
 
 COFFE_HD unsigned int si_eval_count(const Rules &q, const Geometry &g, const SIHalf &h)
@@ -107,7 +132,7 @@ struct DIFunctor {
 /* integrated x integrated piece per unit (x1, x2): outer nodes strided over `ngroups` groups of
    `nlanes` lanes (warps of a CTA on the device) */
 COFFE_HD double di_partial(const Tables &t, const Rules &q, const Geometry &g, const DIConst &k, const double4 *los,
-                           const int group, const int ngroups, const int lane, const int nlanes)
+                           const int group, const int ngroups, const int lane, const int nlanes, double *scratch)
 {
     double acc = 0.0;
     const double sth = sqrt(g.s2);
@@ -116,7 +141,7 @@ COFFE_HD double di_partial(const Tables &t, const Rules &q, const Geometry &g, c
     for (int io = group; io < n_outer; io += ngroups) {
         const double l1 = g.chi1 * outer_x[io];
         DIFunctor f{&t, &k, &g, los, t.los.n, t.los.inv_h, l1, los_eval(los, t.los.n, t.los.inv_h, l1)};
-        acc += outer_w[io] * ridge_integrate(f, g.chi2, l1 * g.c, l1 * sth, q, q.n_panel_di, lane, nlanes);
+        acc += outer_w[io] * ridge_integrate(f, g.chi2, l1 * g.c, l1 * sth, q, q.n_panel_di, lane, nlanes, scratch);
     }
     return acc / g.chi2;
 }

@@ -97,18 +97,32 @@ struct SepConst {
 
 COFFE_HD void ifam_eval_all(const IntegralFamilyView &t, const double r, double out[N_ITAB])
 {
-    const int i = ifam_index(t, r);
-    const double dx = r - t.x[i];
+    /* speculative single round trip: knots and the interleaved record of the guessed interval are loaded
+       together; the (rare) wrong guess reloads */
+    int i = ifam_guess(t, r);
+    double xi = t.x[i];
+    const double xn = t.x[i + 1];
     const double4 *k = t.k + (size_t)i * N_ITAB;
+    double4 c[N_ITAB];
 #pragma unroll
-    for (int j = 0; j < N_ITAB; ++j) out[j] = cubic_eval(k[j], dx);
+    for (int j = 0; j < N_ITAB; ++j) c[j] = k[j];
+    if (!(r >= xi && (r < xn || i == t.n - 2))) {
+        i = ifam_index(t, r);
+        xi = t.x[i];
+        k = t.k + (size_t)i * N_ITAB;
+#pragma unroll
+        for (int j = 0; j < N_ITAB; ++j) c[j] = k[j];
+    }
+    const double dx = r - xi;
+#pragma unroll
+    for (int j = 0; j < N_ITAB; ++j) out[j] = cubic_eval(c[j], dx);
 }
 
 COFFE_HD SepConst sep_const(const Options &o, const Tables &t, const double z_mean, const double sep)
 {
     SepConst s;
     ifam_eval_all(t.ifam, sep, s.i);
-    s.i40 = o.divergent ? spline_eval(t.i40, sep) : 0.0;
+    s.i40 = o.divergent ? hspline_eval(t.i40, sep) : 0.0;
     s.z_mean = z_mean;
     s.chi_mean = bg_chi(t.bg, z_mean);
     const BackgroundAtZ b = bg_eval_all(t.bg, z_mean);
@@ -301,7 +315,8 @@ COFFE_HD double si_half_eval(const Tables &t, const SIHalf &h, const Geometry &g
     const double dl = l - cs;
     double rr = dl * dl + 2.0 * cs * l * g.omc;
     if (rr < 0) rr = 0;
-    const double R = sqrt(rr);
+    const double iR = rr > 0.0 ? COFFE_RSQRT(rr) : 0.0;
+    const double R = rr * iR;
     double I[N_ITAB];
     ifam_eval_all(t.ifam, R, I);
     const double W = los.x, V = los.y, Wa = los.w;
@@ -309,7 +324,7 @@ COFFE_HD double si_half_eval(const Tables &t, const SIHalf &h, const Geometry &g
     if (h.any_lens) {
         double br = 0.0;
         if (rr != 0.0) {
-            const double irr = 1.0 / rr;
+            const double irr = iR * iR;
             const double tc = 2 * c2 - 1;
             if (h.a_denlen != 0.0)                                                                  /* :1592-1640 */
                 br += h.a_denlen * (2 * cs * c * I[I11] - cs * cs * l * s2 * I[I02] * irr);
@@ -351,7 +366,7 @@ COFFE_HD double si_half_eval(const Tables &t, const SIHalf &h, const Geometry &g
     if (h.any_g4 || h.any_g5) {
         double ren = 0.0;
         if (h.need_ren)                                                                             /* :1524-1556 */
-            ren = (rr == 0.0) ? spline_eval(t.ren0, l) : spline_eval(t.i40, R) - renorm2d_eval(t.ren2d, l, cs);
+            ren = (rr == 0.0) ? spline_eval(t.ren0, l) : hspline_eval(t.i40, R) - renorm2d_eval(t.ren2d, l, cs);
         const double b_rsd = (2 * rr / 3. - s2 * l * l) * I[I22] - I[I20] / 3.;
         const double b_d1 = (l * c - cs) * I[I31];
         if (h.any_g4) res += W * (h.g4_i20 * I[I20] + h.g4_rsd * b_rsd + h.g4_d1 * b_d1 + h.g4_ren * ren);
@@ -402,7 +417,8 @@ COFFE_HD double di_eval(const Tables &t, const DIConst &k, const Geometry &g, co
     const double d = l1 - l2;
     double r2 = d * d + 2.0 * l1 * l2 * g.omc;
     if (r2 < 0) r2 = 0;
-    const double R = sqrt(r2);
+    const double ir = r2 > 0.0 ? COFFE_RSQRT(r2) : 0.0;     /* 1/R: one reciprocal square root serves R, 1/r^2, 1/r^4 */
+    const double R = r2 * ir;
     double I[N_ITAB];
     ifam_eval_all(t.ifam, R, I);
     const double ll = l1 * l2;
@@ -412,7 +428,7 @@ COFFE_HD double di_eval(const Tables &t, const DIConst &k, const Geometry &g, co
     if (k.any_ll) {
         double br;
         if (r2 > 1e-20) {
-            const double ir2 = 1.0 / r2;
+            const double ir2 = ir * ir;
             const double cm = -g.s2;     /* cos^2(theta) - 1 */
             br = 2 * cm * ll * I[I00] / 5.
                + 4 * c * I[I20] / 3.
@@ -431,7 +447,7 @@ COFFE_HD double di_eval(const Tables &t, const DIConst &k, const Geometry &g, co
         res += WW * br * (k.k_4l * (w2 + w1) + k.k_5la * los1.z * w2 + k.k_5lb * los2.z * w1);
     }
     if (k.any_ren) {
-        const double ren = (r2 <= 1e-12) ? spline_eval(t.ren0, l1) : spline_eval(t.i40, R) - renorm2d_eval(t.ren2d, l1, l2);
+        const double ren = (r2 <= 1e-12) ? spline_eval(t.ren0, l1) : hspline_eval(t.i40, R) - renorm2d_eval(t.ren2d, l1, l2);
         res += WW * ren * (k.k_44 + k.k_55 * los1.y * los2.y + k.k_45a * los2.y + k.k_45b * los1.y);
     }
     return res * k.h4;

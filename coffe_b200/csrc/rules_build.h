@@ -45,8 +45,20 @@ inline QuadConfig merge_quadrature(const QuadConfig &base, const coffe_b200_quad
     return q;
 }
 
-inline bool quadrature_valid(const QuadConfig &q)
+/* upper bound on the panels of one line-of-sight integral (both sides of the ridge) */
+inline int max_panels(const QuadConfig &q, const double extent = 2.0e4)
 {
+    const int geo = q.eps_min < q.panel_w ? (int)std::ceil(std::log2(q.panel_w / q.eps_min)) + 2 : 0;
+    const int uni = (int)std::ceil(q.panel_du / q.panel_w) + 1;
+    const double start = std::max(q.panel_du, q.panel_w);
+    const int tail = extent > start ? (int)std::ceil(std::log(extent / start) / std::log(q.tail_ratio)) + 2 : 0;
+    return 2 * (geo + uni + tail);
+}
+
+inline bool quadrature_valid(const QuadConfig &q, const int panel_capacity)
+{
+    if (!(q.panel_w > 0 && q.eps_min > 0 && q.tail_ratio > 1.0 && q.panel_du >= 0)) return false;
+    if (max_panels(q) > panel_capacity) return false;
     return q.n_mu_ni >= 2 && q.n_mu_ni <= kMaxRule && q.n_mu_panel >= 2 && q.n_mu_panel <= kMaxRule &&
            q.n_outer >= 0 && q.n_outer <= kMaxRule && q.n_panel_si >= 2 && q.n_panel_si <= kMaxRule &&
            q.n_panel_di >= 2 && q.n_panel_di <= kMaxRule && q.n_z >= 1 && q.n_z <= kMaxRule &&

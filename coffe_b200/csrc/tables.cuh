@@ -44,6 +44,34 @@ COFFE_HD double spline_eval(const SplineView s, const double v)
     return cubic_eval(s.k[i], v - s.x[i]);
 }
 
+/* spline on irregular positive knots with a bucket table in log(x) that gives the starting interval, so a
+   lookup is a couple of forward steps instead of a binary search (I^4_0 has 297 hand-picked knots,
+   src/integrals.c:76-96) */
+struct HintedSplineView {
+    const double *x;
+    const double4 *k;
+    const int *hint;        /* hint[b] = largest i with x[i] <= exp(log_lo + b/inv_dlog), clamped to [0, n-2] */
+    int n, n_hint;
+    double log_lo, inv_dlog;
+};
+
+COFFE_HD double hspline_eval(const HintedSplineView s, const double v)
+{
+    int i = 0;
+    if (v > s.x[1]) {
+#if defined(__CUDA_ARCH__)
+        int b = (int)(((double)__logf((float)v) - s.log_lo) * s.inv_dlog) - 1;
+#else
+        int b = (int)((log(v) - s.log_lo) * s.inv_dlog) - 1;
+#endif
+        if (b < 0) b = 0;
+        if (b > s.n_hint - 1) b = s.n_hint - 1;
+        i = s.hint[b];
+        while (i < s.n - 2 && v >= s.x[i + 1]) ++i;
+    }
+    return cubic_eval(s.k[i], v - s.x[i]);
+}
+
 /* spline on (nominally) uniform knots: O(1) guess, then fix-up against the real knots so that the
    interval is exactly the one a binary search would return */
 struct UniformSplineView {
@@ -116,7 +144,7 @@ struct IntegralFamilyView {
     double r0, inv_dln;
 };
 
-COFFE_HD int ifam_index(const IntegralFamilyView &t, const double r)
+COFFE_HD int ifam_guess(const IntegralFamilyView &t, const double r)
 {
     if (r < t.r0) return knot_search(t.x, t.n_small + 1, r);
 #if defined(__CUDA_ARCH__)
@@ -126,8 +154,15 @@ COFFE_HD int ifam_index(const IntegralFamilyView &t, const double r)
 #endif
     if (i > t.n - 2) i = t.n - 2;
     if (i < t.n_small) i = t.n_small;
-    /* the float log is good to ~1e-6 absolute, far below the knot spacing: at most one step off */
-    while (i > t.n_small && r < t.x[i]) --i;
+    return i;
+}
+
+/* exact interval (the one a binary search returns): the float log is good to ~1e-6 absolute, far below
+   the knot spacing, so the guess is at most one step off and only within ~1e-6 of a knot */
+COFFE_HD int ifam_index(const IntegralFamilyView &t, const double r)
+{
+    int i = ifam_guess(t, r);
+    while (i > 0 && r < t.x[i]) --i;
     while (i < t.n - 2 && r >= t.x[i + 1]) ++i;
     return i;
 }
@@ -137,15 +172,21 @@ struct Renorm2DView {
     const double *x;        /* n knots (same on both axes) */
     const double4 *node;    /* n*n nodes {z, zx, zy, zxy}; index j*n + i with i <-> first argument */
     int n;
-    double x0, inv_dx;
+    double x0, inv_dx, dx;
 };
 
+/* the grid is uniform by construction (chi_j = j/nbins chi_max, src/integrals.c:876-878): the cell index and
+   the in-cell coordinates t, u come straight from the argument, no knot loads */
 COFFE_HD double renorm2d_eval(const Renorm2DView &t, const double x, const double y)
 {
-    const int xi = uniform_index(t.x, t.n, t.x0, t.inv_dx, x);
-    const int yi = uniform_index(t.x, t.n, t.x0, t.inv_dx, y);
-    const double dx = t.x[xi + 1] - t.x[xi], dy = t.x[yi + 1] - t.x[yi];
-    const double tt = (x - t.x[xi]) / dx, u = (y - t.x[yi]) / dy;
+    const double sx = (x - t.x0) * t.inv_dx, sy = (y - t.x0) * t.inv_dx;
+    int xi = (int)sx, yi = (int)sy;
+    if (xi < 0) xi = 0;
+    if (yi < 0) yi = 0;
+    if (xi > t.n - 2) xi = t.n - 2;
+    if (yi > t.n - 2) yi = t.n - 2;
+    const double tt = sx - xi, u = sy - yi;
+    const double dx = t.dx, dy = t.dx;
     const double4 n00 = t.node[yi * t.n + xi], n10 = t.node[yi * t.n + xi + 1];
     const double4 n01 = t.node[(yi + 1) * t.n + xi], n11 = t.node[(yi + 1) * t.n + xi + 1];
     const double t2 = tt * tt, t3 = t2 * tt, u2 = u * u, u3 = u2 * u;
@@ -194,7 +235,7 @@ struct Tables {
     BackgroundView bg;
     SplineView bias[8];        /* galaxy_bias1..4, magnification_bias1,2, evolution_bias1,2 */
     IntegralFamilyView ifam;
-    SplineView i40;            /* I^4_0(r) (divergent, renormalised) */
+    HintedSplineView i40;      /* I^4_0(r) (divergent, renormalised) */
     SplineView ren0;           /* renormalization_zero_separation */
     Renorm2DView ren2d;
     LosView los;

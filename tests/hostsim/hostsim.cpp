@@ -119,11 +119,13 @@ void hs_item(void *h, double z, double sep, double mu, double *out)
     if (opt_has_ni(o)) out[0] = ni_eval(o, s->t, sc, g, e1, e2);
     if (opt_has_si(o)) {
         const SIHalf ha = si_half_setup(o, g, e1, e2, true), hb = si_half_setup(o, g, e2, e1, false);
-        out[1] = si_half_partial(s->t, s->q, g, ha, s->t.los.v, 0, 1) + si_half_partial(s->t, s->q, g, hb, s->t.los.v, 0, 1);
+        double scratch[2 * kMaxPanels];
+        out[1] = si_half_partial(s->t, s->q, g, ha, s->t.los.v, 0, 1, scratch) + si_half_partial(s->t, s->q, g, hb, s->t.los.v, 0, 1, scratch);
     }
     if (opt_has_integrated(o)) {
         const DIConst k = di_setup(o, e1, e2);
-        out[2] = di_partial(s->t, s->q, g, k, s->t.los.v, 0, 1, 0, 1);
+        double scratch[2 * kMaxPanels];
+        out[2] = di_partial(s->t, s->q, g, k, s->t.los.v, 0, 1, 0, 1, scratch);
     }
 }
 

@@ -88,6 +88,23 @@ def test_fixed_node_rules_vs_converged_oracle_pointwise(ref, tableset):
         assert np.all(np.abs(got - want) / tot < 2e-6), (z, s, mu, np.abs(got - want) / tot)
 
 
+def test_stock_reference_truncation_error(ref, tableset, golden):
+    """Why the 1e-5 gate cannot be the stock reference: its lensing-lensing multipoles (Cuhre, 750 009
+    evaluations, fail flag ignored, src/common.c:1098-1118) differ from the converged integral of its own
+    integrands by ~1e-3 (l=0), ~1e-2 (l=2), ~4e-2 (l=4) at r = 10 Mpc/h -- and the golden file agrees with
+    the stock path, not with the converged one."""
+    from oracle.converged import ConvergedOracle
+    ref.set_contributions(["len"])
+    s = 10.0 / 0.67
+    conv = ConvergedOracle(ref, n_outer=64, n_panel=8, mu_kw=dict(n=6, W=24.0)).multipoles_pieces(1.0, s, [0, 2, 4], want=(False, False, True))[2]
+    hs = hostsim_bridge.HostSim(ref, ["len"], tableset=tableset)
+    ours = hs.multipoles(1.0, s, [0, 2, 4])[2]
+    gold = np.array([golden[f"len_multipoles{l}"][0, 1] for l in (0, 2, 4)])
+    assert np.all(np.abs(ours / conv - 1) < 5e-6), ours / conv - 1
+    dev = np.abs(gold / conv - 1)
+    assert 5e-4 < dev[0] < 5e-3 and 5e-3 < dev[1] < 3e-2 and 1e-2 < dev[2] < 8e-2, dev
+
+
 def test_panel_plan_covers_interval():
     """the panel break points are increasing, start at 0 and the counted panels cover the extent"""
     from oracle.converged import breakpoints
