@@ -59,6 +59,14 @@ class Quadrature(C.Structure):
                 ("tail_ratio", C.c_double)]
 
 
+class CovarianceParams(C.Structure):
+    _fields_ = [("pk_k", dp), ("pk_p", dp), ("n_pk", C.c_int), ("k_min", C.c_double), ("k_max", C.c_double), ("n_bins", C.c_int),
+                ("z_mean", dp), ("deltaz", dp), ("z_min", dp), ("z_max", dp),
+                ("fsky", dp), ("density1", dp), ("density2", dp), ("pixelsize", dp),
+                ("sep", dp), ("n_sep", C.c_int), ("l", ip), ("n_l", C.c_int), ("pop", C.c_int * 4),
+                ("cosmic", C.c_int), ("mixed", C.c_int), ("poisson", C.c_int), ("window", C.c_int), ("average", C.c_int)]
+
+
 def darr(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 

@@ -41,7 +41,7 @@ struct Layout {
     size_t ifam_x = 0, ifam_k = 0; int ifam_n = 0, ifam_n_small = 0; double ifam_r0 = 1, ifam_inv_dln = 0;
     size_t ren2d_x = 0, ren2d_node = 0; int ren2d_n = 0; double ren2d_x0 = 0, ren2d_inv_dx = 0, ren2d_dx = 0;
     size_t los = 0; int los_n = 0; double los_h = 0;
-    int has_divergent = 0, has_flat_i1 = 0, has_flat_half = 0;
+    int has_divergent = 0, has_flat_i1 = 0, has_flat_half = 0, has_ifam = 0, interp_kind = 5;
     double chi_max_table = 0;     /* largest chi of the background table */
     double r_max_table = 0;       /* largest r of the I^n_l family */
 };
@@ -119,6 +119,7 @@ static const int kLosSamples = 2048;
 inline bool assemble(const coffe_b200_tables &T, Arena &A, Layout &L, std::string &err)
 {
     const int kind = T.interp_method;
+    L.interp_kind = kind;
     /* ---- background ---- */
     const coffe_b200_spline &chi = T.background[COFFE_B200_BG_COMOVING_DISTANCE];
     if (!chi.x || chi.n < 5) { err = "missing background tables"; return false; }
@@ -149,7 +150,9 @@ inline bool assemble(const coffe_b200_tables &T, Arena &A, Layout &L, std::strin
         if ((i == 2 || i == 3) && !T.bias[i].x) { L.bias[i] = SplineOff(); continue; }
         if (!put_spline(A, T.bias[i], kind, L.bias[i], err, bias_names[i])) return false;
     }
-    /* ---- I^n_l family on shared knots ---- */
+    /* ---- I^n_l family on shared knots (absent when only the covariance is wanted) ---- */
+    L.has_ifam = T.n_integrals > 0;
+    if (L.has_ifam) {
     const coffe_b200_integral *fam[N_ITAB];
     for (int t = 0; t < N_ITAB; ++t) {
         fam[t] = find_integral(T, kFamilyN[t], kFamilyL[t], 0);
@@ -180,9 +183,10 @@ inline bool assemble(const coffe_b200_tables &T, Arena &A, Layout &L, std::strin
         else { L.ifam_r0 = fx[ns]; L.ifam_inv_dln = (m - 1 - ns) / std::log(fx[m - 1] / fx[ns]); }
         L.ifam_n_small = ns;
     }
+    }
     /* ---- divergent extras ---- */
     L.has_divergent = 0;
-    if (T.n_renorm > 0) {
+    if (L.has_ifam && T.n_renorm > 0) {
         const coffe_b200_integral *i40 = find_integral(T, 4, 0, 0);
         if (!i40 || !T.renorm_chi || !T.renorm_z) { err = "renormalisation grid given without I^4_0"; return false; }
         if (!put_spline(A, i40->result, kind, L.i40, err, "I^4_0")) return false;
@@ -218,14 +222,14 @@ inline bool assemble(const coffe_b200_tables &T, Arena &A, Layout &L, std::strin
         L.has_divergent = 1;
     }
     /* ---- flat-sky closed-form tables (optional) ---- */
-    L.has_flat_i1 = 1;
-    for (int i = 0; i < 3; ++i) {
+    L.has_flat_i1 = L.has_ifam;
+    for (int i = 0; i < 3 && L.has_ifam; ++i) {
         const coffe_b200_integral *t = find_integral(T, 1, 2 * i, 0);
         if (!t) { L.has_flat_i1 = 0; break; }
         if (!put_spline(A, t->result, kind, L.flat_i1[i], err, "I^1_l")) return false;
     }
-    L.has_flat_half = 1;
-    {
+    L.has_flat_half = L.has_ifam;
+    if (L.has_ifam) {
         /* I^{(l-2k+3)/2}_{(l-2k+1)/2}, stored by the reference with n = l-2k+3, l = l-2k+1, i.e.
            (n, l) = (3,1), (5,3), (7,5) plus (1,-1)          src/functions.c:4210-4230, src/integrals.c:916-1083 */
         static const int hn[4] = {1, 3, 5, 7}, hl[4] = {-1, 1, 3, 5};

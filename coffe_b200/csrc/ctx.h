@@ -1,0 +1,68 @@
+// Internal state shared by the translation units of libcoffe_b200 (engine.cu, covariance.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "assemble.h"
+#include "item.cuh"
+#include "rules_build.h"
+
+using namespace coffe;
+
+struct coffe_b200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    /* tables */
+    bool have_tables = false;
+    Arena arena;            /* host copy (set-up and range checks only) */
+    Layout layout;
+    double *d_arena = nullptr;
+    Tables t;               /* device view */
+    Tables t_host;          /* host view */
+    double omega_matter = 0, h = 0;
+    /* options / quadrature */
+    Options o;
+    QuadConfig qc;
+    double *d_gl_x = nullptr, *d_gl_w = nullptr;
+    /* timing of the last call */
+    double last_ms = 0;
+    int last_launches = 0;
+    std::mutex mu;
+};
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            return COFFE_B200_ECUDA;                                                                 \
+        }                                                                                            \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t count)
+    {
+        if (p) { cudaFree(p); p = nullptr; }
+        n = count;
+        return cudaMalloc(&p, (count ? count : 1) * sizeof(T));
+    }
+    cudaError_t upload(const std::vector<T> &v, cudaStream_t s)
+    {
+        cudaError_t e = alloc(v.size());
+        if (e != cudaSuccess) return e;
+        if (v.empty()) return cudaSuccess;
+        return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+};

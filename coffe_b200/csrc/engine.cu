@@ -22,11 +22,7 @@
 #include <string>
 #include <vector>
 
-#include "assemble.h"
-#include "item.cuh"
-#include "rules_build.h"
-
-using namespace coffe;
+#include "ctx.h"
 
 namespace {
 
@@ -244,60 +240,9 @@ __global__ void __launch_bounds__(256) dfma_probe_kernel(double *out, const int 
 }  // namespace
 
 /* ================================================================================================= */
-struct coffe_b200_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::string err;
-    /* tables */
-    bool have_tables = false;
-    Arena arena;            /* host copy (set-up and range checks only) */
-    Layout layout;
-    double *d_arena = nullptr;
-    Tables t;               /* device view */
-    Tables t_host;          /* host view */
-    double omega_matter = 0, h = 0;
-    /* options / quadrature */
-    Options o;
-    QuadConfig qc;
-    double *d_gl_x = nullptr, *d_gl_w = nullptr;
-    /* timing of the last call */
-    double last_ms = 0;
-    int last_launches = 0;
-    std::mutex mu;
-};
-
 static std::string g_create_error;
 
-#define CK(call)                                                                                     \
-    do {                                                                                             \
-        cudaError_t e_ = (call);                                                                     \
-        if (e_ != cudaSuccess) {                                                                     \
-            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
-            return COFFE_B200_ECUDA;                                                                 \
-        }                                                                                            \
-    } while (0)
-
 namespace {
-
-template <class T>
-struct DevBuf {
-    T *p = nullptr;
-    size_t n = 0;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t count)
-    {
-        n = count;
-        return cudaMalloc(&p, (count ? count : 1) * sizeof(T));
-    }
-    cudaError_t upload(const std::vector<T> &v, cudaStream_t s)
-    {
-        cudaError_t e = alloc(v.size());
-        if (e != cudaSuccess) return e;
-        if (v.empty()) return cudaSuccess;
-        return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
-    }
-};
 
 Rules make_rules(const coffe_b200_ctx *ctx)
 {
@@ -448,7 +393,7 @@ namespace {
 int plan_build(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double *sep, int n_sep, const int *l, int n_l,
                long begin, long end, coffe_b200_plan &pl)
 {
-    if (!ctx->have_tables) { ctx->err = "no tables uploaded"; return COFFE_B200_ENOTABLES; }
+    if (!ctx->have_tables || !ctx->layout.has_ifam) { ctx->err = "no tables uploaded (the signal needs the I^n_l family)"; return COFFE_B200_ENOTABLES; }
     if (n_z < 0 || n_sep < 0 || (n_z > 0 && !z_mean) || (n_sep > 0 && !sep)) { ctx->err = "bad grid arguments"; return COFFE_B200_EINVAL; }
     int rc = check_l(ctx, l, n_l);
     if (rc) return rc;
@@ -707,7 +652,7 @@ int coffe_b200_corrfunc(coffe_b200_ctx *ctx, const double *z_mean, int n_z, cons
 {
     if (!ctx || !out) return COFFE_B200_EINVAL;
     std::lock_guard<std::mutex> lock(ctx->mu);
-    if (!ctx->have_tables) { ctx->err = "no tables uploaded"; return COFFE_B200_ENOTABLES; }
+    if (!ctx->have_tables || !ctx->layout.has_ifam) { ctx->err = "no tables uploaded (the signal needs the I^n_l family)"; return COFFE_B200_ENOTABLES; }
     if (!z_mean || !sep || !mu || n_z < 0 || n_sep < 0 || n_mu < 0) { ctx->err = "bad grid arguments"; return COFFE_B200_EINVAL; }
     ctx->last_ms = 0; ctx->last_launches = 0;
     const size_t n_out = (size_t)n_z * n_mu * n_sep;
@@ -767,7 +712,7 @@ int coffe_b200_average_multipoles(coffe_b200_ctx *ctx, const double *z_min, cons
 {
     if (!ctx || !out) return COFFE_B200_EINVAL;
     std::lock_guard<std::mutex> lock(ctx->mu);
-    if (!ctx->have_tables) { ctx->err = "no tables uploaded"; return COFFE_B200_ENOTABLES; }
+    if (!ctx->have_tables || !ctx->layout.has_ifam) { ctx->err = "no tables uploaded (the signal needs the I^n_l family)"; return COFFE_B200_ENOTABLES; }
     if (!z_min || !z_max || !sep || n_bins < 0 || n_sep < 0) { ctx->err = "bad grid arguments"; return COFFE_B200_EINVAL; }
     int rc = check_l(ctx, l, n_l);
     if (rc) return rc;

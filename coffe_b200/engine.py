@@ -104,6 +104,36 @@ class Engine:
                                                            capi.iptr(ls), C.c_int(len(ls)), capi.ptr(out)))
         return out
 
+    def covariance(self, pk, sep, l, fsky, density1, density2, pixelsize, z_mean=None, deltaz=None, z_min=None, z_max=None,
+                   pops=(1, 1, 1, 1), cosmic=True, mixed=True, poisson=True, window=False, k_min=None, k_max=None):
+        """[n_bins, n_l, n_sep, n_l, n_sep]; pk = (k, P) knots of the power-spectrum spline"""
+        average = z_mean is None
+        k, p = capi.darr(pk[0]), capi.darr(pk[1])
+        s, ls = capi.darr(sep), capi.iarr(l)
+        n_bins = len(z_min) if average else len(z_mean)
+        arrs = {name: capi.darr(v) for name, v in (("fsky", fsky), ("density1", density1), ("density2", density2), ("pixelsize", pixelsize))}
+        for name, v in arrs.items():
+            assert len(v) == n_bins, name
+        cp = capi.CovarianceParams()
+        cp.pk_k, cp.pk_p, cp.n_pk = capi.ptr(k), capi.ptr(p), len(k)
+        cp.k_min = float(k[0] if k_min is None else k_min)
+        cp.k_max = float(k[-1] if k_max is None else k_max)
+        cp.n_bins = n_bins
+        keep = []
+        for name, v in (("z_mean", z_mean), ("deltaz", deltaz), ("z_min", z_min), ("z_max", z_max)):
+            if v is not None:
+                a = capi.darr(v)
+                keep.append(a)
+                setattr(cp, name, capi.ptr(a))
+        for name, a in arrs.items():
+            setattr(cp, name, capi.ptr(a))
+        cp.sep, cp.n_sep, cp.l, cp.n_l = capi.ptr(s), len(s), capi.iptr(ls), len(ls)
+        cp.pop = (C.c_int * 4)(*pops)
+        cp.cosmic, cp.mixed, cp.poisson, cp.window, cp.average = int(cosmic), int(mixed), int(poisson), int(window), int(average)
+        out = np.empty((n_bins, len(ls), len(s), len(ls), len(s)))
+        self._check(self.lib.coffe_b200_covariance(self._h, C.byref(cp), capi.ptr(out)))
+        return out
+
     # ---- prepared computations (inputs resident in HBM) -----------------------------------------------
     def plan_multipoles(self, z_mean, sep, l, begin=0, end=None):
         z, s, ls = capi.darr(z_mean), capi.darr(sep), capi.iarr(l)

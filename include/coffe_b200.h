@@ -133,6 +133,31 @@ int coffe_b200_corrfunc(coffe_b200_ctx *ctx, const double *z_mean, int n_z, cons
 int coffe_b200_average_multipoles(coffe_b200_ctx *ctx, const double *z_min, const double *z_max, int n_bins,
                                   const double *sep, int n_sep, const int *l, int n_l, double *out);
 
+/* ---- covariance ----------------------------------------------------------------------------------- */
+/* the members of coffe_parameters_t that coffe_covariance_init reads (src/covariance.c:477-1103) */
+typedef struct coffe_b200_covariance_params {
+    const double *pk_k, *pk_p;   /* knots of par->power_spectrum (k [1/Mpc], P [Mpc^3]) */
+    int n_pk;
+    double k_min, k_max;         /* par->k_min, par->k_max */
+    int n_bins;
+    const double *z_mean, *deltaz;       /* covariance of multipoles   (average = 0) */
+    const double *z_min, *z_max;         /* covariance of redshift-averaged multipoles (average = 1) */
+    const double *fsky, *density1, *density2, *pixelsize;   /* per bin */
+    const double *sep;
+    int n_sep;
+    const int *l;
+    int n_l;
+    int pop[4];                  /* covariance_pop1..4, 1-based */
+    int cosmic, mixed, poisson;  /* covariance_cosmic / _mixed / _poisson */
+    int window;                  /* covariance_window (bin-averaged Bessel functions) */
+    int average;                 /* output_type == COVARIANCE_AVERAGE_MULTIPOLES */
+} coffe_b200_covariance_params;
+
+/* out[(((ibin*n_l + il1)*n_sep + ir1)*n_l + il2)*n_sep + ir2]   (order of src/covariance.c:1046-1059);
+   density / rsd switches come from coffe_b200_set_options, background and galaxy_bias1..4 from the uploaded
+   tables; covariance_integration_method = standard */
+int coffe_b200_covariance(coffe_b200_ctx *ctx, const coffe_b200_covariance_params *p, double *out);
+
 /* device time of the kernels of the last compute call [ms] and their launch count (bench / roofline) */
 int coffe_b200_last_timing(const coffe_b200_ctx *ctx, double *kernel_ms, int *n_launches);
 

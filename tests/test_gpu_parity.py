@@ -214,3 +214,74 @@ def test_errors_are_reported_not_fatal(engine, tableset):
         fresh.multipoles([1.0], [50.0], [0])
     assert e.value.code == 3
     assert engine.multipoles([1.0], [], [0]).shape == (1, 1, 0)      # empty grid is fine
+
+
+# ---- covariance ----------------------------------------------------------------------------------------
+COV_SEP_H = np.arange(50.0, 350.0, 50.0)      # tests/test_coffe.py:382-399
+
+
+def _cov_setup(ref, window):
+    """set-up of the reference's covariance test: z = 1, deltaz = 0.1, fsky = 0.2, n = 1e-3 h^3, pixelsize = 50/h"""
+    ref.set_contributions(["den", "rsd"])
+    ref.set_z_mean([1.0]); ref.set_deltaz([0.1])
+    ref.set_sep(COV_SEP_H / H)
+    ref.set_fsky([0.2]); ref.set_density1([1e-3 * H ** 3]); ref.set_density2([1e-3 * H ** 3]); ref.set_pixelsize([50.0 / H])
+    ref.set_covariance(window=int(window))
+
+
+def _cov_restore(ref):
+    ref.set_z_mean([0.5, 1.0, 1.5, 2.0]); ref.set_deltaz([0.3] * 4); ref.set_sep(SEP_H / H)
+
+
+@pytest.mark.parametrize("window", [False, True])
+def test_covariance_matches_reference(engine, ref, window):
+    """every entry of the (3x6)^2 covariance vs the reference's own QAG path.  At the stock precision
+    (integration_1d_prec = 1e-5) QAG itself is only good to ~4e-5 on the oscillatory unbinned integrals
+    (tightening it to 1e-8 moves the stock numbers by 4.2e-5), so: 1e-4 against the stock run, 2e-6 against
+    the same reference code with integration_1d_prec = 1e-8."""
+    from oracle import coffe_oracle as O
+    engine.set_options(["den", "rsd"])
+    got = engine.covariance(O.load_pk(), COV_SEP_H / H, [0, 2, 4], [0.2], [1e-3 * H ** 3], [1e-3 * H ** 3], [50.0 / H],
+                            z_mean=[1.0], deltaz=[0.1], window=window)[0]
+    _cov_setup(ref, window)
+    stock = ref.covariance()[0]
+    ref.set_integration(prec=1e-8)
+    tight = ref.covariance()[0]
+    ref.set_integration(prec=1e-5)
+    _cov_restore(ref)
+    d = np.sqrt(np.abs(np.einsum("iaia->ia", tight)))
+    scale = d[:, :, None, None] * d[None, None, :, :]
+    assert np.all(np.abs(got - stock) <= 1e-4 * np.abs(stock) + 1e-6 * scale), np.abs(got / stock - 1).max()
+    assert np.all(np.abs(got - tight) <= 2e-6 * np.abs(tight) + 1e-8 * scale), np.abs(got / tight - 1).max()
+
+
+def test_covariance_matches_golden(engine, golden):
+    """benchmark_multipoles_covariance_{l1 l2}.dat (defaults: unbinned, tests/test_coffe.py:382-416)"""
+    from oracle import coffe_oracle as O
+    engine.set_options(["den", "rsd"])
+    got = engine.covariance(O.load_pk(), COV_SEP_H / H, [0, 2, 4], [0.2], [1e-3 * H ** 3], [1e-3 * H ** 3], [50.0 / H],
+                            z_mean=[1.0], deltaz=[0.1], window=False)[0]
+    for i1, l1 in enumerate((0, 2, 4)):
+        for i2, l2 in enumerate((0, 2, 4)):
+            g = golden[f"multipoles_covariance_{l1}{l2}"]
+            assert np.allclose(g[:, 0].reshape(6, 6)[:, 0], COV_SEP_H) and np.allclose(g[:, 1].reshape(6, 6)[0], COV_SEP_H)
+            want = g[:, 2].reshape(6, 6)
+            assert np.allclose(got[i1, :, i2, :], want, rtol=5e-4), (l1, l2, got[i1, :, i2, :] / want - 1)
+
+
+def test_covariance_structure(engine):
+    """symmetric, positive definite, Poisson-only diagonal, distinct populations kill shot noise
+    (tests/test_coffe.py:419-430, 496-547)"""
+    from oracle import coffe_oracle as O
+    engine.set_options(["den", "rsd"])
+    kw = dict(z_mean=[1.0], deltaz=[0.1])
+    args = (O.load_pk(), COV_SEP_H / H, [0, 2, 4], [0.2], [1e-3 * H ** 3], [1e-3 * H ** 3], [50.0 / H])
+    cov = engine.covariance(*args, window=True, **kw)[0].reshape(18, 18)
+    assert np.allclose(cov, cov.T, rtol=1e-10)
+    assert np.all(np.linalg.eigvalsh(cov) > 0)
+    zero = engine.covariance(*args, cosmic=False, mixed=False, poisson=False, **kw)
+    assert np.all(zero == 0)
+    pois = engine.covariance(*args, cosmic=False, mixed=False, poisson=True, **kw)[0].reshape(18, 18)
+    assert np.all(np.diag(pois) > 0) and np.count_nonzero(pois - np.diag(np.diag(pois))) == 0
+    distinct = engine.covariance(*args, cosmic=False, mixed=True, poisson=True, pops=(1, 2, 3, 4), **kw)
+    assert np.all(distinct == 0)
