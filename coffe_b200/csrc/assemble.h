@@ -36,12 +36,13 @@ struct HintOff { size_t hint = 0; int n_hint = 0; double log_lo = 0, inv_dlog = 
 struct Layout {
     size_t bg_z = 0; int bg_n = 0; double bg_inv_dz = 0;
     size_t bg_a = 0, bg_Hc = 0, bg_D1 = 0, bg_f = 0, bg_G1 = 0, bg_G2 = 0, bg_chi = 0;
-    SplineOff z_of_chi, bias[8], i40, ren0, flat_i1[3], flat_half[4];
+    SplineOff z_of_chi, bias[8], i40, ren0, extra[kMaxExtra];
+    int extra_n[kMaxExtra] = {0}, extra_l[kMaxExtra] = {0}, extra_half[kMaxExtra] = {0}, n_extra = 0;
     HintOff i40_hint;
     size_t ifam_x = 0, ifam_k = 0; int ifam_n = 0, ifam_n_small = 0; double ifam_r0 = 1, ifam_inv_dln = 0;
     size_t ren2d_x = 0, ren2d_node = 0; int ren2d_n = 0; double ren2d_x0 = 0, ren2d_inv_dx = 0, ren2d_dx = 0;
     size_t los = 0; int los_n = 0; double los_h = 0;
-    int has_divergent = 0, has_flat_i1 = 0, has_flat_half = 0, has_ifam = 0, interp_kind = 5;
+    int has_divergent = 0, has_ifam = 0, interp_kind = 5;
     double chi_max_table = 0;     /* largest chi of the background table */
     double r_max_table = 0;       /* largest r of the I^n_l family */
 };
@@ -84,9 +85,12 @@ inline Tables make_view(const Layout &L, const double *base)
     t.ren2d.n = L.ren2d_n; t.ren2d.x0 = L.ren2d_x0; t.ren2d.inv_dx = L.ren2d_inv_dx; t.ren2d.dx = L.ren2d_dx;
     t.los.v = reinterpret_cast<const double4 *>(base + L.los);
     t.los.n = L.los_n; t.los.h = L.los_h; t.los.inv_h = L.los_h > 0 ? 1.0 / L.los_h : 0.0;
-    for (int i = 0; i < 3; ++i) t.flat_i1[i] = view_of(L.flat_i1[i], base);
-    for (int i = 0; i < 4; ++i) t.flat_half[i] = view_of(L.flat_half[i], base);
-    t.has_divergent = L.has_divergent; t.has_flat_i1 = L.has_flat_i1; t.has_flat_half = L.has_flat_half;
+    t.n_extra = L.n_extra;
+    for (int i = 0; i < L.n_extra; ++i) {
+        t.extra[i].n = L.extra_n[i]; t.extra[i].l = L.extra_l[i]; t.extra[i].half = L.extra_half[i];
+        t.extra[i].s = view_of(L.extra[i], base);
+    }
+    t.has_divergent = L.has_divergent;
     return t;
 }
 
@@ -221,23 +225,18 @@ inline bool assemble(const coffe_b200_tables &T, Arena &A, Layout &L, std::strin
             if (std::fabs(T.renorm_chi[i] - (L.ren2d_x0 + i * L.ren2d_dx)) > 1e-9 * L.ren2d_dx * nr) { err = "renormalisation grid must be uniform"; return false; }
         L.has_divergent = 1;
     }
-    /* ---- flat-sky closed-form tables (optional) ---- */
-    L.has_flat_i1 = L.has_ifam;
-    for (int i = 0; i < 3 && L.has_ifam; ++i) {
-        const coffe_b200_integral *t = find_integral(T, 1, 2 * i, 0);
-        if (!t) { L.has_flat_i1 = 0; break; }
-        if (!put_spline(A, t->result, kind, L.flat_i1[i], err, "I^1_l")) return false;
-    }
-    L.has_flat_half = L.has_ifam;
-    if (L.has_ifam) {
-        /* I^{(l-2k+3)/2}_{(l-2k+1)/2}, stored by the reference with n = l-2k+3, l = l-2k+1, i.e.
-           (n, l) = (3,1), (5,3), (7,5) plus (1,-1)          src/functions.c:4210-4230, src/integrals.c:916-1083 */
-        static const int hn[4] = {1, 3, 5, 7}, hl[4] = {-1, 1, 3, 5};
-        for (int i = 0; i < 4; ++i) {
-            const coffe_b200_integral *t = find_integral(T, hn[i], hl[i], 1);
-            if (!t) { L.has_flat_half = 0; break; }
-            if (!put_spline(A, t->result, kind, L.flat_half[i], err, "half-integer I^n_l")) return false;
-        }
+    /* ---- every other uploaded table (flat-sky closed forms), kept by key ---- */
+    L.n_extra = 0;
+    for (int i = 0; i < T.n_integrals; ++i) {
+        const coffe_b200_integral &it = T.integrals[i];
+        const bool half = it.half_integer != 0;
+        bool in_family = false;
+        for (int t = 0; t < N_ITAB; ++t) in_family = in_family || (!half && it.n == kFamilyN[t] && it.l == kFamilyL[t]);
+        if (in_family || (!half && it.n == 4 && it.l == 0)) continue;
+        if (L.n_extra == kMaxExtra) { err = "too many extra I^n_l tables"; return false; }
+        if (!put_spline(A, it.result, kind, L.extra[L.n_extra], err, "extra I^n_l")) return false;
+        L.extra_n[L.n_extra] = it.n; L.extra_l[L.n_extra] = it.l; L.extra_half[L.n_extra] = half;
+        ++L.n_extra;
     }
     /* ---- line-of-sight table (filled later by evaluating the splines above) ---- */
     L.los_n = kLosSamples;

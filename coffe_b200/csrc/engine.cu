@@ -192,6 +192,33 @@ __global__ void reduce_multipoles_kernel(const int *__restrict__ point_begin, co
     }
 }
 
+/* ---- flat-sky closed forms (src/signal.c:610-631, 707-735) ------------------------------------------- */
+/* adds the density-lensing closed form to piece 1 and the 1-D lensing-lensing integral to piece 2 of
+   pm[(point*3 + piece)*n_l + il]; one warp per (point, l) */
+__global__ void flatsky_multipoles_kernel(const __grid_constant__ Tables t, const __grid_constant__ Options o,
+                                          const double *__restrict__ pz, const double *__restrict__ psep, const int n_points,
+                                          const double *__restrict__ gl_x, const double *__restrict__ gl_w, const int n_x,
+                                          const LList ls, const int do_denlen, const int do_lenlen, double *__restrict__ pm)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_points * ls.n) return;
+    const int point = warp / ls.n, il = warp % ls.n, l = ls.l[il];
+    const double z = pz[point], sep = psep[point];
+    const SepConst sc = sep_const(o, t, z, sep);
+    if (do_denlen && lane == 0) pm[((size_t)point * 3 + 1) * ls.n + il] += flatsky_density_lensing_multipole(o, t, sc, sep, l);
+    if (do_lenlen && l % 2 == 0) {
+        const SplineView *s = find_extra(t, 1, l, 0);
+        double acc = 0.0;
+        if (s) {
+            const double *x = gl_x + rule_offset(n_x), *w = gl_w + rule_offset(n_x);
+            for (int j = lane; j < n_x; j += 32) acc += w[j] * flatsky_lensing_lensing_integrand(o, t, sc, *s, sep, l, x[j]);
+        }
+        else acc = nan("");
+        acc = warp_sum(acc);
+        if (lane == 0) pm[((size_t)point * 3 + 2) * ls.n + il] += 2 * 3.14159265358979323846 * 3.14159265358979323846 * acc;
+    }
+}
+
 /* ---- redshift average ---------------------------------------------------------------------------
    points (bin, r, iz): z = z1 + (z2 - z1) u, z1 = z(chi(z_min) + r/2), z2 = z(chi(z_max) - r/2), weight
    w_u H0 h / (Hc(z) (1+z))                                            src/signal.c:262-283 */
@@ -314,8 +341,9 @@ LList make_llist(const int *l, const int n_l)
 }
 
 /* per-point multipoles of the three pieces into b.pm[(point*3 + piece)*n_l + il] */
-int run_multipole_batch(coffe_b200_ctx *ctx, Batch &b, const LList &ls)
+int run_multipole_batch(coffe_b200_ctx *ctx, Batch &b, const LList &ls, const bool closed_forms)
 {
+    ctx->o.out_multipoles = closed_forms ? 1 : 0;
     const bool has_ni = opt_has_ni(ctx->o);
     if (has_ni) {
         const int blocks = (b.n_points * 32 + 127) / 128;
@@ -331,6 +359,17 @@ int run_multipole_batch(coffe_b200_ctx *ctx, Batch &b, const LList &ls)
                                                               has_ni ? b.ni.p : nullptr, ls, b.pm.p);
     CK(cudaGetLastError());
     ctx->last_launches += 1;
+    /* flat-sky closed forms replace the corresponding full-sky integrals (src/signal.c:610-631, 707-735) */
+    const Options &o = ctx->o;
+    const int do_denlen = closed_forms && o.flatsky_local_nonlocal && o.len && o.den;
+    const int do_lenlen = closed_forms && o.flatsky_nonlocal && o.len && !o.only_cross;
+    if (do_denlen || do_lenlen) {
+        const int nb = (b.n_points * ls.n * 32 + 127) / 128;
+        flatsky_multipoles_kernel<<<nb, 128, 0, ctx->stream>>>(ctx->t, ctx->o, b.pz.p, b.psep.p, b.n_points, ctx->d_gl_x, ctx->d_gl_w, 96, ls,
+                                                               do_denlen, do_lenlen, b.pm.p);
+        CK(cudaGetLastError());
+        ctx->last_launches += 1;
+    }
     return COFFE_B200_OK;
 }
 
@@ -400,9 +439,19 @@ int plan_build(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double 
     const long total = (long)n_z * n_sep;
     if (begin < 0 || end > total || begin > end) { ctx->err = "item range outside the grid"; return COFFE_B200_EINVAL; }
     const Options &o = ctx->o;
-    if ((o.flatsky_local_nonlocal && o.len && (o.den || o.rsd || o.d1)) || (o.flatsky_nonlocal && o.len)) {
-        ctx->err = "flat-sky closed forms for density-lensing / lensing-lensing multipoles are not available in this build";
-        return COFFE_B200_EINVAL;
+    /* tables of the flat-sky closed forms must have been uploaded for every requested even l */
+    for (int i = 0; i < n_l; ++i) {
+        if (l[i] % 2) continue;
+        if (o.flatsky_nonlocal && o.len && !o.only_cross && !find_extra(ctx->t_host, 1, l[i], 0)) {
+            ctx->err = "flat-sky lensing-lensing multipoles need the I^1_l table of every even l (src/integrals.c:1085-1247)";
+            return COFFE_B200_ENOTABLES;
+        }
+        if (o.flatsky_local_nonlocal && o.len && o.den)
+            for (int k = 0; k <= l[i] / 2; ++k)
+                if (!find_extra(ctx->t_host, l[i] - 2 * k + 3, l[i] - 2 * k + 1, 1)) {
+                    ctx->err = "flat-sky density-lensing multipoles need the half-integer I^n_l tables (src/integrals.c:1249-1413)";
+                    return COFFE_B200_ENOTABLES;
+                }
     }
     pl.ctx = ctx; pl.n = end - begin; pl.ls = make_llist(l, n_l);
     if (end == begin) return COFFE_B200_OK;
@@ -435,7 +484,7 @@ int plan_run(coffe_b200_plan &pl)
     if (pl.n == 0) return COFFE_B200_OK;
     CK(cudaSetDevice(ctx->device));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    const int rc = run_multipole_batch(ctx, pl.b, pl.ls);
+    const int rc = run_multipole_batch(ctx, pl.b, pl.ls, true);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     return COFFE_B200_OK;
@@ -685,6 +734,7 @@ int coffe_b200_corrfunc(coffe_b200_ctx *ctx, const double *z_mean, int n_z, cons
     CK(b.si.alloc(b.n_items));
     CK(b.di.alloc(b.n_items));
     CK(b.ni.alloc(b.n_items));
+    ctx->o.out_multipoles = 0;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     if (opt_has_ni(ctx->o)) {
         ni_points_kernel<<<(b.n_items + 127) / 128, 128, 0, ctx->stream>>>(ctx->t, ctx->o, b.pz.p, b.psep.p, b.item_point.p, b.item_mu.p, b.n_items, b.ni.p);
@@ -759,7 +809,7 @@ int coffe_b200_average_multipoles(coffe_b200_ctx *ctx, const double *z_min, cons
                                                                           ctx->d_gl_x, ctx->d_gl_w, nz, b.pz.p, b.psep.p, pw.p);
     CK(cudaGetLastError());
     ctx->last_launches += 1;
-    rc = run_multipole_batch(ctx, b, make_llist(l, n_l));
+    rc = run_multipole_batch(ctx, b, make_llist(l, n_l), false);
     if (rc) return rc;
     average_reduce_kernel<<<(n_groups * 3 * n_l + 127) / 128, 128, 0, ctx->stream>>>(b.pm.p, pw.p, n_groups, nz, n_l, gm.p);
     CK(cudaGetLastError());
@@ -839,6 +889,7 @@ int coffe_b200_plan_count(coffe_b200_plan *plan, double *n_items, double *n_ni_e
     if (b.n_items > 0 && opt_has_integrated(ctx->o)) {
         CK(cudaSetDevice(ctx->device));
         CK(b.evals.alloc((size_t)2 * b.n_items));
+        ctx->o.out_multipoles = 1;
         int rc = launch_integrated(ctx, b);
         if (rc) return rc;
         std::vector<unsigned int> h((size_t)2 * b.n_items);

@@ -28,6 +28,8 @@ struct Options {
     int only_cross;
     int flatsky_local, flatsky_local_nonlocal, flatsky_nonlocal;
     int divergent;
+    int out_multipoles;   /* 1 while serving coffe_multipoles_init: the flat-sky closed forms of src/signal.c:610-631, 707-735
+                             exist only for flag_output == MULTIPOLES, not for the 2PCF or the redshift average */
     double Om;     /* Omega0_cdm + Omega0_baryon */
     double H0h;    /* COFFE_H0 * h  [1/Mpc] */
 };
@@ -393,7 +395,12 @@ COFFE_HD DIConst di_setup(const Options &o, const EndVals &e1, const EndVals &e2
     const double Om2 = o.Om * o.Om;
     const double m1 = 2.0 - 5.0 * e1.s, m2 = 2.0 - 5.0 * e2.s;
     const bool autos = !o.only_cross;
-    k.k_ll = (o.len && autos && !o.flatsky_nonlocal) ? 9. * Om2 * m1 * m2 / 4. : 0.0;
+    /* With flatsky_nonlocal the dispatcher skips the 3-D integral only when neither g4 nor g5 is on
+       (src/signal.c:737-752); when it does run, the integrand still holds the full-sky len-len term because its
+       flat-sky branch needs output_type != MULTIPOLES, which the Python API never sets (src/functions.c:3521,
+       SURVEY.md 8a note 7) -- so the reference then adds both, and so do we. */
+    const bool skip_ll = o.flatsky_nonlocal && o.out_multipoles && !o.g4 && !o.g5;
+    k.k_ll = (o.len && autos && !skip_ll) ? 9. * Om2 * m1 * m2 / 4. : 0.0;
     k.k_4l = (o.g4 && o.len) ? 9 * Om2 / 2. * m1 * m2 : 0.0;
     k.k_5la = (o.g5 && o.len) ? 9 * Om2 / 2. * m2 * e1.G * e1.chi : 0.0;
     k.k_5lb = (o.g5 && o.len) ? 9 * Om2 / 2. * m1 * e2.G * e2.chi : 0.0;
@@ -465,6 +472,60 @@ COFFE_HD double4 los_point(const Tables &t, const double lambda)
     o.z = b.Hc * (b.Hc - 1.0);
     o.w = b.D1 * b.a;
     return o;
+}
+
+/* ---- flat-sky closed forms for the multipoles ----------------------------------------------------- */
+COFFE_HD double factorial_d(const int n)
+{
+    double r = 1.0;
+    for (int k = 2; k <= n; ++k) r *= k;
+    return r;
+}
+
+COFFE_HD double choose_d(const int n, int m)
+{
+    if (m > n) return 0.0;
+    if (m > n - m) m = n - m;
+    double r = 1.0;
+    for (int k = 1; k <= m; ++k) r = r * (n - m + k) / k;
+    return floor(r + 0.5);
+}
+
+/* density-lensing multipole l in the flat-sky limit: finite sum over the half-integer tables
+   I^{(l-2k+3)/2}_{(l-2k+1)/2}(r); includes the reference's 2 pi^2 (src/functions.c:4136-4253, src/signal.c:610-631).
+   Returns NaN when a needed table was not uploaded. */
+COFFE_HD double flatsky_density_lensing_multipole(const Options &o, const Tables &t, const SepConst &sc, const double sep, const int l)
+{
+    if (l % 2 != 0) return 0.0;
+    double sum = 0.0;
+    for (int k = 0; k <= l / 2; ++k) {
+        const SplineView *s = find_extra(t, l - 2 * k + 3, l - 2 * k + 1, 1);
+        if (!s) return nan("");
+        const double sign = (k % 2 == 0) ? 1.0 : -1.0;
+        sum += sign / ldexp(1.0, k) * choose_d(l, k) * choose_d(2 * l - 2 * k, l) * factorial_d(l / 2 - k) * spline_eval(*s, sep);
+    }
+    const double pi = 3.14159265358979323846;
+    sum *= -3 * o.Om / pi / 8 * (2 * l + 1) * sc.D1m * sc.D1m * (1 + sc.z_mean) * sep
+         * ((2 - 5 * sc.sm1) * sc.bm2 + (2 - 5 * sc.sm2) * sc.bm1) * pow(2.0, 1 - l / 2);
+    return 2 * pi * pi * sum / sqrt(2 * pi) * o.H0h * o.H0h;
+}
+
+/* integrand in x of the flat-sky lensing-lensing multipole l (src/functions.c:4020-4132), without the 2 pi^2 */
+COFFE_HD double flatsky_lensing_lensing_integrand(const Options &o, const Tables &t, const SepConst &sc, const SplineView &i1l,
+                                                  const double sep, const int l, const double x)
+{
+    const double pi = 3.14159265358979323846;
+    const double lambda = sc.chi_mean * x;
+    const double z = spline_eval(t.bg.z_of_chi, lambda);
+    const int i = bg_index(t.bg, z);
+    const double D1 = cubic_eval(t.bg.D1[i], z - t.bg.z[i]);
+    const double fl2 = factorial_d(l / 2);
+    double r = (2 * l + 1) * factorial_d(l) / ldexp(1.0, l) / (fl2 * fl2)
+             * 9 * o.Om * o.Om * (2 - 5 * sc.sm1) * (2 - 5 * sc.sm2) * sc.chi_mean * sc.chi_mean * sc.chi_mean / 8. / pi
+             * spline_eval(i1l, x * sep) * D1 * D1 * (1 + z) * (1 + z) * (x * (1 - x)) * (x * (1 - x));
+    const double h2 = o.H0h * o.H0h;
+    if (l > 0) r *= x * sep;
+    return r * h2 * h2;
 }
 
 }  // namespace coffe

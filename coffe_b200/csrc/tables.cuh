@@ -230,6 +230,11 @@ COFFE_HD double4 los_eval(const double4 *v, const int n, const double inv_h, con
     return o;
 }
 
+/* an I^n_l table outside the interleaved family: I^1_l (flat-sky lensing-lensing multipoles, src/integrals.c:
+   1085-1247) and the half-integer tables (n/2, l/2) of the flat-sky density-lensing multipoles (:1249-1413) */
+struct ExtraSpline { int n, l, half; SplineView s; };
+static const int kMaxExtra = 24;
+
 /* everything a kernel needs, passed by value */
 struct Tables {
     BackgroundView bg;
@@ -239,10 +244,17 @@ struct Tables {
     SplineView ren0;           /* renormalization_zero_separation */
     Renorm2DView ren2d;
     LosView los;
-    SplineView flat_i1[3];     /* I^1_l, l = 0, 2, 4 (flat-sky lensing-lensing multipoles) */
-    SplineView flat_half[4];   /* half-integer family for flat-sky density-lensing, see engine */
-    int has_divergent, has_flat_i1, has_flat_half;
+    ExtraSpline extra[kMaxExtra];   /* every other uploaded I^n_l (flat-sky closed forms), looked up by key */
+    int n_extra;
+    int has_divergent;
 };
+
+COFFE_HD const SplineView *find_extra(const Tables &t, const int n, const int l, const int half)
+{
+    for (int i = 0; i < t.n_extra; ++i)
+        if (t.extra[i].n == n && t.extra[i].l == l && t.extra[i].half == half) return &t.extra[i].s;
+    return nullptr;
+}
 
 enum { B_GAL1 = 0, B_GAL2, B_GAL3, B_GAL4, B_MAG1, B_MAG2, B_EVO1, B_EVO2 };
 

@@ -55,6 +55,7 @@ void *hs_create(const coffe_b200_tables *T, const coffe_b200_options *opt)
     o.only_cross = opt->only_cross_correlations;
     o.flatsky_local = opt->flatsky_local; o.flatsky_local_nonlocal = opt->flatsky_local_nonlocal; o.flatsky_nonlocal = opt->flatsky_nonlocal;
     o.divergent = s->layout.has_divergent;
+    o.out_multipoles = 1;
     o.Om = T->omega_matter; o.H0h = T->h / 2997.92458;
     s->qc = default_quadrature();
     set_rules(s);
@@ -161,6 +162,22 @@ int hs_n_mu(void *h, double sep)
     std::vector<double> mu, w;
     build_mu_rule(s->qc, sep, mu, w);
     return (int)mu.size();
+}
+
+/* flat-sky closed forms of one (z, sep, l): out[0] = density-lensing multipole, out[1] = lensing-lensing multipole
+   (same arithmetic as flatsky_multipoles_kernel, n_x Gauss-Legendre nodes in x) */
+void hs_flatsky(void *h, double z, double sep, int l, int n_x, double *out)
+{
+    HostSim *s = (HostSim *)h;
+    const SepConst sc = sep_const(s->o, s->t, z, sep);
+    out[0] = flatsky_density_lensing_multipole(s->o, s->t, sc, sep, l);
+    out[1] = 0.0;
+    const SplineView *sv = find_extra(s->t, 1, l, 0);
+    if (!sv) { out[1] = nan(""); return; }
+    const double *x = s->bx.data() + rule_offset(n_x), *w = s->bw.data() + rule_offset(n_x);
+    double acc = 0.0;
+    for (int j = 0; j < n_x; ++j) acc += w[j] * flatsky_lensing_lensing_integrand(s->o, s->t, sc, *sv, sep, l, x[j]);
+    out[1] = 2 * 3.14159265358979323846 * 3.14159265358979323846 * acc;
 }
 
 }  // extern "C"

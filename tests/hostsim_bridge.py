@@ -54,3 +54,9 @@ class HostSim:
         out = np.zeros(3 * len(ls))
         self.lib.hs_multipoles(self.h, C.c_double(z), C.c_double(sep), capi.iptr(ls), C.c_int(len(ls)), capi.ptr(out))
         return out.reshape(3, len(ls))
+
+    def flatsky(self, z, sep, l, n_x=96):
+        """(density-lensing, lensing-lensing) flat-sky closed-form multipoles"""
+        out = np.zeros(2)
+        self.lib.hs_flatsky(self.h, C.c_double(z), C.c_double(sep), C.c_int(l), C.c_int(n_x), capi.ptr(out))
+        return out

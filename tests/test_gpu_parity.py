@@ -151,6 +151,47 @@ def test_average_multipoles_match_stock_reference(engine, ref):
     assert np.allclose(got, want, rtol=5e-4), got / want - 1
 
 
+def test_flatsky_closed_form_multipoles(ref, golden):
+    """has_flatsky_nonlocal / has_flatsky_local_nonlocal multipoles (tests/test_coffe.py:322-380): kernels vs the
+    reference run with the same switches and vs benchmark_flatsky_{lensing_lensing,density_lensing}_multipoles*.dat"""
+    import coffe_b200
+    from oracle_tables import tableset_from_oracle
+    sep = np.array([20.0, 40.0, 100.0, 150.0]) / H
+    try:
+        ref.set_sep(sep); ref.set_z_mean([1.0]); ref.set_deltaz([0.1])
+        ref.set_contributions(["den", "len"]); ref.set_flags(dict(flatsky_nonlocal=1, flatsky_local_nonlocal=1, only_cross=1))
+        want_dl = ref.multipoles()[0]
+        eng = coffe_b200.Engine(0)
+        eng.upload_tables(tableset_from_oracle(ref))
+        eng.set_options(["den", "len"], flatsky_nonlocal=True, flatsky_local_nonlocal=True, only_cross=True)
+        got_dl = eng.multipoles([1.0], sep, [0, 2, 4])[0]
+        assert np.allclose(got_dl, want_dl, rtol=1e-9), got_dl / want_dl - 1
+        ref.set_contributions(["len"]); ref.set_flags(dict(flatsky_nonlocal=1))
+        want_ll = ref.multipoles()[0]
+        eng.set_options(["len"], flatsky_nonlocal=True)
+        got_ll = eng.multipoles([1.0], sep, [0, 2, 4])[0]
+        assert np.allclose(got_ll, want_ll, rtol=2e-5), got_ll / want_ll - 1      # the reference's QAG runs at 1e-5
+        for il, l in enumerate((0, 2, 4)):
+            assert np.allclose(got_dl[il], golden[f"flatsky_density_lensing_multipoles{l}"][:, 1], rtol=5e-4)
+            assert np.allclose(got_ll[il], golden[f"flatsky_lensing_lensing_multipoles{l}"][:, 1], rtol=5e-4)
+        # odd multipoles of the closed forms are zero; the switches do not touch the 2PCF (SURVEY.md 8a note 7)
+        assert np.all(eng.multipoles([1.0], sep, [1, 3]) == 0)
+        full = coffe_b200.Engine(0)
+        full.upload_tables(tableset_from_oracle(ref)); full.set_options(["len"])
+        assert np.array_equal(eng.corrfunc([1.0], [0.3], sep[:2]), full.corrfunc([1.0], [0.3], sep[:2]))
+        # without the tables the call reports ENOTABLES instead of returning NaN
+        ref.set_flags({})
+        bare = coffe_b200.Engine(0)
+        bare.upload_tables(tableset_from_oracle(ref, want_flat=False)); bare.set_options(["len"], flatsky_nonlocal=True)
+        with pytest.raises(coffe_b200.CoffeB200Error) as e:
+            bare.multipoles([1.0], sep, [0, 2])
+        assert e.value.code == 3
+    finally:
+        ref.set_flags({})
+        ref.set_contributions(list(ALL))
+        _cov_restore(ref)
+
+
 # ---- size-independent properties on a larger grid ----------------------------------------------------
 def test_range_calls_tile_the_full_grid_bit_exactly(engine):
     engine.set_options(ALL)

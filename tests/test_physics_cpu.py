@@ -112,3 +112,36 @@ def test_panel_plan_covers_interval():
         for extent in (0.5, 30.0, 700.0, 5000.0):
             b = breakpoints(extent, eps, 16.0, 320.0, 1.5)
             assert b[0] == 0.0 and np.all(np.diff(b) > 0) and b[-1] >= extent
+
+
+def test_flatsky_closed_forms_match_reference_and_golden(ref, golden):
+    """flat-sky density-lensing (finite sum over half-integer tables) and lensing-lensing (1-D x integral)
+    multipoles: hot-path arithmetic vs the reference's own multipoles with the flat-sky switches set
+    (tests/test_coffe.py:322-380) and vs benchmark_flatsky_*_multipoles{0,2,4}.dat"""
+    from conftest import H
+    from oracle_tables import tableset_from_oracle
+    sep = np.array([20.0, 40.0, 100.0, 150.0]) / H
+    try:
+        ref.set_sep(sep); ref.set_z_mean([1.0]); ref.set_deltaz([0.1])
+        # lensing-lensing
+        ref.set_contributions(["len"]); ref.set_flags(dict(flatsky_nonlocal=1))
+        want_ll = ref.multipoles()[0]
+        ts = tableset_from_oracle(ref)
+        hs = hostsim_bridge.HostSim(ref, ["len"], tableset=ts, flatsky_nonlocal=True)
+        got_ll = np.array([[hs.flatsky(1.0, s, l)[1] for s in sep] for l in (0, 2, 4)])
+        assert np.allclose(got_ll, want_ll, rtol=2e-5), got_ll / want_ll - 1       # reference QAG runs at 1e-5
+        for il, l in enumerate((0, 2, 4)):
+            assert np.allclose(got_ll[il], golden[f"flatsky_lensing_lensing_multipoles{l}"][:, 1], rtol=5e-4)
+        # density-lensing
+        ref.set_contributions(["den", "len"]); ref.set_flags(dict(flatsky_nonlocal=1, flatsky_local_nonlocal=1, only_cross=1))
+        want_dl = ref.multipoles()[0]
+        ts = tableset_from_oracle(ref)      # the half-integer tables exist only with the switch on (src/integrals.c:1249)
+        hs = hostsim_bridge.HostSim(ref, ["den", "len"], tableset=ts, flatsky_nonlocal=True, flatsky_local_nonlocal=True, only_cross=True)
+        got_dl = np.array([[hs.flatsky(1.0, s, l)[0] for s in sep] for l in (0, 2, 4)])
+        assert np.allclose(got_dl, want_dl, rtol=1e-10), got_dl / want_dl - 1
+        for il, l in enumerate((0, 2, 4)):
+            assert np.allclose(got_dl[il], golden[f"flatsky_density_lensing_multipoles{l}"][:, 1], rtol=5e-4)
+    finally:
+        ref.set_flags({})
+        ref.set_contributions(list(ALL))
+        ref.set_sep(np.array([10.0, 20.0, 40.0, 100.0, 150.0]) / H); ref.set_z_mean([0.5, 1.0, 1.5, 2.0]); ref.set_deltaz([0.3] * 4)
