@@ -1,0 +1,132 @@
+// Shared-memory resident tables of the integrated-pieces kernel (K1 v2).
+//
+// The line-of-sight integrands evaluate the eight I^n_l(R) of the family, I^4_0(R) and the line-of-sight
+// functions at every node.  Read through L1/L2 from the full tables (10^4 knots x 256 B per interval,
+// scattered 32-byte records) those lookups bound the kernel (profiles/r1_items_kernel_v1_summary.txt:
+// l1tex at 78 % of peak, FP64 pipe at 22 %).  Here everything a node needs lives in ONE blob that each
+// CTA copies into shared memory once:
+//   * R < r_lo (= 1 Mpc for the reference's tables): the reference's own small-r knots
+//     (src/integrals.c:111-126), exact per-interval cubics, found through a bucket table indexed by the
+//     exponent and top two mantissa bits of R;
+//   * R >= r_lo: the family resampled as cubic Hermite data {f, h f'} on a binary "floating-point" grid:
+//     every quarter octave [2^e (1 + q/4), 2^e (1 + (q+1)/4)) is a region split into 2^m equal intervals,
+//     m chosen per region by the builder (compact_build.h) so that the resampling error stays below a
+//     tolerance within a knot budget.  The interval index, the left knot and 1/h come straight from the
+//     bits of R -- no logarithm, no knot array, no fix-up loop.  All eight functions of a knot are
+//     interleaved (128 B + 16 B padding so that lanes on different knots fall on different banks);
+//   * I^4_0: the reference's 297 hand-picked knots (src/integrals.c:76-96), exact cubics, bucket table on
+//     exponent + 5 mantissa bits.
+// The resampling error is part of the tolerance budget; the exact-table kernel stays
+// available (coffe_b200_set_kernel_variant) and the tests compare the two.
+#pragma once
+#include "tables.cuh"
+
+namespace coffe {
+
+static const int kKnotStride = 18;      /* doubles per compact knot: 8 x {f, h f'} + 2 padding */
+static const int kSmallStride = 34;     /* doubles per small-r interval: 8 x double4 + 2 padding */
+
+/* byte offsets are relative to the start of the blob and multiples of 16 */
+struct CompactHeader {
+    int bytes;                 /* size of the blob */
+    /* regions of the binary grid: id = (hi >> 18) - region0, hi = upper 32 bits of R */
+    int off_region, n_region, region0;
+    int off_knots, n_knots;
+    /* small-r exact records */
+    int off_shint, n_shint, shint0;
+    int off_sx, off_sk, sn;
+    /* I^4_0 */
+    int off_i40hint, n_i40hint, i40hint0;
+    int off_i40x, off_i40k, i40n;
+    double r_lo;               /* 2^e_min: first knot of the binary grid */
+    double max_rel_error;      /* achieved resampling error of the builder (relative to the local envelope) */
+    int valid;
+};
+
+#if defined(__CUDA_ARCH__)
+COFFE_D int hi_word(const double v) { return __double2hiint(v); }
+COFFE_D double from_hi_word(const int hi) { return __hiloint2double(hi, 0); }
+#else
+inline int hi_word(const double v) { long long b; memcpy(&b, &v, 8); return (int)(b >> 32); }
+inline double from_hi_word(const int hi) { const long long b = (long long)(unsigned int)hi << 32; double v; memcpy(&v, &b, 8); return v; }
+#endif
+
+/* view of a staged blob (shared memory on the device, host memory in the CPU harness) */
+struct CompactView {
+    const unsigned char *base;
+    CompactHeader h;
+};
+
+COFFE_HD void compact_ifam_all(const CompactView &c, const double r, double out[N_ITAB])
+{
+    const int hi = hi_word(r);
+    int reg = (hi >> 18) - c.h.region0;
+    if (reg < 0) {
+        /* small-r exact records */
+        int b = (hi >> 18) - c.h.shint0;
+        if (b < 0) b = 0;
+        if (b > c.h.n_shint - 1) b = c.h.n_shint - 1;
+        const int *hint = reinterpret_cast<const int *>(c.base + c.h.off_shint);
+        const double *sx = reinterpret_cast<const double *>(c.base + c.h.off_sx);
+        int i = hint[b];
+        while (i < c.h.sn - 2 && r >= sx[i + 1]) ++i;
+        const double dx = r - sx[i];
+        const double4 *k = reinterpret_cast<const double4 *>(c.base + c.h.off_sk + (size_t)i * kSmallStride * 8);
+#pragma unroll
+        for (int t = 0; t < N_ITAB; ++t) out[t] = cubic_eval(k[t], dx);
+        return;
+    }
+    if (reg > c.h.n_region - 1) reg = c.h.n_region - 1;
+    const int2 rg = reinterpret_cast<const int2 *>(c.base + c.h.off_region)[reg];     /* {first knot, 18 - m} */
+    int idx = rg.x + ((hi & 0x3FFFF) >> rg.y);
+    if (idx > c.h.n_knots - 2) idx = c.h.n_knots - 2;
+    const double xj = from_hi_word(hi & (int)(~0u << rg.y));
+    /* 1/h = 2^(m + 2 - E), m = 18 - rg.y, E = (hi >> 20) - 1023 */
+    const double inv_h = from_hi_word((2046 + 20 - rg.y - (hi >> 20)) << 20);
+    const double u = (r - xj) * inv_h;
+    const double u2 = u * u, um1 = u - 1.0;
+    const double h01 = u2 * fma(-2.0, u, 3.0);      /* 3u^2 - 2u^3 */
+    const double h10 = u * um1 * um1;
+    const double h11 = u2 * um1;
+    const double2 *k0 = reinterpret_cast<const double2 *>(c.base + c.h.off_knots + (size_t)idx * kKnotStride * 8);
+    const double2 *k1 = k0 + kKnotStride / 2;
+#pragma unroll
+    for (int t = 0; t < N_ITAB; ++t) {
+        const double2 a = k0[t], b = k1[t];
+        out[t] = fma(h01, b.x - a.x, fma(h10, a.y, fma(h11, b.y, a.x)));
+    }
+}
+
+COFFE_HD double compact_i40(const CompactView &c, const double r)
+{
+    const int hi = hi_word(r);
+    int b = (hi >> 15) - c.h.i40hint0;
+    if (b < 0) b = 0;
+    if (b > c.h.n_i40hint - 1) b = c.h.n_i40hint - 1;
+    const int *hint = reinterpret_cast<const int *>(c.base + c.h.off_i40hint);
+    const double *x = reinterpret_cast<const double *>(c.base + c.h.off_i40x);
+    int i = hint[b];
+    while (i < c.h.i40n - 2 && r >= x[i + 1]) ++i;
+    const double4 k = reinterpret_cast<const double4 *>(c.base + c.h.off_i40k)[i];
+    return cubic_eval(k, r - x[i]);
+}
+
+/* ---- table accessors: the integrands are written once against this interface ------------------- */
+struct ExactAccess {
+    const Tables *t;
+    COFFE_HD void ifam_all(const double r, double out[N_ITAB]) const { ifam_eval_all(t->ifam, r, out); }
+    COFFE_HD double i40(const double r) const { return hspline_eval(t->i40, r); }
+    COFFE_HD double ren2d(const double a, const double b) const { return renorm2d_eval(t->ren2d, a, b); }
+    COFFE_HD double ren0(const double l) const { return spline_eval(t->ren0, l); }
+};
+
+struct CompactAccess {
+    const Tables *t;           /* renormalisation grid and zero-separation spline stay in global memory (L2) */
+    CompactView c;
+    COFFE_HD void ifam_all(const double r, double out[N_ITAB]) const { compact_ifam_all(c, r, out); }
+    COFFE_HD double i40(const double r) const { return compact_i40(c, r); }
+    COFFE_HD double ren2d(const double a, const double b) const { return renorm2d_eval(t->ren2d, a, b); }
+    COFFE_HD double ren0(const double l) const { return spline_eval(t->ren0, l); }
+};
+
+}  // namespace coffe

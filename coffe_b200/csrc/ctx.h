@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "assemble.h"
+#include "compact_build.h"
 #include "item.cuh"
 #include "rules_build.h"
 
@@ -28,7 +29,14 @@ struct coffe_b200_ctx {
     /* options / quadrature */
     Options o;
     QuadConfig qc;
-    double *d_gl_x = nullptr, *d_gl_w = nullptr;
+    double *d_gl_x = nullptr, *d_gl_w = nullptr, *d_rpow = nullptr;
+    /* shared-memory tables of the integrated-pieces kernel */
+    CompactBuild compact;
+    double *d_blob = nullptr;
+    unsigned int *d_counter = nullptr;
+    int variant = 1;        /* 1 = shared-memory tables (default), 0 = exact tables through L1/L2 */
+    int last_variant = -1;
+    int n_sm = 0, smem_optin = 0;
     /* timing of the last call */
     double last_ms = 0;
     int last_launches = 0;

@@ -150,8 +150,9 @@ __global__ void __launch_bounds__(kItemThreads, COFFE_ITEM_MIN_BLOCKS) integrate
                                              : (has_di ? di_eval_count(q, sh.g) : 0u);
     }
     /* local x integrated: one warp per half (1-D, ~3% of the work); the other warps go straight to the 2-D piece */
-    if (has_si && warp < 2) si = si_half_partial(t, q, sh.g, warp == 0 ? sh.ha : sh.hb, los, lane, 32, sh.panels[warp]);
-    if (has_di) di = di_partial(t, q, sh.g, sh.k, los, warp, kItemWarps, lane, 32, sh.panels[warp]);
+    const ExactAccess ta{&t};
+    if (has_si && warp < 2) si = si_half_partial(ta, t.los, q, sh.g, warp == 0 ? sh.ha : sh.hb, los, lane, 32, sh.panels[warp]);
+    if (has_di) di = di_partial(ta, t.los, q, sh.g, sh.k, los, warp, kItemWarps, lane, 32, sh.panels[warp]);
     di = warp_sum(di);
     si = warp_sum(si);
     if (lane == 0) { sh.red[warp][0] = si; sh.red[warp][1] = di; }
@@ -162,6 +163,84 @@ __global__ void __launch_bounds__(kItemThreads, COFFE_ITEM_MIN_BLOCKS) integrate
         for (int w = 0; w < kItemWarps; ++w) { a += sh.red[w][0]; b += sh.red[w][1]; }
         out_si[item] = a;
         out_di[item] = b;
+    }
+}
+
+
+/* ---- integrated pieces, shared-memory tables: persistent CTAs, one warp per item ------------------
+   Every CTA copies the compact tables (compact.cuh) and the line-of-sight table into shared memory once,
+   then its warps draw items from a global counter until none are left.  A warp owns its item: lanes 0-2
+   fold the end-point amplitudes, all lanes stride over the (panel, node) pairs of the inner ridge rule
+   while the outer line-of-sight nodes are visited in order, so the result of an item does not depend on
+   which warp computed it (bit-reproducible for any grid size or GPU count). */
+struct WarpState {
+    EndVals e[2];
+    SIHalf h[2];
+    DIConst k;
+};
+
+constexpr int kSmemThreads = 384;
+
+__global__ void __launch_bounds__(kSmemThreads, 1) items_smem_kernel(
+    const __grid_constant__ Tables t, const __grid_constant__ Options o, const __grid_constant__ Rules q,
+    const __grid_constant__ CompactHeader ch, const uint4 *__restrict__ blob, const int stage_bytes,
+    const double *__restrict__ pz, const double *__restrict__ psep,
+    const int *__restrict__ item_point, const double *__restrict__ item_mu, const int n_items,
+    const int los_stage_n, const int panel_cap, double *__restrict__ out_si, double *__restrict__ out_di,
+    unsigned int *__restrict__ out_evals, unsigned int *__restrict__ counter)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int n_warps = kSmemThreads / 32;
+    /* layout: [compact blob prefix][line-of-sight table][per-warp state][per-warp panel lists] */
+    double4 *los_s = reinterpret_cast<double4 *>(smem + stage_bytes);
+    WarpState *ws_all = reinterpret_cast<WarpState *>(smem + stage_bytes + (size_t)los_stage_n * sizeof(double4));
+    double *scratch = reinterpret_cast<double *>(ws_all + n_warps) + (size_t)warp * 2 * panel_cap;
+    {
+        uint4 *dst = reinterpret_cast<uint4 *>(smem);
+        for (int i = tid; i < stage_bytes / 16; i += kSmemThreads) dst[i] = blob[i];
+        for (int i = tid; i < los_stage_n; i += kSmemThreads) los_s[i] = t.los.v[i];
+    }
+    __syncthreads();
+    WarpState &ws = ws_all[warp];
+    CompactAccess ta;
+    ta.t = &t; ta.c.base = smem; ta.c.h = ch;
+    LosView lv = t.los;
+    lv.v = los_s;
+    const bool has_si = opt_has_si(o), has_di = opt_has_integrated(o);
+
+    for (;;) {
+        unsigned int item = 0;
+        if (lane == 0) item = atomicAdd(counter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= (unsigned int)n_items) break;
+        const int p = item_point[item];
+        const double z = pz[p], sep = psep[p], mu = item_mu[item];
+        const Geometry g = geometry(bg_chi(t.bg, z), sep, mu);
+        if (lane < 2) ws.e[lane] = end_eval(o, t, lane == 0 ? g.chi1 : g.chi2, lane + 1);
+        __syncwarp();
+        if (lane < 2 && has_si) ws.h[lane] = si_half_setup(o, g, ws.e[lane], ws.e[1 - lane], lane == 0);
+        if (lane == 2 && has_di) ws.k = di_setup(o, ws.e[0], ws.e[1]);
+        __syncwarp();
+        if (out_evals && lane < 2)
+            out_evals[2 * item + lane] = lane == 0 ? (has_si ? si_eval_count(q, g, ws.h[0]) + si_eval_count(q, g, ws.h[1]) : 0u)
+                                                   : (has_di ? di_eval_count(q, g) : 0u);
+        double si = 0.0, di = 0.0;
+        if (has_si) {
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const SIHalf h = ws.h[half];
+                si += si_half_partial(ta, lv, q, g, h, los_s, lane, 32, scratch);
+            }
+        }
+        if (has_di) {
+            const DIConst k = ws.k;
+            di = di_partial(ta, lv, q, g, k, los_s, 0, 1, lane, 32, scratch);
+        }
+        si = warp_sum(si);
+        di = warp_sum(di);
+        if (lane == 0) { out_si[item] = si; out_di[item] = di; }
+        __syncwarp();
     }
 }
 
@@ -274,7 +353,7 @@ namespace {
 Rules make_rules(const coffe_b200_ctx *ctx)
 {
     Rules q;
-    q.gl_x = ctx->d_gl_x; q.gl_w = ctx->d_gl_w;
+    q.gl_x = ctx->d_gl_x; q.gl_w = ctx->d_gl_w; q.rpow = ctx->d_rpow;
     q.n_panel_si = ctx->qc.n_panel_si; q.n_panel_di = ctx->qc.n_panel_di;
     q.n_outer = ctx->qc.n_outer;
     q.panel_w_mpc = ctx->qc.panel_w; q.panel_du = ctx->qc.panel_du; q.eps_min = ctx->qc.eps_min; q.tail_ratio = ctx->qc.tail_ratio;
@@ -322,6 +401,30 @@ int launch_integrated(coffe_b200_ctx *ctx, Batch &b)
     }
     int stage_n = (int)std::ceil(b.chi_max / ctx->layout.los_h) + 4;
     if (stage_n > ctx->layout.los_n) stage_n = ctx->layout.los_n;
+    if (ctx->variant == 1 && ctx->compact.h.valid) {
+        /* shared-memory tables: blob prefix covering R <= 2 chi_max, line-of-sight table, per-warp state and panel lists */
+        const int panel_cap = max_panels(ctx->qc);
+        const int stage_bytes = compact_stage_bytes(ctx->compact, 2.0 * b.chi_max);
+        const size_t need = (size_t)stage_bytes + (size_t)stage_n * sizeof(double4)
+                            + (size_t)(kSmemThreads / 32) * (sizeof(WarpState) + (size_t)2 * panel_cap * sizeof(double));
+        if (need <= (size_t)ctx->smem_optin) {
+            CompactHeader ch = ctx->compact.h;
+            ch.n_knots = (stage_bytes - ch.off_knots) / (kKnotStride * 8);
+            CK(cudaFuncSetAttribute(items_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+            CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int), ctx->stream));
+            const int warps = kSmemThreads / 32;
+            int grid = std::min(ctx->n_sm, (b.n_items + warps - 1) / warps);
+            if (grid < 1) grid = 1;
+            items_smem_kernel<<<grid, kSmemThreads, need, ctx->stream>>>(
+                ctx->t, ctx->o, make_rules(ctx), ch, reinterpret_cast<const uint4 *>(ctx->d_blob), stage_bytes, b.pz.p, b.psep.p,
+                b.item_point.p, b.item_mu.p, b.n_items, stage_n, panel_cap, b.si.p, b.di.p, b.evals.p, ctx->d_counter);
+            CK(cudaGetLastError());
+            ctx->last_launches += 1;
+            ctx->last_variant = 1;
+            return COFFE_B200_OK;
+        }
+    }
+    ctx->last_variant = 0;
     size_t smem = (size_t)stage_n * sizeof(double4);
     if (smem > 160 * 1024) { stage_n = 0; smem = 0; }     /* read the table through L1/L2 instead */
     CK(cudaFuncSetAttribute(integrated_items_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -561,6 +664,17 @@ int coffe_b200_create(int device, coffe_b200_ctx **out)
     if ((e = cudaMemcpy(ctx->d_gl_x, bx.data(), bx.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return fail("cudaMemcpy", e);
     if ((e = cudaMemcpy(ctx->d_gl_w, bw.data(), bw.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return fail("cudaMemcpy", e);
     ctx->qc = default_quadrature();
+    {
+        const std::vector<double> rp = build_rpow(ctx->qc.tail_ratio);
+        if ((e = cudaMalloc(&ctx->d_rpow, kMaxTail * sizeof(double))) != cudaSuccess) return fail("cudaMalloc", e);
+        if ((e = cudaMemcpy(ctx->d_rpow, rp.data(), kMaxTail * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return fail("cudaMemcpy", e);
+        if ((e = cudaMalloc(&ctx->d_counter, sizeof(unsigned int))) != cudaSuccess) return fail("cudaMalloc", e);
+        int v = 0;
+        if ((e = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return fail("cudaDeviceGetAttribute", e);
+        ctx->n_sm = v;
+        if ((e = cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device)) != cudaSuccess) return fail("cudaDeviceGetAttribute", e);
+        ctx->smem_optin = v;
+    }
     std::memset(&ctx->o, 0, sizeof(ctx->o));
     ctx->o.den = 1;
     *out = ctx;
@@ -574,6 +688,9 @@ void coffe_b200_destroy(coffe_b200_ctx *ctx)
     if (ctx->d_arena) cudaFree(ctx->d_arena);
     if (ctx->d_gl_x) cudaFree(ctx->d_gl_x);
     if (ctx->d_gl_w) cudaFree(ctx->d_gl_w);
+    if (ctx->d_rpow) cudaFree(ctx->d_rpow);
+    if (ctx->d_counter) cudaFree(ctx->d_counter);
+    if (ctx->d_blob) cudaFree(ctx->d_blob);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -602,6 +719,17 @@ int coffe_b200_upload_tables(coffe_b200_ctx *ctx, const coffe_b200_tables *T)
     los_build_kernel<<<(L.los_n + 127) / 128, 128, 0, ctx->stream>>>(ctx->t, reinterpret_cast<double4 *>(ctx->d_arena + L.los), L.los_n, L.los_h,
                                                                      L.chi_max_table);
     CK(cudaGetLastError());
+    /* shared-memory tables of the integrated-pieces kernel (absent when the family is not log-spaced: exact-table kernel) */
+    if (ctx->d_blob) { cudaFree(ctx->d_blob); ctx->d_blob = nullptr; }
+    ctx->compact = CompactBuild();
+    if (L.has_ifam) {
+        std::string why;
+        if (build_compact(ctx->t_host, L, kCompactKnotBudget, kCompactTolerance, ctx->compact, why)) {
+            CK(cudaMalloc(&ctx->d_blob, ctx->compact.blob.size() * sizeof(double)));
+            CK(cudaMemcpyAsync(ctx->d_blob, ctx->compact.blob.data(), ctx->compact.blob.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        }
+        else ctx->compact.h.valid = 0;
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->omega_matter = T->omega_matter; ctx->h = T->h;
     ctx->o.Om = T->omega_matter;
@@ -634,7 +762,30 @@ int coffe_b200_set_quadrature(coffe_b200_ctx *ctx, const coffe_b200_quadrature *
         ctx->err = "quadrature sizes out of range (node counts 2..128; the line-of-sight panel plan must fit " + std::to_string(kMaxPanels) + " panels)";
         return COFFE_B200_EINVAL;
     }
+    if (merged.tail_ratio != ctx->qc.tail_ratio) {
+        const std::vector<double> rp = build_rpow(merged.tail_ratio);
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaMemcpy(ctx->d_rpow, rp.data(), kMaxTail * sizeof(double), cudaMemcpyHostToDevice));
+    }
     ctx->qc = merged;
+    return COFFE_B200_OK;
+}
+
+int coffe_b200_set_kernel_variant(coffe_b200_ctx *ctx, int variant)
+{
+    if (!ctx || (variant != 0 && variant != 1)) return COFFE_B200_EINVAL;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->variant = variant;
+    return COFFE_B200_OK;
+}
+
+int coffe_b200_table_info(const coffe_b200_ctx *ctx, int *variant_used, int *compact_knots, int *compact_bytes, double *compact_max_rel_error)
+{
+    if (!ctx) return COFFE_B200_EINVAL;
+    if (variant_used) *variant_used = ctx->last_variant;
+    if (compact_knots) *compact_knots = ctx->compact.h.valid ? ctx->compact.h.n_knots : 0;
+    if (compact_bytes) *compact_bytes = ctx->compact.h.valid ? ctx->compact.h.bytes : 0;
+    if (compact_max_rel_error) *compact_max_rel_error = ctx->compact.h.valid ? ctx->compact.h.max_rel_error : 0.0;
     return COFFE_B200_OK;
 }
 

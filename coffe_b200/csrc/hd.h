@@ -19,6 +19,8 @@
 #define COFFE_HD inline
 #define COFFE_D inline
 #include <cmath>
+#include <cstring>
+struct alignas(8) int2 { int x, y; };
 struct alignas(16) double2 { double x, y; };
 struct alignas(16) double4 { double x, y, z, w; };
 #endif

@@ -13,6 +13,7 @@ namespace coffe {
 
 struct Rules {
     const double *gl_x, *gl_w;      /* bank of Gauss-Legendre rules on [0,1] (quadrature.cuh: rule_offset) */
+    const double *rpow;             /* tail_ratio^n, n < kMaxTail */
     int n_panel_si, n_panel_di;
     int n_outer;                    /* 0 = auto_n_outer(sep) */
     double panel_w_mpc, panel_du, eps_min, tail_ratio;
@@ -31,7 +32,7 @@ COFFE_HD double ridge_integrate(const F &f, const double hi, const double center
                                 const Rules &q, const int n_panel, const int lane, const int nlanes, double *scratch)
 {
     const double *panel_x = q.gl_x + rule_offset(n_panel), *panel_w = q.gl_w + rule_offset(n_panel);
-    const PanelPlan plan = panel_plan(eps, q.eps_min, q.panel_w_mpc, q.panel_du, q.tail_ratio);
+    const PanelPlan plan = panel_plan(eps, q.eps_min, q.panel_w_mpc, q.panel_du, q.tail_ratio, q.rpow);
     /* negative side: |d| in [a_neg, b_neg]; positive side: |d| in [0, b_pos] (center >= 0 always) */
     const double b_neg = center;
     const double a_neg = center > hi ? center - hi : 0.0;
@@ -80,7 +81,7 @@ COFFE_HD double ridge_integrate(const F &f, const double hi, const double center
    the index arithmetic but no evaluation, so they are not counted) */
 COFFE_HD unsigned int ridge_eval_count(const double hi, const double center, const double eps, const Rules &q, const int n_panel)
 {
-    const PanelPlan plan = panel_plan(eps, q.eps_min, q.panel_w_mpc, q.panel_du, q.tail_ratio);
+    const PanelPlan plan = panel_plan(eps, q.eps_min, q.panel_w_mpc, q.panel_du, q.tail_ratio, q.rpow);
     const double b_neg = center, a_neg = center > hi ? center - hi : 0.0, b_pos = hi - center;
     const int k_neg = panel_count(plan, b_neg);
     const int k_pos = b_pos > 0.0 ? panel_count(plan, b_pos) : 0;
@@ -97,8 +98,9 @@ COFFE_HD unsigned int ridge_eval_count(const double hi, const double center, con
     return n;
 }
 
+template <class TA>
 struct SIFunctor {
-    const Tables *t; const SIHalf *h; const Geometry *g; const double4 *los; int los_n; double los_inv_h;
+    const TA *t; const SIHalf *h; const Geometry *g; const double4 *los; int los_n; double los_inv_h;
     COFFE_HD double operator()(const double lambda) const
     {
         return si_half_eval(*t, *h, *g, lambda, los_eval(los, los_n, los_inv_h, lambda));
@@ -106,10 +108,11 @@ struct SIFunctor {
 };
 
 /* one half of the local x integrated piece, per unit x (the reference integrates x in [0,1], src/signal.c:584-606) */
-COFFE_HD double si_half_partial(const Tables &t, const Rules &q, const Geometry &g, const SIHalf &h,
+template <class TA>
+COFFE_HD double si_half_partial(const TA &t, const LosView &lv, const Rules &q, const Geometry &g, const SIHalf &h,
                                 const double4 *los, const int lane, const int nlanes, double *scratch)
 {
-    SIFunctor f{&t, &h, &g, los, t.los.n, t.los.inv_h};
+    SIFunctor<TA> f{&t, &h, &g, los, lv.n, lv.inv_h};
     const double center = h.cs * g.c;
     const double eps = h.cs * sqrt(g.s2);
     return ridge_integrate(f, h.co, center, eps, q, q.n_panel_si, lane, nlanes, scratch) / h.co;
@@ -120,8 +123,9 @@ COFFE_HD unsigned int si_eval_count(const Rules &q, const Geometry &g, const SIH
     return ridge_eval_count(h.co, h.cs * g.c, h.cs * sqrt(g.s2), q, q.n_panel_si);
 }
 
+template <class TA>
 struct DIFunctor {
-    const Tables *t; const DIConst *k; const Geometry *g; const double4 *los; int los_n; double los_inv_h;
+    const TA *t; const DIConst *k; const Geometry *g; const double4 *los; int los_n; double los_inv_h;
     double l1; double4 los1;
     COFFE_HD double operator()(const double l2) const
     {
@@ -131,7 +135,8 @@ struct DIFunctor {
 
 /* integrated x integrated piece per unit (x1, x2): outer nodes strided over `ngroups` groups of
    `nlanes` lanes (warps of a CTA on the device) */
-COFFE_HD double di_partial(const Tables &t, const Rules &q, const Geometry &g, const DIConst &k, const double4 *los,
+template <class TA>
+COFFE_HD double di_partial(const TA &t, const LosView &lv, const Rules &q, const Geometry &g, const DIConst &k, const double4 *los,
                            const int group, const int ngroups, const int lane, const int nlanes, double *scratch)
 {
     double acc = 0.0;
@@ -140,7 +145,7 @@ COFFE_HD double di_partial(const Tables &t, const Rules &q, const Geometry &g, c
     const double *outer_x = q.gl_x + rule_offset(n_outer), *outer_w = q.gl_w + rule_offset(n_outer);
     for (int io = group; io < n_outer; io += ngroups) {
         const double l1 = g.chi1 * outer_x[io];
-        DIFunctor f{&t, &k, &g, los, t.los.n, t.los.inv_h, l1, los_eval(los, t.los.n, t.los.inv_h, l1)};
+        DIFunctor<TA> f{&t, &k, &g, los, lv.n, lv.inv_h, l1, los_eval(los, lv.n, lv.inv_h, l1)};
         acc += outer_w[io] * ridge_integrate(f, g.chi2, l1 * g.c, l1 * sth, q, q.n_panel_di, lane, nlanes, scratch);
     }
     return acc / g.chi2;

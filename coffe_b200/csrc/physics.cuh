@@ -19,7 +19,7 @@
 // (functions.c:3930-3959), rsd-len switches its I^0_4 bracket at |mu| >= 0.999 (functions.c:2199),
 // len-len falls back to 4 + 24 l1 l2 I^1_1(0)/15 for r^2 <= 1e-20 (functions.c:3814-3833).
 #pragma once
-#include "tables.cuh"
+#include "compact.cuh"
 
 namespace coffe {
 
@@ -96,29 +96,6 @@ struct SepConst {
     /* mean-redshift values (flat-sky branches and the final growth factor) */
     double z_mean, chi_mean, fm, Hm, bm1, bm2, Gm1, Gm2, D1m, sm1, sm2;
 };
-
-COFFE_HD void ifam_eval_all(const IntegralFamilyView &t, const double r, double out[N_ITAB])
-{
-    /* speculative single round trip: knots and the interleaved record of the guessed interval are loaded
-       together; the (rare) wrong guess reloads */
-    int i = ifam_guess(t, r);
-    double xi = t.x[i];
-    const double xn = t.x[i + 1];
-    const double4 *k = t.k + (size_t)i * N_ITAB;
-    double4 c[N_ITAB];
-#pragma unroll
-    for (int j = 0; j < N_ITAB; ++j) c[j] = k[j];
-    if (!(r >= xi && (r < xn || i == t.n - 2))) {
-        i = ifam_index(t, r);
-        xi = t.x[i];
-        k = t.k + (size_t)i * N_ITAB;
-#pragma unroll
-        for (int j = 0; j < N_ITAB; ++j) c[j] = k[j];
-    }
-    const double dx = r - xi;
-#pragma unroll
-    for (int j = 0; j < N_ITAB; ++j) out[j] = cubic_eval(c[j], dx);
-}
 
 COFFE_HD SepConst sep_const(const Options &o, const Tables &t, const double z_mean, const double sep)
 {
@@ -309,7 +286,8 @@ COFFE_HD SIHalf si_half_setup(const Options &o, const Geometry &g, const EndVals
 
 /* integrand of one half at lambda (distance along the integrated line of sight), per unit x = lambda/co.
    los = {W, V, U, Wa}(lambda). */
-COFFE_HD double si_half_eval(const Tables &t, const SIHalf &h, const Geometry &g, const double lambda, const double4 los)
+template <class TA>
+COFFE_HD double si_half_eval(const TA &t, const SIHalf &h, const Geometry &g, const double lambda, const double4 los)
 {
     const double c = g.c, c2 = c * c, s2 = g.s2;
     const double cs = h.cs, l = lambda;
@@ -320,7 +298,7 @@ COFFE_HD double si_half_eval(const Tables &t, const SIHalf &h, const Geometry &g
     const double iR = rr > 0.0 ? COFFE_RSQRT(rr) : 0.0;
     const double R = rr * iR;
     double I[N_ITAB];
-    ifam_eval_all(t.ifam, R, I);
+    t.ifam_all(R, I);
     const double W = los.x, V = los.y, Wa = los.w;
     double res = 0.0;
     if (h.any_lens) {
@@ -368,7 +346,7 @@ COFFE_HD double si_half_eval(const Tables &t, const SIHalf &h, const Geometry &g
     if (h.any_g4 || h.any_g5) {
         double ren = 0.0;
         if (h.need_ren)                                                                             /* :1524-1556 */
-            ren = (rr == 0.0) ? spline_eval(t.ren0, l) : hspline_eval(t.i40, R) - renorm2d_eval(t.ren2d, l, cs);
+            ren = (rr == 0.0) ? t.ren0(l) : t.i40(R) - t.ren2d(l, cs);
         const double b_rsd = (2 * rr / 3. - s2 * l * l) * I[I22] - I[I20] / 3.;
         const double b_d1 = (l * c - cs) * I[I31];
         if (h.any_g4) res += W * (h.g4_i20 * I[I20] + h.g4_rsd * b_rsd + h.g4_d1 * b_d1 + h.g4_ren * ren);
@@ -417,7 +395,8 @@ COFFE_HD DIConst di_setup(const Options &o, const EndVals &e1, const EndVals &e2
 }
 
 /* integrand per unit (x1, x2) = (l1/chi1, l2/chi2); los_i = {W, V, U, Wa}(l_i) */
-COFFE_HD double di_eval(const Tables &t, const DIConst &k, const Geometry &g, const double l1, const double l2,
+template <class TA>
+COFFE_HD double di_eval(const TA &t, const DIConst &k, const Geometry &g, const double l1, const double l2,
                         const double4 los1, const double4 los2)
 {
     const double c = g.c, c2 = c * c;
@@ -427,7 +406,7 @@ COFFE_HD double di_eval(const Tables &t, const DIConst &k, const Geometry &g, co
     const double ir = r2 > 0.0 ? COFFE_RSQRT(r2) : 0.0;     /* 1/R: one reciprocal square root serves R, 1/r^2, 1/r^4 */
     const double R = r2 * ir;
     double I[N_ITAB];
-    ifam_eval_all(t.ifam, R, I);
+    t.ifam_all(R, I);
     const double ll = l1 * l2;
     const double WW = los1.x * los2.x;
     const double e1 = g.chi1 - l1, e2 = g.chi2 - l2;    /* chi_i (1 - x_i) */
@@ -454,7 +433,7 @@ COFFE_HD double di_eval(const Tables &t, const DIConst &k, const Geometry &g, co
         res += WW * br * (k.k_4l * (w2 + w1) + k.k_5la * los1.z * w2 + k.k_5lb * los2.z * w1);
     }
     if (k.any_ren) {
-        const double ren = (r2 <= 1e-12) ? spline_eval(t.ren0, l1) : hspline_eval(t.i40, R) - renorm2d_eval(t.ren2d, l1, l2);
+        const double ren = (r2 <= 1e-12) ? t.ren0(l1) : t.i40(R) - t.ren2d(l1, l2);
         res += WW * ren * (k.k_44 + k.k_55 * los1.y * los2.y + k.k_45a * los2.y + k.k_45b * los1.y);
     }
     return res * k.h4;

@@ -18,16 +18,21 @@
 
 namespace coffe {
 
+/* powers of the tail ratio, rpow[n] = ratio^n for n < kMaxTail (built on the host with the rule bank) */
+static const int kMaxTail = 48;
+
 struct PanelPlan {
+    const double *rpow;
     double eps, W, ratio;
     int J;          /* B_k = eps 2^(k-1) for 1 <= k <= J */
     int M;          /* B_k = B_J + (k-J) W for J < k <= J+M */
     double BJ, BJM;
 };
 
-COFFE_HD PanelPlan panel_plan(double eps, const double eps_min, const double W, const double Du, const double ratio)
+COFFE_HD PanelPlan panel_plan(double eps, const double eps_min, const double W, const double Du, const double ratio, const double *rpow)
 {
     PanelPlan p;
+    p.rpow = rpow;
     if (eps < eps_min) eps = eps_min;
     p.eps = eps; p.W = W; p.ratio = ratio;
     int J = 0;
@@ -48,7 +53,8 @@ COFFE_HD double panel_break(const PanelPlan &p, const int k)
     if (k <= 0) return 0.0;
     if (k <= p.J) return ldexp(p.eps, k - 1);
     if (k <= p.J + p.M) return p.BJ + (k - p.J) * p.W;
-    return p.BJM * pow(p.ratio, (double)(k - p.J - p.M));
+    const int n = k - p.J - p.M;
+    return p.BJM * p.rpow[n < kMaxTail ? n : kMaxTail - 1];
 }
 
 /* number of panels needed to cover [0, b] */
@@ -58,10 +64,8 @@ COFFE_HD int panel_count(const PanelPlan &p, const double b)
     int k = 1;
     if (b > p.BJM) {
         k = p.J + p.M;
-        int n = (int)ceil(log(b / p.BJM) / log(p.ratio));
-        if (n < 1) n = 1;
-        /* guard the rounding of the logarithm so that B_(k+n) >= b */
-        if (p.BJM * pow(p.ratio, (double)n) < b) ++n;
+        int n = 1;
+        while (n < kMaxTail - 1 && p.BJM * p.rpow[n] < b) ++n;      /* smallest n with B_(k+n) >= b */
         return k + n;
     }
     if (b > p.BJ || p.J == 0) return p.J + (int)ceil((b - p.BJ) / p.W);

@@ -52,6 +52,7 @@ inline int max_panels(const QuadConfig &q, const double extent = 2.0e4)
     const int uni = (int)std::ceil(q.panel_du / q.panel_w) + 1;
     const double start = std::max(q.panel_du, q.panel_w);
     const int tail = extent > start ? (int)std::ceil(std::log(extent / start) / std::log(q.tail_ratio)) + 2 : 0;
+    if (tail >= kMaxTail) return 1 << 30;
     return 2 * (geo + uni + tail);
 }
 
@@ -77,6 +78,13 @@ inline void build_rule_bank(std::vector<double> &bx, std::vector<double> &bw)
         std::copy(x.begin(), x.end(), bx.begin() + rule_offset(n));
         std::copy(w.begin(), w.end(), bw.begin() + rule_offset(n));
     }
+}
+
+inline std::vector<double> build_rpow(const double ratio)
+{
+    std::vector<double> v(kMaxTail);
+    for (int n = 0; n < kMaxTail; ++n) v[n] = std::pow(ratio, (double)n);
+    return v;
 }
 
 /* mu rule of the integrated pieces for one separation: the integrands are functions of the transverse

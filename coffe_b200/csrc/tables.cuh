@@ -167,6 +167,29 @@ COFFE_HD int ifam_index(const IntegralFamilyView &t, const double r)
     return i;
 }
 
+COFFE_HD void ifam_eval_all(const IntegralFamilyView &t, const double r, double out[N_ITAB])
+{
+    /* speculative single round trip: knots and the interleaved record of the guessed interval are loaded
+       together; the (rare) wrong guess reloads */
+    int i = ifam_guess(t, r);
+    double xi = t.x[i];
+    const double xn = t.x[i + 1];
+    const double4 *k = t.k + (size_t)i * N_ITAB;
+    double4 c[N_ITAB];
+#pragma unroll
+    for (int j = 0; j < N_ITAB; ++j) c[j] = k[j];
+    if (!(r >= xi && (r < xn || i == t.n - 2))) {
+        i = ifam_index(t, r);
+        xi = t.x[i];
+        k = t.k + (size_t)i * N_ITAB;
+#pragma unroll
+        for (int j = 0; j < N_ITAB; ++j) c[j] = k[j];
+    }
+    const double dx = r - xi;
+#pragma unroll
+    for (int j = 0; j < N_ITAB; ++j) out[j] = cubic_eval(c[j], dx);
+}
+
 /* ---- renormalisation(chi1, chi2), bicubic ---------------------------------------------------- */
 struct Renorm2DView {
     const double *x;        /* n knots (same on both axes) */

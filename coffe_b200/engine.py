@@ -60,6 +60,16 @@ class Engine:
         self._check(self.lib.coffe_b200_get_quadrature(self._h, C.byref(q)))
         return {name: getattr(q, name) for name, _ in q._fields_}
 
+    def set_kernel_variant(self, variant):
+        """1 = shared-memory (resampled) I^n_l tables, the default; 0 = exact tables through L1/L2"""
+        self._check(self.lib.coffe_b200_set_kernel_variant(self._h, C.c_int(variant)))
+
+    def table_info(self):
+        """(variant the last call ran, knots / bytes / achieved max relative error of the shared-memory tables)"""
+        v, k, b, err = C.c_int(), C.c_int(), C.c_int(), C.c_double()
+        self._check(self.lib.coffe_b200_table_info(self._h, C.byref(v), C.byref(k), C.byref(b), C.byref(err)))
+        return v.value, k.value, b.value, err.value
+
     def last_timing(self):
         ms, n = C.c_double(), C.c_int()
         self._check(self.lib.coffe_b200_last_timing(self._h, C.byref(ms), C.byref(n)))

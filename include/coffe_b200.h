@@ -114,6 +114,14 @@ int coffe_b200_set_options(coffe_b200_ctx *ctx, const coffe_b200_options *opt);
 int coffe_b200_set_quadrature(coffe_b200_ctx *ctx, const coffe_b200_quadrature *q);
 int coffe_b200_get_quadrature(const coffe_b200_ctx *ctx, coffe_b200_quadrature *q);
 
+/* The line-of-sight kernel reads the I^n_l family either from tables resampled into shared memory
+   (variant 1, default; resampling error reported by coffe_b200_table_info) or from the
+   exact per-interval cubics of the uploaded knots through L1/L2 (variant 0; cross-check). */
+int coffe_b200_set_kernel_variant(coffe_b200_ctx *ctx, int variant);
+/* variant the last compute call ran, and size / achieved resampling error of the shared-memory tables */
+int coffe_b200_table_info(const coffe_b200_ctx *ctx, int *variant_used, int *compact_knots, int *compact_bytes,
+                          double *compact_max_rel_error);
+
 /* ---- signal -------------------------------------------------------------------------------------- */
 /* out[(iz*n_l + il)*n_sep + ir]   (order of src/multipoles.c:75-86) */
 int coffe_b200_multipoles(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double *sep, int n_sep,

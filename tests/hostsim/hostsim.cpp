@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../coffe_b200/csrc/assemble.h"
+#include "../../coffe_b200/csrc/compact_build.h"
 #include "../../coffe_b200/csrc/item.cuh"
 #include "../../coffe_b200/csrc/rules_build.h"
 
@@ -21,16 +22,20 @@ struct HostSim {
     Tables t;
     Options o;
     QuadConfig qc;
-    std::vector<double> bx, bw;
+    std::vector<double> bx, bw, rpow;
     Rules q;
     std::string err;
+    CompactBuild cb;
+    int variant = 0;        /* 0 = exact tables, 1 = compact (shared-memory) tables */
+    CompactAccess compact() const { return CompactAccess{&t, CompactView{reinterpret_cast<const unsigned char *>(cb.blob.data()), cb.h}}; }
 };
 
 static void set_rules(HostSim *s)
 {
     if (s->bx.empty()) build_rule_bank(s->bx, s->bw);
     Rules &q = s->q;
-    q.gl_x = s->bx.data(); q.gl_w = s->bw.data();
+    s->rpow = build_rpow(s->qc.tail_ratio);
+    q.gl_x = s->bx.data(); q.gl_w = s->bw.data(); q.rpow = s->rpow.data();
     q.n_panel_si = s->qc.n_panel_si; q.n_panel_di = s->qc.n_panel_di; q.n_outer = s->qc.n_outer;
     q.panel_w_mpc = s->qc.panel_w; q.panel_du = s->qc.panel_du; q.eps_min = s->qc.eps_min; q.tail_ratio = s->qc.tail_ratio;
 }
@@ -64,6 +69,30 @@ void *hs_create(const coffe_b200_tables *T, const coffe_b200_options *opt)
 
 void hs_destroy(void *h) { delete (HostSim *)h; }
 
+/* builds the compact tables (knot budget, tolerance) and selects them; returns the number of knots (< 0: failed).
+   info[0] = achieved max relative error, info[1] = blob bytes, info[2..] = subdivisions m per region (up to n_info-2) */
+int hs_use_compact(void *h, int knot_budget, double tol, double *info, int n_info)
+{
+    HostSim *s = (HostSim *)h;
+    if (knot_budget == 0) { s->variant = 0; return 0; }
+    if (knot_budget < 0) { knot_budget = kCompactKnotBudget; tol = kCompactTolerance; }      /* the library's defaults */
+    if (!build_compact(s->t, s->layout, knot_budget, tol, s->cb, s->err)) { fprintf(stderr, "hostsim: %s\n", s->err.c_str()); return -1; }
+    s->variant = 1;
+    if (info && n_info >= 2) {
+        info[0] = s->cb.h.max_rel_error; info[1] = s->cb.h.bytes;
+        for (int i = 0; i + 2 < n_info && i < (int)s->cb.region_m.size(); ++i) info[i + 2] = s->cb.region_m[i];
+    }
+    return s->cb.h.n_knots;
+}
+
+/* the eight I^n_l and I^4_0 at r through the selected tables: out[0..7], out[8] */
+void hs_tables_at(void *h, double r, double *out)
+{
+    HostSim *s = (HostSim *)h;
+    if (s->variant) { const CompactAccess ca = s->compact(); ca.ifam_all(r, out); out[8] = s->layout.has_divergent ? ca.i40(r) : 0.0; }
+    else { const ExactAccess ea{&s->t}; ea.ifam_all(r, out); out[8] = s->layout.has_divergent ? ea.i40(r) : 0.0; }
+}
+
 void hs_set_quadrature(void *h, const coffe_b200_quadrature *u)
 {
     HostSim *s = (HostSim *)h;
@@ -92,7 +121,9 @@ double hs_si(void *h, double z, double mu, double sep, double x, int exact)
     const double la = g.chi2 * x, lb = g.chi1 * x;
     const double4 losa = exact ? los_point(s->t, la) : los_eval(s->t.los.v, s->t.los.n, s->t.los.inv_h, la);
     const double4 losb = exact ? los_point(s->t, lb) : los_eval(s->t.los.v, s->t.los.n, s->t.los.inv_h, lb);
-    return si_half_eval(s->t, ha, g, la, losa) + si_half_eval(s->t, hb, g, lb, losb);
+    if (s->variant) { const CompactAccess ca = s->compact(); return si_half_eval(ca, ha, g, la, losa) + si_half_eval(ca, hb, g, lb, losb); }
+    const ExactAccess ea{&s->t};
+    return si_half_eval(ea, ha, g, la, losa) + si_half_eval(ea, hb, g, lb, losb);
 }
 
 double hs_di(void *h, double z, double mu, double sep, double x1, double x2, int exact)
@@ -105,7 +136,8 @@ double hs_di(void *h, double z, double mu, double sep, double x1, double x2, int
     const double l1 = g.chi1 * x1, l2 = g.chi2 * x2;
     const double4 los1 = exact ? los_point(s->t, l1) : los_eval(s->t.los.v, s->t.los.n, s->t.los.inv_h, l1);
     const double4 los2 = exact ? los_point(s->t, l2) : los_eval(s->t.los.v, s->t.los.n, s->t.los.inv_h, l2);
-    return di_eval(s->t, k, g, l1, l2, los1, los2);
+    if (s->variant) return di_eval(s->compact(), k, g, l1, l2, los1, los2);
+    return di_eval(ExactAccess{&s->t}, k, g, l1, l2, los1, los2);
 }
 
 /* the three pieces at one (z, sep, mu) with the fixed-node rules: out[0..2] = NI, SI, DI */
@@ -121,12 +153,14 @@ void hs_item(void *h, double z, double sep, double mu, double *out)
     if (opt_has_si(o)) {
         const SIHalf ha = si_half_setup(o, g, e1, e2, true), hb = si_half_setup(o, g, e2, e1, false);
         double scratch[2 * kMaxPanels];
-        out[1] = si_half_partial(s->t, s->q, g, ha, s->t.los.v, 0, 1, scratch) + si_half_partial(s->t, s->q, g, hb, s->t.los.v, 0, 1, scratch);
+        if (s->variant) { const CompactAccess ca = s->compact(); out[1] = si_half_partial(ca, s->t.los, s->q, g, ha, s->t.los.v, 0, 1, scratch) + si_half_partial(ca, s->t.los, s->q, g, hb, s->t.los.v, 0, 1, scratch); }
+        else { const ExactAccess ea{&s->t}; out[1] = si_half_partial(ea, s->t.los, s->q, g, ha, s->t.los.v, 0, 1, scratch) + si_half_partial(ea, s->t.los, s->q, g, hb, s->t.los.v, 0, 1, scratch); }
     }
     if (opt_has_integrated(o)) {
         const DIConst k = di_setup(o, e1, e2);
         double scratch[2 * kMaxPanels];
-        out[2] = di_partial(s->t, s->q, g, k, s->t.los.v, 0, 1, 0, 1, scratch);
+        if (s->variant) out[2] = di_partial(s->compact(), s->t.los, s->q, g, k, s->t.los.v, 0, 1, 0, 1, scratch);
+        else out[2] = di_partial(ExactAccess{&s->t}, s->t.los, s->q, g, k, s->t.los.v, 0, 1, 0, 1, scratch);
     }
 }
 

@@ -15,7 +15,7 @@ def available():
 
 
 class HostSim:
-    def __init__(self, ref, contributions, tableset=None, **flags):
+    def __init__(self, ref, contributions, tableset=None, compact=True, **flags):
         self.lib = C.CDLL(str(LIB))
         self.lib.hs_create.restype = C.c_void_p
         for f in ("hs_ni", "hs_si", "hs_di"):
@@ -24,6 +24,25 @@ class HostSim:
         o = capi.make_options(contributions, **flags)
         self.h = C.c_void_p(self.lib.hs_create(C.byref(self.ts.struct), C.byref(o)))
         assert self.h.value, "hostsim: table assembly failed"
+        self.lib.hs_use_compact.restype = C.c_int
+        self.compact_info = None
+        if compact:
+            self.use_compact()
+
+    def use_compact(self, knot_budget=-1, tol=0.0):
+        """select the shared-memory (resampled) I^n_l tables, library defaults unless given; 0 = exact tables.
+        Returns (knots, achieved max relative error, blob bytes, subdivisions m per region)"""
+        info = np.zeros(130)
+        n = self.lib.hs_use_compact(self.h, C.c_int(knot_budget), C.c_double(tol), capi.ptr(info), C.c_int(len(info)))
+        assert n >= 0, "hostsim: compact table construction failed"
+        self.compact_info = (n, info[0], int(info[1]), info[2:].astype(int))
+        return self.compact_info
+
+    def tables_at(self, r):
+        """the eight I^n_l and I^4_0 at r through the selected tables"""
+        out = np.zeros(9)
+        self.lib.hs_tables_at(self.h, C.c_double(r), capi.ptr(out))
+        return out
 
     def __del__(self):
         try:

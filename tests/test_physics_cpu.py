@@ -21,7 +21,7 @@ def _rel(a, b):
 
 def _check_terms(ref, tableset, contrib, rng):
     ref.set_contributions(contrib)
-    hs = hostsim_bridge.HostSim(ref, contrib, tableset=tableset)
+    hs = hostsim_bridge.HostSim(ref, contrib, tableset=tableset, compact=False)      # exact tables: this checks the transcription
     worst = [0.0, 0.0, 0.0]
     for (z, s, mu) in POINTS[::3]:
         a = float(ref.f_nonintegrated(z, mu, s))
@@ -145,3 +145,27 @@ def test_flatsky_closed_forms_match_reference_and_golden(ref, golden):
         ref.set_flags({})
         ref.set_contributions(list(ALL))
         ref.set_sep(np.array([10.0, 20.0, 40.0, 100.0, 150.0]) / H); ref.set_z_mean([0.5, 1.0, 1.5, 2.0]); ref.set_deltaz([0.3] * 4)
+
+
+def test_shared_memory_tables_resampling_budget(ref, tableset):
+    """the I^n_l family resampled for shared memory (compact.cuh) against the exact Akima tables: pointwise, and
+    through complete (z, r, mu) work items.  This is the resampling part of the 1e-5 tolerance budget."""
+    ref.set_contributions(list(ALL))
+    hs = hostsim_bridge.HostSim(ref, list(ALL), tableset=tableset, compact=False)
+    rr = np.concatenate([[0.0, 1e-7, 3e-6, 0.0015, 0.0123, 0.13, 0.99], np.geomspace(1.0, 1.2e4, 3001)])
+    exact = np.array([hs.tables_at(r) for r in rr])
+    items = [(1.0, 30.0, 0.3), (1.0, 14.9, 0.9995), (0.5, 150.0, 0.0), (2.0, 300.0, -0.7), (1.5, 224.0, 0.97), (0.7, 60.0, 0.99)]
+    want = [hs.item(*it) for it in items]
+    knots, err, nbytes, m = hs.use_compact()
+    assert 200 < knots <= 800 and nbytes < 160 * 1024, (knots, nbytes)
+    assert err < 1e-5, err                     # relative to the importance-floored envelope (compact_build.h)
+    got = np.array([hs.tables_at(r) for r in rr])
+    # below r_lo = 1 Mpc and for I^4_0 the shared-memory records are the reference's own cubics
+    assert np.array_equal(got[:7], exact[:7]) and np.array_equal(got[:, 8], exact[:, 8])
+    # weight of a function in a line-of-sight integral is r |f|: errors in units of its maximum
+    for j in range(8):
+        G = np.max(rr * np.abs(exact[:, j]))
+        assert np.max(rr * np.abs(got[:, j] - exact[:, j])) / G < 2e-5, j
+    for it, a in zip(items, want):
+        b = hs.item(*it)
+        assert np.all(np.abs(a - b) < 1e-7 * abs(a.sum())), (it, (a - b) / a.sum())
