@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--nsep", type=int, default=1000)
     ap.add_argument("--sample-points", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", type=int, default=-1, help="items kernel variant (experiments; default = library default)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -172,6 +173,8 @@ def main():
     eng = coffe_b200.Engine(local)
     eng.upload_tables(load_default_tableset())
     eng.set_options(ALL)
+    if args.variant >= 0:
+        eng.set_kernel_variant(args.variant)
 
     n_items = len(z) * len(sep)
     per = (n_items + world - 1) // world
