@@ -176,9 +176,9 @@ def main():
     if args.variant >= 0:
         eng.set_kernel_variant(args.variant)
 
+    from coffe_b200 import sharding
     n_items = len(z) * len(sep)
-    per = (n_items + world - 1) // world
-    begin, end = min(rank * per, n_items), min((rank + 1) * per, n_items)
+    begin, end = sharding.block_partition(n_items, world, rank)
     n_pts_total = n_items * len(ls)
 
     def barrier():
@@ -211,15 +211,7 @@ def main():
     n_work, n_ni, n_si, n_di, launches = cnt.tolist()
 
     # one gather of the result slices (NCCL over NVLink); checks the sharded result is complete
-    if world > 1:
-        pad = torch.zeros((len(ls), per), dtype=torch.float64, device="cuda")
-        pad[:, :end - begin] = torch.from_numpy(res_local).cuda()
-        parts = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
-        dist.gather(pad, parts, dst=0)
-        if rank == 0:
-            full = torch.cat(parts, dim=1)[:, :n_items].cpu().numpy()
-    else:
-        full = res_local
+    full = sharding.gather_ranges(res_local, n_items, dist, device="cuda") if world > 1 else res_local
     plan.close()
 
     # ---- end-to-end arm: the C ABI call with host buffers ---------------------------------------------
