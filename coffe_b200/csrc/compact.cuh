@@ -14,8 +14,10 @@
 //     tolerance within a knot budget.  The interval index, the left knot and 1/h come straight from the
 //     bits of R -- no logarithm, no knot array, no fix-up loop.  All eight functions of a knot are
 //     interleaved (128 B + 16 B padding so that lanes on different knots fall on different banks);
-//   * I^4_0: the reference's 297 hand-picked knots (src/integrals.c:76-96), exact cubics, bucket table on
-//     exponent + 5 mantissa bits.
+//   * I^4_0: resampled onto the same binary grid as the ninth function of a knot (what the integrated x
+//     integrated kernel reads); the reference's 297 hand-picked knots (src/integrals.c:76-96) are kept as
+//     exact cubics behind a bucket table on exponent + 5 mantissa bits for R < r_lo and for the
+//     local x integrated piece.
 // The resampling error is part of the tolerance budget; the exact-table kernel stays
 // available (coffe_b200_set_kernel_variant) and the tests compare the two.
 #pragma once
@@ -23,7 +25,10 @@
 
 namespace coffe {
 
-static const int kKnotStride = 18;      /* doubles per compact knot: 8 x {f, h f'} + 2 padding */
+static const int kKnotStride = 18;      /* doubles per compact knot: 9 x {f, h f'}: the eight I^n_l of the family, then I^4_0
+                                           (zero without the divergent tables); 144 B, so lanes on neighbouring knots
+                                           fall on different 16-byte bank groups */
+static const int N_ITAB9 = N_ITAB + 1;
 static const int kSmallStride = 34;     /* doubles per small-r interval: 8 x double4 + 2 padding */
 
 /* byte offsets are relative to the start of the blob and multiples of 16 */
@@ -39,7 +44,8 @@ struct CompactHeader {
     int off_i40hint, n_i40hint, i40hint0;
     int off_i40x, off_i40k, i40n;
     double r_lo;               /* 2^e_min: first knot of the binary grid */
-    double max_rel_error;      /* achieved resampling error of the builder (relative to the local envelope) */
+    double max_rel_error;      /* achieved resampling error of the builder (relative to the local envelope), I^n_l family */
+    double max_rel_error_i40;  /* the same for I^4_0 */
     int valid;
 };
 
@@ -97,6 +103,39 @@ COFFE_HD void compact_ifam_all(const CompactView &c, const double r, double out[
     }
 }
 
+COFFE_HD double compact_i40(const CompactView &c, const double r);
+
+/* the eight I^n_l and (when want_i40) I^4_0 at r: one index computation, one Hermite basis, 2 x 9 16-byte loads */
+COFFE_HD void compact_ifam9(const CompactView &c, const double r, double out[N_ITAB9], const bool want_i40)
+{
+    const int hi = hi_word(r);
+    int reg = (hi >> 18) - c.h.region0;
+    if (reg < 0) {
+        compact_ifam_all(c, r, out);
+        out[N_ITAB] = want_i40 ? compact_i40(c, r) : 0.0;
+        return;
+    }
+    if (reg > c.h.n_region - 1) reg = c.h.n_region - 1;
+    const int2 rg = reinterpret_cast<const int2 *>(c.base + c.h.off_region)[reg];
+    int idx = rg.x + ((hi & 0x3FFFF) >> rg.y);
+    if (idx > c.h.n_knots - 2) idx = c.h.n_knots - 2;
+    const double xj = from_hi_word(hi & (int)(~0u << rg.y));
+    const double inv_h = from_hi_word((2046 + 20 - rg.y - (hi >> 20)) << 20);
+    const HermiteBasis hb = hermite_basis((r - xj) * inv_h);
+    const double2 *k0 = reinterpret_cast<const double2 *>(c.base + c.h.off_knots + (size_t)idx * kKnotStride * 8);
+    const double2 *k1 = k0 + kKnotStride / 2;
+#pragma unroll
+    for (int t = 0; t < N_ITAB; ++t) {
+        const double2 a = k0[t], b = k1[t];
+        out[t] = hermite_eval(hb, a.x, a.y, b.x, b.y);
+    }
+    if (want_i40) {
+        const double2 a = k0[N_ITAB], b = k1[N_ITAB];
+        out[N_ITAB] = hermite_eval(hb, a.x, a.y, b.x, b.y);
+    }
+    else out[N_ITAB] = 0.0;
+}
+
 COFFE_HD double compact_i40(const CompactView &c, const double r)
 {
     const int hi = hi_word(r);
@@ -115,6 +154,11 @@ COFFE_HD double compact_i40(const CompactView &c, const double r)
 struct ExactAccess {
     const Tables *t;
     COFFE_HD void ifam_all(const double r, double out[N_ITAB]) const { ifam_eval_all(t->ifam, r, out); }
+    COFFE_HD void ifam9(const double r, double out[N_ITAB9], const bool want_i40) const
+    {
+        ifam_eval_all(t->ifam, r, out);
+        out[N_ITAB] = want_i40 ? hspline_eval(t->i40, r) : 0.0;
+    }
     COFFE_HD double i40(const double r) const { return hspline_eval(t->i40, r); }
     COFFE_HD double ren2d(const double a, const double b) const { return renorm2d_eval(t->ren2d, a, b); }
     COFFE_HD double ren0(const double l) const { return spline_eval(t->ren0, l); }
@@ -124,6 +168,7 @@ struct CompactAccess {
     const Tables *t;           /* renormalisation grid and zero-separation spline stay in global memory (L2) */
     CompactView c;
     COFFE_HD void ifam_all(const double r, double out[N_ITAB]) const { compact_ifam_all(c, r, out); }
+    COFFE_HD void ifam9(const double r, double out[N_ITAB9], const bool want_i40) const { compact_ifam9(c, r, out, want_i40); }
     COFFE_HD double i40(const double r) const { return compact_i40(c, r); }
     COFFE_HD double ren2d(const double a, const double b) const { return renorm2d_eval(t->ren2d, a, b); }
     COFFE_HD double ren0(const double l) const { return spline_eval(t->ren0, l); }

@@ -23,6 +23,8 @@ namespace coffe {
 /* default knot budget and tolerance of the binary grid */
 static const int kCompactKnotBudget = 800;
 static const double kCompactTolerance = 3e-9;
+/* I^4_0 only enters the renormalised potential terms (relative weight ~1e-4 of the signal): looser target */
+static const double kCompactToleranceI40 = 1e-6;
 
 struct CompactBuild {
     std::vector<double> blob;       /* 16-byte aligned payload (vector<double> storage is 16-byte aligned by the allocator) */
@@ -40,7 +42,19 @@ struct FamilyRef {
     int m, n_small;
     std::vector<double> y[N_ITAB];      /* reference values at the knots */
     std::vector<double> env[N_ITAB];    /* envelope used to normalise errors */
+    bool div = false;                   /* I^4_0 present: ninth function of every knot */
+    double G40 = 0.0;                   /* max r |I^4_0(r)| over its knots */
 };
+
+/* I^4_0 is the reference's Akima interpolant through 297 knots; it is resampled with its own exact derivative
+   (cubic Hermite reproduces a cubic, so only binary-grid intervals that straddle one of the 297 knots carry an
+   error).  Envelope as for the family: largest |f| within +-19 % in r, floored where r |f| is unimportant. */
+inline double i40_envelope(const FamilyRef &F, const double r)
+{
+    double a = 0.0;
+    for (int q = -4; q <= 4; ++q) a = std::max(a, std::fabs(hspline_eval(F.t->i40, r * (1.0 + 0.0475 * q))));
+    return std::max(a, kImportanceFloor * F.G40 / std::max(r, 1e-3));
+}
 
 inline void family_ref_init(const Tables &t, FamilyRef &F)
 {
@@ -52,6 +66,9 @@ inline void family_ref_init(const Tables &t, FamilyRef &F)
         ifam_eval_all(t.ifam, t.ifam.x[i], v);
         for (int f = 0; f < N_ITAB; ++f) F.y[f][i] = v[f];
     }
+    F.div = t.has_divergent != 0;
+    if (F.div)
+        for (int i = 1; i < t.i40.n; ++i) F.G40 = std::max(F.G40, t.i40.x[i] * std::fabs(hspline_eval(t.i40, t.i40.x[i])));
     /* windows in knots of the log-spaced part: +-19 % and a factor 4 below */
     const double dln = t.ifam.inv_dln > 0 ? 1.0 / t.ifam.inv_dln : 0.01;
     const int w1 = std::max(2, (int)(std::log(1.19) / dln)), w4 = std::max(4, (int)(std::log(4.0) / dln));
@@ -106,11 +123,12 @@ inline void family_value_deriv(const FamilyRef &F, double r, double val[N_ITAB],
 struct Region {
     double lo, hi;      /* [lo, hi) */
     int m;
-    double err;
+    double err;         /* worst error of the region in units of its tolerance (family: tol, I^4_0: kCompactToleranceI40) */
+    double err_fam, err_i40;
     std::vector<double> knots;      /* (2^m + 1) x kKnotStride */
 };
 
-inline void region_fill(const FamilyRef &F, Region &R)
+inline void region_fill(const FamilyRef &F, Region &R, const double tol)
 {
     const int n = 1 << R.m;
     const double h = (R.hi - R.lo) / n;
@@ -119,9 +137,14 @@ inline void region_fill(const FamilyRef &F, Region &R)
         double v[N_ITAB], d[N_ITAB];
         family_value_deriv(F, R.lo + j * h, v, d);
         for (int f = 0; f < N_ITAB; ++f) { R.knots[(size_t)j * kKnotStride + 2 * f] = v[f]; R.knots[(size_t)j * kKnotStride + 2 * f + 1] = h * d[f]; }
+        if (F.div) {
+            double der = 0.0;
+            R.knots[(size_t)j * kKnotStride + 2 * N_ITAB] = hspline_eval_deriv(F.t->i40, R.lo + j * h, &der);
+            R.knots[(size_t)j * kKnotStride + 2 * N_ITAB + 1] = h * der;
+        }
     }
     /* error at three interior points per interval */
-    double worst = 0.0;
+    double worst = 0.0, worst40 = 0.0;
     const double *x = F.t->ifam.x;
     for (int j = 0; j < n; ++j)
         for (int q = 1; q <= 3; ++q) {
@@ -137,8 +160,13 @@ inline void region_fill(const FamilyRef &F, Region &R)
                 const double e = std::fabs(got - ex[f]) / std::max(F.env[f][i], 1e-300);
                 worst = std::max(worst, e);
             }
+            if (F.div) {
+                const double got = k0[2 * N_ITAB] + h01 * (k1[2 * N_ITAB] - k0[2 * N_ITAB]) + h10 * k0[2 * N_ITAB + 1] + h11 * k1[2 * N_ITAB + 1];
+                worst40 = std::max(worst40, std::fabs(got - hspline_eval(F.t->i40, r)) / i40_envelope(F, r));
+            }
         }
-    R.err = worst;
+    R.err_fam = worst; R.err_i40 = worst40;
+    R.err = std::max(worst / tol, worst40 / kCompactToleranceI40);
 }
 
 }  // namespace build
@@ -168,7 +196,7 @@ inline bool build_compact(const Tables &t, const Layout &L, const int knot_budge
             Region R;
             R.lo = std::ldexp(1.0 + 0.25 * q, e); R.hi = std::ldexp(1.0 + 0.25 * (q + 1), e);
             R.m = 1;
-            region_fill(F, R);
+            region_fill(F, R, tol);
             regs.push_back(std::move(R));
             if (regs.back().hi >= r_max) { done = true; break; }
         }
@@ -182,15 +210,15 @@ inline bool build_compact(const Tables &t, const Layout &L, const int knot_budge
         const size_t left = (size_t)knot_budget - std::min((size_t)knot_budget, total_knots());
         int worst = -1;
         for (int i = 0; i < (int)regs.size(); ++i)
-            if (regs[i].m < m_cap && regs[i].hi <= r_max && regs[i].err > tol && (size_t)(1 << regs[i].m) <= left
+            if (regs[i].m < m_cap && regs[i].hi <= r_max && regs[i].err > 1.0 && (size_t)(1 << regs[i].m) <= left
                 && (worst < 0 || regs[i].err > regs[worst].err)) worst = i;
         if (worst < 0) break;
         regs[worst].m += 1;
-        region_fill(F, regs[worst]);
+        region_fill(F, regs[worst], tol);
     }
-    double max_err = 0.0;
+    double max_err = 0.0, max_err40 = 0.0;
     for (auto &R : regs)
-        if (R.hi <= r_max) max_err = std::max(max_err, R.err);      /* the last region straddles the end of the table: never reached by a valid point */
+        if (R.hi <= r_max) { max_err = std::max(max_err, R.err_fam); max_err40 = std::max(max_err40, R.err_i40); }      /* the last region straddles the end of the table: never reached by a valid point */
     /* ---- lay out the blob ---- */
     std::vector<double> &B = out.blob;
     B.clear();
@@ -232,6 +260,7 @@ inline bool build_compact(const Tables &t, const Layout &L, const int knot_budge
     H.bytes = (int)(B.size() * 8);
     H.r_lo = r_lo;
     H.max_rel_error = max_err;
+    H.max_rel_error_i40 = max_err40;
     unsigned char *base = reinterpret_cast<unsigned char *>(B.data());
     {
         int2 *rg = reinterpret_cast<int2 *>(base + H.off_region);

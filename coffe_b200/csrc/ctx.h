@@ -8,7 +8,7 @@
 
 #include "assemble.h"
 #include "compact_build.h"
-#include "item.cuh"
+#include "di_fast.cuh"
 #include "rules_build.h"
 
 using namespace coffe;

@@ -42,9 +42,9 @@ __global__ void los_build_kernel(const __grid_constant__ Tables t, double4 *out,
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double lam = i * h;
-    if (lam > chi_max) lam = chi_max;
-    out[i] = los_point(t, lam);
+    double4 k[2];
+    los_knot(t, i, h, chi_max, k);
+    out[2 * i] = k[0]; out[2 * i + 1] = k[1];
 }
 
 /* ---- local x local piece ----------------------------------------------------------------------- */
@@ -98,12 +98,14 @@ __global__ void ni_points_kernel(const __grid_constant__ Tables t, const __grid_
     out[i] = ni_eval(o, t, sc, g, e1, e2);
 }
 
-/* ---- integrated pieces: one CTA per item ------------------------------------------------------- */
+/* ---- integrated pieces, exact tables through L1/L2: one CTA per item (variant 0, cross-check) -----
+   mode 1: local x integrated (one warp per half); mode 2: integrated x integrated (outer nodes strided
+   over the warps).  Dynamic shared memory: [line-of-sight table][one renormalisation row per warp]. */
 struct ItemShared {
     Geometry g;
     SIHalf ha, hb;
     DIConst k;
-    double red[kItemWarps][2];
+    double red[kItemWarps];
     double panels[kItemWarps][2 * kMaxPanels];      /* per-warp panel list of ridge_integrate */
 };
 
@@ -111,103 +113,99 @@ struct ItemShared {
 #define COFFE_ITEM_MIN_BLOCKS 3
 #endif
 __global__ void __launch_bounds__(kItemThreads, COFFE_ITEM_MIN_BLOCKS) integrated_items_kernel(
-    const __grid_constant__ Tables t, const __grid_constant__ Options o, const __grid_constant__ Rules q,
+    const __grid_constant__ Tables t, const __grid_constant__ Options o, const __grid_constant__ Rules q, const int mode,
     const double *__restrict__ pz, const double *__restrict__ psep,
     const int *__restrict__ item_point, const double *__restrict__ item_mu, const int n_items,
-    const int los_stage_n, double *__restrict__ out_si, double *__restrict__ out_di, unsigned int *__restrict__ out_evals)
+    const int los_stage_n, double *__restrict__ out, unsigned int *__restrict__ out_evals)
 {
     extern __shared__ double4 los_s[];
     __shared__ ItemShared sh;
     const int item = blockIdx.x;
     if (item >= n_items) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool has_si = opt_has_si(o), has_di = opt_has_integrated(o);
 
     /* stage the line-of-sight table {W, V, U, Wa}(lambda) */
     const double4 *los = t.los.v;
     if (los_stage_n > 0) {
-        for (int i = tid; i < los_stage_n; i += kItemThreads) los_s[i] = t.los.v[i];
+        for (int i = tid; i < 2 * los_stage_n; i += kItemThreads) los_s[i] = t.los.v[i];
         los = los_s;
     }
+    double2 *row = reinterpret_cast<double2 *>(los_s + 2 * los_stage_n) + (size_t)warp * t.ren2d.n;
     if (tid == 0) {
         const int p = item_point[item];
         const double z = pz[p], sep = psep[p], mu = item_mu[item];
         const double chi_mean = bg_chi(t.bg, z);
         sh.g = geometry(chi_mean, sep, mu);
         const EndVals e1 = end_eval(o, t, sh.g.chi1, 1), e2 = end_eval(o, t, sh.g.chi2, 2);
-        if (has_si) {
+        if (mode == 1) {
             sh.ha = si_half_setup(o, sh.g, e1, e2, true);
             sh.hb = si_half_setup(o, sh.g, e2, e1, false);
         }
-        if (has_di) sh.k = di_setup(o, e1, e2);
+        else sh.k = di_setup(o, e1, e2);
     }
     __syncthreads();
 
-    double di = 0.0, si = 0.0;
-    if (out_evals && tid < 2) {
-        /* integrand evaluations of this item (roofline accounting): [2*item] = SI, [2*item+1] = DI */
-        out_evals[2 * item + tid] = tid == 0 ? (has_si ? si_eval_count(q, sh.g, sh.ha) + si_eval_count(q, sh.g, sh.hb) : 0u)
-                                             : (has_di ? di_eval_count(q, sh.g) : 0u);
-    }
-    /* local x integrated: one warp per half (1-D, ~3% of the work); the other warps go straight to the 2-D piece */
+    if (out_evals && tid == 0)
+        out_evals[item] = mode == 1 ? si_eval_count(q, sh.g, sh.ha) + si_eval_count(q, sh.g, sh.hb) : di_fast_eval_count(q, sh.g, sh.k);
     const ExactAccess ta{&t};
-    if (has_si && warp < 2) si = si_half_partial(ta, t.los, q, sh.g, warp == 0 ? sh.ha : sh.hb, los, lane, 32, sh.panels[warp]);
-    if (has_di) di = di_partial(ta, t.los, q, sh.g, sh.k, los, warp, kItemWarps, lane, 32, sh.panels[warp]);
-    di = warp_sum(di);
-    si = warp_sum(si);
-    if (lane == 0) { sh.red[warp][0] = si; sh.red[warp][1] = di; }
+    double v = 0.0;
+    if (mode == 1) {
+        if (warp < 2) v = si_half_partial(ta, t.los, q, sh.g, warp == 0 ? sh.ha : sh.hb, los, lane, 32, sh.panels[warp]);
+    }
+    else v = di_fast_partial(ta, t, los, q, sh.g, sh.k, row, warp, kItemWarps, lane, 32);
+    v = warp_sum(v);
+    if (lane == 0) sh.red[warp] = v;
     __syncthreads();
     if (tid == 0) {
-        double a = 0.0, b = 0.0;
+        double a = 0.0;
 #pragma unroll
-        for (int w = 0; w < kItemWarps; ++w) { a += sh.red[w][0]; b += sh.red[w][1]; }
-        out_si[item] = a;
-        out_di[item] = b;
+        for (int w = 0; w < kItemWarps; ++w) a += sh.red[w];
+        out[item] = a;
     }
 }
 
 
 /* ---- integrated pieces, shared-memory tables: persistent CTAs, one warp per item ------------------
    Every CTA copies the compact tables (compact.cuh) and the line-of-sight table into shared memory once,
-   then its warps draw items from a global counter until none are left.  A warp owns its item: lanes 0-2
-   fold the end-point amplitudes, all lanes stride over the (panel, node) pairs of the inner ridge rule
-   while the outer line-of-sight nodes are visited in order, so the result of an item does not depend on
-   which warp computed it (bit-reproducible for any grid size or GPU count). */
-struct WarpState {
+   then its warps draw items from a global counter until none are left.  A warp owns its item: the lanes
+   stride over the (panel, node) pairs of the inner ridge rule while the outer line-of-sight nodes are visited
+   in order, so the result of an item does not depend on which warp computed it (bit-reproducible for any
+   grid size or GPU count).  Two kernels so that each gets its own register allocation:
+   si_items_smem_kernel (local x integrated: two 1-D integrals per item) and di_items_smem_kernel
+   (integrated x integrated: the 2-D integral, > 90 % of the device time of a step). */
+struct SIWarpState {
     EndVals e[2];
     SIHalf h[2];
-    DIConst k;
 };
 
-constexpr int kSmemThreads = 384;
+constexpr int kSIThreads = 384;
 
-__global__ void __launch_bounds__(kSmemThreads, 1) items_smem_kernel(
+__global__ void __launch_bounds__(kSIThreads, 1) si_items_smem_kernel(
     const __grid_constant__ Tables t, const __grid_constant__ Options o, const __grid_constant__ Rules q,
     const __grid_constant__ CompactHeader ch, const uint4 *__restrict__ blob, const int stage_bytes,
     const double *__restrict__ pz, const double *__restrict__ psep,
     const int *__restrict__ item_point, const double *__restrict__ item_mu, const int n_items,
-    const int los_stage_n, const int panel_cap, double *__restrict__ out_si, double *__restrict__ out_di,
+    const int los_stage_n, const int panel_cap, double *__restrict__ out,
     unsigned int *__restrict__ out_evals, unsigned int *__restrict__ counter)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int n_warps = kSmemThreads / 32;
+    constexpr int n_warps = kSIThreads / 32;
     /* layout: [compact blob prefix][line-of-sight table][per-warp state][per-warp panel lists] */
     double4 *los_s = reinterpret_cast<double4 *>(smem + stage_bytes);
-    WarpState *ws_all = reinterpret_cast<WarpState *>(smem + stage_bytes + (size_t)los_stage_n * sizeof(double4));
+    SIWarpState *ws_all = reinterpret_cast<SIWarpState *>(smem + stage_bytes + (size_t)2 * los_stage_n * sizeof(double4));
     double *scratch = reinterpret_cast<double *>(ws_all + n_warps) + (size_t)warp * 2 * panel_cap;
     {
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
-        for (int i = tid; i < stage_bytes / 16; i += kSmemThreads) dst[i] = blob[i];
-        for (int i = tid; i < los_stage_n; i += kSmemThreads) los_s[i] = t.los.v[i];
+        for (int i = tid; i < stage_bytes / 16; i += kSIThreads) dst[i] = blob[i];
+        for (int i = tid; i < 2 * los_stage_n; i += kSIThreads) los_s[i] = t.los.v[i];
     }
     __syncthreads();
-    WarpState &ws = ws_all[warp];
+    SIWarpState &ws = ws_all[warp];
     CompactAccess ta;
     ta.t = &t; ta.c.base = smem; ta.c.h = ch;
     LosView lv = t.los;
     lv.v = los_s;
-    const bool has_si = opt_has_si(o), has_di = opt_has_integrated(o);
 
     for (;;) {
         unsigned int item = 0;
@@ -219,48 +217,103 @@ __global__ void __launch_bounds__(kSmemThreads, 1) items_smem_kernel(
         const Geometry g = geometry(bg_chi(t.bg, z), sep, mu);
         if (lane < 2) ws.e[lane] = end_eval(o, t, lane == 0 ? g.chi1 : g.chi2, lane + 1);
         __syncwarp();
-        if (lane < 2 && has_si) ws.h[lane] = si_half_setup(o, g, ws.e[lane], ws.e[1 - lane], lane == 0);
-        if (lane == 2 && has_di) ws.k = di_setup(o, ws.e[0], ws.e[1]);
+        if (lane < 2) ws.h[lane] = si_half_setup(o, g, ws.e[lane], ws.e[1 - lane], lane == 0);
         __syncwarp();
-        if (out_evals && lane < 2)
-            out_evals[2 * item + lane] = lane == 0 ? (has_si ? si_eval_count(q, g, ws.h[0]) + si_eval_count(q, g, ws.h[1]) : 0u)
-                                                   : (has_di ? di_eval_count(q, g) : 0u);
-        double si = 0.0, di = 0.0;
-        if (has_si) {
+        if (out_evals && lane == 0) out_evals[item] = si_eval_count(q, g, ws.h[0]) + si_eval_count(q, g, ws.h[1]);
+        double si = 0.0;
 #pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                const SIHalf h = ws.h[half];
-                si += si_half_partial(ta, lv, q, g, h, los_s, lane, 32, scratch);
-            }
-        }
-        if (has_di) {
-            const DIConst k = ws.k;
-            di = di_partial(ta, lv, q, g, k, los_s, 0, 1, lane, 32, scratch);
+        for (int half = 0; half < 2; ++half) {
+            const SIHalf h = ws.h[half];
+            si += si_half_partial(ta, lv, q, g, h, los_s, lane, 32, scratch);
         }
         si = warp_sum(si);
-        di = warp_sum(di);
-        if (lane == 0) { out_si[item] = si; out_di[item] = di; }
+        if (lane == 0) out[item] = si;
         __syncwarp();
     }
 }
 
+struct DIWarpState {
+    EndVals e[2];
+    DIConst k;
+};
+
+#ifndef COFFE_DI_THREADS
+#define COFFE_DI_THREADS 384
+#endif
+constexpr int kDIThreads = COFFE_DI_THREADS;
+
+__global__ void __launch_bounds__(kDIThreads, 1) di_items_smem_kernel(
+    const __grid_constant__ Tables t, const __grid_constant__ Options o, const __grid_constant__ Rules q,
+    const __grid_constant__ CompactHeader ch, const uint4 *__restrict__ blob, const int stage_bytes,
+    const double *__restrict__ pz, const double *__restrict__ psep,
+    const int *__restrict__ item_point, const double *__restrict__ item_mu, const int n_items,
+    const int los_stage_n, double *__restrict__ out,
+    unsigned int *__restrict__ out_evals, unsigned int *__restrict__ counter)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int n_warps = kDIThreads / 32;
+    /* layout: [compact blob prefix][line-of-sight table][per-warp renormalisation rows][per-warp state] */
+    double4 *los_s = reinterpret_cast<double4 *>(smem + stage_bytes);
+    double2 *row = reinterpret_cast<double2 *>(los_s + 2 * los_stage_n) + (size_t)warp * t.ren2d.n;
+    DIWarpState *ws_all = reinterpret_cast<DIWarpState *>(reinterpret_cast<double2 *>(los_s + 2 * los_stage_n) + (size_t)n_warps * t.ren2d.n);
+    {
+        uint4 *dst = reinterpret_cast<uint4 *>(smem);
+        for (int i = tid; i < stage_bytes / 16; i += kDIThreads) dst[i] = blob[i];
+        for (int i = tid; i < 2 * los_stage_n; i += kDIThreads) los_s[i] = t.los.v[i];
+    }
+    __syncthreads();
+    DIWarpState &ws = ws_all[warp];
+    CompactAccess ta;
+    ta.t = &t; ta.c.base = smem; ta.c.h = ch;
+
+    for (;;) {
+        unsigned int item = 0;
+        if (lane == 0) item = atomicAdd(counter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= (unsigned int)n_items) break;
+        const int p = item_point[item];
+        const double z = pz[p], sep = psep[p], mu = item_mu[item];
+        const Geometry g = geometry(bg_chi(t.bg, z), sep, mu);
+        if (lane < 2) ws.e[lane] = end_eval(o, t, lane == 0 ? g.chi1 : g.chi2, lane + 1);
+        __syncwarp();
+        if (lane == 0) ws.k = di_setup(o, ws.e[0], ws.e[1]);
+        __syncwarp();
+        const DIConst k = ws.k;
+        if (out_evals && lane == 0) out_evals[item] = di_fast_eval_count(q, g, k);
+        double di = di_fast_partial(ta, t, los_s, q, g, k, row, 0, 1, lane, 32);
+        di = warp_sum(di);
+        if (lane == 0) out[item] = di;
+        __syncwarp();
+    }
+}
+
+/* items of a batch: item (point p, node j of the mu rule of p's separation); one thread per point */
+__global__ void expand_items_kernel(const int *__restrict__ point_rule, const int *__restrict__ point_begin, const int n_points,
+                                    const int *__restrict__ rule_begin, const double *__restrict__ rule_mu, const double *__restrict__ rule_w,
+                                    int *__restrict__ item_point, double *__restrict__ item_mu, double *__restrict__ item_w)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_points) return;
+    const int r = point_rule[p], b = rule_begin[r], n = rule_begin[r + 1] - b, dst = point_begin[p];
+    for (int j = 0; j < n; ++j) { item_point[dst + j] = p; item_mu[dst + j] = rule_mu[b + j]; item_w[dst + j] = rule_w[b + j]; }
+}
+
 /* ---- mu reduction: one warp per point, fixed summation order ---------------------------------- */
-/* pm[(point*3 + piece)*n_l + il]; piece 0 (NI) is copied from ni[] */
-__global__ void reduce_multipoles_kernel(const int *__restrict__ point_begin, const int n_points,
-                                         const double *__restrict__ item_mu, const double *__restrict__ item_w,
-                                         const double *__restrict__ si, const double *__restrict__ di,
+/* pm[(point*3 + piece)*n_l + il]; piece 0 (NI) is copied from ni[]; pieces 1 and 2 each have their own mu rule */
+__global__ void reduce_multipoles_kernel(const int n_points,
+                                         const int *__restrict__ si_begin, const double *__restrict__ si_mu, const double *__restrict__ si_w,
+                                         const double *__restrict__ si,
+                                         const int *__restrict__ di_begin, const double *__restrict__ di_mu, const double *__restrict__ di_w,
+                                         const double *__restrict__ di,
                                          const double *__restrict__ ni, const LList ls, double *__restrict__ pm)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n_points) return;
-    const int b = point_begin[warp], e = point_begin[warp + 1];
     for (int il = 0; il < ls.n; ++il) {
         double a = 0.0, c = 0.0;
-        for (int i = b + lane; i < e; i += 32) {
-            const double f = item_w[i] * legendre_p(ls.l[il], item_mu[i]);
-            a += f * si[i];
-            c += f * di[i];
-        }
+        for (int i = si_begin[warp] + lane; i < si_begin[warp + 1]; i += 32) a += si_w[i] * legendre_p(ls.l[il], si_mu[i]) * si[i];
+        for (int i = di_begin[warp] + lane; i < di_begin[warp + 1]; i += 32) c += di_w[i] * legendre_p(ls.l[il], di_mu[i]) * di[i];
         a = warp_sum(a); c = warp_sum(c);
         if (lane == 0) {
             const double pre = 2 * ls.l[il] + 1;
@@ -357,6 +410,7 @@ Rules make_rules(const coffe_b200_ctx *ctx)
     q.n_panel_si = ctx->qc.n_panel_si; q.n_panel_di = ctx->qc.n_panel_di;
     q.n_outer = ctx->qc.n_outer;
     q.panel_w_mpc = ctx->qc.panel_w; q.panel_du = ctx->qc.panel_du; q.eps_min = ctx->qc.eps_min; q.tail_ratio = ctx->qc.tail_ratio;
+    q.panel_w_di = ctx->qc.panel_w_di; q.panel_du_di = ctx->qc.panel_du_di;
     return q;
 }
 
@@ -382,42 +436,62 @@ int check_point(coffe_b200_ctx *ctx, const double z, const double sep, const boo
 
 bool needs_renorm(const Options &o) { return o.d2 || o.g1 || o.g2 || o.g3 || o.g4 || o.g5; }
 
+/* the (point, mu) work items of one integrated piece, on the device */
+struct ItemList {
+    int n = 0;
+    DevBuf<int> point, begin;       /* item -> point; point -> first item (n_points + 1) */
+    DevBuf<double> mu, w, val;
+};
+
 /* a batch of points with their mu items, on the device */
 struct Batch {
-    int n_points = 0, n_items = 0;
-    DevBuf<double> pz, psep, item_mu, item_w, si, di, ni, pm;
-    DevBuf<int> item_point, point_begin;
-    DevBuf<unsigned int> evals;     /* optional: per-item integrand evaluation counts */
+    int n_points = 0;
+    DevBuf<double> pz, psep, ni, pm;
+    ItemList si, di;                /* local x integrated and integrated x integrated pieces: separate mu rules */
+    DevBuf<unsigned int> evals;     /* optional: per-item integrand evaluation counts of the list being launched */
     double chi_max = 0;     /* largest chi2 over the batch: how much of the line-of-sight table to stage */
 };
 
-int launch_integrated(coffe_b200_ctx *ctx, Batch &b)
+/* mode 1: local x integrated over b.si; mode 2: integrated x integrated over b.di */
+int launch_integrated(coffe_b200_ctx *ctx, Batch &b, const int mode, unsigned int *evals = nullptr)
 {
-    if (b.n_items == 0) return COFFE_B200_OK;
-    if (!opt_has_integrated(ctx->o)) {
-        CK(cudaMemsetAsync(b.si.p, 0, sizeof(double) * b.n_items, ctx->stream));
-        CK(cudaMemsetAsync(b.di.p, 0, sizeof(double) * b.n_items, ctx->stream));
+    ItemList &L = mode == 1 ? b.si : b.di;
+    if (L.n == 0) return COFFE_B200_OK;
+    const bool active = mode == 1 ? opt_has_si(ctx->o) : opt_has_integrated(ctx->o);
+    if (!active) {
+        CK(cudaMemsetAsync(L.val.p, 0, sizeof(double) * L.n, ctx->stream));
         return COFFE_B200_OK;
     }
-    int stage_n = (int)std::ceil(b.chi_max / ctx->layout.los_h) + 4;
+    int stage_n = (int)std::ceil(b.chi_max / ctx->layout.los_h) + 3;
     if (stage_n > ctx->layout.los_n) stage_n = ctx->layout.los_n;
+    const size_t los_bytes = (size_t)2 * stage_n * sizeof(double4);
+    const size_t row_bytes = (size_t)(ctx->layout.has_divergent ? ctx->layout.ren2d_n : 0) * sizeof(double2);
     if (ctx->variant == 1 && ctx->compact.h.valid) {
-        /* shared-memory tables: blob prefix covering R <= 2 chi_max, line-of-sight table, per-warp state and panel lists */
-        const int panel_cap = max_panels(ctx->qc);
+        /* shared-memory tables: blob prefix covering R <= 2 chi_max, line-of-sight table, per-warp state */
         const int stage_bytes = compact_stage_bytes(ctx->compact, 2.0 * b.chi_max);
-        const size_t need = (size_t)stage_bytes + (size_t)stage_n * sizeof(double4)
-                            + (size_t)(kSmemThreads / 32) * (sizeof(WarpState) + (size_t)2 * panel_cap * sizeof(double));
+        CompactHeader ch = ctx->compact.h;
+        ch.n_knots = (stage_bytes - ch.off_knots) / (kKnotStride * 8);
+        const int threads = mode == 1 ? kSIThreads : kDIThreads, warps = threads / 32;
+        const int panel_cap = max_panels(ctx->qc);
+        const size_t need = (size_t)stage_bytes + los_bytes +
+                            (mode == 1 ? (size_t)warps * (sizeof(SIWarpState) + (size_t)2 * panel_cap * sizeof(double))
+                                       : (size_t)warps * (sizeof(DIWarpState) + row_bytes));
         if (need <= (size_t)ctx->smem_optin) {
-            CompactHeader ch = ctx->compact.h;
-            ch.n_knots = (stage_bytes - ch.off_knots) / (kKnotStride * 8);
-            CK(cudaFuncSetAttribute(items_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
             CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int), ctx->stream));
-            const int warps = kSmemThreads / 32;
-            int grid = std::min(ctx->n_sm, (b.n_items + warps - 1) / warps);
+            int grid = std::min(ctx->n_sm, (L.n + warps - 1) / warps);
             if (grid < 1) grid = 1;
-            items_smem_kernel<<<grid, kSmemThreads, need, ctx->stream>>>(
-                ctx->t, ctx->o, make_rules(ctx), ch, reinterpret_cast<const uint4 *>(ctx->d_blob), stage_bytes, b.pz.p, b.psep.p,
-                b.item_point.p, b.item_mu.p, b.n_items, stage_n, panel_cap, b.si.p, b.di.p, b.evals.p, ctx->d_counter);
+            if (mode == 1) {
+                CK(cudaFuncSetAttribute(si_items_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+                si_items_smem_kernel<<<grid, threads, need, ctx->stream>>>(
+                    ctx->t, ctx->o, make_rules(ctx), ch, reinterpret_cast<const uint4 *>(ctx->d_blob), stage_bytes, b.pz.p, b.psep.p,
+                    L.point.p, L.mu.p, L.n, stage_n, panel_cap, L.val.p, evals, ctx->d_counter);
+            }
+            else {
+                CK(cudaFuncSetAttribute(di_items_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+                di_items_smem_kernel<<<grid, threads, need, ctx->stream>>>(
+                    ctx->t, ctx->o, make_rules(ctx), ch, reinterpret_cast<const uint4 *>(ctx->d_blob), stage_bytes, b.pz.p, b.psep.p,
+                    L.point.p, L.mu.p, L.n, stage_n, L.val.p, evals, ctx->d_counter);
+            }
             CK(cudaGetLastError());
             ctx->last_launches += 1;
             ctx->last_variant = 1;
@@ -425,11 +499,11 @@ int launch_integrated(coffe_b200_ctx *ctx, Batch &b)
         }
     }
     ctx->last_variant = 0;
-    size_t smem = (size_t)stage_n * sizeof(double4);
-    if (smem > 160 * 1024) { stage_n = 0; smem = 0; }     /* read the table through L1/L2 instead */
+    size_t smem = los_bytes + kItemWarps * row_bytes;
+    if (smem > 160 * 1024) { ctx->err = "line-of-sight table does not fit in shared memory"; return COFFE_B200_EINVAL; }
     CK(cudaFuncSetAttribute(integrated_items_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    integrated_items_kernel<<<b.n_items, kItemThreads, smem, ctx->stream>>>(
-        ctx->t, ctx->o, make_rules(ctx), b.pz.p, b.psep.p, b.item_point.p, b.item_mu.p, b.n_items, stage_n, b.si.p, b.di.p, b.evals.p);
+    integrated_items_kernel<<<L.n, kItemThreads, smem, ctx->stream>>>(
+        ctx->t, ctx->o, make_rules(ctx), mode, b.pz.p, b.psep.p, L.point.p, L.mu.p, L.n, stage_n, L.val.p, evals);
     CK(cudaGetLastError());
     ctx->last_launches += 1;
     return COFFE_B200_OK;
@@ -455,10 +529,13 @@ int run_multipole_batch(coffe_b200_ctx *ctx, Batch &b, const LList &ls, const bo
         CK(cudaGetLastError());
         ctx->last_launches += 1;
     }
-    int rc = launch_integrated(ctx, b);
+    int rc = launch_integrated(ctx, b, 1);
+    if (rc) return rc;
+    rc = launch_integrated(ctx, b, 2);
     if (rc) return rc;
     const int blocks = (b.n_points * 32 + 127) / 128;
-    reduce_multipoles_kernel<<<blocks, 128, 0, ctx->stream>>>(b.point_begin.p, b.n_points, b.item_mu.p, b.item_w.p, b.si.p, b.di.p,
+    reduce_multipoles_kernel<<<blocks, 128, 0, ctx->stream>>>(b.n_points, b.si.begin.p, b.si.mu.p, b.si.w.p, b.si.val.p,
+                                                              b.di.begin.p, b.di.mu.p, b.di.w.p, b.di.val.p,
                                                               has_ni ? b.ni.p : nullptr, ls, b.pm.p);
     CK(cudaGetLastError());
     ctx->last_launches += 1;
@@ -476,33 +553,56 @@ int run_multipole_batch(coffe_b200_ctx *ctx, Batch &b, const LList &ls, const bo
     return COFFE_B200_OK;
 }
 
-/* build the mu items of a list of points (host), upload everything */
-int build_multipole_batch(coffe_b200_ctx *ctx, const std::vector<double> &pz, const std::vector<double> &psep, Batch &b,
-                          const bool points_on_device)
+/* mu items of one piece for a list of points.  The mu rule depends on the separation only: the host builds one
+   rule per distinct separation (`sep`, n_sep entries; point p uses rule point_rule[p]) and uploads those; the
+   (point, mu, weight) items are expanded on the device. */
+int build_item_list(coffe_b200_ctx *ctx, const double *sep, const int n_sep, const std::vector<int> &point_rule, const DevBuf<int> &d_point_rule,
+                    const int n_per_panel, const bool active, ItemList &L)
 {
-    const int n = (int)psep.size();
-    b.n_points = n;
-    std::vector<int> item_point, point_begin(n + 1, 0);
-    std::vector<double> item_mu, item_w, mu, w;
-    const bool integrated = opt_has_integrated(ctx->o);
-    double last_sep = -1.0;
-    for (int p = 0; p < n; ++p) {
-        point_begin[p] = (int)item_mu.size();
-        if (!integrated) continue;
-        if (psep[p] != last_sep) { build_mu_rule(ctx->qc, psep[p], mu, w); last_sep = psep[p]; }
-        for (size_t j = 0; j < mu.size(); ++j) { item_point.push_back(p); item_mu.push_back(mu[j]); item_w.push_back(w[j]); }
+    const int n = (int)point_rule.size();
+    std::vector<int> rule_begin(n_sep + 1, 0), point_begin(n + 1, 0);
+    std::vector<double> rule_mu, rule_w, mu, w;
+    for (int r = 0; r < n_sep; ++r) {
+        rule_begin[r] = (int)rule_mu.size();
+        if (!active) continue;
+        build_mu_rule(ctx->qc, sep[r], mu, w, n_per_panel);
+        rule_mu.insert(rule_mu.end(), mu.begin(), mu.end());
+        rule_w.insert(rule_w.end(), w.begin(), w.end());
     }
-    point_begin[n] = (int)item_mu.size();
-    b.n_items = (int)item_mu.size();
-    if (!points_on_device) {
-        CK(b.pz.upload(pz, ctx->stream));
-        CK(b.psep.upload(psep, ctx->stream));
+    rule_begin[n_sep] = (int)rule_mu.size();
+    long total = 0;
+    for (int p = 0; p < n; ++p) { point_begin[p] = (int)total; total += rule_begin[point_rule[p] + 1] - rule_begin[point_rule[p]]; }
+    if (total > 0x7fffffffL) { ctx->err = "too many (point, mu) work items for one call"; return COFFE_B200_EINVAL; }
+    point_begin[n] = (int)total;
+    L.n = (int)total;
+    DevBuf<int> d_rule_begin;
+    DevBuf<double> d_rule_mu, d_rule_w;
+    CK(d_rule_begin.upload(rule_begin, ctx->stream));
+    CK(d_rule_mu.upload(rule_mu, ctx->stream));
+    CK(d_rule_w.upload(rule_w, ctx->stream));
+    CK(L.begin.upload(point_begin, ctx->stream));
+    CK(L.point.alloc(L.n));
+    CK(L.mu.alloc(L.n));
+    CK(L.w.alloc(L.n));
+    CK(L.val.alloc(L.n));
+    if (L.n > 0) {
+        expand_items_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d_point_rule.p, L.begin.p, n, d_rule_begin.p, d_rule_mu.p, d_rule_w.p,
+                                                                   L.point.p, L.mu.p, L.w.p);
+        CK(cudaGetLastError());
     }
-    CK(b.item_point.upload(item_point, ctx->stream));
-    CK(b.point_begin.upload(point_begin, ctx->stream));
-    CK(b.item_mu.upload(item_mu, ctx->stream));
-    CK(b.item_w.upload(item_w, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));       /* the staging buffers above go out of scope */
     return COFFE_B200_OK;
+}
+
+/* both item lists of a batch of points; point p has separation sep[point_rule[p]] */
+int build_multipole_batch(coffe_b200_ctx *ctx, const double *sep, const int n_sep, const std::vector<int> &point_rule, Batch &b)
+{
+    b.n_points = (int)point_rule.size();
+    DevBuf<int> d_point_rule;
+    CK(d_point_rule.upload(point_rule, ctx->stream));
+    int rc = build_item_list(ctx, sep, n_sep, point_rule, d_point_rule, ctx->qc.n_mu_panel, opt_has_si(ctx->o), b.si);
+    if (rc) return rc;
+    return build_item_list(ctx, sep, n_sep, point_rule, d_point_rule, ctx->qc.n_mu_panel_di, opt_has_integrated(ctx->o), b.di);
 }
 
 int check_finite(coffe_b200_ctx *ctx, const double *v, const size_t n)
@@ -560,23 +660,24 @@ int plan_build(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double 
     if (end == begin) return COFFE_B200_OK;
     CK(cudaSetDevice(ctx->device));
     std::vector<double> pz, psep;
+    std::vector<int> point_rule;
     const bool ren = needs_renorm(ctx->o);
     if (ren && !ctx->layout.has_divergent) { ctx->err = "d2/g1..g5 need the divergent I^4_0 tables (par->divergent)"; return COFFE_B200_EINVAL; }
-    pz.reserve(pl.n); psep.reserve(pl.n);
+    pz.reserve(pl.n); psep.reserve(pl.n); point_rule.reserve(pl.n);
     for (long it = begin; it < end; ++it) {
         const double z = z_mean[it / n_sep], s = sep[it % n_sep];
         rc = check_point(ctx, z, s, ren && opt_has_ni(ctx->o));
         if (rc) return rc;
-        pz.push_back(z); psep.push_back(s);
+        pz.push_back(z); psep.push_back(s); point_rule.push_back((int)(it % n_sep));
         const double chi2 = bg_chi(ctx->t_host.bg, z) + s / 2.;
         if (chi2 > pl.b.chi_max) pl.b.chi_max = chi2;
     }
-    rc = build_multipole_batch(ctx, pz, psep, pl.b, false);
+    CK(pl.b.pz.upload(pz, ctx->stream));
+    CK(pl.b.psep.upload(psep, ctx->stream));
+    rc = build_multipole_batch(ctx, sep, n_sep, point_rule, pl.b);
     if (rc) return rc;
     CK(pl.b.ni.alloc((size_t)pl.b.n_points * n_l));
     CK(pl.b.pm.alloc((size_t)pl.b.n_points * 3 * n_l));
-    CK(pl.b.si.alloc(pl.b.n_items));
-    CK(pl.b.di.alloc(pl.b.n_items));
     return COFFE_B200_OK;
 }
 
@@ -796,6 +897,7 @@ int coffe_b200_get_quadrature(const coffe_b200_ctx *ctx, coffe_b200_quadrature *
     q->n_mu_ni = c.n_mu_ni; q->n_mu_panel = c.n_mu_panel; q->mu_rho0 = c.mu_rho0; q->mu_panel_width = c.mu_panel_w;
     q->mu_uniform_extent = c.mu_du; q->n_outer = c.n_outer; q->n_panel_si = c.n_panel_si; q->n_panel_di = c.n_panel_di;
     q->n_z = c.n_z; q->panel_width = c.panel_w; q->panel_uniform_extent = c.panel_du; q->eps_min = c.eps_min; q->tail_ratio = c.tail_ratio;
+    q->n_mu_panel_di = c.n_mu_panel_di; q->panel_width_di = c.panel_w_di; q->panel_uniform_extent_di = c.panel_du_di;
     return COFFE_B200_OK;
 }
 
@@ -873,33 +975,38 @@ int coffe_b200_corrfunc(coffe_b200_ctx *ctx, const double *z_mean, int n_z, cons
             const double chi2 = bg_chi(ctx->t_host.bg, z_mean[iz]) + sep[ir] / 2.;
             if (chi2 > b.chi_max) b.chi_max = chi2;
         }
-    /* items in output order (iz, imu, ir) */
+    /* items in output order (iz, imu, ir); both integrated pieces are evaluated at the requested mu */
     for (int iz = 0; iz < n_z; ++iz)
         for (int im = 0; im < n_mu; ++im)
             for (int ir = 0; ir < n_sep; ++ir) { item_point.push_back(iz * n_sep + ir); item_mu.push_back(mu[im]); }
-    b.n_points = (int)pz.size(); b.n_items = (int)item_mu.size();
+    b.n_points = (int)pz.size();
+    const int n_items = (int)item_mu.size();
     CK(b.pz.upload(pz, ctx->stream));
     CK(b.psep.upload(psep, ctx->stream));
-    CK(b.item_point.upload(item_point, ctx->stream));
-    CK(b.item_mu.upload(item_mu, ctx->stream));
-    CK(b.si.alloc(b.n_items));
-    CK(b.di.alloc(b.n_items));
-    CK(b.ni.alloc(b.n_items));
+    for (ItemList *L : {&b.si, &b.di}) {
+        L->n = n_items;
+        CK(L->point.upload(item_point, ctx->stream));
+        CK(L->mu.upload(item_mu, ctx->stream));
+        CK(L->val.alloc(n_items));
+    }
+    CK(b.ni.alloc(n_items));
     ctx->o.out_multipoles = 0;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     if (opt_has_ni(ctx->o)) {
-        ni_points_kernel<<<(b.n_items + 127) / 128, 128, 0, ctx->stream>>>(ctx->t, ctx->o, b.pz.p, b.psep.p, b.item_point.p, b.item_mu.p, b.n_items, b.ni.p);
+        ni_points_kernel<<<(n_items + 127) / 128, 128, 0, ctx->stream>>>(ctx->t, ctx->o, b.pz.p, b.psep.p, b.si.point.p, b.si.mu.p, n_items, b.ni.p);
         CK(cudaGetLastError());
         ctx->last_launches += 1;
     }
-    else CK(cudaMemsetAsync(b.ni.p, 0, sizeof(double) * b.n_items, ctx->stream));
-    int rc = launch_integrated(ctx, b);
+    else CK(cudaMemsetAsync(b.ni.p, 0, sizeof(double) * n_items, ctx->stream));
+    int rc = launch_integrated(ctx, b, 1);
+    if (rc) return rc;
+    rc = launch_integrated(ctx, b, 2);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     std::vector<double> ni(n_out), si(n_out), di(n_out);
     CK(cudaMemcpyAsync(ni.data(), b.ni.p, n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(si.data(), b.si.p, n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(di.data(), b.di.p, n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(si.data(), b.si.val.p, n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(di.data(), b.di.val.p, n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
@@ -924,7 +1031,7 @@ int coffe_b200_average_multipoles(coffe_b200_ctx *ctx, const double *z_min, cons
     const bool ren = needs_renorm(ctx->o);
     if (ren && !ctx->layout.has_divergent) { ctx->err = "d2/g1..g5 need the divergent I^4_0 tables (par->divergent)"; return COFFE_B200_EINVAL; }
     Batch b;
-    std::vector<double> psep((size_t)n_groups * nz), pz_dummy;
+    std::vector<int> point_rule((size_t)n_groups * nz);
     const Tables &th = ctx->t_host;
     for (int ib = 0; ib < n_bins; ++ib) {
         if (!(z_min[ib] > 0.0) || !(z_max[ib] > z_min[ib]) || !(z_max[ib] < th.bg.z[th.bg.n - 1])) { ctx->err = "bad redshift bin"; return COFFE_B200_ERANGE; }
@@ -935,7 +1042,7 @@ int coffe_b200_average_multipoles(coffe_b200_ctx *ctx, const double *z_min, cons
                 return COFFE_B200_ERANGE;
             }
             if (ren && opt_has_ni(ctx->o) && !(c2 <= th.ren2d.x[th.ren2d.n - 1])) { ctx->err = "redshift bin outside the renormalisation grid"; return COFFE_B200_ERANGE; }
-            for (int k = 0; k < nz; ++k) psep[((size_t)ib * n_sep + ir) * nz + k] = sep[ir];
+            for (int k = 0; k < nz; ++k) point_rule[((size_t)ib * n_sep + ir) * nz + k] = ir;
         }
         if (c2 > b.chi_max) b.chi_max = c2;
     }
@@ -949,12 +1056,10 @@ int coffe_b200_average_multipoles(coffe_b200_ctx *ctx, const double *z_min, cons
     CK(b.psep.alloc(n_points));
     CK(pw.alloc(n_points));
     CK(gm.alloc((size_t)n_groups * 3 * n_l));
-    rc = build_multipole_batch(ctx, pz_dummy, psep, b, true);
+    rc = build_multipole_batch(ctx, sep, n_sep, point_rule, b);
     if (rc) return rc;
     CK(b.ni.alloc((size_t)b.n_points * n_l));
     CK(b.pm.alloc((size_t)b.n_points * 3 * n_l));
-    CK(b.si.alloc(b.n_items));
-    CK(b.di.alloc(b.n_items));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     average_points_kernel<<<(n_points + 127) / 128, 128, 0, ctx->stream>>>(ctx->t, ctx->o.H0h, d_zmin.p, d_zmax.p, n_bins, d_sep.p, n_sep,
                                                                           ctx->d_gl_x, ctx->d_gl_w, nz, b.pz.p, b.psep.p, pw.p);
@@ -1037,19 +1142,26 @@ int coffe_b200_plan_count(coffe_b200_plan *plan, double *n_items, double *n_ni_e
     std::lock_guard<std::mutex> lock(ctx->mu);
     Batch &b = plan->b;
     double si = 0, di = 0;
-    if (b.n_items > 0 && opt_has_integrated(ctx->o)) {
+    if (opt_has_integrated(ctx->o)) {
         CK(cudaSetDevice(ctx->device));
-        CK(b.evals.alloc((size_t)2 * b.n_items));
         ctx->o.out_multipoles = 1;
-        int rc = launch_integrated(ctx, b);
-        if (rc) return rc;
-        std::vector<unsigned int> h((size_t)2 * b.n_items);
-        CK(cudaMemcpyAsync(h.data(), b.evals.p, h.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        for (int mode = 1; mode <= 2; ++mode) {
+            ItemList &L = mode == 1 ? b.si : b.di;
+            if (L.n == 0) continue;
+            CK(b.evals.alloc(L.n));
+            CK(cudaMemsetAsync(b.evals.p, 0, sizeof(unsigned int) * L.n, ctx->stream));
+            const int rc = launch_integrated(ctx, b, mode, b.evals.p);
+            if (rc) return rc;
+            std::vector<unsigned int> h(L.n);
+            CK(cudaMemcpyAsync(h.data(), b.evals.p, h.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            double tot = 0;
+            for (int i = 0; i < L.n; ++i) tot += h[i];
+            (mode == 1 ? si : di) = tot;
+        }
         cudaFree(b.evals.p); b.evals.p = nullptr; b.evals.n = 0;
-        for (int i = 0; i < b.n_items; ++i) { si += h[2 * i]; di += h[2 * i + 1]; }
     }
-    if (n_items) *n_items = b.n_items;
+    if (n_items) *n_items = (double)b.si.n + (double)b.di.n;
     if (n_ni_evals) *n_ni_evals = opt_has_ni(ctx->o) ? (double)b.n_points * ctx->qc.n_mu_ni : 0.0;
     if (n_si_evals) *n_si_evals = si;
     if (n_di_evals) *n_di_evals = di;

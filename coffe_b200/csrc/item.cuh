@@ -17,6 +17,7 @@ struct Rules {
     int n_panel_si, n_panel_di;
     int n_outer;                    /* 0 = auto_n_outer(sep) */
     double panel_w_mpc, panel_du, eps_min, tail_ratio;
+    double panel_w_di, panel_du_di;  /* panel plan of the inner integral of the integrated x integrated piece */
 };
 
 /* panels one ridge_integrate call can hold in its scratch area (engine.cu checks the configured plan) */

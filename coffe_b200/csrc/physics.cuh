@@ -453,6 +453,35 @@ COFFE_HD double4 los_point(const Tables &t, const double lambda)
     return o;
 }
 
+/* Hermite knot i of the line-of-sight table (tables.cuh: LosView): values at lambda_i = i h and h d/dlambda from
+   fourth-order differences of the same two-level lookup (step h/2: wide enough to average over the kinks of the
+   underlying Akima interpolants, which are rough at the 1e-7 level; one-sided at the two ends of the table) */
+COFFE_HD void los_knot(const Tables &t, const int i, const double h, const double chi_max, double4 out[2])
+{
+    double lam = i * h;
+    if (lam > chi_max) lam = chi_max;
+    const double d = h / 2.0;
+    const double4 f0 = los_point(t, lam);
+    double dv[4];
+    if (lam - 2 * d >= 0.0 && lam + 2 * d <= chi_max) {
+        const double4 m2 = los_point(t, lam - 2 * d), m1 = los_point(t, lam - d), p1 = los_point(t, lam + d), p2 = los_point(t, lam + 2 * d);
+        dv[0] = (m2.x - 8 * m1.x + 8 * p1.x - p2.x) / 12.; dv[1] = (m2.y - 8 * m1.y + 8 * p1.y - p2.y) / 12.;
+        dv[2] = (m2.z - 8 * m1.z + 8 * p1.z - p2.z) / 12.; dv[3] = (m2.w - 8 * m1.w + 8 * p1.w - p2.w) / 12.;
+    }
+    else {
+        const double sg = lam - 2 * d < 0.0 ? 1.0 : -1.0;
+        const double4 a1 = los_point(t, lam + sg * d), a2 = los_point(t, lam + sg * 2 * d), a3 = los_point(t, lam + sg * 3 * d),
+                      a4 = los_point(t, lam + sg * 4 * d);
+        dv[0] = sg * (-25 * f0.x + 48 * a1.x - 36 * a2.x + 16 * a3.x - 3 * a4.x) / 12.;
+        dv[1] = sg * (-25 * f0.y + 48 * a1.y - 36 * a2.y + 16 * a3.y - 3 * a4.y) / 12.;
+        dv[2] = sg * (-25 * f0.z + 48 * a1.z - 36 * a2.z + 16 * a3.z - 3 * a4.z) / 12.;
+        dv[3] = sg * (-25 * f0.w + 48 * a1.w - 36 * a2.w + 16 * a3.w - 3 * a4.w) / 12.;
+    }
+    /* dv = d (df/dlambda); h f' = 2 dv */
+    out[0].x = f0.x; out[0].y = 2 * dv[0]; out[0].z = f0.y; out[0].w = 2 * dv[1];
+    out[1].x = f0.z; out[1].y = 2 * dv[2]; out[1].z = f0.w; out[1].w = 2 * dv[3];
+}
+
 /* ---- flat-sky closed forms for the multipoles ----------------------------------------------------- */
 COFFE_HD double factorial_d(const int n)
 {

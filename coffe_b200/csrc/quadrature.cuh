@@ -86,6 +86,10 @@ struct QuadConfig {
     double panel_du;        /* Du [Mpc] */
     double eps_min;         /* floor on eps [Mpc] */
     double tail_ratio;      /* growth factor of the tail panels beyond Du */
+    /* the integrated x integrated piece is smoother (two line-of-sight integrals) and dominates the cost: it has
+       its own, coarser mu rule and inner panel plan (DESIGN.md section 3.1 holds the convergence evidence) */
+    int n_mu_panel_di;
+    double panel_w_di, panel_du_di;
 };
 
 /* bank of Gauss-Legendre rules on [0,1] for n = 1..kMaxRule, rule n stored at offset n(n-1)/2 */

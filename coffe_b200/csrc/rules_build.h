@@ -17,11 +17,12 @@ inline QuadConfig default_quadrature()
 {
     QuadConfig q;
     q.n_mu_ni = 32;
-    q.n_mu_panel = 5; q.mu_rho0 = 4.0; q.mu_panel_w = 32.0; q.mu_du = 256.0;
+    q.n_mu_panel = 8; q.mu_rho0 = 4.0; q.mu_panel_w = 32.0; q.mu_du = 256.0;
     q.n_outer = 0;
-    q.n_panel_si = 8; q.n_panel_di = 6;
+    q.n_panel_si = 8; q.n_panel_di = 8;
     q.n_z = 8;
     q.panel_w = 16.0; q.panel_du = 320.0; q.eps_min = 1e-3; q.tail_ratio = 1.5;
+    q.n_mu_panel_di = 5; q.panel_w_di = 64.0; q.panel_du_di = 128.0;
     return q;
 }
 
@@ -42,6 +43,9 @@ inline QuadConfig merge_quadrature(const QuadConfig &base, const coffe_b200_quad
     if (u.panel_uniform_extent > 0) q.panel_du = u.panel_uniform_extent;
     if (u.eps_min > 0) q.eps_min = u.eps_min;
     if (u.tail_ratio > 1.0) q.tail_ratio = u.tail_ratio;
+    if (u.n_mu_panel_di > 0) q.n_mu_panel_di = u.n_mu_panel_di;
+    if (u.panel_width_di > 0) q.panel_w_di = u.panel_width_di;
+    if (u.panel_uniform_extent_di > 0) q.panel_du_di = u.panel_uniform_extent_di;
     return q;
 }
 
@@ -64,7 +68,8 @@ inline bool quadrature_valid(const QuadConfig &q, const int panel_capacity)
            q.n_outer >= 0 && q.n_outer <= kMaxRule && q.n_panel_si >= 2 && q.n_panel_si <= kMaxRule &&
            q.n_panel_di >= 2 && q.n_panel_di <= kMaxRule && q.n_z >= 1 && q.n_z <= kMaxRule &&
            q.panel_w > 0 && q.panel_du >= 0 && q.eps_min > 0 && q.tail_ratio > 1.0 &&
-           q.mu_rho0 > 0 && q.mu_panel_w > 0 && q.mu_du >= 0;
+           q.mu_rho0 > 0 && q.mu_panel_w > 0 && q.mu_du >= 0 &&
+           q.n_mu_panel_di >= 2 && q.n_mu_panel_di <= kMaxRule && q.panel_w_di > 0 && q.panel_du_di >= 0;
 }
 
 /* bank of Gauss-Legendre rules on [0,1], rule n at offset n(n-1)/2 */
@@ -93,8 +98,9 @@ inline std::vector<double> build_rpow(const double ratio)
    uniform / geometric plan as the line-of-sight integrals) plus one at |mu| = 0.999 where the reference
    switches formulas; n-point Gauss-Legendre per panel; mirrored to mu < 0.  Weights are for the measure
    dmu/2, i.e. xi_l = (2l+1) sum_j w_j P_l(mu_j) xi(mu_j)      (src/signal.c:97-110, 541). */
-inline void build_mu_rule(const QuadConfig &q, const double sep, std::vector<double> &mu, std::vector<double> &w)
+inline void build_mu_rule(const QuadConfig &q, const double sep, std::vector<double> &mu, std::vector<double> &w, const int n_per_panel = 0)
 {
+    const int n_mu_panel = n_per_panel > 0 ? n_per_panel : q.n_mu_panel;
     mu.clear(); w.clear();
     std::vector<double> bp;
     bp.push_back(0.0);
@@ -106,11 +112,11 @@ inline void build_mu_rule(const QuadConfig &q, const double sep, std::vector<dou
     bp.push_back(sep * std::sqrt(1.0 - kMuSwitch * kMuSwitch));
     std::sort(bp.begin(), bp.end());
     std::vector<double> x, wt;
-    build::gauss_legendre_01(q.n_mu_panel, x, wt);
+    build::gauss_legendre_01(n_mu_panel, x, wt);
     for (size_t k = 0; k + 1 < bp.size(); ++k) {
         const double a = std::asin(std::min(1.0, bp[k] / sep)), c = std::asin(std::min(1.0, bp[k + 1] / sep));
         if (!(c - a > 1e-14)) continue;
-        for (int j = 0; j < q.n_mu_panel; ++j) {
+        for (int j = 0; j < n_mu_panel; ++j) {
             const double phi = a + (c - a) * x[j];
             mu.push_back(std::cos(phi));
             w.push_back((c - a) * wt[j] * std::sin(phi) / 2.0);

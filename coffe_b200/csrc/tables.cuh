@@ -21,6 +21,24 @@ COFFE_HD double cubic_eval(const double4 k, const double dx)
     return fma(dx, fma(dx, fma(dx, k.w, k.z), k.y), k.x);
 }
 
+/* cubic Hermite basis on the unit interval, value form f0 + h01 (f1 - f0) + h10 m0 + h11 m1 */
+struct HermiteBasis { double h01, h10, h11; };
+
+COFFE_HD HermiteBasis hermite_basis(const double u)
+{
+    HermiteBasis b;
+    const double u2 = u * u, um1 = u - 1.0;
+    b.h01 = u2 * fma(-2.0, u, 3.0);      /* 3u^2 - 2u^3 */
+    b.h10 = u * um1 * um1;
+    b.h11 = u2 * um1;
+    return b;
+}
+
+COFFE_HD double hermite_eval(const HermiteBasis &b, const double f0, const double m0, const double f1, const double m1)
+{
+    return fma(b.h01, f1 - f0, fma(b.h10, m0, fma(b.h11, m1, f0)));
+}
+
 /* index i with x[i] <= v < x[i+1], clamped to [0, n-2] (gsl_interp_bsearch semantics) */
 COFFE_HD int knot_search(const double *x, const int n, const double v)
 {
@@ -70,6 +88,20 @@ COFFE_HD double hspline_eval(const HintedSplineView s, const double v)
         while (i < s.n - 2 && v >= s.x[i + 1]) ++i;
     }
     return cubic_eval(s.k[i], v - s.x[i]);
+}
+
+/* value and first derivative of the interpolant (the resampler of compact_build.h needs both) */
+COFFE_HD double hspline_eval_deriv(const HintedSplineView s, const double v, double *der)
+{
+    int i = 0;
+    if (v > s.x[1]) {
+        i = knot_search(s.x, s.n, v);
+        if (i > s.n - 2) i = s.n - 2;
+    }
+    const double4 k = s.k[i];
+    const double dx = v - s.x[i];
+    *der = fma(dx, fma(dx, 3.0 * k.w, 2.0 * k.z), k.y);
+    return cubic_eval(k, dx);
 }
 
 /* spline on (nominally) uniform knots: O(1) guess, then fix-up against the real knots so that the
@@ -194,6 +226,7 @@ COFFE_HD void ifam_eval_all(const IntegralFamilyView &t, const double r, double 
 struct Renorm2DView {
     const double *x;        /* n knots (same on both axes) */
     const double4 *node;    /* n*n nodes {z, zx, zy, zxy}; index j*n + i with i <-> first argument */
+    const double4 *nodeT;   /* the same nodes transposed, index i*n + j: a sweep over the second argument is contiguous */
     int n;
     double x0, inv_dx, dx;
 };
@@ -221,13 +254,56 @@ COFFE_HD double renorm2d_eval(const Renorm2DView &t, const double x, const doubl
          + h11t * (h00u * n10.y + h01u * n11.y + h10u * n10.w + h11u * n11.w);
 }
 
+/* renormalisation(x, .) for a fixed first argument, collapsed onto the knots of the second: row[j] = {value,
+   dy d/dy} at y_j.  ren_row_eval(row, y) is then the same bicubic patch as renorm2d_eval(x, y) with the sums
+   reassociated: the integrated x integrated kernel fills one row per outer line-of-sight node (cooperatively,
+   `nlanes` lanes) and every inner node costs one 1-D Hermite lookup instead of a 16-term patch. */
+COFFE_HD void ren_row_fill(const Renorm2DView &t, const double x, const int n_row, double2 *row, const int lane, const int nlanes)
+{
+    const double sx = (x - t.x0) * t.inv_dx;
+    int xi = (int)sx;
+    if (xi < 0) xi = 0;
+    if (xi > t.n - 2) xi = t.n - 2;
+    const double tt = sx - xi, t2 = tt * tt, t3 = t2 * tt;
+    const double h00 = 2 * t3 - 3 * t2 + 1, h10 = (t3 - 2 * t2 + tt) * t.dx, h01 = -2 * t3 + 3 * t2, h11 = (t3 - t2) * t.dx;
+    const double4 *a = t.nodeT + (size_t)xi * t.n, *b = a + t.n;
+    for (int j = lane; j < n_row; j += nlanes) {
+        const double4 p = a[j], q = b[j];
+        double2 o;
+        o.x = h00 * p.x + h01 * q.x + h10 * p.y + h11 * q.y;
+        o.y = (h00 * p.z + h01 * q.z + h10 * p.w + h11 * q.w) * t.dx;
+        row[j] = o;
+    }
+}
+
+/* rows needed to cover second arguments up to y_max */
+COFFE_HD int ren_row_count(const Renorm2DView &t, const double y_max)
+{
+    int n = (int)((y_max - t.x0) * t.inv_dx) + 3;
+    if (n > t.n) n = t.n;
+    if (n < 2) n = 2;
+    return n;
+}
+
+COFFE_HD double ren_row_eval(const Renorm2DView &t, const double2 *row, const int n_row, const double y)
+{
+    const double sy = (y - t.x0) * t.inv_dx;
+    int yi = (int)sy;
+    if (yi < 0) yi = 0;
+    if (yi > n_row - 2) yi = n_row - 2;
+    const HermiteBasis b = hermite_basis(sy - yi);
+    const double2 p = row[yi], q = row[yi + 1];
+    return hermite_eval(b, p.x, p.y, q.x, q.y);
+}
+
 /* ---- line-of-sight functions resampled on a uniform lambda grid --------------------------------
    W = D1/a, V = Hc (f-1), U = Hc (Hc-1), Wa = D1 a evaluated through the reference's own two-level
-   lookup z = z(lambda) -> spline(z) at n uniformly spaced lambda, read back by 4-point Lagrange
-   interpolation.  These are smooth on Gpc scales, so with spacing ~5 Mpc the resampling error is
-   ~1e-11 relative (tolerance budget). */
+   lookup z = z(lambda) -> spline(z) at n uniformly spaced lambda and stored as cubic Hermite data
+   {f, h f'} per knot: v[2j] = {W, hW', V, hV'}, v[2j+1] = {U, hU', Wa, hWa'}.  These functions are smooth
+   on Gpc scales, so with spacing ~18 Mpc the resampling error is ~1e-11 relative (tolerance
+   budget; tests/test_physics_cpu.py::test_line_of_sight_resampling_error). */
 struct LosView {
-    const double4 *v;   /* {W, V, U, Wa} per knot */
+    const double4 *v;   /* 2 double4 per knot */
     int n;
     double h, inv_h;
 };
@@ -236,20 +312,15 @@ COFFE_HD double4 los_eval(const double4 *v, const int n, const double inv_h, con
 {
     const double s = lambda * inv_h;
     int j = (int)s;
-    if (j < 1) j = 1;
-    if (j > n - 3) j = n - 3;
-    const double p = s - j;             /* in [0,1) in the interior; may extrapolate slightly at the ends */
-    const double pm1 = p - 1.0, pm2 = p - 2.0, pp1 = p + 1.0;
-    const double w0 = -p * pm1 * pm2 * (1.0 / 6.0);
-    const double w1 = pp1 * pm1 * pm2 * 0.5;
-    const double w2 = -pp1 * p * pm2 * 0.5;
-    const double w3 = pp1 * p * pm1 * (1.0 / 6.0);
-    const double4 a = v[j - 1], b = v[j], c = v[j + 1], d = v[j + 2];
+    if (j < 0) j = 0;
+    if (j > n - 2) j = n - 2;
+    const HermiteBasis b = hermite_basis(s - j);
+    const double4 a0 = v[2 * j], a1 = v[2 * j + 1], b0 = v[2 * j + 2], b1 = v[2 * j + 3];
     double4 o;
-    o.x = w0 * a.x + w1 * b.x + w2 * c.x + w3 * d.x;
-    o.y = w0 * a.y + w1 * b.y + w2 * c.y + w3 * d.y;
-    o.z = w0 * a.z + w1 * b.z + w2 * c.z + w3 * d.z;
-    o.w = w0 * a.w + w1 * b.w + w2 * c.w + w3 * d.w;
+    o.x = hermite_eval(b, a0.x, a0.y, b0.x, b0.y);
+    o.y = hermite_eval(b, a0.z, a0.w, b0.z, b0.w);
+    o.z = hermite_eval(b, a1.x, a1.y, b1.x, b1.y);
+    o.w = hermite_eval(b, a1.z, a1.w, b1.z, b1.w);
     return o;
 }
 

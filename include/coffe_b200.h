@@ -103,6 +103,9 @@ typedef struct coffe_b200_quadrature {
     int n_panel_si, n_panel_di;  /* nodes per line-of-sight panel */
     int n_z;                     /* nodes of the redshift average */
     double panel_width, panel_uniform_extent, eps_min, tail_ratio;   /* line-of-sight panel plan [Mpc] */
+    /* the integrated x integrated piece has its own mu rule and inner panel plan (it is smoother and dominates the cost) */
+    int n_mu_panel_di;
+    double panel_width_di, panel_uniform_extent_di;
 } coffe_b200_quadrature;
 
 /* ---- life cycle ---------------------------------------------------------------------------------- */

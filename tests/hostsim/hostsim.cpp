@@ -11,7 +11,7 @@
 
 #include "../../coffe_b200/csrc/assemble.h"
 #include "../../coffe_b200/csrc/compact_build.h"
-#include "../../coffe_b200/csrc/item.cuh"
+#include "../../coffe_b200/csrc/di_fast.cuh"
 #include "../../coffe_b200/csrc/rules_build.h"
 
 using namespace coffe;
@@ -27,6 +27,8 @@ struct HostSim {
     std::string err;
     CompactBuild cb;
     int variant = 0;        /* 0 = exact tables, 1 = compact (shared-memory) tables */
+    int legacy_di = 0;      /* 1 = di_eval on generic ridge panels instead of di_fast.cuh */
+    int di_lanes = 1;       /* lanes emulated by the di_fast path */
     CompactAccess compact() const { return CompactAccess{&t, CompactView{reinterpret_cast<const unsigned char *>(cb.blob.data()), cb.h}}; }
 };
 
@@ -38,6 +40,7 @@ static void set_rules(HostSim *s)
     q.gl_x = s->bx.data(); q.gl_w = s->bw.data(); q.rpow = s->rpow.data();
     q.n_panel_si = s->qc.n_panel_si; q.n_panel_di = s->qc.n_panel_di; q.n_outer = s->qc.n_outer;
     q.panel_w_mpc = s->qc.panel_w; q.panel_du = s->qc.panel_du; q.eps_min = s->qc.eps_min; q.tail_ratio = s->qc.tail_ratio;
+    q.panel_w_di = s->qc.panel_w_di; q.panel_du_di = s->qc.panel_du_di;
 }
 
 extern "C" {
@@ -49,11 +52,7 @@ void *hs_create(const coffe_b200_tables *T, const coffe_b200_options *opt)
     s->t = make_view(s->layout, s->arena.buf.data());
     /* line-of-sight table */
     double4 *los = reinterpret_cast<double4 *>(s->arena.buf.data() + s->layout.los);
-    for (int i = 0; i < s->layout.los_n; ++i) {
-        double lam = i * s->layout.los_h;
-        if (lam > s->layout.chi_max_table) lam = s->layout.chi_max_table;
-        los[i] = los_point(s->t, lam);
-    }
+    for (int i = 0; i < s->layout.los_n; ++i) los_knot(s->t, i, s->layout.los_h, s->layout.chi_max_table, los + 2 * i);
     Options &o = s->o;
     o.den = opt->den; o.rsd = opt->rsd; o.len = opt->len; o.d1 = opt->d1; o.d2 = opt->d2;
     o.g1 = opt->g1; o.g2 = opt->g2; o.g3 = opt->g3; o.g4 = opt->g4; o.g5 = opt->g5;
@@ -70,7 +69,7 @@ void *hs_create(const coffe_b200_tables *T, const coffe_b200_options *opt)
 void hs_destroy(void *h) { delete (HostSim *)h; }
 
 /* builds the compact tables (knot budget, tolerance) and selects them; returns the number of knots (< 0: failed).
-   info[0] = achieved max relative error, info[1] = blob bytes, info[2..] = subdivisions m per region (up to n_info-2) */
+   info[0] = achieved max relative error, info[1] = blob bytes, info[2] = the error of I^4_0, info[3..] = subdivisions m per region (up to n_info-2) */
 int hs_use_compact(void *h, int knot_budget, double tol, double *info, int n_info)
 {
     HostSim *s = (HostSim *)h;
@@ -80,7 +79,8 @@ int hs_use_compact(void *h, int knot_budget, double tol, double *info, int n_inf
     s->variant = 1;
     if (info && n_info >= 2) {
         info[0] = s->cb.h.max_rel_error; info[1] = s->cb.h.bytes;
-        for (int i = 0; i + 2 < n_info && i < (int)s->cb.region_m.size(); ++i) info[i + 2] = s->cb.region_m[i];
+        if (n_info >= 3) info[2] = s->cb.h.max_rel_error_i40;
+        for (int i = 0; i + 3 < n_info && i < (int)s->cb.region_m.size(); ++i) info[i + 3] = s->cb.region_m[i];
     }
     return s->cb.h.n_knots;
 }
@@ -91,6 +91,12 @@ void hs_tables_at(void *h, double r, double *out)
     HostSim *s = (HostSim *)h;
     if (s->variant) { const CompactAccess ca = s->compact(); ca.ifam_all(r, out); out[8] = s->layout.has_divergent ? ca.i40(r) : 0.0; }
     else { const ExactAccess ea{&s->t}; ea.ifam_all(r, out); out[8] = s->layout.has_divergent ? ea.i40(r) : 0.0; }
+}
+
+void hs_set_di_mode(void *h, int legacy, int lanes)
+{
+    HostSim *s = (HostSim *)h;
+    s->legacy_di = legacy; s->di_lanes = lanes > 0 ? lanes : 1;
 }
 
 void hs_set_quadrature(void *h, const coffe_b200_quadrature *u)
@@ -140,8 +146,9 @@ double hs_di(void *h, double z, double mu, double sep, double x1, double x2, int
     return di_eval(ExactAccess{&s->t}, k, g, l1, l2, los1, los2);
 }
 
-/* the three pieces at one (z, sep, mu) with the fixed-node rules: out[0..2] = NI, SI, DI */
-void hs_item(void *h, double z, double sep, double mu, double *out)
+/* the three pieces at one (z, sep, mu) with the fixed-node rules: out[0..2] = NI, SI, DI (pieces not in `mask`
+   = 1 | 2 | 4 are left at zero) */
+static void item_pieces(void *h, double z, double sep, double mu, int mask, double *out)
 {
     HostSim *s = (HostSim *)h;
     const Options &o = s->o;
@@ -149,37 +156,57 @@ void hs_item(void *h, double z, double sep, double mu, double *out)
     const Geometry g = geometry(sc.chi_mean, sep, mu);
     const EndVals e1 = end_eval(o, s->t, g.chi1, 1), e2 = end_eval(o, s->t, g.chi2, 2);
     out[0] = out[1] = out[2] = 0.0;
-    if (opt_has_ni(o)) out[0] = ni_eval(o, s->t, sc, g, e1, e2);
-    if (opt_has_si(o)) {
+    if (opt_has_ni(o) && (mask & 1)) out[0] = ni_eval(o, s->t, sc, g, e1, e2);
+    if (opt_has_si(o) && (mask & 2)) {
         const SIHalf ha = si_half_setup(o, g, e1, e2, true), hb = si_half_setup(o, g, e2, e1, false);
         double scratch[2 * kMaxPanels];
         if (s->variant) { const CompactAccess ca = s->compact(); out[1] = si_half_partial(ca, s->t.los, s->q, g, ha, s->t.los.v, 0, 1, scratch) + si_half_partial(ca, s->t.los, s->q, g, hb, s->t.los.v, 0, 1, scratch); }
         else { const ExactAccess ea{&s->t}; out[1] = si_half_partial(ea, s->t.los, s->q, g, ha, s->t.los.v, 0, 1, scratch) + si_half_partial(ea, s->t.los, s->q, g, hb, s->t.los.v, 0, 1, scratch); }
     }
-    if (opt_has_integrated(o)) {
+    if (opt_has_integrated(o) && (mask & 4)) {
         const DIConst k = di_setup(o, e1, e2);
-        double scratch[2 * kMaxPanels];
-        if (s->variant) out[2] = di_partial(s->compact(), s->t.los, s->q, g, k, s->t.los.v, 0, 1, 0, 1, scratch);
-        else out[2] = di_partial(ExactAccess{&s->t}, s->t.los, s->q, g, k, s->t.los.v, 0, 1, 0, 1, scratch);
+        std::vector<double2> row(s->layout.has_divergent ? s->t.ren2d.n : 1);
+        if (s->legacy_di) {
+            /* the straightforward evaluator (di_eval on the same panels, no pairing): cross-check of di_fast.cuh */
+            double scratch[2 * kMaxPanels];
+            Rules ql = s->q;
+            ql.panel_w_mpc = s->q.panel_w_di; ql.panel_du = s->q.panel_du_di;
+            if (s->variant) out[2] = di_partial(s->compact(), s->t.los, ql, g, k, s->t.los.v, 0, 1, 0, 1, scratch);
+            else out[2] = di_partial(ExactAccess{&s->t}, s->t.los, ql, g, k, s->t.los.v, 0, 1, 0, 1, scratch);
+        }
+        else {
+            /* the kernel's lane decomposition: n_lanes lanes in turn (1 = serial) */
+            const int nl = s->di_lanes;
+            double acc = 0.0;
+            for (int lane = 0; lane < nl; ++lane) {
+                if (s->variant) acc += di_fast_partial(s->compact(), s->t, s->t.los.v, s->q, g, k, row.data(), 0, 1, lane, nl, true);
+                else acc += di_fast_partial(ExactAccess{&s->t}, s->t, s->t.los.v, s->q, g, k, row.data(), 0, 1, lane, nl, true);
+            }
+            out[2] = acc;
+        }
     }
 }
 
-/* multipoles of the three pieces: out[piece*n_l + il]; same rules as the device path */
+void hs_item(void *h, double z, double sep, double mu, double *out) { item_pieces(h, z, sep, mu, 7, out); }
+
+/* multipoles of the three pieces: out[piece*n_l + il]; same rules as the device path (the local x integrated and
+   integrated x integrated pieces each on their own mu rule) */
 void hs_multipoles(void *h, double z, double sep, const int *ls, int n_l, double *out)
 {
     HostSim *s = (HostSim *)h;
-    std::vector<double> mu, w;
-    build_mu_rule(s->qc, sep, mu, w);
-    const int nm = (int)mu.size();
-    std::vector<double> v((size_t)3 * nm);
+    for (int p = 1; p < 3; ++p) {
+        std::vector<double> mu, w;
+        build_mu_rule(s->qc, sep, mu, w, p == 1 ? s->qc.n_mu_panel : s->qc.n_mu_panel_di);
+        const int nm = (int)mu.size();
+        std::vector<double> v((size_t)3 * nm);
 #pragma omp parallel for schedule(dynamic, 1)
-    for (int im = 0; im < nm; ++im) hs_item(h, z, sep, mu[im], &v[(size_t)3 * im]);
-    for (int p = 1; p < 3; ++p)
+        for (int im = 0; im < nm; ++im) item_pieces(h, z, sep, mu[im], p == 1 ? 2 : 4, &v[(size_t)3 * im]);
         for (int il = 0; il < n_l; ++il) {
             double acc = 0.0;
             for (int im = 0; im < nm; ++im) acc += w[im] * legendre_p(ls[il], mu[im]) * v[(size_t)3 * im + p];
             out[p * n_l + il] = (2 * ls[il] + 1) * acc;
         }
+    }
     const int nn = s->qc.n_mu_ni;
     const double *x = s->bx.data() + rule_offset(nn), *wn = s->bw.data() + rule_offset(nn);
     for (int il = 0; il < n_l; ++il) {
@@ -187,6 +214,28 @@ void hs_multipoles(void *h, double z, double sep, const int *ls, int n_l, double
         if (opt_has_ni(s->o))
             for (int j = 0; j < nn; ++j) acc += wn[j] * legendre_p(ls[il], 2 * x[j] - 1) * hs_ni(h, z, 2 * x[j] - 1, sep);
         out[il] = (2 * ls[il] + 1) * acc;
+    }
+}
+
+/* integrand evaluations of the fixed-node rules at one (z, sep): out[0] = SI, out[1] = DI, summed over the mu items */
+void hs_eval_counts(void *h, double z, double sep, double *out)
+{
+    HostSim *s = (HostSim *)h;
+    std::vector<double> mu, w;
+    const double chi_mean = bg_chi(s->t.bg, z);
+    out[0] = out[1] = 0.0;
+    build_mu_rule(s->qc, sep, mu, w, s->qc.n_mu_panel);
+    for (size_t im = 0; im < mu.size(); ++im) {
+        const Geometry g = geometry(chi_mean, sep, mu[im]);
+        const EndVals e1 = end_eval(s->o, s->t, g.chi1, 1), e2 = end_eval(s->o, s->t, g.chi2, 2);
+        const SIHalf ha = si_half_setup(s->o, g, e1, e2, true), hb = si_half_setup(s->o, g, e2, e1, false);
+        out[0] += si_eval_count(s->q, g, ha) + si_eval_count(s->q, g, hb);
+    }
+    build_mu_rule(s->qc, sep, mu, w, s->qc.n_mu_panel_di);
+    for (size_t im = 0; im < mu.size(); ++im) {
+        const Geometry g = geometry(chi_mean, sep, mu[im]);
+        const EndVals e1 = end_eval(s->o, s->t, g.chi1, 1), e2 = end_eval(s->o, s->t, g.chi2, 2);
+        out[1] += di_fast_eval_count(s->q, g, di_setup(s->o, e1, e2));
     }
 }
 

@@ -35,7 +35,8 @@ class HostSim:
         info = np.zeros(130)
         n = self.lib.hs_use_compact(self.h, C.c_int(knot_budget), C.c_double(tol), capi.ptr(info), C.c_int(len(info)))
         assert n >= 0, "hostsim: compact table construction failed"
-        self.compact_info = (n, info[0], int(info[1]), info[2:].astype(int))
+        self.compact_info = (n, info[0], int(info[1]), info[3:].astype(int))
+        self.compact_err_i40 = info[2]
         return self.compact_info
 
     def tables_at(self, r):
@@ -53,6 +54,10 @@ class HostSim:
     def set_quadrature(self, **kw):
         q = capi.make_quadrature(**kw)
         self.lib.hs_set_quadrature(self.h, C.byref(q))
+
+    def set_di_mode(self, legacy=False, lanes=1):
+        """legacy: di_eval on generic ridge panels (cross-check); otherwise di_fast.cuh emulating `lanes` lanes"""
+        self.lib.hs_set_di_mode(self.h, C.c_int(int(legacy)), C.c_int(lanes))
 
     def ni(self, z, mu, sep):
         return self.lib.hs_ni(self.h, C.c_double(z), C.c_double(mu), C.c_double(sep))
@@ -73,6 +78,12 @@ class HostSim:
         out = np.zeros(3 * len(ls))
         self.lib.hs_multipoles(self.h, C.c_double(z), C.c_double(sep), capi.iptr(ls), C.c_int(len(ls)), capi.ptr(out))
         return out.reshape(3, len(ls))
+
+    def eval_counts(self, z, sep):
+        """(SI, DI) integrand evaluations of the fixed-node rules at one (z, sep), summed over the mu items"""
+        out = np.zeros(2)
+        self.lib.hs_eval_counts(self.h, C.c_double(z), C.c_double(sep), capi.ptr(out))
+        return out
 
     def flatsky(self, z, sep, l, n_x=96):
         """(density-lensing, lensing-lensing) flat-sky closed-form multipoles"""
