@@ -84,7 +84,7 @@ inline Tables make_view(const Layout &L, const double *base)
     t.ren2d.node = reinterpret_cast<const double4 *>(base + L.ren2d_node);
     t.ren2d.nodeT = reinterpret_cast<const double4 *>(base + L.ren2d_nodeT);
     t.ren2d.n = L.ren2d_n; t.ren2d.x0 = L.ren2d_x0; t.ren2d.inv_dx = L.ren2d_inv_dx; t.ren2d.dx = L.ren2d_dx;
-    t.los.v = reinterpret_cast<const double4 *>(base + L.los);
+    t.los.v = reinterpret_cast<const double2 *>(base + L.los);
     t.los.n = L.los_n; t.los.h = L.los_h; t.los.inv_h = L.los_h > 0 ? 1.0 / L.los_h : 0.0;
     t.n_extra = L.n_extra;
     for (int i = 0; i < L.n_extra; ++i) {
@@ -248,7 +248,7 @@ inline bool assemble(const coffe_b200_tables &T, Arena &A, Layout &L, std::strin
     /* ---- line-of-sight table (filled later by evaluating the splines above) ---- */
     L.los_n = kLosSamples;
     L.los_h = L.chi_max_table / (kLosSamples - 1);
-    L.los = A.alloc((size_t)8 * kLosSamples);
+    L.los = A.alloc((size_t)2 * kLosStride * kLosSamples);
     return true;
 }
 

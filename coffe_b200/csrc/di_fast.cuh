@@ -105,20 +105,21 @@ COFFE_HD DIShared di_shared(const TA &ta, const DIFast &f, const DIOuter &o, con
 template <class TA>
 struct DISideCtx {
     const TA *ta;
-    const double4 *los; int los_n; double los_inv_h;
+    const double2 *los; int los_n; double los_inv_h;
     const Renorm2DView *r2d; const double2 *row; int n_row;
 };
 
-/* integrand at lambda_2 = l2 (per unit lambda_2, H0^4 and all amplitudes included) */
-template <class TA>
+/* integrand at lambda_2 = l2 (per unit lambda_2, H0^4 and all amplitudes included).  ALL: every group of terms is
+   on and R^2 > 1e-12 is guaranteed by the caller (squared impact parameter above it), so the body is branch-free. */
+template <bool ALL, class TA>
 COFFE_HD double di_side(const DISideCtx<TA> &cx, const DIFast &f, const DIOuter &o, const DIShared &s, const double l2)
 {
     const double4 los2 = los_eval(cx.los, cx.los_n, cx.los_inv_h, l2);
     const double ll = o.l1 * l2, e2 = f.chi2 - l2;
     double acc = 0.0;
-    if (f.any_ll) {
+    if (ALL || f.any_ll) {
         double br;
-        if (s.r2 > 1e-20) {
+        if (ALL || s.r2 > 1e-20) {
             const double q = ll * s.ir2;
             double t = fma(s.I02, fma(f.k02b, q, f.k02a), s.I00k);
             t = fma(s.I04, fma(fma(f.k04c, q, f.k04b), q, f.k04a), t);
@@ -129,13 +130,13 @@ COFFE_HD double di_side(const DISideCtx<TA> &cx, const DIFast &f, const DIOuter 
         else br = fma(f.k_ll1 * ll, s.I11, f.k_ll0);
         acc = o.e1W1 * e2 * br;
     }
-    if (f.any_pl) {
+    if (ALL || f.any_pl) {
         const double G = s.twocI31 - (f.s2 * ll) * s.I22;
         const double F = fma(o.A1, e2, l2 * fma(o.E5, los2.z, o.E4));
         acc = fma(G, F, acc);
     }
-    if (f.any_ren) {
-        const double ren = (s.r2 <= 1e-12) ? cx.ta->ren0(o.l1) : s.I40 - ren_row_eval(*cx.r2d, cx.row, cx.n_row, l2);
+    if (ALL || f.any_ren) {
+        const double ren = (!ALL && s.r2 <= 1e-12) ? cx.ta->ren0(o.l1) : s.I40 - ren_row_eval(*cx.r2d, cx.row, cx.n_row, l2);
         acc = fma(ren, fma(o.B1, los2.y, o.B0), acc);
     }
     return los2.x * acc;
@@ -178,7 +179,7 @@ COFFE_HD void di_single_panel(const DIPanels &p, const bool neg, const int k, do
 }
 
 /* inner integral over lambda_2 in [0, chi2] at one outer node: this lane's partial sum */
-template <class TA>
+template <bool ALL, class TA>
 COFFE_HD double di_inner_partial(const DISideCtx<TA> &cx, const Rules &q, const DIFast &f, const DIOuter &o,
                                  const int lane, const int nlanes)
 {
@@ -186,7 +187,7 @@ COFFE_HD double di_inner_partial(const DISideCtx<TA> &cx, const Rules &q, const 
     const int ppi = nlanes >= np ? nlanes / np : 1;
     const int lp = lane / np, j = lane - lp * np;
     if (nlanes >= np && lp >= ppi) return 0.0;
-    const double *px = q.gl_x + rule_offset(np), *pw = q.gl_w + rule_offset(np);
+    const double *px = q.panel_x ? q.panel_x : q.gl_x + rule_offset(np), *pw = q.panel_w ? q.panel_w : q.gl_w + rule_offset(np);
     const DIPanels p = di_panels(q, f, o);
     double acc = 0.0;
     /* nodes this lane owns: j, j + nlanes, ... (only when a panel has more nodes than there are lanes) */
@@ -197,7 +198,7 @@ COFFE_HD double di_inner_partial(const DISideCtx<TA> &cx, const Rules &q, const 
             const double lo = panel_break(p.plan, k), w = panel_break(p.plan, k + 1) - lo;
             const double d = fma(w, xj, lo);
             const DIShared s = di_shared(*cx.ta, f, o, d);
-            const double v = di_side(cx, f, o, s, o.c0 - d) + di_side(cx, f, o, s, o.c0 + d);
+            const double v = di_side<ALL>(cx, f, o, s, o.c0 - d) + di_side<ALL>(cx, f, o, s, o.c0 + d);
             acc = fma(w * wj, v, acc);
         }
         /* remainders: negative side k_pair..k_neg-1, then positive side k_pair..k_pos-1 */
@@ -209,7 +210,7 @@ COFFE_HD double di_inner_partial(const DISideCtx<TA> &cx, const Rules &q, const 
             if (w == 0.0) continue;
             const double d = fma(w, xj, lo);
             const DIShared s = di_shared(*cx.ta, f, o, d);
-            acc = fma(w * wj, di_side(cx, f, o, s, neg ? o.c0 - d : o.c0 + d), acc);
+            acc = fma(w * wj, di_side<ALL>(cx, f, o, s, neg ? o.c0 - d : o.c0 + d), acc);
         }
     }
     return acc;
@@ -227,7 +228,7 @@ COFFE_HD unsigned int di_inner_eval_count(const Rules &q, const DIFast &f, const
 /* integrated x integrated piece per unit (x1, x2).  Outer nodes strided over `ngroups` groups of `nlanes` lanes;
    `row` is the group's own buffer of t.ren2d.n double2 (renormalisation row), unused without the divergent terms. */
 template <class TA>
-COFFE_HD double di_fast_partial(const TA &ta, const Tables &t, const double4 *los, const Rules &q, const Geometry &g, const DIConst &k,
+COFFE_HD double di_fast_partial(const TA &ta, const Tables &t, const double2 *los, const Rules &q, const Geometry &g, const DIConst &k,
                                 double2 *row, const int group, const int ngroups, const int lane, const int nlanes,
                                 const bool serial_fill = false /* CPU harness: lanes run one after the other, each fills the whole row */)
 {
@@ -247,7 +248,8 @@ COFFE_HD double di_fast_partial(const TA &ta, const Tables &t, const double4 *lo
             ren_row_fill(t.ren2d, l1, cx.n_row, row, serial_fill ? 0 : lane, serial_fill ? 1 : nlanes);
             COFFE_SYNC_LANES();
         }
-        acc = fma(outer_w[io], di_inner_partial(cx, q, f, o, lane, nlanes), acc);
+        const bool all = f.any_ll && f.any_pl && f.any_ren && o.eps2 > 1e-12;
+        acc = fma(outer_w[io], all ? di_inner_partial<true>(cx, q, f, o, lane, nlanes) : di_inner_partial<false>(cx, q, f, o, lane, nlanes), acc);
     }
     return acc / g.chi2;
 }

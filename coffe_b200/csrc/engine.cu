@@ -38,13 +38,13 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 /* ---- set-up: line-of-sight table -------------------------------------------------------------- */
-__global__ void los_build_kernel(const __grid_constant__ Tables t, double4 *out, const int n, const double h, const double chi_max)
+__global__ void los_build_kernel(const __grid_constant__ Tables t, double2 *out, const int n, const double h, const double chi_max)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double4 k[2];
+    double2 k[kLosStride];
     los_knot(t, i, h, chi_max, k);
-    out[2 * i] = k[0]; out[2 * i + 1] = k[1];
+    for (int c = 0; c < kLosStride; ++c) out[(size_t)kLosStride * i + c] = k[c];
 }
 
 /* ---- local x local piece ----------------------------------------------------------------------- */
@@ -118,19 +118,19 @@ __global__ void __launch_bounds__(kItemThreads, COFFE_ITEM_MIN_BLOCKS) integrate
     const int *__restrict__ item_point, const double *__restrict__ item_mu, const int n_items,
     const int los_stage_n, double *__restrict__ out, unsigned int *__restrict__ out_evals)
 {
-    extern __shared__ double4 los_s[];
+    extern __shared__ double2 los_s[];
     __shared__ ItemShared sh;
     const int item = blockIdx.x;
     if (item >= n_items) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     /* stage the line-of-sight table {W, V, U, Wa}(lambda) */
-    const double4 *los = t.los.v;
+    const double2 *los = t.los.v;
     if (los_stage_n > 0) {
-        for (int i = tid; i < 2 * los_stage_n; i += kItemThreads) los_s[i] = t.los.v[i];
+        for (int i = tid; i < kLosStride * los_stage_n; i += kItemThreads) los_s[i] = t.los.v[i];
         los = los_s;
     }
-    double2 *row = reinterpret_cast<double2 *>(los_s + 2 * los_stage_n) + (size_t)warp * t.ren2d.n;
+    double2 *row = los_s + kLosStride * los_stage_n + (size_t)warp * t.ren2d.n;
     if (tid == 0) {
         const int p = item_point[item];
         const double z = pz[p], sep = psep[p], mu = item_mu[item];
@@ -192,13 +192,13 @@ __global__ void __launch_bounds__(kSIThreads, 1) si_items_smem_kernel(
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int n_warps = kSIThreads / 32;
     /* layout: [compact blob prefix][line-of-sight table][per-warp state][per-warp panel lists] */
-    double4 *los_s = reinterpret_cast<double4 *>(smem + stage_bytes);
-    SIWarpState *ws_all = reinterpret_cast<SIWarpState *>(smem + stage_bytes + (size_t)2 * los_stage_n * sizeof(double4));
+    double2 *los_s = reinterpret_cast<double2 *>(smem + stage_bytes);
+    SIWarpState *ws_all = reinterpret_cast<SIWarpState *>(los_s + (size_t)kLosStride * los_stage_n);
     double *scratch = reinterpret_cast<double *>(ws_all + n_warps) + (size_t)warp * 2 * panel_cap;
     {
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
         for (int i = tid; i < stage_bytes / 16; i += kSIThreads) dst[i] = blob[i];
-        for (int i = tid; i < 2 * los_stage_n; i += kSIThreads) los_s[i] = t.los.v[i];
+        for (int i = tid; i < kLosStride * los_stage_n; i += kSIThreads) los_s[i] = t.los.v[i];
     }
     __syncthreads();
     SIWarpState &ws = ws_all[warp];
@@ -240,7 +240,11 @@ struct DIWarpState {
 #ifndef COFFE_DI_THREADS
 #define COFFE_DI_THREADS 384
 #endif
-constexpr int kDIThreads = COFFE_DI_THREADS;
+constexpr int kDIThreads = COFFE_DI_THREADS;        /* upper bound (register allocation); the launch may use fewer warps */
+
+/* doubles of the small read-only block staged next to the tables: powers of the tail ratio, then the nodes and
+   weights of the inner panel rule */
+constexpr int kDISmallDoubles = kMaxTail + 2 * 32;
 
 __global__ void __launch_bounds__(kDIThreads, 1) di_items_smem_kernel(
     const __grid_constant__ Tables t, const __grid_constant__ Options o, const __grid_constant__ Rules q,
@@ -252,20 +256,31 @@ __global__ void __launch_bounds__(kDIThreads, 1) di_items_smem_kernel(
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int n_warps = kDIThreads / 32;
-    /* layout: [compact blob prefix][line-of-sight table][per-warp renormalisation rows][per-warp state] */
-    double4 *los_s = reinterpret_cast<double4 *>(smem + stage_bytes);
-    double2 *row = reinterpret_cast<double2 *>(los_s + 2 * los_stage_n) + (size_t)warp * t.ren2d.n;
-    DIWarpState *ws_all = reinterpret_cast<DIWarpState *>(reinterpret_cast<double2 *>(los_s + 2 * los_stage_n) + (size_t)n_warps * t.ren2d.n);
+    const int n_threads = blockDim.x, n_warps = n_threads >> 5;
+    /* layout: [compact blob prefix][line-of-sight table][tail powers, panel rule][per-warp renormalisation rows][per-warp state] */
+    double2 *los_s = reinterpret_cast<double2 *>(smem + stage_bytes);
+    double *small = reinterpret_cast<double *>(los_s + (size_t)kLosStride * los_stage_n);
+    double2 *rows = reinterpret_cast<double2 *>(small + kDISmallDoubles);
+    double2 *row = rows + (size_t)warp * t.ren2d.n;
+    DIWarpState *ws_all = reinterpret_cast<DIWarpState *>(rows + (size_t)n_warps * t.ren2d.n);
     {
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
-        for (int i = tid; i < stage_bytes / 16; i += kDIThreads) dst[i] = blob[i];
-        for (int i = tid; i < 2 * los_stage_n; i += kDIThreads) los_s[i] = t.los.v[i];
+        for (int i = tid; i < stage_bytes / 16; i += n_threads) dst[i] = blob[i];
+        for (int i = tid; i < kLosStride * los_stage_n; i += n_threads) los_s[i] = t.los.v[i];
+        if (tid < kMaxTail) small[tid] = q.rpow[tid];
+        const int np = q.n_panel_di < 32 ? q.n_panel_di : 32;
+        if (tid < np) {
+            small[kMaxTail + tid] = q.gl_x[rule_offset(q.n_panel_di) + tid];
+            small[kMaxTail + 32 + tid] = q.gl_w[rule_offset(q.n_panel_di) + tid];
+        }
     }
     __syncthreads();
     DIWarpState &ws = ws_all[warp];
     CompactAccess ta;
     ta.t = &t; ta.c.base = smem; ta.c.h = ch;
+    Rules ql = q;
+    ql.rpow = small;
+    if (q.n_panel_di <= 32) { ql.panel_x = small + kMaxTail; ql.panel_w = small + kMaxTail + 32; }
 
     for (;;) {
         unsigned int item = 0;
@@ -280,8 +295,8 @@ __global__ void __launch_bounds__(kDIThreads, 1) di_items_smem_kernel(
         if (lane == 0) ws.k = di_setup(o, ws.e[0], ws.e[1]);
         __syncwarp();
         const DIConst k = ws.k;
-        if (out_evals && lane == 0) out_evals[item] = di_fast_eval_count(q, g, k);
-        double di = di_fast_partial(ta, t, los_s, q, g, k, row, 0, 1, lane, 32);
+        if (out_evals && lane == 0) out_evals[item] = di_fast_eval_count(ql, g, k);
+        double di = di_fast_partial(ta, t, los_s, ql, g, k, row, 0, 1, lane, 32);
         di = warp_sum(di);
         if (lane == 0) out[item] = di;
         __syncwarp();
@@ -411,6 +426,7 @@ Rules make_rules(const coffe_b200_ctx *ctx)
     q.n_outer = ctx->qc.n_outer;
     q.panel_w_mpc = ctx->qc.panel_w; q.panel_du = ctx->qc.panel_du; q.eps_min = ctx->qc.eps_min; q.tail_ratio = ctx->qc.tail_ratio;
     q.panel_w_di = ctx->qc.panel_w_di; q.panel_du_di = ctx->qc.panel_du_di;
+    q.panel_x = q.panel_w = nullptr;
     return q;
 }
 
@@ -464,19 +480,22 @@ int launch_integrated(coffe_b200_ctx *ctx, Batch &b, const int mode, unsigned in
     }
     int stage_n = (int)std::ceil(b.chi_max / ctx->layout.los_h) + 3;
     if (stage_n > ctx->layout.los_n) stage_n = ctx->layout.los_n;
-    const size_t los_bytes = (size_t)2 * stage_n * sizeof(double4);
+    const size_t los_bytes = (size_t)kLosStride * stage_n * sizeof(double2);
     const size_t row_bytes = (size_t)(ctx->layout.has_divergent ? ctx->layout.ren2d_n : 0) * sizeof(double2);
     if (ctx->variant == 1 && ctx->compact.h.valid) {
         /* shared-memory tables: blob prefix covering R <= 2 chi_max, line-of-sight table, per-warp state */
         const int stage_bytes = compact_stage_bytes(ctx->compact, 2.0 * b.chi_max);
         CompactHeader ch = ctx->compact.h;
         ch.n_knots = (stage_bytes - ch.off_knots) / (kKnotStride * 8);
-        const int threads = mode == 1 ? kSIThreads : kDIThreads, warps = threads / 32;
         const int panel_cap = max_panels(ctx->qc);
-        const size_t need = (size_t)stage_bytes + los_bytes +
-                            (mode == 1 ? (size_t)warps * (sizeof(SIWarpState) + (size_t)2 * panel_cap * sizeof(double))
-                                       : (size_t)warps * (sizeof(DIWarpState) + row_bytes));
-        if (need <= (size_t)ctx->smem_optin) {
+        const size_t fixed = (size_t)stage_bytes + los_bytes + (mode == 1 ? 0 : kDISmallDoubles * sizeof(double));
+        const size_t per_warp = mode == 1 ? sizeof(SIWarpState) + (size_t)2 * panel_cap * sizeof(double) : sizeof(DIWarpState) + row_bytes;
+        /* as many warps per SM as the remaining shared memory carries (the kernels are latency-bound: more is faster) */
+        int warps = mode == 1 ? kSIThreads / 32 : kDIThreads / 32;
+        if (mode == 2 && fixed < (size_t)ctx->smem_optin) warps = std::min<int>(warps, (int)(((size_t)ctx->smem_optin - fixed) / per_warp));
+        const int threads = warps * 32;
+        const size_t need = fixed + (size_t)warps * per_warp;
+        if (warps >= 4 && need <= (size_t)ctx->smem_optin) {
             CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int), ctx->stream));
             int grid = std::min(ctx->n_sm, (L.n + warps - 1) / warps);
             if (grid < 1) grid = 1;
@@ -817,7 +836,7 @@ int coffe_b200_upload_tables(coffe_b200_ctx *ctx, const coffe_b200_tables *T)
     ctx->layout = L;
     ctx->t = make_view(L, ctx->d_arena);
     ctx->t_host = make_view(L, ctx->arena.buf.data());
-    los_build_kernel<<<(L.los_n + 127) / 128, 128, 0, ctx->stream>>>(ctx->t, reinterpret_cast<double4 *>(ctx->d_arena + L.los), L.los_n, L.los_h,
+    los_build_kernel<<<(L.los_n + 127) / 128, 128, 0, ctx->stream>>>(ctx->t, reinterpret_cast<double2 *>(ctx->d_arena + L.los), L.los_n, L.los_h,
                                                                      L.chi_max_table);
     CK(cudaGetLastError());
     /* shared-memory tables of the integrated-pieces kernel (absent when the family is not log-spaced: exact-table kernel) */

@@ -18,6 +18,7 @@ struct Rules {
     int n_outer;                    /* 0 = auto_n_outer(sep) */
     double panel_w_mpc, panel_du, eps_min, tail_ratio;
     double panel_w_di, panel_du_di;  /* panel plan of the inner integral of the integrated x integrated piece */
+    const double *panel_x, *panel_w; /* nodes / weights of the n_panel_di rule when staged separately (else null: read from the bank) */
 };
 
 /* panels one ridge_integrate call can hold in its scratch area (engine.cu checks the configured plan) */
@@ -101,7 +102,7 @@ COFFE_HD unsigned int ridge_eval_count(const double hi, const double center, con
 
 template <class TA>
 struct SIFunctor {
-    const TA *t; const SIHalf *h; const Geometry *g; const double4 *los; int los_n; double los_inv_h;
+    const TA *t; const SIHalf *h; const Geometry *g; const double2 *los; int los_n; double los_inv_h;
     COFFE_HD double operator()(const double lambda) const
     {
         return si_half_eval(*t, *h, *g, lambda, los_eval(los, los_n, los_inv_h, lambda));
@@ -111,7 +112,7 @@ struct SIFunctor {
 /* one half of the local x integrated piece, per unit x (the reference integrates x in [0,1], src/signal.c:584-606) */
 template <class TA>
 COFFE_HD double si_half_partial(const TA &t, const LosView &lv, const Rules &q, const Geometry &g, const SIHalf &h,
-                                const double4 *los, const int lane, const int nlanes, double *scratch)
+                                const double2 *los, const int lane, const int nlanes, double *scratch)
 {
     SIFunctor<TA> f{&t, &h, &g, los, lv.n, lv.inv_h};
     const double center = h.cs * g.c;
@@ -126,7 +127,7 @@ COFFE_HD unsigned int si_eval_count(const Rules &q, const Geometry &g, const SIH
 
 template <class TA>
 struct DIFunctor {
-    const TA *t; const DIConst *k; const Geometry *g; const double4 *los; int los_n; double los_inv_h;
+    const TA *t; const DIConst *k; const Geometry *g; const double2 *los; int los_n; double los_inv_h;
     double l1; double4 los1;
     COFFE_HD double operator()(const double l2) const
     {
@@ -137,7 +138,7 @@ struct DIFunctor {
 /* integrated x integrated piece per unit (x1, x2): outer nodes strided over `ngroups` groups of
    `nlanes` lanes (warps of a CTA on the device) */
 template <class TA>
-COFFE_HD double di_partial(const TA &t, const LosView &lv, const Rules &q, const Geometry &g, const DIConst &k, const double4 *los,
+COFFE_HD double di_partial(const TA &t, const LosView &lv, const Rules &q, const Geometry &g, const DIConst &k, const double2 *los,
                            const int group, const int ngroups, const int lane, const int nlanes, double *scratch)
 {
     double acc = 0.0;

@@ -456,7 +456,7 @@ COFFE_HD double4 los_point(const Tables &t, const double lambda)
 /* Hermite knot i of the line-of-sight table (tables.cuh: LosView): values at lambda_i = i h and h d/dlambda from
    fourth-order differences of the same two-level lookup (step h/2: wide enough to average over the kinks of the
    underlying Akima interpolants, which are rough at the 1e-7 level; one-sided at the two ends of the table) */
-COFFE_HD void los_knot(const Tables &t, const int i, const double h, const double chi_max, double4 out[2])
+COFFE_HD void los_knot(const Tables &t, const int i, const double h, const double chi_max, double2 out[kLosStride])
 {
     double lam = i * h;
     if (lam > chi_max) lam = chi_max;
@@ -478,8 +478,9 @@ COFFE_HD void los_knot(const Tables &t, const int i, const double h, const doubl
         dv[3] = sg * (-25 * f0.w + 48 * a1.w - 36 * a2.w + 16 * a3.w - 3 * a4.w) / 12.;
     }
     /* dv = d (df/dlambda); h f' = 2 dv */
-    out[0].x = f0.x; out[0].y = 2 * dv[0]; out[0].z = f0.y; out[0].w = 2 * dv[1];
-    out[1].x = f0.z; out[1].y = 2 * dv[2]; out[1].z = f0.w; out[1].w = 2 * dv[3];
+    out[0].x = f0.x; out[0].y = 2 * dv[0]; out[1].x = f0.y; out[1].y = 2 * dv[1];
+    out[2].x = f0.z; out[2].y = 2 * dv[2]; out[3].x = f0.w; out[3].y = 2 * dv[3];
+    out[4].x = out[4].y = 0.0;
 }
 
 /* ---- flat-sky closed forms for the multipoles ----------------------------------------------------- */

@@ -267,12 +267,24 @@ COFFE_HD void ren_row_fill(const Renorm2DView &t, const double x, const int n_ro
     const double tt = sx - xi, t2 = tt * tt, t3 = t2 * tt;
     const double h00 = 2 * t3 - 3 * t2 + 1, h10 = (t3 - 2 * t2 + tt) * t.dx, h01 = -2 * t3 + 3 * t2, h11 = (t3 - t2) * t.dx;
     const double4 *a = t.nodeT + (size_t)xi * t.n, *b = a + t.n;
-    for (int j = lane; j < n_row; j += nlanes) {
-        const double4 p = a[j], q = b[j];
-        double2 o;
-        o.x = h00 * p.x + h01 * q.x + h10 * p.y + h11 * q.y;
-        o.y = (h00 * p.z + h01 * q.z + h10 * p.w + h11 * q.w) * t.dx;
-        row[j] = o;
+    /* two rows per lane in flight: the loads come from L2 and nothing else can hide their latency here */
+    for (int j0 = lane; j0 < n_row; j0 += 2 * nlanes) {
+        double4 p[2], q[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int j = j0 + u * nlanes;
+            if (j < n_row) { p[u] = a[j]; q[u] = b[j]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int j = j0 + u * nlanes;
+            if (j < n_row) {
+                double2 o;
+                o.x = h00 * p[u].x + h01 * q[u].x + h10 * p[u].y + h11 * q[u].y;
+                o.y = (h00 * p[u].z + h01 * q[u].z + h10 * p[u].w + h11 * q[u].w) * t.dx;
+                row[j] = o;
+            }
+        }
     }
 }
 
@@ -299,28 +311,30 @@ COFFE_HD double ren_row_eval(const Renorm2DView &t, const double2 *row, const in
 /* ---- line-of-sight functions resampled on a uniform lambda grid --------------------------------
    W = D1/a, V = Hc (f-1), U = Hc (Hc-1), Wa = D1 a evaluated through the reference's own two-level
    lookup z = z(lambda) -> spline(z) at n uniformly spaced lambda and stored as cubic Hermite data
-   {f, h f'} per knot: v[2j] = {W, hW', V, hV'}, v[2j+1] = {U, hU', Wa, hWa'}.  These functions are smooth
+   {f, h f'} per knot: v[5j + 0..3] = {W, hW'}, {V, hV'}, {U, hU'}, {Wa, hWa'}, v[5j + 4] = padding (an 80-byte
+   stride puts neighbouring knots on different 16-byte bank groups of shared memory).  These functions are smooth
    on Gpc scales, so with spacing ~18 Mpc the resampling error is ~1e-11 relative (tolerance
    budget; tests/test_physics_cpu.py::test_line_of_sight_resampling_error). */
+static const int kLosStride = 5;     /* double2 per knot */
 struct LosView {
-    const double4 *v;   /* 2 double4 per knot */
+    const double2 *v;   /* kLosStride double2 per knot */
     int n;
     double h, inv_h;
 };
 
-COFFE_HD double4 los_eval(const double4 *v, const int n, const double inv_h, const double lambda)
+COFFE_HD double4 los_eval(const double2 *v, const int n, const double inv_h, const double lambda)
 {
     const double s = lambda * inv_h;
     int j = (int)s;
     if (j < 0) j = 0;
     if (j > n - 2) j = n - 2;
     const HermiteBasis b = hermite_basis(s - j);
-    const double4 a0 = v[2 * j], a1 = v[2 * j + 1], b0 = v[2 * j + 2], b1 = v[2 * j + 3];
+    const double2 *k0 = v + (size_t)kLosStride * j, *k1 = k0 + kLosStride;
     double4 o;
-    o.x = hermite_eval(b, a0.x, a0.y, b0.x, b0.y);
-    o.y = hermite_eval(b, a0.z, a0.w, b0.z, b0.w);
-    o.z = hermite_eval(b, a1.x, a1.y, b1.x, b1.y);
-    o.w = hermite_eval(b, a1.z, a1.w, b1.z, b1.w);
+    { const double2 p = k0[0], q = k1[0]; o.x = hermite_eval(b, p.x, p.y, q.x, q.y); }
+    { const double2 p = k0[1], q = k1[1]; o.y = hermite_eval(b, p.x, p.y, q.x, q.y); }
+    { const double2 p = k0[2], q = k1[2]; o.z = hermite_eval(b, p.x, p.y, q.x, q.y); }
+    { const double2 p = k0[3], q = k1[3]; o.w = hermite_eval(b, p.x, p.y, q.x, q.y); }
     return o;
 }
 

@@ -41,6 +41,7 @@ static void set_rules(HostSim *s)
     q.n_panel_si = s->qc.n_panel_si; q.n_panel_di = s->qc.n_panel_di; q.n_outer = s->qc.n_outer;
     q.panel_w_mpc = s->qc.panel_w; q.panel_du = s->qc.panel_du; q.eps_min = s->qc.eps_min; q.tail_ratio = s->qc.tail_ratio;
     q.panel_w_di = s->qc.panel_w_di; q.panel_du_di = s->qc.panel_du_di;
+    q.panel_x = q.panel_w = nullptr;
 }
 
 extern "C" {
@@ -51,8 +52,8 @@ void *hs_create(const coffe_b200_tables *T, const coffe_b200_options *opt)
     if (!assemble(*T, s->arena, s->layout, s->err)) { fprintf(stderr, "hostsim: %s\n", s->err.c_str()); delete s; return nullptr; }
     s->t = make_view(s->layout, s->arena.buf.data());
     /* line-of-sight table */
-    double4 *los = reinterpret_cast<double4 *>(s->arena.buf.data() + s->layout.los);
-    for (int i = 0; i < s->layout.los_n; ++i) los_knot(s->t, i, s->layout.los_h, s->layout.chi_max_table, los + 2 * i);
+    double2 *los = reinterpret_cast<double2 *>(s->arena.buf.data() + s->layout.los);
+    for (int i = 0; i < s->layout.los_n; ++i) los_knot(s->t, i, s->layout.los_h, s->layout.chi_max_table, los + (size_t)kLosStride * i);
     Options &o = s->o;
     o.den = opt->den; o.rsd = opt->rsd; o.len = opt->len; o.d1 = opt->d1; o.d2 = opt->d2;
     o.g1 = opt->g1; o.g2 = opt->g2; o.g3 = opt->g3; o.g4 = opt->g4; o.g5 = opt->g5;
