@@ -68,6 +68,12 @@ class CovarianceParams(C.Structure):
                 ("cosmic", C.c_int), ("mixed", C.c_int), ("poisson", C.c_int), ("window", C.c_int), ("average", C.c_int)]
 
 
+class IntegralsParams(C.Structure):
+    _fields_ = [("pk_k", dp), ("pk_p", dp), ("n_pk", C.c_int), ("interp_method", C.c_int), ("k_min", C.c_double), ("k_max", C.c_double),
+                ("bessel_bins", C.c_int), ("n", ip), ("l", ip), ("half", ip), ("n_tables", C.c_int), ("divergent", C.c_int),
+                ("chi_max", C.c_double)]
+
+
 def darr(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 

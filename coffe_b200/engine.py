@@ -144,6 +144,33 @@ class Engine:
         self._check(self.lib.coffe_b200_covariance(self._h, C.byref(cp), capi.ptr(out)))
         return out
 
+    # ---- I^n_l tables ---------------------------------------------------------------------------------
+    def integrals(self, pk, k_min, k_max, tables, bessel_bins=10000, divergent=False, chi_max=0.0, interp_method=5):
+        """what coffe_integrals_init builds (src/integrals.c:580-1423), on the device.
+        pk = (k, P) knots; tables = list of (n, l) or (n, l, half).  Returns a dict: r [n_r], tables [n_tables, n_r] and,
+        with divergent, r40, i40, renorm0 (on the knots r40 with r40[0] -> 0), renorm_chi [201], renorm_z [201, 201]
+        with renorm_z[k, j] <-> (chi_j, chi_k); else those are None."""
+        k, p = capi.darr(pk[0]), capi.darr(pk[1])
+        tb = [tuple(t) + (0,) * (3 - len(t)) for t in tables]
+        n_, l_, h_ = capi.iarr([t[0] for t in tb]), capi.iarr([t[1] for t in tb]), capi.iarr([t[2] for t in tb])
+        ip_ = capi.IntegralsParams()
+        ip_.pk_k, ip_.pk_p, ip_.n_pk, ip_.interp_method = capi.ptr(k), capi.ptr(p), len(k), int(interp_method)
+        ip_.k_min, ip_.k_max, ip_.bessel_bins = float(k_min), float(k_max), int(bessel_bins)
+        ip_.n, ip_.l, ip_.half, ip_.n_tables = capi.iptr(n_), capi.iptr(l_), capi.iptr(h_), len(tb)
+        ip_.divergent, ip_.chi_max = int(bool(divergent)), float(chi_max)
+        n_r, n_r40, n_ren = C.c_int(), C.c_int(), C.c_int()
+        self._check(self.lib.coffe_b200_integrals_sizes(C.byref(ip_), C.byref(n_r), C.byref(n_r40), C.byref(n_ren)))
+        r, out = np.zeros(n_r.value), np.zeros((max(len(tb), 1), n_r.value))
+        div = bool(divergent)
+        r40, i40, ren0 = np.zeros(n_r40.value), np.zeros(n_r40.value), np.zeros(n_r40.value)
+        chi, rz = np.zeros(n_ren.value), np.zeros((n_ren.value, n_ren.value))
+        null = C.POINTER(C.c_double)()
+        self._check(self.lib.coffe_b200_integrals(self._h, C.byref(ip_), capi.ptr(r), capi.ptr(out),
+                                                  capi.ptr(r40) if div else null, capi.ptr(i40) if div else null, capi.ptr(ren0) if div else null,
+                                                  capi.ptr(chi) if div else null, capi.ptr(rz) if div else null))
+        return {"r": r, "tables": out[:len(tb)], "r40": r40 if div else None, "i40": i40 if div else None, "renorm0": ren0 if div else None,
+                "renorm_chi": chi if div else None, "renorm_z": rz if div else None}
+
     # ---- prepared computations (inputs resident in HBM) -----------------------------------------------
     def plan_multipoles(self, z_mean, sep, l, begin=0, end=None):
         z, s, ls = capi.darr(z_mean), capi.darr(sep), capi.iarr(l)

@@ -169,6 +169,36 @@ typedef struct coffe_b200_covariance_params {
    tables; covariance_integration_method = standard */
 int coffe_b200_covariance(coffe_b200_ctx *ctx, const coffe_b200_covariance_params *p, double *out);
 
+/* ---- I^n_l tables ----------------------------------------------------------------------------------
+   What coffe_integrals_init builds (src/integrals.c:580-1423): for every requested (n, l) the table of
+   r^(n-l) I^n_l(r) (plain I^n_l(r) when n < l) on the knots r = 0, the reference's 42 separations below 1 Mpc
+   (src/integrals.c:111-126) and the 2-FAST grid r_i = (k_max/k_min)^(i/N), i < N = bessel_bins (src/twofast.c:
+   362-483); with `divergent`, also r^4 I^4_0 and the zero-separation renormalisation (which the reference also
+   stores multiplied by r^4, src/integrals.c:365-371, 816-827) on the reference's 297 knots
+   (src/integrals.c:76-96, 797-849) and the 201 x 201 grid renormalisation(chi_j, chi_k), chi_j = j chi_max / 200
+   (src/integrals.c:851-907).  The driver wraps the arrays into coffe_init_spline / coffe_init_spline2d. */
+typedef struct coffe_b200_integrals_params {
+    const double *pk_k, *pk_p;   /* knots of par->power_spectrum_norm (k [1/Mpc], P [Mpc^3]) */
+    int n_pk;
+    int interp_method;           /* par->interp_method: interpolation of P(k) inside the k-integrals (2-FAST always
+                                    uses the natural cubic spline, src/twofast.c:399) */
+    double k_min, k_max;         /* par->k_min_norm, par->k_max_norm */
+    int bessel_bins;             /* par->bessel_bins; even, prime factors 2, 3, 5 */
+    const int *n, *l;            /* n_tables (n, l) pairs as stored in coffe_integral_t */
+    const int *half;             /* per table: state_n = state_l = COFFE_HALF_INTEGER (may be NULL: all integer) */
+    int n_tables;
+    int divergent;               /* par->divergent */
+    double chi_max;              /* end of the renormalisation grid: chi(max(z_mean + deltaz)), src/integrals.c:858-871 */
+} coffe_b200_integrals_params;
+
+/* array sizes: knots per table, knots of I^4_0, knots per axis of the renormalisation grid */
+int coffe_b200_integrals_sizes(const coffe_b200_integrals_params *p, int *n_r, int *n_r40, int *n_renorm);
+/* r[n_r]; tables[t*n_r + i]; r40[n_r40], i40[n_r40]; renorm0[n_r40] (its knots are r40 with r40[0] replaced by 0);
+   renorm_chi[n_renorm]; renorm_z[k*n_renorm + j] <-> (chi_j, chi_k).  The divergent outputs may be NULL when
+   p->divergent == 0. */
+int coffe_b200_integrals(coffe_b200_ctx *ctx, const coffe_b200_integrals_params *p, double *r, double *tables,
+                         double *r40, double *i40, double *renorm0, double *renorm_chi, double *renorm_z);
+
 /* device time of the kernels of the last compute call [ms] and their launch count (bench / roofline) */
 int coffe_b200_last_timing(const coffe_b200_ctx *ctx, double *kernel_ms, int *n_launches);
 
