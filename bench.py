@@ -11,9 +11,12 @@ GPUs as contiguous blocks of (z, r) work items (no data-path collective; one NCC
            CUDA events on the launching stream, max over ranks)
   e2e    : points/s through the reference-facing C ABI call coffe_b200_multipoles_range with HOST
            buffers: item construction, host->device copies and the device->host copy inside the timed region
-  roofline: FP64; achieved = canonical algorithmic flops (F_NI=700, F_SI=1000, F_DI=450 per
-           integrand evaluation x the evaluations the kernels perform) / device time; peak = the DFMA probe
-           kernel measured on the same device in the same run
+  roofline: FP64, for the dominant kernel di_items_smem_kernel (integrated x integrated piece, ~88 % of the step):
+           achieved = canonical algorithmic flops (F_DI = 450 per integrand evaluation x the
+           evaluations one launch performs) / that kernel's launch duration (CUDA events on its stream, averaged
+           over the timed steps); peak = the DFMA probe kernel measured on the same device in the same run;
+           `step` repeats the accounting for the whole step (NI 700, SI 1000, DI 450 flop per evaluation)
+  covariance: cfg4 (4 z x (3 x 100)^2 entries, flat-sky Gaussian covariance with shot noise) entries/s, rank 0
   cpu_baseline: the reference's own code (oracle/_ref, -O3 -ffast-math like its wheels) on a bounded sample
 
 With --impl reference the reference's CPU implementation is timed instead (rank 0 only).
@@ -116,7 +119,7 @@ def reference_arm(args, z, sep, ls, rank):
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline(z, sep, ls, budget_points=12):
+def cpu_baseline(z, sep, ls, budget_points=72):
     from oracle import coffe_oracle as O
     if not O.available(fast=True) and not O.available():
         return None
@@ -139,6 +142,35 @@ def cpu_baseline(z, sep, ls, budget_points=12):
                       f"reference sources built -O3{' -ffast-math' if fast else ''} -fopenmp, tables prebuilt"}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one di_items_smem_kernel launch, ncu --set full capture of the
+# 2 z x 120 r sample (profiles/r1_di_kernel_v32_summary.txt): the tables are L2-resident, the kernel does not stream HBM
+TRAFFIC_NOTE = {"bytes_per_launch": 1.88e6, "captured_on": "2 z x 120 r sample, ncu --set full", "algorithmic_table_bytes": 2.6e6}
+
+
+def covariance_cfg4(eng, args):
+    """cfg4 of BASELINE.json: flat-sky Gaussian covariance of l = 0, 2, 4, 4 z-bins, 100 x 100 separation blocks,
+    density + RSD with shot noise.  Host buffers in and out (the C ABI call)."""
+    import coffe_b200
+    k, pk = np.loadtxt(Path(coffe_b200.__file__).resolve().parent / "data" / "PkL_CLASS.dat", unpack=True)
+    k, pk = k * H, pk / H ** 3
+    zc = [0.6, 1.0, 1.4, 1.8]
+    sepc = np.linspace(20.0, 218.0, 100) / H
+    eng.set_options(("den", "rsd"))
+    kw = dict(z_mean=zc, deltaz=[0.1] * 4, window=False)
+    argsc = ((k, pk), sepc, [0, 2, 4], [0.2] * 4, [1e-3 * H ** 3] * 4, [1e-3 * H ** 3] * 4, [2.0 / H] * 4)
+    eng.covariance(*argsc, **kw)
+    t0 = time.perf_counter()
+    n_rep = 3
+    for _ in range(n_rep):
+        out = eng.covariance(*argsc, **kw)
+    dt = (time.perf_counter() - t0) / n_rep
+    ms, launches = eng.last_timing()
+    eng.set_options(ALL)
+    assert np.all(np.isfinite(out)) and out.shape == (4, 3, 100, 3, 100)
+    return {"value": out.size / dt, "unit": "entries/s", "entries": int(out.size), "wall_ms": dt * 1e3, "kernel_ms": ms, "gpu_launches": launches,
+            "workload": "cfg4: 4 z x (3 x 100)^2, den + rsd, cosmic + mixed + Poisson, unbinned, covariance_integration_method = standard"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -149,6 +181,7 @@ def main():
     ap.add_argument("--nsep", type=int, default=1000)
     ap.add_argument("--sample-points", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-covariance", action="store_true")
     ap.add_argument("--variant", type=int, default=-1, help="items kernel variant (experiments; default = library default)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -194,16 +227,19 @@ def main():
     with ClockSampler(local) as clocks:
         t0 = time.perf_counter()
         dev_ms = 0.0
+        si_ms = di_ms = 0.0
         for _ in range(args.steps):
             dev_ms += plan.execute()           # CUDA events on the launching stream, synchronised each step
+            a, b = eng.last_kernel_times()
+            si_ms += a; di_ms += b
         barrier()
         wall = time.perf_counter() - t0
     launches = eng.last_timing()[1] * args.steps
     res_local = plan.fetch()
-    t_dev = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
+    t_dev = torch.tensor([dev_ms, wall * 1e3, si_ms, di_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    dev_ms_max, wall_ms_max = t_dev.tolist()
+    dev_ms_max, wall_ms_max, si_ms_max, di_ms_max = t_dev.tolist()
     n_work, n_ni, n_si, n_di = plan.count()
     cnt = torch.tensor([n_work, n_ni, n_si, n_di, launches], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -227,8 +263,9 @@ def main():
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_s = t_e.item()
-    # bytes per step crossing PCIe: z/sep grids + (point, mu, weight) items in; per-point pieces out
-    h2d = int((end - begin) * 16 + n_work / world * 20 + (end - begin + 1) * 4)
+    # bytes per step crossing PCIe: per point z, sep, rule index and the two item offsets; per separation the two mu rules
+    # (nodes + weights; the (point, mu, weight) items themselves are expanded on the device); per-point pieces out
+    h2d = int((end - begin) * 28 + n_work / max(len(z), 1) * 16 + (len(sep) + 1) * 8)
     d2h = int((end - begin) * 3 * len(ls) * 8)
 
     peak_tf = eng.fp64_peak_tflops()
@@ -236,9 +273,17 @@ def main():
         assert np.all(np.isfinite(full)) and full.shape == (len(ls), n_items)
         assert np.array_equal(out, res_local), "C-ABI call and prepared plan must agree bit for bit"
         flops_per_step = F_NI * n_ni + F_SI * n_si + F_DI * n_di
-        # dominant kernel: integrated_items_kernel (>99% of the device time, profiles/); per launch = per step and rank
-        achieved = flops_per_step / world / (dev_ms_max / args.steps * 1e-3) / 1e12
+        achieved_step = flops_per_step / world / (dev_ms_max / args.steps * 1e-3) / 1e12
+        # dominant kernel: di_items_smem_kernel, one launch per step and rank
+        di_launch_ms = di_ms_max / args.steps
+        achieved = F_DI * n_di / world / (di_launch_ms * 1e-3) / 1e12 if di_launch_ms > 0 else None
         value = n_pts_total * args.steps / (dev_ms_max * 1e-3)
+        cov = None
+        if not args.no_covariance:
+            try:
+                cov = covariance_cfg4(eng, args)
+            except Exception as e:
+                cov = {"value": None, "unit": "entries/s", "error": str(e)}
         line = {
             "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -249,12 +294,18 @@ def main():
                        "sharding": f"contiguous blocks of (z, r) items over {world} GPU(s), tables replicated, one NCCL gather",
                        "l2_policy": "compute-bound FP64 kernel; working set (tables 2.6 MB) is L2-resident by design, no HBM streaming to flush",
                        "quadrature": eng.get_quadrature(), "wall_ms_per_step": wall_ms_max / args.steps},
-            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
-                         "traffic": None, "peak_source": "DFMA probe kernel measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                         "flops_per_launch": flops_per_step / world, "accounting": "SURVEY.md 8d: 700/1000/450 flop per NI/SI/DI integrand evaluation"},
+            "roofline": {"bound": "fp64", "kernel": "di_items_smem_kernel", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved / peak_tf if peak_tf and achieved else None,
+                         "traffic": TRAFFIC_NOTE, "peak_source": "DFMA probe kernel measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                         "launch_ms": di_launch_ms, "share_of_step": di_ms_max / dev_ms_max if dev_ms_max else None,
+                         "flops_per_launch": F_DI * n_di / world, "accounting": "SURVEY.md 8d: 450 flop per DI integrand evaluation",
+                         "step": {"achieved": achieved_step, "frac": achieved_step / peak_tf if peak_tf else None, "flops": flops_per_step / world,
+                                  "si_kernel_ms": si_ms_max / args.steps, "accounting": "700/1000/450 flop per NI/SI/DI evaluation"}},
             "e2e": {"value": n_pts_total * args.steps / e2e_s, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks.summary(),
         }
+        if cov is not None:
+            line["covariance"] = cov
         if not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(z, sep, ls)

@@ -17,6 +17,8 @@ struct coffe_b200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_k[4] = {nullptr, nullptr, nullptr, nullptr};   /* around the local x integrated / integrated x integrated kernels */
+    bool have_kernel_times = false;
     std::string err;
     /* tables */
     bool have_tables = false;

@@ -548,10 +548,15 @@ int run_multipole_batch(coffe_b200_ctx *ctx, Batch &b, const LList &ls, const bo
         CK(cudaGetLastError());
         ctx->last_launches += 1;
     }
+    CK(cudaEventRecord(ctx->ev_k[0], ctx->stream));
     int rc = launch_integrated(ctx, b, 1);
     if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev_k[1], ctx->stream));
+    CK(cudaEventRecord(ctx->ev_k[2], ctx->stream));
     rc = launch_integrated(ctx, b, 2);
     if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev_k[3], ctx->stream));
+    ctx->have_kernel_times = true;
     const int blocks = (b.n_points * 32 + 127) / 128;
     reduce_multipoles_kernel<<<blocks, 128, 0, ctx->stream>>>(b.n_points, b.si.begin.p, b.si.mu.p, b.si.w.p, b.si.val.p,
                                                               b.di.begin.p, b.di.mu.p, b.di.w.p, b.di.val.p,
@@ -777,6 +782,8 @@ int coffe_b200_create(int device, coffe_b200_ctx **out)
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return fail("cudaEventCreate", e);
+    for (int i = 0; i < 4; ++i)
+        if ((e = cudaEventCreate(&ctx->ev_k[i])) != cudaSuccess) return fail("cudaEventCreate", e);
     std::vector<double> bx, bw;
     build_rule_bank(bx, bw);
     if ((e = cudaMalloc(&ctx->d_gl_x, bx.size() * sizeof(double))) != cudaSuccess) return fail("cudaMalloc", e);
@@ -813,6 +820,8 @@ void coffe_b200_destroy(coffe_b200_ctx *ctx)
     if (ctx->d_blob) cudaFree(ctx->d_blob);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (int i = 0; i < 4; ++i)
+        if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1110,6 +1119,23 @@ int coffe_b200_last_timing(const coffe_b200_ctx *ctx, double *kernel_ms, int *n_
     if (!ctx) return COFFE_B200_EINVAL;
     if (kernel_ms) *kernel_ms = ctx->last_ms;
     if (n_launches) *n_launches = ctx->last_launches;
+    return COFFE_B200_OK;
+}
+
+int coffe_b200_last_kernel_times(coffe_b200_ctx *ctx, double *si_ms, double *di_ms)
+{
+    if (!ctx) return COFFE_B200_EINVAL;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (si_ms) *si_ms = 0.0;
+    if (di_ms) *di_ms = 0.0;
+    if (!ctx->have_kernel_times) return COFFE_B200_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float a = 0, b = 0;
+    CK(cudaEventElapsedTime(&a, ctx->ev_k[0], ctx->ev_k[1]));
+    CK(cudaEventElapsedTime(&b, ctx->ev_k[2], ctx->ev_k[3]));
+    if (si_ms) *si_ms = a;
+    if (di_ms) *di_ms = b;
     return COFFE_B200_OK;
 }
 

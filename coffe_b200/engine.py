@@ -75,6 +75,12 @@ class Engine:
         self._check(self.lib.coffe_b200_last_timing(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def last_kernel_times(self):
+        """(local x integrated, integrated x integrated) kernel times of the last multipole computation [ms]"""
+        a, b = C.c_double(), C.c_double()
+        self._check(self.lib.coffe_b200_last_kernel_times(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     # ---- signal -------------------------------------------------------------------------------------
     def multipoles(self, z_mean, sep, l):
         z, s, ls = capi.darr(z_mean), capi.darr(sep), capi.iarr(l)

@@ -202,6 +202,11 @@ int coffe_b200_integrals(coffe_b200_ctx *ctx, const coffe_b200_integrals_params 
 /* device time of the kernels of the last compute call [ms] and their launch count (bench / roofline) */
 int coffe_b200_last_timing(const coffe_b200_ctx *ctx, double *kernel_ms, int *n_launches);
 
+/* device time [ms] of the two line-of-sight kernels of the last multipole computation, CUDA events on the launching
+   stream: local x integrated (si_items_smem_kernel) and integrated x integrated (di_items_smem_kernel, the dominant
+   kernel: roofline numerator of bench.py) */
+int coffe_b200_last_kernel_times(coffe_b200_ctx *ctx, double *si_ms, double *di_ms);
+
 /* ---- prepared computations ------------------------------------------------------------------------
    coffe_b200_plan_multipoles uploads the grid and its quadrature items for the (iz, ir) items
    [item_begin, item_end) once; coffe_b200_plan_execute then only launches kernels on inputs that are
