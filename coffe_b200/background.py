@@ -13,7 +13,7 @@ reference integrates linear interpolants of it numerically), chi(z) is a cumulat
 (src/background.c:192-211) is integrated ONCE from a = 0.05, (D, D') = (0.05, 1) with a fixed-step classical
 Runge-Kutta on a fine grid in ln a instead of an adaptive RK2 restarted for every knot (its 1e-6 step control is the
 largest difference between the two: ~1e-6 relative in D1 and f, pinned by tests/test_coffe_class.py against the
-reference's own golden background file and the oracle).
+reference's own golden background file and its compiled sources).
 """
 import numpy as np
 

@@ -21,7 +21,7 @@ inline QuadConfig default_quadrature()
     q.n_outer = 0;
     q.n_panel_si = 8; q.n_panel_di = 8;
     q.n_z = 8;
-    q.panel_w = 16.0; q.panel_du = 320.0; q.eps_min = 1e-3; q.tail_ratio = 1.5;
+    q.panel_w = 64.0; q.panel_du = 128.0; q.eps_min = 1e-3; q.tail_ratio = 1.5;
     q.n_mu_panel_di = 5; q.panel_w_di = 64.0; q.panel_du_di = 128.0;
     return q;
 }

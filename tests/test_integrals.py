@@ -128,10 +128,10 @@ def test_half_integer_and_flatsky_tables(ref):
         if key == (1, -1, 1):
             got *= np.sqrt(2.0 / np.pi) * 2 * np.pi ** 2          # src/integrals.c:955-961
         scale = np.maximum(np.abs(y), 1e-6 * np.max(np.abs(y)))
-        # (1, 0) and the half-integer (1, -1): the first Gamma argument of M_ql has real part (l + q)/2 = 0.475 < 0.5, where the reference's Lanczos
+        # (1, 0) and every half-integer table (l + q = 0.95): the first Gamma argument of M_ql has real part (l + q)/2 = 0.475 < 0.5, where the reference's Lanczos
         # lgamma goes through the reflection formula log(pi) - clog(csin(pi z)) in double complex (src/twofast.c:112-114);
         # csin overflows for |Im z| > ~226, which silently drops the upper ~2/3 of the Fourier modes of that one table.
         # The device code evaluates lgamma by recurrence + Stirling and keeps them: 4e-6 / 5e-5 of the tables' scale.
-        tol = 1e-4 if key in ((1, 0, 0), (1, -1, 1)) else 1e-8
+        tol = 1e-4 if key == (1, 0, 0) or key[2] else 1e-8
         assert np.max(np.abs(got[43:] - y[43:]) / scale[43:]) < tol, key
         assert np.max(np.abs(got[:43] - y[:43]) / np.maximum(np.abs(y[:43]), 1e-3 * np.max(np.abs(y[:43])))) < 3e-5, key
