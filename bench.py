@@ -87,6 +87,9 @@ def reference_arm(args, z, sep, ls, rank):
     """the reference's own CPU implementation (oracle/_ref, fast build) on a bounded sample of the workload"""
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference's OpenMP path gets all the host cores it can use
+    if "LOCAL_RANK" in os.environ:
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     from oracle import coffe_oracle as O
     fast = O.available(fast=True)
     ref = O.RefCoffe(fast=fast)
