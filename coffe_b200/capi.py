@@ -57,7 +57,8 @@ class Quadrature(C.Structure):
                 ("n_outer", C.c_int), ("n_panel_si", C.c_int), ("n_panel_di", C.c_int), ("n_z", C.c_int),
                 ("panel_width", C.c_double), ("panel_uniform_extent", C.c_double), ("eps_min", C.c_double),
                 ("tail_ratio", C.c_double),
-                ("n_mu_panel_di", C.c_int), ("panel_width_di", C.c_double), ("panel_uniform_extent_di", C.c_double)]
+                ("n_mu_panel_di", C.c_int), ("panel_width_di", C.c_double), ("panel_uniform_extent_di", C.c_double),
+                ("mu_panel_width_di", C.c_double)]
 
 
 class CovarianceParams(C.Structure):

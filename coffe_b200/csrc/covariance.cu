@@ -293,7 +293,7 @@ double legendre_integral(const int n, const int m, const int a, const int b)
 extern "C" int coffe_b200_covariance(coffe_b200_ctx *ctx, const coffe_b200_covariance_params *p, double *out)
 {
     if (!ctx || !p || !out) return COFFE_B200_EINVAL;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    COFFE_ENTER(ctx);
     if (!ctx->have_tables) { ctx->err = "no tables uploaded (the covariance needs the background and galaxy bias tables)"; return COFFE_B200_ENOTABLES; }
     ctx->last_ms = 0; ctx->last_launches = 0;
     const int n_l = p->n_l, n_sep = p->n_sep, n_bins = p->n_bins;

@@ -54,25 +54,50 @@ struct coffe_b200_ctx {
         }                                                                                            \
     } while (0)
 
+/* Device buffers of a call come from the stream-ordered allocator (cudaMallocAsync on the context's stream, pool kept
+   warm: release threshold = max), so a compute call does not pay cudaMalloc / cudaFree (and their device-wide
+   synchronisation) for its ~20 transient arrays.  The stream is published per thread by AllocScope at every entry point. */
+inline cudaStream_t &tls_alloc_stream()
+{
+    static thread_local cudaStream_t s = nullptr;
+    return s;
+}
+
+struct AllocScope {
+    cudaStream_t prev;
+    explicit AllocScope(cudaStream_t s) : prev(tls_alloc_stream()) { tls_alloc_stream() = s; }
+    ~AllocScope() { tls_alloc_stream() = prev; }
+};
+
+#define COFFE_ENTER(c) std::lock_guard<std::mutex> lock((c)->mu); AllocScope alloc_scope_((c)->stream)
+
 template <class T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
+    cudaStream_t s = nullptr;       /* stream the buffer was allocated on (null: plain cudaMalloc) */
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
-    ~DevBuf() { if (p) cudaFree(p); }
+    ~DevBuf() { release(); }
+    void release()
+    {
+        if (p) { if (s) cudaFreeAsync(p, s); else cudaFree(p); }
+        p = nullptr; n = 0;
+    }
     cudaError_t alloc(size_t count)
     {
-        if (p) { cudaFree(p); p = nullptr; }
+        release();
         n = count;
-        return cudaMalloc(&p, (count ? count : 1) * sizeof(T));
+        s = tls_alloc_stream();
+        const size_t bytes = (count ? count : 1) * sizeof(T);
+        return s ? cudaMallocAsync(reinterpret_cast<void **>(&p), bytes, s) : cudaMalloc(reinterpret_cast<void **>(&p), bytes);
     }
-    cudaError_t upload(const std::vector<T> &v, cudaStream_t s)
+    cudaError_t upload(const std::vector<T> &v, cudaStream_t stream)
     {
         cudaError_t e = alloc(v.size());
         if (e != cudaSuccess) return e;
         if (v.empty()) return cudaSuccess;
-        return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+        return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, stream);
     }
 };

@@ -581,7 +581,7 @@ int run_multipole_batch(coffe_b200_ctx *ctx, Batch &b, const LList &ls, const bo
    rule per distinct separation (`sep`, n_sep entries; point p uses rule point_rule[p]) and uploads those; the
    (point, mu, weight) items are expanded on the device. */
 int build_item_list(coffe_b200_ctx *ctx, const double *sep, const int n_sep, const std::vector<int> &point_rule, const DevBuf<int> &d_point_rule,
-                    const int n_per_panel, const bool active, ItemList &L)
+                    const int n_per_panel, const double mu_panel_width, const bool active, ItemList &L)
 {
     const int n = (int)point_rule.size();
     std::vector<int> rule_begin(n_sep + 1, 0), point_begin(n + 1, 0);
@@ -589,7 +589,7 @@ int build_item_list(coffe_b200_ctx *ctx, const double *sep, const int n_sep, con
     for (int r = 0; r < n_sep; ++r) {
         rule_begin[r] = (int)rule_mu.size();
         if (!active) continue;
-        build_mu_rule(ctx->qc, sep[r], mu, w, n_per_panel);
+        build_mu_rule(ctx->qc, sep[r], mu, w, n_per_panel, mu_panel_width);
         rule_mu.insert(rule_mu.end(), mu.begin(), mu.end());
         rule_w.insert(rule_w.end(), w.begin(), w.end());
     }
@@ -614,7 +614,7 @@ int build_item_list(coffe_b200_ctx *ctx, const double *sep, const int n_sep, con
                                                                    L.point.p, L.mu.p, L.w.p);
         CK(cudaGetLastError());
     }
-    CK(cudaStreamSynchronize(ctx->stream));       /* the staging buffers above go out of scope */
+    /* the staging buffers above are freed in stream order (cudaFreeAsync) when they go out of scope */
     return COFFE_B200_OK;
 }
 
@@ -624,9 +624,9 @@ int build_multipole_batch(coffe_b200_ctx *ctx, const double *sep, const int n_se
     b.n_points = (int)point_rule.size();
     DevBuf<int> d_point_rule;
     CK(d_point_rule.upload(point_rule, ctx->stream));
-    int rc = build_item_list(ctx, sep, n_sep, point_rule, d_point_rule, ctx->qc.n_mu_panel, opt_has_si(ctx->o), b.si);
+    int rc = build_item_list(ctx, sep, n_sep, point_rule, d_point_rule, ctx->qc.n_mu_panel, ctx->qc.mu_panel_w, opt_has_si(ctx->o), b.si);
     if (rc) return rc;
-    return build_item_list(ctx, sep, n_sep, point_rule, d_point_rule, ctx->qc.n_mu_panel_di, opt_has_integrated(ctx->o), b.di);
+    return build_item_list(ctx, sep, n_sep, point_rule, d_point_rule, ctx->qc.n_mu_panel_di, ctx->qc.mu_panel_w_di, opt_has_integrated(ctx->o), b.di);
 }
 
 int check_finite(coffe_b200_ctx *ctx, const double *v, const size_t n)
@@ -802,6 +802,14 @@ int coffe_b200_create(int device, coffe_b200_ctx **out)
         if ((e = cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device)) != cudaSuccess) return fail("cudaDeviceGetAttribute", e);
         ctx->smem_optin = v;
     }
+    {
+        /* keep the stream-ordered pool warm between calls */
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     std::memset(&ctx->o, 0, sizeof(ctx->o));
     ctx->o.den = 1;
     *out = ctx;
@@ -831,7 +839,7 @@ const char *coffe_b200_last_error(const coffe_b200_ctx *ctx) { return ctx ? ctx-
 int coffe_b200_upload_tables(coffe_b200_ctx *ctx, const coffe_b200_tables *T)
 {
     if (!ctx || !T) return COFFE_B200_EINVAL;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    COFFE_ENTER(ctx);
     Arena A;
     Layout L;
     if (!assemble(*T, A, L, ctx->err)) return COFFE_B200_EINVAL;
@@ -871,7 +879,7 @@ int coffe_b200_upload_tables(coffe_b200_ctx *ctx, const coffe_b200_tables *T)
 int coffe_b200_set_options(coffe_b200_ctx *ctx, const coffe_b200_options *opt)
 {
     if (!ctx || !opt) return COFFE_B200_EINVAL;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    COFFE_ENTER(ctx);
     Options &o = ctx->o;
     o.den = opt->den != 0; o.rsd = opt->rsd != 0; o.len = opt->len != 0; o.d1 = opt->d1 != 0; o.d2 = opt->d2 != 0;
     o.g1 = opt->g1 != 0; o.g2 = opt->g2 != 0; o.g3 = opt->g3 != 0; o.g4 = opt->g4 != 0; o.g5 = opt->g5 != 0;
@@ -885,7 +893,7 @@ int coffe_b200_set_options(coffe_b200_ctx *ctx, const coffe_b200_options *opt)
 int coffe_b200_set_quadrature(coffe_b200_ctx *ctx, const coffe_b200_quadrature *q)
 {
     if (!ctx || !q) return COFFE_B200_EINVAL;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    COFFE_ENTER(ctx);
     const QuadConfig merged = merge_quadrature(default_quadrature(), *q);
     if (!quadrature_valid(merged, kMaxPanels)) {
         ctx->err = "quadrature sizes out of range (node counts 2..128; the line-of-sight panel plan must fit " + std::to_string(kMaxPanels) + " panels)";
@@ -903,7 +911,7 @@ int coffe_b200_set_quadrature(coffe_b200_ctx *ctx, const coffe_b200_quadrature *
 int coffe_b200_set_kernel_variant(coffe_b200_ctx *ctx, int variant)
 {
     if (!ctx || (variant != 0 && variant != 1)) return COFFE_B200_EINVAL;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    COFFE_ENTER(ctx);
     ctx->variant = variant;
     return COFFE_B200_OK;
 }
@@ -926,6 +934,7 @@ int coffe_b200_get_quadrature(const coffe_b200_ctx *ctx, coffe_b200_quadrature *
     q->mu_uniform_extent = c.mu_du; q->n_outer = c.n_outer; q->n_panel_si = c.n_panel_si; q->n_panel_di = c.n_panel_di;
     q->n_z = c.n_z; q->panel_width = c.panel_w; q->panel_uniform_extent = c.panel_du; q->eps_min = c.eps_min; q->tail_ratio = c.tail_ratio;
     q->n_mu_panel_di = c.n_mu_panel_di; q->panel_width_di = c.panel_w_di; q->panel_uniform_extent_di = c.panel_du_di;
+    q->mu_panel_width_di = c.mu_panel_w_di;
     return COFFE_B200_OK;
 }
 
@@ -933,7 +942,7 @@ int coffe_b200_multipoles_pieces(coffe_b200_ctx *ctx, const double *z_mean, int 
                                  const int *l, int n_l, double *out)
 {
     if (!ctx || !out) return COFFE_B200_EINVAL;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    COFFE_ENTER(ctx);
     std::vector<double> hm;
     const int rc = multipoles_core(ctx, z_mean, n_z, sep, n_sep, l, n_l, 0, (long)n_z * n_sep, hm);
     if (rc) return rc;
@@ -949,7 +958,7 @@ int coffe_b200_multipoles_range(coffe_b200_ctx *ctx, const double *z_mean, int n
                                 const int *l, int n_l, long item_begin, long item_end, double *out)
 {
     if (!ctx || !out) return COFFE_B200_EINVAL;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    COFFE_ENTER(ctx);
     std::vector<double> hm;
     const int rc = multipoles_core(ctx, z_mean, n_z, sep, n_sep, l, n_l, item_begin, item_end, hm);
     if (rc) return rc;
@@ -964,7 +973,7 @@ int coffe_b200_multipoles(coffe_b200_ctx *ctx, const double *z_mean, int n_z, co
                           const int *l, int n_l, double *out)
 {
     if (!ctx || !out) return COFFE_B200_EINVAL;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    COFFE_ENTER(ctx);
     std::vector<double> hm;
     const int rc = multipoles_core(ctx, z_mean, n_z, sep, n_sep, l, n_l, 0, (long)n_z * n_sep, hm);
     if (rc) return rc;
@@ -981,7 +990,7 @@ int coffe_b200_corrfunc(coffe_b200_ctx *ctx, const double *z_mean, int n_z, cons
                         const double *sep, int n_sep, double *out)
 {
     if (!ctx || !out) return COFFE_B200_EINVAL;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    COFFE_ENTER(ctx);
     if (!ctx->have_tables || !ctx->layout.has_ifam) { ctx->err = "no tables uploaded (the signal needs the I^n_l family)"; return COFFE_B200_ENOTABLES; }
     if (!z_mean || !sep || !mu || n_z < 0 || n_sep < 0 || n_mu < 0) { ctx->err = "bad grid arguments"; return COFFE_B200_EINVAL; }
     ctx->last_ms = 0; ctx->last_launches = 0;
@@ -1047,7 +1056,7 @@ int coffe_b200_average_multipoles(coffe_b200_ctx *ctx, const double *z_min, cons
                                   const double *sep, int n_sep, const int *l, int n_l, double *out)
 {
     if (!ctx || !out) return COFFE_B200_EINVAL;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    COFFE_ENTER(ctx);
     if (!ctx->have_tables || !ctx->layout.has_ifam) { ctx->err = "no tables uploaded (the signal needs the I^n_l family)"; return COFFE_B200_ENOTABLES; }
     if (!z_min || !z_max || !sep || n_bins < 0 || n_sep < 0) { ctx->err = "bad grid arguments"; return COFFE_B200_EINVAL; }
     int rc = check_l(ctx, l, n_l);
@@ -1125,7 +1134,7 @@ int coffe_b200_last_timing(const coffe_b200_ctx *ctx, double *kernel_ms, int *n_
 int coffe_b200_last_kernel_times(coffe_b200_ctx *ctx, double *si_ms, double *di_ms)
 {
     if (!ctx) return COFFE_B200_EINVAL;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    COFFE_ENTER(ctx);
     if (si_ms) *si_ms = 0.0;
     if (di_ms) *di_ms = 0.0;
     if (!ctx->have_kernel_times) return COFFE_B200_OK;
@@ -1145,7 +1154,7 @@ int coffe_b200_plan_multipoles(coffe_b200_ctx *ctx, const double *z_mean, int n_
 {
     if (!ctx || !out) return COFFE_B200_EINVAL;
     *out = nullptr;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    COFFE_ENTER(ctx);
     coffe_b200_plan *pl = new coffe_b200_plan();
     const int rc = plan_build(ctx, z_mean, n_z, sep, n_sep, l, n_l, item_begin, item_end, *pl);
     if (rc) { delete pl; return rc; }
@@ -1157,7 +1166,7 @@ int coffe_b200_plan_multipoles(coffe_b200_ctx *ctx, const double *z_mean, int n_
 int coffe_b200_plan_execute(coffe_b200_plan *plan, double *kernel_ms)
 {
     if (!plan) return COFFE_B200_EINVAL;
-    std::lock_guard<std::mutex> lock(plan->ctx->mu);
+    COFFE_ENTER(plan->ctx);
     int rc = plan_run(*plan);
     if (rc) return rc;
     rc = plan_sync(*plan);
@@ -1168,7 +1177,7 @@ int coffe_b200_plan_execute(coffe_b200_plan *plan, double *kernel_ms)
 int coffe_b200_plan_fetch(coffe_b200_plan *plan, double *out)
 {
     if (!plan || !out) return COFFE_B200_EINVAL;
-    std::lock_guard<std::mutex> lock(plan->ctx->mu);
+    COFFE_ENTER(plan->ctx);
     std::vector<double> hm;
     const int rc = plan_fetch(*plan, hm);
     if (rc) return rc;
@@ -1184,7 +1193,7 @@ int coffe_b200_plan_count(coffe_b200_plan *plan, double *n_items, double *n_ni_e
 {
     if (!plan) return COFFE_B200_EINVAL;
     coffe_b200_ctx *ctx = plan->ctx;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    COFFE_ENTER(ctx);
     Batch &b = plan->b;
     double si = 0, di = 0;
     if (opt_has_integrated(ctx->o)) {
@@ -1204,7 +1213,7 @@ int coffe_b200_plan_count(coffe_b200_plan *plan, double *n_items, double *n_ni_e
             for (int i = 0; i < L.n; ++i) tot += h[i];
             (mode == 1 ? si : di) = tot;
         }
-        cudaFree(b.evals.p); b.evals.p = nullptr; b.evals.n = 0;
+        b.evals.release();
     }
     if (n_items) *n_items = (double)b.si.n + (double)b.di.n;
     if (n_ni_evals) *n_ni_evals = opt_has_ni(ctx->o) ? (double)b.n_points * ctx->qc.n_mu_ni : 0.0;
@@ -1224,7 +1233,7 @@ void coffe_b200_plan_destroy(coffe_b200_plan *plan)
 int coffe_b200_fp64_peak(coffe_b200_ctx *ctx, double *tflops)
 {
     if (!ctx || !tflops) return COFFE_B200_EINVAL;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    COFFE_ENTER(ctx);
     CK(cudaSetDevice(ctx->device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, ctx->device));

@@ -344,7 +344,7 @@ int coffe_b200_integrals(coffe_b200_ctx *ctx, const coffe_b200_integrals_params 
                          double *r40, double *i40, double *renorm0, double *renorm_chi, double *renorm_z)
 {
     if (!ctx || !p) return COFFE_B200_EINVAL;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    COFFE_ENTER(ctx);
     if (!p->pk_k || !p->pk_p || p->n_pk < 5 || !(p->k_max > p->k_min) || !(p->k_min > 0)) { ctx->err = "bad power spectrum / k range"; return COFFE_B200_EINVAL; }
     if (p->n_tables < 0 || (p->n_tables > 0 && (!p->n || !p->l || !r || !tables))) { ctx->err = "bad table list"; return COFFE_B200_EINVAL; }
     if (p->divergent && (!r40 || !i40 || !renorm0 || !renorm_chi || !renorm_z || !(p->chi_max > 0))) { ctx->err = "divergent tables need output buffers and chi_max > 0"; return COFFE_B200_EINVAL; }

@@ -90,6 +90,7 @@ struct QuadConfig {
        its own, coarser mu rule and inner panel plan (DESIGN.md section 3.1 holds the convergence evidence) */
     int n_mu_panel_di;
     double panel_w_di, panel_du_di;
+    double mu_panel_w_di;   /* width of the uniform r_perp panels of its mu rule */
 };
 
 /* bank of Gauss-Legendre rules on [0,1] for n = 1..kMaxRule, rule n stored at offset n(n-1)/2 */

@@ -22,7 +22,7 @@ inline QuadConfig default_quadrature()
     q.n_panel_si = 8; q.n_panel_di = 8;
     q.n_z = 8;
     q.panel_w = 64.0; q.panel_du = 128.0; q.eps_min = 1e-3; q.tail_ratio = 1.5;
-    q.n_mu_panel_di = 5; q.panel_w_di = 64.0; q.panel_du_di = 128.0;
+    q.n_mu_panel_di = 5; q.panel_w_di = 64.0; q.panel_du_di = 128.0; q.mu_panel_w_di = 64.0;
     return q;
 }
 
@@ -46,6 +46,7 @@ inline QuadConfig merge_quadrature(const QuadConfig &base, const coffe_b200_quad
     if (u.n_mu_panel_di > 0) q.n_mu_panel_di = u.n_mu_panel_di;
     if (u.panel_width_di > 0) q.panel_w_di = u.panel_width_di;
     if (u.panel_uniform_extent_di > 0) q.panel_du_di = u.panel_uniform_extent_di;
+    if (u.mu_panel_width_di > 0) q.mu_panel_w_di = u.mu_panel_width_di;
     return q;
 }
 
@@ -69,7 +70,7 @@ inline bool quadrature_valid(const QuadConfig &q, const int panel_capacity)
            q.n_panel_di >= 2 && q.n_panel_di <= kMaxRule && q.n_z >= 1 && q.n_z <= kMaxRule &&
            q.panel_w > 0 && q.panel_du >= 0 && q.eps_min > 0 && q.tail_ratio > 1.0 &&
            q.mu_rho0 > 0 && q.mu_panel_w > 0 && q.mu_du >= 0 &&
-           q.n_mu_panel_di >= 2 && q.n_mu_panel_di <= kMaxRule && q.panel_w_di > 0 && q.panel_du_di >= 0;
+           q.n_mu_panel_di >= 2 && q.n_mu_panel_di <= kMaxRule && q.panel_w_di > 0 && q.panel_du_di >= 0 && q.mu_panel_w_di > 0;
 }
 
 /* bank of Gauss-Legendre rules on [0,1], rule n at offset n(n-1)/2 */
@@ -98,15 +99,17 @@ inline std::vector<double> build_rpow(const double ratio)
    uniform / geometric plan as the line-of-sight integrals) plus one at |mu| = 0.999 where the reference
    switches formulas; n-point Gauss-Legendre per panel; mirrored to mu < 0.  Weights are for the measure
    dmu/2, i.e. xi_l = (2l+1) sum_j w_j P_l(mu_j) xi(mu_j)      (src/signal.c:97-110, 541). */
-inline void build_mu_rule(const QuadConfig &q, const double sep, std::vector<double> &mu, std::vector<double> &w, const int n_per_panel = 0)
+inline void build_mu_rule(const QuadConfig &q, const double sep, std::vector<double> &mu, std::vector<double> &w, const int n_per_panel = 0,
+                          const double panel_width = 0.0)
 {
     const int n_mu_panel = n_per_panel > 0 ? n_per_panel : q.n_mu_panel;
+    const double mu_panel_w = panel_width > 0.0 ? panel_width : q.mu_panel_w;
     mu.clear(); w.clear();
     std::vector<double> bp;
     bp.push_back(0.0);
     double b = q.mu_rho0;
-    while (b < q.mu_panel_w && b < sep) { bp.push_back(b); b *= 2.0; }
-    while (b < q.mu_du && b < sep) { bp.push_back(b); b += q.mu_panel_w; }
+    while (b < mu_panel_w && b < sep) { bp.push_back(b); b *= 2.0; }
+    while (b < q.mu_du && b < sep) { bp.push_back(b); b += mu_panel_w; }
     while (b < sep) { bp.push_back(b); b *= q.tail_ratio; }
     bp.push_back(sep);
     bp.push_back(sep * std::sqrt(1.0 - kMuSwitch * kMuSwitch));

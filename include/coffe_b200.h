@@ -106,6 +106,7 @@ typedef struct coffe_b200_quadrature {
     /* the integrated x integrated piece has its own mu rule and inner panel plan (it is smoother and dominates the cost) */
     int n_mu_panel_di;
     double panel_width_di, panel_uniform_extent_di;
+    double mu_panel_width_di;
 } coffe_b200_quadrature;
 
 /* ---- life cycle ---------------------------------------------------------------------------------- */

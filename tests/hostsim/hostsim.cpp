@@ -197,7 +197,7 @@ void hs_multipoles(void *h, double z, double sep, const int *ls, int n_l, double
     HostSim *s = (HostSim *)h;
     for (int p = 1; p < 3; ++p) {
         std::vector<double> mu, w;
-        build_mu_rule(s->qc, sep, mu, w, p == 1 ? s->qc.n_mu_panel : s->qc.n_mu_panel_di);
+        build_mu_rule(s->qc, sep, mu, w, p == 1 ? s->qc.n_mu_panel : s->qc.n_mu_panel_di, p == 1 ? s->qc.mu_panel_w : s->qc.mu_panel_w_di);
         const int nm = (int)mu.size();
         std::vector<double> v((size_t)3 * nm);
 #pragma omp parallel for schedule(dynamic, 1)
@@ -232,7 +232,7 @@ void hs_eval_counts(void *h, double z, double sep, double *out)
         const SIHalf ha = si_half_setup(s->o, g, e1, e2, true), hb = si_half_setup(s->o, g, e2, e1, false);
         out[0] += si_eval_count(s->q, g, ha) + si_eval_count(s->q, g, hb);
     }
-    build_mu_rule(s->qc, sep, mu, w, s->qc.n_mu_panel_di);
+    build_mu_rule(s->qc, sep, mu, w, s->qc.n_mu_panel_di, s->qc.mu_panel_w_di);
     for (size_t im = 0; im < mu.size(); ++im) {
         const Geometry g = geometry(chi_mean, sep, mu[im]);
         const EndVals e1 = end_eval(s->o, s->t, g.chi1, 1), e2 = end_eval(s->o, s->t, g.chi2, 2);
