@@ -151,6 +151,37 @@ def test_average_multipoles_match_stock_reference(engine, ref):
     assert np.allclose(got, want, rtol=5e-4), got / want - 1
 
 
+def test_average_multipoles_with_lensing_cfg3(engine, ref):
+    """cfg3 of BASELINE.json (den + rsd + len, bins of width 0.1875): (i) the redshift average of the kernels (8 z-nodes)
+    against the same average assembled here from per-redshift multipoles on a 24-node rule -- bin limits shrunk by r/2,
+    weight H0 h / (Hc (1+z)), no Jacobian (src/signal.c:262-283) -- to 1e-5; (ii) one bin against the reference's own 2/3/4-D
+    Cuhre path at the accuracy that path has with lensing (its 4-D integrals exhaust the evaluation budget)"""
+    contrib = ["den", "rsd", "len"]
+    engine.set_options(contrib)
+    zmin, zmax = [0.5, 1.8125], [0.6875, 2.0]
+    sep = np.array([10.0, 60.0, 160.0]) / H
+    got = engine.average_multipoles(zmin, zmax, sep, [0, 2, 4])
+    x, w = np.polynomial.legendre.leggauss(24)
+    x, w = 0.5 * (x + 1), 0.5 * w
+    H0h = H / 2997.92458
+    for ib in range(2):
+        for ir, r in enumerate(sep):
+            c1 = ref.background_eval("comoving_distance", zmin[ib])[0] + r / 2
+            c2 = ref.background_eval("comoving_distance", zmax[ib])[0] - r / 2
+            z1, z2 = ref.background_eval("z_as_chi", c1)[0], ref.background_eval("z_as_chi", c2)[0]
+            zs = z1 + (z2 - z1) * x
+            per_z = engine.multipoles(zs, [r], [0, 2, 4])[:, :, 0]
+            wz = w * H0h / (ref.background_eval("conformal_Hz", zs) * (1 + zs))
+            want = (wz[:, None] * per_z).sum(0)
+            assert np.all(np.abs(got[ib, :, ir] / want - 1) < 1e-5), (ib, r, got[ib, :, ir] / want - 1)
+    ref.set_contributions(contrib)
+    ref.set_z_min([0.9]); ref.set_z_max([1.1]); ref.set_sep(np.array([60.0]) / H)
+    stock = ref.average_multipoles()[0][:, 0]
+    ref.set_sep(SEP_H / H); ref.set_contributions(list(ALL))
+    ours = engine.average_multipoles([0.9], [1.1], np.array([60.0]) / H, [0, 2, 4])[0][:, 0]
+    assert np.allclose(ours, stock, rtol=2e-3), ours / stock - 1
+
+
 def test_flatsky_closed_form_multipoles(ref, golden):
     """has_flatsky_nonlocal / has_flatsky_local_nonlocal multipoles (tests/test_coffe.py:322-380): kernels vs the
     reference run with the same switches and vs benchmark_flatsky_{lensing_lensing,density_lensing}_multipoles*.dat"""
