@@ -98,11 +98,16 @@ static const int kMaxRule = 128;
 COFFE_HD int rule_offset(const int n) { return n * (n - 1) / 2; }
 
 /* outer node count when QuadConfig::n_outer == 0: the inner integral as a function of lambda_1 carries
-   the structure of I(R) stretched by 1/sin(theta) ~ chi/r_perp, so wider separations need more nodes */
+   the structure of I(R) stretched by 1/sin(theta) ~ chi/r_perp, so wider separations need more nodes.
+   Measured on 16 (z, r) points against a rule with every count doubled (errors relative to the piece itself,
+   worst multipole): r <= 224 Mpc is converged to the 2e-6 floor of the other rules with 24 nodes; r = 299 Mpc
+   needs 28 (1e-6; 24 gives 1e-5), r = 448 Mpc needs 44 (2e-6; 36 gives 1e-5, 24 gives 2e-4): independent of z.
+   The floor of 30 keeps the l = 4 multipole at r = 60-150 Mpc below 3e-6 (26 nodes: 6e-6). */
 COFFE_HD int auto_n_outer(const double sep)
 {
-    int n = 32 + (int)(sep / 12.0);
-    if (n > 80) n = 80;
+    int n = 10 + (int)(sep / 12.0);
+    if (n < 30) n = 30;
+    if (n > 96) n = 96;
     return n & ~1;
 }
 
