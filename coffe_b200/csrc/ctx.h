@@ -31,7 +31,7 @@ struct coffe_b200_ctx {
     /* options / quadrature */
     Options o;
     QuadConfig qc;
-    double *d_gl_x = nullptr, *d_gl_w = nullptr, *d_rpow = nullptr;
+    double *d_gl_x = nullptr, *d_gl_w = nullptr, *d_rpow = nullptr, *d_rpow_di = nullptr;
     /* shared-memory tables of the integrated-pieces kernel */
     CompactBuild compact;
     double *d_blob = nullptr;

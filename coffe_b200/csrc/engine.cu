@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(kDIThreads, 1) di_items_smem_kernel(
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
         for (int i = tid; i < stage_bytes / 16; i += n_threads) dst[i] = blob[i];
         for (int i = tid; i < kLosStride * los_stage_n; i += n_threads) los_s[i] = t.los.v[i];
-        if (tid < kMaxTail) small[tid] = q.rpow[tid];
+        if (tid < kMaxTail) small[tid] = q.rpow_di[tid];
         const int np = q.n_panel_di < 32 ? q.n_panel_di : 32;
         if (tid < np) {
             small[kMaxTail + tid] = q.gl_x[rule_offset(q.n_panel_di) + tid];
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(kDIThreads, 1) di_items_smem_kernel(
     CompactAccess ta;
     ta.t = &t; ta.c.base = smem; ta.c.h = ch;
     Rules ql = q;
-    ql.rpow = small;
+    ql.rpow_di = small;
     if (q.n_panel_di <= 32) { ql.panel_x = small + kMaxTail; ql.panel_w = small + kMaxTail + 32; }
 
     for (;;) {
@@ -427,6 +427,7 @@ Rules make_rules(const coffe_b200_ctx *ctx)
     q.panel_w_mpc = ctx->qc.panel_w; q.panel_du = ctx->qc.panel_du; q.eps_min = ctx->qc.eps_min; q.tail_ratio = ctx->qc.tail_ratio;
     q.panel_w_di = ctx->qc.panel_w_di; q.panel_du_di = ctx->qc.panel_du_di;
     q.panel_x = q.panel_w = nullptr;
+    q.rpow_di = ctx->d_rpow_di; q.tail_ratio_di = ctx->qc.tail_ratio_di;
     return q;
 }
 
@@ -795,6 +796,9 @@ int coffe_b200_create(int device, coffe_b200_ctx **out)
         const std::vector<double> rp = build_rpow(ctx->qc.tail_ratio);
         if ((e = cudaMalloc(&ctx->d_rpow, kMaxTail * sizeof(double))) != cudaSuccess) return fail("cudaMalloc", e);
         if ((e = cudaMemcpy(ctx->d_rpow, rp.data(), kMaxTail * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return fail("cudaMemcpy", e);
+        const std::vector<double> rpd = build_rpow(ctx->qc.tail_ratio_di);
+        if ((e = cudaMalloc(&ctx->d_rpow_di, kMaxTail * sizeof(double))) != cudaSuccess) return fail("cudaMalloc", e);
+        if ((e = cudaMemcpy(ctx->d_rpow_di, rpd.data(), kMaxTail * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return fail("cudaMemcpy", e);
         if ((e = cudaMalloc(&ctx->d_counter, sizeof(unsigned int))) != cudaSuccess) return fail("cudaMalloc", e);
         int v = 0;
         if ((e = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return fail("cudaDeviceGetAttribute", e);
@@ -824,6 +828,7 @@ void coffe_b200_destroy(coffe_b200_ctx *ctx)
     if (ctx->d_gl_x) cudaFree(ctx->d_gl_x);
     if (ctx->d_gl_w) cudaFree(ctx->d_gl_w);
     if (ctx->d_rpow) cudaFree(ctx->d_rpow);
+    if (ctx->d_rpow_di) cudaFree(ctx->d_rpow_di);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
     if (ctx->d_blob) cudaFree(ctx->d_blob);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -904,6 +909,11 @@ int coffe_b200_set_quadrature(coffe_b200_ctx *ctx, const coffe_b200_quadrature *
         CK(cudaSetDevice(ctx->device));
         CK(cudaMemcpy(ctx->d_rpow, rp.data(), kMaxTail * sizeof(double), cudaMemcpyHostToDevice));
     }
+    if (merged.tail_ratio_di != ctx->qc.tail_ratio_di) {
+        const std::vector<double> rp = build_rpow(merged.tail_ratio_di);
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaMemcpy(ctx->d_rpow_di, rp.data(), kMaxTail * sizeof(double), cudaMemcpyHostToDevice));
+    }
     ctx->qc = merged;
     return COFFE_B200_OK;
 }
@@ -934,7 +944,7 @@ int coffe_b200_get_quadrature(const coffe_b200_ctx *ctx, coffe_b200_quadrature *
     q->mu_uniform_extent = c.mu_du; q->n_outer = c.n_outer; q->n_panel_si = c.n_panel_si; q->n_panel_di = c.n_panel_di;
     q->n_z = c.n_z; q->panel_width = c.panel_w; q->panel_uniform_extent = c.panel_du; q->eps_min = c.eps_min; q->tail_ratio = c.tail_ratio;
     q->n_mu_panel_di = c.n_mu_panel_di; q->panel_width_di = c.panel_w_di; q->panel_uniform_extent_di = c.panel_du_di;
-    q->mu_panel_width_di = c.mu_panel_w_di;
+    q->mu_panel_width_di = c.mu_panel_w_di; q->tail_ratio_di = c.tail_ratio_di;
     return COFFE_B200_OK;
 }
 

@@ -19,6 +19,8 @@ struct Rules {
     double panel_w_mpc, panel_du, eps_min, tail_ratio;
     double panel_w_di, panel_du_di;  /* panel plan of the inner integral of the integrated x integrated piece */
     const double *panel_x, *panel_w; /* nodes / weights of the n_panel_di rule when staged separately (else null: read from the bank) */
+    const double *rpow_di;           /* tail_ratio_di^n, n < kMaxTail */
+    double tail_ratio_di;
 };
 
 /* panels one ridge_integrate call can hold in its scratch area (engine.cu checks the configured plan) */

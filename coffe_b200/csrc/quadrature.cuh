@@ -91,6 +91,7 @@ struct QuadConfig {
     int n_mu_panel_di;
     double panel_w_di, panel_du_di;
     double mu_panel_w_di;   /* width of the uniform r_perp panels of its mu rule */
+    double tail_ratio_di;   /* growth factor of its tail panels */
 };
 
 /* bank of Gauss-Legendre rules on [0,1] for n = 1..kMaxRule, rule n stored at offset n(n-1)/2 */

@@ -107,6 +107,7 @@ typedef struct coffe_b200_quadrature {
     int n_mu_panel_di;
     double panel_width_di, panel_uniform_extent_di;
     double mu_panel_width_di;
+    double tail_ratio_di;
 } coffe_b200_quadrature;
 
 /* ---- life cycle ---------------------------------------------------------------------------------- */

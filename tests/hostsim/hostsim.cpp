@@ -22,7 +22,7 @@ struct HostSim {
     Tables t;
     Options o;
     QuadConfig qc;
-    std::vector<double> bx, bw, rpow;
+    std::vector<double> bx, bw, rpow, rpow_di;
     Rules q;
     std::string err;
     CompactBuild cb;
@@ -42,6 +42,8 @@ static void set_rules(HostSim *s)
     q.panel_w_mpc = s->qc.panel_w; q.panel_du = s->qc.panel_du; q.eps_min = s->qc.eps_min; q.tail_ratio = s->qc.tail_ratio;
     q.panel_w_di = s->qc.panel_w_di; q.panel_du_di = s->qc.panel_du_di;
     q.panel_x = q.panel_w = nullptr;
+    s->rpow_di = build_rpow(s->qc.tail_ratio_di);
+    q.rpow_di = s->rpow_di.data(); q.tail_ratio_di = s->qc.tail_ratio_di;
 }
 
 extern "C" {
@@ -171,7 +173,7 @@ static void item_pieces(void *h, double z, double sep, double mu, int mask, doub
             /* the straightforward evaluator (di_eval on the same panels, no pairing): cross-check of di_fast.cuh */
             double scratch[2 * kMaxPanels];
             Rules ql = s->q;
-            ql.panel_w_mpc = s->q.panel_w_di; ql.panel_du = s->q.panel_du_di;
+            ql.panel_w_mpc = s->q.panel_w_di; ql.panel_du = s->q.panel_du_di; ql.tail_ratio = s->q.tail_ratio_di; ql.rpow = s->q.rpow_di;
             if (s->variant) out[2] = di_partial(s->compact(), s->t.los, ql, g, k, s->t.los.v, 0, 1, 0, 1, scratch);
             else out[2] = di_partial(ExactAccess{&s->t}, s->t.los, ql, g, k, s->t.los.v, 0, 1, 0, 1, scratch);
         }
