@@ -117,6 +117,38 @@ def test_integrated_pieces_match_converged_oracle(engine, ref):
     assert np.all(np.abs(got / want - 1) < 1e-5), got / want - 1
 
 
+@pytest.mark.parametrize("z,s", [(1.0, 100.0 / H), (0.5, 300.0 / H), (2.0, 200.0 / H), (1.5, 40.0 / H)])
+def test_lensing_only_multipoles_match_converged_oracle_across_the_grid(engine, ref, z, s):
+    """the integrated x integrated piece alone (what a lensing-only run returns) against the converged oracle over the
+    corners of the cfg5 grid: every multipole to 1e-5 of itself.  Guards the node counts of DESIGN.md 3.1, which were
+    sized on sweeps of the product's own rules, with an independent rule over the reference's integrands."""
+    from oracle.converged import ConvergedOracle
+    ref.set_contributions(["len"])
+    engine.set_options(["len"])
+    want = ConvergedOracle(ref, n_outer=72, n_panel=8, mu_kw=dict(n=6, W=24.0)).multipoles_pieces(z, s, [0, 2, 4], want=(False, False, True))[2]
+    got = engine.multipoles([z], [s], [0, 2, 4])[0, :, 0]
+    ref.set_contributions(list(ALL))
+    assert np.all(np.abs(got / want - 1) < 1e-5), (z, s, got / want - 1)
+
+
+@pytest.mark.parametrize("z,s", [(1.0, 20.0 / H), (0.7, 150.0 / H), (1.8, 300.0 / H)])
+def test_density_lensing_cross_matches_converged_oracle(engine, ref, z, s):
+    """the local x integrated piece alone (density x lensing, cross-correlations only): every multipole to 1e-5 of the
+    l = 0 .. 4 scale of the piece"""
+    from oracle.converged import ConvergedOracle
+    ref.set_contributions(["den", "len"])
+    ref.set_flags({"only_cross": 1})
+    engine.set_options(["den", "len"], only_cross=True)
+    try:
+        want = ConvergedOracle(ref, n_panel=10, mu_kw=dict(n=10, W=16.0)).multipoles_pieces(z, s, [0, 2, 4], want=(False, True, False))[1]
+    finally:
+        ref.set_flags({})
+        ref.set_contributions(list(ALL))
+    got = engine.multipoles_pieces([z], [s], [0, 2, 4])[1, 0, :, 0]
+    engine.set_options(ALL)
+    assert np.all(np.abs(got - want) < 1e-5 * np.max(np.abs(want))), (z, s, (got - want) / np.max(np.abs(want)), got / want - 1)
+
+
 def test_corrfunc_matches_converged_oracle(engine, ref):
     from oracle.converged import ConvergedOracle
     ref.set_contributions(list(ALL))
