@@ -152,7 +152,7 @@ struct DIPanels {
 COFFE_HD DIPanels di_panels(const Rules &q, const DIFast &f, const DIOuter &o)
 {
     DIPanels p;
-    p.plan = panel_plan(sqrt(o.eps2), q.eps_min, q.panel_w_di, q.panel_du_di, q.tail_ratio_di, q.rpow_di);
+    p.plan = panel_plan(sqrt(o.eps2), q.eps_min, q.panel_w_di, q.panel_du_di, q.tail_ratio_di, q.rpow_di, q.geo_shift_di);
     p.b_neg = o.c0;
     p.a_neg = o.c0 > f.chi2 ? o.c0 - f.chi2 : 0.0;
     p.b_pos = f.chi2 - o.c0;

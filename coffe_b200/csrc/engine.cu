@@ -427,7 +427,7 @@ Rules make_rules(const coffe_b200_ctx *ctx)
     q.panel_w_mpc = ctx->qc.panel_w; q.panel_du = ctx->qc.panel_du; q.eps_min = ctx->qc.eps_min; q.tail_ratio = ctx->qc.tail_ratio;
     q.panel_w_di = ctx->qc.panel_w_di; q.panel_du_di = ctx->qc.panel_du_di;
     q.panel_x = q.panel_w = nullptr;
-    q.rpow_di = ctx->d_rpow_di; q.tail_ratio_di = ctx->qc.tail_ratio_di;
+    q.rpow_di = ctx->d_rpow_di; q.tail_ratio_di = ctx->qc.tail_ratio_di; q.geo_shift_di = ctx->qc.geo_shift_di;
     return q;
 }
 
@@ -944,7 +944,7 @@ int coffe_b200_get_quadrature(const coffe_b200_ctx *ctx, coffe_b200_quadrature *
     q->mu_uniform_extent = c.mu_du; q->n_outer = c.n_outer; q->n_panel_si = c.n_panel_si; q->n_panel_di = c.n_panel_di;
     q->n_z = c.n_z; q->panel_width = c.panel_w; q->panel_uniform_extent = c.panel_du; q->eps_min = c.eps_min; q->tail_ratio = c.tail_ratio;
     q->n_mu_panel_di = c.n_mu_panel_di; q->panel_width_di = c.panel_w_di; q->panel_uniform_extent_di = c.panel_du_di;
-    q->mu_panel_width_di = c.mu_panel_w_di; q->tail_ratio_di = c.tail_ratio_di;
+    q->mu_panel_width_di = c.mu_panel_w_di; q->tail_ratio_di = c.tail_ratio_di; q->geometric_shift_di = c.geo_shift_di;
     return COFFE_B200_OK;
 }
 

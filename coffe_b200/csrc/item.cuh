@@ -21,6 +21,7 @@ struct Rules {
     const double *panel_x, *panel_w; /* nodes / weights of the n_panel_di rule when staged separately (else null: read from the bank) */
     const double *rpow_di;           /* tail_ratio_di^n, n < kMaxTail */
     double tail_ratio_di;
+    int geo_shift_di;
 };
 
 /* panels one ridge_integrate call can hold in its scratch area (engine.cu checks the configured plan) */

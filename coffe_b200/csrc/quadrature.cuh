@@ -24,22 +24,25 @@ static const int kMaxTail = 48;
 struct PanelPlan {
     const double *rpow;
     double eps, W, ratio;
-    int J;          /* B_k = eps 2^(k-1) for 1 <= k <= J */
+    int shift;      /* log2 of the growth factor of the geometric panels (1: doubling, 2: x4) */
+    int J;          /* B_k = eps 2^(shift (k-1)) for 1 <= k <= J */
     int M;          /* B_k = B_J + (k-J) W for J < k <= J+M */
     double BJ, BJM;
 };
 
-COFFE_HD PanelPlan panel_plan(double eps, const double eps_min, const double W, const double Du, const double ratio, const double *rpow)
+COFFE_HD PanelPlan panel_plan(double eps, const double eps_min, const double W, const double Du, const double ratio, const double *rpow,
+                              const int shift = 1)
 {
     PanelPlan p;
     p.rpow = rpow;
+    p.shift = shift;
     if (eps < eps_min) eps = eps_min;
     p.eps = eps; p.W = W; p.ratio = ratio;
     int J = 0;
     double b = 0.0;
     if (eps < W) {          /* otherwise the cusp is wider than a uniform panel: uniform panels from d = 0 */
         J = 1; b = eps;
-        while (b < W) { b *= 2.0; ++J; }
+        while (b < W) { b = ldexp(b, shift); ++J; }
     }
     p.J = J; p.BJ = b;
     int M = 0;
@@ -51,7 +54,7 @@ COFFE_HD PanelPlan panel_plan(double eps, const double eps_min, const double W, 
 COFFE_HD double panel_break(const PanelPlan &p, const int k)
 {
     if (k <= 0) return 0.0;
-    if (k <= p.J) return ldexp(p.eps, k - 1);
+    if (k <= p.J) return ldexp(p.eps, p.shift * (k - 1));
     if (k <= p.J + p.M) return p.BJ + (k - p.J) * p.W;
     const int n = k - p.J - p.M;
     return p.BJM * p.rpow[n < kMaxTail ? n : kMaxTail - 1];
@@ -70,7 +73,7 @@ COFFE_HD int panel_count(const PanelPlan &p, const double b)
     }
     if (b > p.BJ || p.J == 0) return p.J + (int)ceil((b - p.BJ) / p.W);
     double e = p.eps;
-    while (e < b) { e *= 2.0; ++k; }
+    while (e < b) { e = ldexp(e, p.shift); ++k; }
     return k;
 }
 
@@ -92,6 +95,7 @@ struct QuadConfig {
     double panel_w_di, panel_du_di;
     double mu_panel_w_di;   /* width of the uniform r_perp panels of its mu rule */
     double tail_ratio_di;   /* growth factor of its tail panels */
+    int geo_shift_di;       /* log2 of the growth factor of its geometric panels (1 or 2) */
 };
 
 /* bank of Gauss-Legendre rules on [0,1] for n = 1..kMaxRule, rule n stored at offset n(n-1)/2 */

@@ -22,7 +22,7 @@ inline QuadConfig default_quadrature()
     q.n_panel_si = 8; q.n_panel_di = 8;
     q.n_z = 8;
     q.panel_w = 64.0; q.panel_du = 128.0; q.eps_min = 1e-3; q.tail_ratio = 1.5;
-    q.n_mu_panel_di = 5; q.panel_w_di = 64.0; q.panel_du_di = 128.0; q.mu_panel_w_di = 64.0; q.tail_ratio_di = 2.5;
+    q.n_mu_panel_di = 5; q.panel_w_di = 64.0; q.panel_du_di = 128.0; q.mu_panel_w_di = 64.0; q.tail_ratio_di = 2.5; q.geo_shift_di = 1;
     return q;
 }
 
@@ -48,6 +48,7 @@ inline QuadConfig merge_quadrature(const QuadConfig &base, const coffe_b200_quad
     if (u.panel_uniform_extent_di > 0) q.panel_du_di = u.panel_uniform_extent_di;
     if (u.mu_panel_width_di > 0) q.mu_panel_w_di = u.mu_panel_width_di;
     if (u.tail_ratio_di > 1.0) q.tail_ratio_di = u.tail_ratio_di;
+    if (u.geometric_shift_di > 0) q.geo_shift_di = u.geometric_shift_di;
     return q;
 }
 
@@ -71,7 +72,8 @@ inline bool quadrature_valid(const QuadConfig &q, const int panel_capacity)
            q.n_panel_di >= 2 && q.n_panel_di <= kMaxRule && q.n_z >= 1 && q.n_z <= kMaxRule &&
            q.panel_w > 0 && q.panel_du >= 0 && q.eps_min > 0 && q.tail_ratio > 1.0 &&
            q.mu_rho0 > 0 && q.mu_panel_w > 0 && q.mu_du >= 0 &&
-           q.n_mu_panel_di >= 2 && q.n_mu_panel_di <= kMaxRule && q.panel_w_di > 0 && q.panel_du_di >= 0 && q.mu_panel_w_di > 0 && q.tail_ratio_di > 1.0;
+           q.n_mu_panel_di >= 2 && q.n_mu_panel_di <= kMaxRule && q.panel_w_di > 0 && q.panel_du_di >= 0 && q.mu_panel_w_di > 0 && q.tail_ratio_di > 1.0 &&
+           q.geo_shift_di >= 1 && q.geo_shift_di <= 3;
 }
 
 /* bank of Gauss-Legendre rules on [0,1], rule n at offset n(n-1)/2 */

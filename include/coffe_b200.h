@@ -108,6 +108,7 @@ typedef struct coffe_b200_quadrature {
     double panel_width_di, panel_uniform_extent_di;
     double mu_panel_width_di;
     double tail_ratio_di;
+    int geometric_shift_di;      /* log2 of the growth factor of its geometric panels: 1 = doubling, 2 = x4 */
 } coffe_b200_quadrature;
 
 /* ---- life cycle ---------------------------------------------------------------------------------- */

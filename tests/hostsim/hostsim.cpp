@@ -43,7 +43,7 @@ static void set_rules(HostSim *s)
     q.panel_w_di = s->qc.panel_w_di; q.panel_du_di = s->qc.panel_du_di;
     q.panel_x = q.panel_w = nullptr;
     s->rpow_di = build_rpow(s->qc.tail_ratio_di);
-    q.rpow_di = s->rpow_di.data(); q.tail_ratio_di = s->qc.tail_ratio_di;
+    q.rpow_di = s->rpow_di.data(); q.tail_ratio_di = s->qc.tail_ratio_di; q.geo_shift_di = s->qc.geo_shift_di;
 }
 
 extern "C" {

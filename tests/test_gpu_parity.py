@@ -297,7 +297,7 @@ def test_quadrature_self_convergence_on_a_wide_grid(engine):
     s = [15.0, 120.0, 448.0]
     base = engine.multipoles(z, s, [0, 2, 4])
     engine.set_quadrature(n_mu_panel=12, n_mu_panel_di=10, mu_panel_width=16.0, n_outer=96, n_panel_si=12, n_panel_di=12, panel_width=8.0,
-                          panel_uniform_extent=640.0, panel_width_di=16.0, panel_uniform_extent_di=640.0, mu_panel_width_di=16.0, tail_ratio=1.3, tail_ratio_di=1.3, n_mu_ni=64)
+                          panel_uniform_extent=640.0, panel_width_di=16.0, panel_uniform_extent_di=640.0, mu_panel_width_di=16.0, tail_ratio=1.3, tail_ratio_di=1.3, geometric_shift_di=1, n_mu_ni=64)
     fine = engine.multipoles(z, s, [0, 2, 4])
     engine.set_quadrature()
     err = np.abs(base / fine - 1)
