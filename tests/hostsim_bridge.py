@@ -79,6 +79,11 @@ class HostSim:
         self.lib.hs_multipoles(self.h, C.c_double(z), C.c_double(sep), capi.iptr(ls), C.c_int(len(ls)), capi.ptr(out))
         return out.reshape(3, len(ls))
 
+    def n_mu(self, sep):
+        """nodes of the mu rule of the local x integrated piece at this separation"""
+        self.lib.hs_n_mu.restype = C.c_int
+        return self.lib.hs_n_mu(self.h, C.c_double(sep))
+
     def eval_counts(self, z, sep):
         """(SI, DI) integrand evaluations of the fixed-node rules at one (z, sep), summed over the mu items"""
         out = np.zeros(2)
