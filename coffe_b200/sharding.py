@@ -21,18 +21,44 @@ def block_size(n_items, world):
     return (n_items + world - 1) // world
 
 
-def gather_ranges(local, n_items, dist, device="cpu", dst=0):
+def weighted_bounds(weights, world):
+    """world + 1 boundaries of contiguous blocks of the flattened items with (nearly) equal total weight: the cost of a
+    (z, r) item grows with the separation (more mu and outer nodes) and with the distance (more tail panels), so equal
+    item counts leave the ranks that hold the high-redshift rows with ~10 % more work.  Deterministic: every rank
+    computes the same boundaries from the same weights."""
+    w = np.asarray(weights, dtype=np.float64).ravel()
+    if world < 1:
+        raise ValueError("need world >= 1")
+    if w.size == 0:
+        return [0] * (world + 1)
+    if np.any(w < 0) or not np.all(np.isfinite(w)) or w.sum() <= 0:
+        raise ValueError("weights must be finite, non-negative and not all zero")
+    c = np.concatenate([[0.0], np.cumsum(w)])
+    targets = c[-1] * np.arange(1, world) / world
+    cuts = np.searchsorted(c, targets, side="left")
+    # the boundary closest to the target of the two neighbours
+    cuts = np.array([k if k == 0 or abs(c[k] - t) <= abs(c[k - 1] - t) else k - 1 for k, t in zip(cuts, targets)], dtype=int)
+    bounds = np.concatenate([[0], np.clip(cuts, 0, w.size), [w.size]])
+    return [int(b) for b in np.maximum.accumulate(bounds)]
+
+
+def gather_ranges(local, n_items, dist, device="cpu", dst=0, bounds=None):
     """Gather the per-rank result slices of coffe_b200_multipoles_range.
 
     local : [n_l, end - begin] array of this rank (layout of coffe_b200_multipoles_range)
-    Returns [n_l, n_items] on rank `dst`, None elsewhere.  One collective, padded to equal blocks.
+    bounds: world + 1 block boundaries (weighted_bounds); default: equal blocks (block_partition)
+    Returns [n_l, n_items] on rank `dst`, None elsewhere.  One collective, padded to the largest block.
     """
     import torch
     world, rank = dist.get_world_size(), dist.get_rank()
-    per = block_size(n_items, world)
+    if bounds is None:
+        bounds = [block_partition(n_items, world, r)[0] for r in range(world)] + [n_items]
+    if len(bounds) != world + 1 or bounds[0] != 0 or bounds[-1] != n_items:
+        raise ValueError("bounds must run from 0 to n_items in world + 1 steps")
+    per = max(max(bounds[r + 1] - bounds[r] for r in range(world)), 1)
     local = np.ascontiguousarray(local, dtype=np.float64)
     n_l = local.shape[0]
-    begin, end = block_partition(n_items, world, rank)
+    begin, end = bounds[rank], bounds[rank + 1]
     if local.shape != (n_l, end - begin):
         raise ValueError(f"rank {rank}: expected a slice of shape {(n_l, end - begin)}, got {local.shape}")
     pad = torch.zeros((n_l, per), dtype=torch.float64, device=device)
@@ -42,7 +68,28 @@ def gather_ranges(local, n_items, dist, device="cpu", dst=0):
     dist.gather(pad, parts, dst=dst)
     if rank != dst:
         return None
-    return torch.cat(parts, dim=1)[:, :n_items].cpu().numpy()
+    out = [parts[r][:, :bounds[r + 1] - bounds[r]] for r in range(world)]
+    return torch.cat(out, dim=1).cpu().numpy()
+
+
+def separable_cost(engine, z_mean, sep, l, n_z_samples=5, n_sep_samples=16):
+    """Estimated relative cost of every (z, r) item, [n_z, n_sep]: integrand evaluations counted by the library itself
+    (coffe_b200_plan_count) on a few rows and columns of the grid, combined as f(z) g(r).  Costs a few ms of GPU time."""
+    z, s = np.asarray(z_mean, float), np.asarray(sep, float)
+
+    def cost(zs, ss):
+        plan = engine.plan_multipoles(zs, ss, l)
+        _, _, n_si, n_di = plan.count()
+        plan.close()
+        return n_di + 2.0 * n_si          # a local x integrated evaluation costs about two integrated x integrated ones
+
+    iz = np.unique(np.linspace(0, len(z) - 1, min(n_z_samples, len(z))).round().astype(int))
+    js = np.unique(np.linspace(0, len(s) - 1, min(n_sep_samples, len(s))).round().astype(int))
+    f = np.array([cost(z[i:i + 1], s[js]) for i in iz])
+    g = np.array([cost(z[iz[len(iz) // 2]:iz[len(iz) // 2] + 1], s[j:j + 1]) for j in js])
+    fz = np.interp(z, z[iz], f) if len(iz) > 1 else np.full(len(z), f[0])
+    gs = np.interp(s, s[js], g) if len(js) > 1 else np.full(len(s), g[0])
+    return np.outer(fz, gs)
 
 
 def ranges_to_grid(flat, n_z, n_sep):
@@ -53,16 +100,21 @@ def ranges_to_grid(flat, n_z, n_sep):
     return np.ascontiguousarray(flat.reshape(n_l, n_z, n_sep).transpose(1, 0, 2))
 
 
-def multipoles_sharded(engine, z_mean, sep, l, dist=None, device=None):
+def multipoles_sharded(engine, z_mean, sep, l, dist=None, device=None, balanced=False):
     """Sharded equivalent of Engine.multipoles: every rank computes its block on its own GPU, rank 0 returns
     the full [n_z, n_l, n_sep] array (None on the other ranks).  Without a process group: single GPU."""
     n_z, n_sep = len(z_mean), len(sep)
     n_items = n_z * n_sep
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
         return ranges_to_grid(engine.multipoles_range(z_mean, sep, l, 0, n_items), n_z, n_sep)
-    begin, end = block_partition(n_items, dist.get_world_size(), dist.get_rank())
+    bounds = None
+    if balanced:
+        bounds = weighted_bounds(separable_cost(engine, z_mean, sep, l), dist.get_world_size())
+        begin, end = bounds[dist.get_rank()], bounds[dist.get_rank() + 1]
+    else:
+        begin, end = block_partition(n_items, dist.get_world_size(), dist.get_rank())
     local = engine.multipoles_range(z_mean, sep, l, begin, end)
     if device is None:
         device = f"cuda:{engine.device}" if dist.get_backend() == "nccl" else "cpu"
-    flat = gather_ranges(local, n_items, dist, device=device)
+    flat = gather_ranges(local, n_items, dist, device=device, bounds=bounds)
     return None if flat is None else ranges_to_grid(flat, n_z, n_sep)

@@ -24,6 +24,21 @@ def test_block_partition_covers_the_grid_once():
         sharding.block_partition(10, 2, 2)
 
 
+def test_weighted_bounds_balance_and_cover():
+    rng = np.random.default_rng(3)
+    for n in (1, 7, 1000):
+        for world in (1, 2, 3, 8):
+            w = rng.uniform(0.5, 2.0, n) * np.linspace(1.0, 3.0, n)
+            b = sharding.weighted_bounds(w, world)
+            assert len(b) == world + 1 and b[0] == 0 and b[-1] == n and all(x <= y for x, y in zip(b, b[1:]))
+            if n >= 100 * world:
+                parts = np.array([w[b[r]:b[r + 1]].sum() for r in range(world)])
+                assert parts.max() / parts.mean() < 1.02
+    assert sharding.weighted_bounds(np.ones(8), 4) == [0, 2, 4, 6, 8]
+    with pytest.raises(ValueError):
+        sharding.weighted_bounds([1.0, -1.0], 2)
+
+
 def test_ranges_to_grid_is_the_reference_loop_order():
     n_z, n_sep, n_l = 3, 5, 2
     flat = np.empty((n_l, n_z * n_sep))
@@ -49,6 +64,23 @@ class FakeEngine:
         return out
 
 
+class CountingPlan:
+    def __init__(self, z, sep):
+        self.z, self.sep = z, sep
+
+    def count(self):
+        c = sum((1.0 + zz) * (10.0 + ss) for zz in self.z for ss in self.sep)
+        return (0.0, 0.0, 0.0, c)
+
+    def close(self):
+        pass
+
+
+class FakeEngineWithPlans(FakeEngine):
+    def plan_multipoles(self, z, sep, l, begin=0, end=None):
+        return CountingPlan(list(z), list(sep))
+
+
 def _worker(rank, world, port, n_z, n_sep, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -57,6 +89,11 @@ def _worker(rank, world, port, n_z, n_sep, q):
     try:
         z, sep, l = np.linspace(0.5, 2.0, n_z), np.linspace(10, 300, n_sep), [0, 2, 4]
         got = sharding.multipoles_sharded(FakeEngine(), z, sep, l, dist=dist)
+        bal = sharding.multipoles_sharded(FakeEngineWithPlans(), z, sep, l, dist=dist, balanced=True)
+        if rank == 0:
+            assert np.array_equal(bal, got)
+        else:
+            assert bal is None
         if rank == 0:
             want = sharding.ranges_to_grid(FakeEngine().multipoles_range(z, sep, l, 0, n_z * n_sep), n_z, n_sep)
             q.put(bool(np.array_equal(got, want)) and got.shape == (n_z, 3, n_sep))
