@@ -68,3 +68,41 @@ def test_product_never_imports_the_oracle():
             text = f.read_text()
             assert "oracle" not in text.replace("# oracle-free", ""), f"{f} mentions the oracle"
             assert "hostsim" not in text or f.name in ("hd.h", "assemble.h", "item.cuh"), f"{f} mentions hostsim"
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/coffe_b200.h compiles as C99 (and as C++), and a C program linked against the library gets a clean
+    error code -- not a crash, not a fallback -- from coffe_b200_create when there is no GPU"""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    from coffe_b200 import capi
+    inc = ROOT / "include"
+    src = tmp_path / "t.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "coffe_b200.h"
+int main(void)
+{
+    coffe_b200_ctx *ctx = NULL;
+    coffe_b200_quadrature q = {0};
+    coffe_b200_integrals_params ip = {0};
+    int n_r = 0, n_r40 = 0, n_ren = 0;
+    ip.bessel_bins = 10000;
+    if (coffe_b200_integrals_sizes(&ip, &n_r, &n_r40, &n_ren) != COFFE_B200_OK) return 3;
+    printf("sizes %d %d %d\n", n_r, n_r40, n_ren);
+    int rc = coffe_b200_create(0, &ctx);
+    printf("create rc=%d msg=%s\n", rc, coffe_b200_last_error(NULL));
+    if (rc == COFFE_B200_OK) { rc = coffe_b200_get_quadrature(ctx, &q); coffe_b200_destroy(ctx); return rc ? 4 : 0; }
+    return ctx == NULL ? 0 : 5;
+}
+''')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", f"-I{inc}", str(src)], check=True)
+    subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", f"-I{inc}", str(src)], check=True)
+    exe = tmp_path / "t"
+    lib = capi.LIB_PATH
+    subprocess.run(["gcc", "-std=c99", f"-I{inc}", str(src), "-o", str(exe), str(lib), f"-Wl,-rpath,{lib.parent}"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "sizes 10043 297 201" in r.stdout
