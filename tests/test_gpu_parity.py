@@ -270,6 +270,63 @@ def test_range_calls_tile_the_full_grid_bit_exactly(engine):
     assert np.array_equal(again, full), "results must be deterministic run to run"
 
 
+def test_cfg5_full_grid_properties():
+    """BASELINE.json configs[4] at full size (32 z_mean x 1000 separations x l = 0, 2, 4, all effects) through the C ABI with the
+    package's default tables: size-independent properties -- the grid tiles bit-exactly into unequal item ranges (what the
+    multi-GPU sharding relies on), single points reproduce their grid entries bit for bit (a result does not depend on which
+    warp, CTA or call computed it), every value is finite, and the monopole is smooth in r (no isolated outliers from a
+    mis-indexed table or panel)."""
+    import coffe_b200
+    from coffe_b200.default_tables import load_default_tableset
+    eng = coffe_b200.Engine(0)
+    eng.upload_tables(load_default_tableset())
+    eng.set_options(ALL)
+    z, sep, ls = np.linspace(0.5, 2.0, 32), np.linspace(10.0, 300.0, 1000) / H, [0, 2, 4]
+    full = eng.multipoles(z, sep, ls)
+    assert full.shape == (32, 3, 1000) and np.all(np.isfinite(full))
+    n = 32000
+    cuts = [0, 1, 12345, 20000, n]
+    flat = np.concatenate([eng.multipoles_range(z, sep, ls, a, b) for a, b in zip(cuts[:-1], cuts[1:])], axis=1)
+    assert np.array_equal(flat.reshape(3, 32, 1000).transpose(1, 0, 2), full)
+    for iz, ir in ((0, 0), (17, 503), (31, 999)):
+        one = eng.multipoles([z[iz]], [sep[ir]], ls)[0, :, 0]
+        assert np.array_equal(one, full[iz, :, ir])
+    mono = full[:, 0, :] * sep[None, :] ** 2
+    second = np.abs(mono[:, 2:] - 2 * mono[:, 1:-1] + mono[:, :-2])
+    assert np.max(second) < 2e-3 * np.max(np.abs(mono)), np.max(second) / np.max(np.abs(mono))
+
+
+def test_cfg4_full_size_covariance_properties():
+    """BASELINE.json configs[3] at full size: 4 z-bins x (3 x 100)^2 entries with shot noise -- every 300 x 300 block is
+    symmetric and positive definite, cosmic + mixed + Poisson add up, and only the first bin's pixel size enters the windowed
+    integrals (reference quirk, src/covariance.c:527, 668-670)."""
+    import coffe_b200
+    from coffe_b200.default_tables import load_default_tableset
+    from oracle import coffe_oracle as O
+    eng = coffe_b200.Engine(0)
+    eng.upload_tables(load_default_tableset())
+    eng.set_options(["den", "rsd"])
+    sep = np.linspace(20.0, 218.0, 100) / H
+    args = (O.load_pk(), sep, [0, 2, 4], [0.2] * 4, [1e-3 * H ** 3] * 4, [1e-3 * H ** 3] * 4)
+    kw = dict(z_mean=[0.6, 1.0, 1.4, 1.8], deltaz=[0.1] * 4)
+    for window in (False, True):
+        cov = eng.covariance(*args, [2.0 / H] * 4, window=window, **kw)
+        assert cov.shape == (4, 3, 100, 3, 100) and np.all(np.isfinite(cov))
+        parts = sum(eng.covariance(*args, [2.0 / H] * 4, window=window, cosmic=c, mixed=m, poisson=p, **kw)
+                    for c, m, p in ((True, False, False), (False, True, False), (False, False, True)))
+        assert np.allclose(parts, cov, rtol=1e-12, atol=0)
+        for ib in range(4):
+            m = cov[ib].reshape(300, 300)
+            assert np.allclose(m, m.T, rtol=1e-9, atol=1e-30)
+            if window:
+                assert np.all(np.linalg.eigvalsh(0.5 * (m + m.T)) > 0)
+    # the windowed Bessel integrals (cosmic-variance part) read the first bin's pixel size only
+    only_cv = dict(cosmic=True, mixed=False, poisson=False)
+    a = eng.covariance(*args, [2.0 / H] * 4, window=True, **only_cv, **kw)
+    b = eng.covariance(*args, [2.0 / H, 7.0 / H, 9.0 / H, 11.0 / H], window=True, **only_cv, **kw)
+    assert np.array_equal(a, b)
+
+
 def test_pieces_add_up_and_terms_are_bilinear(engine):
     """xi(den+rsd) = xi(den) + xi(rsd) + cross, and the cross term alone is what only_cross keeps"""
     z, s = [1.0, 1.7], np.linspace(15.0, 300.0, 6)
