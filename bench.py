@@ -145,9 +145,11 @@ def cpu_baseline(z, sep, ls, budget_points=72):
                       f"reference sources built -O3{' -ffast-math' if fast else ''} -fopenmp, tables prebuilt"}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one di_items_smem_kernel launch, ncu --set full capture of the
-# 2 z x 120 r sample (profiles/r1_di_kernel_v32_summary.txt): the tables are L2-resident, the kernel does not stream HBM
-TRAFFIC_NOTE = {"bytes_per_launch": 1.88e6, "captured_on": "2 z x 120 r sample, ncu --set full", "algorithmic_table_bytes": 2.6e6}
+# dram__bytes_read.sum + dram__bytes_write.sum of one di_items_smem_kernel launch on this very workload (cfg5, one GPU), from
+# the ncu --set full capture summarised in profiles/r1_di_kernel_cfg5_v37_ncu.txt: 73.6 MB read + 58.8 MB written in a 399 ms
+# launch.  Algorithmic bytes of that launch: the (point, mu) items in (12 B each), one double per item out, the 6 MB of tables
+# once = ~60 MB; either way ~0.3 GB/s -- the kernel does not stream HBM (L2 hit rate 99.98 %), its bound is the FP64 pipe.
+TRAFFIC_BYTES_PER_LAUNCH_CFG5_1GPU = 1.3238e8
 
 
 def covariance_cfg4(eng, args):
@@ -303,7 +305,9 @@ def main():
                        "quadrature": eng.get_quadrature(), "wall_ms_per_step": wall_ms_max / args.steps},
             "roofline": {"bound": "fp64", "kernel": "di_items_smem_kernel", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved / peak_tf if peak_tf and achieved else None,
-                         "traffic": TRAFFIC_NOTE, "peak_source": "DFMA probe kernel measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                         "traffic": TRAFFIC_BYTES_PER_LAUNCH_CFG5_1GPU if (world == 1 and args.nz == 32 and args.nsep == 1000) else None,
+                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_di_kernel_cfg5_v37_ncu.txt",
+                         "peak_source": "DFMA probe kernel measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                          "launch_ms": di_launch_ms, "share_of_step": di_ms_max / dev_ms_max if dev_ms_max else None,
                          "flops_per_launch": F_DI * n_di / world, "accounting": "SURVEY.md 8d: 450 flop per DI integrand evaluation",
                          "step": {"achieved": achieved_step, "frac": achieved_step / peak_tf if peak_tf else None, "flops": flops_per_step / world,
