@@ -66,7 +66,8 @@ class CovarianceParams(C.Structure):
                 ("z_mean", dp), ("deltaz", dp), ("z_min", dp), ("z_max", dp),
                 ("fsky", dp), ("density1", dp), ("density2", dp), ("pixelsize", dp),
                 ("sep", dp), ("n_sep", C.c_int), ("l", ip), ("n_l", C.c_int), ("pop", C.c_int * 4),
-                ("cosmic", C.c_int), ("mixed", C.c_int), ("poisson", C.c_int), ("window", C.c_int), ("average", C.c_int)]
+                ("cosmic", C.c_int), ("mixed", C.c_int), ("poisson", C.c_int), ("window", C.c_int), ("average", C.c_int),
+                ("integration_method", C.c_int), ("integration_bins", C.c_int)]
 
 
 class IntegralsParams(C.Structure):

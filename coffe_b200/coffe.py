@@ -11,8 +11,7 @@ O(10^4) host computation, coffe_b200/background.py) and argument checking run on
 without the built library or a GPU the first compute call raises.
 
 Not mirrored (out of the hot-path scope): CLASS coupling (`pk_type` other than "linear",
-`cross_spectrum`, the CLASS precision knobs), `from_file` / `to_file` (libconfig-style settings files) and the
-2-D FFTLog covariance (`covariance_integration_method = "fftlog"`).
+`cross_spectrum`, the CLASS precision knobs) and `from_file` / `to_file` (libconfig-style settings files).
 """
 import numpy as np
 
@@ -167,6 +166,7 @@ class Coffe:
         self._pk = None
         self._k_min, self._k_max = 1e-5, 300.0
         self._bessel_bins, self._background_bins = 10000, 10000
+        self._cov_method, self._cov_bins = "standard", 8000
         self._background = None
         self._integrals = None
         self._tables_uploaded = False
@@ -306,14 +306,27 @@ class Coffe:
             getattr(self, f)()
 
     @property
-    def covariance_integration_method(self): return "standard"
+    def covariance_integration_method(self): return self._cov_method
 
     @covariance_integration_method.setter
     def covariance_integration_method(self, value):
+        """'standard' (k-quadrature) or 'fftlog' (2-D FFTLog), python/coffe/coffe.pyx:2243-2272"""
         if value not in ("standard", "fftlog"):
             raise ValueError(f"The value `covariance_integration_method={value}` is not one of `['standard', 'fftlog']")
-        if value != "standard":
-            raise ValueError("coffe_b200 implements covariance_integration_method = 'standard' (DESIGN.md section 8)")
+        self._cov_method = value
+        for f in _COV:
+            getattr(self, f)()
+
+    @property
+    def covariance_integration_sampling(self): return self._cov_bins
+
+    @covariance_integration_sampling.setter
+    def covariance_integration_sampling(self, value):
+        """number of points of the 2-D FFTLog (python/coffe/coffe.pyx:2275-2296); default 8000"""
+        _check_parameter("covariance_integration_sampling", value, int, 0, 2147483647)
+        self._cov_bins = int(value)
+        for f in _COV:
+            getattr(self, f)()
 
     @property
     def integrals_fftlog_sampling(self): return self._bessel_bins
@@ -658,7 +671,7 @@ class Coffe:
             self._cache[key] = eng.covariance(self._pk, self.sep, self.l, self.fsky, self.number_density1, self.number_density2, self.pixelsize,
                                               pops=tuple(self._populations), cosmic=self.covariance_cosmic, mixed=self.covariance_mixed,
                                               poisson=self.covariance_poisson, window=self.has_binned_covariance,
-                                              k_min=self.k_min, k_max=self.k_max, **kw)
+                                              k_min=self.k_min, k_max=self.k_max, method=self._cov_method, bins=self._cov_bins, **kw)
         return self._cache[key]
 
     def compute_covariance_array(self, recompute=False):

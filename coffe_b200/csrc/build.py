@@ -5,7 +5,7 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 SOURCES = ["engine.cu", "covariance.cu", "integrals.cu"]
-HEADERS = ["hd.h", "tables.cuh", "physics.cuh", "quadrature.cuh", "item.cuh", "di_fast.cuh", "assemble.h", "compact.cuh", "compact_build.h", "table_build.h", "rules_build.h", "ctx.h", "special.cuh",
+HEADERS = ["hd.h", "tables.cuh", "physics.cuh", "quadrature.cuh", "item.cuh", "di_fast.cuh", "assemble.h", "compact.cuh", "compact_build.h", "table_build.h", "rules_build.h", "ctx.h", "special.cuh", "fft.cuh",
            "../../include/coffe_b200.h"]
 OUT = HERE / "libcoffe_b200.so"
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",

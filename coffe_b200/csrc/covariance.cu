@@ -18,6 +18,7 @@
 
 #include "ctx.h"
 #include "special.cuh"
+#include "fft.cuh"
 
 namespace {
 
@@ -251,7 +252,131 @@ __global__ void cov_assemble_kernel(const CovAssembly a, const CovBin *__restric
     out[idx] = v;
 }
 
+/* ---- stage A, covariance_integration_method = fftlog: 2-D FFTLog (src/covariance.c:357-470, src/twobessel.c:16-113) -----
+   The reference transforms the N x N matrix diag(k^3 P^p / dlnk) with a 2-D FFTLog.  A diagonal input makes the forward 2-D
+   transform a 1-D one, F[(m + n) mod N]; what remains is the inverse 2-D transform of
+       X[m][n] = conj(F[(m+n) mod N] A[m] B[n]),   A, B = windowed (k0 r0)^(-+ i eta) g_l(eta)            (src/twobessel.c:60-90)
+   done as N/2+1 column transforms (one CTA each, the column is generated on the fly) followed by the real row transforms of
+   the rows the requested separations need (+-50 knots: the reach of the natural-spline derivative estimates of the bicubic
+   resampling at double precision). */
+struct FftlogGeom { int N; double kmin, ratio, dlnk, nu; };
+
+__device__ double fftlog_window(const long i, const long ncut)       /* src/utils.c:233-236 */
+{
+    return (double)i / ncut - sin(2. * i * 3.14159265358979323846 / ncut) / (2. * 3.14159265358979323846);
+}
+
+/* diag[p][i] = k_i^(3 - 2 nu) S(k_i)^(p+1) / dlnk, as complex numbers ready for the forward transform */
+__global__ void cov_fftlog_diag_kernel(const FftlogGeom g, const SplineView pk, cplx *__restrict__ d1, cplx *__restrict__ d2)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.N) return;
+    const double k = g.kmin * pow(g.ratio, (double)i / g.N);
+    const double P = spline_eval(pk, k), pre = pow(k, 3.0 - 2.0 * g.nu) / g.dlnk;
+    d1[i] = {pre * P, 0.0};
+    d2[i] = {pre * P * P, 0.0};
+}
+
+/* one CTA per transform: buf[b*N .. ] -> forward FFT in place (result copied back to buf) */
+__global__ void __launch_bounds__(1024) cov_fft1d_kernel(const FftPlan plan, cplx *__restrict__ buf, cplx *__restrict__ work, const double sign)
+{
+    cplx *a = buf + (size_t)blockIdx.x * plan.n, *b = work + (size_t)blockIdx.x * plan.n;
+    cplx *r = fft_run(plan, a, b, sign);
+    if (r != a)
+        for (int i = threadIdx.x; i < plan.n; i += blockDim.x) a[i] = r[i];
+}
+
+/* T[l_index][m], m = 0..N/2: (k0 r0)^(-i eta_m) g_l(eta_m), g_l = 2^z Gamma((l+z)/2) / Gamma((3+l-z)/2), z = nu + i eta   (src/utils.c:196-207) */
+__global__ void cov_fftlog_gl_kernel(const FftlogGeom g, const int *__restrict__ ls, const int n_l, cplx *__restrict__ T)
+{
+    const int half = g.N / 2;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_l * (half + 1)) return;
+    const int il = idx / (half + 1), m = idx % (half + 1);
+    const double l = ls[il], eta = 2 * 3.14159265358979323846 / g.dlnk / g.N * m;
+    const cplx a = clgamma({(l + g.nu) / 2., eta / 2.}), b = clgamma({(3. + l - g.nu) / 2., -eta / 2.});
+    const double ln2 = 0.69314718055994530942;
+    /* k0 r0 = k[0] / k[N-1] */
+    const double lkr = -log(g.ratio) * (double)(g.N - 1) / g.N;
+    const cplx e = {g.nu * ln2 + a.re - b.re, eta * ln2 + a.im - b.im - eta * lkr};
+    T[idx] = cexp_(e);
+}
+
+/* columns: for every n <= N/2 the inverse transform over m of X[m][n]; rows i_lo .. i_lo + n_sub - 1 are kept:
+   Y[(i - i_lo) * (N/2+1) + n] */
+__global__ void __launch_bounds__(1024) cov_fftlog_columns_kernel(const FftPlan plan, const cplx *__restrict__ F, const cplx *__restrict__ T1,
+                                                                  const cplx *__restrict__ T2, const int i_lo, const int n_sub,
+                                                                  cplx *__restrict__ work, cplx *__restrict__ Y)
+{
+    const int N = plan.n, half = N / 2;
+    const long ncut = (long)(half * 0.25);
+    cplx *a = work + (size_t)blockIdx.x * 2 * N, *b = a + N;
+    for (int n = blockIdx.x; n <= half; n += gridDim.x) {
+        cplx Bn = T2[n];
+        if (n >= half - ncut) { const double w = fftlog_window(half - n, ncut); Bn.re *= w; Bn.im *= w; }
+        for (int m = threadIdx.x; m < N; m += blockDim.x) {
+            cplx Am;
+            double w = 1.0;
+            if (m <= half) { Am = T1[m]; if (m >= half - ncut) w = fftlog_window(half - m, ncut); }
+            else { Am = T1[N - m]; Am.im = -Am.im; if (m <= half + 1 + ncut) w = fftlog_window(m - half - 1, ncut); }
+            const cplx v = cmul(cmul(F[(m + n) % N], Am), Bn);
+            a[m] = {v.re * w, -v.im * w};
+        }
+        __syncthreads();
+        const cplx *r = fft_run(plan, a, b, +1.0);
+        for (int i = threadIdx.x; i < n_sub; i += blockDim.x) Y[(size_t)i * (half + 1) + n] = r[i_lo + i];
+        __syncthreads();
+    }
+}
+
+/* rows: the real inverse transform over n of row i (Hermitian completion, imaginary parts of the n = 0 and n = N/2 bins dropped
+   as FFTW's c2r does), columns i_lo .. kept, scaled by pi / (16 N^2 r_i^nu r_j^nu): R[(i - i_lo) * n_sub + (j - i_lo)] */
+__global__ void __launch_bounds__(1024) cov_fftlog_rows_kernel(const FftPlan plan, const FftlogGeom g, const cplx *__restrict__ Y, const int i_lo,
+                                                               const int n_sub, cplx *__restrict__ work, double *__restrict__ R)
+{
+    const int N = plan.n, half = N / 2;
+    cplx *a = work + (size_t)blockIdx.x * 2 * N, *b = a + N;
+    for (int row = blockIdx.x; row < n_sub; row += gridDim.x) {
+        const cplx *y = Y + (size_t)row * (half + 1);
+        for (int n = threadIdx.x; n <= half; n += blockDim.x) {
+            cplx v = y[n];
+            if (n == 0 || n == half) v.im = 0.0;
+            a[n] = v;
+            if (n > 0 && n < half) a[N - n] = {v.re, -v.im};
+        }
+        __syncthreads();
+        const cplx *r = fft_run(plan, a, b, +1.0);
+        /* r_i = 1 / k[N-1-i] */
+        const double ri = 1.0 / (g.kmin * pow(g.ratio, (double)(N - 1 - (i_lo + row)) / N));
+        for (int j = threadIdx.x; j < n_sub; j += blockDim.x) {
+            const double rj = 1.0 / (g.kmin * pow(g.ratio, (double)(N - 1 - (i_lo + j)) / N));
+            R[(size_t)row * n_sub + j] = r[i_lo + j].re * 3.14159265358979323846 / (16. * (double)N * (double)N * pow(rj, g.nu) * pow(ri, g.nu));
+        }
+        __syncthreads();
+    }
+}
+
 /* ---- host helpers ----------------------------------------------------------------------------------- */
+/* bicubic patch on a (possibly non-uniform) grid from node data {z, z_x, z_y, z_xy}, node index j*nx + i (gsl_interp2d_bicubic) */
+double bicubic_eval_host(const std::vector<double> &xa, const std::vector<double> &ya, const std::vector<build::Coef> &node, const double x, const double y)
+{
+    const int nx = (int)xa.size(), ny = (int)ya.size();
+    int xi = (int)(std::upper_bound(xa.begin(), xa.end(), x) - xa.begin()) - 1, yi = (int)(std::upper_bound(ya.begin(), ya.end(), y) - ya.begin()) - 1;
+    xi = std::max(0, std::min(nx - 2, xi)); yi = std::max(0, std::min(ny - 2, yi));
+    const double dx = xa[xi + 1] - xa[xi], dy = ya[yi + 1] - ya[yi];
+    const double t = (x - xa[xi]) / dx, u = (y - ya[yi]) / dy;
+    const build::Coef &n00 = node[(size_t)yi * nx + xi], &n10 = node[(size_t)yi * nx + xi + 1];
+    const build::Coef &n01 = node[(size_t)(yi + 1) * nx + xi], &n11 = node[(size_t)(yi + 1) * nx + xi + 1];
+    const double t2 = t * t, t3 = t2 * t, u2 = u * u, u3 = u2 * u;
+    const double h00t = 2 * t3 - 3 * t2 + 1, h10t = (t3 - 2 * t2 + t) * dx, h01t = -2 * t3 + 3 * t2, h11t = (t3 - t2) * dx;
+    const double h00u = 2 * u3 - 3 * u2 + 1, h10u = (u3 - 2 * u2 + u) * dy, h01u = -2 * u3 + 3 * u2, h11u = (u3 - u2) * dy;
+    /* Coef members {y, b, c, d} hold {z, z_x, z_y, z_xy} */
+    return h00t * (h00u * n00.y + h01u * n01.y + h10u * n00.c + h11u * n01.c)
+         + h01t * (h00u * n10.y + h01u * n11.y + h10u * n10.c + h11u * n11.c)
+         + h10t * (h00u * n00.b + h01u * n01.b + h10u * n00.d + h11u * n01.d)
+         + h11t * (h00u * n10.b + h01u * n11.b + h10u * n10.d + h11u * n11.d);
+}
+
 double covariance_coefficient(const double b1, const double b2, const double f, const int ell)      /* src/covariance.c:40-57 */
 {
     switch (ell) {
@@ -286,6 +411,90 @@ double legendre_integral(const int n, const int m, const int a, const int b)
         r += (2. * l + 1) * x * x * y * y;
     }
     return 2 * r;
+}
+
+/* G^(p)[(i1, m), (i2, n)] of stage B from the 2-D FFTLog: h_G[p * Mpad^2 + row * Mpad + col] */
+int fill_G_fftlog(coffe_b200_ctx *ctx, const coffe_b200_covariance_params *p, const int Mpad, std::vector<double> &h_G)
+{
+    const int n_l = p->n_l, n_sep = p->n_sep;
+    const int N = p->integration_bins > 0 ? p->integration_bins : 8000;
+    FftPlan plan;
+    if (N < 64 || N % 2 || !make_fft_plan(N, plan)) { ctx->err = "covariance_integration_bins must be even with prime factors 2, 3, 5 only"; return COFFE_B200_EINVAL; }
+    FftlogGeom g;
+    g.N = N; g.kmin = p->k_min; g.ratio = p->k_max / p->k_min; g.dlnk = std::log(g.ratio) / N; g.nu = 1.01;      /* src/covariance.c:375-377 */
+    /* r_i = 1 / k[N-1-i], ascending; rows / columns needed: the cells of the requested separations +- the reach of the spline derivatives */
+    std::vector<double> r(N);
+    for (int i = 0; i < N; ++i) r[i] = 1.0 / (g.kmin * std::pow(g.ratio, (double)(N - 1 - i) / N));
+    double smin = 1e300, smax = 0;
+    for (int i = 0; i < n_sep; ++i) { smin = std::min(smin, p->sep[i]); smax = std::max(smax, p->sep[i]); }
+    if (!(smin > r[0]) || !(smax < r[N - 1])) { ctx->err = "separations outside the range 1/k_max .. 1/k_min of the 2-D FFTLog"; return COFFE_B200_ERANGE; }
+    const int reach = 50;
+    int i_lo = (int)(std::upper_bound(r.begin(), r.end(), smin) - r.begin()) - 1 - reach;
+    int i_hi = (int)(std::upper_bound(r.begin(), r.end(), smax) - r.begin()) + reach;
+    i_lo = std::max(0, i_lo); i_hi = std::min(N - 1, i_hi);
+    const int n_sub = i_hi - i_lo + 1, half = N / 2;
+    if ((size_t)n_sub * (half + 1) * sizeof(cplx) > ((size_t)8 << 30)) { ctx->err = "separation range too wide for the 2-D FFTLog work space"; return COFFE_B200_EINVAL; }
+    std::vector<double> rs(r.begin() + i_lo, r.begin() + i_hi + 1);
+
+    const int kind = ctx->layout.interp_kind;
+    std::vector<build::Coef> c1;
+    if (!build::spline_coefs(kind, p->pk_k, p->pk_p, p->n_pk, c1)) { ctx->err = "cannot build the P(k) spline"; return COFFE_B200_EINVAL; }
+    DevBuf<double> d_pkx, d_c1, d_F, d_fw, d_T, d_work, d_Y, d_R;
+    DevBuf<int> d_l;
+    CK(d_pkx.upload(std::vector<double>(p->pk_k, p->pk_k + p->n_pk), ctx->stream));
+    CK(d_c1.upload(std::vector<double>(reinterpret_cast<double *>(c1.data()), reinterpret_cast<double *>(c1.data()) + 4 * c1.size()), ctx->stream));
+    CK(d_l.upload(std::vector<int>(p->l, p->l + n_l), ctx->stream));
+    CK(d_F.alloc((size_t)2 * 2 * N));          /* two spectra (P, P^2), complex */
+    CK(d_fw.alloc((size_t)2 * 2 * N));
+    CK(d_T.alloc((size_t)n_l * (half + 1) * 2));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, ctx->device));
+    const int n_cta = 2 * prop.multiProcessorCount;
+    CK(d_work.alloc((size_t)n_cta * 2 * N * 2));
+    CK(d_Y.alloc((size_t)n_sub * (half + 1) * 2));
+    CK(d_R.alloc((size_t)n_sub * n_sub));
+    const SplineView s1{d_pkx.p, reinterpret_cast<const double4 *>(d_c1.p), p->n_pk};
+    cplx *F = reinterpret_cast<cplx *>(d_F.p);
+    cov_fftlog_diag_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(g, s1, F, F + N);
+    CK(cudaGetLastError());
+    cov_fft1d_kernel<<<2, 1024, 0, ctx->stream>>>(plan, F, reinterpret_cast<cplx *>(d_fw.p), -1.0);
+    CK(cudaGetLastError());
+    cov_fftlog_gl_kernel<<<(n_l * (half + 1) + 255) / 256, 256, 0, ctx->stream>>>(g, d_l.p, n_l, reinterpret_cast<cplx *>(d_T.p));
+    CK(cudaGetLastError());
+    ctx->last_launches += 3;
+
+    h_G.assign((size_t)2 * Mpad * Mpad, 0.0);
+    std::vector<double> h_R((size_t)n_sub * n_sub), z((size_t)n_sub * n_sub);
+    const double pi = 3.14159265358979323846;
+    for (int i1 = 0; i1 < n_l; ++i1)
+        for (int i2 = i1; i2 < n_l; ++i2)
+            for (int pw = 0; pw < 2; ++pw) {
+                if ((pw == 0 && !p->mixed) || (pw == 1 && !p->cosmic)) continue;
+                const cplx *T = reinterpret_cast<const cplx *>(d_T.p);
+                cov_fftlog_columns_kernel<<<std::min(n_cta, half + 1), 1024, 0, ctx->stream>>>(plan, F + (size_t)pw * N, T + (size_t)i1 * (half + 1),
+                                                                                         T + (size_t)i2 * (half + 1), i_lo, n_sub,
+                                                                                         reinterpret_cast<cplx *>(d_work.p), reinterpret_cast<cplx *>(d_Y.p));
+                CK(cudaGetLastError());
+                cov_fftlog_rows_kernel<<<std::min(n_cta, n_sub), 1024, 0, ctx->stream>>>(plan, g, reinterpret_cast<const cplx *>(d_Y.p), i_lo, n_sub,
+                                                                                      reinterpret_cast<cplx *>(d_work.p), d_R.p);
+                CK(cudaGetLastError());
+                ctx->last_launches += 2;
+                CK(cudaMemcpyAsync(h_R.data(), d_R.p, h_R.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+                /* bicubic resampling onto the separations (gsl_interp2d_bicubic on the (r1, r2) grid, z[j*nx + i] <-> (r1_i, r2_j),
+                   src/covariance.c:428-455); derivative estimates from natural cubic splines along the rows and columns of the block */
+                for (int i = 0; i < n_sub; ++i)
+                    for (int j = 0; j < n_sub; ++j) z[(size_t)j * n_sub + i] = h_R[(size_t)i * n_sub + j];
+                const std::vector<build::Coef> node = build::bicubic_nodes(rs.data(), rs.data(), z.data(), n_sub, n_sub);
+                const double norm = (pw == 0 ? 2.0 : 1.0) / pi / pi;               /* src/covariance.c:760-769 */
+                for (int m = 0; m < n_sep; ++m)
+                    for (int n = 0; n < n_sep; ++n) {
+                        const double v = norm * bicubic_eval_host(rs, rs, node, p->sep[m], p->sep[n]);
+                        h_G[(size_t)pw * Mpad * Mpad + (size_t)(i1 * n_sep + m) * Mpad + (i2 * n_sep + n)] = v;
+                        if (i2 != i1) h_G[(size_t)pw * Mpad * Mpad + (size_t)(i2 * n_sep + n) * Mpad + (i1 * n_sep + m)] = v;   /* :779-788 */
+                    }
+            }
+    return COFFE_B200_OK;
 }
 
 }  // namespace
@@ -371,7 +580,17 @@ extern "C" int coffe_b200_covariance(coffe_b200_ctx *ctx, const coffe_b200_covar
     CK(d_G.alloc((size_t)2 * Mpad * Mpad));
 
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    const bool fftlog = p->integration_method == 2;        /* COFFE_COVARIANCE_INTEGRATION_FFTLOG, src/common.h:301-302 */
+    if (fftlog) {
+        /* the reference has no binned variant of this path and falls back to the unbinned one with a warning (src/covariance.c:713-720) */
+        std::vector<double> h_G;
+        const int rc = fill_G_fftlog(ctx, p, Mpad, h_G);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(d_G.p, h_G.data(), h_G.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     SplineView s1{d_pkx.p, reinterpret_cast<const double4 *>(d_c1.p), p->n_pk}, s2{d_pkx.p, reinterpret_cast<const double4 *>(d_c2.p), p->n_pk};
+    if (!fftlog) {
     cov_node_weights_kernel<<<(n_nodes + 255) / 256, 256, 0, ctx->stream>>>(d_k.p, d_w.p, n_nodes, s1, s2, p->mixed != 0, p->cosmic != 0, d_W.p);
     CK(cudaGetLastError());
     ctx->last_launches += 1;
@@ -390,6 +609,7 @@ extern "C" int coffe_b200_covariance(coffe_b200_ctx *ctx, const coffe_b200_covar
         ctx->last_launches += 1;
     }
     else CK(cudaMemsetAsync(d_G.p, 0, sizeof(double) * 2 * Mpad * Mpad, ctx->stream));
+    }
 
     /* ---- stage B inputs: per-bin scalars and coefficient matrices (O(n_bins n_l^2) host work) ---- */
     const Tables &th = ctx->t_host;

@@ -20,43 +20,12 @@
 
 #include "ctx.h"
 #include "special.cuh"
+#include "fft.cuh"
 
 namespace {
 
 constexpr double kPi = 3.14159265358979323846;
 constexpr double kSqrtPi = 1.7724538509055160272981674833411451827975494561224;
-
-/* ---- complex helpers ------------------------------------------------------------------------------ */
-struct cplx { double re, im; };
-__device__ __forceinline__ cplx cmul(const cplx a, const cplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
-__device__ __forceinline__ cplx cadd(const cplx a, const cplx b) { return {a.re + b.re, a.im + b.im}; }
-__device__ __forceinline__ cplx clog_(const cplx a) { return {log(hypot(a.re, a.im)), atan2(a.im, a.re)}; }
-__device__ __forceinline__ cplx cexp_(const cplx a)
-{
-    double s, c;
-    sincos(a.im, &s, &c);
-    const double e = exp(a.re);
-    return {e * c, e * s};
-}
-__device__ __forceinline__ cplx cinv(const cplx a) { const double d = a.re * a.re + a.im * a.im; return {a.re / d, -a.im / d}; }
-
-/* log Gamma(z), Re z > 0: shift to Re z >= 12 with the recurrence, then the Stirling series.  The imaginary part is
-   defined modulo 2 pi (only exp of differences is used). */
-__device__ cplx clgamma(cplx z)
-{
-    cplx prod = {1.0, 0.0};
-    while (z.re < 12.0) { prod = cmul(prod, z); z.re += 1.0; }
-    const cplx lz = clog_(z), zi = cinv(z), zi2 = cmul(zi, zi);
-    /* (z - 1/2) ln z - z + ln(2 pi)/2 + sum B_2k / (2k (2k-1) z^(2k-1)) */
-    cplx r = cmul({z.re - 0.5, z.im}, lz);
-    r.re += -z.re + 0.91893853320467274178; r.im += -z.im;
-    const double c[7] = {1.0 / 12.0, -1.0 / 360.0, 1.0 / 1260.0, -1.0 / 1680.0, 1.0 / 1188.0, -691.0 / 360360.0, 1.0 / 156.0};
-    cplx acc = {c[6], 0.0};
-    for (int i = 5; i >= 0; --i) { acc = cmul(acc, zi2); acc.re += c[i]; }
-    r = cadd(r, cmul(acc, zi));
-    const cplx lp = clog_(prod);
-    return {r.re - lp.re, r.im - lp.im};
-}
 
 /* M_ql(t) of src/twofast.c:196-224: alpha^(i t - q) 2^(n-1) sqrt(pi) Gamma((1+l+n)/2) / Gamma((2+l-n)/2), n = q - 1 - i t */
 __device__ cplx mql(const double t, const double q, const double l, const double alpha)
@@ -106,59 +75,6 @@ __device__ double pk_eval(const PkView &s, const double v)
 }
 
 /* ---- K2: FFTLog ------------------------------------------------------------------------------------ */
-struct FftPlan { int n; int n_stage; int radix[24]; };
-
-/* one Stockham autosort pass of radix R over the n points of src -> dst; sign = -1 forward, +1 inverse */
-template <int R>
-__device__ void stockham_pass(const cplx *__restrict__ src, cplx *__restrict__ dst, const int n, const int ns, const double sign)
-{
-    const int m = n / R;
-    for (int j = threadIdx.x; j < m; j += blockDim.x) {
-        const int k = j % ns;
-        cplx v[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            v[r] = src[j + r * m];
-            if (r > 0 && k > 0) {
-                double s, c;
-                sincospi(sign * 2.0 * (double)k * r / ((double)ns * R), &s, &c);
-                v[r] = cmul(v[r], {c, s});
-            }
-        }
-        cplx o[R];
-#pragma unroll
-        for (int a = 0; a < R; ++a) {
-            cplx acc = v[0];
-#pragma unroll
-            for (int r = 1; r < R; ++r) {
-                double s, c;
-                sincospi(sign * 2.0 * (double)((a * r) % R) / R, &s, &c);
-                acc = cadd(acc, cmul(v[r], {c, s}));
-            }
-            o[a] = acc;
-        }
-        const int j0 = (j / ns) * ns * R + k;
-#pragma unroll
-        for (int a = 0; a < R; ++a) dst[j0 + a * ns] = o[a];
-    }
-}
-
-/* in-place-looking FFT over two ping-pong buffers; returns the buffer that holds the result */
-__device__ cplx *fft_run(const FftPlan &p, cplx *a, cplx *b, const double sign)
-{
-    int ns = 1;
-    for (int s = 0; s < p.n_stage; ++s) {
-        const int R = p.radix[s];
-        if (R == 2) stockham_pass<2>(a, b, p.n, ns, sign);
-        else if (R == 3) stockham_pass<3>(a, b, p.n, ns, sign);
-        else stockham_pass<5>(a, b, p.n, ns, sign);
-        ns *= R;
-        __syncthreads();
-        cplx *t = a; a = b; b = t;
-    }
-    return a;
-}
-
 struct FftlogTable { double l, nu; int power; /* multiply by r^power afterwards (n - l when n >= l) */ };
 
 /* out[table * N + i] = r_i^power I^nu_l(r_i), r_i = r0 (kmax/kmin)^(i/N), r0 = 1      src/twofast.c:362-483, src/integrals.c:496-522 */
@@ -289,14 +205,6 @@ __global__ void direct_integrals_kernel(const PkView pk, const DirectTask *__res
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) out[warp] = acc * t.scale;
-}
-
-bool make_fft_plan(int n, FftPlan &p)
-{
-    p.n = n; p.n_stage = 0;
-    for (const int r : {5, 3, 2})
-        while (n % r == 0) { if (p.n_stage >= 24) return false; p.radix[p.n_stage++] = r; n /= r; }
-    return n == 1;
 }
 
 /* the reference's knot lists (src/integrals.c:76-126) */

@@ -121,7 +121,8 @@ class Engine:
         return out
 
     def covariance(self, pk, sep, l, fsky, density1, density2, pixelsize, z_mean=None, deltaz=None, z_min=None, z_max=None,
-                   pops=(1, 1, 1, 1), cosmic=True, mixed=True, poisson=True, window=False, k_min=None, k_max=None):
+                   pops=(1, 1, 1, 1), cosmic=True, mixed=True, poisson=True, window=False, k_min=None, k_max=None,
+                   method="standard", bins=8000):
         """[n_bins, n_l, n_sep, n_l, n_sep]; pk = (k, P) knots of the power-spectrum spline"""
         average = z_mean is None
         k, p = capi.darr(pk[0]), capi.darr(pk[1])
@@ -146,6 +147,7 @@ class Engine:
         cp.sep, cp.n_sep, cp.l, cp.n_l = capi.ptr(s), len(s), capi.iptr(ls), len(ls)
         cp.pop = (C.c_int * 4)(*pops)
         cp.cosmic, cp.mixed, cp.poisson, cp.window, cp.average = int(cosmic), int(mixed), int(poisson), int(window), int(average)
+        cp.integration_method, cp.integration_bins = {"standard": 1, "fftlog": 2}[method], int(bins)
         out = np.empty((n_bins, len(ls), len(s), len(ls), len(s)))
         self._check(self.lib.coffe_b200_covariance(self._h, C.byref(cp), capi.ptr(out)))
         return out

@@ -165,11 +165,14 @@ typedef struct coffe_b200_covariance_params {
     int cosmic, mixed, poisson;  /* covariance_cosmic / _mixed / _poisson */
     int window;                  /* covariance_window (bin-averaged Bessel functions) */
     int average;                 /* output_type == COVARIANCE_AVERAGE_MULTIPOLES */
+    int integration_method;      /* par->covariance_integration_method: 0 or 1 = standard (k-quadrature), 2 = fftlog (2-D FFTLog,
+                                    src/covariance.c:357-470, 710-770; always unbinned, like the reference) */
+    int integration_bins;        /* par->covariance_integration_bins (fftlog; 0 = 8000); even, prime factors 2, 3, 5 */
 } coffe_b200_covariance_params;
 
 /* out[(((ibin*n_l + il1)*n_sep + ir1)*n_l + il2)*n_sep + ir2]   (order of src/covariance.c:1046-1059);
    density / rsd switches come from coffe_b200_set_options, background and galaxy_bias1..4 from the uploaded
-   tables; covariance_integration_method = standard */
+   tables */
 int coffe_b200_covariance(coffe_b200_ctx *ctx, const coffe_b200_covariance_params *p, double *out);
 
 /* ---- I^n_l tables ----------------------------------------------------------------------------------

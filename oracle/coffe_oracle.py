@@ -133,6 +133,9 @@ class RefCoffe:
         self.lib.ref_set_covariance(self.h_, (C.c_int * 4)(*pops), C.c_int(cosmic), C.c_int(mixed), C.c_int(poisson),
                                     C.c_int(window), C.c_int(method))
 
+    def set_covariance_bins(self, bins):
+        self.lib.ref_set_covariance_bins(self.h_, C.c_int(int(bins)))
+
     def set_nthreads(self, n):
         self.lib.ref_set_nthreads(self.h_, C.c_int(n))
 

@@ -211,6 +211,14 @@ void ref_set_covariance(void *h, const int *pops, int cosmic, int mixed, int poi
     free_outputs(s);
 }
 
+/* par->covariance_integration_bins: sampling of the 2-D FFTLog covariance (src/parser.c:809) */
+void ref_set_covariance_bins(void *h, int bins)
+{
+    ref_state *s = h;
+    s->par.covariance_integration_bins = bins;
+    free_outputs(s);
+}
+
 int ref_background(void *h)
 {
     ref_state *s = h;

@@ -83,6 +83,10 @@ def test_parameters():
         Coffe(not_a_parameter=1)
     with pytest.raises(ValueError):
         cosmo.covariance_populations = [1, 2, 3]
+    with pytest.raises(ValueError):
+        cosmo.covariance_integration_method = "montecarlo"
+    cosmo.covariance_integration_method = "fftlog"
+    assert cosmo.covariance_integration_method == "fftlog" and cosmo.covariance_integration_sampling == 8000
 
 
 def test_defaults_and_parameter_round_trip():
@@ -278,6 +282,11 @@ def test_covariance_multipoles(golden):
     cov = _matrix(result, 18)
     assert np.allclose(cov, cov.T)
     assert np.all(np.linalg.eigvalsh(cov) > 0)
+    # the 2-D FFTLog path of the same class (tests/test_coffe.py has no golden for it: compared with the k-quadrature)
+    cosmo.covariance_integration_method = "fftlog"
+    fl = _matrix(cosmo.compute_covariance_bulk(), 18)
+    d = np.sqrt(np.diag(cov))
+    assert np.max(np.abs(fl - cov) / np.outer(d, d)) < 5e-2
 
 
 @pytest.mark.gpu

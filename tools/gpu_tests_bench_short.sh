@@ -1,3 +1,3 @@
 set -x
-(time python -m pytest tests -m gpu -x -q) > gpurun_out/pytest_gpu_v35.log 2>&1; tail -5 gpurun_out/pytest_gpu_v35.log
-python bench.py > gpurun_out/bench_v35_full.log 2>&1; tail -1 gpurun_out/bench_v35_full.log | cut -c1-300
+(time python -m pytest tests -m gpu -x -q) > gpurun_out/pytest_gpu_latest.log 2>&1; tail -5 gpurun_out/pytest_gpu_latest.log
+python bench.py > gpurun_out/bench_latest_full.log 2>&1; tail -1 gpurun_out/bench_latest_full.log | cut -c1-300
