@@ -118,6 +118,47 @@ inline const coffe_b200_integral *find_integral(const coffe_b200_tables &T, cons
     return nullptr;
 }
 
+/* The integrated x integrated integrand is invariant under the exchange of the two galaxies, f(mu; x1, x2) = f(-mu; x2, x1)
+   (checked against the reference's functions_double_integrated), whenever the two populations carry the same magnification
+   and evolution bias -- the only population-dependent inputs of that piece are s_i(z) and G_i(z).  Then xi_DI(mu) = xi_DI(-mu):
+   the multipole sums need the mu > 0 nodes only and the odd multipoles of the piece vanish. */
+inline bool same_knots(const coffe_b200_spline &a, const coffe_b200_spline &b)
+{
+    if (!a.x || !b.x || a.n != b.n) return false;
+    for (int i = 0; i < a.n; ++i) {
+        const bool nan_a = a.y[i] != a.y[i], nan_b = b.y[i] != b.y[i];
+        if (a.x[i] != b.x[i] || (nan_a != nan_b) || (!nan_a && a.y[i] != b.y[i])) return false;
+    }
+    return true;
+}
+
+inline bool tables_di_symmetric(const coffe_b200_tables &T)
+{
+    return same_knots(T.bias[COFFE_B200_BIAS_MAGNIFICATION1], T.bias[COFFE_B200_BIAS_MAGNIFICATION2]) &&
+           same_knots(T.background[COFFE_B200_BG_G1], T.background[COFFE_B200_BG_G2]);
+}
+
+/* The local x integrated piece is the sum of two halves with the roles of the galaxies exchanged, so it has the same mirror
+   symmetry when the two populations are identical in every bias -- except for one reference quirk: the second half of the
+   d1 x lensing term takes (2 - 5 s) at its own end instead of the other one (src/functions.c:2776-2779, SURVEY.md 8a note 1),
+   which only cancels when the magnification bias does not depend on redshift.  (Checked numerically: identical populations with
+   s(z) = 0.1 + 0.05 z break the symmetry of the piece at the 6e-4 level, constant s keeps it to the last bit.) */
+inline bool tables_populations_identical(const coffe_b200_tables &T)
+{
+    return tables_di_symmetric(T) &&
+           same_knots(T.bias[COFFE_B200_BIAS_GALAXY1], T.bias[COFFE_B200_BIAS_GALAXY2]) &&
+           same_knots(T.bias[COFFE_B200_BIAS_EVOLUTION1], T.bias[COFFE_B200_BIAS_EVOLUTION2]);
+}
+
+inline bool tables_magnification_constant(const coffe_b200_tables &T)
+{
+    const coffe_b200_spline &s = T.bias[COFFE_B200_BIAS_MAGNIFICATION1];
+    if (!s.y || s.n < 1) return false;
+    for (int i = 1; i < s.n; ++i)
+        if (s.y[i] != s.y[0]) return false;
+    return true;
+}
+
 /* number of uniformly spaced lambda samples of the line-of-sight table */
 static const int kLosSamples = 512;
 

@@ -22,6 +22,8 @@ struct coffe_b200_ctx {
     std::string err;
     /* tables */
     bool have_tables = false;
+    bool di_mu_symmetric = false;   /* assemble.h: tables_di_symmetric */
+    bool pops_identical = false, mag_constant = false;   /* assemble.h: when the local x integrated piece is mirror symmetric too */
     Arena arena;            /* host copy (set-up and range checks only) */
     Layout layout;
     double *d_arena = nullptr;

@@ -318,17 +318,19 @@ __global__ void expand_items_kernel(const int *__restrict__ point_rule, const in
 /* pm[(point*3 + piece)*n_l + il]; piece 0 (NI) is copied from ni[]; pieces 1 and 2 each have their own mu rule */
 __global__ void reduce_multipoles_kernel(const int n_points,
                                          const int *__restrict__ si_begin, const double *__restrict__ si_mu, const double *__restrict__ si_w,
-                                         const double *__restrict__ si,
+                                         const double *__restrict__ si, const int si_half,
                                          const int *__restrict__ di_begin, const double *__restrict__ di_mu, const double *__restrict__ di_w,
-                                         const double *__restrict__ di,
+                                         const double *__restrict__ di, const int di_half,
                                          const double *__restrict__ ni, const LList ls, double *__restrict__ pm)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n_points) return;
     for (int il = 0; il < ls.n; ++il) {
         double a = 0.0, c = 0.0;
-        for (int i = si_begin[warp] + lane; i < si_begin[warp + 1]; i += 32) a += si_w[i] * legendre_p(ls.l[il], si_mu[i]) * si[i];
-        for (int i = di_begin[warp] + lane; i < di_begin[warp + 1]; i += 32) c += di_w[i] * legendre_p(ls.l[il], di_mu[i]) * di[i];
+        if (!(si_half && (ls.l[il] & 1)))
+            for (int i = si_begin[warp] + lane; i < si_begin[warp + 1]; i += 32) a += si_w[i] * legendre_p(ls.l[il], si_mu[i]) * si[i];
+        if (!(di_half && (ls.l[il] & 1)))
+            for (int i = di_begin[warp] + lane; i < di_begin[warp + 1]; i += 32) c += di_w[i] * legendre_p(ls.l[il], di_mu[i]) * di[i];
         a = warp_sum(a); c = warp_sum(c);
         if (lane == 0) {
             const double pre = 2 * ls.l[il] + 1;
@@ -467,6 +469,8 @@ struct Batch {
     ItemList si, di;                /* local x integrated and integrated x integrated pieces: separate mu rules */
     DevBuf<unsigned int> evals;     /* optional: per-item integrand evaluation counts of the list being launched */
     double chi_max = 0;     /* largest chi2 over the batch: how much of the line-of-sight table to stage */
+    bool di_half = false;   /* the integrated x integrated items cover mu > 0 only (mirror symmetry): odd multipoles of the piece are zero */
+    bool si_half = false;   /* the same for the local x integrated items */
 };
 
 /* mode 1: local x integrated over b.si; mode 2: integrated x integrated over b.di */
@@ -559,8 +563,8 @@ int run_multipole_batch(coffe_b200_ctx *ctx, Batch &b, const LList &ls, const bo
     CK(cudaEventRecord(ctx->ev_k[3], ctx->stream));
     ctx->have_kernel_times = true;
     const int blocks = (b.n_points * 32 + 127) / 128;
-    reduce_multipoles_kernel<<<blocks, 128, 0, ctx->stream>>>(b.n_points, b.si.begin.p, b.si.mu.p, b.si.w.p, b.si.val.p,
-                                                              b.di.begin.p, b.di.mu.p, b.di.w.p, b.di.val.p,
+    reduce_multipoles_kernel<<<blocks, 128, 0, ctx->stream>>>(b.n_points, b.si.begin.p, b.si.mu.p, b.si.w.p, b.si.val.p, b.si_half ? 1 : 0,
+                                                              b.di.begin.p, b.di.mu.p, b.di.w.p, b.di.val.p, b.di_half ? 1 : 0,
                                                               has_ni ? b.ni.p : nullptr, ls, b.pm.p);
     CK(cudaGetLastError());
     ctx->last_launches += 1;
@@ -582,7 +586,7 @@ int run_multipole_batch(coffe_b200_ctx *ctx, Batch &b, const LList &ls, const bo
    rule per distinct separation (`sep`, n_sep entries; point p uses rule point_rule[p]) and uploads those; the
    (point, mu, weight) items are expanded on the device. */
 int build_item_list(coffe_b200_ctx *ctx, const double *sep, const int n_sep, const std::vector<int> &point_rule, const DevBuf<int> &d_point_rule,
-                    const int n_per_panel, const double mu_panel_width, const bool active, ItemList &L)
+                    const int n_per_panel, const double mu_panel_width, const bool half_only, const bool active, ItemList &L)
 {
     const int n = (int)point_rule.size();
     std::vector<int> rule_begin(n_sep + 1, 0), point_begin(n + 1, 0);
@@ -590,7 +594,7 @@ int build_item_list(coffe_b200_ctx *ctx, const double *sep, const int n_sep, con
     for (int r = 0; r < n_sep; ++r) {
         rule_begin[r] = (int)rule_mu.size();
         if (!active) continue;
-        build_mu_rule(ctx->qc, sep[r], mu, w, n_per_panel, mu_panel_width);
+        build_mu_rule(ctx->qc, sep[r], mu, w, n_per_panel, mu_panel_width, half_only);
         rule_mu.insert(rule_mu.end(), mu.begin(), mu.end());
         rule_w.insert(rule_w.end(), w.begin(), w.end());
     }
@@ -625,9 +629,12 @@ int build_multipole_batch(coffe_b200_ctx *ctx, const double *sep, const int n_se
     b.n_points = (int)point_rule.size();
     DevBuf<int> d_point_rule;
     CK(d_point_rule.upload(point_rule, ctx->stream));
-    int rc = build_item_list(ctx, sep, n_sep, point_rule, d_point_rule, ctx->qc.n_mu_panel, ctx->qc.mu_panel_w, opt_has_si(ctx->o), b.si);
+    b.si_half = ctx->pops_identical && (ctx->mag_constant || !(ctx->o.d1 && ctx->o.len));
+    int rc = build_item_list(ctx, sep, n_sep, point_rule, d_point_rule, ctx->qc.n_mu_panel, ctx->qc.mu_panel_w, b.si_half, opt_has_si(ctx->o), b.si);
     if (rc) return rc;
-    return build_item_list(ctx, sep, n_sep, point_rule, d_point_rule, ctx->qc.n_mu_panel_di, ctx->qc.mu_panel_w_di, opt_has_integrated(ctx->o), b.di);
+    b.di_half = ctx->di_mu_symmetric;
+    return build_item_list(ctx, sep, n_sep, point_rule, d_point_rule, ctx->qc.n_mu_panel_di, ctx->qc.mu_panel_w_di, b.di_half,
+                           opt_has_integrated(ctx->o), b.di);
 }
 
 int check_finite(coffe_b200_ctx *ctx, const double *v, const size_t n)
@@ -877,6 +884,9 @@ int coffe_b200_upload_tables(coffe_b200_ctx *ctx, const coffe_b200_tables *T)
     ctx->o.Om = T->omega_matter;
     ctx->o.H0h = T->h / 2997.92458;          /* COFFE_H0 = 1/2997.92458 h/Mpc, src/common.h:75-77 */
     ctx->o.divergent = L.has_divergent;
+    ctx->di_mu_symmetric = tables_di_symmetric(*T);
+    ctx->pops_identical = tables_populations_identical(*T);
+    ctx->mag_constant = tables_magnification_constant(*T);
     ctx->have_tables = true;
     return COFFE_B200_OK;
 }

@@ -103,7 +103,7 @@ inline std::vector<double> build_rpow(const double ratio)
    switches formulas; n-point Gauss-Legendre per panel; mirrored to mu < 0.  Weights are for the measure
    dmu/2, i.e. xi_l = (2l+1) sum_j w_j P_l(mu_j) xi(mu_j)      (src/signal.c:97-110, 541). */
 inline void build_mu_rule(const QuadConfig &q, const double sep, std::vector<double> &mu, std::vector<double> &w, const int n_per_panel = 0,
-                          const double panel_width = 0.0)
+                          const double panel_width = 0.0, const bool half_only = false)
 {
     const int n_mu_panel = n_per_panel > 0 ? n_per_panel : q.n_mu_panel;
     const double mu_panel_w = panel_width > 0.0 ? panel_width : q.mu_panel_w;
@@ -129,6 +129,11 @@ inline void build_mu_rule(const QuadConfig &q, const double sep, std::vector<dou
         }
     }
     const size_t n = mu.size();
+    if (half_only) {
+        /* xi(mu) = xi(-mu): the mu < 0 half is the mirror image, its weight moves onto the mu > 0 nodes (even multipoles) */
+        for (size_t i = 0; i < n; ++i) w[i] *= 2.0;
+        return;
+    }
     for (size_t i = 0; i < n; ++i) { mu.push_back(-mu[i]); w.push_back(w[i]); }
 }
 

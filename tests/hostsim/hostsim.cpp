@@ -29,6 +29,9 @@ struct HostSim {
     int variant = 0;        /* 0 = exact tables, 1 = compact (shared-memory) tables */
     int legacy_di = 0;      /* 1 = di_eval on generic ridge panels instead of di_fast.cuh */
     int di_lanes = 1;       /* lanes emulated by the di_fast path */
+    bool di_half = false;   /* tables_di_symmetric: the integrated x integrated mu rule covers mu > 0 only */
+    bool pops_identical = false, mag_constant = false;
+    bool si_half() const { return pops_identical && (mag_constant || !(o.d1 && o.len)); }
     CompactAccess compact() const { return CompactAccess{&t, CompactView{reinterpret_cast<const unsigned char *>(cb.blob.data()), cb.h}}; }
 };
 
@@ -53,6 +56,9 @@ void *hs_create(const coffe_b200_tables *T, const coffe_b200_options *opt)
     HostSim *s = new HostSim();
     if (!assemble(*T, s->arena, s->layout, s->err)) { fprintf(stderr, "hostsim: %s\n", s->err.c_str()); delete s; return nullptr; }
     s->t = make_view(s->layout, s->arena.buf.data());
+    s->di_half = tables_di_symmetric(*T);
+    s->pops_identical = tables_populations_identical(*T);
+    s->mag_constant = tables_magnification_constant(*T);
     /* line-of-sight table */
     double2 *los = reinterpret_cast<double2 *>(s->arena.buf.data() + s->layout.los);
     for (int i = 0; i < s->layout.los_n; ++i) los_knot(s->t, i, s->layout.los_h, s->layout.chi_max_table, los + (size_t)kLosStride * i);
@@ -199,14 +205,16 @@ void hs_multipoles(void *h, double z, double sep, const int *ls, int n_l, double
     HostSim *s = (HostSim *)h;
     for (int p = 1; p < 3; ++p) {
         std::vector<double> mu, w;
-        build_mu_rule(s->qc, sep, mu, w, p == 1 ? s->qc.n_mu_panel : s->qc.n_mu_panel_di, p == 1 ? s->qc.mu_panel_w : s->qc.mu_panel_w_di);
+        build_mu_rule(s->qc, sep, mu, w, p == 1 ? s->qc.n_mu_panel : s->qc.n_mu_panel_di, p == 1 ? s->qc.mu_panel_w : s->qc.mu_panel_w_di,
+                      p == 2 ? s->di_half : s->si_half());
         const int nm = (int)mu.size();
         std::vector<double> v((size_t)3 * nm);
 #pragma omp parallel for schedule(dynamic, 1)
         for (int im = 0; im < nm; ++im) item_pieces(h, z, sep, mu[im], p == 1 ? 2 : 4, &v[(size_t)3 * im]);
         for (int il = 0; il < n_l; ++il) {
             double acc = 0.0;
-            for (int im = 0; im < nm; ++im) acc += w[im] * legendre_p(ls[il], mu[im]) * v[(size_t)3 * im + p];
+            if (!((p == 2 ? s->di_half : s->si_half()) && (ls[il] & 1)))
+                for (int im = 0; im < nm; ++im) acc += w[im] * legendre_p(ls[il], mu[im]) * v[(size_t)3 * im + p];
             out[p * n_l + il] = (2 * ls[il] + 1) * acc;
         }
     }
@@ -227,14 +235,14 @@ void hs_eval_counts(void *h, double z, double sep, double *out)
     std::vector<double> mu, w;
     const double chi_mean = bg_chi(s->t.bg, z);
     out[0] = out[1] = 0.0;
-    build_mu_rule(s->qc, sep, mu, w, s->qc.n_mu_panel);
+    build_mu_rule(s->qc, sep, mu, w, s->qc.n_mu_panel, 0.0, s->si_half());
     for (size_t im = 0; im < mu.size(); ++im) {
         const Geometry g = geometry(chi_mean, sep, mu[im]);
         const EndVals e1 = end_eval(s->o, s->t, g.chi1, 1), e2 = end_eval(s->o, s->t, g.chi2, 2);
         const SIHalf ha = si_half_setup(s->o, g, e1, e2, true), hb = si_half_setup(s->o, g, e2, e1, false);
         out[0] += si_eval_count(s->q, g, ha) + si_eval_count(s->q, g, hb);
     }
-    build_mu_rule(s->qc, sep, mu, w, s->qc.n_mu_panel_di, s->qc.mu_panel_w_di);
+    build_mu_rule(s->qc, sep, mu, w, s->qc.n_mu_panel_di, s->qc.mu_panel_w_di, s->di_half);
     for (size_t im = 0; im < mu.size(); ++im) {
         const Geometry g = geometry(chi_mean, sep, mu[im]);
         const EndVals e1 = end_eval(s->o, s->t, g.chi1, 1), e2 = end_eval(s->o, s->t, g.chi2, 2);
