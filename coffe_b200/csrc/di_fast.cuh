@@ -156,8 +156,8 @@ COFFE_HD DIPanels di_panels(const Rules &q, const DIFast &f, const DIOuter &o)
     p.b_neg = o.c0;
     p.a_neg = o.c0 > f.chi2 ? o.c0 - f.chi2 : 0.0;
     p.b_pos = f.chi2 - o.c0;
-    p.k_neg = panel_count(p.plan, p.b_neg);
-    p.k_pos = p.b_pos > 0.0 ? panel_count(p.plan, p.b_pos) : 0;
+    p.k_neg = panel_count_by_break(p.plan, p.b_neg);
+    p.k_pos = p.b_pos > 0.0 ? panel_count_by_break(p.plan, p.b_pos) : 0;
     p.k_pair = 0;
     if (p.a_neg == 0.0 && p.k_pos > 0 && p.k_neg > 0) {
         const double bmin = p.b_neg < p.b_pos ? p.b_neg : p.b_pos;
@@ -216,6 +216,65 @@ COFFE_HD double di_inner_partial(const DISideCtx<TA> &cx, const Rules &q, const 
     return acc;
 }
 
+#if defined(__CUDA_ARCH__)
+/* The same sum on a full warp, with the panel bookkeeping done by the warp instead of by every lane: lane k holds the break
+   B_k, the panel counts are ballots, and a panel's ends are two shuffles (profiles/README.md: the scalar bookkeeping -- doubling
+   loops, per-iteration break formulas -- was 15 % of the kernel's instructions with ~3 inner iterations per outer node).  Same
+   breaks, same counts, same nodes, same summation order as di_inner_partial: bit-identical.  Only valid when a side never has more
+   than 31 panels and the panel rule is staged (q.panel_x): the host checks the configured plan (rules_build.h: di_side_panels) and
+   launches the WARP_PANELS instantiation of the kernel. */
+template <bool ALL, class TA>
+__device__ __forceinline__ double di_inner_partial_warp(const DISideCtx<TA> &cx, const Rules &q, const DIFast &f, const DIOuter &o, const int lane)
+{
+    const unsigned int full = 0xffffffffu;
+    const int np = q.n_panel_di;            /* <= 32 (the caller checks) */
+    const int ppi = 32 / np;
+    const int lp = lane / np, j = lane - lp * np;
+    const bool on = lp < ppi;
+    const PanelPlan plan = panel_plan(sqrt(o.eps2), q.eps_min, q.panel_w_di, q.panel_du_di, q.tail_ratio_di, q.rpow_di, q.geo_shift_di);
+    const double brk = panel_break(plan, lane);
+    const double b_neg = o.c0, a_neg = o.c0 > f.chi2 ? o.c0 - f.chi2 : 0.0, b_pos = f.chi2 - o.c0;
+    const int k_neg = b_neg > 0.0 ? __popc(__ballot_sync(full, brk < b_neg)) : 0;
+    const int k_pos = b_pos > 0.0 ? __popc(__ballot_sync(full, brk < b_pos)) : 0;
+    int k_pair = 0;
+    if (a_neg == 0.0 && k_pos > 0 && k_neg > 0) {
+        const double bmin = b_neg < b_pos ? b_neg : b_pos;
+        const int kc = k_neg < k_pos ? k_neg : k_pos;
+        k_pair = __shfl_sync(full, brk, kc) > bmin ? kc - 1 : kc;
+    }
+    const double xj = q.panel_x[j], wj = q.panel_w[j];
+    double acc = 0.0;
+    for (int k0 = 0; k0 < k_pair; k0 += ppi) {
+        const int k = k0 + lp;
+        const double lo = __shfl_sync(full, brk, k & 31), up = __shfl_sync(full, brk, (k + 1) & 31);
+        if (on && k < k_pair) {
+            const double w = up - lo;
+            const double d = fma(w, xj, lo);
+            const DIShared s = di_shared(*cx.ta, f, o, d);
+            const double v = di_side<ALL>(cx, f, o, s, o.c0 - d) + di_side<ALL>(cx, f, o, s, o.c0 + d);
+            acc = fma(w * wj, v, acc);
+        }
+    }
+    const int n_negl = k_neg - k_pair, n_left = n_negl + (k_pos - k_pair);
+    for (int e0 = 0; e0 < n_left; e0 += ppi) {
+        const int e = e0 + lp;
+        const bool neg = e < n_negl;
+        const int k = k_pair + (neg ? e : e - n_negl);
+        double lo = __shfl_sync(full, brk, k & 31), up = __shfl_sync(full, brk, (k + 1) & 31);
+        const double a = neg ? a_neg : 0.0, b = neg ? b_neg : b_pos;
+        if (lo < a) lo = a;
+        if (up > b) up = b;
+        if (on && e < n_left && up > lo) {
+            const double w = up - lo;
+            const double d = fma(w, xj, lo);
+            const DIShared s = di_shared(*cx.ta, f, o, d);
+            acc = fma(w * wj, di_side<ALL>(cx, f, o, s, neg ? o.c0 - d : o.c0 + d), acc);
+        }
+    }
+    return acc;
+}
+#endif
+
 COFFE_HD unsigned int di_inner_eval_count(const Rules &q, const DIFast &f, const DIOuter &o)
 {
     const DIPanels p = di_panels(q, f, o);
@@ -227,7 +286,7 @@ COFFE_HD unsigned int di_inner_eval_count(const Rules &q, const DIFast &f, const
 
 /* integrated x integrated piece per unit (x1, x2).  Outer nodes strided over `ngroups` groups of `nlanes` lanes;
    `row` is the group's own buffer of t.ren2d.n double2 (renormalisation row), unused without the divergent terms. */
-template <class TA>
+template <class TA, bool WARP_PANELS = false>
 COFFE_HD double di_fast_partial(const TA &ta, const Tables &t, const double2 *los, const Rules &q, const Geometry &g, const DIConst &k,
                                 double2 *row, const int group, const int ngroups, const int lane, const int nlanes,
                                 const bool serial_fill = false /* CPU harness: lanes run one after the other, each fills the whole row */)
@@ -249,6 +308,12 @@ COFFE_HD double di_fast_partial(const TA &ta, const Tables &t, const double2 *lo
             COFFE_SYNC_LANES();
         }
         const bool all = f.any_ll && f.any_pl && f.any_ren && o.eps2 > 1e-12;
+#if defined(__CUDA_ARCH__) && !defined(COFFE_NO_WARP_PANELS)
+        if (WARP_PANELS) {
+            acc = fma(outer_w[io], all ? di_inner_partial_warp<true>(cx, q, f, o, lane) : di_inner_partial_warp<false>(cx, q, f, o, lane), acc);
+            continue;
+        }
+#endif
         acc = fma(outer_w[io], all ? di_inner_partial<true>(cx, q, f, o, lane, nlanes) : di_inner_partial<false>(cx, q, f, o, lane, nlanes), acc);
     }
     return acc / g.chi2;

@@ -246,6 +246,9 @@ constexpr int kDIThreads = COFFE_DI_THREADS;        /* upper bound (register all
    weights of the inner panel rule */
 constexpr int kDISmallDoubles = kMaxTail + 2 * 32;
 
+/* WARP_PANELS: the panel bookkeeping of the inner integral lives in the lanes of the warp (di_fast.cuh: di_inner_partial_warp);
+   the host selects it when the configured plan never has more than 31 panels on a side (the default plan: 29) */
+template <bool WARP_PANELS>
 __global__ void __launch_bounds__(kDIThreads, 1) di_items_smem_kernel(
     const __grid_constant__ Tables t, const __grid_constant__ Options o, const __grid_constant__ Rules q,
     const __grid_constant__ CompactHeader ch, const uint4 *__restrict__ blob, const int stage_bytes,
@@ -296,7 +299,7 @@ __global__ void __launch_bounds__(kDIThreads, 1) di_items_smem_kernel(
         __syncwarp();
         const DIConst k = ws.k;
         if (out_evals && lane == 0) out_evals[item] = di_fast_eval_count(ql, g, k);
-        double di = di_fast_partial(ta, t, los_s, ql, g, k, row, 0, 1, lane, 32);
+        double di = di_fast_partial<CompactAccess, WARP_PANELS>(ta, t, los_s, ql, g, k, row, 0, 1, lane, 32);
         di = warp_sum(di);
         if (lane == 0) out[item] = di;
         __syncwarp();
@@ -511,8 +514,11 @@ int launch_integrated(coffe_b200_ctx *ctx, Batch &b, const int mode, unsigned in
                     L.point.p, L.mu.p, L.n, stage_n, panel_cap, L.val.p, evals, ctx->d_counter);
             }
             else {
-                CK(cudaFuncSetAttribute(di_items_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-                di_items_smem_kernel<<<grid, threads, need, ctx->stream>>>(
+                const bool warp_panels = ctx->qc.n_panel_di <= 32 &&
+                                         di_side_panels(ctx->qc, std::max(2.0e4, 1.01 * ctx->layout.chi_max_table)) <= 31;
+                auto kernel = warp_panels ? di_items_smem_kernel<true> : di_items_smem_kernel<false>;
+                CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+                kernel<<<grid, threads, need, ctx->stream>>>(
                     ctx->t, ctx->o, make_rules(ctx), ch, reinterpret_cast<const uint4 *>(ctx->d_blob), stage_bytes, b.pz.p, b.psep.p,
                     L.point.p, L.mu.p, L.n, stage_n, L.val.p, evals, ctx->d_counter);
             }

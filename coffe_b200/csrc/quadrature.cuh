@@ -41,8 +41,11 @@ COFFE_HD PanelPlan panel_plan(double eps, const double eps_min, const double W, 
     int J = 0;
     double b = 0.0;
     if (eps < W) {          /* otherwise the cusp is wider than a uniform panel: uniform panels from d = 0 */
-        J = 1; b = eps;
-        while (b < W) { b = ldexp(b, shift); ++J; }
+        /* J - 1 = smallest m >= 1 with eps 2^(shift m) >= W, from the exponents (exact: the same J and B_J as repeated doubling) */
+        const int e0 = ilogb(W) - ilogb(eps);
+        const int n = ldexp(eps, e0) >= W ? e0 : e0 + 1;         /* smallest n with eps 2^n >= W; n >= 1 here */
+        const int m = (n + shift - 1) / shift;
+        J = m + 1; b = ldexp(eps, shift * m);
     }
     p.J = J; p.BJ = b;
     int M = 0;
@@ -74,6 +77,18 @@ COFFE_HD int panel_count(const PanelPlan &p, const double b)
     if (b > p.BJ || p.J == 0) return p.J + (int)ceil((b - p.BJ) / p.W);
     double e = p.eps;
     while (e < b) { e = ldexp(e, p.shift); ++k; }
+    return k;
+}
+
+/* the same count from the breaks themselves: smallest k >= 1 with B_k >= b.  This is the definition the integrated x integrated
+   kernel uses (its warp holds B_0..B_31 in its lanes and counts with one ballot, di_fast.cuh); it differs from panel_count only
+   when b sits within rounding of a uniform break, where the extra panel is a few ulp wide. */
+COFFE_HD int panel_count_by_break(const PanelPlan &p, const double b)
+{
+    if (b <= 0.0) return 0;
+    const int k_max = p.J + p.M + kMaxTail - 1;
+    int k = 1;
+    while (k < k_max && panel_break(p, k) < b) ++k;
     return k;
 }
 

@@ -63,6 +63,17 @@ inline int max_panels(const QuadConfig &q, const double extent = 2.0e4)
     return 2 * (geo + uni + tail);
 }
 
+/* upper bound on the panels of ONE side of the ridge of the integrated x integrated plan (its own knobs) */
+inline int di_side_panels(const QuadConfig &q, const double extent = 2.0e4)
+{
+    const int geo = q.eps_min < q.panel_w_di ? (int)std::ceil(std::log2(q.panel_w_di / q.eps_min) / q.geo_shift_di) + 2 : 0;
+    const int uni = (int)std::ceil(q.panel_du_di / q.panel_w_di) + 1;
+    const double start = std::max(q.panel_du_di, q.panel_w_di);
+    const int tail = extent > start ? (int)std::ceil(std::log(extent / start) / std::log(q.tail_ratio_di)) + 2 : 0;
+    if (tail >= kMaxTail) return 1 << 30;
+    return geo + uni + tail;
+}
+
 inline bool quadrature_valid(const QuadConfig &q, const int panel_capacity)
 {
     if (!(q.panel_w > 0 && q.eps_min > 0 && q.tail_ratio > 1.0 && q.panel_du >= 0)) return false;

@@ -258,6 +258,8 @@ COFFE_HD double renorm2d_eval(const Renorm2DView &t, const double x, const doubl
    dy d/dy} at y_j.  ren_row_eval(row, y) is then the same bicubic patch as renorm2d_eval(x, y) with the sums
    reassociated: the integrated x integrated kernel fills one row per outer line-of-sight node (cooperatively,
    `nlanes` lanes) and every inner node costs one 1-D Hermite lookup instead of a 16-term patch. */
+/* knots per lane in flight in ren_row_fill (3 measured slower: the extra registers spill) */
+static const int kRowInFlight = 2;
 COFFE_HD void ren_row_fill(const Renorm2DView &t, const double x, const int n_row, double2 *row, const int lane, const int nlanes)
 {
     const double sx = (x - t.x0) * t.inv_dx;
@@ -267,16 +269,16 @@ COFFE_HD void ren_row_fill(const Renorm2DView &t, const double x, const int n_ro
     const double tt = sx - xi, t2 = tt * tt, t3 = t2 * tt;
     const double h00 = 2 * t3 - 3 * t2 + 1, h10 = (t3 - 2 * t2 + tt) * t.dx, h01 = -2 * t3 + 3 * t2, h11 = (t3 - t2) * t.dx;
     const double4 *a = t.nodeT + (size_t)xi * t.n, *b = a + t.n;
-    /* two rows per lane in flight: the loads come from L2 and nothing else can hide their latency here */
-    for (int j0 = lane; j0 < n_row; j0 += 2 * nlanes) {
-        double4 p[2], q[2];
+    /* kRowInFlight knots per lane in flight: the loads come from L2 and nothing else can hide their latency here */
+    for (int j0 = lane; j0 < n_row; j0 += kRowInFlight * nlanes) {
+        double4 p[kRowInFlight], q[kRowInFlight];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < kRowInFlight; ++u) {
             const int j = j0 + u * nlanes;
             if (j < n_row) { p[u] = a[j]; q[u] = b[j]; }
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < kRowInFlight; ++u) {
             const int j = j0 + u * nlanes;
             if (j < n_row) {
                 double2 o;
