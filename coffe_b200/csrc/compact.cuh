@@ -12,8 +12,8 @@
 //     every quarter octave [2^e (1 + q/4), 2^e (1 + (q+1)/4)) is a region split into 2^m equal intervals,
 //     m chosen per region by the builder (compact_build.h) so that the resampling error stays below a
 //     tolerance within a knot budget.  The interval index, the left knot and 1/h come straight from the
-//     bits of R -- no logarithm, no knot array, no fix-up loop.  All eight functions of a knot are
-//     interleaved (128 B + 16 B padding so that lanes on different knots fall on different banks);
+//     bits of R -- no logarithm, no knot array, no fix-up loop.  All functions of a knot are
+//     interleaved in one 112-byte record (kKnotBytes below);
 //   * I^4_0: resampled onto the same binary grid as the ninth function of a knot (what the integrated x
 //     integrated kernel reads); the reference's 297 hand-picked knots (src/integrals.c:76-96) are kept as
 //     exact cubics behind a bucket table on exponent + 5 mantissa bits for R < r_lo and for the
@@ -25,9 +25,16 @@
 
 namespace coffe {
 
-static const int kKnotStride = 18;      /* doubles per compact knot: 9 x {f, h f'}: the eight I^n_l of the family, then I^4_0
-                                           (zero without the divergent tables); 144 B, so lanes on neighbouring knots
-                                           fall on different 16-byte bank groups */
+static const int kKnotStride = 18;      /* doubles per knot in the builder's working copy: 9 x {f, h f'}: the eight I^n_l of the family, then I^4_0
+                                           (zero without the divergent tables) */
+/* A knot as it is staged in shared memory: the nine values as doubles, the nine scaled slopes h f' as the upper 32 bits of their
+   doubles (20-bit mantissa, rounded to nearest by the builder; the low word is zero when the value is rebuilt, which costs no
+   conversion instruction), 4 bytes of padding: 112 B instead of 144.  The integrated kernels run at 81 % of the shared-memory /
+   L1 data pipe (profiles/r1_di_kernel_cfg5_v40_ncu.txt), so bytes per lookup are what they pay for.  A slope enters the Hermite
+   form with weight |h10|, |h11| <= 4/27 and |h f'| is a fraction of the local envelope, so its 2.4e-7 relative rounding moves
+   the interpolant by < 4e-8 of the envelope -- the builder's error check (region_fill) runs on the rounded slopes and
+   reports it inside max_rel_error.  A 112-byte stride is 7 bank groups of 16 bytes: neighbouring knots fall on different ones. */
+static const int kKnotBytes = 112;
 static const int N_ITAB9 = N_ITAB + 1;
 static const int kSmallStride = 34;     /* doubles per small-r interval: 8 x double4 + 2 padding */
 
@@ -56,6 +63,71 @@ COFFE_D double from_hi_word(const int hi) { return __hiloint2double(hi, 0); }
 inline int hi_word(const double v) { long long b; memcpy(&b, &v, 8); return (int)(b >> 32); }
 inline double from_hi_word(const int hi) { const long long b = (long long)(unsigned int)hi << 32; double v; memcpy(&v, &b, 8); return v; }
 #endif
+
+/* h f' as stored: the double rounded to its upper 32 bits */
+COFFE_HD int slope_word(const double v)
+{
+#if defined(__CUDA_ARCH__)
+    const long long b = __double_as_longlong(v);
+#else
+    long long b; memcpy(&b, &v, 8);
+#endif
+    return (int)((unsigned long long)(b + 0x80000000LL) >> 32);
+}
+COFFE_HD double slope_rounded(const double v) { return from_hi_word(slope_word(v)); }
+
+/* the 16-byte words of a packed knot */
+struct KnotWord { int x, y, z, w; };
+COFFE_HD double word_pair(const int lo, const int hi)
+{
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(hi, lo);
+#else
+    const long long b = ((long long)(unsigned int)hi << 32) | (unsigned int)lo; double v; memcpy(&v, &b, 8); return v;
+#endif
+}
+
+/* Layout of a packed knot (byte offsets): two groups of four functions, {f0 f1 | f2 f3 | d0 d1 d2 d3} at 0 and
+   {f4 f5 | f6 f7 | d4 d5 d6 d7} at 48 (values as doubles, slopes as 32-bit words), then {f8 | d8, padding} at 96: a group is
+   evaluated as soon as its three 16-byte words of the two knots have arrived, so few registers are live at a time. */
+static const int kKnotGroupBytes = 48;
+COFFE_HD int knot_value_offset(const int f) { return f < 8 ? (f >> 2) * kKnotGroupBytes + (f & 3) * 8 : 96; }
+COFFE_HD int knot_slope_offset(const int f) { return f < 8 ? (f >> 2) * kKnotGroupBytes + 32 + (f & 3) * 4 : 104; }
+
+COFFE_HD void knot_words(const unsigned char *p, KnotWord &w)
+{
+#if defined(__CUDA_ARCH__)
+    const int4 v = *reinterpret_cast<const int4 *>(p);
+    w.x = v.x; w.y = v.y; w.z = v.z; w.w = v.w;
+#else
+    memcpy(&w, p, 16);
+#endif
+}
+
+/* Hermite interpolant of functions 4g..4g+3 between the knots at k0 and k1 */
+template <class HB>
+COFFE_HD void knot_group_eval(const unsigned char *k0, const unsigned char *k1, const int g, const HB &hb, double *out)
+{
+    const double2 *q0 = reinterpret_cast<const double2 *>(k0 + g * kKnotGroupBytes), *q1 = reinterpret_cast<const double2 *>(k1 + g * kKnotGroupBytes);
+    const double2 a0 = q0[0], a1 = q0[1], b0 = q1[0], b1 = q1[1];
+    KnotWord s0, s1;
+    knot_words(k0 + g * kKnotGroupBytes + 32, s0);
+    knot_words(k1 + g * kKnotGroupBytes + 32, s1);
+    out[0] = hermite_eval(hb, a0.x, from_hi_word(s0.x), b0.x, from_hi_word(s1.x));
+    out[1] = hermite_eval(hb, a0.y, from_hi_word(s0.y), b0.y, from_hi_word(s1.y));
+    out[2] = hermite_eval(hb, a1.x, from_hi_word(s0.z), b1.x, from_hi_word(s1.z));
+    out[3] = hermite_eval(hb, a1.y, from_hi_word(s0.w), b1.y, from_hi_word(s1.w));
+}
+
+/* the ninth function (I^4_0) */
+template <class HB>
+COFFE_HD double knot_tail_eval(const unsigned char *k0, const unsigned char *k1, const HB &hb)
+{
+    KnotWord t0, t1;
+    knot_words(k0 + 96, t0);
+    knot_words(k1 + 96, t1);
+    return hermite_eval(hb, word_pair(t0.x, t0.y), from_hi_word(t0.z), word_pair(t1.x, t1.y), from_hi_word(t1.z));
+}
 
 /* view of a staged blob (shared memory on the device, host memory in the CPU harness) */
 struct CompactView {
@@ -94,18 +166,15 @@ COFFE_HD void compact_ifam_all(const CompactView &c, const double r, double out[
     const double h01 = u2 * fma(-2.0, u, 3.0);      /* 3u^2 - 2u^3 */
     const double h10 = u * um1 * um1;
     const double h11 = u2 * um1;
-    const double2 *k0 = reinterpret_cast<const double2 *>(c.base + c.h.off_knots + (size_t)idx * kKnotStride * 8);
-    const double2 *k1 = k0 + kKnotStride / 2;
-#pragma unroll
-    for (int t = 0; t < N_ITAB; ++t) {
-        const double2 a = k0[t], b = k1[t];
-        out[t] = fma(h01, b.x - a.x, fma(h10, a.y, fma(h11, b.y, a.x)));
-    }
+    const unsigned char *k0 = c.base + c.h.off_knots + (size_t)idx * kKnotBytes;
+    HermiteBasis hb; hb.h01 = h01; hb.h10 = h10; hb.h11 = h11;
+    knot_group_eval(k0, k0 + kKnotBytes, 0, hb, out);
+    knot_group_eval(k0, k0 + kKnotBytes, 1, hb, out + 4);
 }
 
 COFFE_HD double compact_i40(const CompactView &c, const double r);
 
-/* the eight I^n_l and (when want_i40) I^4_0 at r: one index computation, one Hermite basis, 2 x 9 16-byte loads */
+/* the eight I^n_l and (when want_i40) I^4_0 at r: one index computation, one Hermite basis, 2 x 7 16-byte loads */
 COFFE_HD void compact_ifam9(const CompactView &c, const double r, double out[N_ITAB9], const bool want_i40)
 {
     const int hi = hi_word(r);
@@ -122,18 +191,10 @@ COFFE_HD void compact_ifam9(const CompactView &c, const double r, double out[N_I
     const double xj = from_hi_word(hi & (int)(~0u << rg.y));
     const double inv_h = from_hi_word((2046 + 20 - rg.y - (hi >> 20)) << 20);
     const HermiteBasis hb = hermite_basis((r - xj) * inv_h);
-    const double2 *k0 = reinterpret_cast<const double2 *>(c.base + c.h.off_knots + (size_t)idx * kKnotStride * 8);
-    const double2 *k1 = k0 + kKnotStride / 2;
-#pragma unroll
-    for (int t = 0; t < N_ITAB; ++t) {
-        const double2 a = k0[t], b = k1[t];
-        out[t] = hermite_eval(hb, a.x, a.y, b.x, b.y);
-    }
-    if (want_i40) {
-        const double2 a = k0[N_ITAB], b = k1[N_ITAB];
-        out[N_ITAB] = hermite_eval(hb, a.x, a.y, b.x, b.y);
-    }
-    else out[N_ITAB] = 0.0;
+    const unsigned char *k0 = c.base + c.h.off_knots + (size_t)idx * kKnotBytes;
+    knot_group_eval(k0, k0 + kKnotBytes, 0, hb, out);
+    knot_group_eval(k0, k0 + kKnotBytes, 1, hb, out + 4);
+    out[N_ITAB] = want_i40 ? knot_tail_eval(k0, k0 + kKnotBytes, hb) : 0.0;
 }
 
 COFFE_HD double compact_i40(const CompactView &c, const double r)

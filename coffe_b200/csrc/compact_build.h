@@ -136,11 +136,12 @@ inline void region_fill(const FamilyRef &F, Region &R, const double tol)
     for (int j = 0; j <= n; ++j) {
         double v[N_ITAB], d[N_ITAB];
         family_value_deriv(F, R.lo + j * h, v, d);
-        for (int f = 0; f < N_ITAB; ++f) { R.knots[(size_t)j * kKnotStride + 2 * f] = v[f]; R.knots[(size_t)j * kKnotStride + 2 * f + 1] = h * d[f]; }
+        /* slopes as they are stored (compact.cuh: kKnotBytes): the error check below sees the rounded values */
+        for (int f = 0; f < N_ITAB; ++f) { R.knots[(size_t)j * kKnotStride + 2 * f] = v[f]; R.knots[(size_t)j * kKnotStride + 2 * f + 1] = slope_rounded(h * d[f]); }
         if (F.div) {
             double der = 0.0;
             R.knots[(size_t)j * kKnotStride + 2 * N_ITAB] = hspline_eval_deriv(F.t->i40, R.lo + j * h, &der);
-            R.knots[(size_t)j * kKnotStride + 2 * N_ITAB + 1] = h * der;
+            R.knots[(size_t)j * kKnotStride + 2 * N_ITAB + 1] = slope_rounded(h * der);
         }
     }
     /* error at three interior points per interval */
@@ -256,7 +257,7 @@ inline bool build_compact(const Tables &t, const Layout &L, const int knot_budge
     H.off_knots = alloc_bytes(0);
     size_t nk = total_knots();
     H.n_knots = (int)nk;
-    alloc_bytes(nk * kKnotStride * 8);
+    alloc_bytes(nk * kKnotBytes);
     H.bytes = (int)(B.size() * 8);
     H.r_lo = r_lo;
     H.max_rel_error = max_err;
@@ -264,13 +265,23 @@ inline bool build_compact(const Tables &t, const Layout &L, const int knot_budge
     unsigned char *base = reinterpret_cast<unsigned char *>(B.data());
     {
         int2 *rg = reinterpret_cast<int2 *>(base + H.off_region);
-        double *kn = reinterpret_cast<double *>(base + H.off_knots);
+        unsigned char *kn = base + H.off_knots;
         int first = 0;
         out.region_m.clear();
         for (int i = 0; i < n_region; ++i) {
             rg[i].x = first; rg[i].y = 18 - regs[i].m;
-            std::copy(regs[i].knots.begin(), regs[i].knots.end(), kn + (size_t)first * kKnotStride);
-            first += (1 << regs[i].m) + 1;
+            /* pack (compact.cuh: knot_value_offset / knot_slope_offset) */
+            const int nk_reg = (1 << regs[i].m) + 1;
+            for (int j = 0; j < nk_reg; ++j) {
+                const double *src = &regs[i].knots[(size_t)j * kKnotStride];
+                unsigned char *dst = kn + (size_t)(first + j) * kKnotBytes;
+                for (int f = 0; f < N_ITAB9; ++f) {
+                    std::memcpy(dst + knot_value_offset(f), &src[2 * f], 8);
+                    const int w = slope_word(src[2 * f + 1]);
+                    std::memcpy(dst + knot_slope_offset(f), &w, 4);
+                }
+            }
+            first += nk_reg;
             out.region_m.push_back(regs[i].m);
         }
     }
@@ -313,7 +324,7 @@ inline int compact_stage_bytes(const CompactBuild &cb, const double r_need)
     if (reg < 0) reg = 0;
     int knots = H.n_knots;
     if (reg + 1 < H.n_region) knots = rg[reg + 1].x;
-    return H.off_knots + knots * kKnotStride * 8;
+    return (H.off_knots + knots * kKnotBytes + 15) / 16 * 16;
 }
 
 }  // namespace coffe

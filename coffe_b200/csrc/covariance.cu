@@ -447,9 +447,7 @@ int fill_G_fftlog(coffe_b200_ctx *ctx, const coffe_b200_covariance_params *p, co
     CK(d_F.alloc((size_t)2 * 2 * N));          /* two spectra (P, P^2), complex */
     CK(d_fw.alloc((size_t)2 * 2 * N));
     CK(d_T.alloc((size_t)n_l * (half + 1) * 2));
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, ctx->device));
-    const int n_cta = 2 * prop.multiProcessorCount;
+    const int n_cta = 2 * ctx->n_sm;
     CK(d_work.alloc((size_t)n_cta * 2 * N * 2));
     CK(d_Y.alloc((size_t)n_sub * (half + 1) * 2));
     CK(d_R.alloc((size_t)n_sub * n_sub));
@@ -569,9 +567,7 @@ extern "C" int coffe_b200_covariance(coffe_b200_ctx *ctx, const coffe_b200_covar
     CK(d_l.upload(std::vector<int>(p->l, p->l + n_l), ctx->stream));
     const int M = n_l * n_sep, Mpad = ((M + kTile - 1) / kTile) * kTile;
     const int tiles = Mpad / kTile;
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, ctx->device));
-    int n_splits = std::max(1, (4 * prop.multiProcessorCount) / (tiles * tiles));
+    int n_splits = std::max(1, (4 * ctx->n_sm) / (tiles * tiles));
     const int chunk = std::max(kKc, std::min(n_nodes, (int)std::min<size_t>((size_t)1 << 31, ((size_t)2 << 30) / ((size_t)Mpad * 8))));
     if (n_splits > (chunk + kKc - 1) / kKc) n_splits = (chunk + kKc - 1) / kKc;
     CK(d_W.alloc((size_t)2 * n_nodes));

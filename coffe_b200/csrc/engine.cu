@@ -494,7 +494,7 @@ int launch_integrated(coffe_b200_ctx *ctx, Batch &b, const int mode, unsigned in
         /* shared-memory tables: blob prefix covering R <= 2 chi_max, line-of-sight table, per-warp state */
         const int stage_bytes = compact_stage_bytes(ctx->compact, 2.0 * b.chi_max);
         CompactHeader ch = ctx->compact.h;
-        ch.n_knots = (stage_bytes - ch.off_knots) / (kKnotStride * 8);
+        ch.n_knots = (stage_bytes - ch.off_knots) / kKnotBytes;
         const int panel_cap = max_panels(ctx->qc);
         const size_t fixed = (size_t)stage_bytes + los_bytes + (mode == 1 ? 0 : kDISmallDoubles * sizeof(double));
         const size_t per_warp = mode == 1 ? sizeof(SIWarpState) + (size_t)2 * panel_cap * sizeof(double) : sizeof(DIWarpState) + row_bytes;
@@ -1261,9 +1261,7 @@ int coffe_b200_fp64_peak(coffe_b200_ctx *ctx, double *tflops)
     if (!ctx || !tflops) return COFFE_B200_EINVAL;
     COFFE_ENTER(ctx);
     CK(cudaSetDevice(ctx->device));
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, ctx->device));
-    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+    const int blocks = ctx->n_sm * 8, threads = 256, iters = 1 << 16;
     DevBuf<double> out;
     CK(out.alloc((size_t)blocks * threads));
     double best = 0;
