@@ -146,10 +146,15 @@ def cpu_baseline(z, sep, ls, budget_points=72):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one di_items_smem_kernel launch on this very workload (cfg5, one GPU), from
-# the ncu --set full capture summarised in profiles/r1_di_kernel_cfg5_v37_ncu.txt: 73.6 MB read + 58.8 MB written in a 399 ms
+# the ncu --set full capture summarised in profiles/r1_di_kernel_cfg5_v41_ncu.txt: 19.04 MB read + 15 KB written in a 169 ms
 # launch.  Algorithmic bytes of that launch: the (point, mu) items in (12 B each), one double per item out, the 6 MB of tables
-# once = ~60 MB; either way ~0.3 GB/s -- the kernel does not stream HBM (L2 hit rate 99.98 %), its bound is the FP64 pipe.
-TRAFFIC_BYTES_PER_LAUNCH_CFG5_1GPU = 1.3238e8
+# once = ~45 MB (the items are expanded on the device by the step's own expand_items_kernel and are still in L2); either way
+# ~0.1 GB/s -- the kernel does not stream HBM (L2 hit rate 99.97 %).  Its ceiling is on-chip: the same capture has the L1 /
+# shared-memory data pipe at 77 % of peak (81 % before the knots were packed) and the FP64 pipe at 36 %.
+TRAFFIC_BYTES_PER_LAUNCH_CFG5_1GPU = 1.9051e7
+NCU_PIPES_CFG5_1GPU = {"source": "profiles/r1_di_kernel_cfg5_v41_ncu.txt (ncu --set full of this kernel on this workload)",
+                       "l1tex_data_pipe_pct_of_peak": 76.7, "shared_memory_pct_of_peak": 58.2, "fp64_pipe_pct_of_peak": 35.6,
+                       "issue_active_pct": 43.0}
 
 
 def covariance_cfg4(eng, args):
@@ -313,7 +318,8 @@ def main():
             "roofline": {"bound": "fp64", "kernel": "di_items_smem_kernel", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved / peak_tf if peak_tf and achieved else None,
                          "traffic": TRAFFIC_BYTES_PER_LAUNCH_CFG5_1GPU if (world == 1 and args.nz == 32 and args.nsep == 1000) else None,
-                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_di_kernel_cfg5_v37_ncu.txt",
+                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_di_kernel_cfg5_v41_ncu.txt",
+                         "ncu_pipes": NCU_PIPES_CFG5_1GPU if (world == 1 and args.nz == 32 and args.nsep == 1000) else None,
                          "peak_source": "DFMA probe kernel measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                          "launch_ms": di_launch_ms, "share_of_step": di_ms_max / dev_ms_max if dev_ms_max else None,
                          "flops_per_launch": F_DI * n_di / world, "accounting": "SURVEY.md 8d: 450 flop per DI integrand evaluation",

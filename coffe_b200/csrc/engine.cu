@@ -21,6 +21,8 @@
 #include <mutex>
 #include <string>
 #include <vector>
+#include <chrono>
+#include <cstdlib>
 
 #include "ctx.h"
 
@@ -758,14 +760,24 @@ int plan_fetch(coffe_b200_plan &pl, std::vector<double> &hm)
 int multipoles_core(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double *sep, int n_sep, const int *l, int n_l,
                     long begin, long end, std::vector<double> &hm)
 {
+    /* COFFE_B200_TRACE=1: host-side phase times of the call on stderr (set-up and launch, result copy queued, device done) */
+    static const bool trace = std::getenv("COFFE_B200_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto ms_since = [&](const std::chrono::steady_clock::time_point &a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
     coffe_b200_plan pl;
     int rc = plan_build(ctx, z_mean, n_z, sep, n_sep, l, n_l, begin, end, pl);
     if (rc) return rc;
+    const double t_build = ms_since(t0);
     rc = plan_run(pl);
     if (rc) return rc;
+    const double t_run = ms_since(t0);
     rc = plan_fetch(pl, hm);          /* the copy is ordered after the kernels on the same stream */
     if (rc) return rc;
-    return plan_sync(pl);
+    const double t_fetch = ms_since(t0);
+    rc = plan_sync(pl);
+    if (trace) std::fprintf(stderr, "coffe_b200 trace: plan_build %.3f ms, launches queued at %.3f ms, fetch returned at %.3f ms, synchronised at %.3f ms\n",
+                            t_build, t_run, t_fetch, ms_since(t0));
+    return rc;
 }
 
 }  // namespace
