@@ -33,6 +33,16 @@ struct coffe_b200_ctx {
     /* options / quadrature */
     Options o;
     QuadConfig qc;
+    /* the mu rules of the last call, one slot per integrated piece: they depend on the separations and the quadrature
+       configuration only, and building them (two rules per separation, ~100 nodes of asin / cos / sin each) was 8 of the 9 ms of
+       host work of a cfg5 call -- a sweep over cosmologies or redshifts on a fixed separation grid builds them once */
+    struct MuRuleCache {
+        std::vector<double> sep;
+        QuadConfig qc;
+        int n_per_panel = 0; double panel_width = 0; bool half_only = false, active = false, valid = false;
+        std::vector<int> rule_begin;
+        std::vector<double> rule_mu, rule_w;
+    } mu_cache[2];
     double *d_gl_x = nullptr, *d_gl_w = nullptr, *d_rpow = nullptr, *d_rpow_di = nullptr;
     /* shared-memory tables of the integrated-pieces kernel */
     CompactBuild compact;

@@ -175,6 +175,10 @@ __global__ void __launch_bounds__(kItemThreads, COFFE_ITEM_MIN_BLOCKS) integrate
    grid size or GPU count).  Two kernels so that each gets its own register allocation:
    si_items_smem_kernel (local x integrated: two 1-D integrals per item) and di_items_smem_kernel
    (integrated x integrated: the 2-D integral, > 90 % of the device time of a step). */
+/* doubles of the small read-only block staged next to the tables: powers of the tail ratio, then the nodes and
+   weights of the inner panel rule */
+constexpr int kDISmallDoubles = kMaxTail + 2 * 32;
+
 struct SIWarpState {
     EndVals e[2];
     SIHalf h[2];
@@ -183,7 +187,7 @@ struct SIWarpState {
 constexpr int kSIThreads = 384;
 
 __global__ void __launch_bounds__(kSIThreads, 1) si_items_smem_kernel(
-    const __grid_constant__ Tables t, const __grid_constant__ Options o, const __grid_constant__ Rules q,
+    const __grid_constant__ Tables t, const __grid_constant__ Options o, const __grid_constant__ Rules q_in,
     const __grid_constant__ CompactHeader ch, const uint4 *__restrict__ blob, const int stage_bytes,
     const double *__restrict__ pz, const double *__restrict__ psep,
     const int *__restrict__ item_point, const double *__restrict__ item_mu, const int n_items,
@@ -193,14 +197,21 @@ __global__ void __launch_bounds__(kSIThreads, 1) si_items_smem_kernel(
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int n_warps = kSIThreads / 32;
-    /* layout: [compact blob prefix][line-of-sight table][per-warp state][per-warp panel lists] */
+    /* layout: [compact blob prefix][line-of-sight table][tail powers, panel rule][per-warp state][per-warp panel lists] */
     double2 *los_s = reinterpret_cast<double2 *>(smem + stage_bytes);
-    SIWarpState *ws_all = reinterpret_cast<SIWarpState *>(los_s + (size_t)kLosStride * los_stage_n);
+    double *small = reinterpret_cast<double *>(los_s + (size_t)kLosStride * los_stage_n);
+    SIWarpState *ws_all = reinterpret_cast<SIWarpState *>(small + kDISmallDoubles);
     double *scratch = reinterpret_cast<double *>(ws_all + n_warps) + (size_t)warp * 2 * panel_cap;
     {
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
         for (int i = tid; i < stage_bytes / 16; i += kSIThreads) dst[i] = blob[i];
         for (int i = tid; i < kLosStride * los_stage_n; i += kSIThreads) los_s[i] = t.los.v[i];
+        if (tid < kMaxTail) small[tid] = q_in.rpow[tid];
+        const int np = q_in.n_panel_si < 32 ? q_in.n_panel_si : 32;
+        if (tid < np) {
+            small[kMaxTail + tid] = q_in.gl_x[rule_offset(q_in.n_panel_si) + tid];
+            small[kMaxTail + 32 + tid] = q_in.gl_w[rule_offset(q_in.n_panel_si) + tid];
+        }
     }
     __syncthreads();
     SIWarpState &ws = ws_all[warp];
@@ -208,6 +219,10 @@ __global__ void __launch_bounds__(kSIThreads, 1) si_items_smem_kernel(
     ta.t = &t; ta.c.base = smem; ta.c.h = ch;
     LosView lv = t.los;
     lv.v = los_s;
+    /* the tail powers and the panel rule are read by every panel of every item: from shared memory, not through L1 */
+    Rules q = q_in;
+    q.rpow = small;
+    if (q_in.n_panel_si <= 32) { q.panel_x_si = small + kMaxTail; q.panel_w_si = small + kMaxTail + 32; }
 
     for (;;) {
         unsigned int item = 0;
@@ -244,9 +259,6 @@ struct DIWarpState {
 #endif
 constexpr int kDIThreads = COFFE_DI_THREADS;        /* upper bound (register allocation); the launch may use fewer warps */
 
-/* doubles of the small read-only block staged next to the tables: powers of the tail ratio, then the nodes and
-   weights of the inner panel rule */
-constexpr int kDISmallDoubles = kMaxTail + 2 * 32;
 
 /* WARP_PANELS: the panel bookkeeping of the inner integral lives in the lanes of the warp (di_fast.cuh: di_inner_partial_warp);
    the host selects it when the configured plan never has more than 31 panels on a side (the default plan: 29) */
@@ -434,6 +446,7 @@ Rules make_rules(const coffe_b200_ctx *ctx)
     q.panel_w_mpc = ctx->qc.panel_w; q.panel_du = ctx->qc.panel_du; q.eps_min = ctx->qc.eps_min; q.tail_ratio = ctx->qc.tail_ratio;
     q.panel_w_di = ctx->qc.panel_w_di; q.panel_du_di = ctx->qc.panel_du_di;
     q.panel_x = q.panel_w = nullptr;
+    q.panel_x_si = q.panel_w_si = nullptr;
     q.rpow_di = ctx->d_rpow_di; q.tail_ratio_di = ctx->qc.tail_ratio_di; q.geo_shift_di = ctx->qc.geo_shift_di;
     return q;
 }
@@ -498,7 +511,7 @@ int launch_integrated(coffe_b200_ctx *ctx, Batch &b, const int mode, unsigned in
         CompactHeader ch = ctx->compact.h;
         ch.n_knots = (stage_bytes - ch.off_knots) / kKnotBytes;
         const int panel_cap = max_panels(ctx->qc);
-        const size_t fixed = (size_t)stage_bytes + los_bytes + (mode == 1 ? 0 : kDISmallDoubles * sizeof(double));
+        const size_t fixed = (size_t)stage_bytes + los_bytes + kDISmallDoubles * sizeof(double);
         const size_t per_warp = mode == 1 ? sizeof(SIWarpState) + (size_t)2 * panel_cap * sizeof(double) : sizeof(DIWarpState) + row_bytes;
         /* as many warps per SM as the remaining shared memory carries (the kernels are latency-bound: more is faster) */
         int warps = mode == 1 ? kSIThreads / 32 : kDIThreads / 32;
@@ -594,19 +607,36 @@ int run_multipole_batch(coffe_b200_ctx *ctx, Batch &b, const LList &ls, const bo
    rule per distinct separation (`sep`, n_sep entries; point p uses rule point_rule[p]) and uploads those; the
    (point, mu, weight) items are expanded on the device. */
 int build_item_list(coffe_b200_ctx *ctx, const double *sep, const int n_sep, const std::vector<int> &point_rule, const DevBuf<int> &d_point_rule,
-                    const int n_per_panel, const double mu_panel_width, const bool half_only, const bool active, ItemList &L)
+                    const int n_per_panel, const double mu_panel_width, const bool half_only, const bool active, const int slot, ItemList &L)
 {
     const int n = (int)point_rule.size();
-    std::vector<int> rule_begin(n_sep + 1, 0), point_begin(n + 1, 0);
-    std::vector<double> rule_mu, rule_w, mu, w;
-    for (int r = 0; r < n_sep; ++r) {
-        rule_begin[r] = (int)rule_mu.size();
-        if (!active) continue;
-        build_mu_rule(ctx->qc, sep[r], mu, w, n_per_panel, mu_panel_width, half_only);
-        rule_mu.insert(rule_mu.end(), mu.begin(), mu.end());
-        rule_w.insert(rule_w.end(), w.begin(), w.end());
+    std::vector<int> point_begin(n + 1, 0);
+    coffe_b200_ctx::MuRuleCache &mc = ctx->mu_cache[slot];
+    const bool hit = mc.valid && mc.n_per_panel == n_per_panel && mc.panel_width == mu_panel_width && mc.half_only == half_only &&
+                     mc.active == active && (int)mc.sep.size() == n_sep && std::memcmp(&mc.qc, &ctx->qc, sizeof(QuadConfig)) == 0 &&
+                     (n_sep == 0 || std::memcmp(mc.sep.data(), sep, sizeof(double) * n_sep) == 0);
+    if (!hit) {
+        mc.valid = false;
+        mc.rule_begin.assign(n_sep + 1, 0);
+        mc.rule_mu.clear(); mc.rule_w.clear();
+        std::vector<double> mu, w;
+        for (int r = 0; r < n_sep; ++r) {
+            mc.rule_begin[r] = (int)mc.rule_mu.size();
+            if (!active) continue;
+            build_mu_rule(ctx->qc, sep[r], mu, w, n_per_panel, mu_panel_width, half_only);
+            mc.rule_mu.insert(mc.rule_mu.end(), mu.begin(), mu.end());
+            mc.rule_w.insert(mc.rule_w.end(), w.begin(), w.end());
+        }
+        mc.rule_begin[n_sep] = (int)mc.rule_mu.size();
+        mc.sep.assign(sep, sep + n_sep);
+        std::memcpy(&mc.qc, &ctx->qc, sizeof(QuadConfig));
+        mc.n_per_panel = n_per_panel; mc.panel_width = mu_panel_width; mc.half_only = half_only; mc.active = active;
+        mc.valid = true;
     }
-    rule_begin[n_sep] = (int)rule_mu.size();
+    const std::vector<int> &rule_begin = mc.rule_begin;
+    const std::vector<double> &rule_mu = mc.rule_mu, &rule_w = mc.rule_w;
+    static const bool trace = std::getenv("COFFE_B200_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     long total = 0;
     for (int p = 0; p < n; ++p) { point_begin[p] = (int)total; total += rule_begin[point_rule[p] + 1] - rule_begin[point_rule[p]]; }
     if (total > 0x7fffffffL) { ctx->err = "too many (point, mu) work items for one call"; return COFFE_B200_EINVAL; }
@@ -627,6 +657,8 @@ int build_item_list(coffe_b200_ctx *ctx, const double *sep, const int n_sep, con
                                                                    L.point.p, L.mu.p, L.w.p);
         CK(cudaGetLastError());
     }
+    if (trace) std::fprintf(stderr, "coffe_b200 trace: item list of %d items: uploads, allocations and expansion launch %.3f ms\n", L.n,
+                            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     /* the staging buffers above are freed in stream order (cudaFreeAsync) when they go out of scope */
     return COFFE_B200_OK;
 }
@@ -638,11 +670,11 @@ int build_multipole_batch(coffe_b200_ctx *ctx, const double *sep, const int n_se
     DevBuf<int> d_point_rule;
     CK(d_point_rule.upload(point_rule, ctx->stream));
     b.si_half = ctx->pops_identical && (ctx->mag_constant || !(ctx->o.d1 && ctx->o.len));
-    int rc = build_item_list(ctx, sep, n_sep, point_rule, d_point_rule, ctx->qc.n_mu_panel, ctx->qc.mu_panel_w, b.si_half, opt_has_si(ctx->o), b.si);
+    int rc = build_item_list(ctx, sep, n_sep, point_rule, d_point_rule, ctx->qc.n_mu_panel, ctx->qc.mu_panel_w, b.si_half, opt_has_si(ctx->o), 0, b.si);
     if (rc) return rc;
     b.di_half = ctx->di_mu_symmetric;
     return build_item_list(ctx, sep, n_sep, point_rule, d_point_rule, ctx->qc.n_mu_panel_di, ctx->qc.mu_panel_w_di, b.di_half,
-                           opt_has_integrated(ctx->o), b.di);
+                           opt_has_integrated(ctx->o), 1, b.di);
 }
 
 int check_finite(coffe_b200_ctx *ctx, const double *v, const size_t n)
@@ -704,6 +736,9 @@ int plan_build(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double 
     const bool ren = needs_renorm(ctx->o);
     if (ren && !ctx->layout.has_divergent) { ctx->err = "d2/g1..g5 need the divergent I^4_0 tables (par->divergent)"; return COFFE_B200_EINVAL; }
     pz.reserve(pl.n); psep.reserve(pl.n); point_rule.reserve(pl.n);
+    static const bool trace = std::getenv("COFFE_B200_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto ms_since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
     for (long it = begin; it < end; ++it) {
         const double z = z_mean[it / n_sep], s = sep[it % n_sep];
         rc = check_point(ctx, z, s, ren && opt_has_ni(ctx->o));
@@ -712,12 +747,17 @@ int plan_build(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double 
         const double chi2 = bg_chi(ctx->t_host.bg, z) + s / 2.;
         if (chi2 > pl.b.chi_max) pl.b.chi_max = chi2;
     }
+    const double t_check = ms_since();
     CK(pl.b.pz.upload(pz, ctx->stream));
     CK(pl.b.psep.upload(psep, ctx->stream));
+    const double t_up = ms_since();
     rc = build_multipole_batch(ctx, sep, n_sep, point_rule, pl.b);
     if (rc) return rc;
+    const double t_batch = ms_since();
     CK(pl.b.ni.alloc((size_t)pl.b.n_points * n_l));
     CK(pl.b.pm.alloc((size_t)pl.b.n_points * 3 * n_l));
+    if (trace) std::fprintf(stderr, "coffe_b200 trace: plan_build: range checks %.3f ms, point upload %.3f ms, item lists %.3f ms, output buffers %.3f ms\n",
+                            t_check, t_up - t_check, t_batch - t_up, ms_since() - t_batch);
     return COFFE_B200_OK;
 }
 

@@ -19,6 +19,7 @@ struct Rules {
     double panel_w_mpc, panel_du, eps_min, tail_ratio;
     double panel_w_di, panel_du_di;  /* panel plan of the inner integral of the integrated x integrated piece */
     const double *panel_x, *panel_w; /* nodes / weights of the n_panel_di rule when staged separately (else null: read from the bank) */
+    const double *panel_x_si, *panel_w_si;   /* the same for the n_panel_si rule */
     const double *rpow_di;           /* tail_ratio_di^n, n < kMaxTail */
     double tail_ratio_di;
     int geo_shift_di;
@@ -36,7 +37,8 @@ template <class F>
 COFFE_HD double ridge_integrate(const F &f, const double hi, const double center, const double eps,
                                 const Rules &q, const int n_panel, const int lane, const int nlanes, double *scratch)
 {
-    const double *panel_x = q.gl_x + rule_offset(n_panel), *panel_w = q.gl_w + rule_offset(n_panel);
+    const bool staged = q.panel_x_si && n_panel == q.n_panel_si;
+    const double *panel_x = staged ? q.panel_x_si : q.gl_x + rule_offset(n_panel), *panel_w = staged ? q.panel_w_si : q.gl_w + rule_offset(n_panel);
     const PanelPlan plan = panel_plan(eps, q.eps_min, q.panel_w_mpc, q.panel_du, q.tail_ratio, q.rpow);
     /* negative side: |d| in [a_neg, b_neg]; positive side: |d| in [0, b_pos] (center >= 0 always) */
     const double b_neg = center;

@@ -45,6 +45,7 @@ static void set_rules(HostSim *s)
     q.panel_w_mpc = s->qc.panel_w; q.panel_du = s->qc.panel_du; q.eps_min = s->qc.eps_min; q.tail_ratio = s->qc.tail_ratio;
     q.panel_w_di = s->qc.panel_w_di; q.panel_du_di = s->qc.panel_du_di;
     q.panel_x = q.panel_w = nullptr;
+    q.panel_x_si = q.panel_w_si = nullptr;
     s->rpow_di = build_rpow(s->qc.tail_ratio_di);
     q.rpow_di = s->rpow_di.data(); q.tail_ratio_di = s->qc.tail_ratio_di; q.geo_shift_di = s->qc.geo_shift_di;
 }

@@ -180,6 +180,28 @@ def test_two_populations_with_different_biases_match_converged_oracle():
     assert abs(want[2, 1]) > 1e-3 * abs(want[2, 0])          # the dipole of the integrated x integrated piece is really there
 
 
+def test_mu_rule_cache_follows_separations_and_quadrature(engine):
+    """the mu rules of the last call are kept per context (ctx.h: MuRuleCache): a repeated grid must reuse them bit for bit, a
+    different grid, a different option set (the mirror-symmetry decision) or a different quadrature must rebuild them"""
+    engine.set_options(ALL)
+    z, l = [0.8, 1.3], [0, 2, 4]
+    sa, sb = np.array([30.0, 90.0, 150.0]) / H, np.array([30.0, 95.0, 150.0]) / H
+    a1 = engine.multipoles(z, sa, l)
+    a2 = engine.multipoles(z, sa, l)                       # hit
+    b = engine.multipoles(z, sb, l)                        # same length, one separation moved: miss
+    a3 = engine.multipoles(z, sa, l)
+    assert np.array_equal(a1, a2) and np.array_equal(a1, a3)
+    assert np.array_equal(b[:, :, 0], a1[:, :, 0]) and np.array_equal(b[:, :, 2], a1[:, :, 2]) and not np.array_equal(b[:, :, 1], a1[:, :, 1])
+    q0 = engine.get_quadrature()
+    try:
+        engine.set_quadrature(n_mu_panel_di=q0["n_mu_panel_di"] + 2)
+        c = engine.multipoles(z, sa, l)
+        assert not np.array_equal(c, a1) and np.all(np.abs(c / a1 - 1) < 1e-5)
+    finally:
+        engine.set_quadrature(**q0)
+    assert np.array_equal(engine.multipoles(z, sa, l), a1)
+
+
 def test_corrfunc_matches_converged_oracle(engine, ref):
     from oracle.converged import ConvergedOracle
     ref.set_contributions(list(ALL))
