@@ -205,6 +205,10 @@ int coffe_b200_integrals_sizes(const coffe_b200_integrals_params *p, int *n_r, i
 int coffe_b200_integrals(coffe_b200_ctx *ctx, const coffe_b200_integrals_params *p, double *r, double *tables,
                          double *r40, double *i40, double *renorm0, double *renorm_chi, double *renorm_z);
 
+/* Tracing: with COFFE_B200_TRACE set in the environment the multipole entry points print the host phases of a call on
+   stderr (range checks, uploads, mu-rule construction, launches queued, result fetched).  The mu rules of the last call are
+   kept in the context and reused when the separations and the quadrature configuration are unchanged. */
+
 /* device time of the kernels of the last compute call [ms] and their launch count (bench / roofline) */
 int coffe_b200_last_timing(const coffe_b200_ctx *ctx, double *kernel_ms, int *n_launches);
 

@@ -78,6 +78,23 @@ void *hs_create(const coffe_b200_tables *T, const coffe_b200_options *opt)
 
 void hs_destroy(void *h) { delete (HostSim *)h; }
 
+/* panel plan of quadrature.cuh without a context: out = {J, M, B_J, B_(J+M), panel_count(b), panel_count_by_break(b),
+   J and B_J by repeated doubling (the definition the closed form must reproduce)} */
+void hs_panel_plan(double eps, double eps_min, double W, double Du, double ratio, int shift, double b, double *out)
+{
+    const std::vector<double> rp = build_rpow(ratio);
+    const PanelPlan p = panel_plan(eps, eps_min, W, Du, ratio, rp.data(), shift);
+    out[0] = p.J; out[1] = p.M; out[2] = p.BJ; out[3] = p.BJM;
+    out[4] = panel_count(p, b); out[5] = panel_count_by_break(p, b);
+    double e = eps < eps_min ? eps_min : eps;
+    int J = 0; double bj = 0.0;
+    if (e < W) { J = 1; bj = e; while (bj < W) { bj = ldexp(bj, shift); ++J; } }
+    out[6] = J; out[7] = bj;
+}
+
+/* a slope as the packed knots store it (compact.cuh) */
+double hs_slope_rounded(double v) { return slope_rounded(v); }
+
 /* builds the compact tables (knot budget, tolerance) and selects them; returns the number of knots (< 0: failed).
    info[0] = achieved max relative error, info[1] = blob bytes, info[2] = the error of I^4_0, info[3..] = subdivisions m per region (up to n_info-2) */
 int hs_use_compact(void *h, int knot_budget, double tol, double *info, int n_info)

@@ -176,3 +176,43 @@ def test_shared_memory_tables_resampling_budget(ref, tableset):
     for it, a in zip(items, want):
         b = hs.item(*it)
         assert np.all(np.abs(a - b) < 1e-7 * abs(a.sum())), (it, (a - b) / a.sum())
+
+
+def test_panel_plan_closed_form_and_break_counts():
+    """quadrature.cuh: the number of geometric panels from the exponents of eps and W equals repeated doubling (same J, same B_J,
+    bit for bit), and the count taken from the breaks themselves (what the warp of the integrated x integrated kernel does with one
+    ballot, di_fast.cuh) equals panel_count except within rounding of a uniform break, where it may differ by one ulp-wide panel"""
+    import ctypes as C
+    lib = C.CDLL(str(hostsim_bridge.LIB))
+    lib.hs_panel_plan.argtypes = [C.c_double] * 5 + [C.c_int, C.c_double, C.POINTER(C.c_double)]
+    out = np.zeros(8)
+    rng = np.random.default_rng(11)
+    n_diff = 0
+    for _ in range(4000):
+        eps = 10.0 ** rng.uniform(-4, 3)
+        W = rng.choice([16.0, 64.0, 48.0, 100.0])
+        Du = rng.choice([0.0, 128.0, 320.0])
+        ratio = rng.choice([1.5, 2.0, 2.5])
+        shift = int(rng.choice([1, 2, 3]))
+        b = 10.0 ** rng.uniform(-5, 4)
+        if rng.uniform() < 0.2:
+            eps = float(2.0 ** rng.integers(-8, 8))         # exact powers of two: the boundary cases of the exponent arithmetic
+        lib.hs_panel_plan(eps, 1e-3, W, Du, ratio, shift, b, out.ctypes.data_as(C.POINTER(C.c_double)))
+        assert out[0] == out[6] and out[2] == out[7], (eps, W, shift, out)
+        assert abs(out[4] - out[5]) <= 1, (eps, W, Du, ratio, shift, b, out)
+        n_diff += out[4] != out[5]
+    assert n_diff <= 4
+
+
+def test_packed_knot_slopes_round_to_nearest():
+    """compact.cuh: a scaled slope is stored as the upper 32 bits of its double, rounded to nearest: relative error <= 2^-21"""
+    import ctypes as C
+    lib = C.CDLL(str(hostsim_bridge.LIB))
+    lib.hs_slope_rounded.restype = C.c_double
+    lib.hs_slope_rounded.argtypes = [C.c_double]
+    rng = np.random.default_rng(3)
+    v = np.concatenate([rng.normal(size=2000) * 10.0 ** rng.uniform(-30, 30, 2000), [0.0, 1.0, -1.0, 1.0 + 2.0 ** -21, 1.0 + 2.0 ** -20]])
+    got = np.array([lib.hs_slope_rounded(float(x)) for x in v])
+    nz = v != 0
+    assert np.all(np.abs(got[nz] / v[nz] - 1) <= 2.0 ** -21) and got[~nz].tolist() == [0.0]
+    assert lib.hs_slope_rounded(1.0) == 1.0 and lib.hs_slope_rounded(1.0 + 2.0 ** -20) == 1.0 + 2.0 ** -20
