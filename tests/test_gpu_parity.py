@@ -349,6 +349,49 @@ def test_cfg5_full_grid_properties():
     assert np.max(second) < 2e-3 * np.max(np.abs(mono)), np.max(second) / np.max(np.abs(mono))
 
 
+def test_cfg1_full_matches_stock_reference(ref):
+    """BASELINE.json configs[0] at full size: flat-sky density + RSD multipoles l = 0, 2, 4 at z_mean = 1.0 on the 110 entries of
+    separations.dat with 10 <= r <= 200 Mpc/h, against the reference itself run in full on the host (local terms
+    only: its QAG converges, so the stock output is the truth here).  Tolerance 1e-5 per multipole (north_star)."""
+    import coffe_b200
+    from pathlib import Path
+    from oracle_tables import tableset_from_oracle
+    r = np.loadtxt(Path(coffe_b200.__file__).resolve().parent / "data" / "separations.dat")
+    sep = r[(r >= 10.0) & (r <= 200.0)] / H
+    assert sep.size == 110
+    try:
+        ref.set_sep(sep); ref.set_z_mean([1.0]); ref.set_deltaz([0.2]); ref.set_l([0, 2, 4])
+        ref.set_contributions(["den", "rsd"]); ref.set_flags(dict(flatsky_local=1))
+        want = ref.multipoles()
+        eng = coffe_b200.Engine(0)
+        eng.upload_tables(tableset_from_oracle(ref))
+        eng.set_options(["den", "rsd"], flatsky_local=True)
+        got = eng.multipoles([1.0], sep, [0, 2, 4])
+    finally:
+        ref.set_flags({}); ref.set_deltaz([0.1])
+    assert got.shape == want.shape == (1, 3, 110)
+    scale = np.max(np.abs(want), axis=2, keepdims=True)
+    assert np.all(np.abs(got - want) < 1e-5 * scale), np.max(np.abs(got - want) / scale)
+
+
+def test_cfg2_full_grid_properties(engine):
+    """BASELINE.json configs[1] at full size (full-sky 2PCF, all effects, z_mean = 1.0, 100 separations x 50 mu): the stock
+    reference needs hours for it, so the full grid is checked through size-independent properties -- every value finite; with one
+    galaxy population the 2PCF is invariant under the exchange of the two galaxies, xi(mu) = xi(-mu), which the kernels are never
+    told (corrfunc evaluates each requested mu on its own, no mirror rule: a mis-indexed table or panel at one (mu, r) would break
+    it); single values reproduce their grid entries bit for bit.  Values on a sub-grid against the converged oracle are in test_corrfunc_matches_converged_oracle."""
+    engine.set_options(ALL)
+    sep, mu = np.linspace(10.0, 300.0, 100) / H, np.linspace(-0.98, 0.98, 50)
+    out = engine.corrfunc([1.0], mu, sep)
+    assert out.shape == (1, 50, 100) and np.all(np.isfinite(out))
+    scale = np.max(np.abs(out), axis=1, keepdims=True)
+    # mu and -mu swap the roles of the two lines of sight (outer / inner variable, panel placement): the difference is an independent
+    # measure of the quadrature error of the integrated pieces.  Measured 2.5e-7 of the largest value at that separation.
+    assert np.all(np.abs(out - out[:, ::-1, :]) < 2e-6 * scale), np.max(np.abs(out - out[:, ::-1, :]) / scale)
+    for im, ir in ((0, 0), (24, 50), (49, 99)):
+        assert engine.corrfunc([1.0], [mu[im]], [sep[ir]])[0, 0, 0] == out[0, im, ir]
+
+
 def test_cfg4_full_size_covariance_properties():
     """BASELINE.json configs[3] at full size: 4 z-bins x (3 x 100)^2 entries with shot noise -- every 300 x 300 block is
     symmetric and positive definite, cosmic + mixed + Poisson add up, and only the first bin's pixel size enters the windowed
