@@ -54,6 +54,10 @@ struct coffe_b200_ctx {
     /* timing of the last call */
     double last_ms = 0;
     int last_launches = 0;
+    /* bumped by every call that changes what a prepared plan was built from (tables, options, quadrature, kernel variant):
+       a plan refuses to run against a different generation (coffe_b200_plan_execute -> EINVAL) */
+    unsigned long generation = 0;
+    std::vector<struct coffe_b200_plan *> live_plans;   /* released (device buffers freed, ctx cleared) by coffe_b200_destroy */
     std::mutex mu;
 };
 

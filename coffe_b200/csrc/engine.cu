@@ -473,6 +473,15 @@ int check_point(coffe_b200_ctx *ctx, const double z, const double sep, const boo
 
 bool needs_renorm(const Options &o) { return o.d2 || o.g1 || o.g2 || o.g3 || o.g4 || o.g5; }
 
+/* does any term read renormalisation(chi_a, chi_b) up to chi_mean + sep/2?  The local potential terms (d2, g1..g3) at the end
+   points and against g4/g5 along the line of sight, and the g4-g4 / g5-g5 / g4-g5 terms of the integrated x integrated piece
+   (DIConst.any_ren) -- the latter also when no local effect is on.  The kernels clamp the cell index and would extrapolate the
+   patch beyond the grid; the reference aborts there, so such a point is refused (ERANGE). */
+bool renorm_range_needed(const Options &o)
+{
+    return o.d2 || o.g1 || o.g2 || o.g3 || ((o.g4 || o.g5) && (!o.only_cross || (o.g4 && o.g5)));
+}
+
 /* the (point, mu) work items of one integrated piece, on the device */
 struct ItemList {
     int n = 0;
@@ -489,6 +498,12 @@ struct Batch {
     double chi_max = 0;     /* largest chi2 over the batch: how much of the line-of-sight table to stage */
     bool di_half = false;   /* the integrated x integrated items cover mu > 0 only (mirror symmetry): odd multipoles of the piece are zero */
     bool si_half = false;   /* the same for the local x integrated items */
+    void release()
+    {
+        pz.release(); psep.release(); ni.release(); pm.release(); evals.release();
+        for (ItemList *L : {&si, &di}) { L->point.release(); L->begin.release(); L->mu.release(); L->w.release(); L->val.release(); L->n = 0; }
+        n_points = 0;
+    }
 };
 
 /* mode 1: local x integrated over b.si; mode 2: integrated x integrated over b.di */
@@ -696,10 +711,11 @@ int check_l(coffe_b200_ctx *ctx, const int *l, const int n_l)
 
 /* a prepared multipole computation: the (z, r) items [begin, end) with their mu rules resident in HBM */
 struct coffe_b200_plan {
-    coffe_b200_ctx *ctx = nullptr;
+    coffe_b200_ctx *ctx = nullptr;  /* cleared when the context is destroyed first: the plan is then inert */
     Batch b;
     LList ls;
     long n = 0;
+    unsigned long generation = 0;   /* ctx->generation the item lists, stage sizes and mirror-symmetry decisions were built under */
 };
 
 namespace {
@@ -728,7 +744,7 @@ int plan_build(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double 
                     return COFFE_B200_ENOTABLES;
                 }
     }
-    pl.ctx = ctx; pl.n = end - begin; pl.ls = make_llist(l, n_l);
+    pl.ctx = ctx; pl.n = end - begin; pl.ls = make_llist(l, n_l); pl.generation = ctx->generation;
     if (end == begin) return COFFE_B200_OK;
     CK(cudaSetDevice(ctx->device));
     std::vector<double> pz, psep;
@@ -741,7 +757,7 @@ int plan_build(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double 
     auto ms_since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
     for (long it = begin; it < end; ++it) {
         const double z = z_mean[it / n_sep], s = sep[it % n_sep];
-        rc = check_point(ctx, z, s, ren && opt_has_ni(ctx->o));
+        rc = check_point(ctx, z, s, ren && renorm_range_needed(ctx->o));
         if (rc) return rc;
         pz.push_back(z); psep.push_back(s); point_rule.push_back((int)(it % n_sep));
         const double chi2 = bg_chi(ctx->t_host.bg, z) + s / 2.;
@@ -889,6 +905,14 @@ void coffe_b200_destroy(coffe_b200_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    {
+        /* plans that outlive their context become inert: their device buffers go back to the pool while the stream still exists */
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        AllocScope scope(ctx->stream);
+        for (coffe_b200_plan *pl : ctx->live_plans) { pl->b.release(); pl->ctx = nullptr; }
+        ctx->live_plans.clear();
+        cudaStreamSynchronize(ctx->stream);
+    }
     if (ctx->d_arena) cudaFree(ctx->d_arena);
     if (ctx->d_gl_x) cudaFree(ctx->d_gl_x);
     if (ctx->d_gl_w) cudaFree(ctx->d_gl_w);
@@ -946,6 +970,7 @@ int coffe_b200_upload_tables(coffe_b200_ctx *ctx, const coffe_b200_tables *T)
     ctx->pops_identical = tables_populations_identical(*T);
     ctx->mag_constant = tables_magnification_constant(*T);
     ctx->have_tables = true;
+    ctx->generation++;
     return COFFE_B200_OK;
 }
 
@@ -960,6 +985,7 @@ int coffe_b200_set_options(coffe_b200_ctx *ctx, const coffe_b200_options *opt)
     o.flatsky_local = opt->flatsky_local != 0;
     o.flatsky_local_nonlocal = opt->flatsky_local_nonlocal != 0;
     o.flatsky_nonlocal = opt->flatsky_nonlocal != 0;
+    ctx->generation++;
     return COFFE_B200_OK;
 }
 
@@ -983,6 +1009,7 @@ int coffe_b200_set_quadrature(coffe_b200_ctx *ctx, const coffe_b200_quadrature *
         CK(cudaMemcpy(ctx->d_rpow_di, rp.data(), kMaxTail * sizeof(double), cudaMemcpyHostToDevice));
     }
     ctx->qc = merged;
+    ctx->generation++;
     return COFFE_B200_OK;
 }
 
@@ -991,6 +1018,7 @@ int coffe_b200_set_kernel_variant(coffe_b200_ctx *ctx, int variant)
     if (!ctx || (variant != 0 && variant != 1)) return COFFE_B200_EINVAL;
     COFFE_ENTER(ctx);
     ctx->variant = variant;
+    ctx->generation++;
     return COFFE_B200_OK;
 }
 
@@ -1084,7 +1112,7 @@ int coffe_b200_corrfunc(coffe_b200_ctx *ctx, const double *z_mean, int n_z, cons
     std::vector<int> item_point;
     for (int iz = 0; iz < n_z; ++iz)
         for (int ir = 0; ir < n_sep; ++ir) {
-            const int rc = check_point(ctx, z_mean[iz], sep[ir], ren && opt_has_ni(ctx->o));
+            const int rc = check_point(ctx, z_mean[iz], sep[ir], ren && renorm_range_needed(ctx->o));
             if (rc) return rc;
             pz.push_back(z_mean[iz]); psep.push_back(sep[ir]);
             const double chi2 = bg_chi(ctx->t_host.bg, z_mean[iz]) + sep[ir] / 2.;
@@ -1156,7 +1184,7 @@ int coffe_b200_average_multipoles(coffe_b200_ctx *ctx, const double *z_min, cons
                 ctx->err = "separation does not fit inside the redshift bin (need chi(z_min) + r/2 < chi(z_max) - r/2)";
                 return COFFE_B200_ERANGE;
             }
-            if (ren && opt_has_ni(ctx->o) && !(c2 <= th.ren2d.x[th.ren2d.n - 1])) { ctx->err = "redshift bin outside the renormalisation grid"; return COFFE_B200_ERANGE; }
+            if (ren && renorm_range_needed(ctx->o) && !(c2 <= th.ren2d.x[th.ren2d.n - 1])) { ctx->err = "redshift bin outside the renormalisation grid"; return COFFE_B200_ERANGE; }
             for (int k = 0; k < nz; ++k) point_rule[((size_t)ib * n_sep + ir) * nz + k] = ir;
         }
         if (c2 > b.chi_max) b.chi_max = c2;
@@ -1237,14 +1265,19 @@ int coffe_b200_plan_multipoles(coffe_b200_ctx *ctx, const double *z_mean, int n_
     const int rc = plan_build(ctx, z_mean, n_z, sep, n_sep, l, n_l, item_begin, item_end, *pl);
     if (rc) { delete pl; return rc; }
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { delete pl; ctx->err = "upload failed"; return COFFE_B200_ECUDA; }
+    ctx->live_plans.push_back(pl);
     *out = pl;
     return COFFE_B200_OK;
 }
 
 int coffe_b200_plan_execute(coffe_b200_plan *plan, double *kernel_ms)
 {
-    if (!plan) return COFFE_B200_EINVAL;
+    if (!plan || !plan->ctx) return COFFE_B200_EINVAL;
     COFFE_ENTER(plan->ctx);
+    if (plan->generation != plan->ctx->generation) {
+        plan->ctx->err = "the plan was prepared under different tables, options or quadrature settings: prepare it again";
+        return COFFE_B200_EINVAL;
+    }
     int rc = plan_run(*plan);
     if (rc) return rc;
     rc = plan_sync(*plan);
@@ -1254,7 +1287,7 @@ int coffe_b200_plan_execute(coffe_b200_plan *plan, double *kernel_ms)
 
 int coffe_b200_plan_fetch(coffe_b200_plan *plan, double *out)
 {
-    if (!plan || !out) return COFFE_B200_EINVAL;
+    if (!plan || !out || !plan->ctx) return COFFE_B200_EINVAL;
     COFFE_ENTER(plan->ctx);
     std::vector<double> hm;
     const int rc = plan_fetch(*plan, hm);
@@ -1269,9 +1302,13 @@ int coffe_b200_plan_fetch(coffe_b200_plan *plan, double *out)
 
 int coffe_b200_plan_count(coffe_b200_plan *plan, double *n_items, double *n_ni_evals, double *n_si_evals, double *n_di_evals)
 {
-    if (!plan) return COFFE_B200_EINVAL;
+    if (!plan || !plan->ctx) return COFFE_B200_EINVAL;
     coffe_b200_ctx *ctx = plan->ctx;
     COFFE_ENTER(ctx);
+    if (plan->generation != ctx->generation) {
+        ctx->err = "the plan was prepared under different tables, options or quadrature settings: prepare it again";
+        return COFFE_B200_EINVAL;
+    }
     Batch &b = plan->b;
     double si = 0, di = 0;
     if (opt_has_integrated(ctx->o)) {
@@ -1303,7 +1340,13 @@ int coffe_b200_plan_count(coffe_b200_plan *plan, double *n_items, double *n_ni_e
 void coffe_b200_plan_destroy(coffe_b200_plan *plan)
 {
     if (!plan) return;
-    cudaSetDevice(plan->ctx->device);
+    if (coffe_b200_ctx *ctx = plan->ctx) {
+        COFFE_ENTER(ctx);
+        cudaSetDevice(ctx->device);
+        for (size_t i = 0; i < ctx->live_plans.size(); ++i)
+            if (ctx->live_plans[i] == plan) { ctx->live_plans.erase(ctx->live_plans.begin() + i); break; }
+        plan->b.release();          /* device buffers back to the pool in stream order, under the context's allocation scope */
+    }
     delete plan;
 }
 

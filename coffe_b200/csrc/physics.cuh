@@ -373,11 +373,12 @@ COFFE_HD DIConst di_setup(const Options &o, const EndVals &e1, const EndVals &e2
     const double Om2 = o.Om * o.Om;
     const double m1 = 2.0 - 5.0 * e1.s, m2 = 2.0 - 5.0 * e2.s;
     const bool autos = !o.only_cross;
-    /* With flatsky_nonlocal the dispatcher skips the 3-D integral only when neither g4 nor g5 is on
-       (src/signal.c:737-752); when it does run, the integrand still holds the full-sky len-len term because its
-       flat-sky branch needs output_type != MULTIPOLES, which the Python API never sets (src/functions.c:3521,
-       SURVEY.md 8a note 7) -- so the reference then adds both, and so do we. */
-    const bool skip_ll = o.flatsky_nonlocal && o.out_multipoles && !o.g4 && !o.g5;
+    /* With flatsky_nonlocal the reference integrand carries no len-len term at all: its flat-sky branch needs
+       output_type != MULTIPOLES, which the Python API never sets, and the full-sky branch is `else if (!flatsky_nonlocal)`
+       (src/functions.c:3521-3562, SURVEY.md 8a note 7).  The 3-D integral then holds only the g4/g5 terms
+       (src/signal.c:737-752), the closed form of src/signal.c:707-735 supplies len-len for the multipoles, and the
+       2PCF / redshift-averaged multipoles lose the term -- reproduced as is. */
+    const bool skip_ll = o.flatsky_nonlocal != 0;
     k.k_ll = (o.len && autos && !skip_ll) ? 9. * Om2 * m1 * m2 / 4. : 0.0;
     k.k_4l = (o.g4 && o.len) ? 9 * Om2 / 2. * m1 * m2 : 0.0;
     k.k_5la = (o.g5 && o.len) ? 9 * Om2 / 2. * m2 * e1.G * e1.chi : 0.0;

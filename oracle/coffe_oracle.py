@@ -44,7 +44,7 @@ def load(fast=False):
     lib = C.CDLL(str(HERE / "_ref" / name))
     lib.ref_new.restype = C.c_void_p
     for f in ("ref_background_eval", "ref_integral_eval", "ref_renorm_eval", "ref_integrate",
-              "ref_f_nonintegrated", "ref_f_single", "ref_f_double"):
+              "ref_f_nonintegrated", "ref_f_single", "ref_f_double", "ref_cuhre_direct"):
         getattr(lib, f).restype = C.c_double
     _LIBS[name] = lib
     return lib
@@ -209,6 +209,15 @@ class RefCoffe:
     def integrate(self, z_mean, sep, mu, l, piece, output, z_min=0.0, z_max=0.0):
         return self.lib.ref_integrate(self.h_, C.c_double(z_mean), C.c_double(z_min), C.c_double(z_max), C.c_double(sep),
                                       C.c_double(mu), C.c_int(l), C.c_int(piece), C.c_int(output))
+
+    def cuhre_direct(self, which, z, sep, mu, l, epsrel=1e-7, maxeval=50_000_000):
+        """the vendored Cuhre called directly on the reference's integrands with caller-chosen accuracy (ref_driver.c:
+        ref_cuhre_direct).  which: 0 = local x integrated multipole l (2-D), 1 = integrated x integrated 2PCF at mu (2-D),
+        2 = integrated x integrated multipole l (3-D).  Returns (value, absolute error estimate, evaluations, fail)."""
+        err, ne, fail = C.c_double(), C.c_int(), C.c_int()
+        v = self.lib.ref_cuhre_direct(self.h_, C.c_int(which), C.c_double(z), C.c_double(sep), C.c_double(mu), C.c_int(l),
+                                      C.c_double(epsrel), C.c_int(int(maxeval)), C.byref(err), C.byref(ne), C.byref(fail))
+        return v, err.value, ne.value, fail.value
 
     # --- raw integrands ------------------------------------------------------------------
     def f_nonintegrated(self, z, mu, sep):

@@ -146,3 +146,34 @@ class ConvergedOracle:
                 out[1, il] = (2 * l + 1) * np.sum(w * P[il](mu) * si)
                 out[2, il] = (2 * l + 1) * np.sum(w * P[il](mu) * di)
         return out
+
+    # ---- redshift average (src/signal.c:243-463) --------------------------------------------------------------------
+    def average_nodes(self, z_min, z_max, sep, n_z=16):
+        """nodes and weights of the reference's redshift average of one (bin, separation): the bin limits are moved inwards by r/2 in
+        comoving distance, z = z1 + (z2 - z1) v with v in [0, 1], weight H0 h / (Hc(z) (1 + z)) and NO Jacobian (z2 - z1)
+        (src/signal.c:262-283: the same four lines open every average_multipoles_*_integrand)."""
+        H0h = 0.67 / 2997.92458 if not hasattr(self, "H0h") else self.H0h       # COFFE_H0 * par->h (src/common.h:75-77)
+        c1 = float(self.ref.background_eval("comoving_distance", z_min)[0]) + sep / 2
+        c2 = float(self.ref.background_eval("comoving_distance", z_max)[0]) - sep / 2
+        z1 = float(self.ref.background_eval("z_as_chi", c1)[0]); z2 = float(self.ref.background_eval("z_as_chi", c2)[0])
+        v, w = gl01(n_z)
+        z = z1 + (z2 - z1) * v
+        return z, w * H0h / (self.ref.background_eval("conformal_Hz", z) * (1 + z))
+
+    def average_multipoles_pieces(self, z_min, z_max, sep, ls, n_z=16, want=(True, True, True)):
+        """[3 pieces, n_l] of the redshift-averaged multipoles of one bin: Gauss-Legendre in v over multipoles_pieces(z(v))"""
+        z, w = self.average_nodes(z_min, z_max, sep, n_z)
+        return sum(wk * self.multipoles_pieces(float(zk), sep, ls, want) for zk, wk in zip(z, w))
+
+    # ---- pieces with the scheme-independent integrators where they exist --------------------------------------------
+    def si_multipoles_cuhre(self, z, sep, ls, epsrel=1e-7, maxeval=50_000_000):
+        """local x integrated multipoles by the vendored Cuhre called directly on the reference's integrand (2-D, converges):
+        returns (values[n_l], estimated relative errors[n_l], fail flags[n_l])"""
+        out = [self.ref.cuhre_direct(0, z, sep, 0.0, int(l), epsrel, maxeval) for l in ls]
+        val = np.array([o[0] for o in out])
+        return val, np.array([o[1] for o in out]) / np.max(np.abs(val)), np.array([o[3] for o in out])
+
+    def di_corrfunc_cuhre(self, z, sep, mu, epsrel=1e-7, maxeval=200_000_000):
+        """integrated x integrated 2PCF at fixed mu by Cuhre directly (2-D): (value, estimated relative error, fail)"""
+        v, e, n, f = self.ref.cuhre_direct(1, z, sep, mu, 0, epsrel, maxeval)
+        return v, e / abs(v) if v else e, f

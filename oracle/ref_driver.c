@@ -496,3 +496,47 @@ void ref_corrfunc_converged(void *h, double z_mean, double sep, double mu,
         out[2] = tot;
     }
 }
+
+/* ---- scheme-independent truth: the vendored Cuhre called DIRECTLY on the reference's integrands ----------------------
+ * The stock path hard-codes epsrel = 5e-4 and maxeval = integration_bins (src/common.c:1098-1118, result used whatever `fail`
+ * says).  Here the same library routine runs on the same integrand functions with caller-chosen epsrel / maxeval, so that where
+ * it converges (2-D: the local x integrated multipole in (mu, x), src/signal.c:141-187, and the integrated x integrated 2PCF in
+ * (x1, x2), src/signal.c:44-80) it is an adaptive, panel-free arbiter for both oracle/converged.py and the kernels.
+ *   which = 0: (2l+1) int du dx  P_l(2u-1) functions_single_integrated(z, 2u-1, sep, x)          [2-D]
+ *   which = 1:        int dx1 dx2 functions_double_integrated(z, mu, sep, x1, x2)                  [2-D]
+ *   which = 2: (2l+1) int du dx1 dx2 P_l(2u-1) functions_double_integrated(z, 2u-1, sep, x1, x2)  [3-D]
+ * Cuhre needs >= 2 dimensions, so the 1-D local x integrated 2PCF is not offered.  Returns the integral; error, neval, fail out. */
+typedef struct { ref_state *s; double z, sep, mu; int l, which; } cuhre_job;
+
+static int cuhre_direct_integrand(const int *ndim, const cubareal v[], const int *ncomp, cubareal f[], void *p)
+{
+    const cuhre_job *j = (const cuhre_job *)p;
+    ref_state *s = j->s;
+    double val;
+    if (j->which == 1) val = functions_double_integrated(&s->par, &s->bg, &s->integral, j->z, j->mu, j->sep, v[0], v[1]);
+    else {
+        const double mu = 2 * v[0] - 1;
+        val = j->which == 0 ? functions_single_integrated(&s->par, &s->bg, &s->integral, j->z, mu, j->sep, v[1])
+                            : functions_double_integrated(&s->par, &s->bg, &s->integral, j->z, mu, j->sep, v[1], v[2]);
+        if (j->l) val *= gsl_sf_legendre_Pl(j->l, mu);
+    }
+    f[0] = val;
+    return 0;
+}
+
+double ref_cuhre_direct(void *h, int which, double z, double sep, double mu, int l, double epsrel, int maxeval,
+                        double *error, int *neval_out, int *fail_out)
+{
+    ref_state *s = h;
+    ref_integrals(h);
+    cuhre_job j = {s, z, sep, mu, l, which};
+    int nregions = 0, neval = 0, fail = 0;
+    double result[1] = {0}, err[1] = {0}, prob[1] = {0};
+    Cuhre(which == 2 ? 3 : 2, 1, cuhre_direct_integrand, &j, 1, epsrel, 0, 0, 1, maxeval, 0, NULL, NULL,
+          &nregions, &neval, &fail, result, err, prob);
+    const double pre = which == 1 ? 1.0 : 2 * l + 1;
+    if (error) *error = pre * err[0];
+    if (neval_out) *neval_out = neval;
+    if (fail_out) *fail_out = fail;
+    return pre * result[0];
+}

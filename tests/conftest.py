@@ -18,6 +18,36 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def _cuda_device_present():
+    """True when libcoffe_b200.so loads and coffe_b200_create(0) finds a device.  Only used to SKIP `gpu`-marked tests on a
+    GPU-less machine (so `pytest tests` stays readable there); on a GPU box nothing is skipped and a missing library fails loudly."""
+    import ctypes as C
+    try:
+        from coffe_b200 import capi
+        lib = capi.load()
+    except Exception:
+        # no library: on a machine with a GPU this must fail, not skip
+        try:
+            C.CDLL("libcuda.so.1").cuInit(0)
+            return True
+        except OSError:
+            return False
+    h = C.c_void_p()
+    rc = lib.coffe_b200_create(C.c_int(0), C.byref(h))
+    if rc == 0:
+        lib.coffe_b200_destroy(h)
+    return rc != 2          # COFFE_B200_ECUDA: no device
+
+
+def pytest_collection_modifyitems(config, items):
+    gpu_items = [it for it in items if it.get_closest_marker("gpu")]
+    if not gpu_items or _cuda_device_present():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device: coffe_b200 has no CPU fallback (gpu-marked tests run on the B200 box)")
+    for it in gpu_items:
+        it.add_marker(skip)
+
+
 def _oracle_available():
     from oracle import coffe_oracle as O
     return O.available()

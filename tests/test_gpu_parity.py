@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import hostsim_bridge
-from conftest import ALL, H
+from conftest import ALL, H, ROOT
 
 pytestmark = pytest.mark.gpu
 
@@ -290,11 +290,14 @@ def test_flatsky_closed_form_multipoles(ref, golden):
         for il, l in enumerate((0, 2, 4)):
             assert np.allclose(got_dl[il], golden[f"flatsky_density_lensing_multipoles{l}"][:, 1], rtol=5e-4)
             assert np.allclose(got_ll[il], golden[f"flatsky_lensing_lensing_multipoles{l}"][:, 1], rtol=5e-4)
-        # odd multipoles of the closed forms are zero; the switches do not touch the 2PCF (SURVEY.md 8a note 7)
+        # odd multipoles of the closed forms are zero
         assert np.all(eng.multipoles([1.0], sep, [1, 3]) == 0)
-        full = coffe_b200.Engine(0)
-        full.upload_tables(tableset_from_oracle(ref)); full.set_options(["len"])
-        assert np.array_equal(eng.corrfunc([1.0], [0.3], sep[:2]), full.corrfunc([1.0], [0.3], sep[:2]))
+        # the 2PCF under flatsky_nonlocal: from the Python API output_type stays MULTIPOLES, so the reference integrand takes neither the
+        # flat-sky nor the full-sky len-len branch (src/functions.c:3521-3562) and the lensing-only 2PCF is exactly zero -- reproduced
+        ref.set_mu([0.3]); ref.set_sep(sep[:2])
+        want_cf = ref.corrfunc()
+        ref.set_sep(sep)
+        assert np.all(want_cf == 0) and np.all(eng.corrfunc([1.0], [0.3], sep[:2]) == 0)
         # without the tables the call reports ENOTABLES instead of returning NaN
         ref.set_flags({})
         bare = coffe_b200.Engine(0)
@@ -306,6 +309,39 @@ def test_flatsky_closed_form_multipoles(ref, golden):
         ref.set_flags({})
         ref.set_contributions(list(ALL))
         _cov_restore(ref)
+
+
+def test_flatsky_nonlocal_with_potential_terms_matches_oracle(ref):
+    """['len', 'g4'] with flatsky_nonlocal: the reference's 3-D integral then carries only the g4 terms (its integrand has no len-len
+    term under the flag, src/functions.c:3521-3562) and the closed form of src/signal.c:707-735 supplies len-len.  Oracle = the
+    reference's closed form (its QAG at 1e-5) + the reference's integrand under the converged rule; the full-sky len-len term must
+    not be counted a second time.  Also the 2PCF and the lensing x g4 cross-only case."""
+    import coffe_b200
+    from oracle.converged import ConvergedOracle
+    from oracle_tables import tableset_from_oracle
+    s = np.array([40.0]) / H
+    try:
+        ref.set_sep(s); ref.set_z_mean([1.0]); ref.set_deltaz([0.1]); ref.set_mu([0.4])
+        ref.set_contributions(["len"]); ref.set_flags(dict(flatsky_nonlocal=1))
+        closed = ref.multipoles()[0, :, 0]
+        ref.set_contributions(["len", "g4"]); ref.set_flags(dict(flatsky_nonlocal=1))
+        co = ConvergedOracle(ref, n_outer=64, n_panel=8, mu_kw=dict(n=6, W=24.0))
+        di = co.multipoles_pieces(1.0, s[0], [0, 2, 4], want=(False, False, True))[2]
+        cf = co.corrfunc_pieces(1.0, s[0], 0.4, want=(False, False, True))[2]
+        eng = coffe_b200.Engine(0)
+        eng.upload_tables(tableset_from_oracle(ref))
+        eng.set_options(["len", "g4"], flatsky_nonlocal=True)
+        got = eng.multipoles([1.0], s, [0, 2, 4])[0, :, 0]
+        got_cf = eng.corrfunc([1.0], [0.4], s)[0, 0, 0]
+        ref.set_flags({}); ref.set_contributions(["len", "g4"])
+        full = ConvergedOracle(ref, n_outer=64, n_panel=8, mu_kw=dict(n=6, W=24.0)).multipoles_pieces(1.0, s[0], [0], want=(False, False, True))[2]
+    finally:
+        ref.set_flags({}); ref.set_contributions(list(ALL)); ref.set_mu([0.0])
+        _cov_restore(ref)
+    want = closed + di
+    assert abs(full[0] - di[0]) > 0.3 * abs(full[0])          # the dropped full-sky len-len term is most of the piece: a double count would show
+    assert np.all(np.abs(got - want) < 2e-5 * np.abs(want)), got / want - 1
+    assert abs(got_cf / cf - 1) < 1e-5, got_cf / cf - 1
 
 
 # ---- size-independent properties on a larger grid ----------------------------------------------------
@@ -574,3 +610,141 @@ def test_covariance_structure(engine):
     assert np.all(np.diag(pois) > 0) and np.count_nonzero(pois - np.diag(np.diag(pois))) == 0
     distinct = engine.covariance(*args, cosmic=False, mixed=True, poisson=True, pops=(1, 2, 3, 4), **kw)
     assert np.all(distinct == 0)
+
+
+# ---- dense parity on the benchmarked grids (task 1) -------------------------------------------
+FINE_RULES = dict(n_mu_panel=12, n_mu_panel_di=10, mu_panel_width=16.0, n_outer=96, n_panel_si=12, n_panel_di=12, panel_width=8.0,
+                  panel_uniform_extent=640.0, panel_width_di=16.0, panel_uniform_extent_di=640.0, mu_panel_width_di=16.0,
+                  tail_ratio=1.3, tail_ratio_di=1.3, geometric_shift_di=1, n_mu_ni=64)
+
+
+def cfg5_grid():
+    return np.linspace(0.5, 2.0, 32), np.linspace(10.0, 300.0, 1000) / H, [0, 2, 4]
+
+
+def test_cfg5_dense_self_convergence_default_vs_doubled_rules():
+    """Every point of a dense subsample of the benchmarked cfg5 grid -- all 32 z_mean x (every 8th separation + the separations
+    within +-2 grid knots of every rule switch: the mu-panel plan changes at r_perp = 16, 32, 64, 96 ... 256, 384 Mpc and the outer
+    rule max(30, 10 + r/12) has its kink at 240 Mpc and then steps every 12 Mpc) -- with the default fixed-node rules against the
+    same kernels with every node count doubled and every panel narrowed (FINE_RULES): each multipole within 1e-5 of the l = 0..4
+    scale of the point.  ~5 900 (z, r) points; a node count that fails here is raised, not the tolerance."""
+    import coffe_b200
+    from coffe_b200.default_tables import load_default_tableset
+    eng = coffe_b200.Engine(0)
+    eng.upload_tables(load_default_tableset())
+    eng.set_options(ALL)
+    z, sep, ls = cfg5_grid()
+    pick = set(range(0, 1000, 8)) | {999}
+    switches = [16.0, 32.0, 64.0, 96.0, 128.0, 160.0, 192.0, 224.0, 240.0, 256.0, 384.0] + [240.0 + 12.0 * k for k in range(1, 18)]
+    for s in switches:
+        j = int(np.searchsorted(sep, s))
+        pick |= {k for k in range(j - 2, j + 2) if 0 <= k < 1000}
+    idx = np.array(sorted(pick))
+    assert len(idx) * len(z) >= 4000
+    base = eng.multipoles(z, sep[idx], ls)
+    eng.set_quadrature(**FINE_RULES)
+    fine = np.concatenate([eng.multipoles(z[i:i + 4], sep[idx], ls) for i in range(0, len(z), 4)])
+    eng.set_quadrature()
+    scale = np.max(np.abs(fine), axis=1, keepdims=True)
+    err = np.abs(base - fine) / scale
+    worst = np.unravel_index(np.argmax(err), err.shape)
+    assert err.max() < 1e-5, (err.max(), z[worst[0]], ls[worst[1]], sep[idx][worst[2]] * H)
+    # relative to each multipole itself wherever it is not crossing zero
+    big = np.abs(fine) > 0.05 * scale
+    assert np.max((np.abs(base - fine) / np.abs(fine))[big]) < 5e-5
+
+
+def test_cfg5_matches_converged_oracle_fixture():
+    """tests/golden/converged_cfg5.npz (tests/golden/make_converged_cfg5.py): the REFERENCE's integrands under the converged rule at
+    128 stratified (z, r) points of the benchmarked grid, pieces kept apart.  Kernels through the C ABI on the package's default
+    tables: every multipole within 1e-5 of the l = 0..4 scale of the point, and each integrated piece within 1e-5 of its own scale."""
+    import coffe_b200
+    from coffe_b200.default_tables import load_default_tableset
+    fx = np.load(ROOT / "tests" / "golden" / "converged_cfg5.npz")
+    eng = coffe_b200.Engine(0)
+    eng.upload_tables(load_default_tableset())
+    eng.set_options(ALL)
+    z, sep, ls = cfg5_grid()
+    iz, ir, want = fx["iz"], fx["ir"], fx["pieces"]            # want[k, piece, l]
+    assert len(iz) >= 128 and np.array_equal(fx["l"], ls)
+    assert np.allclose(fx["z"], z[iz], rtol=0, atol=1e-14) and np.allclose(fx["sep"], sep[ir], rtol=1e-15)
+    got = np.empty_like(want)
+    for k in range(len(iz)):
+        got[k] = eng.multipoles_pieces([z[iz[k]]], [sep[ir[k]]], ls)[:, 0, :, 0]
+    tot_w, tot_g = want.sum(1), got.sum(1)
+    scale = np.max(np.abs(tot_w), axis=1, keepdims=True)
+    err = np.abs(tot_g - tot_w) / scale
+    k = np.unravel_index(np.argmax(err), err.shape)
+    assert err.max() < 1e-5, (err.max(), z[iz[k[0]]], sep[ir[k[0]]] * H, ls[k[1]])
+    for piece in (1, 2):
+        ps = np.max(np.abs(want[:, piece]), axis=1, keepdims=True)
+        perr = np.abs(got[:, piece] - want[:, piece]) / ps
+        assert perr.max() < 1e-5, (piece, perr.max())
+    # the oracle's own convergence (two rule sizes) is recorded with the fixture and must sit well below the gate
+    assert float(fx["oracle_self_error"].max()) < 3e-6
+
+
+def test_cfg2_matches_converged_oracle_fixture(engine):
+    """the same for the full-sky 2PCF of cfg2 (z = 1, all effects): 32 (mu, r) points of its 50 x 100 grid"""
+    fx = np.load(ROOT / "tests" / "golden" / "converged_cfg2.npz")
+    engine.set_options(ALL)
+    sep, mu = np.linspace(10.0, 300.0, 100) / H, np.linspace(-0.98, 0.98, 50)
+    im, ir, want = fx["imu"], fx["ir"], fx["pieces"]            # want[k, piece]
+    assert len(im) >= 32
+    got = np.array([engine.corrfunc([1.0], [mu[a]], [sep[b]])[0, 0, 0] for a, b in zip(im, ir)])
+    err = np.abs(got / want.sum(1) - 1)
+    assert err.max() < 1e-5, (err.max(), mu[im[np.argmax(err)]], sep[ir[np.argmax(err)]] * H)
+    assert float(fx["oracle_self_error"].max()) < 3e-6
+
+
+def test_plan_refuses_stale_state_and_survives_its_context(engine):
+    """a prepared plan snapshots the generation of tables / options / quadrature it was built under and refuses to run
+    against another one; destroying the context first leaves the plan inert instead of dangling"""
+    import coffe_b200
+    from coffe_b200.default_tables import load_default_tableset
+    eng = coffe_b200.Engine(0)
+    eng.upload_tables(load_default_tableset())
+    eng.set_options(ALL)
+    plan = eng.plan_multipoles([1.0], [50.0, 80.0], [0, 2])
+    plan.execute()
+    a = plan.fetch()
+    eng.set_options(["len"])
+    with pytest.raises(coffe_b200.CoffeB200Error) as e:
+        plan.execute()
+    assert e.value.code == 1
+    eng.set_options(ALL)        # same options, but a new generation: still refused (the snapshot is conservative)
+    with pytest.raises(coffe_b200.CoffeB200Error):
+        plan.execute()
+    plan2 = eng.plan_multipoles([1.0], [50.0, 80.0], [0, 2])
+    plan2.execute()
+    assert np.array_equal(plan2.fetch(), a)
+    eng.close()                 # context first ...
+    with pytest.raises(coffe_b200.CoffeB200Error):
+        plan2.execute()
+    plan2.close(); plan.close()  # ... then the plans: no use-after-free
+
+
+def test_renormalisation_range_is_checked_for_potential_terms_alone(ref):
+    """g4 / g5 without any local effect still read renormalisation(l1, l2) up to chi_mean + sep/2; beyond the grid the call
+    must report ERANGE (the reference aborts there) instead of extrapolating the patch"""
+    import coffe_b200
+    from oracle_tables import tableset_from_oracle
+    try:
+        ref.set_z_mean([1.0]); ref.set_deltaz([0.1])          # grid to chi(1.1)
+        ref.set_contributions(["g4", "g5"])
+        eng = coffe_b200.Engine(0)
+        eng.upload_tables(tableset_from_oracle(ref))
+    finally:
+        ref.set_contributions(list(ALL))
+        _cov_restore(ref)
+    for opts in (["g4"], ["g5"], ["len", "g4", "g5"]):
+        eng.set_options(opts)
+        assert np.all(np.isfinite(eng.multipoles([1.0], [50.0], [0])))
+        with pytest.raises(coffe_b200.CoffeB200Error) as e:
+            eng.multipoles([1.4], [50.0], [0])
+        assert e.value.code == 5
+        with pytest.raises(coffe_b200.CoffeB200Error) as e:
+            eng.corrfunc([1.4], [0.2], [50.0])
+        assert e.value.code == 5
+    eng.set_options(["len", "g4"], only_cross=True)          # cross only: no renormalised term left
+    assert np.all(np.isfinite(eng.multipoles([1.4], [50.0], [0])))
