@@ -112,12 +112,22 @@ def reference_arm(args, z, sep, ls, rank):
             times.append(time.perf_counter() - t)
     tot = sum(times)
     v = n_pts * len(times) / tot
+    # per-stratum cost, so that the extrapolation from the sample to the full grid can be judged: single-core seconds of
+    # coffe_integrate (all three pieces, l = 0) at the corners and the middle of the grid
+    strata = []
+    for zq in (z[0], z[-1]):
+        for rq in (sep[0], sep[len(sep) // 2], sep[-1]):
+            t = time.perf_counter()
+            for piece in (0, 1, 2):
+                ref.integrate(float(zq), float(rq), 0.0, 0, piece, 2)
+            strata.append({"z": float(zq), "r_mpc_h": float(rq * H), "core_seconds_per_point": time.perf_counter() - t})
     sample = f"{len(zs)} z x {len(ss)} r x {len(ls)} l = {n_pts} points per step, stratified over the cfg5 grid, tables prebuilt"
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "points/s", "n_gpus": args.gpus, "steps": len(times),
             "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"cfg5 bulk sweep {len(z)} z_mean x {len(sep)} sep x l=0,2,4, all effects incl. lensing, full-sky (bounded sample)"},
-            "cpu_baseline": {"value": v, "unit": "points/s", "cores": int(cores), "kind": "reference" if fast else "reference (-O2)", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "points/s", "cores": int(cores), "kind": "reference" if fast else "reference (-O2)", "sample": sample,
+                             "strata": strata},
             "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -145,16 +155,99 @@ def cpu_baseline(z, sep, ls, budget_points=72):
                       f"reference sources built -O3{' -ffast-math' if fast else ''} -fopenmp, tables prebuilt"}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one di_items_smem_kernel launch on this very workload (cfg5, one GPU), from
-# the ncu --set full capture summarised in profiles/r1_di_kernel_cfg5_v41_ncu.txt: 19.04 MB read + 15 KB written in a 169 ms
-# launch.  Algorithmic bytes of that launch: the (point, mu) items in (12 B each), one double per item out, the 6 MB of tables
-# once = ~45 MB (the items are expanded on the device by the step's own expand_items_kernel and are still in L2); either way
-# ~0.1 GB/s -- the kernel does not stream HBM (L2 hit rate 99.97 %).  Its ceiling is on-chip: the same capture has the L1 /
-# shared-memory data pipe at 77 % of peak (81 % before the knots were packed) and the FP64 pipe at 36 %.
-TRAFFIC_BYTES_PER_LAUNCH_CFG5_1GPU = 1.9051e7
-NCU_PIPES_CFG5_1GPU = {"source": "profiles/r1_di_kernel_cfg5_v41_ncu.txt (ncu --set full of this kernel on this workload)",
-                       "l1tex_data_pipe_pct_of_peak": 76.7, "shared_memory_pct_of_peak": 58.2, "fp64_pipe_pct_of_peak": 35.6,
-                       "issue_active_pct": 43.0}
+def ncu_summary():
+    """per-launch DRAM traffic and pipe utilisations of the dominant kernel on this very workload (cfg5, one GPU), read from the
+    committed summary of an `ncu --set full` capture (profiles/ncu_di_kernel_cfg5.json, written by tools/ncu_summary.py from the
+    .ncu-rep; the file names the capture and the library version it was taken on).  None when the file is missing."""
+    f = ROOT / "profiles" / "ncu_di_kernel_cfg5.json"
+    if not f.exists():
+        return None
+    return json.loads(f.read_text())
+
+
+def parity_check(eng, full, z, sep, ls):
+    """max error of the multipoles this run just TIMED against the converged-oracle fixture (tests/golden/converged_cfg5.npz: the
+    reference's integrands under adaptive / converged integration at 128 stratified points of this grid), relative to the
+    l = 0..4 scale of each point.  `full` is [n_l, n_items] in the layout of coffe_b200_multipoles_range."""
+    f = ROOT / "tests" / "golden" / "converged_cfg5.npz"
+    if not f.exists() or len(z) != 32 or len(sep) != 1000:
+        return None
+    fx = np.load(f)
+    want = fx["pieces"].sum(1)                                   # [k, l]
+    got = full[:, fx["iz"] * len(sep) + fx["ir"]].T              # [k, l]
+    scale = np.max(np.abs(want), axis=1, keepdims=True)
+    err = np.abs(got - want) / scale
+    return {"max_rel_err": float(err.max()), "median_rel_err": float(np.median(err)), "n_points": int(len(fx["iz"])) * len(ls),
+            "fixture": "tests/golden/converged_cfg5.npz", "tolerance": 1e-5, "ok": bool(err.max() < 1e-5),
+            "oracle_self_error": float(fx["oracle_self_error"].max())}
+
+
+def load_tables():
+    from coffe_b200.default_tables import load_default_tableset
+    return load_default_tableset()
+
+
+CONTRIB_FLAGS = {"den": "has_density", "rsd": "has_rsd", "len": "has_lensing", "d1": "has_d1", "d2": "has_d2", "g1": "has_g1",
+                 "g2": "has_g2", "g3": "has_g3", "g4": "has_g4", "g5": "has_g5"}
+
+
+def own_tables(eng, z):
+    """the repo's own table pipeline from P(k) + cosmology (coffe_b200.Coffe: background.py on the host, coffe_b200_integrals on
+    the device), timed phase by phase: what a first call on a new cosmology pays before any signal kernel runs"""
+    import coffe_b200
+    c = coffe_b200.Coffe(device=eng.device, z_mean=[2.0], deltaz=[0.3], sep=[100.0], l=[0, 2, 4], **{f: True for f in CONTRIB_FLAGS.values()})
+    c._engine = eng                                   # same context as the benchmark (one table upload, one stream)
+    t = {}
+    t0 = time.perf_counter(); c._background_init(); t["background_ms"] = 1e3 * (time.perf_counter() - t0)
+    c._power_spectrum_init()
+    t0 = time.perf_counter(); c._integrals_init(); t["integrals_ms"] = 1e3 * (time.perf_counter() - t0)
+    t["integrals_kernel_ms"] = eng.last_timing()[0]
+    t0 = time.perf_counter(); ts = c._tableset(); t["tableset_ms"] = 1e3 * (time.perf_counter() - t0)
+    return ts, t
+
+
+def extras(eng, tables):
+    """the other configurations of BASELINE.json through the same C ABI, host buffers in and out (wall clock around the call,
+    second call of two): cfg2 (full-sky 2PCF, 100 separations x 50 mu at z = 1), cfg3 (redshift-averaged multipoles, den + rsd + len,
+    8 bins x 200 separations) and the set-up path (table upload = host assembly + shared-memory table build + H2D)"""
+    out = {}
+    sep2, mu2 = np.linspace(10.0, 300.0, 100) / H, np.linspace(-0.98, 0.98, 50)
+    eng.set_options(ALL)
+    eng.corrfunc([1.0], mu2, sep2)
+    t0 = time.perf_counter(); r = eng.corrfunc([1.0], mu2, sep2); dt = time.perf_counter() - t0
+    out["cfg2_corrfunc"] = {"value": r.size / dt, "unit": "points/s", "points": int(r.size), "wall_ms": dt * 1e3, "kernel_ms": eng.last_timing()[0],
+                            "workload": "cfg2: full-sky 2PCF, all effects, z_mean = 1.0, 100 separations x 50 mu"}
+    edges = np.linspace(0.5, 2.0, 9)
+    sep3 = np.linspace(10.0, 160.0, 200) / H
+    eng.set_options(("den", "rsd", "len"))
+    eng.average_multipoles(edges[:-1], edges[1:], sep3, [0, 2, 4])
+    t0 = time.perf_counter(); r = eng.average_multipoles(edges[:-1], edges[1:], sep3, [0, 2, 4]); dt = time.perf_counter() - t0
+    out["cfg3_average_multipoles"] = {"value": r.size / dt, "unit": "points/s", "points": int(r.size), "wall_ms": dt * 1e3, "kernel_ms": eng.last_timing()[0],
+                                      "workload": "cfg3: redshift-averaged multipoles l = 0,2,4, den + rsd + len, 8 bins 0.5-2.0, 200 separations (10-160 Mpc/h: "
+                                                  "the bins of width 0.1875 hold no larger separation)"}
+    eng.set_options(ALL)
+    t0 = time.perf_counter(); eng.upload_tables(tables); out["upload_tables_ms"] = 1e3 * (time.perf_counter() - t0)
+    return out
+
+
+def covariance_cpu_baseline(k, pk, sep):
+    """the reference's own coffe_covariance_init (OpenMP over all host cores) on a 20 x 20 separation
+    sub-block of cfg4, one redshift bin: (3 x 20)^2 entries"""
+    from oracle import coffe_oracle as O
+    if not O.available(fast=True) and not O.available():
+        return None
+    fast = O.available(fast=True)
+    ref = O.RefCoffe(fast=fast)
+    ref.set_power_spectrum((k, pk))
+    ref.set_contributions(["den", "rsd"]); ref.set_z_mean([1.0]); ref.set_deltaz([0.1]); ref.set_l([0, 2, 4]); ref.set_sep(sep)
+    ref.set_fsky([0.2]); ref.set_density1([1e-3 * H ** 3]); ref.set_density2([1e-3 * H ** 3]); ref.set_pixelsize([2.0 / H])
+    ref.set_covariance(window=0)
+    ref.lib.ref_background(ref.h_)
+    t = time.perf_counter()
+    c = ref.covariance()
+    dt = time.perf_counter() - t
+    return {"value": c.size / dt, "unit": "entries/s", "cores": int(ref.lib.ref_nthreads(ref.h_)), "kind": "reference",
+            "sample": f"1 z x (3 x {len(sep)})^2 = {c.size} entries (every 5th separation of cfg4) in {dt:.1f} s, covariance_integration_method = standard"}
 
 
 def covariance_cfg4(eng, args):
@@ -182,7 +275,14 @@ def covariance_cfg4(eng, args):
     dt_f = time.perf_counter() - t0
     ms_f, launches_f = eng.last_timing()
     eng.set_options(ALL)
+    base = None
+    if not args.no_cpu_baseline:
+        try:
+            base = covariance_cpu_baseline(k, pk, sepc[::5])
+        except Exception as e:
+            base = {"value": None, "unit": "entries/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
     return {"value": out.size / dt, "unit": "entries/s", "entries": int(out.size), "wall_ms": dt * 1e3, "kernel_ms": ms, "gpu_launches": launches,
+            "cpu_baseline": base,
             "workload": "cfg4: 4 z x (3 x 100)^2, den + rsd, cosmic + mixed + Poisson, unbinned, covariance_integration_method = standard",
             "fftlog": {"value": out_f.size / dt_f, "unit": "entries/s", "wall_ms": dt_f * 1e3, "kernel_ms": ms_f, "gpu_launches": launches_f,
                        "sampling": 8000}}
@@ -199,6 +299,10 @@ def main():
     ap.add_argument("--sample-points", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-covariance", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the cfg2 / cfg3 / set-up measurements")
+    ap.add_argument("--tables", default="reference", choices=("reference", "own"),
+                    help="reference: tables the reference built (tests/golden/default_tables.npz); own: the repo's own pipeline "
+                         "(Coffe -> background.py -> coffe_b200_integrals -> upload) from P(k) and the cosmology")
     ap.add_argument("--variant", type=int, default=-1, help="items kernel variant (experiments; default = library default)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -210,10 +314,12 @@ def main():
         reference_arm(args, z, sep, ls, rank)
         return
 
+    # torch here is plumbing of the benchmark harness only (process group for the barrier / max-over-ranks and for handing the
+    # 128-byte NCCL id to the ranks); the product package is torch-free and gathers with its own NCCL calls
     import torch
     import torch.distributed as dist
     import coffe_b200
-    from coffe_b200.default_tables import load_default_tableset
+    from coffe_b200 import engine as E
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: coffe_b200 has no CPU fallback")
@@ -221,16 +327,33 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng = coffe_b200.Engine(local)
-    eng.upload_tables(load_default_tableset())
+    setup = None
+    if args.tables == "own":
+        tables, setup = own_tables(eng, z)
+    else:
+        tables = load_tables()
+    t0 = time.perf_counter()
+    eng.upload_tables(tables)
+    t_upload = 1e3 * (time.perf_counter() - t0)
     eng.set_options(ALL)
+    if args.tables == "own" and world == 1:
+        # time to first result on a new cosmology: background + integrals + table upload + the first full-grid call (cold mu rules)
+        t0 = time.perf_counter()
+        eng.multipoles_range(z, sep, ls, 0, len(z) * len(sep))
+        setup["upload_ms"] = t_upload
+        setup["first_call_ms"] = 1e3 * (time.perf_counter() - t0)
+        setup["time_to_first_result_ms"] = setup["background_ms"] + setup["integrals_ms"] + setup["tableset_ms"] + t_upload + setup["first_call_ms"]
     if args.variant >= 0:
         eng.set_kernel_variant(args.variant)
+    if world > 1:
+        uid = [E.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        eng.comm_init(rank, world, uid[0])
 
-    from coffe_b200 import sharding
     n_items = len(z) * len(sep)
-    # contiguous blocks of (z, r) items with equal estimated cost (evaluations counted by the library on a few rows and
-    # columns of the grid, outside the timed region); every rank derives the same boundaries
-    bounds = sharding.weighted_bounds(sharding.separable_cost(eng, z, sep, ls), world) if world > 1 else [0, n_items]
+    # contiguous blocks of (z, r) items with equal estimated cost (integrand evaluations counted per item by the library,
+    # outside the timed region for the kernel-only arm, inside it for the end-to-end arm); every rank derives the same boundaries
+    bounds = E.balance_bounds(eng.multipoles_cost(z, sep, ls), world) if world > 1 else [0, n_items]
     begin, end = bounds[rank], bounds[rank + 1]
     n_pts_total = n_items * len(ls)
 
@@ -239,44 +362,55 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- kernel-only arm: inputs resident in HBM ------------------------------------------------------
+    # ---- kernel-only arm: inputs resident in HBM; at N > 1 the NCCL gather of the blocks is part of every step ----------
     plan = eng.plan_multipoles(z, sep, ls, begin, end)
+
+    def step():
+        if world > 1:
+            k, g = plan.execute_gather(bounds)
+            return k + g, g
+        return plan.execute(), 0.0
+
     for _ in range(args.warmup):
-        plan.execute()
+        step()
     barrier()
     with ClockSampler(local) as clocks:
         t0 = time.perf_counter()
-        dev_ms = 0.0
+        dev_ms = gather_ms = 0.0
         si_ms = di_ms = 0.0
         for _ in range(args.steps):
-            dev_ms += plan.execute()           # CUDA events on the launching stream, synchronised each step
+            a, g = step()                       # CUDA events on the launching stream, synchronised each step
+            dev_ms += a; gather_ms += g
             a, b = eng.last_kernel_times()
             si_ms += a; di_ms += b
         barrier()
         wall = time.perf_counter() - t0
     launches = eng.last_timing()[1] * args.steps
-    res_local = plan.fetch()
-    t_dev = torch.tensor([dev_ms, wall * 1e3, si_ms, di_ms], dtype=torch.float64, device="cuda")
+    full = plan.fetch_gathered() if world > 1 else plan.fetch()
+    t_dev = torch.tensor([dev_ms, wall * 1e3, si_ms, di_ms, gather_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    dev_ms_max, wall_ms_max, si_ms_max, di_ms_max = t_dev.tolist()
+    dev_ms_max, wall_ms_max, si_ms_max, di_ms_max, gather_ms_max = t_dev.tolist()
     n_work, n_ni, n_si, n_di = plan.count()
     cnt = torch.tensor([n_work, n_ni, n_si, n_di, launches], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     n_work, n_ni, n_si, n_di, launches = cnt.tolist()
-
-    # one gather of the result slices (NCCL over NVLink); checks the sharded result is complete
-    full = sharding.gather_ranges(res_local, n_items, dist, device="cuda", bounds=bounds) if world > 1 else res_local
     plan.close()
 
-    # ---- end-to-end arm: the C ABI call with host buffers ---------------------------------------------
+    # ---- end-to-end arm: the C ABI call with HOST buffers.  N = 1: coffe_b200_multipoles_range.  N > 1: coffe_b200_multipoles_sharded
+    # (block boundaries, this rank's kernels, device-to-device NCCL gather, D2H of the full grid on rank 0) -- all inside the timed region
+    def e2e_call():
+        if world > 1:
+            return eng.multipoles_sharded(z, sep, ls, bounds=None, want_result=(rank == 0))[0]
+        return eng.multipoles_range(z, sep, ls, 0, n_items)
+
     for _ in range(min(args.warmup, 1)):
-        eng.multipoles_range(z, sep, ls, begin, end)
+        e2e_call()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out = eng.multipoles_range(z, sep, ls, begin, end)
+        out = e2e_call()
     barrier()
     e2e_s = time.perf_counter() - t0
     t_e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -286,18 +420,23 @@ def main():
     # bytes per step crossing PCIe: per point z, sep, rule index and the two item offsets; per separation the two mu rules
     # (nodes + weights; the (point, mu, weight) items themselves are expanded on the device); per-point pieces out
     h2d = int((end - begin) * 28 + n_work / max(len(z), 1) * 16 + (len(sep) + 1) * 8)
-    d2h = int((end - begin) * 3 * len(ls) * 8)
+    d2h = int((n_items if world > 1 else (end - begin)) * 3 * len(ls) * 8)
 
     peak_tf = eng.fp64_peak_tflops()
     if rank == 0:
         assert np.all(np.isfinite(full)) and full.shape == (len(ls), n_items)
-        assert np.array_equal(out, res_local), "C-ABI call and prepared plan must agree bit for bit"
+        if world > 1:
+            from coffe_b200 import sharding
+            assert np.array_equal(out, sharding.ranges_to_grid(full, len(z), len(sep))), "sharded C-ABI call and prepared plan must agree bit for bit"
+        else:
+            assert np.array_equal(out, full), "C-ABI call and prepared plan must agree bit for bit"
         flops_per_step = F_NI * n_ni + F_SI * n_si + F_DI * n_di
         achieved_step = flops_per_step / world / (dev_ms_max / args.steps * 1e-3) / 1e12
         # dominant kernel: di_items_smem_kernel, one launch per step and rank
         di_launch_ms = di_ms_max / args.steps
         achieved = F_DI * n_di / world / (di_launch_ms * 1e-3) / 1e12 if di_launch_ms > 0 else None
         value = n_pts_total * args.steps / (dev_ms_max * 1e-3)
+        ncu = ncu_summary() if (world == 1 and args.nz == 32 and args.nsep == 1000) else None
         cov = None
         if not args.no_covariance:
             try:
@@ -310,26 +449,42 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"cfg5 bulk sweep {len(z)} z_mean x {len(sep)} sep x l=0,2,4, all effects incl. lensing, full-sky",
                        "points": n_pts_total, "work_items_z_r_mu": int(n_work), "integrand_evaluations": {"NI": n_ni, "SI": n_si, "DI": n_di},
-                       "tables": "DEFAULT_SETTINGS cosmology, PkL_CLASS.dat (coffe_b200/data/default_tables.npz)",
-                       "sharding": f"contiguous cost-balanced blocks of (z, r) items over {world} GPU(s), tables replicated, one NCCL gather",
+                       "tables": ("DEFAULT_SETTINGS cosmology, PkL_CLASS.dat; tables built by the reference (tests/golden/default_tables.npz)" if args.tables == "reference"
+                                  else "DEFAULT_SETTINGS cosmology, PkL_CLASS.dat; tables built by the repo's own pipeline (background.py + coffe_b200_integrals)"),
+                       "sharding": f"contiguous cost-balanced blocks of (z, r) items over {world} GPU(s), tables replicated, blocks gathered device to device "
+                                   f"by the library's NCCL calls on the compute stream" + (" (inside every timed step)" if world > 1 else " (none at N = 1)"),
                        "block_items": [bounds[r + 1] - bounds[r] for r in range(world)],
                        "l2_policy": "compute-bound FP64 kernel; working set (tables 2.6 MB) is L2-resident by design, no HBM streaming to flush",
                        "quadrature": eng.get_quadrature(), "wall_ms_per_step": wall_ms_max / args.steps},
             "roofline": {"bound": "fp64", "kernel": "di_items_smem_kernel", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved / peak_tf if peak_tf and achieved else None,
-                         "traffic": TRAFFIC_BYTES_PER_LAUNCH_CFG5_1GPU if (world == 1 and args.nz == 32 and args.nsep == 1000) else None,
-                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_di_kernel_cfg5_v41_ncu.txt",
-                         "ncu_pipes": NCU_PIPES_CFG5_1GPU if (world == 1 and args.nz == 32 and args.nsep == 1000) else None,
+                         "frac_meaning": "canonical-flop equivalent (SURVEY.md 8d: 450 flop per integrand evaluation) over the measured DFMA rate; "
+                                         "the executed-instruction utilisation is ncu_pipes.fp64_pipe_pct_of_peak",
+                         "traffic": ncu["traffic_bytes_per_launch"] if ncu else None,
+                         "traffic_source": ncu["source"] if ncu else None,
+                         "ncu_pipes": ncu["pipes"] if ncu else None,
                          "peak_source": "DFMA probe kernel measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                          "launch_ms": di_launch_ms, "share_of_step": di_ms_max / dev_ms_max if dev_ms_max else None,
                          "flops_per_launch": F_DI * n_di / world, "accounting": "SURVEY.md 8d: 450 flop per DI integrand evaluation",
                          "step": {"achieved": achieved_step, "frac": achieved_step / peak_tf if peak_tf else None, "flops": flops_per_step / world,
-                                  "si_kernel_ms": si_ms_max / args.steps, "accounting": "700/1000/450 flop per NI/SI/DI evaluation"}},
-            "e2e": {"value": n_pts_total * args.steps / e2e_s, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                                  "si_kernel_ms": si_ms_max / args.steps, "gather_ms": gather_ms_max / args.steps,
+                                  "accounting": "700/1000/450 flop per NI/SI/DI evaluation"}},
+            "e2e": {"value": n_pts_total * args.steps / e2e_s, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "call": "coffe_b200_multipoles_sharded (cost model + kernels + NCCL gather + D2H)" if world > 1 else "coffe_b200_multipoles_range"},
             "gpu_launches": int(launches), "clocks": clocks.summary(),
         }
+        parity = parity_check(eng, full, z, sep, ls)
+        if parity is not None:
+            line["parity"] = parity
+        if setup is not None:
+            line["setup"] = setup
         if cov is not None:
             line["covariance"] = cov
+        if not args.no_extras and world == 1:
+            try:
+                line["extras"] = extras(eng, tables)
+            except Exception as e:
+                line["extras"] = {"error": str(e)}
         if not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(z, sep, ls)
@@ -337,6 +492,7 @@ def main():
                 line["cpu_baseline"] = {"value": None, "unit": "points/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
         print(json.dumps(line), flush=True)
     if world > 1:
+        eng.comm_destroy()
         dist.destroy_process_group()
 
 

@@ -529,13 +529,12 @@ class Coffe:
         self._integrals = res
         self._tables_uploaded = False
 
-    def _upload(self):
+    def _tableset(self):
+        """the coffe_b200_tables the drivers hand to the library: background, biases, the I^n_l family and the divergent extras"""
         if self._background is None:
             self._background_init()
         if self._integrals is None or (self._divergent and self._integrals["i40"] is None):
             self._integrals_init()
-        if self._tables_uploaded:
-            return
         res = self._integrals
         integrals = [(n, l, half, res["r"], res["tables"][i]) for i, (n, l, half) in enumerate(res["keys"])]
         renorm = renorm0 = None
@@ -545,8 +544,14 @@ class Coffe:
             x0 = res["r40"].copy()
             x0[0] = 0.0
             renorm0 = (x0, res["renorm0"])
-        ts = capi.TableSet(self._background, self._bias, integrals, self.omega_cdm + self.omega_baryon, self.h, interp_method=5,
-                           renorm=renorm, renorm0=renorm0)
+        return capi.TableSet(self._background, self._bias, integrals, self.omega_cdm + self.omega_baryon, self.h, interp_method=5,
+                             renorm=renorm, renorm0=renorm0)
+
+    def _upload(self):
+        if self._tables_uploaded and self._background is not None and self._integrals is not None and \
+                not (self._divergent and self._integrals["i40"] is None):
+            return
+        ts = self._tableset()
         self._get_engine().upload_tables(ts)
         self._tables_uploaded = True
 

@@ -134,12 +134,13 @@ __global__ void cov_bessel_kernel(const double *__restrict__ k, const int n_node
 
 /* partial Gram products over a k range: P[split][p][row][col] += sum_k W_p(k) V[k][row] V[k][col] */
 __global__ void __launch_bounds__(256) cov_gram_kernel(const double *__restrict__ V, const double *__restrict__ W, const int n_nodes,
-                                                       const int Mpad, const int n_splits, double *__restrict__ P, const int accumulate)
+                                                       const int Mpad, const int n_splits, double *__restrict__ P, const int accumulate,
+                                                       const int tr0, const int n_tr /* tile rows [tr0, tr0 + n_tr): the rows this device owns */)
 {
     __shared__ double As[kKc][kTile], Bs[kKc][kTile], Ws[kKc][2];
     const int tiles = Mpad / kTile;
-    const int tile = blockIdx.x % (tiles * tiles), split = blockIdx.x / (tiles * tiles);
-    const int tr = tile / tiles, tc = tile % tiles;
+    const int tile = blockIdx.x % (n_tr * tiles), split = blockIdx.x / (n_tr * tiles);
+    const int tr = tr0 + tile / tiles, tc = tile % tiles;
     const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
     const int per = (n_nodes + n_splits - 1) / n_splits;
     const int k0 = split * per, k1 = min(n_nodes, k0 + per);
@@ -208,24 +209,25 @@ struct CovAssembly {
     int l[kMaxCovL];
     int poisson, mixed, cosmic, window;
     int d13, d24, d14, d23;     /* Kronecker deltas of the populations */
+    int row_begin, n_rows;      /* rows (i1*n_sep + m) of every bin's matrix this launch assembles */
 };
 
 __device__ __forceinline__ int sign_of(const int m) { return (abs(m) % 2 == 0) ? 1 : -1; }
 
-/* out[(((ib*n_l + i1)*n_sep + m)*n_l + i2)*n_sep + n]                         src/covariance.c:896-1044 */
+/* out[((ib*n_rows + (row - row_begin))*n_l + i2)*n_sep + n], row = i1*n_sep + m     src/covariance.c:896-1044 */
 __global__ void cov_assemble_kernel(const CovAssembly a, const CovBin *__restrict__ bins, const double *__restrict__ coef_cosmic,
                                     const double *__restrict__ coef_mixed, const double *__restrict__ G, const double *__restrict__ sep,
                                     double *__restrict__ out)
 {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t per_bin = (size_t)a.n_l * a.n_sep * a.n_l * a.n_sep;
+    const size_t per_bin = (size_t)a.n_rows * a.n_l * a.n_sep;
     if (idx >= per_bin * a.n_bins) return;
     const int ib = (int)(idx / per_bin);
     size_t r = idx % per_bin;
     const int n = (int)(r % a.n_sep); r /= a.n_sep;
     const int i2 = (int)(r % a.n_l); r /= a.n_l;
-    const int m = (int)(r % a.n_sep); r /= a.n_sep;
-    const int i1 = (int)r;
+    const int row = a.row_begin + (int)r;
+    const int m = row % a.n_sep, i1 = row / a.n_sep;
     const int l1 = a.l[i1], l2 = a.l[i2];
     const CovBin b = bins[ib];
     const size_t M2 = (size_t)a.Mpad * a.Mpad;
@@ -497,15 +499,18 @@ int fill_G_fftlog(coffe_b200_ctx *ctx, const coffe_b200_covariance_params *p, co
 
 }  // namespace
 
-extern "C" int coffe_b200_covariance(coffe_b200_ctx *ctx, const coffe_b200_covariance_params *p, double *out)
+/* rows [row_begin, row_end) of every bin (row = il1*n_sep + ir1; row_end < 0: all rows) into the full-size host buffer `out` */
+static int covariance_core(coffe_b200_ctx *ctx, const coffe_b200_covariance_params *p, int row_begin, int row_end, double *out)
 {
-    if (!ctx || !p || !out) return COFFE_B200_EINVAL;
-    COFFE_ENTER(ctx);
     if (!ctx->have_tables) { ctx->err = "no tables uploaded (the covariance needs the background and galaxy bias tables)"; return COFFE_B200_ENOTABLES; }
     ctx->last_ms = 0; ctx->last_launches = 0;
     const int n_l = p->n_l, n_sep = p->n_sep, n_bins = p->n_bins;
     if (n_l < 1 || n_l > kMaxCovL || n_sep < 0 || n_bins < 0 || !p->l || (n_sep > 0 && !p->sep)) { ctx->err = "bad covariance grid"; return COFFE_B200_EINVAL; }
     if (n_bins == 0 || n_sep == 0) return COFFE_B200_OK;
+    if (row_end < 0) { row_begin = 0; row_end = n_l * n_sep; }
+    if (row_begin < 0 || row_end > n_l * n_sep || row_begin > row_end) { ctx->err = "row range outside the matrix"; return COFFE_B200_EINVAL; }
+    if (row_begin == row_end) return COFFE_B200_OK;
+    if (p->integration_method == 2 && (row_begin != 0 || row_end != n_l * n_sep)) { ctx->err = "the 2-D FFTLog covariance is not row-separable"; return COFFE_B200_EINVAL; }
     if (!p->fsky || !p->density1 || !p->density2 || !p->pixelsize || (p->average ? (!p->z_min || !p->z_max) : (!p->z_mean || !p->deltaz))) {
         ctx->err = "missing per-bin covariance arrays"; return COFFE_B200_EINVAL;
     }
@@ -567,7 +572,8 @@ extern "C" int coffe_b200_covariance(coffe_b200_ctx *ctx, const coffe_b200_covar
     CK(d_l.upload(std::vector<int>(p->l, p->l + n_l), ctx->stream));
     const int M = n_l * n_sep, Mpad = ((M + kTile - 1) / kTile) * kTile;
     const int tiles = Mpad / kTile;
-    int n_splits = std::max(1, (4 * ctx->n_sm) / (tiles * tiles));
+    const int tr0 = row_begin / kTile, n_tr = (row_end - 1) / kTile - tr0 + 1;
+    int n_splits = std::max(1, (4 * ctx->n_sm) / (n_tr * tiles));
     const int chunk = std::max(kKc, std::min(n_nodes, (int)std::min<size_t>((size_t)1 << 31, ((size_t)2 << 30) / ((size_t)Mpad * 8))));
     if (n_splits > (chunk + kKc - 1) / kKc) n_splits = (chunk + kKc - 1) / kKc;
     CK(d_W.alloc((size_t)2 * n_nodes));
@@ -596,7 +602,7 @@ extern "C" int coffe_b200_covariance(coffe_b200_ctx *ctx, const coffe_b200_covar
             const size_t tot = (size_t)nn * Mpad;
             cov_bessel_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(d_k.p + c0, nn, d_sep.p, n_sep, d_l.p, n_l, delta, Mpad, d_V.p);
             CK(cudaGetLastError());
-            cov_gram_kernel<<<tiles * tiles * n_splits, 256, 0, ctx->stream>>>(d_V.p, d_W.p + 2 * (size_t)c0, nn, Mpad, n_splits, d_P.p, it > 0);
+            cov_gram_kernel<<<n_tr * tiles * n_splits, 256, 0, ctx->stream>>>(d_V.p, d_W.p + 2 * (size_t)c0, nn, Mpad, n_splits, d_P.p, it > 0, tr0, n_tr);
             CK(cudaGetLastError());
             ctx->last_launches += 2;
         }
@@ -674,18 +680,38 @@ extern "C" int coffe_b200_covariance(coffe_b200_ctx *ctx, const coffe_b200_covar
     for (int i = 0; i < n_l; ++i) a.l[i] = p->l[i];
     a.poisson = p->poisson != 0; a.mixed = p->mixed != 0; a.cosmic = p->cosmic != 0; a.window = p->window != 0;
     a.d13 = p->pop[0] == p->pop[2]; a.d24 = p->pop[1] == p->pop[3]; a.d14 = p->pop[0] == p->pop[3]; a.d23 = p->pop[1] == p->pop[2];
-    const size_t n_out = (size_t)n_bins * n_l * n_sep * n_l * n_sep;
+    a.row_begin = row_begin; a.n_rows = row_end - row_begin;
+    const size_t n_out = (size_t)n_bins * a.n_rows * n_l * n_sep;
     CK(d_out.alloc(n_out));
     cov_assemble_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, ctx->stream>>>(a, d_bins.p, d_cc.p, d_cm.p, d_G.p, d_sep.p, d_out.p);
     CK(cudaGetLastError());
     ctx->last_launches += 1;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
-    CK(cudaMemcpyAsync(out, d_out.p, n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    /* each bin's rows are one contiguous run of the caller's full-size buffer */
+    const size_t run = (size_t)a.n_rows * M * sizeof(double);
+    CK(cudaMemcpy2DAsync(out + (size_t)row_begin * M, (size_t)M * M * sizeof(double), d_out.p, run, run, n_bins, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_ms = ms;
-    for (size_t i = 0; i < n_out; ++i)
-        if (!std::isfinite(out[i])) { ctx->err = "non-finite covariance entry"; return COFFE_B200_ENONFINITE; }
+    for (int ib = 0; ib < n_bins; ++ib) {
+        const double *o = out + ((size_t)ib * M + row_begin) * M;
+        for (size_t i = 0; i < (size_t)a.n_rows * M; ++i)
+            if (!std::isfinite(o[i])) { ctx->err = "non-finite covariance entry"; return COFFE_B200_ENONFINITE; }
+    }
     return COFFE_B200_OK;
+}
+
+extern "C" int coffe_b200_covariance(coffe_b200_ctx *ctx, const coffe_b200_covariance_params *p, double *out)
+{
+    if (!ctx || !p || !out) return COFFE_B200_EINVAL;
+    COFFE_ENTER(ctx);
+    return covariance_core(ctx, p, 0, -1, out);
+}
+
+extern "C" int coffe_b200_covariance_rows(coffe_b200_ctx *ctx, const coffe_b200_covariance_params *p, int row_begin, int row_end, double *out)
+{
+    if (!ctx || !p || !out || row_end < 0) return COFFE_B200_EINVAL;
+    COFFE_ENTER(ctx);
+    return covariance_core(ctx, p, row_begin, row_end, out);
 }

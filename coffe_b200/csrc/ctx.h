@@ -56,6 +56,10 @@ struct coffe_b200_ctx {
     int last_launches = 0;
     /* bumped by every call that changes what a prepared plan was built from (tables, options, quadrature, kernel variant):
        a plan refuses to run against a different generation (coffe_b200_plan_execute -> EINVAL) */
+    /* one process per GPU: NCCL communicator (group.inc), events around the gather */
+    void *comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
+    cudaEvent_t ev_g[2] = {nullptr, nullptr};
     unsigned long generation = 0;
     std::vector<struct coffe_b200_plan *> live_plans;   /* released (device buffers freed, ctx cleared) by coffe_b200_destroy */
     std::mutex mu;

@@ -331,6 +331,24 @@ __global__ void expand_items_kernel(const int *__restrict__ point_rule, const in
     for (int j = 0; j < n; ++j) { item_point[dst + j] = p; item_mu[dst + j] = rule_mu[b + j]; item_w[dst + j] = rule_w[b + j]; }
 }
 
+/* integrand evaluations of every item of one list, accumulated per point (integers: the sum does not depend on the order);
+   mode 1 = local x integrated (two halves), mode 2 = integrated x integrated.  Used to cut cost-balanced blocks for the GPUs. */
+__global__ void item_cost_kernel(const __grid_constant__ Tables t, const __grid_constant__ Options o, const __grid_constant__ Rules q,
+                                 const int mode, const double *__restrict__ pz, const double *__restrict__ psep,
+                                 const int *__restrict__ item_point, const double *__restrict__ item_mu, const int n_items,
+                                 const unsigned int weight, unsigned long long *__restrict__ cost)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    const int p = item_point[i];
+    const Geometry g = geometry(bg_chi(t.bg, pz[p]), psep[p], item_mu[i]);
+    const EndVals e1 = end_eval(o, t, g.chi1, 1), e2 = end_eval(o, t, g.chi2, 2);
+    unsigned int c;
+    if (mode == 1) c = si_eval_count(q, g, si_half_setup(o, g, e1, e2, true)) + si_eval_count(q, g, si_half_setup(o, g, e2, e1, false));
+    else c = di_fast_eval_count(q, g, di_setup(o, e1, e2));
+    atomicAdd(&cost[p], (unsigned long long)c * weight);
+}
+
 /* ---- mu reduction: one warp per point, fixed summation order ---------------------------------- */
 /* pm[(point*3 + piece)*n_l + il]; piece 0 (NI) is copied from ni[]; pieces 1 and 2 each have their own mu rule */
 __global__ void reduce_multipoles_kernel(const int n_points,
@@ -389,17 +407,16 @@ __global__ void flatsky_multipoles_kernel(const __grid_constant__ Tables t, cons
    points (bin, r, iz): z = z1 + (z2 - z1) u, z1 = z(chi(z_min) + r/2), z2 = z(chi(z_max) - r/2), weight
    w_u H0 h / (Hc(z) (1+z))                                            src/signal.c:262-283 */
 __global__ void average_points_kernel(const __grid_constant__ Tables t, const double H0h,
-                                      const double *__restrict__ zmin, const double *__restrict__ zmax, const int n_bins,
-                                      const double *__restrict__ sep, const int n_sep,
-                                      const double *__restrict__ gl_x, const double *__restrict__ gl_w, const int n_z,
+                                      const double *__restrict__ zmin, const double *__restrict__ zmax, const double *__restrict__ gsep,
+                                      const int n_groups, const double *__restrict__ gl_x, const double *__restrict__ gl_w, const int n_z,
                                       double *__restrict__ pz, double *__restrict__ psep, double *__restrict__ pw)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_bins * n_sep * n_z) return;
-    const int iz = i % n_z, ir = (i / n_z) % n_sep, ib = i / (n_z * n_sep);
-    const double r = sep[ir];
-    const double z1 = spline_eval(t.bg.z_of_chi, bg_chi(t.bg, zmin[ib]) + r / 2.);
-    const double z2 = spline_eval(t.bg.z_of_chi, bg_chi(t.bg, zmax[ib]) - r / 2.);
+    if (i >= n_groups * n_z) return;
+    const int iz = i % n_z, ig = i / n_z;
+    const double r = gsep[ig];
+    const double z1 = spline_eval(t.bg.z_of_chi, bg_chi(t.bg, zmin[ig]) + r / 2.);
+    const double z2 = spline_eval(t.bg.z_of_chi, bg_chi(t.bg, zmax[ig]) - r / 2.);
     const double z = (z2 - z1) * gl_x[rule_offset(n_z) + iz] + z1;
     const int k = bg_index(t.bg, z);
     const double Hc = cubic_eval(t.bg.Hc[k], z - t.bg.z[k]);
@@ -716,6 +733,8 @@ struct coffe_b200_plan {
     LList ls;
     long n = 0;
     unsigned long generation = 0;   /* ctx->generation the item lists, stage sizes and mirror-symmetry decisions were built under */
+    DevBuf<double> full;            /* gathered result of all ranks (coffe_b200_plan_execute_gather) */
+    long n_total = 0;
 };
 
 namespace {
@@ -909,10 +928,13 @@ void coffe_b200_destroy(coffe_b200_ctx *ctx)
         /* plans that outlive their context become inert: their device buffers go back to the pool while the stream still exists */
         std::lock_guard<std::mutex> lock(ctx->mu);
         AllocScope scope(ctx->stream);
-        for (coffe_b200_plan *pl : ctx->live_plans) { pl->b.release(); pl->ctx = nullptr; }
+        for (coffe_b200_plan *pl : ctx->live_plans) { pl->b.release(); pl->full.release(); pl->ctx = nullptr; }
         ctx->live_plans.clear();
         cudaStreamSynchronize(ctx->stream);
     }
+    if (ctx->comm) coffe_b200_comm_destroy(ctx);
+    for (int i = 0; i < 2; ++i)
+        if (ctx->ev_g[i]) cudaEventDestroy(ctx->ev_g[i]);
     if (ctx->d_arena) cudaFree(ctx->d_arena);
     if (ctx->d_gl_x) cudaFree(ctx->d_gl_x);
     if (ctx->d_gl_w) cudaFree(ctx->d_gl_w);
@@ -1092,15 +1114,17 @@ int coffe_b200_multipoles(coffe_b200_ctx *ctx, const double *z_mean, int n_z, co
     return COFFE_B200_OK;
 }
 
-int coffe_b200_corrfunc(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double *mu, int n_mu,
-                        const double *sep, int n_sep, double *out)
+/* 2PCF pieces of the flattened output entries (iz*n_mu + imu)*n_sep + ir in [begin, end): pieces[piece*(end-begin) + k] */
+static int corrfunc_core(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double *mu, int n_mu,
+                         const double *sep, int n_sep, long begin, long end, std::vector<double> &pieces)
 {
-    if (!ctx || !out) return COFFE_B200_EINVAL;
-    COFFE_ENTER(ctx);
     if (!ctx->have_tables || !ctx->layout.has_ifam) { ctx->err = "no tables uploaded (the signal needs the I^n_l family)"; return COFFE_B200_ENOTABLES; }
-    if (!z_mean || !sep || !mu || n_z < 0 || n_sep < 0 || n_mu < 0) { ctx->err = "bad grid arguments"; return COFFE_B200_EINVAL; }
+    if (n_z < 0 || n_sep < 0 || n_mu < 0 || (n_z > 0 && !z_mean) || (n_sep > 0 && !sep) || (n_mu > 0 && !mu)) { ctx->err = "bad grid arguments"; return COFFE_B200_EINVAL; }
     ctx->last_ms = 0; ctx->last_launches = 0;
-    const size_t n_out = (size_t)n_z * n_mu * n_sep;
+    const long total = (long)n_z * n_mu * n_sep;
+    if (begin < 0 || end > total || begin > end) { ctx->err = "entry range outside the grid"; return COFFE_B200_EINVAL; }
+    const size_t n_out = (size_t)(end - begin);
+    pieces.assign(3 * n_out, 0.0);
     if (n_out == 0) return COFFE_B200_OK;
     for (int i = 0; i < n_mu; ++i)
         if (!(mu[i] > -1.0 && mu[i] < 1.0)) { ctx->err = "mu must lie strictly inside (-1, 1)"; return COFFE_B200_EINVAL; }
@@ -1110,18 +1134,27 @@ int coffe_b200_corrfunc(coffe_b200_ctx *ctx, const double *z_mean, int n_z, cons
     Batch b;
     std::vector<double> pz, psep, item_mu;
     std::vector<int> item_point;
-    for (int iz = 0; iz < n_z; ++iz)
+    /* points: the (iz, ir) pairs the range touches, in (iz, ir) order; items in output order (iz, imu, ir) */
+    const int iz_lo = (int)(begin / ((long)n_mu * n_sep)), iz_hi = (int)((end - 1) / ((long)n_mu * n_sep));
+    for (int iz = iz_lo; iz <= iz_hi; ++iz)
         for (int ir = 0; ir < n_sep; ++ir) {
-            const int rc = check_point(ctx, z_mean[iz], sep[ir], ren && renorm_range_needed(ctx->o));
-            if (rc) return rc;
             pz.push_back(z_mean[iz]); psep.push_back(sep[ir]);
-            const double chi2 = bg_chi(ctx->t_host.bg, z_mean[iz]) + sep[ir] / 2.;
-            if (chi2 > b.chi_max) b.chi_max = chi2;
         }
-    /* items in output order (iz, imu, ir); both integrated pieces are evaluated at the requested mu */
-    for (int iz = 0; iz < n_z; ++iz)
-        for (int im = 0; im < n_mu; ++im)
-            for (int ir = 0; ir < n_sep; ++ir) { item_point.push_back(iz * n_sep + ir); item_mu.push_back(mu[im]); }
+    std::vector<char> used(pz.size(), 0);
+    item_point.reserve(n_out); item_mu.reserve(n_out);
+    for (long e = begin; e < end; ++e) {
+        const int ir = (int)(e % n_sep), im = (int)((e / n_sep) % n_mu), iz = (int)(e / ((long)n_sep * n_mu));
+        const int p = (iz - iz_lo) * n_sep + ir;
+        item_point.push_back(p); item_mu.push_back(mu[im]);
+        used[p] = 1;
+    }
+    for (size_t p = 0; p < pz.size(); ++p) {
+        if (!used[p]) continue;
+        const int rc = check_point(ctx, pz[p], psep[p], ren && renorm_range_needed(ctx->o));
+        if (rc) return rc;
+        const double chi2 = bg_chi(ctx->t_host.bg, pz[p]) + psep[p] / 2.;
+        if (chi2 > b.chi_max) b.chi_max = chi2;
+    }
     b.n_points = (int)pz.size();
     const int n_items = (int)item_mu.size();
     CK(b.pz.upload(pz, ctx->stream));
@@ -1146,54 +1179,86 @@ int coffe_b200_corrfunc(coffe_b200_ctx *ctx, const double *z_mean, int n_z, cons
     rc = launch_integrated(ctx, b, 2);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
-    std::vector<double> ni(n_out), si(n_out), di(n_out);
-    CK(cudaMemcpyAsync(ni.data(), b.ni.p, n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(si.data(), b.si.val.p, n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(di.data(), b.di.val.p, n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(pieces.data(), b.ni.p, n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(pieces.data() + n_out, b.si.val.p, n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(pieces.data() + 2 * n_out, b.di.val.p, n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_ms = ms;
-    for (size_t i = 0; i < n_out; ++i) out[i] = ni[i] + si[i] + di[i];
-    return check_finite(ctx, out, n_out);
+    return check_finite(ctx, pieces.data(), pieces.size());
 }
 
-int coffe_b200_average_multipoles(coffe_b200_ctx *ctx, const double *z_min, const double *z_max, int n_bins,
-                                  const double *sep, int n_sep, const int *l, int n_l, double *out)
+int coffe_internal_corrfunc_range(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double *mu, int n_mu,
+                                  const double *sep, int n_sep, long begin, long end, double *out_sum)
+{
+    std::vector<double> pc;
+    const int rc = corrfunc_core(ctx, z_mean, n_z, mu, n_mu, sep, n_sep, begin, end, pc);
+    if (rc) return rc;
+    const size_t n = (size_t)(end - begin);
+    for (size_t i = 0; i < n; ++i) out_sum[i] = pc[i] + pc[n + i] + pc[2 * n + i];
+    return COFFE_B200_OK;
+}
+
+int coffe_b200_corrfunc(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double *mu, int n_mu,
+                        const double *sep, int n_sep, double *out)
 {
     if (!ctx || !out) return COFFE_B200_EINVAL;
     COFFE_ENTER(ctx);
+    return coffe_internal_corrfunc_range(ctx, z_mean, n_z, mu, n_mu, sep, n_sep, 0, (long)n_z * n_mu * n_sep, out);
+}
+
+int coffe_b200_corrfunc_range_pieces(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double *mu, int n_mu,
+                                     const double *sep, int n_sep, long begin, long end, double *out)
+{
+    if (!ctx || !out) return COFFE_B200_EINVAL;
+    COFFE_ENTER(ctx);
+    std::vector<double> pc;
+    const int rc = corrfunc_core(ctx, z_mean, n_z, mu, n_mu, sep, n_sep, begin, end, pc);
+    if (rc) return rc;
+    std::memcpy(out, pc.data(), pc.size() * sizeof(double));
+    return COFFE_B200_OK;
+}
+
+/* redshift-averaged multipoles of the flattened (ibin*n_sep + ir) groups [begin, end): hm[(k*3 + piece)*n_l + il] */
+int coffe_internal_average_core(coffe_b200_ctx *ctx, const double *z_min, const double *z_max, int n_bins,
+                                const double *sep, int n_sep, const int *l, int n_l, long begin, long end, std::vector<double> &hm)
+{
     if (!ctx->have_tables || !ctx->layout.has_ifam) { ctx->err = "no tables uploaded (the signal needs the I^n_l family)"; return COFFE_B200_ENOTABLES; }
-    if (!z_min || !z_max || !sep || n_bins < 0 || n_sep < 0) { ctx->err = "bad grid arguments"; return COFFE_B200_EINVAL; }
+    if (n_bins < 0 || n_sep < 0 || (n_bins > 0 && (!z_min || !z_max)) || (n_sep > 0 && !sep)) { ctx->err = "bad grid arguments"; return COFFE_B200_EINVAL; }
     int rc = check_l(ctx, l, n_l);
     if (rc) return rc;
     ctx->last_ms = 0; ctx->last_launches = 0;
-    const int n_groups = n_bins * n_sep, nz = ctx->qc.n_z;
+    const long total = (long)n_bins * n_sep;
+    if (begin < 0 || end > total || begin > end) { ctx->err = "group range outside the grid"; return COFFE_B200_EINVAL; }
+    const int n_groups = (int)(end - begin), nz = ctx->qc.n_z;
+    hm.assign((size_t)n_groups * 3 * n_l, 0.0);
     if (n_groups == 0) return COFFE_B200_OK;
     CK(cudaSetDevice(ctx->device));
     const bool ren = needs_renorm(ctx->o);
     if (ren && !ctx->layout.has_divergent) { ctx->err = "d2/g1..g5 need the divergent I^4_0 tables (par->divergent)"; return COFFE_B200_EINVAL; }
     Batch b;
     std::vector<int> point_rule((size_t)n_groups * nz);
+    std::vector<double> g_zmin(n_groups), g_zmax(n_groups), g_sep(n_groups);
     const Tables &th = ctx->t_host;
-    for (int ib = 0; ib < n_bins; ++ib) {
+    for (long gi = begin; gi < end; ++gi) {
+        const int ib = (int)(gi / n_sep), ir = (int)(gi % n_sep), k = (int)(gi - begin);
         if (!(z_min[ib] > 0.0) || !(z_max[ib] > z_min[ib]) || !(z_max[ib] < th.bg.z[th.bg.n - 1])) { ctx->err = "bad redshift bin"; return COFFE_B200_ERANGE; }
         const double c1 = bg_chi(th.bg, z_min[ib]), c2 = bg_chi(th.bg, z_max[ib]);
-        for (int ir = 0; ir < n_sep; ++ir) {
-            if (!(sep[ir] > 0.0) || !(c1 + sep[ir] / 2. < c2 - sep[ir] / 2.)) {
-                ctx->err = "separation does not fit inside the redshift bin (need chi(z_min) + r/2 < chi(z_max) - r/2)";
-                return COFFE_B200_ERANGE;
-            }
-            if (ren && renorm_range_needed(ctx->o) && !(c2 <= th.ren2d.x[th.ren2d.n - 1])) { ctx->err = "redshift bin outside the renormalisation grid"; return COFFE_B200_ERANGE; }
-            for (int k = 0; k < nz; ++k) point_rule[((size_t)ib * n_sep + ir) * nz + k] = ir;
+        if (!(sep[ir] > 0.0) || !(c1 + sep[ir] / 2. < c2 - sep[ir] / 2.)) {
+            ctx->err = "separation does not fit inside the redshift bin (need chi(z_min) + r/2 < chi(z_max) - r/2)";
+            return COFFE_B200_ERANGE;
         }
+        if (ren && renorm_range_needed(ctx->o) && !(c2 <= th.ren2d.x[th.ren2d.n - 1])) { ctx->err = "redshift bin outside the renormalisation grid"; return COFFE_B200_ERANGE; }
+        for (int j = 0; j < nz; ++j) point_rule[(size_t)k * nz + j] = ir;
+        g_zmin[k] = z_min[ib]; g_zmax[k] = z_max[ib]; g_sep[k] = sep[ir];
         if (c2 > b.chi_max) b.chi_max = c2;
     }
-    /* points on the device */
+    /* points on the device: one (zmin, zmax, sep) triple per group */
     DevBuf<double> d_zmin, d_zmax, d_sep, pw, gm;
-    CK(d_zmin.upload(std::vector<double>(z_min, z_min + n_bins), ctx->stream));
-    CK(d_zmax.upload(std::vector<double>(z_max, z_max + n_bins), ctx->stream));
-    CK(d_sep.upload(std::vector<double>(sep, sep + n_sep), ctx->stream));
+    CK(d_zmin.upload(g_zmin, ctx->stream));
+    CK(d_zmax.upload(g_zmax, ctx->stream));
+    CK(d_sep.upload(g_sep, ctx->stream));
     const int n_points = n_groups * nz;
     CK(b.pz.alloc(n_points));
     CK(b.psep.alloc(n_points));
@@ -1204,7 +1269,7 @@ int coffe_b200_average_multipoles(coffe_b200_ctx *ctx, const double *z_min, cons
     CK(b.ni.alloc((size_t)b.n_points * n_l));
     CK(b.pm.alloc((size_t)b.n_points * 3 * n_l));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    average_points_kernel<<<(n_points + 127) / 128, 128, 0, ctx->stream>>>(ctx->t, ctx->o.H0h, d_zmin.p, d_zmax.p, n_bins, d_sep.p, n_sep,
+    average_points_kernel<<<(n_points + 127) / 128, 128, 0, ctx->stream>>>(ctx->t, ctx->o.H0h, d_zmin.p, d_zmax.p, d_sep.p, n_groups,
                                                                           ctx->d_gl_x, ctx->d_gl_w, nz, b.pz.p, b.psep.p, pw.p);
     CK(cudaGetLastError());
     ctx->last_launches += 1;
@@ -1214,19 +1279,44 @@ int coffe_b200_average_multipoles(coffe_b200_ctx *ctx, const double *z_min, cons
     CK(cudaGetLastError());
     ctx->last_launches += 1;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
-    std::vector<double> hm((size_t)n_groups * 3 * n_l);
     CK(cudaMemcpyAsync(hm.data(), gm.p, hm.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_ms = ms;
+    return check_finite(ctx, hm.data(), hm.size());
+}
+
+int coffe_b200_average_multipoles(coffe_b200_ctx *ctx, const double *z_min, const double *z_max, int n_bins,
+                                  const double *sep, int n_sep, const int *l, int n_l, double *out)
+{
+    if (!ctx || !out) return COFFE_B200_EINVAL;
+    COFFE_ENTER(ctx);
+    std::vector<double> hm;
+    const int rc = coffe_internal_average_core(ctx, z_min, z_max, n_bins, sep, n_sep, l, n_l, 0, (long)n_bins * n_sep, hm);
+    if (rc) return rc;
     for (int ib = 0; ib < n_bins; ++ib)
         for (int il = 0; il < n_l; ++il)
             for (int ir = 0; ir < n_sep; ++ir) {
                 const size_t g = (size_t)ib * n_sep + ir;
                 out[((size_t)ib * n_l + il) * n_sep + ir] = hm[(g * 3 + 0) * n_l + il] + hm[(g * 3 + 1) * n_l + il] + hm[(g * 3 + 2) * n_l + il];
             }
-    return check_finite(ctx, out, (size_t)n_groups * n_l);
+    return COFFE_B200_OK;
+}
+
+int coffe_b200_average_multipoles_range_pieces(coffe_b200_ctx *ctx, const double *z_min, const double *z_max, int n_bins,
+                                               const double *sep, int n_sep, const int *l, int n_l, long begin, long end, double *out)
+{
+    if (!ctx || !out) return COFFE_B200_EINVAL;
+    COFFE_ENTER(ctx);
+    std::vector<double> hm;
+    const int rc = coffe_internal_average_core(ctx, z_min, z_max, n_bins, sep, n_sep, l, n_l, begin, end, hm);
+    if (rc) return rc;
+    const size_t n = (size_t)(end - begin);
+    for (size_t k = 0; k < n; ++k)
+        for (int piece = 0; piece < 3; ++piece)
+            for (int il = 0; il < n_l; ++il) out[((size_t)piece * n_l + il) * n + k] = hm[(k * 3 + piece) * n_l + il];
+    return COFFE_B200_OK;
 }
 
 int coffe_b200_last_timing(const coffe_b200_ctx *ctx, double *kernel_ms, int *n_launches)
@@ -1345,6 +1435,7 @@ void coffe_b200_plan_destroy(coffe_b200_plan *plan)
         cudaSetDevice(ctx->device);
         for (size_t i = 0; i < ctx->live_plans.size(); ++i)
             if (ctx->live_plans[i] == plan) { ctx->live_plans.erase(ctx->live_plans.begin() + i); break; }
+        plan->full.release();
         plan->b.release();          /* device buffers back to the pool in stream order, under the context's allocation scope */
     }
     delete plan;
@@ -1375,4 +1466,90 @@ int coffe_b200_fp64_peak(coffe_b200_ctx *ctx, double *tflops)
     return COFFE_B200_OK;
 }
 
+/* ================================================================================================= */
+/* ---- cost model and block boundaries ---------------------------------------------------------------- */
+int coffe_b200_balance_bounds(const double *cost, long n_items, int n_parts, long *bounds)
+{
+    if (!bounds || n_parts < 1 || n_items < 0 || (n_items > 0 && !cost)) return COFFE_B200_EINVAL;
+    for (int r = 0; r <= n_parts; ++r) bounds[r] = 0;
+    if (n_items == 0) return COFFE_B200_OK;
+    std::vector<double> c((size_t)n_items + 1, 0.0);
+    for (long i = 0; i < n_items; ++i) {
+        if (!(cost[i] >= 0.0) || !std::isfinite(cost[i])) return COFFE_B200_EINVAL;
+        c[i + 1] = c[i] + cost[i];
+    }
+    if (!(c[n_items] > 0.0)) return COFFE_B200_EINVAL;
+    bounds[n_parts] = n_items;
+    for (int r = 1; r < n_parts; ++r) {
+        const double target = c[n_items] * r / n_parts;
+        long k = (long)(std::lower_bound(c.begin(), c.end(), target) - c.begin());      /* first c[k] >= target */
+        if (k > n_items) k = n_items;
+        if (k > 0 && std::fabs(c[k] - target) > std::fabs(c[k - 1] - target)) --k;        /* the closer of the two neighbours */
+        bounds[r] = std::max(k, bounds[r - 1]);
+    }
+    return COFFE_B200_OK;
+}
+
+namespace {
+
+/* cost[iz*n_sep + ir]: evaluations counted exactly on a few rows of the grid (every separation: the rules switch with r), linear in
+   z between them (the z dependence is the slow growth of the tail panels with distance) */
+int multipoles_cost_core(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double *sep, int n_sep, const int *l, int n_l,
+                         std::vector<double> &cost)
+{
+    cost.assign((size_t)n_z * n_sep, 1.0);
+    if (n_z == 0 || n_sep == 0 || !opt_has_integrated(ctx->o)) return COFFE_B200_OK;
+    std::vector<int> rows;
+    const int n_rows = std::min(n_z, 9);
+    for (int k = 0; k < n_rows; ++k) {
+        const int iz = n_rows == 1 ? 0 : (int)std::lround((double)k * (n_z - 1) / (n_rows - 1));
+        if (rows.empty() || rows.back() != iz) rows.push_back(iz);
+    }
+    std::vector<double> zs;
+    for (int iz : rows) zs.push_back(z_mean[iz]);
+    coffe_b200_plan pl;
+    int rc = plan_build(ctx, zs.data(), (int)zs.size(), sep, n_sep, l, n_l, 0, (long)zs.size() * n_sep, pl);
+    if (rc) return rc;
+    Batch &b = pl.b;
+    DevBuf<unsigned long long> d_cost;
+    CK(d_cost.alloc((size_t)b.n_points));
+    CK(cudaMemsetAsync(d_cost.p, 0, sizeof(unsigned long long) * b.n_points, ctx->stream));
+    ctx->o.out_multipoles = 1;
+    const Rules q = make_rules(ctx);
+    /* a local x integrated evaluation costs about two integrated x integrated ones (ncu: 713 against 342 instructions) */
+    if (opt_has_si(ctx->o) && b.si.n > 0)
+        item_cost_kernel<<<(b.si.n + 127) / 128, 128, 0, ctx->stream>>>(ctx->t, ctx->o, q, 1, b.pz.p, b.psep.p, b.si.point.p, b.si.mu.p, b.si.n, 2u, d_cost.p);
+    if (b.di.n > 0)
+        item_cost_kernel<<<(b.di.n + 127) / 128, 128, 0, ctx->stream>>>(ctx->t, ctx->o, q, 2, b.pz.p, b.psep.p, b.di.point.p, b.di.mu.p, b.di.n, 1u, d_cost.p);
+    CK(cudaGetLastError());
+    std::vector<unsigned long long> h((size_t)b.n_points);
+    CK(cudaMemcpyAsync(h.data(), d_cost.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int iz = 0, k = 0; iz < n_z; ++iz) {
+        while (k + 1 < (int)rows.size() - 1 && rows[k + 1] <= iz) ++k;
+        const int a = rows[k], bb = rows[std::min(k + 1, (int)rows.size() - 1)];
+        const double t = bb > a ? (double)(iz - a) / (bb - a) : 0.0;
+        const int ka = k, kb = std::min(k + 1, (int)rows.size() - 1);
+        for (int ir = 0; ir < n_sep; ++ir)
+            cost[(size_t)iz * n_sep + ir] = 1.0 + (1.0 - t) * (double)h[(size_t)ka * n_sep + ir] + t * (double)h[(size_t)kb * n_sep + ir];
+    }
+    return COFFE_B200_OK;
+}
+
+}  // namespace
+
+int coffe_b200_multipoles_cost(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double *sep, int n_sep,
+                               const int *l, int n_l, double *cost)
+{
+    if (!ctx || !cost) return COFFE_B200_EINVAL;
+    COFFE_ENTER(ctx);
+    std::vector<double> c;
+    const int rc = multipoles_cost_core(ctx, z_mean, n_z, sep, n_sep, l, n_l, c);
+    if (rc) return rc;
+    std::memcpy(cost, c.data(), c.size() * sizeof(double));
+    return COFFE_B200_OK;
+}
+
 }  // extern "C"
+
+#include "group.inc"

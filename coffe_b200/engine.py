@@ -112,6 +112,54 @@ class Engine:
                                                  capi.ptr(s), C.c_int(len(s)), capi.ptr(out)))
         return out
 
+    def corrfunc_pieces(self, z_mean, mu, sep, begin=0, end=None):
+        """[3 pieces, end - begin] of the flattened output entries (iz*n_mu + imu)*n_sep + ir in [begin, end)"""
+        z, m, s = capi.darr(z_mean), capi.darr(mu), capi.darr(sep)
+        if end is None:
+            end = len(z) * len(m) * len(s)
+        out = np.empty((3, max(end - begin, 0)))
+        self._check(self.lib.coffe_b200_corrfunc_range_pieces(self._h, capi.ptr(z), C.c_int(len(z)), capi.ptr(m), C.c_int(len(m)),
+                                                              capi.ptr(s), C.c_int(len(s)), C.c_long(begin), C.c_long(end), capi.ptr(out)))
+        return out
+
+    def average_multipoles_pieces(self, z_min, z_max, sep, l, begin=0, end=None):
+        """[3 pieces, n_l, end - begin] of the flattened (ibin*n_sep + ir) groups in [begin, end)"""
+        a, b, s, ls = capi.darr(z_min), capi.darr(z_max), capi.darr(sep), capi.iarr(l)
+        if end is None:
+            end = len(a) * len(s)
+        out = np.empty((3, len(ls), max(end - begin, 0)))
+        self._check(self.lib.coffe_b200_average_multipoles_range_pieces(self._h, capi.ptr(a), capi.ptr(b), C.c_int(len(a)), capi.ptr(s), C.c_int(len(s)),
+                                                                        capi.iptr(ls), C.c_int(len(ls)), C.c_long(begin), C.c_long(end), capi.ptr(out)))
+        return out
+
+    def multipoles_cost(self, z_mean, sep, l):
+        """[n_z, n_sep] estimated cost (integrand evaluations) of every item, counted on the device"""
+        z, s, ls = capi.darr(z_mean), capi.darr(sep), capi.iarr(l)
+        out = np.empty((len(z), len(s)))
+        self._check(self.lib.coffe_b200_multipoles_cost(self._h, capi.ptr(z), C.c_int(len(z)), capi.ptr(s), C.c_int(len(s)),
+                                                        capi.iptr(ls), C.c_int(len(ls)), capi.ptr(out)))
+        return out
+
+    # ---- one process per GPU: NCCL inside the library ------------------------------------------------------
+    def comm_init(self, rank, world, unique_id):
+        buf = (C.c_ubyte * 128).from_buffer_copy(bytes(unique_id))
+        self._check(self.lib.coffe_b200_comm_init(self._h, C.c_int(rank), C.c_int(world), buf))
+        self.rank, self.world = rank, world
+
+    def comm_destroy(self):
+        self.lib.coffe_b200_comm_destroy(self._h)
+
+    def multipoles_sharded(self, z_mean, sep, l, bounds=None, want_result=True):
+        """every rank computes its block, the blocks are gathered device to device (NCCL) and copied to the host of the ranks that
+        ask for it.  Returns ([n_z, n_l, n_sep] or None, kernel ms, gather ms)"""
+        z, s, ls = capi.darr(z_mean), capi.darr(sep), capi.iarr(l)
+        out = np.empty((len(z), len(ls), len(s))) if want_result else None
+        bd = (C.c_long * len(bounds))(*bounds) if bounds is not None else None
+        kms, gms = C.c_double(), C.c_double()
+        self._check(self.lib.coffe_b200_multipoles_sharded(self._h, capi.ptr(z), C.c_int(len(z)), capi.ptr(s), C.c_int(len(s)), capi.iptr(ls), C.c_int(len(ls)),
+                                                           bd, capi.ptr(out) if want_result else None, C.byref(kms), C.byref(gms)))
+        return out, kms.value, gms.value
+
     def average_multipoles(self, z_min, z_max, sep, l):
         a, b, s, ls = capi.darr(z_min), capi.darr(z_max), capi.darr(sep), capi.iarr(l)
         assert len(a) == len(b)
@@ -120,10 +168,9 @@ class Engine:
                                                            capi.iptr(ls), C.c_int(len(ls)), capi.ptr(out)))
         return out
 
-    def covariance(self, pk, sep, l, fsky, density1, density2, pixelsize, z_mean=None, deltaz=None, z_min=None, z_max=None,
-                   pops=(1, 1, 1, 1), cosmic=True, mixed=True, poisson=True, window=False, k_min=None, k_max=None,
-                   method="standard", bins=8000):
-        """[n_bins, n_l, n_sep, n_l, n_sep]; pk = (k, P) knots of the power-spectrum spline"""
+    def _covariance_params(self, pk, sep, l, fsky, density1, density2, pixelsize, z_mean=None, deltaz=None, z_min=None, z_max=None,
+                           pops=(1, 1, 1, 1), cosmic=True, mixed=True, poisson=True, window=False, k_min=None, k_max=None,
+                           method="standard", bins=8000):
         average = z_mean is None
         k, p = capi.darr(pk[0]), capi.darr(pk[1])
         s, ls = capi.darr(sep), capi.iarr(l)
@@ -148,8 +195,19 @@ class Engine:
         cp.pop = (C.c_int * 4)(*pops)
         cp.cosmic, cp.mixed, cp.poisson, cp.window, cp.average = int(cosmic), int(mixed), int(poisson), int(window), int(average)
         cp.integration_method, cp.integration_bins = {"standard": 1, "fftlog": 2}[method], int(bins)
-        out = np.empty((n_bins, len(ls), len(s), len(ls), len(s)))
-        self._check(self.lib.coffe_b200_covariance(self._h, C.byref(cp), capi.ptr(out)))
+        self._cov_keep = (k, p, s, ls, keep, arrs)
+        return cp, (n_bins, len(ls), len(s), len(ls), len(s))
+
+    def covariance(self, *args, rows=None, **kw):
+        """[n_bins, n_l, n_sep, n_l, n_sep]; pk = (k, P) knots of the power-spectrum spline.  rows = (begin, end): only the rows
+        il1*n_sep + ir1 in that range of every bin are computed (the rest of the array stays NaN): the unit of multi-GPU sharding"""
+        cp, shape = self._covariance_params(*args, **kw)
+        if rows is None:
+            out = np.empty(shape)
+            self._check(self.lib.coffe_b200_covariance(self._h, C.byref(cp), capi.ptr(out)))
+        else:
+            out = np.full(shape, np.nan)
+            self._check(self.lib.coffe_b200_covariance_rows(self._h, C.byref(cp), C.c_int(rows[0]), C.c_int(rows[1]), capi.ptr(out)))
         return out
 
     # ---- I^n_l tables ---------------------------------------------------------------------------------
@@ -210,6 +268,19 @@ class Plan:
         self.engine._check(self.engine.lib.coffe_b200_plan_fetch(self._p, capi.ptr(out)))
         return out
 
+    def execute_gather(self, bounds):
+        """kernels of this rank's block + the NCCL gather of all blocks, both on the compute stream: (kernel ms, gather ms)"""
+        bd = (C.c_long * len(bounds))(*bounds)
+        self._n_total = int(bounds[-1])
+        kms, gms = C.c_double(), C.c_double()
+        self.engine._check(self.engine.lib.coffe_b200_plan_execute_gather(self._p, bd, C.c_long(self._n_total), C.byref(kms), C.byref(gms)))
+        return kms.value, gms.value
+
+    def fetch_gathered(self):
+        out = np.empty((self.n_l, self._n_total))
+        self.engine._check(self.engine.lib.coffe_b200_plan_fetch_gathered(self._p, capi.ptr(out)))
+        return out
+
     def count(self):
         """(work items, NI evaluations, SI evaluations, DI evaluations)"""
         v = [C.c_double() for _ in range(4)]
@@ -226,3 +297,100 @@ class Plan:
             self.close()
         except Exception:
             pass
+
+
+def comm_unique_id():
+    """128 opaque bytes from rank 0 (ncclGetUniqueId); hand them to every rank's Engine.comm_init"""
+    lib = capi.load()
+    buf = (C.c_ubyte * 128)()
+    rc = lib.coffe_b200_comm_unique_id(buf)
+    if rc:
+        raise CoffeB200Error(rc, lib.coffe_b200_last_error(None).decode())
+    return bytes(buf)
+
+
+def balance_bounds(cost, n_parts):
+    """n_parts + 1 boundaries of contiguous blocks of (nearly) equal total cost (host arithmetic of the library, no GPU needed)"""
+    lib = capi.load()
+    c = capi.darr(np.asarray(cost).ravel())
+    out = (C.c_long * (n_parts + 1))()
+    rc = lib.coffe_b200_balance_bounds(capi.ptr(c), C.c_long(c.size), C.c_int(n_parts), out)
+    if rc:
+        raise ValueError("cost must be finite, non-negative and not all zero; n_parts >= 1")
+    return [int(v) for v in out]
+
+
+class Group:
+    """All GPUs of the box behind one call (coffe_b200_group_*): the counterpart of the reference's OpenMP loop over the output grid."""
+
+    def __init__(self, n_devices=-1):
+        self.lib = capi.load()
+        self.lib.coffe_b200_group_last_error.restype = C.c_char_p
+        self.lib.coffe_b200_group_last_error.argtypes = [C.c_void_p]
+        h = C.c_void_p()
+        rc = self.lib.coffe_b200_group_create(C.c_int(n_devices), C.byref(h))
+        if rc:
+            raise CoffeB200Error(rc, self.lib.coffe_b200_group_last_error(None).decode())
+        self._h = h
+        self.size = self.lib.coffe_b200_group_size(h)
+        self._tables = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.coffe_b200_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise CoffeB200Error(rc, self.lib.coffe_b200_group_last_error(self._h).decode())
+
+    def upload_tables(self, tableset):
+        self._tables = tableset
+        self._check(self.lib.coffe_b200_group_upload_tables(self._h, C.byref(tableset.struct)))
+
+    def set_options(self, contributions, **flags):
+        o = capi.make_options(contributions, **flags)
+        self._check(self.lib.coffe_b200_group_set_options(self._h, C.byref(o)))
+
+    def set_quadrature(self, **kw):
+        q = capi.make_quadrature(**kw)
+        self._check(self.lib.coffe_b200_group_set_quadrature(self._h, C.byref(q)))
+
+    def multipoles(self, z_mean, sep, l):
+        z, s, ls = capi.darr(z_mean), capi.darr(sep), capi.iarr(l)
+        out = np.empty((len(z), len(ls), len(s)))
+        self._check(self.lib.coffe_b200_group_multipoles(self._h, capi.ptr(z), C.c_int(len(z)), capi.ptr(s), C.c_int(len(s)),
+                                                         capi.iptr(ls), C.c_int(len(ls)), capi.ptr(out)))
+        return out
+
+    def corrfunc(self, z_mean, mu, sep):
+        z, m, s = capi.darr(z_mean), capi.darr(mu), capi.darr(sep)
+        out = np.empty((len(z), len(m), len(s)))
+        self._check(self.lib.coffe_b200_group_corrfunc(self._h, capi.ptr(z), C.c_int(len(z)), capi.ptr(m), C.c_int(len(m)),
+                                                       capi.ptr(s), C.c_int(len(s)), capi.ptr(out)))
+        return out
+
+    def average_multipoles(self, z_min, z_max, sep, l):
+        a, b, s, ls = capi.darr(z_min), capi.darr(z_max), capi.darr(sep), capi.iarr(l)
+        out = np.empty((len(a), len(ls), len(s)))
+        self._check(self.lib.coffe_b200_group_average_multipoles(self._h, capi.ptr(a), capi.ptr(b), C.c_int(len(a)), capi.ptr(s), C.c_int(len(s)),
+                                                                 capi.iptr(ls), C.c_int(len(ls)), capi.ptr(out)))
+        return out
+
+    def covariance(self, *args, **kw):
+        cp, shape = Engine._covariance_params(self, *args, **kw)
+        out = np.empty(shape)
+        self._check(self.lib.coffe_b200_group_covariance(self._h, C.byref(cp), capi.ptr(out)))
+        return out
+
+    def last_blocks(self):
+        """(block boundaries of the last call, device time of every member [ms])"""
+        bd, ms = (C.c_long * (self.size + 1))(), (C.c_double * self.size)()
+        self._check(self.lib.coffe_b200_group_last_blocks(self._h, bd, ms))
+        return [int(v) for v in bd], [float(v) for v in ms]

@@ -1,12 +1,21 @@
-"""Multi-GPU sharding of the output grid.
+"""Multi-GPU sharding of the output grid: host logic only.
 
 Every (z_mean, separation) work item is independent given the tables -- the reference itself runs a flat
 `omp parallel for` over them (src/multipoles.c:88-125) -- so the flattened items iz*n_sep + ir are cut into
-contiguous blocks, one per rank, the tables are replicated, and the only communication is one gather of the
-FP64 result slices.  This module holds that host logic; it works with any torch.distributed backend (NCCL
-on the GPUs, gloo in the CPU tests) and does no arithmetic on the results.
+contiguous blocks of equal estimated cost, one per GPU, with the tables replicated.  Two ways to drive the GPUs:
+
+  * one process, all devices: `coffe_b200.Group` (coffe_b200_group_* in the library: one host thread per device, every block
+    copied device -> host straight into the caller's array; no collective);
+  * one process per GPU (torchrun / mpirun): `multipoles_sharded` below -- each rank computes its block and the blocks are
+    gathered device to device by the library's own NCCL calls (`NcclComm`).
+
+The arithmetic of the block boundaries lives in the library (coffe_b200_balance_bounds, coffe_b200_multipoles_cost); this
+module only arranges arrays.  The collective is reached through a small communicator protocol (`rank`, `world`,
+`allgather_blocks`) so that the CPU tests can drive the same code over a gloo process group they set up themselves.
 """
 import numpy as np
+
+from . import engine as _engine
 
 
 def block_partition(n_items, world, rank):
@@ -25,71 +34,19 @@ def weighted_bounds(weights, world):
     """world + 1 boundaries of contiguous blocks of the flattened items with (nearly) equal total weight: the cost of a
     (z, r) item grows with the separation (more mu and outer nodes) and with the distance (more tail panels), so equal
     item counts leave the ranks that hold the high-redshift rows with ~10 % more work.  Deterministic: every rank
-    computes the same boundaries from the same weights."""
+    computes the same boundaries from the same weights (coffe_b200_balance_bounds, host arithmetic of the library)."""
     w = np.asarray(weights, dtype=np.float64).ravel()
     if world < 1:
         raise ValueError("need world >= 1")
     if w.size == 0:
         return [0] * (world + 1)
-    if np.any(w < 0) or not np.all(np.isfinite(w)) or w.sum() <= 0:
-        raise ValueError("weights must be finite, non-negative and not all zero")
-    c = np.concatenate([[0.0], np.cumsum(w)])
-    targets = c[-1] * np.arange(1, world) / world
-    cuts = np.searchsorted(c, targets, side="left")
-    # the boundary closest to the target of the two neighbours
-    cuts = np.array([k if k == 0 or abs(c[k] - t) <= abs(c[k - 1] - t) else k - 1 for k, t in zip(cuts, targets)], dtype=int)
-    bounds = np.concatenate([[0], np.clip(cuts, 0, w.size), [w.size]])
-    return [int(b) for b in np.maximum.accumulate(bounds)]
+    return _engine.balance_bounds(w, world)
 
 
-def gather_ranges(local, n_items, dist, device="cpu", dst=0, bounds=None):
-    """Gather the per-rank result slices of coffe_b200_multipoles_range.
-
-    local : [n_l, end - begin] array of this rank (layout of coffe_b200_multipoles_range)
-    bounds: world + 1 block boundaries (weighted_bounds); default: equal blocks (block_partition)
-    Returns [n_l, n_items] on rank `dst`, None elsewhere.  One collective, padded to the largest block.
-    """
-    import torch
-    world, rank = dist.get_world_size(), dist.get_rank()
-    if bounds is None:
-        bounds = [block_partition(n_items, world, r)[0] for r in range(world)] + [n_items]
-    if len(bounds) != world + 1 or bounds[0] != 0 or bounds[-1] != n_items:
-        raise ValueError("bounds must run from 0 to n_items in world + 1 steps")
-    per = max(max(bounds[r + 1] - bounds[r] for r in range(world)), 1)
-    local = np.ascontiguousarray(local, dtype=np.float64)
-    n_l = local.shape[0]
-    begin, end = bounds[rank], bounds[rank + 1]
-    if local.shape != (n_l, end - begin):
-        raise ValueError(f"rank {rank}: expected a slice of shape {(n_l, end - begin)}, got {local.shape}")
-    pad = torch.zeros((n_l, per), dtype=torch.float64, device=device)
-    if end > begin:
-        pad[:, :end - begin] = torch.from_numpy(local).to(device)
-    parts = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
-    dist.gather(pad, parts, dst=dst)
-    if rank != dst:
-        return None
-    out = [parts[r][:, :bounds[r + 1] - bounds[r]] for r in range(world)]
-    return torch.cat(out, dim=1).cpu().numpy()
-
-
-def separable_cost(engine, z_mean, sep, l, n_z_samples=5, n_sep_samples=16):
-    """Estimated relative cost of every (z, r) item, [n_z, n_sep]: integrand evaluations counted by the library itself
-    (coffe_b200_plan_count) on a few rows and columns of the grid, combined as f(z) g(r).  Costs a few ms of GPU time."""
-    z, s = np.asarray(z_mean, float), np.asarray(sep, float)
-
-    def cost(zs, ss):
-        plan = engine.plan_multipoles(zs, ss, l)
-        _, _, n_si, n_di = plan.count()
-        plan.close()
-        return n_di + 2.0 * n_si          # a local x integrated evaluation costs about two integrated x integrated ones
-
-    iz = np.unique(np.linspace(0, len(z) - 1, min(n_z_samples, len(z))).round().astype(int))
-    js = np.unique(np.linspace(0, len(s) - 1, min(n_sep_samples, len(s))).round().astype(int))
-    f = np.array([cost(z[i:i + 1], s[js]) for i in iz])
-    g = np.array([cost(z[iz[len(iz) // 2]:iz[len(iz) // 2] + 1], s[j:j + 1]) for j in js])
-    fz = np.interp(z, z[iz], f) if len(iz) > 1 else np.full(len(z), f[0])
-    gs = np.interp(s, s[js], g) if len(js) > 1 else np.full(len(s), g[0])
-    return np.outer(fz, gs)
+def item_cost(engine, z_mean, sep, l):
+    """[n_z, n_sep] estimated cost of every (z, r) item: integrand evaluations counted by the library on the device
+    (coffe_b200_multipoles_cost: exact on a few rows of the grid, every separation; linear in z between them)"""
+    return engine.multipoles_cost(z_mean, sep, l)
 
 
 def ranges_to_grid(flat, n_z, n_sep):
@@ -100,21 +57,34 @@ def ranges_to_grid(flat, n_z, n_sep):
     return np.ascontiguousarray(flat.reshape(n_l, n_z, n_sep).transpose(1, 0, 2))
 
 
-def multipoles_sharded(engine, z_mean, sep, l, dist=None, device=None, balanced=False):
-    """Sharded equivalent of Engine.multipoles: every rank computes its block on its own GPU, rank 0 returns
-    the full [n_z, n_l, n_sep] array (None on the other ranks).  Without a process group: single GPU."""
+class NcclComm:
+    """The library's own communicator (coffe_b200_comm_init): the gather runs device to device inside
+    coffe_b200_multipoles_sharded, so `multipoles_sharded` hands the whole call to the engine."""
+
+    def __init__(self, engine, rank, world, unique_id):
+        engine.comm_init(rank, world, unique_id)
+        self.engine, self.rank, self.world = engine, rank, world
+        self.device_gather = True
+
+
+def multipoles_sharded(engine, z_mean, sep, l, comm=None, bounds=None, balanced=True):
+    """Sharded equivalent of Engine.multipoles, one process per GPU: returns the full [n_z, n_l, n_sep] array on every rank.
+    comm: None (single process) | NcclComm | any object with `rank`, `world` and
+    `allgather_blocks(local [n_l, n_local], bounds) -> [n_l, n_items]` (the CPU tests pass a gloo-backed one)."""
     n_z, n_sep = len(z_mean), len(sep)
     n_items = n_z * n_sep
-    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+    if comm is None or comm.world == 1:
         return ranges_to_grid(engine.multipoles_range(z_mean, sep, l, 0, n_items), n_z, n_sep)
-    bounds = None
-    if balanced:
-        bounds = weighted_bounds(separable_cost(engine, z_mean, sep, l), dist.get_world_size())
-        begin, end = bounds[dist.get_rank()], bounds[dist.get_rank() + 1]
-    else:
-        begin, end = block_partition(n_items, dist.get_world_size(), dist.get_rank())
-    local = engine.multipoles_range(z_mean, sep, l, begin, end)
-    if device is None:
-        device = f"cuda:{engine.device}" if dist.get_backend() == "nccl" else "cpu"
-    flat = gather_ranges(local, n_items, dist, device=device, bounds=bounds)
-    return None if flat is None else ranges_to_grid(flat, n_z, n_sep)
+    if bounds is None:
+        if balanced:
+            bounds = weighted_bounds(item_cost(engine, z_mean, sep, l), comm.world)
+        else:
+            bounds = [block_partition(n_items, comm.world, r)[0] for r in range(comm.world)] + [n_items]
+    if len(bounds) != comm.world + 1 or bounds[0] != 0 or bounds[-1] != n_items:
+        raise ValueError("bounds must run from 0 to n_items in world + 1 steps")
+    if getattr(comm, "device_gather", False):
+        out, _, _ = engine.multipoles_sharded(z_mean, sep, l, bounds=bounds)
+        return out
+    local = engine.multipoles_range(z_mean, sep, l, bounds[comm.rank], bounds[comm.rank + 1])
+    flat = comm.allgather_blocks(np.ascontiguousarray(local, dtype=np.float64), bounds)
+    return ranges_to_grid(flat, n_z, n_sep)

@@ -13,7 +13,9 @@
  *   coffe_b200_multipoles         coffe_multipoles_init            src/multipoles.h:47, src/multipoles.c:50-133
  *   coffe_b200_corrfunc           coffe_corrfunc_init              src/corrfunc.h:36,   src/corrfunc.c:56-139
  *   coffe_b200_average_multipoles coffe_average_multipoles_init    src/average_multipoles.h:36, src/average_multipoles.c:72-156
- *   coffe_b200_signal_pieces      coffe_integrate (per piece)      src/signal.h:17-29, src/signal.c:472-771
+ *   coffe_b200_multipoles_pieces, coffe_b200_corrfunc_range_pieces, coffe_b200_average_multipoles_range_pieces
+ *                                 coffe_integrate (per piece)      src/signal.h:17-29, src/signal.c:472-771
+ *   coffe_b200_group_*            the `omp parallel for num_threads(par->nthreads)` of the drivers: one call -> all devices
  *   coffe_b200_covariance         coffe_covariance_init            src/covariance.h:48, src/covariance.c:477-1103
  *   coffe_b200_integrals          coffe_integrals_init             src/integrals.h:84, src/integrals.c:580-1423
  * Output buffers are caller-owned, dense, and in the reference's own loop order so that a patched
@@ -147,6 +149,16 @@ int coffe_b200_corrfunc(coffe_b200_ctx *ctx, const double *z_mean, int n_z, cons
 int coffe_b200_average_multipoles(coffe_b200_ctx *ctx, const double *z_min, const double *z_max, int n_bins,
                                   const double *sep, int n_sep, const int *l, int n_l, double *out);
 
+/* Range and piece variants of the two calls above (same role as coffe_b200_multipoles_range / _pieces): the unit of multi-GPU
+   sharding and what a single-point coffe_integrate(flag_integral, flag_output) maps to (src/signal.c:472-771).
+   corrfunc: flattened output entries (iz*n_mu + imu)*n_sep + ir in [begin, end); out has 3*(end-begin) entries,
+             out[piece*(end-begin) + k], pieces NONINTEGRATED / SINGLE_INTEGRATED / DOUBLE_INTEGRATED.
+   average multipoles: flattened (ibin*n_sep + ir) groups in [begin, end); out[(piece*n_l + il)*(end-begin) + k]. */
+int coffe_b200_corrfunc_range_pieces(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double *mu, int n_mu,
+                                     const double *sep, int n_sep, long begin, long end, double *out);
+int coffe_b200_average_multipoles_range_pieces(coffe_b200_ctx *ctx, const double *z_min, const double *z_max, int n_bins,
+                                               const double *sep, int n_sep, const int *l, int n_l, long begin, long end, double *out);
+
 /* ---- covariance ----------------------------------------------------------------------------------- */
 /* the members of coffe_parameters_t that coffe_covariance_init reads (src/covariance.c:477-1103) */
 typedef struct coffe_b200_covariance_params {
@@ -174,6 +186,11 @@ typedef struct coffe_b200_covariance_params {
    density / rsd switches come from coffe_b200_set_options, background and galaxy_bias1..4 from the uploaded
    tables */
 int coffe_b200_covariance(coffe_b200_ctx *ctx, const coffe_b200_covariance_params *p, double *out);
+
+/* rows [row_begin, row_end) of every bin's matrix, row = il1*n_sep + ir1 (the unit of multi-GPU sharding of the covariance,
+   src/covariance.c:653, 680 loop over the same rows): only out[((ibin*n_rows + row)*n_l + il2)*n_sep + ir2] of those rows is
+   written, `out` is the full-size buffer of coffe_b200_covariance (standard integration method only) */
+int coffe_b200_covariance_rows(coffe_b200_ctx *ctx, const coffe_b200_covariance_params *p, int row_begin, int row_end, double *out);
 
 /* ---- I^n_l tables ----------------------------------------------------------------------------------
    What coffe_integrals_init builds (src/integrals.c:580-1423): for every requested (n, l) the table of
@@ -230,6 +247,55 @@ int coffe_b200_plan_execute(coffe_b200_plan *plan, double *kernel_ms);
 int coffe_b200_plan_fetch(coffe_b200_plan *plan, double *out);
 int coffe_b200_plan_count(coffe_b200_plan *plan, double *n_items, double *n_ni_evals, double *n_si_evals, double *n_di_evals);
 void coffe_b200_plan_destroy(coffe_b200_plan *plan);
+
+/* ---- multi-GPU -------------------------------------------------------------------------------------
+   The reference's drivers use every host core from ONE call (omp parallel for num_threads(par->nthreads), src/multipoles.c:88,
+   par->nthreads = omp_get_max_threads(), src/parser.c:737-741).  A group does the same with the GPUs of the box: one host call
+   cuts the output grid into contiguous cost-balanced blocks (integrand evaluations counted per item by the library), drives every
+   device from its own host thread and stream with the tables replicated, and each block lands by D2H straight in the caller's
+   buffer.  No data-path collective; results are bit-identical to the single-device calls whatever the device count. */
+typedef struct coffe_b200_group coffe_b200_group;
+int coffe_b200_group_create(int n_devices /* -1: every visible device */, coffe_b200_group **out);
+void coffe_b200_group_destroy(coffe_b200_group *g);
+int coffe_b200_group_size(const coffe_b200_group *g);
+coffe_b200_ctx *coffe_b200_group_member(coffe_b200_group *g, int i);      /* the i-th device's context (owned by the group) */
+const char *coffe_b200_group_last_error(const coffe_b200_group *g);
+int coffe_b200_group_upload_tables(coffe_b200_group *g, const coffe_b200_tables *tables);
+int coffe_b200_group_set_options(coffe_b200_group *g, const coffe_b200_options *opt);
+int coffe_b200_group_set_quadrature(coffe_b200_group *g, const coffe_b200_quadrature *q);
+/* same arguments and output order as the single-device calls */
+int coffe_b200_group_multipoles(coffe_b200_group *g, const double *z_mean, int n_z, const double *sep, int n_sep,
+                                const int *l, int n_l, double *out);
+int coffe_b200_group_corrfunc(coffe_b200_group *g, const double *z_mean, int n_z, const double *mu, int n_mu,
+                              const double *sep, int n_sep, double *out);
+int coffe_b200_group_average_multipoles(coffe_b200_group *g, const double *z_min, const double *z_max, int n_bins,
+                                        const double *sep, int n_sep, const int *l, int n_l, double *out);
+int coffe_b200_group_covariance(coffe_b200_group *g, const coffe_b200_covariance_params *p, double *out);
+/* the block boundaries the last group call used (n_parts + 1 entries) and the device time of each member [ms] */
+int coffe_b200_group_last_blocks(const coffe_b200_group *g, long *bounds, double *member_ms);
+
+/* Estimated cost (integrand evaluations: integrated x integrated + 2 x local x integrated) of every (iz, ir) item of a multipole grid,
+   cost[iz*n_sep + ir], counted by the library on the device, and the boundaries of n_parts contiguous blocks of (nearly) equal
+   cost (n_parts + 1 entries, deterministic: every process derives the same ones).  coffe_b200_balance_bounds is host arithmetic. */
+int coffe_b200_multipoles_cost(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double *sep, int n_sep,
+                               const int *l, int n_l, double *cost);
+int coffe_b200_balance_bounds(const double *cost, long n_items, int n_parts, long *bounds);
+
+/* One process per GPU (the launch torchrun / mpirun give): every rank computes its block, and the blocks are gathered device to
+   device with NCCL (libnccl.so.2 is loaded on first use; grouped ncclBroadcast of the variable-size blocks, issued on the compute
+   stream right behind the kernels), then copied to the host buffer of every rank that passes one.  The unique id comes from
+   rank 0 (coffe_b200_comm_unique_id) and travels to the other ranks by whatever the launcher offers (MPI_Bcast, a file, a
+   torch.distributed broadcast): 128 bytes. */
+int coffe_b200_comm_unique_id(unsigned char id[128]);
+int coffe_b200_comm_init(coffe_b200_ctx *ctx, int rank, int world, const unsigned char id[128]);
+void coffe_b200_comm_destroy(coffe_b200_ctx *ctx);
+/* bounds: world + 1 item boundaries (NULL: cost-balanced, computed identically on every rank); out: full grid in the order of
+   coffe_b200_multipoles, or NULL on ranks that do not need the result; gather_ms: device time of the collective alone */
+int coffe_b200_multipoles_sharded(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double *sep, int n_sep,
+                                  const int *l, int n_l, const long *bounds, double *out, double *kernel_ms, double *gather_ms);
+/* prepared variant (inputs resident in HBM): execute launches this rank's kernels and the gather, returns their device times */
+int coffe_b200_plan_execute_gather(coffe_b200_plan *plan, const long *bounds, long n_items_total, double *kernel_ms, double *gather_ms);
+int coffe_b200_plan_fetch_gathered(coffe_b200_plan *plan, double *out /* [n_l][n_items_total], layout of coffe_b200_multipoles_range */);
 
 /* measured FP64 FMA throughput of the device [TFLOP/s] (dependent-chain-free DFMA probe kernel) */
 int coffe_b200_fp64_peak(coffe_b200_ctx *ctx, double *tflops);

@@ -36,16 +36,19 @@ def available(fast=False):
     return (HERE / "_ref" / ("libcoffe_ref_fast.so" if fast else "libcoffe_ref.so")).exists()
 
 
-def load(fast=False):
-    name = "libcoffe_ref_fast.so" if fast else "libcoffe_ref.so"
+def load(fast=False, path=None):
+    """path: another build of oracle/ref_driver.c with the same entry points -- the drop-in harness
+    (dropin/_build/libcoffe_dropin_harness.so: the same driver over COFFE's symbols as exported by the drop-in library)"""
+    name = str(path) if path else ("libcoffe_ref_fast.so" if fast else "libcoffe_ref.so")
     if name in _LIBS:
         return _LIBS[name]
     os.environ.setdefault("CUBACORES", "0")  # coffe.pyx:507
-    lib = C.CDLL(str(HERE / "_ref" / name))
+    lib = C.CDLL(name if path else str(HERE / "_ref" / name))
     lib.ref_new.restype = C.c_void_p
     for f in ("ref_background_eval", "ref_integral_eval", "ref_renorm_eval", "ref_integrate",
               "ref_f_nonintegrated", "ref_f_single", "ref_f_double", "ref_cuhre_direct"):
-        getattr(lib, f).restype = C.c_double
+        if hasattr(lib, f):
+            getattr(lib, f).restype = C.c_double
     _LIBS[name] = lib
     return lib
 
@@ -66,8 +69,8 @@ def composite_gl_01(panels, n):
 class RefCoffe:
     """Thin mirror of the subset of `coffe.Coffe` (python/coffe/coffe.pyx) the parity tests need."""
 
-    def __init__(self, fast=False, **kw):
-        self.lib = load(fast)
+    def __init__(self, fast=False, lib_path=None, **kw):
+        self.lib = load(fast, lib_path)
         self.h_ = C.c_void_p(self.lib.ref_new())
         self._n = {"sep": 100, "mu": 1, "z_mean": 1, "l": 3, "z_min": 1}
         for k, v in kw.items():

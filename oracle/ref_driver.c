@@ -28,7 +28,9 @@
 #include "parser.h"
 #include "background.h"
 #include "integrals.h"
+#ifndef COFFE_DROPIN_BUILD
 #include "functions.h"
+#endif
 #include "signal.h"
 #include "corrfunc.h"
 #include "multipoles.h"
@@ -395,6 +397,7 @@ double ref_integrate(void *h, double z_mean, double z_min, double z_max, double 
                            (enum coffe_integral_type)flag_integral, (enum coffe_output_type)flag_output);
 }
 
+#ifndef COFFE_DROPIN_BUILD   /* everything below needs the reference's own integrands / Cuhre; the drop-in harness stops here */
 /* raw integrands, for kernel-level parity of the physics (src/functions.c:89,1486,3460) */
 double ref_f_nonintegrated(void *h, double z, double mu, double sep)
 { ref_state *s = h; ref_integrals(h); return functions_nonintegrated(&s->par, &s->bg, &s->integral, z, mu, sep); }
@@ -540,3 +543,4 @@ double ref_cuhre_direct(void *h, int which, double z, double sep, double mu, int
     if (fail_out) *fail_out = fail;
     return pre * result[0];
 }
+#endif /* COFFE_DROPIN_BUILD */

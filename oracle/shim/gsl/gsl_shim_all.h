@@ -204,6 +204,31 @@ void gsl_odeiv2_evolve_free(gsl_odeiv2_evolve *e);
 int gsl_odeiv2_evolve_apply(gsl_odeiv2_evolve *e, gsl_odeiv2_control *con, gsl_odeiv2_step *step,
                             const gsl_odeiv2_system *dydt, double *t, double t1, double *h, double y[]);
 
+/* ---- Monte-Carlo integration: declarations only, so that src/common.c compiles WITHOUT -DHAVE_CUBA (the drop-in build of
+   dropin/Makefile keeps coffe_integrate_multidimensional out of every call path; the stubs in gsl_shim.c abort if reached) ---- */
+typedef struct gsl_monte_function { double (*f)(double *x, size_t dim, void *params); size_t dim; void *params; } gsl_monte_function;
+typedef struct gsl_rng_type { const char *name; } gsl_rng_type;
+typedef struct gsl_rng { const gsl_rng_type *type; } gsl_rng;
+extern const gsl_rng_type *gsl_rng_default;
+const gsl_rng_type *gsl_rng_env_setup(void);
+gsl_rng *gsl_rng_alloc(const gsl_rng_type *T);
+void gsl_rng_free(gsl_rng *r);
+typedef struct gsl_monte_plain_state { size_t dim; } gsl_monte_plain_state;
+typedef struct gsl_monte_miser_state { size_t dim; } gsl_monte_miser_state;
+typedef struct gsl_monte_vegas_state { size_t dim; } gsl_monte_vegas_state;
+gsl_monte_plain_state *gsl_monte_plain_alloc(size_t dim);
+gsl_monte_miser_state *gsl_monte_miser_alloc(size_t dim);
+gsl_monte_vegas_state *gsl_monte_vegas_alloc(size_t dim);
+void gsl_monte_plain_free(gsl_monte_plain_state *s);
+void gsl_monte_miser_free(gsl_monte_miser_state *s);
+void gsl_monte_vegas_free(gsl_monte_vegas_state *s);
+int gsl_monte_plain_integrate(const gsl_monte_function *f, const double xl[], const double xu[], size_t dim, size_t calls, gsl_rng *r,
+                              gsl_monte_plain_state *state, double *result, double *abserr);
+int gsl_monte_miser_integrate(gsl_monte_function *f, const double xl[], const double xu[], size_t dim, size_t calls, gsl_rng *r,
+                              gsl_monte_miser_state *state, double *result, double *abserr);
+int gsl_monte_vegas_integrate(gsl_monte_function *f, double xl[], double xu[], size_t dim, size_t calls, gsl_rng *r,
+                              gsl_monte_vegas_state *state, double *result, double *abserr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -903,3 +903,31 @@ int gsl_odeiv2_evolve_apply(gsl_odeiv2_evolve *e, gsl_odeiv2_control *con, gsl_o
     if (final_step == 0) *h = h0;
     return step_status;
 }
+
+
+/* ---- Monte-Carlo stubs (see gsl_shim_all.h): never on a call path of the oracle (it builds with -DHAVE_CUBA) or of the drop-in */
+static void monte_unavailable(void)
+{
+    fprintf(stderr, "gsl shim: Monte-Carlo integration is not provided (the reference uses it only without CUBA)\n");
+    abort();
+}
+static const gsl_rng_type shim_rng_type = {"shim"};
+const gsl_rng_type *gsl_rng_default = &shim_rng_type;
+const gsl_rng_type *gsl_rng_env_setup(void) { return gsl_rng_default; }
+gsl_rng *gsl_rng_alloc(const gsl_rng_type *T) { gsl_rng *r = (gsl_rng *)malloc(sizeof(gsl_rng)); r->type = T; return r; }
+void gsl_rng_free(gsl_rng *r) { free(r); }
+gsl_monte_plain_state *gsl_monte_plain_alloc(size_t dim) { (void)dim; monte_unavailable(); return NULL; }
+gsl_monte_miser_state *gsl_monte_miser_alloc(size_t dim) { (void)dim; monte_unavailable(); return NULL; }
+gsl_monte_vegas_state *gsl_monte_vegas_alloc(size_t dim) { (void)dim; monte_unavailable(); return NULL; }
+void gsl_monte_plain_free(gsl_monte_plain_state *s) { (void)s; }
+void gsl_monte_miser_free(gsl_monte_miser_state *s) { (void)s; }
+void gsl_monte_vegas_free(gsl_monte_vegas_state *s) { (void)s; }
+int gsl_monte_plain_integrate(const gsl_monte_function *f, const double xl[], const double xu[], size_t dim, size_t calls, gsl_rng *r,
+                              gsl_monte_plain_state *state, double *result, double *abserr)
+{ (void)f; (void)xl; (void)xu; (void)dim; (void)calls; (void)r; (void)state; (void)result; (void)abserr; monte_unavailable(); return 1; }
+int gsl_monte_miser_integrate(gsl_monte_function *f, const double xl[], const double xu[], size_t dim, size_t calls, gsl_rng *r,
+                              gsl_monte_miser_state *state, double *result, double *abserr)
+{ (void)f; (void)xl; (void)xu; (void)dim; (void)calls; (void)r; (void)state; (void)result; (void)abserr; monte_unavailable(); return 1; }
+int gsl_monte_vegas_integrate(gsl_monte_function *f, double xl[], double xu[], size_t dim, size_t calls, gsl_rng *r,
+                              gsl_monte_vegas_state *state, double *result, double *abserr)
+{ (void)f; (void)xl; (void)xu; (void)dim; (void)calls; (void)r; (void)state; (void)result; (void)abserr; monte_unavailable(); return 1; }

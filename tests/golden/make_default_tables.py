@@ -1,4 +1,4 @@
-"""Generate coffe_b200/data/default_tables.npz: the tables the reference builds for its DEFAULT_SETTINGS
+"""Generate tests/golden/default_tables.npz: the tables the reference builds for its DEFAULT_SETTINGS
 cosmology with PkL_CLASS.dat (background splines, the I^n_l family, the divergent I^4_0 extras with the
 renormalisation grid out to chi(z = 2.3)), i.e. exactly what a patched reference driver hands to
 coffe_b200_upload_tables.  bench.py uses them as its synthetic input (the benchmark times signal
@@ -17,7 +17,7 @@ from oracle import coffe_oracle as O  # noqa: E402
 
 ALL = ("den", "rsd", "len", "d1", "d2", "g1", "g2", "g3", "g4", "g5")
 FAMILY = [(0, 0), (0, 2), (0, 4), (1, 1), (1, 3), (2, 0), (2, 2), (3, 1)]
-OUT = ROOT / "coffe_b200" / "data" / "default_tables.npz"
+OUT = ROOT / "tests" / "golden" / "default_tables.npz"
 
 r = O.RefCoffe()
 r.set_power_spectrum(O.load_pk())

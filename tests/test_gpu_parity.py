@@ -748,3 +748,29 @@ def test_renormalisation_range_is_checked_for_potential_terms_alone(ref):
         assert e.value.code == 5
     eng.set_options(["len", "g4"], only_cross=True)          # cross only: no renormalised term left
     assert np.all(np.isfinite(eng.multipoles([1.4], [50.0], [0])))
+
+
+def test_cfg3_average_multipoles_match_converged_oracle_fixture(engine):
+    """Row a9: redshift-averaged multipoles of cfg3 (den + rsd + len, bins of width 0.1875 at both ends of 0.5-2.0, r = 10, 60, 160
+    Mpc/h) against tests/golden/converged_cfg3.npz -- the REFERENCE's integrands averaged over z with the reference's own weight and
+    shrunken limits (src/signal.c:262-283) by a 16-node rule (converged: 16 vs 32 nodes 1e-7), the local x integrated piece by Cuhre
+    called directly (epsrel 2e-7), the integrated x integrated piece by oracle/converged.py.  Each multipole within 1e-5 of the
+    l = 0..4 scale of the (bin, r) point; pieces within 1e-5 of their own scale."""
+    fx = np.load(ROOT / "tests" / "golden" / "converged_cfg3.npz")
+    engine.set_options([str(c) for c in fx["contributions"]])
+    try:
+        got = engine.average_multipoles_pieces(fx["z_min"], fx["z_max"], fx["sep"], fx["l"])       # [3, n_l, n_groups]
+        tot = engine.average_multipoles(fx["z_min"], fx["z_max"], fx["sep"], fx["l"])             # [n_bins, n_l, n_sep]
+    finally:
+        engine.set_options(ALL)
+    want = fx["pieces"]                                             # [bin, sep, piece, l]
+    nb, ns = want.shape[:2]
+    got = got.reshape(3, len(fx["l"]), nb, ns).transpose(2, 3, 0, 1)
+    wt = want.sum(2)
+    scale = np.max(np.abs(wt), axis=2, keepdims=True)
+    err = np.abs(tot.transpose(0, 2, 1) - wt) / scale
+    assert err.max() < 1e-5, err
+    for piece in (0, 1, 2):
+        ps = np.max(np.abs(want[:, :, piece]), axis=2, keepdims=True)
+        assert np.max(np.abs(got[:, :, piece] - want[:, :, piece]) / ps) < 1e-5, (piece, np.abs(got[:, :, piece] - want[:, :, piece]) / ps)
+    assert float(fx["oracle_self_error"].max()) < 1e-6 and float(fx["z_rule_error"]) < 1e-6

@@ -1,7 +1,8 @@
-"""Host logic of the multi-GPU path (coffe_b200/sharding.py) on CPU: block partition of the (z, r) items and the
-single gather of the result slices, world size 2 and 3 over gloo.  The per-rank compute call is replaced by a
-stand-in with the layout of coffe_b200_multipoles_range (the kernels need a GPU; their sharded result is
-compared bit for bit with the unsharded one in tests/test_gpu_parity.py)."""
+"""Host logic of the multi-GPU path (coffe_b200/sharding.py + coffe_b200_balance_bounds in the library) on CPU: block partition of the
+(z, r) items and the gather of the result blocks, world size 2 and 3 over a gloo process group this test sets up (the product package
+itself is torch-free: on the GPUs the gather is the library's own NCCL call).  The per-rank compute call is replaced by a stand-in
+with the layout of coffe_b200_multipoles_range (the kernels need a GPU; their sharded result is compared bit for bit with the
+unsharded one in tests/test_gpu_parity.py and tests/test_multigpu.py)."""
 import os
 import socket
 
@@ -52,7 +53,7 @@ def test_ranges_to_grid_is_the_reference_loop_order():
 
 
 class FakeEngine:
-    """stand-in for coffe_b200.Engine.multipoles_range: value = f(z, r, l), layout [n_l, end - begin]"""
+    """stand-in for coffe_b200.Engine: value = f(z, r, l), layout [n_l, end - begin]; cost model (1 + z)(10 + r)"""
     device = 0
 
     def multipoles_range(self, z, sep, l, begin, end):
@@ -63,22 +64,25 @@ class FakeEngine:
                 out[il, k] = np.sin(z[iz]) * sep[ir] + ll
         return out
 
-
-class CountingPlan:
-    def __init__(self, z, sep):
-        self.z, self.sep = z, sep
-
-    def count(self):
-        c = sum((1.0 + zz) * (10.0 + ss) for zz in self.z for ss in self.sep)
-        return (0.0, 0.0, 0.0, c)
-
-    def close(self):
-        pass
+    def multipoles_cost(self, z, sep, l):
+        return np.outer(1.0 + np.asarray(z), 10.0 + np.asarray(sep))
 
 
-class FakeEngineWithPlans(FakeEngine):
-    def plan_multipoles(self, z, sep, l, begin=0, end=None):
-        return CountingPlan(list(z), list(sep))
+class GlooComm:
+    """the communicator protocol of coffe_b200.sharding over torch.distributed (gloo): variable-size blocks padded to the largest"""
+
+    def __init__(self, dist):
+        self.dist, self.rank, self.world = dist, dist.get_rank(), dist.get_world_size()
+
+    def allgather_blocks(self, local, bounds):
+        import torch
+        n_l = local.shape[0]
+        per = max(max(bounds[r + 1] - bounds[r] for r in range(self.world)), 1)
+        pad = torch.zeros((n_l, per), dtype=torch.float64)
+        pad[:, :local.shape[1]] = torch.from_numpy(local)
+        parts = [torch.empty_like(pad) for _ in range(self.world)]
+        self.dist.all_gather(parts, pad)
+        return torch.cat([parts[r][:, :bounds[r + 1] - bounds[r]] for r in range(self.world)], dim=1).numpy()
 
 
 def _worker(rank, world, port, n_z, n_sep, q):
@@ -88,17 +92,16 @@ def _worker(rank, world, port, n_z, n_sep, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         z, sep, l = np.linspace(0.5, 2.0, n_z), np.linspace(10, 300, n_sep), [0, 2, 4]
-        got = sharding.multipoles_sharded(FakeEngine(), z, sep, l, dist=dist)
-        bal = sharding.multipoles_sharded(FakeEngineWithPlans(), z, sep, l, dist=dist, balanced=True)
-        if rank == 0:
-            assert np.array_equal(bal, got)
-        else:
-            assert bal is None
-        if rank == 0:
-            want = sharding.ranges_to_grid(FakeEngine().multipoles_range(z, sep, l, 0, n_z * n_sep), n_z, n_sep)
-            q.put(bool(np.array_equal(got, want)) and got.shape == (n_z, 3, n_sep))
-        else:
-            q.put(got is None)
+        comm = GlooComm(dist)
+        want = sharding.ranges_to_grid(FakeEngine().multipoles_range(z, sep, l, 0, n_z * n_sep), n_z, n_sep)
+        eq = sharding.multipoles_sharded(FakeEngine(), z, sep, l, comm=comm, balanced=False)
+        bal = sharding.multipoles_sharded(FakeEngine(), z, sep, l, comm=comm, balanced=True)
+        # every rank derives the same cost-balanced boundaries, and they differ from the equal-count ones on this grid
+        bounds = sharding.weighted_bounds(sharding.item_cost(FakeEngine(), z, sep, l), world)
+        allb = [None] * world
+        dist.all_gather_object(allb, bounds)
+        ok = all(b == bounds for b in allb) and np.array_equal(eq, want) and np.array_equal(bal, want) and eq.shape == (n_z, 3, n_sep)
+        q.put(bool(ok))
     finally:
         dist.destroy_process_group()
 
@@ -123,3 +126,12 @@ def test_sharded_gather_equals_unsharded(world, n_z, n_sep):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(results)
+
+
+def test_product_package_is_torch_free():
+    """north_star: "no PyTorch" in the product; torch is plumbing of bench.py and of the tests only"""
+    from pathlib import Path
+    import coffe_b200
+    for f in Path(coffe_b200.__file__).resolve().parent.rglob("*.py"):
+        text = f.read_text()
+        assert "import torch" not in text and "from torch" not in text, f
