@@ -4,16 +4,15 @@ section 8); the tables it returns are what `coffe_b200_upload_tables` takes as `
 
 What is tabulated follows the reference (10 000 uniform knots on z in [0, 15], `background_sampling`):
     a, H(z), conformal H, its conformal-time derivative, D1 (normalised to 1 at z = 0), f, G1, G2, chi(z) [Mpc]
-and the inverse z(chi).  How it is computed does not: w(z) = w0 + wa z/(1+z) is integrated in closed form (the
-reference integrates linear interpolants of it numerically), chi(z) is a cumulative 8-point Gauss-Legendre sum
-(the reference calls QAG per knot at 1e-5), and the growth ODE
+and the inverse z(chi).  w(z) = w0 + wa z/(1+z) is integrated in closed form (the reference integrates linear interpolants of
+it numerically) and chi(z) is a cumulative 8-point Gauss-Legendre sum (the reference calls QAG per knot at 1e-5): both agree
+with the reference's tables to 4e-15.  The growth ODE
 
     D'' = -3/2 (1 - w/(1+x)) D'/a + 3/2 x/(1+x) D/a^2,    x(a) = Omega_m/(1-Omega_m) a^(3(w0+wa)) e^(3 wa (1-a)),
 
-(src/background.c:192-211) is integrated ONCE from a = 0.05, (D, D') = (0.05, 1) with a fixed-step classical
-Runge-Kutta on a fine grid in ln a instead of an adaptive RK2 restarted for every knot (its 1e-6 step control is the
-largest difference between the two: ~1e-6 relative in D1 and f, pinned by tests/test_coffe_class.py against the
-reference's own golden background file and its compiled sources).
+(src/background.c:192-211) is different: the reference's adaptive RK2 at eps_rel = 1e-6, restarted for every knot, leaves a
+scheme-specific 2e-6 in D1 and f, so it is integrated by the same scheme (coffe_b200_background_growth, host code of the library);
+what remains is the reproducibility of that scheme under rounding: 8e-8 in D1, 6e-7 in f (tests/test_coffe_class.py).
 """
 import numpy as np
 
@@ -84,37 +83,18 @@ def compute_background(omega_m, omega_gamma, omega_de, h, w0=-1.0, wa=0.0, n=100
     seg = (0.5 * (zr - zl))[:, None] * gw[None, :] / ee
     chi = np.concatenate([[0.0], np.cumsum(seg.sum(1))]) / (h * COFFE_H0)
 
-    # growth: RK4 in s = ln a from a = 0.05 to a = 1 on a grid fine enough for ~1e-10, sampled at the knots
-    def x_of_a(av):
-        return omega_m / (1.0 - omega_m) * av ** (3.0 * (w0 + wa)) * np.exp(3.0 * wa * (1.0 - av))
-
-    def rhs(s, y):
-        av = np.exp(s)
-        wv = w0 + wa * (1.0 - av)
-        xv = x_of_a(av)
-        # y = (D, dD/da); d/ds = a d/da
-        return np.array([av * y[1], av * (-1.5 * (1 - wv / (1 + xv)) * y[1] / av + 1.5 * xv / (1 + xv) * y[0] / av ** 2)])
-
-    s_knots = np.log(a[::-1])                        # increasing, from ln(1/16) to 0
-    n_sub = 4000
-    s_grid = np.linspace(np.log(0.05), 0.0, n_sub + 1)
-    ys = np.empty((n_sub + 1, 2))
-    ys[0] = (0.05, 1.0)
-    ds = s_grid[1] - s_grid[0]
-    for i in range(n_sub):
-        s0, y0 = s_grid[i], ys[i]
-        k1 = rhs(s0, y0); k2 = rhs(s0 + ds / 2, y0 + ds / 2 * k1); k3 = rhs(s0 + ds / 2, y0 + ds / 2 * k2); k4 = rhs(s0 + ds, y0 + ds * k3)
-        ys[i + 1] = y0 + ds / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
-    # cubic Hermite through the RK4 states (value and derivative known at every grid point)
-    dys = np.array([rhs(s, y) for s, y in zip(s_grid, ys)])
-    idx = np.clip(np.searchsorted(s_grid, s_knots, side="right") - 1, 0, n_sub - 1)
-    u = (s_knots - s_grid[idx]) / ds
-    h00, h10, h01, h11 = 2 * u ** 3 - 3 * u ** 2 + 1, u ** 3 - 2 * u ** 2 + u, -2 * u ** 3 + 3 * u ** 2, u ** 3 - u ** 2
-    d_at = h00 * ys[idx, 0] + h10 * ds * dys[idx, 0] + h01 * ys[idx + 1, 0] + h11 * ds * dys[idx + 1, 0]
-    dp_at = h00 * ys[idx, 1] + h10 * ds * dys[idx, 1] + h01 * ys[idx + 1, 1] + h11 * ds * dys[idx + 1, 1]
-    d1 = d_at[::-1]
-    f = (dp_at[::-1]) * a / d1
-    d1 = d1 / d1[0]
+    # growth factor and rate: the reference's own scheme (adaptive RK2(3) at 1e-6, restarted per knot), restated as host code of the
+    # library (coffe_b200/csrc/growth_host.cpp).  A converged solution of the same ODE differs from the reference's tables by 2e-6
+    # in D1 and up to 2.4e-6 in f -- the whole "same inputs" deviation of the multipoles -- so the scheme is part of the result.
+    import ctypes as C
+    from . import capi
+    lib = capi.load()
+    d1, f = np.empty(n), np.empty(n)
+    if abs(z_max - 15.0) > 0:
+        raise ValueError("the background grid of coffe_background_init ends at z = 15 (src/background.c:446)")
+    rc = lib.coffe_b200_background_growth(C.c_double(omega_m), C.c_double(w0), C.c_double(wa), C.c_int(n), capi.ptr(d1), capi.ptr(f))
+    if rc:
+        raise ValueError("coffe_b200_background_growth: need 0 < omega_m < 1 and at least two knots")
 
     bias_z = np.arange(0.0, 11.0)
     default0 = (bias_z, np.zeros_like(bias_z))

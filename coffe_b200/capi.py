@@ -26,7 +26,8 @@ class Spline(C.Structure):
 
 
 class Integral(C.Structure):
-    _fields_ = [("n", C.c_int), ("l", C.c_int), ("half_integer", C.c_int), ("result", Spline)]
+    _fields_ = [("n", C.c_int), ("l", C.c_int), ("half_integer", C.c_int), ("result", Spline),
+                ("z2d", dp), ("values2d", dp), ("n_z2d", C.c_int)]
 
 
 class Tables(C.Structure):
@@ -48,7 +49,7 @@ class Tables(C.Structure):
 class Options(C.Structure):
     _fields_ = [(n, C.c_int) for n in CONTRIBUTIONS] + [
         ("only_cross_correlations", C.c_int),
-        ("flatsky_local", C.c_int), ("flatsky_local_nonlocal", C.c_int), ("flatsky_nonlocal", C.c_int)]
+        ("flatsky_local", C.c_int), ("flatsky_local_nonlocal", C.c_int), ("flatsky_nonlocal", C.c_int), ("midpoint", C.c_int)]
 
 
 class Quadrature(C.Structure):
@@ -95,9 +96,10 @@ def iptr(a):
 class TableSet:
     """Owns the numpy buffers behind a `Tables` struct (keeps them alive while C reads them)."""
 
-    def __init__(self, background, bias, integrals, omega_matter, h, interp_method=5, renorm=None, renorm0=None):
+    def __init__(self, background, bias, integrals, omega_matter, h, interp_method=5, renorm=None, renorm0=None, integrals2d=None):
         """background: dict name -> (x, y); bias: dict name -> (x, y); integrals: list of (n, l, half, x, y);
-        renorm: (chi, z[n, n]) with z[j, i] <-> (chi_i, chi_j); renorm0: (x, y)."""
+        renorm: (chi, z[n, n]) with z[j, i] <-> (chi_i, chi_j); renorm0: (x, y);
+        integrals2d: optional (z [n_z], {(n, l): values [n_r, n_z]}) -- the I^n_l(z, r) tables of the midpoint approximation."""
         self._keep = []
         t = Tables()
         for i, name in enumerate(BG_NAMES):
@@ -111,6 +113,11 @@ class TableSet:
         for i, (n, l, half, x, y) in enumerate(integrals):
             arr[i].n, arr[i].l, arr[i].half_integer = int(n), int(l), int(bool(half))
             arr[i].result = self._spline(x, y)
+            if integrals2d is not None and not half and (int(n), int(l)) in integrals2d[1]:
+                z2, v2 = darr(integrals2d[0]), darr(integrals2d[1][(int(n), int(l))])
+                assert v2.shape == (len(x), len(z2)), "values2d must be [n_r, n_z]"
+                self._keep += [z2, v2]
+                arr[i].z2d, arr[i].values2d, arr[i].n_z2d = ptr(z2), ptr(v2), len(z2)
         self._keep.append(arr)
         t.integrals = C.cast(arr, C.POINTER(Integral))
         t.n_integrals = len(integrals)
@@ -134,7 +141,7 @@ class TableSet:
         return s
 
 
-def make_options(contributions, only_cross=False, flatsky_local=False, flatsky_local_nonlocal=False, flatsky_nonlocal=False):
+def make_options(contributions, only_cross=False, flatsky_local=False, flatsky_local_nonlocal=False, flatsky_nonlocal=False, midpoint=False):
     o = Options()
     for n in CONTRIBUTIONS:
         setattr(o, n, 1 if n in contributions else 0)
@@ -142,6 +149,7 @@ def make_options(contributions, only_cross=False, flatsky_local=False, flatsky_l
     o.flatsky_local = int(flatsky_local)
     o.flatsky_local_nonlocal = int(flatsky_local_nonlocal)
     o.flatsky_nonlocal = int(flatsky_nonlocal)
+    o.midpoint = int(midpoint)
     return o
 
 

@@ -164,6 +164,8 @@ class Coffe:
         self._populations = [1, 1, 1, 1]
         self._bias = {name: (np.arange(0.0, 11.0), np.full(11, 1.0 if name.startswith("galaxy") else 0.0)) for name in _BIASES}
         self._pk = None
+        self._pk2d = None                 # (z [n_z], P(k, z_i) [n_z, n_k]) for the midpoint approximation
+        self._midpoint = False
         self._k_min, self._k_max = 1e-5, 300.0
         self._bessel_bins, self._background_bins = 10000, 10000
         self._cov_method, self._cov_bins = "standard", 8000
@@ -419,6 +421,36 @@ class Coffe:
         self._free_integrals()
         self._cache.clear()
 
+    def set_power_spectrum_2d(self, k, z, pk2d, k_min=None, k_max=None):
+        """P(k, z_i) on the knots k (1/Mpc, Mpc^3), rows pk2d[i] = P(k, z_i): the input of the midpoint approximation.  In the reference
+        these rows come out of CLASS inside parse_external_power_spectrum (src/parser.c:655-709, 100 redshifts z_i = 3 i/100) when
+        `pk_type` is not linear; here the host hands them over (no Boltzmann code in this package).  Needs the 1-D spectrum too
+        (set_power_spectrum_linear: CLASS's linear P(k, 0)), which the potential terms keep using."""
+        k, z, pk2d = np.array(k, dtype=float), np.array(z, dtype=float), np.array(pk2d, dtype=float)
+        if pk2d.shape != (len(z), len(k)):
+            raise ValueError("pk2d must have shape (len(z), len(k))")
+        if self._pk is None or len(self._pk[0]) != len(k) or not np.allclose(self._pk[0], k):
+            raise ValueError("set_power_spectrum_linear must be called first, with the same k knots")
+        self._pk2d = (z, pk2d)
+        if k_min is not None:
+            self._k_min = float(k_min)
+        if k_max is not None:
+            self._k_max = float(k_max)
+        self._free_integrals()
+        self._cache.clear()
+
+    @property
+    def midpoint_approximation(self):
+        """python/coffe/coffe.pyx `midpoint_approximation` (par->midpoint_approximation, used with pk_type != linear):
+        the standard terms read I^n_l((z_a + z_b)/2, r) built from P(k, z) instead of D1 D1 I^n_l(r)"""
+        return self._midpoint
+
+    @midpoint_approximation.setter
+    def midpoint_approximation(self, value):
+        self._midpoint = bool(value)
+        self._free_integrals()
+        self._cache.clear()
+
     def _power_spectrum_init(self):
         """default spectrum: the PkL_CLASS.dat table shipped with the package, k h and P / h^3 (src/parser.c:811-829)"""
         from pathlib import Path
@@ -526,6 +558,13 @@ class Coffe:
             if t == (1, -1, 1):
                 res["tables"][i] = res["tables"][i] * np.sqrt(2.0 / np.pi) * 2 * np.pi ** 2
         res["keys"] = tables
+        res["z2d"] = res["tables2d"] = None
+        if self._midpoint:
+            if self._pk2d is None:
+                raise ValueError("midpoint_approximation needs P(k, z): call set_power_spectrum_2d")
+            fam = [(n, l) for n, l in FAMILY]
+            _, v = eng.integrals2d(self._pk[0], self._pk2d[1], self.k_min, self.k_max, fam, bessel_bins=self._bessel_bins)
+            res["z2d"], res["tables2d"] = self._pk2d[0], {key: v[i] for i, key in enumerate(fam)}
         self._integrals = res
         self._tables_uploaded = False
 
@@ -544,8 +583,9 @@ class Coffe:
             x0 = res["r40"].copy()
             x0[0] = 0.0
             renorm0 = (x0, res["renorm0"])
+        i2d = (res["z2d"], res["tables2d"]) if res.get("tables2d") is not None else None
         return capi.TableSet(self._background, self._bias, integrals, self.omega_cdm + self.omega_baryon, self.h, interp_method=5,
-                             renorm=renorm, renorm0=renorm0)
+                             renorm=renorm, renorm0=renorm0, integrals2d=i2d)
 
     def _upload(self):
         if self._tables_uploaded and self._background is not None and self._integrals is not None and \
@@ -558,7 +598,8 @@ class Coffe:
     def _prepare_signal(self):
         self._upload()
         self._get_engine().set_options(self._contributions(), only_cross=self.has_only_cross_correlations, flatsky_local=self.has_flatsky_local,
-                                       flatsky_local_nonlocal=self.has_flatsky_local_nonlocal, flatsky_nonlocal=self.has_flatsky_nonlocal)
+                                       flatsky_local_nonlocal=self.has_flatsky_local_nonlocal, flatsky_nonlocal=self.has_flatsky_nonlocal,
+                                       midpoint=self._midpoint)
 
     def integral(self, *, r, n, l):
         """r^(n-l) I^n_l(r) for n > l, I^n_l(r) otherwise (python/coffe/coffe.pyx:1657-1713)"""

@@ -3,7 +3,10 @@
 // or viewed in place by the CPU debugging harness (tests/hostsim).
 #pragma once
 #include <cstring>
+#include <map>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "../../include/coffe_b200.h"
@@ -43,6 +46,7 @@ struct Layout {
     size_t ren2d_x = 0, ren2d_node = 0, ren2d_nodeT = 0; int ren2d_n = 0; double ren2d_x0 = 0, ren2d_inv_dx = 0, ren2d_dx = 0;
     size_t los = 0; int los_n = 0; double los_h = 0;
     int has_divergent = 0, has_ifam = 0, interp_kind = 5;
+    size_t mid_z = 0, mid_node[N_ITAB] = {0}; int mid_nz = 0, mid_nr = 0; double mid_z0 = 0, mid_inv_dz = 0;     /* 2-D I^n_l(z, r) tables */
     double chi_max_table = 0;     /* largest chi of the background table */
     double r_max_table = 0;       /* largest r of the I^n_l family */
 };
@@ -92,7 +96,57 @@ inline Tables make_view(const Layout &L, const double *base)
         t.extra[i].s = view_of(L.extra[i], base);
     }
     t.has_divergent = L.has_divergent;
+    t.mid.nz = L.mid_nz; t.mid.nr = L.mid_nr; t.mid.z0 = L.mid_z0; t.mid.inv_dz = L.mid_inv_dz;
+    t.mid.z = base + L.mid_z;
+    for (int k = 0; k < N_ITAB; ++k) t.mid.node[k] = reinterpret_cast<const double4 *>(base + L.mid_node[k]);
     return t;
+}
+
+/* The per-interval cubic coefficients of every uploaded spline (~25 tables of 10^4 knots: 45 ms when built one after the other, most
+   of a table upload) are independent of each other: assemble() builds them all up front on a few host threads and the code below
+   picks them up by the address of their ordinates. */
+struct CoefCache {
+    std::map<const double *, std::vector<build::Coef>> done;
+    std::vector<std::pair<const double *, std::pair<const double *, int>>> jobs;      /* y -> (x, n) */
+    void want(const coffe_b200_spline &s) { if (s.x && s.y && s.n >= 2 && !done.count(s.y)) { done[s.y]; jobs.push_back({s.y, {s.x, s.n}}); } }
+    void run(const int kind)
+    {
+        const unsigned hw = std::thread::hardware_concurrency();
+        const int n_threads = (int)std::max(1u, std::min<unsigned>(hw ? hw : 4u, std::min<size_t>(jobs.size(), 16)));
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; ++t)
+            th.emplace_back([this, t, n_threads, kind]() {
+                for (size_t j = t; j < jobs.size(); j += n_threads) {
+                    std::vector<build::Coef> k;
+                    const double *x = jobs[j].second.first;
+                    bool ok = true;
+                    for (int i = 0; i + 1 < jobs[j].second.second && ok; ++i) ok = x[i + 1] > x[i];
+                    if (ok && build::spline_coefs(kind, x, jobs[j].first, jobs[j].second.second, k)) done.find(jobs[j].first)->second = std::move(k);
+                }
+            });
+        for (auto &t : th) t.join();
+    }
+    /* false: not precomputed (or the table was rejected): the caller builds it itself and reports the error */
+    bool take(const double *y, std::vector<build::Coef> &k)
+    {
+        auto it = done.find(y);
+        if (it == done.end() || it->second.empty()) return false;
+        k = std::move(it->second);
+        done.erase(it);
+        return true;
+    }
+};
+
+inline CoefCache *&active_coef_cache()
+{
+    static thread_local CoefCache *c = nullptr;
+    return c;
+}
+
+inline bool cached_spline_coefs(const int kind, const double *x, const double *y, const int n, std::vector<build::Coef> &k)
+{
+    if (active_coef_cache() && active_coef_cache()->take(y, k)) return true;
+    return build::spline_coefs(kind, x, y, n, k);
 }
 
 inline bool put_spline(Arena &A, const coffe_b200_spline &s, const int kind, SplineOff &out, std::string &err, const char *what)
@@ -101,7 +155,7 @@ inline bool put_spline(Arena &A, const coffe_b200_spline &s, const int kind, Spl
     for (int i = 0; i + 1 < s.n; ++i)
         if (!(s.x[i + 1] > s.x[i])) { err = std::string("knots not strictly increasing in table: ") + what; return false; }
     std::vector<build::Coef> k;
-    if (!build::spline_coefs(kind, s.x, s.y, s.n, k)) { err = std::string("unsupported interpolation type or too few knots for table: ") + what; return false; }
+    if (!cached_spline_coefs(kind, s.x, s.y, s.n, k)) { err = std::string("unsupported interpolation type or too few knots for table: ") + what; return false; }
     out.x = A.put(s.x, s.n);
     out.k = A.put(k);
     out.n = s.n;
@@ -162,7 +216,24 @@ inline bool tables_magnification_constant(const coffe_b200_tables &T)
 /* number of uniformly spaced lambda samples of the line-of-sight table */
 static const int kLosSamples = 512;
 
+inline bool assemble_serial(const coffe_b200_tables &T, Arena &A, Layout &L, std::string &err);
+
 inline bool assemble(const coffe_b200_tables &T, Arena &A, Layout &L, std::string &err)
+{
+    /* every spline's coefficients up front, in parallel; assemble_serial then only validates and lays out */
+    CoefCache cache;
+    for (int i = 0; i < COFFE_B200_BG_COUNT; ++i) cache.want(T.background[i]);
+    for (int i = 0; i < COFFE_B200_BIAS_COUNT; ++i) cache.want(T.bias[i]);
+    for (int i = 0; i < T.n_integrals; ++i) cache.want(T.integrals[i].result);
+    if (T.n_renorm > 0) cache.want(T.renorm_zero_separation);
+    cache.run(T.interp_method);
+    active_coef_cache() = &cache;
+    const bool ok = assemble_serial(T, A, L, err);
+    active_coef_cache() = nullptr;
+    return ok;
+}
+
+inline bool assemble_serial(const coffe_b200_tables &T, Arena &A, Layout &L, std::string &err)
 {
     const int kind = T.interp_method;
     L.interp_kind = kind;
@@ -184,7 +255,7 @@ inline bool assemble(const coffe_b200_tables &T, Arena &A, Layout &L, std::strin
         for (int i = 0; i < n; ++i)
             if (s.x[i] != chi.x[i]) { err = std::string("background tables must share their z knots: ") + e.name; return false; }
         std::vector<build::Coef> k;
-        if (!build::spline_coefs(kind, s.x, s.y, n, k)) { err = "unsupported interpolation type for the background"; return false; }
+        if (!cached_spline_coefs(kind, s.x, s.y, n, k)) { err = "unsupported interpolation type for the background"; return false; }
         *e.off = A.put(k);
     }
     if (!put_spline(A, T.background[COFFE_B200_BG_Z_AS_CHI], kind, L.z_of_chi, err, "z_as_chi")) return false;
@@ -214,7 +285,7 @@ inline bool assemble(const coffe_b200_tables &T, Arena &A, Layout &L, std::strin
         std::vector<build::Coef> inter((size_t)(m - 1) * N_ITAB);
         for (int t = 0; t < N_ITAB; ++t) {
             std::vector<build::Coef> k;
-            if (!build::spline_coefs(kind, fx, fam[t]->result.y, m, k)) { err = "unsupported interpolation type for I^n_l"; return false; }
+            if (!cached_spline_coefs(kind, fx, fam[t]->result.y, m, k)) { err = "unsupported interpolation type for I^n_l"; return false; }
             for (int i = 0; i < m - 1; ++i) inter[(size_t)i * N_ITAB + t] = k[i];
         }
         L.ifam_x = A.put(fx, m);
@@ -229,6 +300,35 @@ inline bool assemble(const coffe_b200_tables &T, Arena &A, Layout &L, std::strin
         else { L.ifam_r0 = fx[ns]; L.ifam_inv_dln = (m - 1 - ns) / std::log(fx[m - 1] / fx[ns]); }
         L.ifam_n_small = ns;
     }
+    }
+    /* ---- 2-D tables of the midpoint approximation: all eight family members or none ---- */
+    L.mid_nz = 0;
+    if (L.has_ifam) {
+        const coffe_b200_integral *fam2[N_ITAB];
+        int have = 0;
+        for (int t = 0; t < N_ITAB; ++t) { fam2[t] = find_integral(T, kFamilyN[t], kFamilyL[t], 0); have += fam2[t]->n_z2d > 0 && fam2[t]->z2d && fam2[t]->values2d; }
+        if (have != 0 && have != N_ITAB) { err = "the 2-D tables I^n_l(z, r) must be given for all eight family members or for none"; return false; }
+        if (have == N_ITAB) {
+            const int nz = fam2[0]->n_z2d, nr = fam2[0]->result.n;
+            if (nz < 4) { err = "2-D tables need at least four redshift knots"; return false; }
+            for (int t = 0; t < N_ITAB; ++t) {
+                if (fam2[t]->n_z2d != nz) { err = "2-D tables must share their redshift knots"; return false; }
+                for (int i = 0; i < nz; ++i)
+                    if (fam2[t]->z2d[i] != fam2[0]->z2d[i] || (i > 0 && !(fam2[t]->z2d[i] > fam2[t]->z2d[i - 1]))) { err = "2-D tables must share strictly increasing redshift knots"; return false; }
+            }
+            L.mid_z = A.put(fam2[0]->z2d, nz);
+            L.mid_nz = nz; L.mid_nr = nr;
+            L.mid_z0 = fam2[0]->z2d[0];
+            L.mid_inv_dz = (nz - 1) / (fam2[0]->z2d[nz - 1] - fam2[0]->z2d[0]);
+            /* bicubic node data per table, built in parallel (1e6 nodes each) */
+            std::vector<std::vector<build::Coef>> nodes(N_ITAB);
+            std::vector<std::thread> th;
+            const double *fx = fam2[0]->result.x;
+            for (int t = 0; t < N_ITAB; ++t)
+                th.emplace_back([&, t]() { nodes[t] = build::bicubic_nodes(fam2[t]->z2d, fx, fam2[t]->values2d, nz, nr); });
+            for (auto &x : th) x.join();
+            for (int t = 0; t < N_ITAB; ++t) L.mid_node[t] = A.put(nodes[t]);
+        }
     }
     /* ---- divergent extras ---- */
     L.has_divergent = 0;

@@ -4,7 +4,7 @@ import sys
 from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
-SOURCES = ["engine.cu", "covariance.cu", "integrals.cu"]
+SOURCES = ["engine.cu", "covariance.cu", "integrals.cu", "growth_host.cpp"]
 HEADERS = ["hd.h", "tables.cuh", "physics.cuh", "quadrature.cuh", "item.cuh", "di_fast.cuh", "assemble.h", "compact.cuh", "compact_build.h", "table_build.h", "rules_build.h", "ctx.h", "special.cuh", "fft.cuh", "group.inc",
            "../../include/coffe_b200.h"]
 OUT = HERE / "libcoffe_b200.so"

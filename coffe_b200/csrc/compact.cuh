@@ -223,6 +223,7 @@ struct ExactAccess {
     COFFE_HD double i40(const double r) const { return hspline_eval(t->i40, r); }
     COFFE_HD double ren2d(const double a, const double b) const { return renorm2d_eval(t->ren2d, a, b); }
     COFFE_HD double ren0(const double l) const { return spline_eval(t->ren0, l); }
+    COFFE_HD void ifam_mid(const double r, const double z, double out[N_ITAB]) const { mid2d_eval_all(t->mid, t->ifam, z, r, out); }
 };
 
 struct CompactAccess {
@@ -233,6 +234,8 @@ struct CompactAccess {
     COFFE_HD double i40(const double r) const { return compact_i40(c, r); }
     COFFE_HD double ren2d(const double a, const double b) const { return renorm2d_eval(t->ren2d, a, b); }
     COFFE_HD double ren0(const double l) const { return spline_eval(t->ren0, l); }
+    /* the 2-D tables are never resampled into shared memory: the host routes midpoint runs to the exact-table kernel */
+    COFFE_HD void ifam_mid(const double r, const double z, double out[N_ITAB]) const { mid2d_eval_all(t->mid, t->ifam, z, r, out); }
 };
 
 }  // namespace coffe

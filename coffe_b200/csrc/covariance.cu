@@ -573,7 +573,9 @@ static int covariance_core(coffe_b200_ctx *ctx, const coffe_b200_covariance_para
     const int M = n_l * n_sep, Mpad = ((M + kTile - 1) / kTile) * kTile;
     const int tiles = Mpad / kTile;
     const int tr0 = row_begin / kTile, n_tr = (row_end - 1) / kTile - tr0 + 1;
-    int n_splits = std::max(1, (4 * ctx->n_sm) / (n_tr * tiles));
+    /* the k split (and with it the order of the partial sums) is fixed by the FULL matrix, not by the rows this call computes: a row
+       range must reproduce the entries of the full call bit for bit (multi-GPU sharding over rows) */
+    int n_splits = std::max(1, (4 * ctx->n_sm) / (tiles * tiles));
     const int chunk = std::max(kKc, std::min(n_nodes, (int)std::min<size_t>((size_t)1 << 31, ((size_t)2 << 30) / ((size_t)Mpad * 8))));
     if (n_splits > (chunk + kKc - 1) / kKc) n_splits = (chunk + kKc - 1) / kKc;
     CK(d_W.alloc((size_t)2 * n_nodes));

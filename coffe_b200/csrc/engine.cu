@@ -148,12 +148,18 @@ __global__ void __launch_bounds__(kItemThreads, COFFE_ITEM_MIN_BLOCKS) integrate
     __syncthreads();
 
     if (out_evals && tid == 0)
-        out_evals[item] = mode == 1 ? si_eval_count(q, sh.g, sh.ha) + si_eval_count(q, sh.g, sh.hb) : di_fast_eval_count(q, sh.g, sh.k);
+        out_evals[item] = mode == 1 ? si_eval_count(q, sh.g, sh.ha) + si_eval_count(q, sh.g, sh.hb)
+                                    : (o.midpoint ? di_eval_count(q, sh.g) : di_fast_eval_count(q, sh.g, sh.k));
     const ExactAccess ta{&t};
     double v = 0.0;
     if (mode == 1) {
-        if (warp < 2) v = si_half_partial(ta, t.los, q, sh.g, warp == 0 ? sh.ha : sh.hb, los, lane, 32, sh.panels[warp]);
+        if (warp < 2)
+            v = o.midpoint ? si_half_partial<ExactAccess, true>(ta, t.los, q, sh.g, warp == 0 ? sh.ha : sh.hb, los, lane, 32, sh.panels[warp])
+                           : si_half_partial(ta, t.los, q, sh.g, warp == 0 ? sh.ha : sh.hb, los, lane, 32, sh.panels[warp]);
     }
+    /* midpoint approximation: the mirror nodes of di_fast share one table lookup, which the 2-D tables (z differs between the
+       mirror nodes) do not allow: the plain ridge rule over di_eval, same panels and nodes */
+    else if (o.midpoint) v = di_partial(ta, t.los, q, sh.g, sh.k, los, warp, kItemWarps, lane, 32, sh.panels[warp]);
     else v = di_fast_partial(ta, t, los, q, sh.g, sh.k, row, warp, kItemWarps, lane, 32);
     v = warp_sum(v);
     if (lane == 0) sh.red[warp] = v;
@@ -478,6 +484,11 @@ int check_point(coffe_b200_ctx *ctx, const double z, const double sep, const boo
     if (!(chi - sep / 2. > 0.0)) { ctx->err = "separation larger than twice the comoving distance to z_mean"; return COFFE_B200_ERANGE; }
     if (!(chi + sep / 2. < ctx->layout.chi_max_table)) { ctx->err = "chi_mean + sep/2 outside the background table"; return COFFE_B200_ERANGE; }
     if (!(sep <= ctx->layout.r_max_table)) { ctx->err = "separation outside the I^n_l tables"; return COFFE_B200_ERANGE; }
+    if (ctx->o.midpoint && ctx->layout.mid_nz > 0) {
+        /* the 2-D tables are read at redshifts up to z(chi_mean + sep/2) (the reference's grid ends at z = 2.97, src/integrals.c:679-689) */
+        const double z_hi = spline_eval(t.bg.z_of_chi, chi + sep / 2.);
+        if (!(z_hi <= t.mid.z[t.mid.nz - 1])) { ctx->err = "z(chi_mean + sep/2) beyond the redshift grid of the 2-D tables"; return COFFE_B200_ERANGE; }
+    }
     if (need_renorm) {
         const double rmax = t.ren2d.x[t.ren2d.n - 1];
         if (!(chi + sep / 2. <= rmax)) {
@@ -485,6 +496,17 @@ int check_point(coffe_b200_ctx *ctx, const double z, const double sep, const boo
             return COFFE_B200_ERANGE;
         }
     }
+    return COFFE_B200_OK;
+}
+
+/* midpoint approximation: needs the 2-D tables; the reference's flat-sky variants of it (src/functions.c:136-155 ff., 4046-4248) and
+   its covariance branch (src/covariance.c, P(k, z) per bin) are not built */
+int check_midpoint(coffe_b200_ctx *ctx)
+{
+    const Options &o = ctx->o;
+    if (!o.midpoint) return COFFE_B200_OK;
+    if (ctx->layout.mid_nz == 0) { ctx->err = "the midpoint approximation needs the 2-D tables I^n_l(z, r) (coffe_b200_integral.values2d)"; return COFFE_B200_ENOTABLES; }
+    if (o.flatsky_local || o.flatsky_local_nonlocal || o.flatsky_nonlocal) { ctx->err = "the midpoint approximation is not available together with the flat-sky switches"; return COFFE_B200_EINVAL; }
     return COFFE_B200_OK;
 }
 
@@ -537,7 +559,7 @@ int launch_integrated(coffe_b200_ctx *ctx, Batch &b, const int mode, unsigned in
     if (stage_n > ctx->layout.los_n) stage_n = ctx->layout.los_n;
     const size_t los_bytes = (size_t)kLosStride * stage_n * sizeof(double2);
     const size_t row_bytes = (size_t)(ctx->layout.has_divergent ? ctx->layout.ren2d_n : 0) * sizeof(double2);
-    if (ctx->variant == 1 && ctx->compact.h.valid) {
+    if (ctx->variant == 1 && ctx->compact.h.valid && !ctx->o.midpoint) {
         /* shared-memory tables: blob prefix covering R <= 2 chi_max, line-of-sight table, per-warp state */
         const int stage_bytes = compact_stage_bytes(ctx->compact, 2.0 * b.chi_max);
         CompactHeader ch = ctx->compact.h;
@@ -763,6 +785,8 @@ int plan_build(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double 
                     return COFFE_B200_ENOTABLES;
                 }
     }
+    rc = check_midpoint(ctx);
+    if (rc) return rc;
     pl.ctx = ctx; pl.n = end - begin; pl.ls = make_llist(l, n_l); pl.generation = ctx->generation;
     if (end == begin) return COFFE_B200_OK;
     CK(cudaSetDevice(ctx->device));
@@ -1007,6 +1031,7 @@ int coffe_b200_set_options(coffe_b200_ctx *ctx, const coffe_b200_options *opt)
     o.flatsky_local = opt->flatsky_local != 0;
     o.flatsky_local_nonlocal = opt->flatsky_local_nonlocal != 0;
     o.flatsky_nonlocal = opt->flatsky_nonlocal != 0;
+    o.midpoint = opt->midpoint != 0;
     ctx->generation++;
     return COFFE_B200_OK;
 }
@@ -1126,6 +1151,7 @@ static int corrfunc_core(coffe_b200_ctx *ctx, const double *z_mean, int n_z, con
     const size_t n_out = (size_t)(end - begin);
     pieces.assign(3 * n_out, 0.0);
     if (n_out == 0) return COFFE_B200_OK;
+    { const int rcm = check_midpoint(ctx); if (rcm) return rcm; }
     for (int i = 0; i < n_mu; ++i)
         if (!(mu[i] > -1.0 && mu[i] < 1.0)) { ctx->err = "mu must lie strictly inside (-1, 1)"; return COFFE_B200_EINVAL; }
     CK(cudaSetDevice(ctx->device));
@@ -1234,6 +1260,7 @@ int coffe_internal_average_core(coffe_b200_ctx *ctx, const double *z_min, const 
     const int n_groups = (int)(end - begin), nz = ctx->qc.n_z;
     hm.assign((size_t)n_groups * 3 * n_l, 0.0);
     if (n_groups == 0) return COFFE_B200_OK;
+    { const int rcm = check_midpoint(ctx); if (rcm) return rcm; }
     CK(cudaSetDevice(ctx->device));
     const bool ren = needs_renorm(ctx->o);
     if (ren && !ctx->layout.has_divergent) { ctx->err = "d2/g1..g5 need the divergent I^4_0 tables (par->divergent)"; return COFFE_B200_EINVAL; }

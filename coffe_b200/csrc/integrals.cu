@@ -399,4 +399,28 @@ int coffe_b200_integrals(coffe_b200_ctx *ctx, const coffe_b200_integrals_params 
     return COFFE_B200_OK;
 }
 
+/* I^n_l(z, r) for the midpoint approximation: one coffe_b200_integrals pass per redshift row of P(k, z) (src/integrals.c:663-767 does
+   exactly this, 100 times per table).  Set-up work: ~100 x 5 ms. */
+int coffe_b200_integrals2d(coffe_b200_ctx *ctx, const coffe_b200_integrals_params *p, const double *pk2d, int n_z, double *tables2d)
+{
+    if (!ctx || !p || !pk2d || !tables2d || n_z < 1) return COFFE_B200_EINVAL;
+    int n_r = 0, n_r40 = 0, n_ren = 0;
+    int rc = coffe_b200_integrals_sizes(p, &n_r, &n_r40, &n_ren);
+    if (rc) return rc;
+    coffe_b200_integrals_params q = *p;
+    q.divergent = 0;
+    std::vector<double> r((size_t)n_r), tab((size_t)n_r * p->n_tables);
+    double total_ms = 0;
+    for (int i = 0; i < n_z; ++i) {
+        q.pk_p = pk2d + (size_t)i * p->n_pk;
+        rc = coffe_b200_integrals(ctx, &q, r.data(), tab.data(), nullptr, nullptr, nullptr, nullptr, nullptr);
+        if (rc) return rc;
+        total_ms += ctx->last_ms;
+        for (int t = 0; t < p->n_tables; ++t)
+            for (int j = 0; j < n_r; ++j) tables2d[((size_t)t * n_r + j) * n_z + i] = tab[(size_t)t * n_r + j];
+    }
+    ctx->last_ms = total_ms;
+    return COFFE_B200_OK;
+}
+
 }  // extern "C"

@@ -105,21 +105,21 @@ COFFE_HD unsigned int ridge_eval_count(const double hi, const double center, con
     return n;
 }
 
-template <class TA>
+template <class TA, bool MID = false>
 struct SIFunctor {
     const TA *t; const SIHalf *h; const Geometry *g; const double2 *los; int los_n; double los_inv_h;
     COFFE_HD double operator()(const double lambda) const
     {
-        return si_half_eval(*t, *h, *g, lambda, los_eval(los, los_n, los_inv_h, lambda));
+        return si_half_eval<MID>(*t, *h, *g, lambda, los_eval(los, los_n, los_inv_h, lambda));
     }
 };
 
 /* one half of the local x integrated piece, per unit x (the reference integrates x in [0,1], src/signal.c:584-606) */
-template <class TA>
+template <class TA, bool MID = false>
 COFFE_HD double si_half_partial(const TA &t, const LosView &lv, const Rules &q, const Geometry &g, const SIHalf &h,
                                 const double2 *los, const int lane, const int nlanes, double *scratch)
 {
-    SIFunctor<TA> f{&t, &h, &g, los, lv.n, lv.inv_h};
+    SIFunctor<TA, MID> f{&t, &h, &g, los, lv.n, lv.inv_h};
     const double center = h.cs * g.c;
     const double eps = h.cs * sqrt(g.s2);
     return ridge_integrate(f, h.co, center, eps, q, q.n_panel_si, lane, nlanes, scratch) / h.co;

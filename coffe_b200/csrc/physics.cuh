@@ -28,6 +28,7 @@ struct Options {
     int only_cross;
     int flatsky_local, flatsky_local_nonlocal, flatsky_nonlocal;
     int divergent;
+    int midpoint;         /* pk_type != linear with midpoint_approximation: the standard terms read I^n_l((z_a + z_b)/2, r) (tables.cuh: Mid2DView) */
     int out_multipoles;   /* 1 while serving coffe_multipoles_init: the flat-sky closed forms of src/signal.c:610-631, 707-735
                              exist only for flag_output == MULTIPOLES, not for the 2PCF or the redshift average */
     double Om;     /* Omega0_cdm + Omega0_baryon */
@@ -92,6 +93,7 @@ COFFE_HD Geometry geometry(const double chi_mean, const double sep, const double
 /* ---- values at the separation / mean redshift, constant over mu ------------------------------ */
 struct SepConst {
     double i[N_ITAB];   /* I^n_l(sep) */
+    double imid[N_ITAB];/* midpoint approximation: I^n_l(z_mean, sep) from the 2-D tables (src/functions.c:136-155) */
     double i40;         /* I^4_0(sep) */
     /* mean-redshift values (flat-sky branches and the final growth factor) */
     double z_mean, chi_mean, fm, Hm, bm1, bm2, Gm1, Gm2, D1m, sm1, sm2;
@@ -101,6 +103,7 @@ COFFE_HD SepConst sep_const(const Options &o, const Tables &t, const double z_me
 {
     SepConst s;
     ifam_eval_all(t.ifam, sep, s.i);
+    if (o.midpoint) mid2d_eval_all(t.mid, t.ifam, z_mean, sep, s.imid);
     s.i40 = o.divergent ? hspline_eval(t.i40, sep) : 0.0;
     s.z_mean = z_mean;
     s.chi_mean = bg_chi(t.bg, z_mean);
@@ -134,15 +137,15 @@ COFFE_HD double ni_eval(const Options &o, const Tables &t, const SepConst &sc, c
     const double f1 = e1.f, f2 = e2.f, H1 = e1.Hc, H2 = e2.Hc, b1 = e1.b, b2 = e2.b;
     const double G1 = e1.G, G2 = e2.G, a1 = e1.a, a2 = e2.a;
     const double q1 = 3.0 - e1.fevo, q2 = 3.0 - e2.fevo;
-    const double *I = sc.i;
     const bool autos = !o.only_cross;
     double res = 0.0;
-
-    /* divergent bracket I^4_0(r) - renormalisation(chi1, chi2)   src/functions.c:574-597 */
-    double ren = 0.0;
-    if (o.divergent && (o.d2 || o.g1 || o.g2 || o.g3))
-        ren = sc.i40 - renorm2d_eval(t.ren2d, chi1, chi2);
-
+    /* Midpoint approximation (HAVE_CLASS, pk_type != linear; src/functions.c:136-155, 188-199, 237-297, 370-571, 677-786, 778-1022):
+       the six standard terms den-den, rsd-rsd, d1-d1, den-rsd, den-d1, rsd-d1 take I^n_l(z_mean, r) from the 2-D tables, growth
+       included, instead of D1 D1 I^n_l(r).  They are summed apart (res_std) so that the growth factor at the end leaves them alone. */
+    double res_std = 0.0;
+    {
+    const double *I = o.midpoint ? sc.imid : sc.i;
+    double &res = res_std;
     if (o.flatsky_local) {
         const double p2 = 0.5 * (3.0 * mu * mu - 1.0);
         const double fm = sc.fm, Hm = sc.Hm;
@@ -193,6 +196,12 @@ COFFE_HD double ni_eval(const Options &o, const Tables &t, const SepConst &sc, c
                  + (f1 * f2 * H2 * G2 * pa / 5 + f2 * f1 * H1 * G1 * pb / 5) * I[I13] / r2;
         }
     }
+    }
+    const double *I = sc.i;
+    /* divergent bracket I^4_0(r) - renormalisation(chi1, chi2)   src/functions.c:574-597 */
+    double ren = 0.0;
+    if (o.divergent && (o.d2 || o.g1 || o.g2 || o.g3))
+        ren = sc.i40 - renorm2d_eval(t.ren2d, chi1, chi2);
     /* the remaining terms have no flat-sky variant in the reference */
     if (o.d2 && autos) res += q1 * q2 * H1 * H1 * H2 * H2 * f1 * f2 * ren;                     /* :574-597 */
     if (o.g1 || o.g2 || o.g3) {
@@ -223,6 +232,8 @@ COFFE_HD double ni_eval(const Options &o, const Tables &t, const SepConst &sc, c
         res += -(q2 * H1 * H2 * H2 * f1 * f2 * (chi2 * c - chi1) + q1 * H2 * H1 * H1 * f2 * f1 * (chi1 * c - chi2)) * I[I31];
 
     /* growth: D1(z_mean)^2 in flat-sky, D1(z1) D1(z2) otherwise            src/functions.c:1456-1467 */
+    if (o.midpoint) return res_std + (o.flatsky_local ? res * sc.D1m * sc.D1m : res * e1.D1 * e2.D1);
+    res += res_std;
     return o.flatsky_local ? res * sc.D1m * sc.D1m : res * e1.D1 * e2.D1;
 }
 
@@ -236,6 +247,8 @@ struct SIHalf {
     double g5_i20, g5_rsd, g5_d1, g5_ren;           /* x V(lambda) x {Wa | W} x bracket (co, G_other folded in) */
     int alt_i04;                                    /* |mu| >= 0.999 */
     int any_lens, any_g4, any_g5, need_ren;
+    int mid;                                        /* midpoint approximation: den/rsd/d1 x len read the 2-D tables */
+    double zs, D1s;                                 /* redshift and growth factor of the local end */
 };
 
 /* src = local end, oth = the end whose line of sight is integrated.  `first` selects the quirks of the
@@ -276,6 +289,7 @@ COFFE_HD SIHalf si_half_setup(const Options &o, const Geometry &g, const EndVals
         if (o.d2) h.g5_ren += h2 * (-3 * Om) * pre * q * src.f * src.Hc * src.Hc * src.D1;                  /* :3279-3299 */
         if (o.g1 || o.g2 || o.g3) h.g5_ren += h4 * (9 * Om * Om / 2.) * pre * src.phi * src.D1 / src.a;     /* :3321-3423 */
     }
+    h.mid = o.midpoint; h.zs = src.z; h.D1s = src.D1;
     h.alt_i04 = fabs(g.mu) >= 0.999;
     h.any_lens = (h.a_denlen != 0.0) || (h.a_rsdlen != 0.0) || (h.a_d1len != 0.0) || (h.a_pot != 0.0);
     h.any_g4 = o.g4 && opt_has_ni(o);
@@ -286,7 +300,7 @@ COFFE_HD SIHalf si_half_setup(const Options &o, const Geometry &g, const EndVals
 
 /* integrand of one half at lambda (distance along the integrated line of sight), per unit x = lambda/co.
    los = {W, V, U, Wa}(lambda). */
-template <class TA>
+template <bool MID = false, class TA>
 COFFE_HD double si_half_eval(const TA &t, const SIHalf &h, const Geometry &g, const double lambda, const double4 los)
 {
     const double c = g.c, c2 = c * c, s2 = g.s2;
@@ -301,16 +315,30 @@ COFFE_HD double si_half_eval(const TA &t, const SIHalf &h, const Geometry &g, co
     t.ifam_all(R, I);
     const double W = los.x, V = los.y, Wa = los.w;
     double res = 0.0;
+    /* Midpoint approximation (src/functions.c:1626-1700, 2061-2326, 2492-2918): den-len, rsd-len and d1-len read
+       I^n_l((z_src + z(lambda))/2, R) from the 2-D tables in place of D1(z_src) D1(z(lambda)) I^n_l(R).  The growth factors stay
+       folded into the amplitudes, so the table value is divided by them; z(lambda) and D1(lambda) follow from W = D1/a, Wa = D1 a.
+       The potential terms (a_pot, g4, g5) have no such variant and keep the linear tables. */
+    double Imid[N_ITAB];
+    const double *Is = I;
+    if (MID && h.mid && h.any_lens) {
+        const double D1l = sqrt(W * Wa), zl = sqrt(W / Wa) - 1.0;
+        t.ifam_mid(R, 0.5 * (h.zs + zl), Imid);
+        const double inv = 1.0 / (h.D1s * D1l);
+#pragma unroll
+        for (int k = 0; k < N_ITAB; ++k) Imid[k] *= inv;
+        Is = Imid;
+    }
     if (h.any_lens) {
         double br = 0.0;
         if (rr != 0.0) {
             const double irr = iR * iR;
             const double tc = 2 * c2 - 1;
             if (h.a_denlen != 0.0)                                                                  /* :1592-1640 */
-                br += h.a_denlen * (2 * cs * c * I[I11] - cs * cs * l * s2 * I[I02] * irr);
+                br += h.a_denlen * (2 * cs * c * Is[I11] - cs * cs * l * s2 * Is[I02] * irr);
             if (h.a_rsdlen != 0.0) {                                                                /* :2059-2390 */
-                double b = (l - 6 * cs * c + 3 * l * tc) * I[I00] / 15.
-                         - (6 * cs * cs * cs * c - cs * cs * l * (9 * c2 + 11) + cs * l * l * c * (3 * tc + 19) - 2 * l * l * l * (3 * tc + 1)) * I[I02] * irr / 21.;
+                double b = (l - 6 * cs * c + 3 * l * tc) * Is[I00] / 15.
+                         - (6 * cs * cs * cs * c - cs * cs * l * (9 * c2 + 11) + cs * l * l * c * (3 * tc + 19) - 2 * l * l * l * (3 * tc + 1)) * Is[I02] * irr / 21.;
                 if (!h.alt_i04) {
                     /* the reference's quintic (functions.c:2205-2214) cancels from O(chi^5) to O(chi r^4); the same
                        polynomial expanded in the small quantities d = l - cs and w = 1 - cos(theta): */
@@ -320,15 +348,15 @@ COFFE_HD double si_half_eval(const TA &t, const SIHalf &h, const Geometry &g, co
                                     + w * (-6 * l2 * (2 * cs2 * cs + 6 * cs2 * dl + 6 * cs * d2 + d2 * dl)
                                     + w * (2 * cs * l2 * (2 * cs2 + 4 * cs * dl + 3 * d2)
                                     + w * cs2 * l2 * l)));
-                    b += -p5 * I[I04] * irr * irr / 35.;
+                    b += -p5 * Is[I04] * irr * irr / 35.;
                 }
-                else b += 4. * (l + cs) * I[I04] / 35.;
+                else b += 4. * (l + cs) * Is[I04] / 35.;
                 br += h.a_rsdlen * b;
             }
             if (h.a_d1len != 0.0) {                                                                 /* :2490-2560 */
                 const double cs2 = cs * cs, l2 = l * l;
-                br += h.a_d1len * (2 * (c * (l2 - 2 * cs2) + cs * l * (2 * tc - 1)) * I[I11] / 15. + 2 * c * I[I20] / 3.
-                                   - (4 * cs2 * cs2 * c - cs2 * cs * l * (c2 + 9) + cs2 * l2 * c * (c2 + 5) - 2 * cs * l2 * l * (tc - 2) - 2 * l2 * l2 * c) * I[I13] * irr / 15.);
+                br += h.a_d1len * (2 * (c * (l2 - 2 * cs2) + cs * l * (2 * tc - 1)) * Is[I11] / 15. + 2 * c * Is[I20] / 3.
+                                   - (4 * cs2 * cs2 * c - cs2 * cs * l * (c2 + 9) + cs2 * l2 * c * (c2 + 5) - 2 * cs * l2 * l * (tc - 2) - 2 * l2 * l2 * c) * Is[I13] * irr / 15.);
             }
             if (h.a_pot != 0.0)                                                                     /* :3000-3121 */
                 br += h.a_pot * (2 * cs * c * I[I31] - cs * cs * l * s2 * I[I22]);
@@ -336,11 +364,11 @@ COFFE_HD double si_half_eval(const TA &t, const SIHalf &h, const Geometry &g, co
         }
         else {
             /* r == 0 limits                                             src/functions.c:1641-1760, 2391-2480, 2631-2990 */
-            if (h.a_denlen != 0.0) br += h.a_denlen * 2 * cs * I[I11];
-            if (h.a_d1len != 0.0) br += h.a_d1len * 2 * I[I20] / 3.;
+            if (h.a_denlen != 0.0) br += h.a_denlen * 2 * cs * Is[I11];
+            if (h.a_d1len != 0.0) br += h.a_d1len * 2 * Is[I20] / 3.;
             if (h.a_pot != 0.0) br += h.a_pot * (2 * cs * c * I[I31] - cs * cs * l * s2 * I[I22]);
             res += (h.co - l) * W * br;
-            if (h.a_rsdlen != 0.0) res += h.a_rsdlen * (h.co - cs) * W * (-2 * cs * I[I00] / 15.);
+            if (h.a_rsdlen != 0.0) res += h.a_rsdlen * (h.co - cs) * W * (-2 * cs * Is[I00] / 15.);
         }
     }
     if (h.any_g4 || h.any_g5) {
@@ -365,6 +393,7 @@ struct DIConst {
     double k_45a, k_45b;      /* 9 Om^2 G2 (2-5s1) chi2 ; G1 (2-5s2) chi1       g4-g5    :3966-3988 */
     double h4;
     int any_ll, any_pl, any_ren;
+    int mid;                  /* midpoint approximation: len-len reads the 2-D tables (src/functions.c:3564-3836) */
 };
 
 COFFE_HD DIConst di_setup(const Options &o, const EndVals &e1, const EndVals &e2)
@@ -389,6 +418,7 @@ COFFE_HD DIConst di_setup(const Options &o, const EndVals &e1, const EndVals &e2
     k.k_45b = (o.g4 && o.g5) ? 9 * Om2 * e1.G * m2 * e1.chi : 0.0;
     const double h2 = o.H0h * o.H0h;
     k.h4 = h2 * h2;
+    k.mid = o.midpoint;
     k.any_ll = k.k_ll != 0.0;
     k.any_pl = (k.k_4l != 0.0) || (k.k_5la != 0.0) || (k.k_5lb != 0.0);
     k.any_ren = o.divergent && ((k.k_44 != 0.0) || (k.k_55 != 0.0) || (k.k_45a != 0.0) || (k.k_45b != 0.0));
@@ -413,18 +443,30 @@ COFFE_HD double di_eval(const TA &t, const DIConst &k, const Geometry &g, const 
     const double e1 = g.chi1 - l1, e2 = g.chi2 - l2;    /* chi_i (1 - x_i) */
     double res = 0.0;
     if (k.any_ll) {
+        /* midpoint approximation: I^n_l((z(l1) + z(l2))/2, R) from the 2-D tables over the growth factors folded into W W */
+        double Imid[N_ITAB];
+        const double *Il = I;
+        if (k.mid) {
+            const double z1 = sqrt(los1.x / los1.w) - 1.0, z2 = sqrt(los2.x / los2.w) - 1.0;
+            t.ifam_mid(R, 0.5 * (z1 + z2), Imid);
+            const double inv = 1.0 / sqrt(los1.x * los1.w * los2.x * los2.w);
+#pragma unroll
+            for (int j = 0; j < N_ITAB; ++j) Imid[j] *= inv;
+            Il = Imid;
+        }
         double br;
         if (r2 > 1e-20) {
             const double ir2 = ir * ir;
             const double cm = -g.s2;     /* cos^2(theta) - 1 */
-            br = 2 * cm * ll * I[I00] / 5.
-               + 4 * c * I[I20] / 3.
-               + 4 * c * (r2 + 6 * c * ll) * I[I11] / 15.
-               + 2 * cm * ll * (2 * r2 + 3 * c * ll) * I[I02] / 7. * ir2
-               + 2 * c * (2 * r2 * r2 + 12 * c * r2 * ll + 15 * cm * ll * ll) * I[I13] / 15. * ir2
-               + cm * ll * (6 * r2 * r2 + 30 * c * r2 * ll + 35 * cm * ll * ll) * I[I04] / 35. * ir2 * ir2;
+            br = 2 * cm * ll * Il[I00] / 5.
+               + 4 * c * Il[I20] / 3.
+               + 4 * c * (r2 + 6 * c * ll) * Il[I11] / 15.
+               + 2 * cm * ll * (2 * r2 + 3 * c * ll) * Il[I02] / 7. * ir2
+               + 2 * c * (2 * r2 * r2 + 12 * c * r2 * ll + 15 * cm * ll * ll) * Il[I13] / 15. * ir2
+               + cm * ll * (6 * r2 * r2 + 30 * c * r2 * ll + 35 * cm * ll * ll) * Il[I04] / 35. * ir2 * ir2;
         }
-        else br = 4. + 24. * ll * I[I11] / 15.;
+        /* coincident points: the linear branch reads I^1_1(0), the midpoint branch of the reference its (2, 0) table (src/functions.c:3796-3808) */
+        else br = 4. + 24. * ll * (k.mid ? Il[I20] : I[I11]) / 15.;
         res += k.k_ll * e1 * e2 * WW * br;
     }
     if (k.any_pl) {

@@ -340,6 +340,41 @@ COFFE_HD double4 los_eval(const double2 *v, const int n, const double inv_h, con
     return o;
 }
 
+/* ---- I^n_l(z, r) tables of the midpoint approximation (coffe_integral_t.result2d, src/integrals.c:663-767) ------------------
+   GSL's bicubic interpolant on the (z, r) grid: per node {f, f_z, f_r, f_zr} (table_build.h: bicubic_nodes restates how GSL
+   estimates the derivatives), evaluated with the Hermite patch of the cell; z knots uniform, r knots = the family's own.
+   node[t][j*nz + i] <-> table t at (z_i, r_j).  Read through L1/L2: this is the path of the non-linear P(k), not the benchmark's. */
+struct Mid2DView {
+    const double *z;
+    const double4 *node[N_ITAB];
+    int nz, nr;
+    double z0, inv_dz;
+};
+
+COFFE_HD void mid2d_eval_all(const Mid2DView &m, const IntegralFamilyView &fam, double zq, double r, double out[N_ITAB])
+{
+    int iz = (int)((zq - m.z0) * m.inv_dz);
+    if (iz < 0) iz = 0;
+    if (iz > m.nz - 2) iz = m.nz - 2;
+    while (iz > 0 && zq < m.z[iz]) --iz;
+    while (iz < m.nz - 2 && zq >= m.z[iz + 1]) ++iz;
+    const int ir = ifam_index(fam, r);
+    const double dz = m.z[iz + 1] - m.z[iz], dr = fam.x[ir + 1] - fam.x[ir];
+    const double tt = (zq - m.z[iz]) / dz, u = (r - fam.x[ir]) / dr;
+    const double t2 = tt * tt, t3 = t2 * tt, u2 = u * u, u3 = u2 * u;
+    const double h00t = 2 * t3 - 3 * t2 + 1, h10t = (t3 - 2 * t2 + tt) * dz, h01t = -2 * t3 + 3 * t2, h11t = (t3 - t2) * dz;
+    const double h00u = 2 * u3 - 3 * u2 + 1, h10u = (u3 - 2 * u2 + u) * dr, h01u = -2 * u3 + 3 * u2, h11u = (u3 - u2) * dr;
+    const size_t a = (size_t)ir * m.nz + iz, b = a + m.nz;
+#pragma unroll
+    for (int k = 0; k < N_ITAB; ++k) {
+        const double4 n00 = m.node[k][a], n10 = m.node[k][a + 1], n01 = m.node[k][b], n11 = m.node[k][b + 1];
+        out[k] = h00t * (h00u * n00.x + h01u * n01.x + h10u * n00.z + h11u * n01.z)
+               + h01t * (h00u * n10.x + h01u * n11.x + h10u * n10.z + h11u * n11.z)
+               + h10t * (h00u * n00.y + h01u * n01.y + h10u * n00.w + h11u * n01.w)
+               + h11t * (h00u * n10.y + h01u * n11.y + h10u * n10.w + h11u * n11.w);
+    }
+}
+
 /* an I^n_l table outside the interleaved family: I^1_l (flat-sky lensing-lensing multipoles, src/integrals.c:
    1085-1247) and the half-integer tables (n/2, l/2) of the flat-sky density-lensing multipoles (:1249-1413) */
 struct ExtraSpline { int n, l, half; SplineView s; };
@@ -357,6 +392,7 @@ struct Tables {
     ExtraSpline extra[kMaxExtra];   /* every other uploaded I^n_l (flat-sky closed forms), looked up by key */
     int n_extra;
     int has_divergent;
+    Mid2DView mid;             /* nz = 0 unless the 2-D tables were uploaded */
 };
 
 COFFE_HD const SplineView *find_extra(const Tables &t, const int n, const int l, const int half)

@@ -237,6 +237,24 @@ class Engine:
         return {"r": r, "tables": out[:len(tb)], "r40": r40 if div else None, "i40": i40 if div else None, "renorm0": ren0 if div else None,
                 "renorm_chi": chi if div else None, "renorm_z": rz if div else None}
 
+    def integrals2d(self, k, pk2d, k_min, k_max, tables, bessel_bins=10000, interp_method=5):
+        """I^n_l(z_i, r) of every table from the rows pk2d[i] = P(k, z_i): what coffe_integrals_init adds per table with CLASS and the
+        midpoint approximation (src/integrals.c:663-767).  Returns (r [n_r], values [n_tables, n_r, n_z])."""
+        k, pk2d = capi.darr(k), capi.darr(pk2d)
+        assert pk2d.ndim == 2 and pk2d.shape[1] == len(k)
+        tb = [tuple(t) + (0,) * (3 - len(t)) for t in tables]
+        n_, l_, h_ = capi.iarr([t[0] for t in tb]), capi.iarr([t[1] for t in tb]), capi.iarr([t[2] for t in tb])
+        ip_ = capi.IntegralsParams()
+        ip_.pk_k, ip_.pk_p, ip_.n_pk, ip_.interp_method = capi.ptr(k), capi.ptr(pk2d), len(k), int(interp_method)
+        ip_.k_min, ip_.k_max, ip_.bessel_bins = float(k_min), float(k_max), int(bessel_bins)
+        ip_.n, ip_.l, ip_.half, ip_.n_tables = capi.iptr(n_), capi.iptr(l_), capi.iptr(h_), len(tb)
+        n_r, n_r40, n_ren = C.c_int(), C.c_int(), C.c_int()
+        self._check(self.lib.coffe_b200_integrals_sizes(C.byref(ip_), C.byref(n_r), C.byref(n_r40), C.byref(n_ren)))
+        out = np.zeros((len(tb), n_r.value, pk2d.shape[0]))
+        self._check(self.lib.coffe_b200_integrals2d(self._h, C.byref(ip_), capi.ptr(pk2d), C.c_int(pk2d.shape[0]), capi.ptr(out)))
+        r = self.integrals((k, pk2d[0]), k_min, k_max, tables[:1], bessel_bins=bessel_bins, interp_method=interp_method)["r"]
+        return r, out
+
     # ---- prepared computations (inputs resident in HBM) -----------------------------------------------
     def plan_multipoles(self, z_mean, sep, l, begin=0, end=None):
         z, s, ls = capi.darr(z_mean), capi.darr(sep), capi.iarr(l)

@@ -77,6 +77,7 @@ static coffe_b200_options options_of(const coffe_parameters_t *par)
     o.g4 = par->correlation_contrib.g4; o.g5 = par->correlation_contrib.g5;
     o.only_cross_correlations = par->only_cross_correlations;
     o.flatsky_local = par->flatsky_local; o.flatsky_local_nonlocal = par->flatsky_local_nonlocal; o.flatsky_nonlocal = par->flatsky_nonlocal;
+    o.midpoint = par->pk_type != COFFE_PK_LINEAR && par->midpoint_approximation;      /* src/functions.c:136-155 */
     return o;
 }
 
@@ -106,6 +107,7 @@ static int upload(const coffe_parameters_t *par, const coffe_background_t *bg, c
     T.interp_method = par->interp_method;
     const size_t n = integral ? integral->size : 0;
     coffe_b200_integral *I = (coffe_b200_integral *)coffe_malloc(sizeof(coffe_b200_integral) * (n ? n : 1));
+    memset(I, 0, sizeof(coffe_b200_integral) * (n ? n : 1));
     int used = 0;
     for (size_t i = 0; i < n; ++i) {
         const coffe_integral_t *it = &integral->array[i];
@@ -113,6 +115,10 @@ static int upload(const coffe_parameters_t *par, const coffe_background_t *bg, c
         I[used].n = it->n; I[used].l = it->l;
         I[used].half_integer = it->state_n == COFFE_HALF_INTEGER;
         I[used].result = view(&it->result);
+        if (it->result2d.spline) {                 /* I^n_l(z, r) of the midpoint approximation (HAVE_CLASS builds, src/integrals.c:663-767) */
+            const gsl_spline2d *r2 = it->result2d.spline;
+            I[used].z2d = r2->xarr; I[used].values2d = r2->zarr; I[used].n_z2d = (int)r2->xsize;
+        }
         if (it->n == 4 && it->l == 0 && it->state_n == COFFE_INTEGER && it->renormalization.spline) {      /* src/integrals.c:773-914 */
             const gsl_spline2d *r = it->renormalization.spline;
             T.renorm_chi = r->xarr; T.renorm_z = r->zarr; T.n_renorm = (int)r->xsize;

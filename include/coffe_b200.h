@@ -70,6 +70,12 @@ typedef struct coffe_b200_integral {
     int n, l;
     int half_integer;            /* COFFE_HALF_INTEGER family (flat-sky closed forms) */
     coffe_b200_spline result;
+    /* optional coffe_integral_t.result2d (src/integrals.h:29-30), the table I^n_l(z, r) the reference builds from P(k, z) when it is
+       compiled with CLASS and pk_type != linear with midpoint_approximation (src/integrals.c:663-767): n_z2d redshift knots
+       (gsl_spline2d->xarr), values2d[j*n_z2d + i] <-> (z2d[i], result.x[j]) (->zarr); n_z2d = 0 when absent */
+    const double *z2d;
+    const double *values2d;
+    int n_z2d;
 } coffe_b200_integral;
 
 typedef struct coffe_b200_tables {
@@ -93,6 +99,10 @@ typedef struct coffe_b200_options {
     int den, rsd, len, d1, d2, g1, g2, g3, g4, g5;
     int only_cross_correlations;
     int flatsky_local, flatsky_local_nonlocal, flatsky_nonlocal;
+    /* par->pk_type != COFFE_PK_LINEAR && par->midpoint_approximation (src/functions.c:136-155 and the same pattern in every standard
+       term): den, rsd, d1 and len auto- and cross-terms read I^n_l((z_a + z_b)/2, r) from the 2-D tables instead of
+       D1(z_a) D1(z_b) I^n_l(r); needs result2d of the eight family tables.  Not combined with the flat-sky switches. */
+    int midpoint;
 } coffe_b200_options;
 
 /* fixed-node quadrature sizes (0 = keep the library default); DESIGN.md holds the convergence evidence.
@@ -214,6 +224,11 @@ typedef struct coffe_b200_integrals_params {
     double chi_max;              /* end of the renormalisation grid: chi(max(z_mean + deltaz)), src/integrals.c:858-871 */
 } coffe_b200_integrals_params;
 
+/* the 2-D tables I^n_l(z, r) of the same (n, l) list from P(k, z_i) rows on the knots pk_k (what coffe_integrals_init adds per table under
+   HAVE_CLASS, src/integrals.c:663-767: one 2-FAST transform + small-r integrals per redshift): pk2d[i*n_pk + j] = P(k_j, z_i);
+   tables2d[(t*n_r + j)*n_z + i] <-> table t at (z_i, r_j), the layout of coffe_b200_integral.values2d.  divergent is ignored. */
+int coffe_b200_integrals2d(coffe_b200_ctx *ctx, const coffe_b200_integrals_params *p, const double *pk2d, int n_z, double *tables2d);
+
 /* array sizes: knots per table, knots of I^4_0, knots per axis of the renormalisation grid */
 int coffe_b200_integrals_sizes(const coffe_b200_integrals_params *p, int *n_r, int *n_r40, int *n_renorm);
 /* r[n_r]; tables[t*n_r + i]; r40[n_r40], i40[n_r40]; renorm0[n_r40] (its knots are r40 with r40[0] replaced by 0);
@@ -221,6 +236,13 @@ int coffe_b200_integrals_sizes(const coffe_b200_integrals_params *p, int *n_r, i
    p->divergent == 0. */
 int coffe_b200_integrals(coffe_b200_ctx *ctx, const coffe_b200_integrals_params *p, double *r, double *tables,
                          double *r40, double *i40, double *renorm0, double *renorm_chi, double *renorm_z);
+
+/* ---- background: growth factor and growth rate --------------------------------------------------------
+   D1(z_i) (normalised to 1 at z = 0) and f(z_i) on the background grid z_i = 15 i/(bins - 1) of coffe_background_init
+   (src/background.c:427-480, 536-541), by the reference's own scheme: embedded RK2(3) at eps_rel = 1e-6, restarted at a = 0.05 for
+   every knot with the step size and the stepper state carried over (coffe_b200/csrc/growth_host.cpp says why the scheme matters).
+   Host arithmetic, no GPU needed.  omega_matter = Omega0_cdm + Omega0_baryon. */
+int coffe_b200_background_growth(double omega_matter, double w0, double wa, int bins, double *D1, double *f);
 
 /* Tracing: with COFFE_B200_TRACE set in the environment the multipole entry points print the host phases of a call on
    stderr (range checks, uploads, mu-rule construction, launches queued, result fetched).  The mu rules of the last call are

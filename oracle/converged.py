@@ -121,7 +121,7 @@ class ConvergedOracle:
         return float(np.sum(WW * f))
 
     def ni(self, z, sep, mu):
-        return float(self.ref.f_nonintegrated(z, mu, sep))
+        return float(np.ravel(self.ref.f_nonintegrated(z, mu, sep))[0])
 
     def corrfunc_pieces(self, z, sep, mu, want=(True, True, True)):
         return np.array([self.ni(z, sep, mu) if want[0] else 0.0,

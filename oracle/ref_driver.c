@@ -544,3 +544,68 @@ double ref_cuhre_direct(void *h, int which, double z, double sep, double mu, int
     return pre * result[0];
 }
 #endif /* COFFE_DROPIN_BUILD */
+
+#ifdef REF_HAVE_CLASS
+/* ---- third flavour only (oracle/Makefile: class): the reference compiled with -DHAVE_CLASS ------------------------------------
+ * coffe.pyx:2760-2928 (set_power_spectrum with pk_type / midpoint_approximation): runs CLASS inside the reference
+ * (parse_external_power_spectrum, src/parser.c:283-790), which also replaces par->power_spectrum by CLASS's linear P(k, z = 0) and
+ * fills the 2-D P(k, z) splines; coffe_integrals_init then adds the 2-D tables I^n_l(z, r) (src/integrals.c:663-767). */
+int ref_run_class(void *h, int pk_type, int midpoint)
+{
+    ref_state *s = h;
+    s->par.pk_type = (enum coffe_pk_type)pk_type;
+    s->par.midpoint_approximation = midpoint;
+    s->par.have_class = 1;
+    ref_invalidate(h);
+    return parse_external_power_spectrum(&s->par);
+}
+
+int ref_power_spectrum_size(void *h) { ref_state *s = h; return (int)s->par.power_spectrum.spline->size; }
+void ref_power_spectrum_table(void *h, double *k, double *pk)
+{
+    ref_state *s = h;
+    const gsl_spline *sp = s->par.power_spectrum.spline;
+    memcpy(k, sp->x, sizeof(double) * sp->size);
+    memcpy(pk, sp->y, sizeof(double) * sp->size);
+}
+double ref_k_min(void *h) { return ((ref_state *)h)->par.k_min_norm; }
+double ref_k_max(void *h) { return ((ref_state *)h)->par.k_max_norm; }
+
+/* the rows P(k_j, z_i) of par->power_spectrum2d (src/parser.c:655-709: what CLASS returned at the 100 redshifts z_i = 3 i/100, the same
+   rows coffe_integrals_init transforms into the 2-D tables): rows[i*n_k + j] */
+int ref_pk2d_nz(void *h) { ref_state *s = h; return s->par.power_spectrum2d.spline ? (int)s->par.power_spectrum2d.spline->xsize : 0; }
+void ref_pk2d_table(void *h, double *z, double *rows)
+{
+    ref_state *s = h;
+    const gsl_spline2d *sp = s->par.power_spectrum2d.spline;
+    memcpy(z, sp->xarr, sizeof(double) * sp->xsize);
+    for (size_t i = 0; i < sp->xsize; ++i)
+        for (size_t j = 0; j < sp->ysize; ++j) rows[i * sp->ysize + j] = sp->zarr[j * sp->xsize + i];
+}
+
+/* 2-D table of one (n, l): sizes, then z[nz], r[nr], values[j*nz + i] <-> (z_i, r_j)  (src/integrals.c:745) */
+int ref_integral2d_sizes(void *h, int n, int l, int *nz, int *nr)
+{
+    ref_state *s = h;
+    ref_integrals(h);
+    coffe_integral_t *it = coffe_find_integral(&s->integral, n, l, COFFE_INTEGER, COFFE_INTEGER);
+    if (!it || !it->result2d.spline) return 0;
+    *nz = (int)it->result2d.spline->xsize; *nr = (int)it->result2d.spline->ysize;
+    return 1;
+}
+void ref_integral2d_table(void *h, int n, int l, double *z, double *r, double *values)
+{
+    ref_state *s = h;
+    coffe_integral_t *it = coffe_find_integral(&s->integral, n, l, COFFE_INTEGER, COFFE_INTEGER);
+    const gsl_spline2d *sp = it->result2d.spline;
+    memcpy(z, sp->xarr, sizeof(double) * sp->xsize);
+    memcpy(r, sp->yarr, sizeof(double) * sp->ysize);
+    memcpy(values, sp->zarr, sizeof(double) * sp->xsize * sp->ysize);
+}
+double ref_integral2d_eval(void *h, int n, int l, double z, double r)
+{
+    ref_state *s = h;
+    coffe_integral_t *it = coffe_find_integral(&s->integral, n, l, COFFE_INTEGER, COFFE_INTEGER);
+    return coffe_interp_spline2d(&it->result2d, z, r);
+}
+#endif /* REF_HAVE_CLASS */

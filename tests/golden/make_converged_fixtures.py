@@ -64,7 +64,8 @@ def cached(name, fn):
 
 def job_multipoles(args):
     """one (z, sep): dict of the pieces under each integrator"""
-    tag, contributions, z, sep = args
+    tag, contributions, z, sep = args[:4]
+    with_check = args[4] if len(args) > 4 else True
     from oracle.converged import ConvergedOracle
 
     def run():
@@ -73,10 +74,11 @@ def job_multipoles(args):
         check = ConvergedOracle(ref, **RULE_CHECK)
         out = {"z": z, "sep": sep}
         out["ni"] = truth.multipoles_pieces(z, sep, LS, want=(True, False, False))[0]
-        out["si_cuhre"], out["si_cuhre_err"], out["si_cuhre_fail"] = truth.si_multipoles_cuhre(z, sep, LS, epsrel=2e-7, maxeval=20_000_000)
+        out["si_cuhre"], out["si_cuhre_err"], out["si_cuhre_fail"] = truth.si_multipoles_cuhre(z, sep, LS, epsrel=2e-7, maxeval=6_000_000)
         out["si_rule"] = truth.multipoles_pieces(z, sep, LS, want=(False, True, False))[1]
         out["di"] = truth.multipoles_pieces(z, sep, LS, want=(False, False, True))[2]
-        out["di_check"] = check.multipoles_pieces(z, sep, LS, want=(False, False, True))[2]
+        # the second rule size of the 3-D piece (the oracle's own convergence) on a quarter of the points: it is a third of the cost
+        out["di_check"] = check.multipoles_pieces(z, sep, LS, want=(False, False, True))[2] if with_check else np.full(len(LS), np.nan)
         return out
     return cached(f"{tag}_z{z:.10f}_s{sep:.10f}", run)
 
@@ -114,17 +116,19 @@ def cfg5_points():
 
 def make_cfg5(pool):
     z, sep, iz, ir = cfg5_points()
-    res = pool.map(job_multipoles, [("cfg5", ALL, float(z[a]), float(sep[b])) for a, b in zip(iz, ir)], chunksize=1)
+    res = pool.map(job_multipoles, [("cfg5", ALL, float(z[a]), float(sep[b]), k % 4 == 0) for k, (a, b) in enumerate(zip(iz, ir))], chunksize=1)
     pieces = np.array([[r["ni"], r["si_cuhre"], r["di"]] for r in res])             # [k, piece, l]
     scale = np.max(np.abs(pieces.sum(1)), axis=1, keepdims=True)
     si_scale = np.max(np.abs(pieces[:, 1]), axis=1, keepdims=True)
     di_scale = np.max(np.abs(pieces[:, 2]), axis=1, keepdims=True)
     si_rule = np.array([r["si_rule"] for r in res])
     di_check = np.array([r["di_check"] for r in res])
-    self_err = np.maximum(np.abs(pieces[:, 1] - si_rule), np.abs(pieces[:, 2] - di_check)) / scale
-    self_err_pieces = np.stack([np.abs(pieces[:, 1] - si_rule) / si_scale, np.abs(pieces[:, 2] - di_check) / di_scale], axis=1)
+    checked = np.isfinite(di_check[:, 0])
+    di_dev = np.where(checked[:, None], np.abs(pieces[:, 2] - np.nan_to_num(di_check)), 0.0)
+    self_err = np.maximum(np.abs(pieces[:, 1] - si_rule), di_dev) / scale
+    self_err_pieces = np.stack([np.abs(pieces[:, 1] - si_rule) / si_scale, di_dev / di_scale], axis=1)
     cuhre_err = np.array([r["si_cuhre_err"] for r in res])
-    print(f"cfg5: {len(res)} points; oracle self error (of the point scale) max {self_err.max():.2e}; per piece (SI Cuhre vs rule, DI two rule sizes) "
+    print(f"cfg5: {len(res)} points ({int(checked.sum())} with the second rule size of the 3-D piece); oracle self error (of the point scale) max {self_err.max():.2e}; per piece (SI Cuhre vs rule, DI two rule sizes) "
           f"{self_err_pieces[:, 0].max():.2e} {self_err_pieces[:, 1].max():.2e}; Cuhre's own estimate max {cuhre_err.max():.2e}, "
           f"budget exhausted on {int(sum(np.any(r['si_cuhre_fail']) for r in res))} points")
     np.savez_compressed(ROOT / "tests" / "golden" / "converged_cfg5.npz", iz=iz, ir=ir, z=z[iz], sep=sep[ir], l=np.array(LS), pieces=pieces,

@@ -44,6 +44,7 @@ def test_struct_layouts_match_header():
         fields += [n.strip() for n in names.split(",")]
     assert fields == [n for n, _ in capi.Quadrature._fields_]
     body = re.search(r"typedef struct coffe_b200_options \{(.*?)\} coffe_b200_options;", text, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     fields = []
     for decl in body.split(";"):
         decl = decl.strip()

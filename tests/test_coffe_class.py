@@ -131,12 +131,13 @@ def test_background(golden):
 
 
 def test_background_matches_reference_tables(ref):
-    """every table of coffe_background_init against the reference's own (oracle): exact for the algebraic ones, within
-    the reference's ODE step control (1e-6) for D1 and f"""
+    """every table of coffe_background_init against the reference's own (oracle): exact for the algebraic ones; D1 and f come from
+    the reference's own ODE scheme restated in the library (coffe_b200_background_growth) and agree to the reproducibility of that
+    scheme under rounding (its step-size decisions amplify 1e-16 to 1e-7); a converged ODE solution would be off by 2e-6"""
     cosmo = Coffe()
     cosmo.comoving_distance(1.0)
     for name, tol in (("a", 1e-15), ("Hz", 1e-14), ("conformal_Hz", 1e-14), ("conformal_Hz_prime", 1e-10), ("comoving_distance", 1e-12),
-                      ("D1", 5e-6), ("f", 1e-5), ("G1", 1e-8), ("G2", 1e-8)):
+                      ("D1", 2e-7), ("f", 1e-6), ("G1", 1e-8), ("G2", 1e-8)):
         x, y = ref.background_table(name)
         mx, my = cosmo._background[name]
         ok = np.isfinite(y) & (x > 0)
@@ -146,7 +147,7 @@ def test_background_matches_reference_tables(ref):
     x, y = ref.background_table("f")
     mx, my = cosmo._background["f"]
     sel = (x > 0.4) & (x < 2.5)
-    assert np.max(np.abs(my[sel] / y[sel] - 1)) < 2e-6          # where the signal is evaluated
+    assert np.max(np.abs(my[sel] / y[sel] - 1)) < 8e-7          # where the signal is evaluated
 
 
 # ---- device side (tests/test_coffe.py:208-470) -----------------------------------------------------------------
@@ -307,8 +308,10 @@ def test_average_covariance_multipoles(golden):
 @pytest.mark.gpu
 def test_class_matches_engine_on_reference_tables(engine, ref):
     """End to end with the package's own tables (host background + coffe_b200_integrals) against the same kernels fed
-    the reference's tables: what the table construction contributes to the error budget.  The reference's own
-    tables carry its QAG tolerance (1e-5) and ODE step control (1e-6)."""
+    the reference's tables: what the table construction contributes to the error budget ("same inputs" = P(k) + cosmology, not
+    pre-built tables).  Attribution table by table: tools/attribute_tables.py (profiles/r2_attribute_tables.log) -- before the
+    growth ODE followed the reference's scheme the whole deviation (5e-6) came from D1 and f; the I^n_l, I^4_0 and renormalisation
+    tables contribute < 1e-10 although they differ from the reference's by its QAG tolerance."""
     ALL = list(CONTRIBUTIONS)
     sep = np.array([10.0, 20.0, 40.0, 100.0, 150.0]) / h
     z = [0.5, 1.0, 1.5, 2.0]
@@ -318,5 +321,5 @@ def test_class_matches_engine_on_reference_tables(engine, ref):
     engine.set_options(ALL)
     want = engine.multipoles(z, sep, [0, 2, 4])
     dev = np.abs(got / want - 1)
-    assert np.all(dev < 5e-5), dev.max()
-    assert np.median(dev) < 1e-5
+    assert np.all(dev < 3e-6), dev.max()
+    assert np.median(dev) < 5e-7
