@@ -59,7 +59,8 @@ class Quadrature(C.Structure):
                 ("panel_width", C.c_double), ("panel_uniform_extent", C.c_double), ("eps_min", C.c_double),
                 ("tail_ratio", C.c_double),
                 ("n_mu_panel_di", C.c_int), ("panel_width_di", C.c_double), ("panel_uniform_extent_di", C.c_double),
-                ("mu_panel_width_di", C.c_double), ("tail_ratio_di", C.c_double), ("geometric_shift_di", C.c_int)]
+                ("mu_panel_width_di", C.c_double), ("tail_ratio_di", C.c_double), ("geometric_shift_di", C.c_int),
+                ("accuracy_target", C.c_int)]
 
 
 class CovarianceParams(C.Structure):

@@ -32,7 +32,9 @@ struct coffe_b200_ctx {
     double omega_matter = 0, h = 0;
     /* options / quadrature */
     Options o;
-    QuadConfig qc;
+    QuadConfig qc;          /* rules in force: library defaults for the accuracy target, overridden by user_q where it is non-zero */
+    coffe_b200_quadrature user_q = {};    /* what coffe_b200_set_quadrature was given (zeros = library default) */
+    int target_in_force = 1;              /* COFFE_B200_TARGET_PIECE / _TOTAL behind qc */
     /* the mu rules of the last call, one slot per integrated piece: they depend on the separations and the quadrature
        configuration only, and building them (two rules per separation, ~100 nodes of asin / cos / sin each) was 8 of the 9 ms of
        host work of a cfg5 call -- a sweep over cosmologies or redshifts on a fixed separation grid builds them once */

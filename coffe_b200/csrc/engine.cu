@@ -192,6 +192,11 @@ struct SIWarpState {
 
 constexpr int kSIThreads = 384;
 
+/* WARP_PANELS: panel bookkeeping of the two 1-D integrals held by the warp (item.cuh: si_half_partial_warp); the host selects it when
+   the configured plan never has more than 63 panels on a side (default: at most 36).  Per warp: one renormalisation column
+   (tables.cuh: ren_col_fill -- renormalisation(lambda, chi_source) collapsed onto lambda once per half, so a node costs one 1-D
+   Hermite lookup in shared memory instead of a 16-term bicubic patch through L2), then its state and the scalar path's panel list. */
+template <bool WARP_PANELS>
 __global__ void __launch_bounds__(kSIThreads, 1) si_items_smem_kernel(
     const __grid_constant__ Tables t, const __grid_constant__ Options o, const __grid_constant__ Rules q_in,
     const __grid_constant__ CompactHeader ch, const uint4 *__restrict__ blob, const int stage_bytes,
@@ -203,10 +208,13 @@ __global__ void __launch_bounds__(kSIThreads, 1) si_items_smem_kernel(
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int n_warps = kSIThreads / 32;
-    /* layout: [compact blob prefix][line-of-sight table][tail powers, panel rule][per-warp state][per-warp panel lists] */
+    const int n_col_max = t.has_divergent ? t.ren2d.n : 0;
+    /* layout: [compact blob prefix][line-of-sight table][tail powers, panel rule][per-warp columns][per-warp state][per-warp panel lists] */
     double2 *los_s = reinterpret_cast<double2 *>(smem + stage_bytes);
     double *small = reinterpret_cast<double *>(los_s + (size_t)kLosStride * los_stage_n);
-    SIWarpState *ws_all = reinterpret_cast<SIWarpState *>(small + kDISmallDoubles);
+    double2 *cols = reinterpret_cast<double2 *>(small + kDISmallDoubles);
+    double2 *col = cols + (size_t)warp * n_col_max;
+    SIWarpState *ws_all = reinterpret_cast<SIWarpState *>(cols + (size_t)n_warps * n_col_max);
     double *scratch = reinterpret_cast<double *>(ws_all + n_warps) + (size_t)warp * 2 * panel_cap;
     {
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
@@ -238,7 +246,11 @@ __global__ void __launch_bounds__(kSIThreads, 1) si_items_smem_kernel(
         const int p = item_point[item];
         const double z = pz[p], sep = psep[p], mu = item_mu[item];
         const Geometry g = geometry(bg_chi(t.bg, z), sep, mu);
-        if (lane < 2) ws.e[lane] = end_eval(o, t, lane == 0 ? g.chi1 : g.chi2, lane + 1);
+        if (lane < 2) {
+            /* redshift of the end point from the staged line-of-sight table (fifth slot), not from a bisection of z(chi) through L2 */
+            const double chi_e = lane == 0 ? g.chi1 : g.chi2;
+            ws.e[lane] = end_eval_at(o, t, chi_e, los_z(los_s, lv.n, lv.inv_h, chi_e), lane + 1);
+        }
         __syncwarp();
         if (lane < 2) ws.h[lane] = si_half_setup(o, g, ws.e[lane], ws.e[1 - lane], lane == 0);
         __syncwarp();
@@ -247,6 +259,17 @@ __global__ void __launch_bounds__(kSIThreads, 1) si_items_smem_kernel(
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
             const SIHalf h = ws.h[half];
+            if (h.need_ren) {
+                __syncwarp();           /* the previous half's readers are done */
+                ta.n_col = ren_row_count(t.ren2d, h.co);
+                ren_col_fill(t.ren2d, h.cs, ta.n_col, col, lane, 32);
+                ta.col = col;
+                __syncwarp();
+            }
+            else ta.col = nullptr;
+#if defined(__CUDA_ARCH__)
+            if (WARP_PANELS) { si += si_half_partial_warp(ta, lv, q, g, h, los_s, lane); continue; }
+#endif
             si += si_half_partial(ta, lv, q, g, h, los_s, lane, 32, scratch);
         }
         si = warp_sum(si);
@@ -313,7 +336,10 @@ __global__ void __launch_bounds__(kDIThreads, 1) di_items_smem_kernel(
         const int p = item_point[item];
         const double z = pz[p], sep = psep[p], mu = item_mu[item];
         const Geometry g = geometry(bg_chi(t.bg, z), sep, mu);
-        if (lane < 2) ws.e[lane] = end_eval(o, t, lane == 0 ? g.chi1 : g.chi2, lane + 1);
+        if (lane < 2) {
+            const double chi_e = lane == 0 ? g.chi1 : g.chi2;
+            ws.e[lane] = end_eval_at(o, t, chi_e, los_z(los_s, t.los.n, t.los.inv_h, chi_e), lane + 1);
+        }
         __syncwarp();
         if (lane == 0) ws.k = di_setup(o, ws.e[0], ws.e[1]);
         __syncwarp();
@@ -474,6 +500,37 @@ Rules make_rules(const coffe_b200_ctx *ctx)
     return q;
 }
 
+/* (re)derive the rules in force: defaults of the accuracy target, then the caller's non-zero knobs.  want_pieces: the call returns
+   the pieces themselves (coffe_integrate per flag_integral), which an automatic target always serves at piece accuracy. */
+int apply_quadrature(coffe_b200_ctx *ctx, const bool want_pieces)
+{
+    int target = ctx->user_q.accuracy_target;
+    if (target != COFFE_B200_TARGET_PIECE && target != COFFE_B200_TARGET_TOTAL)
+        target = (!want_pieces && (ctx->o.den || ctx->o.rsd) && !ctx->o.midpoint) ? COFFE_B200_TARGET_TOTAL : COFFE_B200_TARGET_PIECE;
+    const QuadConfig merged = merge_quadrature(target == COFFE_B200_TARGET_TOTAL ? total_target_quadrature() : default_quadrature(), ctx->user_q);
+    if (!quadrature_valid(merged, kMaxPanels)) {
+        ctx->err = "quadrature sizes out of range (node counts 2..128; the line-of-sight panel plan must fit " + std::to_string(kMaxPanels) + " panels)";
+        return COFFE_B200_EINVAL;
+    }
+    if (std::memcmp(&merged, &ctx->qc, sizeof(QuadConfig)) == 0 && target == ctx->target_in_force) return COFFE_B200_OK;
+    if (merged.tail_ratio != ctx->qc.tail_ratio) {
+        const std::vector<double> rp = build_rpow(merged.tail_ratio);
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaMemcpyAsync(ctx->d_rpow, rp.data(), kMaxTail * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (merged.tail_ratio_di != ctx->qc.tail_ratio_di) {
+        const std::vector<double> rp = build_rpow(merged.tail_ratio_di);
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaMemcpyAsync(ctx->d_rpow_di, rp.data(), kMaxTail * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->qc = merged;
+    ctx->target_in_force = target;
+    ctx->generation++;
+    return COFFE_B200_OK;
+}
+
 /* host-side range check of one point: the reference aborts (non-finite integrand) outside the tables */
 int check_point(coffe_b200_ctx *ctx, const double z, const double sep, const bool need_renorm)
 {
@@ -566,7 +623,11 @@ int launch_integrated(coffe_b200_ctx *ctx, Batch &b, const int mode, unsigned in
         ch.n_knots = (stage_bytes - ch.off_knots) / kKnotBytes;
         const int panel_cap = max_panels(ctx->qc);
         const size_t fixed = (size_t)stage_bytes + los_bytes + kDISmallDoubles * sizeof(double);
-        const size_t per_warp = mode == 1 ? sizeof(SIWarpState) + (size_t)2 * panel_cap * sizeof(double) : sizeof(DIWarpState) + row_bytes;
+        /* the local x integrated kernel is compiled for a fixed warp count: the scalar path's panel lists are dropped when the
+           warp-held bookkeeping is selected (they would not fit next to the renormalisation columns) */
+        const bool si_warp_panels = ctx->qc.n_panel_si <= 32 && si_side_panels(ctx->qc, std::max(2.0e4, 1.01 * ctx->layout.chi_max_table)) <= 63;
+        const size_t per_warp = mode == 1 ? sizeof(SIWarpState) + row_bytes + (si_warp_panels ? 0 : (size_t)2 * panel_cap * sizeof(double))
+                                          : sizeof(DIWarpState) + row_bytes;
         /* as many warps per SM as the remaining shared memory carries (the kernels are latency-bound: more is faster) */
         int warps = mode == 1 ? kSIThreads / 32 : kDIThreads / 32;
         if (mode == 2 && fixed < (size_t)ctx->smem_optin) warps = std::min<int>(warps, (int)(((size_t)ctx->smem_optin - fixed) / per_warp));
@@ -577,10 +638,11 @@ int launch_integrated(coffe_b200_ctx *ctx, Batch &b, const int mode, unsigned in
             int grid = std::min(ctx->n_sm, (L.n + warps - 1) / warps);
             if (grid < 1) grid = 1;
             if (mode == 1) {
-                CK(cudaFuncSetAttribute(si_items_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-                si_items_smem_kernel<<<grid, threads, need, ctx->stream>>>(
+                auto kernel = si_warp_panels ? si_items_smem_kernel<true> : si_items_smem_kernel<false>;
+                CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+                kernel<<<grid, threads, need, ctx->stream>>>(
                     ctx->t, ctx->o, make_rules(ctx), ch, reinterpret_cast<const uint4 *>(ctx->d_blob), stage_bytes, b.pz.p, b.psep.p,
-                    L.point.p, L.mu.p, L.n, stage_n, panel_cap, L.val.p, evals, ctx->d_counter);
+                    L.point.p, L.mu.p, L.n, stage_n, si_warp_panels ? 0 : panel_cap, L.val.p, evals, ctx->d_counter);
             }
             else {
                 const bool warp_panels = ctx->qc.n_panel_di <= 32 &&
@@ -747,6 +809,14 @@ int check_l(coffe_b200_ctx *ctx, const int *l, const int n_l)
 }
 
 }  // namespace
+
+/* the *_pieces entry points: piece-accuracy rules for the duration of the call (see coffe_b200_quadrature.accuracy_target) */
+struct PieceRules {
+    coffe_b200_ctx *ctx;
+    int rc;
+    explicit PieceRules(coffe_b200_ctx *c) : ctx(c), rc(apply_quadrature(c, true)) {}
+    ~PieceRules() { apply_quadrature(ctx, false); }
+};
 
 /* a prepared multipole computation: the (z, r) items [begin, end) with their mu rules resident in HBM */
 struct coffe_b200_plan {
@@ -1033,31 +1103,19 @@ int coffe_b200_set_options(coffe_b200_ctx *ctx, const coffe_b200_options *opt)
     o.flatsky_nonlocal = opt->flatsky_nonlocal != 0;
     o.midpoint = opt->midpoint != 0;
     ctx->generation++;
-    return COFFE_B200_OK;
+    return apply_quadrature(ctx, false);
 }
 
 int coffe_b200_set_quadrature(coffe_b200_ctx *ctx, const coffe_b200_quadrature *q)
 {
     if (!ctx || !q) return COFFE_B200_EINVAL;
     COFFE_ENTER(ctx);
-    const QuadConfig merged = merge_quadrature(default_quadrature(), *q);
-    if (!quadrature_valid(merged, kMaxPanels)) {
-        ctx->err = "quadrature sizes out of range (node counts 2..128; the line-of-sight panel plan must fit " + std::to_string(kMaxPanels) + " panels)";
-        return COFFE_B200_EINVAL;
-    }
-    if (merged.tail_ratio != ctx->qc.tail_ratio) {
-        const std::vector<double> rp = build_rpow(merged.tail_ratio);
-        CK(cudaSetDevice(ctx->device));
-        CK(cudaMemcpy(ctx->d_rpow, rp.data(), kMaxTail * sizeof(double), cudaMemcpyHostToDevice));
-    }
-    if (merged.tail_ratio_di != ctx->qc.tail_ratio_di) {
-        const std::vector<double> rp = build_rpow(merged.tail_ratio_di);
-        CK(cudaSetDevice(ctx->device));
-        CK(cudaMemcpy(ctx->d_rpow_di, rp.data(), kMaxTail * sizeof(double), cudaMemcpyHostToDevice));
-    }
-    ctx->qc = merged;
-    ctx->generation++;
-    return COFFE_B200_OK;
+    if (q->accuracy_target < 0 || q->accuracy_target > 2) { ctx->err = "accuracy_target must be 0 (automatic), 1 (piece) or 2 (total)"; return COFFE_B200_EINVAL; }
+    const coffe_b200_quadrature keep = ctx->user_q;
+    ctx->user_q = *q;
+    const int rc = apply_quadrature(ctx, false);
+    if (rc) ctx->user_q = keep;
+    return rc;
 }
 
 int coffe_b200_set_kernel_variant(coffe_b200_ctx *ctx, int variant)
@@ -1088,6 +1146,7 @@ int coffe_b200_get_quadrature(const coffe_b200_ctx *ctx, coffe_b200_quadrature *
     q->n_z = c.n_z; q->panel_width = c.panel_w; q->panel_uniform_extent = c.panel_du; q->eps_min = c.eps_min; q->tail_ratio = c.tail_ratio;
     q->n_mu_panel_di = c.n_mu_panel_di; q->panel_width_di = c.panel_w_di; q->panel_uniform_extent_di = c.panel_du_di;
     q->mu_panel_width_di = c.mu_panel_w_di; q->tail_ratio_di = c.tail_ratio_di; q->geometric_shift_di = c.geo_shift_di;
+    q->accuracy_target = ctx->target_in_force;
     return COFFE_B200_OK;
 }
 
@@ -1096,6 +1155,8 @@ int coffe_b200_multipoles_pieces(coffe_b200_ctx *ctx, const double *z_mean, int 
 {
     if (!ctx || !out) return COFFE_B200_EINVAL;
     COFFE_ENTER(ctx);
+    PieceRules pr(ctx);
+    if (pr.rc) return pr.rc;
     std::vector<double> hm;
     const int rc = multipoles_core(ctx, z_mean, n_z, sep, n_sep, l, n_l, 0, (long)n_z * n_sep, hm);
     if (rc) return rc;
@@ -1239,6 +1300,8 @@ int coffe_b200_corrfunc_range_pieces(coffe_b200_ctx *ctx, const double *z_mean, 
 {
     if (!ctx || !out) return COFFE_B200_EINVAL;
     COFFE_ENTER(ctx);
+    PieceRules pr(ctx);
+    if (pr.rc) return pr.rc;
     std::vector<double> pc;
     const int rc = corrfunc_core(ctx, z_mean, n_z, mu, n_mu, sep, n_sep, begin, end, pc);
     if (rc) return rc;
@@ -1336,6 +1399,8 @@ int coffe_b200_average_multipoles_range_pieces(coffe_b200_ctx *ctx, const double
 {
     if (!ctx || !out) return COFFE_B200_EINVAL;
     COFFE_ENTER(ctx);
+    PieceRules pr(ctx);
+    if (pr.rc) return pr.rc;
     std::vector<double> hm;
     const int rc = coffe_internal_average_core(ctx, z_min, z_max, n_bins, sep, n_sep, l, n_l, begin, end, hm);
     if (rc) return rc;
@@ -1513,6 +1578,28 @@ int coffe_b200_balance_bounds(const double *cost, long n_items, int n_parts, lon
         if (k > n_items) k = n_items;
         if (k > 0 && std::fabs(c[k] - target) > std::fabs(c[k - 1] - target)) --k;        /* the closer of the two neighbours */
         bounds[r] = std::max(k, bounds[r - 1]);
+    }
+    return COFFE_B200_OK;
+}
+
+int coffe_b200_rebalance_cost(double *cost, long n_items, int n_parts, const long *bounds, const double *part_ms)
+{
+    if (!cost || !bounds || !part_ms || n_parts < 1 || n_items < 0) return COFFE_B200_EINVAL;
+    if (bounds[0] != 0 || bounds[n_parts] != n_items) return COFFE_B200_EINVAL;
+    double total_cost = 0, total_ms = 0;
+    std::vector<double> block(n_parts, 0.0);
+    for (int r = 0; r < n_parts; ++r) {
+        if (bounds[r + 1] < bounds[r] || !(part_ms[r] >= 0.0)) return COFFE_B200_EINVAL;
+        for (long i = bounds[r]; i < bounds[r + 1]; ++i) block[r] += cost[i];
+        total_cost += block[r]; total_ms += part_ms[r];
+    }
+    if (!(total_cost > 0.0) || !(total_ms > 0.0)) return COFFE_B200_OK;
+    for (int r = 0; r < n_parts; ++r) {
+        if (!(block[r] > 0.0) || !(part_ms[r] > 0.0)) continue;
+        /* time per unit cost of this block relative to the average; damped so that one noisy measurement cannot overshoot */
+        double s = (part_ms[r] / block[r]) / (total_ms / total_cost);
+        s = std::min(1.25, std::max(0.8, s));
+        for (long i = bounds[r]; i < bounds[r + 1]; ++i) cost[i] *= s;
     }
     return COFFE_B200_OK;
 }

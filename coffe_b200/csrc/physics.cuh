@@ -50,11 +50,19 @@ struct EndVals {
     double phi_auto[3];
 };
 
+COFFE_HD EndVals end_eval_at(const Options &o, const Tables &t, const double chi, const double z, const int which);
+
 COFFE_HD EndVals end_eval(const Options &o, const Tables &t, const double chi, const int which /* 1 or 2 */)
+{
+    return end_eval_at(o, t, chi, spline_eval(t.bg.z_of_chi, chi), which);
+}
+
+/* the same with the redshift of the end point supplied by the caller (kernels: from the line-of-sight table in shared memory) */
+COFFE_HD EndVals end_eval_at(const Options &o, const Tables &t, const double chi, const double z, const int which /* 1 or 2 */)
 {
     EndVals e;
     e.chi = chi;
-    e.z = spline_eval(t.bg.z_of_chi, chi);
+    e.z = z;
     const BackgroundAtZ b = bg_eval_all(t.bg, e.z);
     e.a = b.a; e.Hc = b.Hc; e.D1 = b.D1; e.f = b.f;
     e.G = (which == 1) ? b.G1 : b.G2;
@@ -311,8 +319,8 @@ COFFE_HD double si_half_eval(const TA &t, const SIHalf &h, const Geometry &g, co
     if (rr < 0) rr = 0;
     const double iR = rr > 0.0 ? COFFE_RSQRT(rr) : 0.0;
     const double R = rr * iR;
-    double I[N_ITAB];
-    t.ifam_all(R, I);
+    double I[N_ITAB9];
+    t.ifam9(R, I, h.need_ren != 0);          /* the eight I^n_l and, for the renormalised potential terms, I^4_0 in the same lookup */
     const double W = los.x, V = los.y, Wa = los.w;
     double res = 0.0;
     /* Midpoint approximation (src/functions.c:1626-1700, 2061-2326, 2492-2918): den-len, rsd-len and d1-len read
@@ -374,7 +382,7 @@ COFFE_HD double si_half_eval(const TA &t, const SIHalf &h, const Geometry &g, co
     if (h.any_g4 || h.any_g5) {
         double ren = 0.0;
         if (h.need_ren)                                                                             /* :1524-1556 */
-            ren = (rr == 0.0) ? t.ren0(l) : t.i40(R) - t.ren2d(l, cs);
+            ren = (rr == 0.0) ? t.ren0(l) : I[N_ITAB] - t.ren2d(l, cs);
         const double b_rsd = (2 * rr / 3. - s2 * l * l) * I[I22] - I[I20] / 3.;
         const double b_d1 = (l * c - cs) * I[I31];
         if (h.any_g4) res += W * (h.g4_i20 * I[I20] + h.g4_rsd * b_rsd + h.g4_d1 * b_d1 + h.g4_ren * ren);
@@ -523,7 +531,20 @@ COFFE_HD void los_knot(const Tables &t, const int i, const double h, const doubl
     /* dv = d (df/dlambda); h f' = 2 dv */
     out[0].x = f0.x; out[0].y = 2 * dv[0]; out[1].x = f0.y; out[1].y = 2 * dv[1];
     out[2].x = f0.z; out[2].y = 2 * dv[2]; out[3].x = f0.w; out[3].y = 2 * dv[3];
-    out[4].x = out[4].y = 0.0;
+    /* fifth slot: z(lambda) itself, {z, h dz/dlambda} -- the kernels' item set-up reads the redshift of the two end points from here
+       (one Hermite lookup in shared memory) instead of bisecting the 10^4-knot z(chi) spline through L2 */
+    {
+        const double z0 = spline_eval(t.bg.z_of_chi, lam);
+        double dz;
+        if (lam - 2 * d >= 0.0 && lam + 2 * d <= chi_max)
+            dz = (spline_eval(t.bg.z_of_chi, lam - 2 * d) - 8 * spline_eval(t.bg.z_of_chi, lam - d) + 8 * spline_eval(t.bg.z_of_chi, lam + d) - spline_eval(t.bg.z_of_chi, lam + 2 * d)) / 12.;
+        else {
+            const double sg = lam - 2 * d < 0.0 ? 1.0 : -1.0;
+            dz = sg * (-25 * z0 + 48 * spline_eval(t.bg.z_of_chi, lam + sg * d) - 36 * spline_eval(t.bg.z_of_chi, lam + sg * 2 * d)
+                       + 16 * spline_eval(t.bg.z_of_chi, lam + sg * 3 * d) - 3 * spline_eval(t.bg.z_of_chi, lam + sg * 4 * d)) / 12.;
+        }
+        out[4].x = z0; out[4].y = 2 * dz;
+    }
 }
 
 /* ---- flat-sky closed forms for the multipoles ----------------------------------------------------- */

@@ -26,6 +26,23 @@ inline QuadConfig default_quadrature()
     return q;
 }
 
+/* Defaults when the 1e-5 gate is measured against the TOTAL a call returns and the local terms (density, RSD) are on: the two
+   line-of-sight pieces are then at most a few per cent of every multipole of the benchmarked grid, and rules sized for 1e-5 of
+   each piece spend 30 % of the step on digits nobody can see.  Chosen on GPU sweeps over 2 000 (z, r) points of cfg5 against the
+   doubled rules (profiles/r2_quad_sweep_{a,b,c}.log): 6 instead of 8 nodes per inner panel of the integrated x integrated piece
+   (5 panels x 6 nodes fill 30 lanes), tail growth 3 instead of 2.5, 4 instead of 5 mu nodes per r_perp panel; 64 instead of 32 Mpc
+   mu panels, 7 instead of 8 mu nodes and 6 instead of 8 inner nodes for the local x integrated piece, first r_perp break of the mu rules
+   at 8 instead of 4 Mpc: worst total error 2.9e-6 of the l = 0..4 scale (piece rules: 6.5e-7; profiles/r2_quad_sweep_e.log), 0.49 /
+   0.47 of the evaluations.  Guarded by the dense tests of tests/test_gpu_parity.py. */
+inline QuadConfig total_target_quadrature()
+{
+    QuadConfig q = default_quadrature();
+    q.n_panel_di = 6; q.tail_ratio_di = 3.0; q.n_mu_panel_di = 4;
+    q.mu_panel_w = 64.0; q.n_mu_panel = 7; q.n_panel_si = 6;
+    q.mu_rho0 = 8.0;
+    return q;
+}
+
 inline QuadConfig merge_quadrature(const QuadConfig &base, const coffe_b200_quadrature &u)
 {
     QuadConfig q = base;
@@ -70,6 +87,17 @@ inline int di_side_panels(const QuadConfig &q, const double extent = 2.0e4)
     const int uni = (int)std::ceil(q.panel_du_di / q.panel_w_di) + 1;
     const double start = std::max(q.panel_du_di, q.panel_w_di);
     const int tail = extent > start ? (int)std::ceil(std::log(extent / start) / std::log(q.tail_ratio_di)) + 2 : 0;
+    if (tail >= kMaxTail) return 1 << 30;
+    return geo + uni + tail;
+}
+
+/* the same bound for the local x integrated plan */
+inline int si_side_panels(const QuadConfig &q, const double extent = 2.0e4)
+{
+    const int geo = q.eps_min < q.panel_w ? (int)std::ceil(std::log2(q.panel_w / q.eps_min)) + 2 : 0;
+    const int uni = (int)std::ceil(q.panel_du / q.panel_w) + 1;
+    const double start = std::max(q.panel_du, q.panel_w);
+    const int tail = extent > start ? (int)std::ceil(std::log(extent / start) / std::log(q.tail_ratio)) + 2 : 0;
     if (tail >= kMaxTail) return 1 << 30;
     return geo + uni + tail;
 }

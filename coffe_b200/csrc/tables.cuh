@@ -291,6 +291,38 @@ COFFE_HD void ren_row_fill(const Renorm2DView &t, const double x, const int n_ro
 }
 
 /* rows needed to cover second arguments up to y_max */
+/* the same collapse along the other axis: renormalisation(., y) for a fixed SECOND argument, col[i] = {value, dx d/dx} at x_i (the local x
+   integrated piece evaluates renormalisation(lambda, chi_source) with the source end fixed per half).  Reads two contiguous rows
+   of the node table; ren_row_eval(col, x) is then the bicubic patch with the sums reassociated. */
+COFFE_HD void ren_col_fill(const Renorm2DView &t, const double y, const int n_col, double2 *col, const int lane, const int nlanes)
+{
+    const double sy = (y - t.x0) * t.inv_dx;
+    int yi = (int)sy;
+    if (yi < 0) yi = 0;
+    if (yi > t.n - 2) yi = t.n - 2;
+    const double u = sy - yi, u2 = u * u, u3 = u2 * u;
+    const double h00 = 2 * u3 - 3 * u2 + 1, h10 = (u3 - 2 * u2 + u) * t.dx, h01 = -2 * u3 + 3 * u2, h11 = (u3 - u2) * t.dx;
+    const double4 *a = t.node + (size_t)yi * t.n, *b = a + t.n;
+    for (int i0 = lane; i0 < n_col; i0 += kRowInFlight * nlanes) {
+        double4 p[kRowInFlight], q[kRowInFlight];
+#pragma unroll
+        for (int v = 0; v < kRowInFlight; ++v) {
+            const int i = i0 + v * nlanes;
+            if (i < n_col) { p[v] = a[i]; q[v] = b[i]; }
+        }
+#pragma unroll
+        for (int v = 0; v < kRowInFlight; ++v) {
+            const int i = i0 + v * nlanes;
+            if (i < n_col) {
+                double2 o;
+                o.x = h00 * p[v].x + h01 * q[v].x + h10 * p[v].z + h11 * q[v].z;
+                o.y = (h00 * p[v].y + h01 * q[v].y + h10 * p[v].w + h11 * q[v].w) * t.dx;
+                col[i] = o;
+            }
+        }
+    }
+}
+
 COFFE_HD int ren_row_count(const Renorm2DView &t, const double y_max)
 {
     int n = (int)((y_max - t.x0) * t.inv_dx) + 3;
@@ -373,6 +405,18 @@ COFFE_HD void mid2d_eval_all(const Mid2DView &m, const IntegralFamilyView &fam, 
                + h10t * (h00u * n00.y + h01u * n01.y + h10u * n00.w + h11u * n01.w)
                + h11t * (h00u * n10.y + h01u * n11.y + h10u * n10.w + h11u * n11.w);
     }
+}
+
+/* z(lambda) from the fifth slot of the line-of-sight table */
+COFFE_HD double los_z(const double2 *v, const int n, const double inv_h, const double lambda)
+{
+    const double s = lambda * inv_h;
+    int j = (int)s;
+    if (j < 0) j = 0;
+    if (j > n - 2) j = n - 2;
+    const HermiteBasis b = hermite_basis(s - j);
+    const double2 p = v[(size_t)kLosStride * j + 4], q = v[(size_t)kLosStride * (j + 1) + 4];
+    return hermite_eval(b, p.x, p.y, q.x, q.y);
 }
 
 /* an I^n_l table outside the interleaved family: I^1_l (flat-sky lensing-lensing multipoles, src/integrals.c:

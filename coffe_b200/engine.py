@@ -338,6 +338,18 @@ def balance_bounds(cost, n_parts):
     return [int(v) for v in out]
 
 
+def rebalance_cost(cost, bounds, part_ms):
+    """fold the measured device time of every block into the cost of its items (coffe_b200_rebalance_cost); returns the new cost"""
+    lib = capi.load()
+    c = capi.darr(np.asarray(cost).ravel()).copy()
+    bd = (C.c_long * len(bounds))(*bounds)
+    ms = capi.darr(part_ms)
+    rc = lib.coffe_b200_rebalance_cost(capi.ptr(c), C.c_long(c.size), C.c_int(len(bounds) - 1), bd, capi.ptr(ms))
+    if rc:
+        raise ValueError("bounds must run from 0 to len(cost); times must be non-negative")
+    return c
+
+
 class Group:
     """All GPUs of the box behind one call (coffe_b200_group_*): the counterpart of the reference's OpenMP loop over the output grid."""
 

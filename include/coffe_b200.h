@@ -121,7 +121,17 @@ typedef struct coffe_b200_quadrature {
     double mu_panel_width_di;
     double tail_ratio_di;
     int geometric_shift_di;      /* log2 of the growth factor of its geometric panels: 1 = doubling, 2 = x4 */
+    /* What the 1e-5 gate is measured against, which picks the library defaults the zeros above stand for:
+       0 = automatic: COFFE_B200_TARGET_TOTAL when density or RSD is among the contributions and the call returns totals
+           (multipoles / corrfunc / average multipoles / their group and sharded forms), COFFE_B200_TARGET_PIECE otherwise and
+           always for the *_pieces entry points (a caller of coffe_integrate(flag_integral) gets each piece to 1e-5 of itself);
+       1 = COFFE_B200_TARGET_PIECE: every piece (local x local, local x integrated, integrated x integrated) within 1e-5 of its own
+           l = 0..4 scale -- what a lensing-only or cross-only configuration needs;
+       2 = COFFE_B200_TARGET_TOTAL: the returned multipole within 1e-5 of the l = 0..4 scale of the point; the integrated pieces are
+           then at most a few per cent of the total and carry coarser rules (0.7 of the evaluations). */
+    int accuracy_target;
 } coffe_b200_quadrature;
+enum { COFFE_B200_TARGET_AUTO = 0, COFFE_B200_TARGET_PIECE = 1, COFFE_B200_TARGET_TOTAL = 2 };
 
 /* ---- life cycle ---------------------------------------------------------------------------------- */
 int coffe_b200_create(int device, coffe_b200_ctx **out);
@@ -302,6 +312,12 @@ int coffe_b200_group_last_blocks(const coffe_b200_group *g, long *bounds, double
 int coffe_b200_multipoles_cost(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double *sep, int n_sep,
                                const int *l, int n_l, double *cost);
 int coffe_b200_balance_bounds(const double *cost, long n_items, int n_parts, long *bounds);
+
+/* Feedback for repeated calls on the same grid (a sweep over cosmologies): given the device time every block took, scale the cost of its
+   items by the block's measured time per unit cost (normalised so the total is unchanged), in place; the next coffe_b200_balance_bounds
+   then evens out what the evaluation count does not see (per-item and per-outer-node set-up).  Host arithmetic.  The group calls and
+   coffe_b200_multipoles_sharded(bounds = NULL) apply it themselves whenever the grid of the previous call repeats. */
+int coffe_b200_rebalance_cost(double *cost, long n_items, int n_parts, const long *bounds, const double *part_ms);
 
 /* One process per GPU (the launch torchrun / mpirun give): every rank computes its block, and the blocks are gathered device to
    device with NCCL (libnccl.so.2 is loaded on first use; grouped ncclBroadcast of the variable-size blocks, issued on the compute

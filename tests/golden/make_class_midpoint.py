@@ -49,13 +49,31 @@ store["sample_z"], store["sample_r"] = zs, rs
 store["sample_i2d"] = np.array([[[r.lib.ref_integral2d_eval(r.h_, C.c_int(nn), C.c_int(ll), C.c_double(a), C.c_double(b)) for b in rs] for a in zs]
                                 for (nn, ll) in FAMILY])
 store["stock_multipoles"] = r.multipoles()
-co = ConvergedOracle(r, n_outer=64, n_panel=8, mu_kw=dict(n=6, W=24.0))
+# exact knot values of the reference's 2-D tables on a sub-grid (no interpolation involved on either side): pins the product's builder
+nzr, nrr = C.c_int(), C.c_int()
+kz = np.array([0, 27, 40, 60, 99]); kr = None
+knots = []
+for (nn, ll) in FAMILY:
+    r.lib.ref_integral2d_sizes(r.h_, C.c_int(nn), C.c_int(ll), C.byref(nzr), C.byref(nrr))
+    zz_, rr_, vv_ = np.empty(nzr.value), np.empty(nrr.value), np.empty(nzr.value * nrr.value)
+    r.lib.ref_integral2d_table(r.h_, C.c_int(nn), C.c_int(ll), zz_.ctypes.data_as(O.dp), rr_.ctypes.data_as(O.dp), vv_.ctypes.data_as(O.dp))
+    if kr is None:
+        kr = np.unique(np.concatenate([np.arange(0, 44), np.arange(44, nrr.value, 37)]))
+    knots.append(vv_.reshape(nrr.value, nzr.value)[np.ix_(kr, kz)])
+store["knot_z_idx"], store["knot_r_idx"], store["knot_r"], store["knot_values"] = kz, kr, rr_[kr], np.array(knots)
+# converged pieces: local x integrated by Cuhre called directly on the reference's integrand (scheme-independent, 2e-7), integrated x
+# integrated by oracle/converged.py at its larger rule size (the fixed rule's own local x integrated value is kept for comparison)
+co = ConvergedOracle(r, n_outer=96, n_panel=10, mu_kw=dict(n=8, W=16.0))
 conv = np.zeros((len(Z_MEAN), len(SEP), 3, len(LS)))
+si_rule = np.zeros((len(Z_MEAN), len(SEP), len(LS)))
+si_err = np.zeros((len(Z_MEAN), len(SEP), len(LS)))
 for iz, zz in enumerate(Z_MEAN):
     for ir, ss in enumerate(SEP):
         conv[iz, ir] = co.multipoles_pieces(zz, float(ss), LS)
-        print(zz, ss * H, conv[iz, ir].sum(0), store["stock_multipoles"][iz, :, ir], flush=True)
-store["converged_pieces"] = conv
+        si_rule[iz, ir] = conv[iz, ir, 1]
+        conv[iz, ir, 1], si_err[iz, ir], _ = co.si_multipoles_cuhre(zz, float(ss), LS, epsrel=2e-7, maxeval=10_000_000)
+        print(zz, ss * H, conv[iz, ir].sum(0), store["stock_multipoles"][iz, :, ir], "SI rule vs Cuhre", np.abs(si_rule[iz, ir] - conv[iz, ir, 1]) / np.abs(conv[iz, ir, 1]).max(), flush=True)
+store["converged_pieces"], store["si_rule"], store["si_cuhre_rel_error_estimate"] = conv, si_rule, si_err
 # the same integrands WITHOUT the midpoint approximation (linear D1 D1 I(r) with CLASS's linear spectrum): how much the layer moves the result
 out = ROOT / "tests" / "golden" / "class_midpoint.npz"
 np.savez_compressed(out, **store)

@@ -68,6 +68,7 @@ void *hs_create(const coffe_b200_tables *T, const coffe_b200_options *opt)
     o.g1 = opt->g1; o.g2 = opt->g2; o.g3 = opt->g3; o.g4 = opt->g4; o.g5 = opt->g5;
     o.only_cross = opt->only_cross_correlations;
     o.flatsky_local = opt->flatsky_local; o.flatsky_local_nonlocal = opt->flatsky_local_nonlocal; o.flatsky_nonlocal = opt->flatsky_nonlocal;
+    o.midpoint = opt->midpoint;
     o.divergent = s->layout.has_divergent;
     o.out_multipoles = 1;
     o.Om = T->omega_matter; o.H0h = T->h / 2997.92458;
@@ -156,6 +157,7 @@ double hs_si(void *h, double z, double mu, double sep, double x, int exact)
     const double4 losb = exact ? los_point(s->t, lb) : los_eval(s->t.los.v, s->t.los.n, s->t.los.inv_h, lb);
     if (s->variant) { const CompactAccess ca = s->compact(); return si_half_eval(ca, ha, g, la, losa) + si_half_eval(ca, hb, g, lb, losb); }
     const ExactAccess ea{&s->t};
+    if (s->o.midpoint) return si_half_eval<true>(ea, ha, g, la, losa) + si_half_eval<true>(ea, hb, g, lb, losb);
     return si_half_eval(ea, ha, g, la, losa) + si_half_eval(ea, hb, g, lb, losb);
 }
 

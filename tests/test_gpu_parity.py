@@ -85,7 +85,11 @@ def test_corrfunc_kernels_reproduce_cpu_evaluation(engine, ref, tableset):
     hs = hostsim_bridge.HostSim(ref, list(ALL), tableset=tableset)
     engine.set_options(ALL)
     mus = [-0.9, 0.0, 0.3, 0.97, 0.9995]
-    got = engine.corrfunc([1.0], mus, [15.0, 224.0])[0]
+    engine.set_quadrature(accuracy_target=1)          # the CPU harness runs the piece-accuracy rules (default_quadrature)
+    try:
+        got = engine.corrfunc([1.0], mus, [15.0, 224.0])[0]
+    finally:
+        engine.set_quadrature()
     for im, mu in enumerate(mus):
         for ir, s in enumerate((15.0, 224.0)):
             want = hs.item(1.0, s, mu).sum()
@@ -198,7 +202,7 @@ def test_mu_rule_cache_follows_separations_and_quadrature(engine):
         c = engine.multipoles(z, sa, l)
         assert not np.array_equal(c, a1) and np.all(np.abs(c / a1 - 1) < 1e-5)
     finally:
-        engine.set_quadrature(**q0)
+        engine.set_quadrature()             # back to the library defaults of the accuracy target (zeros = default)
     assert np.array_equal(engine.multipoles(z, sa, l), a1)
 
 
@@ -467,8 +471,16 @@ def test_pieces_add_up_and_terms_are_bilinear(engine):
     engine.set_options(["rsd"]); rsd = engine.multipoles(z, s, [0, 2, 4])
     engine.set_options(["den", "rsd"], only_cross=True); cross = engine.multipoles(z, s, [0, 2, 4])
     assert np.allclose(both, den + rsd + cross, rtol=1e-12, atol=1e-18)
-    engine.set_options(ALL); pieces = engine.multipoles_pieces(z, s, [0, 2, 4]); tot = engine.multipoles(z, s, [0, 2, 4])
+    # the pieces entry point runs the piece-accuracy rules; pinned to the same target the total is their sum to the last bits, under the
+    # automatic target (rules sized for the total) it agrees with it within the gate
+    engine.set_options(ALL); pieces = engine.multipoles_pieces(z, s, [0, 2, 4]); auto = engine.multipoles(z, s, [0, 2, 4])
+    engine.set_quadrature(accuracy_target=1)
+    try:
+        tot = engine.multipoles(z, s, [0, 2, 4])
+    finally:
+        engine.set_quadrature()
     assert np.array_equal(pieces.sum(0), tot) or np.allclose(pieces.sum(0), tot, rtol=1e-15)
+    assert np.all(np.abs(auto - tot) < 1e-5 * np.max(np.abs(tot), axis=1, keepdims=True))
 
 
 def test_odd_multipoles_of_symmetric_terms_vanish(engine):
@@ -489,8 +501,17 @@ def test_quadrature_self_convergence_on_a_wide_grid(engine):
                           panel_uniform_extent=640.0, panel_width_di=16.0, panel_uniform_extent_di=640.0, mu_panel_width_di=16.0, tail_ratio=1.3, tail_ratio_di=1.3, geometric_shift_di=1, n_mu_ni=64)
     fine = engine.multipoles(z, s, [0, 2, 4])
     engine.set_quadrature()
-    err = np.abs(base / fine - 1)
+    err = np.abs(base - fine) / np.max(np.abs(fine), axis=1, keepdims=True)
     assert np.all(err < 1e-5), err
+    # the same at piece accuracy (what a lensing-only caller gets): every piece within 1e-5 of its own scale
+    engine.set_quadrature(accuracy_target=1)
+    pb = engine.multipoles_pieces(z, s, [0, 2, 4])
+    engine.set_quadrature(accuracy_target=1, n_mu_panel=12, n_mu_panel_di=10, mu_panel_width=16.0, n_outer=96, n_panel_si=12, n_panel_di=12, panel_width=8.0,
+                          panel_uniform_extent=640.0, panel_width_di=16.0, panel_uniform_extent_di=640.0, mu_panel_width_di=16.0, tail_ratio=1.3, tail_ratio_di=1.3, geometric_shift_di=1, n_mu_ni=64)
+    pf = engine.multipoles_pieces(z, s, [0, 2, 4])
+    engine.set_quadrature()
+    perr = np.abs(pb - pf) / np.max(np.abs(pf), axis=2, keepdims=True)
+    assert np.all(perr < 1e-5), perr.max(axis=(1, 2, 3))
 
 
 def test_errors_are_reported_not_fatal(engine, tableset):
@@ -676,6 +697,12 @@ def test_cfg5_matches_converged_oracle_fixture():
     err = np.abs(tot_g - tot_w) / scale
     k = np.unravel_index(np.argmax(err), err.shape)
     assert err.max() < 1e-5, (err.max(), z[iz[k[0]]], sep[ir[k[0]]] * H, ls[k[1]])
+    # what the benchmark times: the plain total call under the automatic accuracy target (rules sized for the total)
+    assert eng.get_quadrature()["accuracy_target"] == 2
+    full = eng.multipoles(z[np.unique(iz)], sep[np.unique(ir)], ls)
+    zi, ri = np.searchsorted(np.unique(iz), iz), np.searchsorted(np.unique(ir), ir)
+    terr = np.abs(full[zi, :, ri] - tot_w) / scale
+    assert terr.max() < 1e-5, terr.max()
     for piece in (1, 2):
         ps = np.max(np.abs(want[:, piece]), axis=1, keepdims=True)
         perr = np.abs(got[:, piece] - want[:, piece]) / ps

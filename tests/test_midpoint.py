@@ -10,6 +10,9 @@ from conftest import H, ROOT
 
 FIXTURE = ROOT / "tests" / "golden" / "class_midpoint.npz"
 FAMILY = [(0, 0), (0, 2), (0, 4), (1, 1), (1, 3), (2, 0), (2, 2), (3, 1)]
+FINE_RULES = dict(n_mu_panel=12, n_mu_panel_di=10, mu_panel_width=16.0, n_outer=96, n_panel_si=12, n_panel_di=12, panel_width=8.0,
+                  panel_uniform_extent=640.0, panel_width_di=16.0, panel_uniform_extent_di=640.0, mu_panel_width_di=16.0,
+                  tail_ratio=1.3, tail_ratio_di=1.3, geometric_shift_di=1, n_mu_ni=64)
 
 
 def test_fixture_holds_a_nonlinear_spectrum_and_the_layer_matters():
@@ -61,13 +64,27 @@ def test_midpoint_multipoles_match_the_class_reference():
     assert err.max() < 1e-5, err
     # (iii) and the layer is really on: the plain linear evaluation of the same inputs is off by per cents at small separations
     assert np.max(np.abs(linear - want) / scale) > 1e-2
-    # pieces: local x integrated and integrated x integrated each within 1e-5 of their own scale
+    # pieces: local x integrated and integrated x integrated each within 1e-5 of their own scale.  The library's default rules were
+    # sized on the linear spectrum; halofit puts more power below 10 Mpc, and the PIECES then need more nodes (default rules: 2e-5 /
+    # 7e-5 of the piece, 4e-7 of the total; tools/midpoint_diag.py) -- node counts are per call, like the reference's integration_bins
     eng = cosmo._get_engine()
-    pieces = eng.multipoles_pieces(fx["z_mean"], fx["sep"], [int(v) for v in fx["l"]])      # [3, z, l, sep]
+    eng.set_quadrature(**FINE_RULES)
+    try:
+        pieces = eng.multipoles_pieces(fx["z_mean"], fx["sep"], [int(v) for v in fx["l"]])      # [3, z, l, sep]
+    finally:
+        eng.set_quadrature()
     wp = fx["converged_pieces"].transpose(2, 0, 3, 1)
     for piece in (0, 1, 2):
         ps = np.max(np.abs(wp[piece]), axis=1, keepdims=True)
         assert np.max(np.abs(pieces[piece] - wp[piece]) / ps) < 1e-5, (piece, np.abs(pieces[piece] - wp[piece]) / ps)
+    # (iv) the builder exactly at knots: the 2-FAST part of every table to 1e-10 of its scale, the small-r knots to the reference's QAG tolerance
+    kz, kr = fx["knot_z_idx"], fx["knot_r_idx"]
+    for t, key in enumerate(FAMILY):
+        mine, ref_v = res["tables2d"][key][np.ix_(kr, kz)], fx["knot_values"][t]
+        sc = np.max(np.abs(ref_v), axis=0, keepdims=True)
+        small = fx["knot_r"] <= 1.0
+        assert np.max(np.abs(mine - ref_v)[~small] / np.broadcast_to(sc, ref_v.shape)[~small]) < 1e-10, key
+        assert np.max(np.abs(mine - ref_v)[small] / np.broadcast_to(sc, ref_v.shape)[small]) < 1e-4, key
 
 
 @pytest.mark.gpu

@@ -80,6 +80,7 @@ def test_group_calls_match_single_device_bit_for_bit(single, group):
 def test_range_and_row_variants_tile_the_full_results(single):
     z, sep, ls = GRID
     mu = [-0.9, -0.2, 0.4, 0.97]
+    single.set_quadrature(accuracy_target=1)        # pieces are always served at piece accuracy: pin the totals to the same rules
     full = single.corrfunc(z[:3], mu, sep[:11])
     n = full.size
     cuts = [0, 5, 44, 45, 100, n]
@@ -88,8 +89,13 @@ def test_range_and_row_variants_tile_the_full_results(single):
     assert np.array_equal(tiled.sum(0).reshape(full.shape), full) or np.array_equal((tiled[0] + tiled[1] + tiled[2]).reshape(full.shape), full)
     zmin, zmax = [0.5, 1.8125], [0.6875, 2.0]
     fa = single.average_multipoles(zmin, zmax, sep[:7], ls)
+    single.set_quadrature()
+    pa_auto = single.average_multipoles(zmin, zmax, sep[:7], ls)
+    assert np.all(np.abs(pa_auto - fa) < 1e-5 * np.max(np.abs(fa), axis=1, keepdims=True))      # automatic target: within the gate of the piece rules
+    single.set_quadrature(accuracy_target=1)
     pa = np.concatenate([single.average_multipoles_pieces(zmin, zmax, sep[:7], ls, a, b) for a, b in ((0, 3), (3, 4), (4, 14))], axis=2)
     assert np.array_equal((pa[0] + pa[1] + pa[2]).reshape(3, 2, 7).transpose(1, 0, 2), fa)
+    single.set_quadrature()
     single.set_options(["den", "rsd"])
     try:
         kw = dict(z_mean=COV["z_mean"], deltaz=COV["deltaz"])
