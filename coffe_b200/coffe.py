@@ -10,8 +10,9 @@ Every number a `compute_*` method returns is produced by the sm_100a kernels beh
 O(10^4) host computation, coffe_b200/background.py) and argument checking run on the host; there is no CPU fallback:
 without the built library or a GPU the first compute call raises.
 
-Not mirrored (out of the hot-path scope): CLASS coupling (`pk_type` other than "linear",
-`cross_spectrum`, the CLASS precision knobs) and `from_file` / `to_file` (libconfig-style settings files).
+`from_file` / `to_file` read and write COFFE settings files (coffe_b200/settings.py).  CLASS itself is not part of this package:
+`pk_type` stays "linear", and the reference's CLASS-midpoint mode is reached by handing over what CLASS would have produced
+(`set_power_spectrum_2d` + `midpoint_approximation`).  Not mirrored: `cross_spectrum`, the CLASS precision knobs.
 """
 import numpy as np
 
@@ -176,6 +177,17 @@ class Coffe:
         if kwargs:
             self.set_parameters(**kwargs)
 
+    @staticmethod
+    def from_file(filename):
+        """python/coffe/coffe.pyx:537-793: a Coffe object with the parameters of a COFFE settings file"""
+        from .settings import apply_settings, read_settings
+        return apply_settings(Coffe(), read_settings(filename))
+
+    def to_file(self, filename):
+        """python/coffe/coffe.pyx:794-866"""
+        from .settings import write_settings
+        write_settings(self, filename)
+
     # ---- cache invalidation, named as in python/coffe/coffe.pyx:948-993 -------------------------------
     def _free_background(self):
         self._background = None
@@ -267,7 +279,8 @@ class Coffe:
     @pk_type.setter
     def pk_type(self, value):
         if value != "linear":
-            raise ValueError("coffe_b200 evaluates the signal for pk_type = 'linear' only (CLASS coupling is out of scope)")
+            raise ValueError("no Boltzmann code in coffe_b200: keep pk_type = 'linear' and, for the reference's CLASS-midpoint mode, pass "
+                             "P(k, z) with set_power_spectrum_2d and set midpoint_approximation = True")
 
     # ---- coordinates with integer / special handling ----------------------------------------------------
     @property

@@ -1046,48 +1046,87 @@ void coffe_b200_destroy(coffe_b200_ctx *ctx)
 
 const char *coffe_b200_last_error(const coffe_b200_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
+/* host half of a table upload: validation, per-interval coefficients, arena layout, shared-memory table build -- independent of the
+   device, so a group does it once for all its members */
+struct PreparedTables {
+    Arena A;
+    Layout L;
+    CompactBuild compact;
+    bool has_compact = false;
+    double omega_matter = 0, h = 0;
+    bool di_mu_symmetric = false, pops_identical = false, mag_constant = false;
+};
+
+int coffe_internal_prepare_tables(const coffe_b200_tables *T, PreparedTables &P, std::string &err)
+{
+    if (!assemble(*T, P.A, P.L, err)) return COFFE_B200_EINVAL;
+    if (!(T->omega_matter > 0) || !(T->h > 0)) { err = "omega_matter and h must be positive"; return COFFE_B200_EINVAL; }
+    P.omega_matter = T->omega_matter; P.h = T->h;
+    P.di_mu_symmetric = tables_di_symmetric(*T);
+    P.pops_identical = tables_populations_identical(*T);
+    P.mag_constant = tables_magnification_constant(*T);
+    P.has_compact = false;
+    if (P.L.has_ifam) {
+        /* the shared-memory tables of the integrated-pieces kernels are built from the exact interval cubics of the host arena; the
+           line-of-sight table is not needed for that */
+        const Tables th = make_view(P.L, P.A.buf.data());
+        std::string why;
+        P.has_compact = build_compact(th, P.L, kCompactKnotBudget, kCompactTolerance, P.compact, why);
+    }
+    return COFFE_B200_OK;
+}
+
+/* device half: copy the arena and the blob, build the line-of-sight table there.  `P` may be shared between contexts (read only);
+   with `own` the context takes the buffers instead of copying them */
+int coffe_internal_commit_tables(coffe_b200_ctx *ctx, PreparedTables &P, const bool own)
+{
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->d_arena) { cudaFree(ctx->d_arena); ctx->d_arena = nullptr; }
+    ctx->have_tables = false;
+    CK(cudaMalloc(&ctx->d_arena, P.A.buf.size() * sizeof(double)));
+    CK(cudaMemcpyAsync(ctx->d_arena, P.A.buf.data(), P.A.buf.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const Layout &L = P.L;
+    ctx->layout = L;
+    ctx->t = make_view(L, ctx->d_arena);
+    los_build_kernel<<<(L.los_n + 127) / 128, 128, 0, ctx->stream>>>(ctx->t, reinterpret_cast<double2 *>(ctx->d_arena + L.los), L.los_n, L.los_h,
+                                                                     L.chi_max_table);
+    CK(cudaGetLastError());
+    if (ctx->d_blob) { cudaFree(ctx->d_blob); ctx->d_blob = nullptr; }
+    if (P.has_compact) {
+        CK(cudaMalloc(&ctx->d_blob, P.compact.blob.size() * sizeof(double)));
+        CK(cudaMemcpyAsync(ctx->d_blob, P.compact.blob.data(), P.compact.blob.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (own) { ctx->arena = std::move(P.A); ctx->compact = std::move(P.compact); }
+    else { ctx->arena = P.A; ctx->compact = P.compact; }
+    if (!P.has_compact) { ctx->compact = CompactBuild(); ctx->compact.h.valid = 0; }
+    ctx->t_host = make_view(L, ctx->arena.buf.data());
+    ctx->omega_matter = P.omega_matter; ctx->h = P.h;
+    ctx->o.Om = P.omega_matter;
+    ctx->o.H0h = P.h / 2997.92458;          /* COFFE_H0 = 1/2997.92458 h/Mpc, src/common.h:75-77 */
+    ctx->o.divergent = L.has_divergent;
+    ctx->di_mu_symmetric = P.di_mu_symmetric;
+    ctx->pops_identical = P.pops_identical;
+    ctx->mag_constant = P.mag_constant;
+    ctx->have_tables = true;
+    ctx->generation++;
+    return COFFE_B200_OK;
+}
+
 int coffe_b200_upload_tables(coffe_b200_ctx *ctx, const coffe_b200_tables *T)
 {
     if (!ctx || !T) return COFFE_B200_EINVAL;
     COFFE_ENTER(ctx);
-    Arena A;
-    Layout L;
-    if (!assemble(*T, A, L, ctx->err)) return COFFE_B200_EINVAL;
-    if (!(T->omega_matter > 0) || !(T->h > 0)) { ctx->err = "omega_matter and h must be positive"; return COFFE_B200_EINVAL; }
-    CK(cudaSetDevice(ctx->device));
-    if (ctx->d_arena) { cudaFree(ctx->d_arena); ctx->d_arena = nullptr; }
-    ctx->have_tables = false;
-    CK(cudaMalloc(&ctx->d_arena, A.buf.size() * sizeof(double)));
-    CK(cudaMemcpyAsync(ctx->d_arena, A.buf.data(), A.buf.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    ctx->arena = std::move(A);
-    ctx->layout = L;
-    ctx->t = make_view(L, ctx->d_arena);
-    ctx->t_host = make_view(L, ctx->arena.buf.data());
-    los_build_kernel<<<(L.los_n + 127) / 128, 128, 0, ctx->stream>>>(ctx->t, reinterpret_cast<double2 *>(ctx->d_arena + L.los), L.los_n, L.los_h,
-                                                                     L.chi_max_table);
-    CK(cudaGetLastError());
-    /* shared-memory tables of the integrated-pieces kernel (absent when the family is not log-spaced: exact-table kernel) */
-    if (ctx->d_blob) { cudaFree(ctx->d_blob); ctx->d_blob = nullptr; }
-    ctx->compact = CompactBuild();
-    if (L.has_ifam) {
-        std::string why;
-        if (build_compact(ctx->t_host, L, kCompactKnotBudget, kCompactTolerance, ctx->compact, why)) {
-            CK(cudaMalloc(&ctx->d_blob, ctx->compact.blob.size() * sizeof(double)));
-            CK(cudaMemcpyAsync(ctx->d_blob, ctx->compact.blob.data(), ctx->compact.blob.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        }
-        else ctx->compact.h.valid = 0;
-    }
-    CK(cudaStreamSynchronize(ctx->stream));
-    ctx->omega_matter = T->omega_matter; ctx->h = T->h;
-    ctx->o.Om = T->omega_matter;
-    ctx->o.H0h = T->h / 2997.92458;          /* COFFE_H0 = 1/2997.92458 h/Mpc, src/common.h:75-77 */
-    ctx->o.divergent = L.has_divergent;
-    ctx->di_mu_symmetric = tables_di_symmetric(*T);
-    ctx->pops_identical = tables_populations_identical(*T);
-    ctx->mag_constant = tables_magnification_constant(*T);
-    ctx->have_tables = true;
-    ctx->generation++;
-    return COFFE_B200_OK;
+    static const bool trace = std::getenv("COFFE_B200_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    PreparedTables P;
+    int rc = coffe_internal_prepare_tables(T, P, ctx->err);
+    if (rc) return rc;
+    const double t_host = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    rc = coffe_internal_commit_tables(ctx, P, true);
+    if (trace) std::fprintf(stderr, "coffe_b200 trace: upload_tables: host assembly + shared-memory tables %.3f ms, device copies + line-of-sight table %.3f ms\n",
+                            t_host, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() - t_host);
+    return rc;
 }
 
 int coffe_b200_set_options(coffe_b200_ctx *ctx, const coffe_b200_options *opt)

@@ -323,3 +323,49 @@ def test_class_matches_engine_on_reference_tables(engine, ref):
     dev = np.abs(got / want - 1)
     assert np.all(dev < 3e-6), dev.max()
     assert np.median(dev) < 5e-7
+
+
+def test_settings_file_round_trip(tmp_path):
+    """Coffe.from_file / to_file (python/coffe/coffe.pyx:537-866): today's option names, the renamed options of older files (with the
+    reference's deprecation warnings), integer enum codes, constant and tabulated biases; to_file -> from_file reproduces every parameter"""
+    import warnings
+    cfg = tmp_path / "old_style.cfg"
+    bias = tmp_path / "bias.dat"
+    np.savetxt(bias, np.column_stack([np.linspace(0, 3, 7), 1.0 + 0.5 * np.linspace(0, 3, 7)]))
+    cfg.write_text(f"""
+# comment line
+omega_m = 0.31;
+h = 0.68
+correlation_contributions = ["den", "len", "g4"];
+multipoles = [0, 2];
+covariance_z_mean = [0.5, 1.5];
+covariance_deltaz = [0.1, 0.2];
+covariance_density = [1e-3, 2e-3];
+covariance_window = 1;
+flatsky_local = 1
+covariance_integration_method = 2;
+sep = [10., 20., 30.];
+read_galaxy_bias1 = 1;
+input_galaxy_bias1 = "{bias}";
+galaxy_bias2 = 1.7;
+input_galaxy_bias2 = "";
+magnification_bias1_redshifts = [0., 1., 2., 3., 4.];
+magnification_bias1_values = [0.1, 0.2, 0.3, 0.4, 0.5];
+covariance_step_size = 5.0;
+""")
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        c = Coffe.from_file(cfg)
+    assert sum(issubclass(x.category, DeprecationWarning) for x in w) >= 7
+    assert c.omega_m == 0.31 and c.h == 0.68 and c.has_density and c.has_lensing and c.has_g4 and not c.has_rsd
+    assert list(c.l) == [0, 2] and np.allclose(c.z_mean, [0.5, 1.5]) and np.allclose(c.deltaz, [0.1, 0.2])
+    assert np.allclose(c.number_density1, [1e-3, 2e-3]) and np.allclose(c.number_density2, [1e-3, 2e-3])
+    assert c.has_binned_covariance and c.has_flatsky_local and c.covariance_integration_method == "fftlog"
+    assert np.isclose(c.galaxy_bias1(1.5), 1.75, rtol=1e-3) and np.isclose(c.galaxy_bias2(0.7), 1.7)
+    assert np.isclose(c.magnification_bias1(2.0), 0.3)
+    out = tmp_path / "new_style.cfg"
+    c.to_file(out)
+    d = Coffe.from_file(out)
+    for key, value in c.parameters.items():
+        assert np.array_equal(np.asarray(value), np.asarray(d.parameters[key])), key
+    assert np.isclose(d.galaxy_bias1(1.5), c.galaxy_bias1(1.5)) and np.isclose(d.magnification_bias1(2.0), 0.3)
