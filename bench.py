@@ -407,6 +407,19 @@ def main():
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
     dev_ms_max, wall_ms_max, si_ms_max, di_ms_max, gather_ms_max = t_dev.tolist()
     n_work, n_ni, n_si, n_di = plan.count()
+    # the same kernels under the piece-accuracy rules (every piece to 1e-5 of itself, what a lensing-only run gets): one extra untimed
+    # pass at N = 1, so that the line shows the kernel's efficiency did not change with the rule sizes, only the work did
+    piece_rules = None
+    if world == 1:
+        eng.set_quadrature(accuracy_target=1)
+        pp = eng.plan_multipoles(z, sep, ls, begin, end)
+        pp.execute(); p_ms = pp.execute()
+        p_si, p_di = eng.last_kernel_times()
+        _, _, pn_si, pn_di = pp.count()
+        pp.close()
+        eng.set_quadrature()
+        piece_rules = {"ms_per_step": p_ms, "value": n_pts_total / (p_ms * 1e-3), "di_launch_ms": p_di, "si_launch_ms": p_si,
+                       "integrand_evaluations": {"SI": pn_si, "DI": pn_di}, "di_achieved_tflops": F_DI * pn_di / (p_di * 1e-3) / 1e12}
     cnt = torch.tensor([n_work, n_ni, n_si, n_di, launches], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
@@ -481,6 +494,9 @@ def main():
                          "peak_source": "DFMA probe kernel measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                          "launch_ms": di_launch_ms, "share_of_step": di_ms_max / dev_ms_max if dev_ms_max else None,
                          "flops_per_launch": F_DI * n_di / world, "accounting": "SURVEY.md 8d: 450 flop per DI integrand evaluation",
+                         "piece_rules": ({**piece_rules, "di_frac": piece_rules["di_achieved_tflops"] / peak_tf if peak_tf else None,
+                                          "note": "accuracy_target = 1 (each piece to 1e-5 of itself); the timed run uses the automatic target, "
+                                                  "which sizes the rules for the total when density / RSD are on (DESIGN.md 3.1)"} if piece_rules else None),
                          "step": {"achieved": achieved_step, "frac": achieved_step / peak_tf if peak_tf else None, "flops": flops_per_step / world,
                                   "si_kernel_ms": si_ms_max / args.steps, "gather_ms": gather_ms_max / args.steps,
                                   "accounting": "700/1000/450 flop per NI/SI/DI evaluation"}},
