@@ -1,25 +1,29 @@
 #!/usr/bin/env python
 """bench.py -- multipole points/sec of the all-effects signal path (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl coffe_b200|reference] [--nz 32] [--nsep 1000]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl coffe_b200|reference] [--tables reference|own] [--nz 32] [--nsep 1000]
 
-One "step" = one pass of the hot path over the whole cfg5 grid: 32 z_mean x 1000 separations x l = 0,2,4,
-all effects (den, rsd, len, d1, d2, g1..g5), full-sky, = 96 000 multipole points, sharded over the N
-GPUs as contiguous blocks of (z, r) work items (no data-path collective; one NCCL gather of the result).
+One "step" = one pass of the hot path over the whole cfg5 grid: 32 z_mean x 1000 separations x l = 0,2,4, all effects (den, rsd, len,
+d1, d2, g1..g5), full-sky, = 96 000 multipole points, sharded over the N GPUs as contiguous cost-balanced blocks of (z, r) items; at
+N > 1 the blocks are gathered device to device by the library's own NCCL calls INSIDE every timed step.
 
-  value  : points/s with the grid and its quadrature items already resident in HBM (kernels only,
-           CUDA events on the launching stream, max over ranks)
-  e2e    : points/s through the reference-facing C ABI call coffe_b200_multipoles_range with HOST
-           buffers: item construction, host->device copies and the device->host copy inside the timed region
-  roofline: FP64, for the dominant kernel di_items_smem_kernel (integrated x integrated piece, ~88 % of the step):
-           achieved = canonical algorithmic flops (F_DI = 450 per integrand evaluation x the
-           evaluations one launch performs) / that kernel's launch duration (CUDA events on its stream, averaged
-           over the timed steps); peak = the DFMA probe kernel measured on the same device in the same run;
-           `step` repeats the accounting for the whole step (NI 700, SI 1000, DI 450 flop per evaluation)
-  covariance: cfg4 (4 z x (3 x 100)^2 entries, flat-sky Gaussian covariance with shot noise) entries/s, rank 0
+  value   : points/s with the grid and its quadrature items already resident in HBM (kernels + gather, CUDA events on the launching
+            stream, max over ranks)
+  e2e     : points/s through the reference-facing C ABI call with HOST buffers (coffe_b200_multipoles_range; at N > 1
+            coffe_b200_multipoles_sharded: block boundaries, kernels, NCCL gather, D2H of the full grid): item construction,
+            host->device copies and the device->host copy inside the timed region
+  parity  : the multipoles this run timed against the converged-oracle fixture tests/golden/converged_cfg5.npz (max / median error
+            relative to the l = 0..4 scale of the point; gate 1e-5)
+  roofline: FP64, for the dominant kernel di_items_smem_kernel: achieved = canonical algorithmic flops (450 per integrand
+            evaluation x the evaluations one launch performs) / that kernel's launch duration (CUDA events on its stream); peak = the
+            DFMA probe kernel measured in the same run; traffic / ncu_pipes from profiles/ncu_di_kernel_cfg5.json (ncu --set full);
+            piece_rules = the same kernels under the piece-accuracy rules, measured in the same run
+  covariance: cfg4 (4 z x (3 x 100)^2 entries) entries/s with the reference's coffe_covariance_init on a 20 x 20 sub-block beside it
+  extras  : cfg2 (2PCF, 100 r x 50 mu) and cfg3 (averaged multipoles, 8 bins x 200 r) points/s, table upload
+  setup   : with --tables own: background / I^n_l tables / upload / first call from P(k) + cosmology (time to first result)
   cpu_baseline: the reference's own code (oracle/_ref, -O3 -ffast-math like its wheels) on a bounded sample
 
-With --impl reference the reference's CPU implementation is timed instead (rank 0 only).
+With --impl reference the reference's CPU implementation is timed instead (rank 0 only), with single-core seconds per stratum.
 """
 import argparse
 import json

@@ -26,17 +26,21 @@ struct LinearTable {
     {
         slope.resize(x.size() - 1);
         for (size_t i = 0; i + 1 < x.size(); ++i) slope[i] = (y[i + 1] - y[i]) / (x[i + 1] - x[i]);
+        inv_dx = (x.size() - 1) / (x.back() - x.front());
     }
-    /* interval by bisection with x[i] <= v < x[i+1] semantics (what gsl_interp_bsearch returns), then y_i + slope_i (v - x_i) */
+    /* interval with x[i] <= v < x[i+1] semantics (what gsl_interp_bsearch returns) -- the knots are uniform, so the index comes from
+       the argument and is then corrected against the knots themselves -- then y_i + slope_i (v - x_i) */
     double eval(const double v) const
     {
-        size_t lo = 0, hi = x.size() - 1;
-        while (hi > lo + 1) {
-            const size_t mid = (hi + lo) / 2;
-            if (x[mid] > v) hi = mid; else lo = mid;
-        }
+        const size_t last = x.size() - 2;
+        double s = (v - x[0]) * inv_dx;
+        size_t lo = s > 0.0 ? (size_t)s : 0;
+        if (lo > last) lo = last;
+        while (lo > 0 && x[lo] > v) --lo;
+        while (lo < last && x[lo + 1] <= v) ++lo;
         return y[lo] + slope[lo] * (v - x[lo]);
     }
+    double inv_dx = 0;
 };
 
 struct Growth {
