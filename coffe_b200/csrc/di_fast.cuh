@@ -10,10 +10,10 @@
 //     the panels on the two sides of the ridge are mirror images, so as long as neither side is clipped by the
 //     ends of the line of sight the nodes at -d and +d share R and therefore ONE lookup of the nine I^n_l
 //     (the dominant shared-memory traffic); only the remainder of the longer side is evaluated singly;
-//   * renormalisation(lambda_1, lambda_2) is read from the row collapsed at lambda_1 (tables.cuh: ren_row_fill),
-//     filled once per outer node by the lanes of the warp.
-// The functions are lane-strided like item.cuh: `nlanes` cooperating lanes (a warp on the device; the CPU
-// harness calls them with nlanes = n_panel lanes in turn), lane = panel slot * n_panel + node.
+//   * of the renormalised potential terms only I^4_0(R) rides on the ridge panels; renormalisation(lambda_1, lambda_2), which has no
+//     structure on the scale of the impact parameter, has its own inner rule (di_ren_smooth_partial).
+// Lane layout: groups of n_panel lanes, one group per outer node, lane j of a group = node j of every panel (di_inner_group);
+// the CPU harness calls the same functions for the n_panel lanes of one group in turn.
 #pragma once
 #include "item.cuh"
 
@@ -106,7 +106,7 @@ template <class TA>
 struct DISideCtx {
     const TA *ta;
     const double2 *los; int los_n; double los_inv_h;
-    const Renorm2DView *r2d; const double2 *row; int n_row;
+    const Renorm2DView *r2d;
 };
 
 /* integrand at lambda_2 = l2 (per unit lambda_2, H0^4 and all amplitudes included).  ALL: every group of terms is
@@ -136,185 +136,195 @@ COFFE_HD double di_side(const DISideCtx<TA> &cx, const DIFast &f, const DIOuter 
         acc = fma(G, F, acc);
     }
     if (ALL || f.any_ren) {
-        const double ren = (!ALL && s.r2 <= 1e-12) ? cx.ta->ren0(o.l1) : s.I40 - ren_row_eval(*cx.r2d, cx.row, cx.n_row, l2);
+        /* renormalization(l1, l2) itself is integrated apart (di_ren_smooth_partial): only I^4_0(R) carries the cusp */
+        const double ren = (!ALL && s.r2 <= 1e-12) ? cx.ta->ren0(o.l1) + renorm2d_eval(*cx.r2d, o.l1, l2) : s.I40;
         acc = fma(ren, fma(o.B1, los2.y, o.B0), acc);
     }
     return los2.x * acc;
 }
 
-/* the panels of one inner integral: a prefix of K_pair mirror pairs, then the remainders of the two sides */
-struct DIPanels {
-    PanelPlan plan;
+/* The renormalised potential terms are (I^4_0(R) - renormalization(l1, l2)) x smooth line-of-sight factors (src/functions.c:3838-4016).
+   The two halves are of the same size (both carry the infrared part of the spectrum) and cancel to a few per cent, but only I^4_0(R)
+   has structure on the scale of the impact parameter: renormalization(l1, l2), a bicubic interpolant on a ~30 Mpc grid, varies on
+   scales of hundreds of Mpc, with its curvature concentrated around the diagonal l2 = l1.  Its inner integral therefore gets its own
+   rule -- two Gauss-Legendre panels split at the diagonal, n_ren nodes together (one per lane on the device) -- instead of riding on
+   the ridge panels: against a composite rule on the cells of the grid 2 x 16 nodes leave 4e-8 of this half (CPU experiment, three
+   distances), i.e. < 1e-6 of the difference.  Returns this lane's share of - integral dl2 W2 (B0 + B1 V2) renormalization(l1, l2). */
+COFFE_HD double di_ren_smooth_partial(const Renorm2DView &r2d, const double2 *los, const int los_n, const double los_inv_h, const Rules &q,
+                                      const DIFast &f, const DIOuter &o, const int lane, const int nlanes)
+{
+    const int half = q.n_ren / 2;
+    const double *x = q.gl_x + rule_offset(half), *w = q.gl_w + rule_offset(half);
+    const double split = o.l1 < f.chi2 ? o.l1 : f.chi2;
+    double acc = 0.0;
+    for (int i = lane; i < 2 * half; i += nlanes) {
+        const bool upper = i >= half;
+        const int jj = upper ? i - half : i;
+        const double lo = upper ? split : 0.0, wd = upper ? f.chi2 - split : split;
+        const double l2 = fma(wd, x[jj], lo);
+        const double4 los2 = los_eval(los, los_n, los_inv_h, l2);
+        acc = fma(wd * w[jj], los2.x * renorm2d_eval(r2d, o.l1, l2) * fma(o.B1, los2.y, o.B0), acc);
+    }
+    return -acc;
+}
+
+/* The inner integral over lambda_2 in [0, chi2] at one outer node, on ONE GROUP of n_panel lanes: lane j owns node j of every panel
+   and walks through the panels in sequence -- first the K_pair mirror pairs (panels that neither side clips: the nodes at -d and +d
+   share R, hence one lookup of the nine I^n_l), then the remaining panels of the two sides singly.  A warp runs 32 / n_panel groups
+   side by side, each on its own outer node (engine.cu: di_items_smem_kernel), so the lanes stay busy whatever the panel counts are
+   and the set-up of an outer node is paid once per group, not once per warp.
+   Walking the panels in order makes the mapped nodes cheap: on the sinh-map panels (quadrature.cuh) sinh / cosh of t = L (k + x_j)
+   follow from the addition theorem and a two-term recurrence in k (one exp per lane and outer node), on the log-mapped tail panels
+   the node is the panel's start times ratio^x_j.  Returns this lane's partial sum. */
+struct DISides {
     double a_neg, b_neg, b_pos;
     int k_neg, k_pos, k_pair;
 };
 
-COFFE_HD DIPanels di_panels(const Rules &q, const DIFast &f, const DIOuter &o)
+COFFE_HD DISides di_sides(const PanelPlan &plan, const DIFast &f, const DIOuter &o)
 {
-    DIPanels p;
-    p.plan = panel_plan(sqrt(o.eps2), q.eps_min, q.panel_w_di, q.panel_du_di, q.tail_ratio_di, q.rpow_di, q.geo_shift_di);
+    DISides p;
     p.b_neg = o.c0;
     p.a_neg = o.c0 > f.chi2 ? o.c0 - f.chi2 : 0.0;
     p.b_pos = f.chi2 - o.c0;
-    p.k_neg = panel_count_by_break(p.plan, p.b_neg);
-    p.k_pos = p.b_pos > 0.0 ? panel_count_by_break(p.plan, p.b_pos) : 0;
-    p.k_pair = 0;
-    if (p.a_neg == 0.0 && p.k_pos > 0 && p.k_neg > 0) {
-        const double bmin = p.b_neg < p.b_pos ? p.b_neg : p.b_pos;
-        const int kc = p.k_neg < p.k_pos ? p.k_neg : p.k_pos;           /* panels of the shorter side */
-        p.k_pair = panel_break(p.plan, kc) > bmin ? kc - 1 : kc;        /* its last panel is clipped unless a break falls on the end */
-    }
+    p.k_neg = panel_count(plan, p.b_neg);
+    p.k_pos = p.b_pos > 0.0 ? panel_count(plan, p.b_pos) : 0;
+    /* the last panel of the shorter side is clipped (or ends within rounding of the end of the line of sight): not paired */
+    const int kc = p.k_neg < p.k_pos ? p.k_neg : p.k_pos;
+    p.k_pair = (p.a_neg == 0.0 && kc > 0) ? kc - 1 : 0;
     return p;
 }
 
-/* clipped panel k of one side: [lo, lo + w) in |d|; w = 0 if empty */
-COFFE_HD void di_single_panel(const DIPanels &p, const bool neg, const int k, double &lo, double &w)
+COFFE_HD PanelPlan di_plan(const Rules &q, const DIOuter &o)
 {
-    lo = panel_break(p.plan, k);
-    double up = panel_break(p.plan, k + 1);
-    const double a = neg ? p.a_neg : 0.0, b = neg ? p.b_neg : p.b_pos;
-    if (lo < a) lo = a;
-    if (up > b) up = b;
-    w = up > lo ? up - lo : 0.0;
+    return panel_plan(sqrt(o.eps2), q.eps_min, q.panel_w_di, q.panel_du_di, q.tail_ratio_di, q.rpow_di, q.geo_shift_di, q.geo_L_di, q.tail_lnr_di);
 }
 
-/* inner integral over lambda_2 in [0, chi2] at one outer node: this lane's partial sum */
 template <bool ALL, class TA>
-COFFE_HD double di_inner_partial(const DISideCtx<TA> &cx, const Rules &q, const DIFast &f, const DIOuter &o,
-                                 const int lane, const int nlanes)
+COFFE_HD double di_inner_group(const DISideCtx<TA> &cx, const Rules &q, const DIFast &f, const DIOuter &o, const int j)
 {
     const int np = q.n_panel_di;
-    const int ppi = nlanes >= np ? nlanes / np : 1;
-    const int lp = lane / np, j = lane - lp * np;
-    if (nlanes >= np && lp >= ppi) return 0.0;
-    const double *px = q.panel_x ? q.panel_x : q.gl_x + rule_offset(np), *pw = q.panel_w ? q.panel_w : q.gl_w + rule_offset(np);
-    const DIPanels p = di_panels(q, f, o);
+    const double xj = q.panel_x ? q.panel_x[j] : q.gl_x[rule_offset(np) + j], wj = q.panel_w ? q.panel_w[j] : q.gl_w[rule_offset(np) + j];
+    const PanelPlan plan = di_plan(q, o);
+    const DISides p = di_sides(plan, f, o);
     double acc = 0.0;
-    /* nodes this lane owns: j, j + nlanes, ... (only when a panel has more nodes than there are lanes) */
-    for (int jj = nlanes >= np ? j : lane; jj < np; jj += nlanes >= np ? np : nlanes) {
-        const double xj = px[jj], wj = pw[jj];
-        /* mirror pairs */
-        for (int k = nlanes >= np ? lp : 0; k < p.k_pair; k += ppi) {
-            const double lo = panel_break(p.plan, k), w = panel_break(p.plan, k + 1) - lo;
-            const double d = fma(w, xj, lo);
+    const double pj = plan.lnr > 0.0 ? (q.panel_p ? q.panel_p[j] : exp(plan.lnr * xj)) : 0.0;         /* ratio^x_j */
+    /* ---- mirror pairs, k = 0 .. k_pair-1: never clipped ---- */
+    {
+        /* sinh-map state: (S, C) = (sinh, cosh)(k L), (sj, cj) = (sinh, cosh)(L x_j), (S1, C1) = (sinh, cosh)(L) */
+        double S = 0.0, C = 1.0, sj = 0.0, cj = 1.0, S1 = 0.0, C1 = 1.0;
+        if (plan.L > 0.0 && p.k_pair > 0) {
+            const double e = exp(plan.L * xj), ie = 1.0 / e, e1 = exp(plan.L), ie1 = 1.0 / e1;
+            sj = 0.5 * (e - ie); cj = 0.5 * (e + ie); S1 = 0.5 * (e1 - ie1); C1 = 0.5 * (e1 + ie1);
+        }
+        const int JM = plan.J + plan.M;
+        for (int k = 0; k < p.k_pair; ++k) {
+            double d, wgt;
+            if (k < plan.J) {
+                if (plan.L > 0.0) {
+                    d = plan.eps * fma(S, cj, C * sj);
+                    wgt = (plan.eps * plan.L * wj) * fma(C, cj, S * sj);
+                    const double Sn = fma(S, C1, C * S1);
+                    C = fma(C, C1, S * S1);
+                    S = Sn;
+                }
+                else {
+                    const double lo = panel_break(plan, k), wd = panel_break(plan, k + 1) - lo;
+                    d = fma(wd, xj, lo); wgt = wd * wj;
+                }
+            }
+            else if (k < JM) {
+                d = fma(plan.W, xj, plan.BJ + (k - plan.J) * plan.W);
+                wgt = plan.W * wj;
+            }
+            else {
+                const int n = k - JM;
+                const double lo = plan.BJM * plan.rpow[n < kMaxTail ? n : kMaxTail - 1];
+                if (plan.lnr > 0.0) { d = lo * pj; wgt = d * (plan.lnr * wj); }
+                else {
+                    const double wd = plan.BJM * plan.rpow[n + 1 < kMaxTail ? n + 1 : kMaxTail - 1] - lo;
+                    d = fma(wd, xj, lo); wgt = wd * wj;
+                }
+            }
             const DIShared s = di_shared(*cx.ta, f, o, d);
             const double v = di_side<ALL>(cx, f, o, s, o.c0 - d) + di_side<ALL>(cx, f, o, s, o.c0 + d);
-            acc = fma(w * wj, v, acc);
-        }
-        /* remainders: negative side k_pair..k_neg-1, then positive side k_pair..k_pos-1 */
-        const int n_negl = p.k_neg - p.k_pair, n_left = n_negl + (p.k_pos - p.k_pair);
-        for (int e = nlanes >= np ? lp : 0; e < n_left; e += ppi) {
-            const bool neg = e < n_negl;
-            double lo, w;
-            di_single_panel(p, neg, p.k_pair + (neg ? e : e - n_negl), lo, w);
-            if (w == 0.0) continue;
-            const double d = fma(w, xj, lo);
-            const DIShared s = di_shared(*cx.ta, f, o, d);
-            acc = fma(w * wj, di_side<ALL>(cx, f, o, s, neg ? o.c0 - d : o.c0 + d), acc);
+            acc = fma(wgt, v, acc);
         }
     }
-    return acc;
-}
-
-#if defined(__CUDA_ARCH__)
-/* The same sum on a full warp, with the panel bookkeeping done by the warp instead of by every lane: lane k holds the break
-   B_k, the panel counts are ballots, and a panel's ends are two shuffles (profiles/README.md: the scalar bookkeeping -- doubling
-   loops, per-iteration break formulas -- was 15 % of the kernel's instructions with ~3 inner iterations per outer node).  Same
-   breaks, same counts, same nodes, same summation order as di_inner_partial: bit-identical.  Only valid when a side never has more
-   than 31 panels and the panel rule is staged (q.panel_x): the host checks the configured plan (rules_build.h: di_side_panels) and
-   launches the WARP_PANELS instantiation of the kernel. */
-template <bool ALL, class TA>
-__device__ __forceinline__ double di_inner_partial_warp(const DISideCtx<TA> &cx, const Rules &q, const DIFast &f, const DIOuter &o, const int lane)
-{
-    const unsigned int full = 0xffffffffu;
-    const int np = q.n_panel_di;            /* <= 32 (the caller checks) */
-    const int ppi = 32 / np;
-    const int lp = lane / np, j = lane - lp * np;
-    const bool on = lp < ppi;
-    const PanelPlan plan = panel_plan(sqrt(o.eps2), q.eps_min, q.panel_w_di, q.panel_du_di, q.tail_ratio_di, q.rpow_di, q.geo_shift_di);
-    const double brk = panel_break(plan, lane);
-    const double b_neg = o.c0, a_neg = o.c0 > f.chi2 ? o.c0 - f.chi2 : 0.0, b_pos = f.chi2 - o.c0;
-    const int k_neg = b_neg > 0.0 ? __popc(__ballot_sync(full, brk < b_neg)) : 0;
-    const int k_pos = b_pos > 0.0 ? __popc(__ballot_sync(full, brk < b_pos)) : 0;
-    int k_pair = 0;
-    if (a_neg == 0.0 && k_pos > 0 && k_neg > 0) {
-        const double bmin = b_neg < b_pos ? b_neg : b_pos;
-        const int kc = k_neg < k_pos ? k_neg : k_pos;
-        k_pair = __shfl_sync(full, brk, kc) > bmin ? kc - 1 : kc;
-    }
-    const double xj = q.panel_x[j], wj = q.panel_w[j];
-    double acc = 0.0;
-    for (int k0 = 0; k0 < k_pair; k0 += ppi) {
-        const int k = k0 + lp;
-        const double lo = __shfl_sync(full, brk, k & 31), up = __shfl_sync(full, brk, (k + 1) & 31);
-        if (on && k < k_pair) {
-            const double w = up - lo;
-            const double d = fma(w, xj, lo);
-            const DIShared s = di_shared(*cx.ta, f, o, d);
-            const double v = di_side<ALL>(cx, f, o, s, o.c0 - d) + di_side<ALL>(cx, f, o, s, o.c0 + d);
-            acc = fma(w * wj, v, acc);
-        }
-    }
-    const int n_negl = k_neg - k_pair, n_left = n_negl + (k_pos - k_pair);
-    for (int e0 = 0; e0 < n_left; e0 += ppi) {
-        const int e = e0 + lp;
+    /* ---- what is left of the two sides: negative side k_pair .. k_neg-1, then positive side k_pair .. k_pos-1 ---- */
+    const int n_negl = p.k_neg - p.k_pair, n_left = n_negl + (p.k_pos - p.k_pair);
+    for (int e = 0; e < n_left; ++e) {
         const bool neg = e < n_negl;
-        const int k = k_pair + (neg ? e : e - n_negl);
-        double lo = __shfl_sync(full, brk, k & 31), up = __shfl_sync(full, brk, (k + 1) & 31);
-        const double a = neg ? a_neg : 0.0, b = neg ? b_neg : b_pos;
-        if (lo < a) lo = a;
-        if (up > b) up = b;
-        if (on && e < n_left && up > lo) {
-            const double w = up - lo;
-            const double d = fma(w, xj, lo);
-            const DIShared s = di_shared(*cx.ta, f, o, d);
-            acc = fma(w * wj, di_side<ALL>(cx, f, o, s, neg ? o.c0 - d : o.c0 + d), acc);
+        const int k = p.k_pair + (neg ? e : e - n_negl);
+        double lo = panel_break(plan, k), up = panel_break(plan, k + 1);
+        const double a = neg ? p.a_neg : 0.0, b = neg ? p.b_neg : p.b_pos;
+        const bool lo_cl = lo < a, up_cl = up > b;
+        if (lo_cl) lo = a;
+        if (up_cl) up = b;
+        if (!(up > lo)) continue;
+        double d, wgt;
+        const int map = panel_map(plan, k);
+        if (map == 2) {
+            /* log-mapped tail panel: the unclipped one costs no transcendental */
+            if (lo_cl || up_cl) {
+                const double h = log(up / lo);
+                d = lo * exp(h * xj); wgt = d * (h * wj);
+            }
+            else { d = lo * pj; wgt = d * (plan.lnr * wj); }
         }
+        else if (map == 1) panel_node(plan, k, lo, up, lo_cl, up_cl, xj, wj, d, wgt);
+        else { const double wd = up - lo; d = fma(wd, xj, lo); wgt = wd * wj; }
+        const DIShared s = di_shared(*cx.ta, f, o, d);
+        acc = fma(wgt, di_side<ALL>(cx, f, o, s, neg ? o.c0 - d : o.c0 + d), acc);
     }
     return acc;
 }
-#endif
 
 COFFE_HD unsigned int di_inner_eval_count(const Rules &q, const DIFast &f, const DIOuter &o)
 {
-    const DIPanels p = di_panels(q, f, o);
+    const PanelPlan plan = di_plan(q, o);
+    const DISides p = di_sides(plan, f, o);
     unsigned int n = 2u * p.k_pair;
-    for (int k = p.k_pair; k < p.k_neg; ++k) { double lo, w; di_single_panel(p, true, k, lo, w); if (w > 0.0) ++n; }
-    for (int k = p.k_pair; k < p.k_pos; ++k) { double lo, w; di_single_panel(p, false, k, lo, w); if (w > 0.0) ++n; }
+    for (int side = 0; side < 2; ++side) {
+        const double a = side == 0 ? p.a_neg : 0.0, b = side == 0 ? p.b_neg : p.b_pos;
+        for (int k = p.k_pair; k < (side == 0 ? p.k_neg : p.k_pos); ++k) {
+            double lo = panel_break(plan, k), up = panel_break(plan, k + 1);
+            if (lo < a) lo = a;
+            if (up > b) up = b;
+            if (up > lo) ++n;
+        }
+    }
     return n * q.n_panel_di;
 }
 
-/* integrated x integrated piece per unit (x1, x2).  Outer nodes strided over `ngroups` groups of `nlanes` lanes;
-   `row` is the group's own buffer of t.ren2d.n double2 (renormalisation row), unused without the divergent terms. */
-template <class TA, bool WARP_PANELS = false>
+/* integrated x integrated piece per unit (x1, x2): outer nodes strided over `ngroups` groups of n_panel lanes, `j` = this lane's node.
+   The loop is uniform over the groups (a group without an outer node in the last round idles): no lane leaves early, so the device
+   kernels may use warp-wide votes inside. */
+template <class TA>
 COFFE_HD double di_fast_partial(const TA &ta, const Tables &t, const double2 *los, const Rules &q, const Geometry &g, const DIConst &k,
-                                double2 *row, const int group, const int ngroups, const int lane, const int nlanes,
-                                const bool serial_fill = false /* CPU harness: lanes run one after the other, each fills the whole row */)
+                                const int group, const int ngroups, const int j)
 {
     const DIFast f = di_fast_setup(k, g);
     const int n_outer = q.n_outer > 0 ? q.n_outer : auto_n_outer(g.sep);
     const double *outer_x = q.gl_x + rule_offset(n_outer), *outer_w = q.gl_w + rule_offset(n_outer);
     DISideCtx<TA> cx;
     cx.ta = &ta; cx.los = los; cx.los_n = t.los.n; cx.los_inv_h = t.los.inv_h;
-    cx.r2d = &t.ren2d; cx.row = row;
-    cx.n_row = f.any_ren ? ren_row_count(t.ren2d, g.chi2) : 0;
+    cx.r2d = &t.ren2d;
     double acc = 0.0;
-    for (int io = group; io < n_outer; io += ngroups) {
-        const double l1 = g.chi1 * outer_x[io];
+    for (int io0 = 0; io0 < n_outer; io0 += ngroups) {
+        const int io = io0 + group;
+        const bool valid = group < ngroups && io < n_outer;
+        const double l1 = g.chi1 * outer_x[valid ? io : io0];
         const DIOuter o = di_outer_setup(f, l1, los_eval(los, t.los.n, t.los.inv_h, l1));
-        if (f.any_ren) {
-            COFFE_SYNC_LANES();             /* the previous node's readers are done */
-            ren_row_fill(t.ren2d, l1, cx.n_row, row, serial_fill ? 0 : lane, serial_fill ? 1 : nlanes);
-            COFFE_SYNC_LANES();
-        }
-        const bool all = f.any_ll && f.any_pl && f.any_ren && o.eps2 > 1e-12;
-#if defined(__CUDA_ARCH__) && !defined(COFFE_NO_WARP_PANELS)
-        if (WARP_PANELS) {
-            acc = fma(outer_w[io], all ? di_inner_partial_warp<true>(cx, q, f, o, lane) : di_inner_partial_warp<false>(cx, q, f, o, lane), acc);
-            continue;
-        }
+        bool all = f.any_ll && f.any_pl && f.any_ren && o.eps2 > 1e-12;
+#if defined(__CUDA_ARCH__)
+        all = __all_sync(0xffffffffu, all);       /* one instantiation per round for the whole warp */
 #endif
-        acc = fma(outer_w[io], all ? di_inner_partial<true>(cx, q, f, o, lane, nlanes) : di_inner_partial<false>(cx, q, f, o, lane, nlanes), acc);
+        if (valid) {
+            double v = all ? di_inner_group<true>(cx, q, f, o, j) : di_inner_group<false>(cx, q, f, o, j);
+            if (f.any_ren) v += di_ren_smooth_partial(t.ren2d, los, t.los.n, t.los.inv_h, q, f, o, j, q.n_panel_di);
+            acc = fma(outer_w[io], v, acc);
+        }
     }
     return acc / g.chi2;
 }

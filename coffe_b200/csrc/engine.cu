@@ -102,7 +102,7 @@ __global__ void ni_points_kernel(const __grid_constant__ Tables t, const __grid_
 
 /* ---- integrated pieces, exact tables through L1/L2: one CTA per item (variant 0, cross-check) -----
    mode 1: local x integrated (one warp per half); mode 2: integrated x integrated (outer nodes strided
-   over the warps).  Dynamic shared memory: [line-of-sight table][one renormalisation row per warp]. */
+   over the warps).  Dynamic shared memory: [line-of-sight table]. */
 struct ItemShared {
     Geometry g;
     SIHalf ha, hb;
@@ -132,7 +132,6 @@ __global__ void __launch_bounds__(kItemThreads, COFFE_ITEM_MIN_BLOCKS) integrate
         for (int i = tid; i < kLosStride * los_stage_n; i += kItemThreads) los_s[i] = t.los.v[i];
         los = los_s;
     }
-    double2 *row = los_s + kLosStride * los_stage_n + (size_t)warp * t.ren2d.n;
     if (tid == 0) {
         const int p = item_point[item];
         const double z = pz[p], sep = psep[p], mu = item_mu[item];
@@ -160,7 +159,11 @@ __global__ void __launch_bounds__(kItemThreads, COFFE_ITEM_MIN_BLOCKS) integrate
     /* midpoint approximation: the mirror nodes of di_fast share one table lookup, which the 2-D tables (z differs between the
        mirror nodes) do not allow: the plain ridge rule over di_eval, same panels and nodes */
     else if (o.midpoint) v = di_partial(ta, t.los, q, sh.g, sh.k, los, warp, kItemWarps, lane, 32, sh.panels[warp]);
-    else v = di_fast_partial(ta, t, los, q, sh.g, sh.k, row, warp, kItemWarps, lane, 32);
+    else {
+        /* groups of n_panel lanes, one outer node each (di_fast.cuh); a rule with more than 32 nodes per panel has no lane layout */
+        const int np = q.n_panel_di, ppi = 32 / np, grp = lane / np;
+        v = di_fast_partial(ta, t, los, q, sh.g, sh.k, grp < ppi ? warp * ppi + grp : kItemWarps * ppi, kItemWarps * ppi, lane - grp * np);
+    }
     v = warp_sum(v);
     if (lane == 0) sh.red[warp] = v;
     __syncthreads();
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(kItemThreads, COFFE_ITEM_MIN_BLOCKS) integrate
    (integrated x integrated: the 2-D integral, > 90 % of the device time of a step). */
 /* doubles of the small read-only block staged next to the tables: powers of the tail ratio, then the nodes and
    weights of the inner panel rule */
-constexpr int kDISmallDoubles = kMaxTail + 2 * 32;
+constexpr int kDISmallDoubles = kMaxTail + 3 * 32;
 
 struct SIWarpState {
     EndVals e[2];
@@ -288,10 +291,11 @@ struct DIWarpState {
 #endif
 constexpr int kDIThreads = COFFE_DI_THREADS;        /* upper bound (register allocation); the launch may use fewer warps */
 
-
-/* WARP_PANELS: the panel bookkeeping of the inner integral lives in the lanes of the warp (di_fast.cuh: di_inner_partial_warp);
-   the host selects it when the configured plan never has more than 31 panels on a side (the default plan: 29) */
-template <bool WARP_PANELS>
+/* Lane layout (di_fast.cuh): the lanes of a warp are 32 / n_panel groups of n_panel lanes; a group owns ONE outer line-of-sight node
+   at a time and walks through the panels of its inner integral in sequence (lane = node of the panel), so the outer nodes in flight
+   fill the warp whatever their panel counts are.  (Until round 2 a warp held one outer node and spread its panels over the lanes, five
+   at a time: with ~8 mirror pairs and ~3 single panels per outer node 30 % of the sweeps ran empty, and every lane paid the set-up of
+   every outer node.) */
 __global__ void __launch_bounds__(kDIThreads, 1) di_items_smem_kernel(
     const __grid_constant__ Tables t, const __grid_constant__ Options o, const __grid_constant__ Rules q,
     const __grid_constant__ CompactHeader ch, const uint4 *__restrict__ blob, const int stage_bytes,
@@ -302,22 +306,22 @@ __global__ void __launch_bounds__(kDIThreads, 1) di_items_smem_kernel(
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n_threads = blockDim.x, n_warps = n_threads >> 5;
-    /* layout: [compact blob prefix][line-of-sight table][tail powers, panel rule][per-warp renormalisation rows][per-warp state] */
+    const int n_threads = blockDim.x;
+    const int np = q.n_panel_di, ppi = 32 / np;             /* n_panel_di <= 32: the host checks */
+    const int grp = lane / np, j = lane - grp * np;
+    /* layout: [compact blob prefix][line-of-sight table][tail powers, panel rule][per-warp state] */
     double2 *los_s = reinterpret_cast<double2 *>(smem + stage_bytes);
     double *small = reinterpret_cast<double *>(los_s + (size_t)kLosStride * los_stage_n);
-    double2 *rows = reinterpret_cast<double2 *>(small + kDISmallDoubles);
-    double2 *row = rows + (size_t)warp * t.ren2d.n;
-    DIWarpState *ws_all = reinterpret_cast<DIWarpState *>(rows + (size_t)n_warps * t.ren2d.n);
+    DIWarpState *ws_all = reinterpret_cast<DIWarpState *>(small + kDISmallDoubles);
     {
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
         for (int i = tid; i < stage_bytes / 16; i += n_threads) dst[i] = blob[i];
         for (int i = tid; i < kLosStride * los_stage_n; i += n_threads) los_s[i] = t.los.v[i];
         if (tid < kMaxTail) small[tid] = q.rpow_di[tid];
-        const int np = q.n_panel_di < 32 ? q.n_panel_di : 32;
         if (tid < np) {
-            small[kMaxTail + tid] = q.gl_x[rule_offset(q.n_panel_di) + tid];
-            small[kMaxTail + 32 + tid] = q.gl_w[rule_offset(q.n_panel_di) + tid];
+            small[kMaxTail + tid] = q.gl_x[rule_offset(np) + tid];
+            small[kMaxTail + 32 + tid] = q.gl_w[rule_offset(np) + tid];
+            small[kMaxTail + 64 + tid] = exp(q.tail_lnr_di * q.gl_x[rule_offset(np) + tid]);
         }
     }
     __syncthreads();
@@ -326,7 +330,7 @@ __global__ void __launch_bounds__(kDIThreads, 1) di_items_smem_kernel(
     ta.t = &t; ta.c.base = smem; ta.c.h = ch;
     Rules ql = q;
     ql.rpow_di = small;
-    if (q.n_panel_di <= 32) { ql.panel_x = small + kMaxTail; ql.panel_w = small + kMaxTail + 32; }
+    ql.panel_x = small + kMaxTail; ql.panel_w = small + kMaxTail + 32; ql.panel_p = small + kMaxTail + 64;
 
     for (;;) {
         unsigned int item = 0;
@@ -345,7 +349,7 @@ __global__ void __launch_bounds__(kDIThreads, 1) di_items_smem_kernel(
         __syncwarp();
         const DIConst k = ws.k;
         if (out_evals && lane == 0) out_evals[item] = di_fast_eval_count(ql, g, k);
-        double di = di_fast_partial<CompactAccess, WARP_PANELS>(ta, t, los_s, ql, g, k, row, 0, 1, lane, 32);
+        double di = di_fast_partial(ta, t, los_s, ql, g, k, grp < ppi ? grp : ppi, ppi, j);
         di = warp_sum(di);
         if (lane == 0) out[item] = di;
         __syncwarp();
@@ -494,9 +498,14 @@ Rules make_rules(const coffe_b200_ctx *ctx)
     q.n_outer = ctx->qc.n_outer;
     q.panel_w_mpc = ctx->qc.panel_w; q.panel_du = ctx->qc.panel_du; q.eps_min = ctx->qc.eps_min; q.tail_ratio = ctx->qc.tail_ratio;
     q.panel_w_di = ctx->qc.panel_w_di; q.panel_du_di = ctx->qc.panel_du_di;
-    q.panel_x = q.panel_w = nullptr;
+    q.panel_x = q.panel_w = q.panel_p = nullptr;
     q.panel_x_si = q.panel_w_si = nullptr;
     q.rpow_di = ctx->d_rpow_di; q.tail_ratio_di = ctx->qc.tail_ratio_di; q.geo_shift_di = ctx->qc.geo_shift_di;
+    q.n_ren = ctx->qc.n_ren;
+    q.tail_lnr = ctx->qc.tail_log ? std::log(ctx->qc.tail_ratio) : 0.0;
+    q.tail_lnr_di = ctx->qc.tail_log_di ? std::log(ctx->qc.tail_ratio_di) : 0.0;
+    q.geo_L = ctx->qc.geo_growth > 1.0 ? std::log(ctx->qc.geo_growth) : 0.0;
+    q.geo_L_di = ctx->qc.geo_growth_di > 1.0 ? std::log(ctx->qc.geo_growth_di) : 0.0;
     return q;
 }
 
@@ -616,7 +625,7 @@ int launch_integrated(coffe_b200_ctx *ctx, Batch &b, const int mode, unsigned in
     if (stage_n > ctx->layout.los_n) stage_n = ctx->layout.los_n;
     const size_t los_bytes = (size_t)kLosStride * stage_n * sizeof(double2);
     const size_t row_bytes = (size_t)(ctx->layout.has_divergent ? ctx->layout.ren2d_n : 0) * sizeof(double2);
-    if (ctx->variant == 1 && ctx->compact.h.valid && !ctx->o.midpoint) {
+    if (ctx->variant == 1 && ctx->compact.h.valid && !ctx->o.midpoint && (mode == 1 || ctx->qc.n_panel_di <= 32)) {
         /* shared-memory tables: blob prefix covering R <= 2 chi_max, line-of-sight table, per-warp state */
         const int stage_bytes = compact_stage_bytes(ctx->compact, 2.0 * b.chi_max);
         CompactHeader ch = ctx->compact.h;
@@ -627,7 +636,7 @@ int launch_integrated(coffe_b200_ctx *ctx, Batch &b, const int mode, unsigned in
            warp-held bookkeeping is selected (they would not fit next to the renormalisation columns) */
         const bool si_warp_panels = ctx->qc.n_panel_si <= 32 && si_side_panels(ctx->qc, std::max(2.0e4, 1.01 * ctx->layout.chi_max_table)) <= 63;
         const size_t per_warp = mode == 1 ? sizeof(SIWarpState) + row_bytes + (si_warp_panels ? 0 : (size_t)2 * panel_cap * sizeof(double))
-                                          : sizeof(DIWarpState) + row_bytes;
+                                          : sizeof(DIWarpState);
         /* as many warps per SM as the remaining shared memory carries (the kernels are latency-bound: more is faster) */
         int warps = mode == 1 ? kSIThreads / 32 : kDIThreads / 32;
         if (mode == 2 && fixed < (size_t)ctx->smem_optin) warps = std::min<int>(warps, (int)(((size_t)ctx->smem_optin - fixed) / per_warp));
@@ -645,9 +654,7 @@ int launch_integrated(coffe_b200_ctx *ctx, Batch &b, const int mode, unsigned in
                     L.point.p, L.mu.p, L.n, stage_n, si_warp_panels ? 0 : panel_cap, L.val.p, evals, ctx->d_counter);
             }
             else {
-                const bool warp_panels = ctx->qc.n_panel_di <= 32 &&
-                                         di_side_panels(ctx->qc, std::max(2.0e4, 1.01 * ctx->layout.chi_max_table)) <= 31;
-                auto kernel = warp_panels ? di_items_smem_kernel<true> : di_items_smem_kernel<false>;
+                auto kernel = di_items_smem_kernel;
                 CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
                 kernel<<<grid, threads, need, ctx->stream>>>(
                     ctx->t, ctx->o, make_rules(ctx), ch, reinterpret_cast<const uint4 *>(ctx->d_blob), stage_bytes, b.pz.p, b.psep.p,
@@ -660,7 +667,7 @@ int launch_integrated(coffe_b200_ctx *ctx, Batch &b, const int mode, unsigned in
         }
     }
     ctx->last_variant = 0;
-    size_t smem = los_bytes + kItemWarps * row_bytes;
+    size_t smem = los_bytes;
     if (smem > 160 * 1024) { ctx->err = "line-of-sight table does not fit in shared memory"; return COFFE_B200_EINVAL; }
     CK(cudaFuncSetAttribute(integrated_items_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     integrated_items_kernel<<<L.n, kItemThreads, smem, ctx->stream>>>(
@@ -1185,6 +1192,8 @@ int coffe_b200_get_quadrature(const coffe_b200_ctx *ctx, coffe_b200_quadrature *
     q->n_z = c.n_z; q->panel_width = c.panel_w; q->panel_uniform_extent = c.panel_du; q->eps_min = c.eps_min; q->tail_ratio = c.tail_ratio;
     q->n_mu_panel_di = c.n_mu_panel_di; q->panel_width_di = c.panel_w_di; q->panel_uniform_extent_di = c.panel_du_di;
     q->mu_panel_width_di = c.mu_panel_w_di; q->tail_ratio_di = c.tail_ratio_di; q->geometric_shift_di = c.geo_shift_di;
+    q->geometric_growth = c.geo_growth; q->geometric_growth_di = c.geo_growth_di; q->n_renorm = c.n_ren;
+    q->tail_map = c.tail_log ? 2 : 1; q->tail_map_di = c.tail_log_di ? 2 : 1;
     q->accuracy_target = ctx->target_in_force;
     return COFFE_B200_OK;
 }

@@ -19,10 +19,14 @@ struct Rules {
     double panel_w_mpc, panel_du, eps_min, tail_ratio;
     double panel_w_di, panel_du_di;  /* panel plan of the inner integral of the integrated x integrated piece */
     const double *panel_x, *panel_w; /* nodes / weights of the n_panel_di rule when staged separately (else null: read from the bank) */
+    const double *panel_p;           /* tail_ratio_di^x_j for the nodes of that rule, when staged (log-mapped tail panels) */
     const double *panel_x_si, *panel_w_si;   /* the same for the n_panel_si rule */
     const double *rpow_di;           /* tail_ratio_di^n, n < kMaxTail */
     double tail_ratio_di;
     int geo_shift_di;
+    int n_ren;                       /* nodes of the inner rule of renormalization(l1, l2) (di_fast.cuh: di_ren_smooth_partial), even */
+    double tail_lnr, tail_lnr_di;    /* log of the tail ratio when the tail panels carry their nodes in log(d) (quadrature.cuh); 0 = in d */
+    double geo_L, geo_L_di;          /* log of the growth factor of the sinh-map geometric panels (quadrature.cuh); 0 = doubling panels */
 };
 
 /* panels one ridge_integrate call can hold in its scratch area (engine.cu checks the configured plan) */
@@ -39,7 +43,7 @@ COFFE_HD double ridge_integrate(const F &f, const double hi, const double center
 {
     const bool staged = q.panel_x_si && n_panel == q.n_panel_si;
     const double *panel_x = staged ? q.panel_x_si : q.gl_x + rule_offset(n_panel), *panel_w = staged ? q.panel_w_si : q.gl_w + rule_offset(n_panel);
-    const PanelPlan plan = panel_plan(eps, q.eps_min, q.panel_w_mpc, q.panel_du, q.tail_ratio, q.rpow);
+    const PanelPlan plan = panel_plan(eps, q.eps_min, q.panel_w_mpc, q.panel_du, q.tail_ratio, q.rpow, 1, q.geo_L, q.tail_lnr);
     /* negative side: |d| in [a_neg, b_neg]; positive side: |d| in [0, b_pos] (center >= 0 always) */
     const double b_neg = center;
     const double a_neg = center > hi ? center - hi : 0.0;
@@ -48,16 +52,19 @@ COFFE_HD double ridge_integrate(const F &f, const double hi, const double center
     const int k_pos = b_pos > 0.0 ? panel_count(plan, b_pos) : 0;
     int total = k_neg + k_pos;
     if (total > kMaxPanels) total = kMaxPanels;
+    /* scratch: the ends of every clipped panel in the variable of its rule (quadrature.cuh: panel_map) */
     for (int p = lane; p < total; p += nlanes) {
         const bool neg = p < k_neg;
         const int k = neg ? p : p - k_neg;
         double lo = panel_break(plan, k), up = panel_break(plan, k + 1);
         const double a = neg ? a_neg : 0.0, b = neg ? b_neg : b_pos;
-        if (lo < a) lo = a;
-        if (up > b) up = b;
-        const double width = up > lo ? up - lo : 0.0;
-        scratch[2 * p] = neg ? center - lo : center + lo;
-        scratch[2 * p + 1] = neg ? -width : width;
+        const bool lo_cl = lo < a, up_cl = up > b;
+        if (lo_cl) lo = a;
+        if (up_cl) up = b;
+        if (!(up > lo)) up = lo;
+        else panel_map_ends(plan, panel_map(plan, k), k, lo, up, lo_cl, up_cl, lo, up);
+        scratch[2 * p] = lo;
+        scratch[2 * p + 1] = up;
     }
     COFFE_SYNC_LANES();
     double acc = 0.0;
@@ -67,17 +74,26 @@ COFFE_HD double ridge_integrate(const F &f, const double hi, const double center
         if (lp < ppi) {
             const double xj = panel_x[j], wj = panel_w[j];
             for (int p = lp; p < total; p += ppi) {
-                const double a = scratch[2 * p], w = scratch[2 * p + 1];
-                if (w == 0.0) continue;
-                acc += fabs(w) * wj * f(a + w * xj);
+                const double s0 = scratch[2 * p], s1 = scratch[2 * p + 1];
+                if (!(s1 > s0)) continue;
+                const bool neg = p < k_neg;
+                double d, wgt;
+                panel_node_ends(plan, panel_map(plan, neg ? p : p - k_neg), s0, s1, xj, wj, d, wgt);
+                acc += wgt * f(neg ? center - d : center + d);
             }
         }
     }
     else {
         for (int p = 0; p < total; ++p) {
-            const double a = scratch[2 * p], w = scratch[2 * p + 1];
-            if (w == 0.0) continue;
-            for (int jj = lane; jj < n_panel; jj += nlanes) acc += fabs(w) * panel_w[jj] * f(a + w * panel_x[jj]);
+            const double s0 = scratch[2 * p], s1 = scratch[2 * p + 1];
+            if (!(s1 > s0)) continue;
+            const bool neg = p < k_neg;
+            const int mapped = panel_map(plan, neg ? p : p - k_neg);
+            for (int jj = lane; jj < n_panel; jj += nlanes) {
+                double d, wgt;
+                panel_node_ends(plan, mapped, s0, s1, panel_x[jj], panel_w[jj], d, wgt);
+                acc += wgt * f(neg ? center - d : center + d);
+            }
         }
     }
     COFFE_SYNC_LANES();
@@ -88,7 +104,7 @@ COFFE_HD double ridge_integrate(const F &f, const double hi, const double center
    the index arithmetic but no evaluation, so they are not counted) */
 COFFE_HD unsigned int ridge_eval_count(const double hi, const double center, const double eps, const Rules &q, const int n_panel)
 {
-    const PanelPlan plan = panel_plan(eps, q.eps_min, q.panel_w_mpc, q.panel_du, q.tail_ratio, q.rpow);
+    const PanelPlan plan = panel_plan(eps, q.eps_min, q.panel_w_mpc, q.panel_du, q.tail_ratio, q.rpow, 1, q.geo_L, q.tail_lnr);
     const double b_neg = center, a_neg = center > hi ? center - hi : 0.0, b_pos = hi - center;
     const int k_neg = panel_count(plan, b_neg);
     const int k_pos = b_pos > 0.0 ? panel_count(plan, b_pos) : 0;
@@ -148,7 +164,7 @@ __device__ __forceinline__ double si_half_partial_warp(const TA &t, const LosVie
     const int lp = lane / np, j = lane - lp * np;
     const bool on = lp < ppi;
     const double center = h.cs * g.c, eps = h.cs * sqrt(g.s2), hi = h.co;
-    const PanelPlan plan = panel_plan(eps, q.eps_min, q.panel_w_mpc, q.panel_du, q.tail_ratio, q.rpow);
+    const PanelPlan plan = panel_plan(eps, q.eps_min, q.panel_w_mpc, q.panel_du, q.tail_ratio, q.rpow, 1, q.geo_L, q.tail_lnr);
     /* breaks B_0 .. B_63 in two registers per lane (the default plan needs up to 36 per side: 18 geometric from the eps floor,
        3 uniform, 15 tail panels at ratio 1.5) */
     const double brk0 = panel_break(plan, lane), brk1 = panel_break(plan, lane + 32);
@@ -166,13 +182,14 @@ __device__ __forceinline__ double si_half_partial_warp(const TA &t, const LosVie
         const double up0 = __shfl_sync(full, brk0, (k + 1) & 31), up1 = __shfl_sync(full, brk1, (k + 1) & 31);
         double lo = k < 32 ? lo0 : lo1, up = k + 1 < 32 ? up0 : up1;
         const double a = neg ? a_neg : 0.0, b = neg ? b_neg : b_pos;
-        if (lo < a) lo = a;
-        if (up > b) up = b;
+        const bool lo_cl = lo < a, up_cl = up > b;
+        if (lo_cl) lo = a;
+        if (up_cl) up = b;
         if (on && e < n_all && up > lo) {
-            const double w = up - lo;
-            const double d = fma(w, xj, lo);
+            double d, wgt;
+            panel_node(plan, k, lo, up, lo_cl, up_cl, xj, wj, d, wgt);
             const double lambda = neg ? center - d : center + d;
-            acc = fma(w * wj, si_half_eval(t, h, g, lambda, los_eval(los, lv.n, lv.inv_h, lambda)), acc);
+            acc = fma(wgt, si_half_eval(t, h, g, lambda, los_eval(los, lv.n, lv.inv_h, lambda)), acc);
         }
     }
     return acc / h.co;

@@ -28,19 +28,36 @@ struct PanelPlan {
     int J;          /* B_k = eps 2^(shift (k-1)) for 1 <= k <= J */
     int M;          /* B_k = B_J + (k-J) W for J < k <= J+M */
     double BJ, BJM;
+    double L;       /* > 0: the sinh map.  B_k = eps sinh(k L) for k <= J with J L = asinh(W / eps), i.e. B_J = W exactly, and the
+                       nodes of a geometric panel are Gauss-Legendre in t = asinh(d / eps) (panel_node) */
+    double lnr;     /* > 0: log(ratio), and the nodes of a tail panel are Gauss-Legendre in log(d): the tails are power laws times
+                       line-of-sight factors that are polynomials in d, entire in log(d), whereas in d a panel [b, ratio b] sees
+                       the singularity of d^-p at the origin (rho = 3.7 for ratio 3, 2 for ratio 9) */
 };
 
 COFFE_HD PanelPlan panel_plan(double eps, const double eps_min, const double W, const double Du, const double ratio, const double *rpow,
-                              const int shift = 1)
+                              const int shift = 1, const double geo_L = 0.0, const double tail_lnr = 0.0)
 {
     PanelPlan p;
+    p.lnr = tail_lnr;
     p.rpow = rpow;
     p.shift = shift;
     if (eps < eps_min) eps = eps_min;
     p.eps = eps; p.W = W; p.ratio = ratio;
+    p.L = 0.0;
     int J = 0;
     double b = 0.0;
-    if (eps < W) {          /* otherwise the cusp is wider than a uniform panel: uniform panels from d = 0 */
+    if (eps < W && geo_L > 0.0) {
+        /* sinh map: f(sqrt(d^2 + eps^2)) = f(eps cosh t) under d = eps sinh t has its singularities at t = +- i pi/2 whatever the
+           panel, so a Gauss-Legendre rule in t converges like rho^(-2n) with (rho - 1/rho) = 2 pi / L on a panel of length L in t:
+           rho = 4.7 for L = ln 4.  The region [0, W] is cut into J equal panels in t, the fewest with L <= geo_L. */
+        const double T = asinh(W / eps);
+        J = (int)ceil(T / geo_L);
+        if (J < 1) J = 1;
+        p.L = T / J;
+        b = W;
+    }
+    else if (eps < W) {          /* otherwise the cusp is wider than a uniform panel: uniform panels from d = 0 */
         /* J - 1 = smallest m >= 1 with eps 2^(shift m) >= W, from the exponents (exact: the same J and B_J as repeated doubling) */
         const int e0 = ilogb(W) - ilogb(eps);
         const int n = ldexp(eps, e0) >= W ? e0 : e0 + 1;         /* smallest n with eps 2^n >= W; n >= 1 here */
@@ -57,6 +74,7 @@ COFFE_HD PanelPlan panel_plan(double eps, const double eps_min, const double W, 
 COFFE_HD double panel_break(const PanelPlan &p, const int k)
 {
     if (k <= 0) return 0.0;
+    if (p.L > 0.0 && k <= p.J) return k == p.J ? p.BJ : p.eps * sinh(k * p.L);
     if (k <= p.J) return ldexp(p.eps, p.shift * (k - 1));
     if (k <= p.J + p.M) return p.BJ + (k - p.J) * p.W;
     const int n = k - p.J - p.M;
@@ -75,6 +93,10 @@ COFFE_HD int panel_count(const PanelPlan &p, const double b)
         return k + n;
     }
     if (b > p.BJ || p.J == 0) return p.J + (int)ceil((b - p.BJ) / p.W);
+    if (p.L > 0.0) {
+        k = (int)ceil(asinh(b / p.eps) / p.L);
+        return k < 1 ? 1 : k > p.J ? p.J : k;
+    }
     double e = p.eps;
     while (e < b) { e = ldexp(e, p.shift); ++k; }
     return k;
@@ -90,6 +112,53 @@ COFFE_HD int panel_count_by_break(const PanelPlan &p, const double b)
     int k = 1;
     while (k < k_max && panel_break(p, k) < b) ++k;
     return k;
+}
+
+/* Node and weight (in |d|) of abscissa x (weight w, rule on [0,1]) of panel k clipped to [lo, up]: Gauss-Legendre in d, or in
+   t = asinh(d / eps) on the geometric panels of a sinh-map plan.  lo_clipped / up_clipped: that end is not the panel's own break. */
+/* variable of the rule of panel k: 0 = d, 1 = t = asinh(d / eps) (geometric panels of a sinh-map plan), 2 = log(d) (tail panels
+   of a log-tail plan) */
+COFFE_HD int panel_map(const PanelPlan &p, const int k) { return (p.L > 0.0 && k < p.J) ? 1 : (p.lnr > 0.0 && k >= p.J + p.M) ? 2 : 0; }
+
+/* the same from the panel's ends s0 < s1 in the variable of its rule */
+COFFE_HD void panel_node_ends(const PanelPlan &p, const int map, const double s0, const double s1, const double x, const double w,
+                              double &d, double &wgt)
+{
+    const double h = s1 - s0;
+    if (map == 1) {
+        const double e = exp(fma(h, x, s0)), ie = 1.0 / e;
+        d = (0.5 * p.eps) * (e - ie);
+        wgt = (0.5 * p.eps) * (e + ie) * (h * w);
+        return;
+    }
+    if (map == 2) {
+        d = exp(fma(h, x, s0));
+        wgt = d * (h * w);
+        return;
+    }
+    d = fma(h, x, s0);
+    wgt = h * w;
+}
+
+/* the ends of panel k clipped to [lo, up] in the variable of its rule (lo > 0 on a tail panel) */
+COFFE_HD void panel_map_ends(const PanelPlan &p, const int map, const int k, const double lo, const double up, const bool lo_clipped,
+                             const bool up_clipped, double &s0, double &s1)
+{
+    if (map == 1) {
+        s0 = lo_clipped ? asinh(lo / p.eps) : k * p.L;
+        s1 = up_clipped ? asinh(up / p.eps) : (k + 1) * p.L;
+    }
+    else if (map == 2) { s0 = log(lo); s1 = log(up); }
+    else { s0 = lo; s1 = up; }
+}
+
+COFFE_HD void panel_node(const PanelPlan &p, const int k, const double lo, const double up, const bool lo_clipped, const bool up_clipped,
+                         const double x, const double w, double &d, double &wgt)
+{
+    const int map = panel_map(p, k);
+    double s0, s1;
+    panel_map_ends(p, map, k, lo, up, lo_clipped, up_clipped, s0, s1);
+    panel_node_ends(p, map, s0, s1, x, w, d, wgt);
 }
 
 /* runtime quadrature configuration (mirrors coffe_b200_quadrature, include/coffe_b200.h) */
@@ -111,6 +180,10 @@ struct QuadConfig {
     double mu_panel_w_di;   /* width of the uniform r_perp panels of its mu rule */
     double tail_ratio_di;   /* growth factor of its tail panels */
     int geo_shift_di;       /* log2 of the growth factor of its geometric panels (1 or 2) */
+    /* growth factor per geometric panel under the sinh map (panel_plan); <= 1: the doubling panels with Gauss-Legendre nodes in d */
+    double geo_growth, geo_growth_di;
+    int tail_log, tail_log_di;     /* tail panels with Gauss-Legendre nodes in log(d) instead of d */
+    int n_ren;              /* nodes of the inner rule of renormalization(l1, l2) in the integrated x integrated piece (even) */
 };
 
 /* bank of Gauss-Legendre rules on [0,1] for n = 1..kMaxRule, rule n stored at offset n(n-1)/2 */

@@ -22,7 +22,10 @@ inline QuadConfig default_quadrature()
     q.n_panel_si = 8; q.n_panel_di = 8;
     q.n_z = 8;
     q.panel_w = 64.0; q.panel_du = 128.0; q.eps_min = 1e-3; q.tail_ratio = 1.5;
-    q.n_mu_panel_di = 5; q.panel_w_di = 64.0; q.panel_du_di = 128.0; q.mu_panel_w_di = 64.0; q.tail_ratio_di = 2.5; q.geo_shift_di = 1;
+    q.n_mu_panel_di = 5; q.panel_w_di = 64.0; q.panel_du_di = 192.0; q.mu_panel_w_di = 64.0; q.tail_ratio_di = 6.0; q.geo_shift_di = 1;
+    q.geo_growth = 1.0; q.geo_growth_di = 8.0;
+    q.n_ren = 32;
+    q.tail_log = 0; q.tail_log_di = 1;
     return q;
 }
 
@@ -37,7 +40,7 @@ inline QuadConfig default_quadrature()
 inline QuadConfig total_target_quadrature()
 {
     QuadConfig q = default_quadrature();
-    q.n_panel_di = 6; q.tail_ratio_di = 3.0; q.n_mu_panel_di = 4;
+    q.n_panel_di = 6; q.n_mu_panel_di = 4;
     q.mu_panel_w = 64.0; q.n_mu_panel = 7; q.n_panel_si = 6;
     q.mu_rho0 = 8.0;
     return q;
@@ -66,13 +69,26 @@ inline QuadConfig merge_quadrature(const QuadConfig &base, const coffe_b200_quad
     if (u.mu_panel_width_di > 0) q.mu_panel_w_di = u.mu_panel_width_di;
     if (u.tail_ratio_di > 1.0) q.tail_ratio_di = u.tail_ratio_di;
     if (u.geometric_shift_di > 0) q.geo_shift_di = u.geometric_shift_di;
+    if (u.geometric_growth > 0) q.geo_growth = u.geometric_growth;
+    if (u.geometric_growth_di > 0) q.geo_growth_di = u.geometric_growth_di;
+    if (u.n_renorm > 0) q.n_ren = u.n_renorm & ~1;
+    if (u.tail_map > 0) q.tail_log = u.tail_map == 2;
+    if (u.tail_map_di > 0) q.tail_log_di = u.tail_map_di == 2;
     return q;
+}
+
+/* upper bound on the geometric panels of one side: doubling panels (x 2^shift), or the sinh map with `growth` per panel */
+inline int geometric_panels(const double eps_min, const double W, const int shift, const double growth)
+{
+    if (!(eps_min < W)) return 0;
+    if (growth > 1.0) return (int)std::ceil(std::asinh(W / eps_min) / std::log(growth)) + 1;
+    return (int)std::ceil(std::log2(W / eps_min) / shift) + 2;
 }
 
 /* upper bound on the panels of one line-of-sight integral (both sides of the ridge) */
 inline int max_panels(const QuadConfig &q, const double extent = 2.0e4)
 {
-    const int geo = q.eps_min < q.panel_w ? (int)std::ceil(std::log2(q.panel_w / q.eps_min)) + 2 : 0;
+    const int geo = geometric_panels(q.eps_min, q.panel_w, 1, q.geo_growth);
     const int uni = (int)std::ceil(q.panel_du / q.panel_w) + 1;
     const double start = std::max(q.panel_du, q.panel_w);
     const int tail = extent > start ? (int)std::ceil(std::log(extent / start) / std::log(q.tail_ratio)) + 2 : 0;
@@ -83,7 +99,7 @@ inline int max_panels(const QuadConfig &q, const double extent = 2.0e4)
 /* upper bound on the panels of ONE side of the ridge of the integrated x integrated plan (its own knobs) */
 inline int di_side_panels(const QuadConfig &q, const double extent = 2.0e4)
 {
-    const int geo = q.eps_min < q.panel_w_di ? (int)std::ceil(std::log2(q.panel_w_di / q.eps_min) / q.geo_shift_di) + 2 : 0;
+    const int geo = geometric_panels(q.eps_min, q.panel_w_di, q.geo_shift_di, q.geo_growth_di);
     const int uni = (int)std::ceil(q.panel_du_di / q.panel_w_di) + 1;
     const double start = std::max(q.panel_du_di, q.panel_w_di);
     const int tail = extent > start ? (int)std::ceil(std::log(extent / start) / std::log(q.tail_ratio_di)) + 2 : 0;
@@ -94,7 +110,7 @@ inline int di_side_panels(const QuadConfig &q, const double extent = 2.0e4)
 /* the same bound for the local x integrated plan */
 inline int si_side_panels(const QuadConfig &q, const double extent = 2.0e4)
 {
-    const int geo = q.eps_min < q.panel_w ? (int)std::ceil(std::log2(q.panel_w / q.eps_min)) + 2 : 0;
+    const int geo = geometric_panels(q.eps_min, q.panel_w, 1, q.geo_growth);
     const int uni = (int)std::ceil(q.panel_du / q.panel_w) + 1;
     const double start = std::max(q.panel_du, q.panel_w);
     const int tail = extent > start ? (int)std::ceil(std::log(extent / start) / std::log(q.tail_ratio)) + 2 : 0;
@@ -112,7 +128,7 @@ inline bool quadrature_valid(const QuadConfig &q, const int panel_capacity)
            q.panel_w > 0 && q.panel_du >= 0 && q.eps_min > 0 && q.tail_ratio > 1.0 &&
            q.mu_rho0 > 0 && q.mu_panel_w > 0 && q.mu_du >= 0 &&
            q.n_mu_panel_di >= 2 && q.n_mu_panel_di <= kMaxRule && q.panel_w_di > 0 && q.panel_du_di >= 0 && q.mu_panel_w_di > 0 && q.tail_ratio_di > 1.0 &&
-           q.geo_shift_di >= 1 && q.geo_shift_di <= 3;
+           q.geo_shift_di >= 1 && q.geo_shift_di <= 3 && q.geo_growth >= 0 && q.geo_growth_di >= 0 && q.n_ren >= 2 && q.n_ren <= 2 * kMaxRule;
 }
 
 /* bank of Gauss-Legendre rules on [0,1], rule n at offset n(n-1)/2 */

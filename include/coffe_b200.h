@@ -130,6 +130,18 @@ typedef struct coffe_b200_quadrature {
        2 = COFFE_B200_TARGET_TOTAL: the returned multipole within 1e-5 of the l = 0..4 scale of the point; the integrated pieces are
            then at most a few per cent of the total and carry coarser rules (0.7 of the evaluations). */
     int accuracy_target;
+    /* Geometric panels of the line-of-sight plans under the sinh map d = eps sinh(t) (eps = impact parameter of the two lines of
+       sight, d = distance from their closest approach): the region |d| < panel_width is cut into equal panels in t with a growth
+       factor of at most this per panel, Gauss-Legendre nodes in t (quadrature.cuh: panel_plan).  0 = library default, (0, 1] = off
+       (doubling panels with nodes in d, the round-1 scheme), > 1 = growth factor.  First: local x integrated, second: integrated
+       x integrated. */
+    double geometric_growth, geometric_growth_di;
+    /* nodes of the inner rule of renormalization(lambda_1, lambda_2) in the integrated x integrated piece: two Gauss-Legendre panels
+       split at the diagonal, this many nodes together (even; default 32 = one per lane).  I^4_0(R) stays on the ridge panels. */
+    int n_renorm;
+    /* variable of the Gauss-Legendre nodes on the tail panels beyond the uniform extent: 0 = library default, 1 = d, 2 = log(d)
+       (power-law tails are entire functions of log(d): wider panels at the same node count).  First: local x integrated. */
+    int tail_map, tail_map_di;
 } coffe_b200_quadrature;
 enum { COFFE_B200_TARGET_AUTO = 0, COFFE_B200_TARGET_PIECE = 1, COFFE_B200_TARGET_TOTAL = 2 };
 

@@ -44,10 +44,15 @@ static void set_rules(HostSim *s)
     q.n_panel_si = s->qc.n_panel_si; q.n_panel_di = s->qc.n_panel_di; q.n_outer = s->qc.n_outer;
     q.panel_w_mpc = s->qc.panel_w; q.panel_du = s->qc.panel_du; q.eps_min = s->qc.eps_min; q.tail_ratio = s->qc.tail_ratio;
     q.panel_w_di = s->qc.panel_w_di; q.panel_du_di = s->qc.panel_du_di;
-    q.panel_x = q.panel_w = nullptr;
+    q.panel_x = q.panel_w = q.panel_p = nullptr;
     q.panel_x_si = q.panel_w_si = nullptr;
     s->rpow_di = build_rpow(s->qc.tail_ratio_di);
     q.rpow_di = s->rpow_di.data(); q.tail_ratio_di = s->qc.tail_ratio_di; q.geo_shift_di = s->qc.geo_shift_di;
+    q.n_ren = s->qc.n_ren;
+    q.tail_lnr = s->qc.tail_log ? std::log(s->qc.tail_ratio) : 0.0;
+    q.tail_lnr_di = s->qc.tail_log_di ? std::log(s->qc.tail_ratio_di) : 0.0;
+    q.geo_L = s->qc.geo_growth > 1.0 ? std::log(s->qc.geo_growth) : 0.0;
+    q.geo_L_di = s->qc.geo_growth_di > 1.0 ? std::log(s->qc.geo_growth_di) : 0.0;
 }
 
 extern "C" {
@@ -194,7 +199,6 @@ static void item_pieces(void *h, double z, double sep, double mu, int mask, doub
     }
     if (opt_has_integrated(o) && (mask & 4)) {
         const DIConst k = di_setup(o, e1, e2);
-        std::vector<double2> row(s->layout.has_divergent ? s->t.ren2d.n : 1);
         if (s->legacy_di) {
             /* the straightforward evaluator (di_eval on the same panels, no pairing): cross-check of di_fast.cuh */
             double scratch[2 * kMaxPanels];
@@ -204,12 +208,11 @@ static void item_pieces(void *h, double z, double sep, double mu, int mask, doub
             else out[2] = di_partial(ExactAccess{&s->t}, s->t.los, ql, g, k, s->t.los.v, 0, 1, 0, 1, scratch);
         }
         else {
-            /* the kernel's lane decomposition: n_lanes lanes in turn (1 = serial) */
-            const int nl = s->di_lanes;
+            /* the kernel's lane decomposition: the n_panel lanes of one group in turn */
             double acc = 0.0;
-            for (int lane = 0; lane < nl; ++lane) {
-                if (s->variant) acc += di_fast_partial(s->compact(), s->t, s->t.los.v, s->q, g, k, row.data(), 0, 1, lane, nl, true);
-                else acc += di_fast_partial(ExactAccess{&s->t}, s->t, s->t.los.v, s->q, g, k, row.data(), 0, 1, lane, nl, true);
+            for (int j = 0; j < s->q.n_panel_di; ++j) {
+                if (s->variant) acc += di_fast_partial(s->compact(), s->t, s->t.los.v, s->q, g, k, 0, 1, j);
+                else acc += di_fast_partial(ExactAccess{&s->t}, s->t, s->t.los.v, s->q, g, k, 0, 1, j);
             }
             out[2] = acc;
         }
