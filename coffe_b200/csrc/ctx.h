@@ -41,7 +41,7 @@ struct coffe_b200_ctx {
     struct MuRuleCache {
         std::vector<double> sep;
         QuadConfig qc;
-        int n_per_panel = 0; double panel_width = 0; bool half_only = false, active = false, valid = false;
+        int piece = 0; bool half_only = false, active = false, valid = false;
         std::vector<int> rule_begin;
         std::vector<double> rule_mu, rule_w;
     } mu_cache[2];

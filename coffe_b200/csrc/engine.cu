@@ -188,10 +188,31 @@ __global__ void __launch_bounds__(kItemThreads, COFFE_ITEM_MIN_BLOCKS) integrate
    weights of the inner panel rule */
 constexpr int kDISmallDoubles = kMaxTail + 3 * 32;
 
-struct SIWarpState {
-    EndVals e[2];
-    SIHalf h[2];
-};
+/* What an item needs before its line-of-sight integrals start: the values at its two end points (background, biases; a dozen
+   dependent spline lookups through L2) folded into the amplitudes of the two halves / of the integrated x integrated terms.  Computed
+   by item_setup_kernel, one THREAD per item, ahead of the integration kernels: inside them this chain ran on one or two lanes of a
+   warp while the other thirty waited (a third of the local x integrated kernel's time). */
+struct SIItemSetup { SIHalf h[2]; };
+struct DIItemSetup { DIConst k; };
+
+__global__ void item_setup_kernel(const __grid_constant__ Tables t, const __grid_constant__ Options o, const int mode,
+                                  const double *__restrict__ pz, const double *__restrict__ psep,
+                                  const int *__restrict__ item_point, const double *__restrict__ item_mu, const int n_items,
+                                  SIItemSetup *__restrict__ si_out, DIItemSetup *__restrict__ di_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    const int p = item_point[i];
+    const Geometry g = geometry(bg_chi(t.bg, pz[p]), psep[p], item_mu[i]);
+    /* redshift of the end points from the line-of-sight table (fifth slot), as the integration kernels read it along the way */
+    const EndVals e1 = end_eval_at(o, t, g.chi1, los_z(t.los.v, t.los.n, t.los.inv_h, g.chi1), 1);
+    const EndVals e2 = end_eval_at(o, t, g.chi2, los_z(t.los.v, t.los.n, t.los.inv_h, g.chi2), 2);
+    if (mode == 1) {
+        si_out[i].h[0] = si_half_setup(o, g, e1, e2, true);
+        si_out[i].h[1] = si_half_setup(o, g, e2, e1, false);
+    }
+    else di_out[i].k = di_setup(o, e1, e2);
+}
 
 constexpr int kSIThreads = 384;
 
@@ -204,7 +225,7 @@ __global__ void __launch_bounds__(kSIThreads, 1) si_items_smem_kernel(
     const __grid_constant__ Tables t, const __grid_constant__ Options o, const __grid_constant__ Rules q_in,
     const __grid_constant__ CompactHeader ch, const uint4 *__restrict__ blob, const int stage_bytes,
     const double *__restrict__ pz, const double *__restrict__ psep,
-    const int *__restrict__ item_point, const double *__restrict__ item_mu, const int n_items,
+    const int *__restrict__ item_point, const double *__restrict__ item_mu, const SIItemSetup *__restrict__ item_setup, const int n_items,
     const int los_stage_n, const int panel_cap, double *__restrict__ out,
     unsigned int *__restrict__ out_evals, unsigned int *__restrict__ counter)
 {
@@ -212,13 +233,12 @@ __global__ void __launch_bounds__(kSIThreads, 1) si_items_smem_kernel(
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int n_warps = kSIThreads / 32;
     const int n_col_max = t.has_divergent ? t.ren2d.n : 0;
-    /* layout: [compact blob prefix][line-of-sight table][tail powers, panel rule][per-warp columns][per-warp state][per-warp panel lists] */
+    /* layout: [compact blob prefix][line-of-sight table][tail powers, panel rule][per-warp columns][per-warp panel lists] */
     double2 *los_s = reinterpret_cast<double2 *>(smem + stage_bytes);
     double *small = reinterpret_cast<double *>(los_s + (size_t)kLosStride * los_stage_n);
     double2 *cols = reinterpret_cast<double2 *>(small + kDISmallDoubles);
     double2 *col = cols + (size_t)warp * n_col_max;
-    SIWarpState *ws_all = reinterpret_cast<SIWarpState *>(cols + (size_t)n_warps * n_col_max);
-    double *scratch = reinterpret_cast<double *>(ws_all + n_warps) + (size_t)warp * 2 * panel_cap;
+    double *scratch = reinterpret_cast<double *>(cols + (size_t)n_warps * n_col_max) + (size_t)warp * 2 * panel_cap;
     {
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
         for (int i = tid; i < stage_bytes / 16; i += kSIThreads) dst[i] = blob[i];
@@ -231,7 +251,6 @@ __global__ void __launch_bounds__(kSIThreads, 1) si_items_smem_kernel(
         }
     }
     __syncthreads();
-    SIWarpState &ws = ws_all[warp];
     CompactAccess ta;
     ta.t = &t; ta.c.base = smem; ta.c.h = ch;
     LosView lv = t.los;
@@ -249,19 +268,12 @@ __global__ void __launch_bounds__(kSIThreads, 1) si_items_smem_kernel(
         const int p = item_point[item];
         const double z = pz[p], sep = psep[p], mu = item_mu[item];
         const Geometry g = geometry(bg_chi(t.bg, z), sep, mu);
-        if (lane < 2) {
-            /* redshift of the end point from the staged line-of-sight table (fifth slot), not from a bisection of z(chi) through L2 */
-            const double chi_e = lane == 0 ? g.chi1 : g.chi2;
-            ws.e[lane] = end_eval_at(o, t, chi_e, los_z(los_s, lv.n, lv.inv_h, chi_e), lane + 1);
-        }
-        __syncwarp();
-        if (lane < 2) ws.h[lane] = si_half_setup(o, g, ws.e[lane], ws.e[1 - lane], lane == 0);
-        __syncwarp();
-        if (out_evals && lane == 0) out_evals[item] = si_eval_count(q, g, ws.h[0]) + si_eval_count(q, g, ws.h[1]);
+        const SIItemSetup *su = item_setup + item;
+        if (out_evals && lane == 0) out_evals[item] = si_eval_count(q, g, su->h[0]) + si_eval_count(q, g, su->h[1]);
         double si = 0.0;
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
-            const SIHalf h = ws.h[half];
+            const SIHalf h = su->h[half];
             if (h.need_ren) {
                 __syncwarp();           /* the previous half's readers are done */
                 ta.n_col = ren_row_count(t.ren2d, h.co);
@@ -281,11 +293,6 @@ __global__ void __launch_bounds__(kSIThreads, 1) si_items_smem_kernel(
     }
 }
 
-struct DIWarpState {
-    EndVals e[2];
-    DIConst k;
-};
-
 #ifndef COFFE_DI_THREADS
 #define COFFE_DI_THREADS 384
 #endif
@@ -300,19 +307,18 @@ __global__ void __launch_bounds__(kDIThreads, 1) di_items_smem_kernel(
     const __grid_constant__ Tables t, const __grid_constant__ Options o, const __grid_constant__ Rules q,
     const __grid_constant__ CompactHeader ch, const uint4 *__restrict__ blob, const int stage_bytes,
     const double *__restrict__ pz, const double *__restrict__ psep,
-    const int *__restrict__ item_point, const double *__restrict__ item_mu, const int n_items,
+    const int *__restrict__ item_point, const double *__restrict__ item_mu, const DIItemSetup *__restrict__ item_setup, const int n_items,
     const int los_stage_n, double *__restrict__ out,
     unsigned int *__restrict__ out_evals, unsigned int *__restrict__ counter)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int n_threads = blockDim.x;
     const int np = q.n_panel_di, ppi = 32 / np;             /* n_panel_di <= 32: the host checks */
     const int grp = lane / np, j = lane - grp * np;
-    /* layout: [compact blob prefix][line-of-sight table][tail powers, panel rule][per-warp state] */
+    /* layout: [compact blob prefix][line-of-sight table][tail powers, panel rule] */
     double2 *los_s = reinterpret_cast<double2 *>(smem + stage_bytes);
     double *small = reinterpret_cast<double *>(los_s + (size_t)kLosStride * los_stage_n);
-    DIWarpState *ws_all = reinterpret_cast<DIWarpState *>(small + kDISmallDoubles);
     {
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
         for (int i = tid; i < stage_bytes / 16; i += n_threads) dst[i] = blob[i];
@@ -325,7 +331,6 @@ __global__ void __launch_bounds__(kDIThreads, 1) di_items_smem_kernel(
         }
     }
     __syncthreads();
-    DIWarpState &ws = ws_all[warp];
     CompactAccess ta;
     ta.t = &t; ta.c.base = smem; ta.c.h = ch;
     Rules ql = q;
@@ -340,14 +345,7 @@ __global__ void __launch_bounds__(kDIThreads, 1) di_items_smem_kernel(
         const int p = item_point[item];
         const double z = pz[p], sep = psep[p], mu = item_mu[item];
         const Geometry g = geometry(bg_chi(t.bg, z), sep, mu);
-        if (lane < 2) {
-            const double chi_e = lane == 0 ? g.chi1 : g.chi2;
-            ws.e[lane] = end_eval_at(o, t, chi_e, los_z(los_s, t.los.n, t.los.inv_h, chi_e), lane + 1);
-        }
-        __syncwarp();
-        if (lane == 0) ws.k = di_setup(o, ws.e[0], ws.e[1]);
-        __syncwarp();
-        const DIConst k = ws.k;
+        const DIConst k = item_setup[item].k;
         if (out_evals && lane == 0) out_evals[item] = di_fast_eval_count(ql, g, k);
         double di = di_fast_partial(ta, t, los_s, ql, g, k, grp < ppi ? grp : ppi, ppi, j);
         di = warp_sum(di);
@@ -495,7 +493,7 @@ Rules make_rules(const coffe_b200_ctx *ctx)
     Rules q;
     q.gl_x = ctx->d_gl_x; q.gl_w = ctx->d_gl_w; q.rpow = ctx->d_rpow;
     q.n_panel_si = ctx->qc.n_panel_si; q.n_panel_di = ctx->qc.n_panel_di;
-    q.n_outer = ctx->qc.n_outer;
+    q.n_outer = ctx->qc.n_outer; q.n_outer_min = ctx->qc.n_outer_min; q.n_outer_step = ctx->qc.n_outer_step;
     q.panel_w_mpc = ctx->qc.panel_w; q.panel_du = ctx->qc.panel_du; q.eps_min = ctx->qc.eps_min; q.tail_ratio = ctx->qc.tail_ratio;
     q.panel_w_di = ctx->qc.panel_w_di; q.panel_du_di = ctx->qc.panel_du_di;
     q.panel_x = q.panel_w = q.panel_p = nullptr;
@@ -516,7 +514,11 @@ int apply_quadrature(coffe_b200_ctx *ctx, const bool want_pieces)
     int target = ctx->user_q.accuracy_target;
     if (target != COFFE_B200_TARGET_PIECE && target != COFFE_B200_TARGET_TOTAL)
         target = (!want_pieces && (ctx->o.den || ctx->o.rsd) && !ctx->o.midpoint) ? COFFE_B200_TARGET_TOTAL : COFFE_B200_TARGET_PIECE;
-    const QuadConfig merged = merge_quadrature(target == COFFE_B200_TARGET_TOTAL ? total_target_quadrature() : default_quadrature(), ctx->user_q);
+    QuadConfig base = target == COFFE_B200_TARGET_TOTAL ? total_target_quadrature() : default_quadrature();
+    /* potential terms without lensing: the integrated x integrated piece is then smooth in mu but its l = 4 moment sets the scale of
+       what 5 nodes per r_perp panel leave (1.0e-5 of the piece at r = 30 Mpc; 6 nodes: 1.9e-6, profiles/r2_piece_sweep_b.log) */
+    if (target != COFFE_B200_TARGET_TOTAL && !ctx->o.len && (ctx->o.g4 || ctx->o.g5)) base.n_mu_panel_di = 6;
+    const QuadConfig merged = merge_quadrature(base, ctx->user_q);
     if (!quadrature_valid(merged, kMaxPanels)) {
         ctx->err = "quadrature sizes out of range (node counts 2..128; the line-of-sight panel plan must fit " + std::to_string(kMaxPanels) + " panels)";
         return COFFE_B200_EINVAL;
@@ -592,6 +594,7 @@ struct ItemList {
     int n = 0;
     DevBuf<int> point, begin;       /* item -> point; point -> first item (n_points + 1) */
     DevBuf<double> mu, w, val;
+    DevBuf<unsigned char> setup;    /* SIItemSetup / DIItemSetup per item, (re)written by item_setup_kernel in front of every launch */
 };
 
 /* a batch of points with their mu items, on the device */
@@ -606,7 +609,7 @@ struct Batch {
     void release()
     {
         pz.release(); psep.release(); ni.release(); pm.release(); evals.release();
-        for (ItemList *L : {&si, &di}) { L->point.release(); L->begin.release(); L->mu.release(); L->w.release(); L->val.release(); L->n = 0; }
+        for (ItemList *L : {&si, &di}) { L->point.release(); L->begin.release(); L->mu.release(); L->w.release(); L->val.release(); L->setup.release(); L->n = 0; }
         n_points = 0;
     }
 };
@@ -635,15 +638,20 @@ int launch_integrated(coffe_b200_ctx *ctx, Batch &b, const int mode, unsigned in
         /* the local x integrated kernel is compiled for a fixed warp count: the scalar path's panel lists are dropped when the
            warp-held bookkeeping is selected (they would not fit next to the renormalisation columns) */
         const bool si_warp_panels = ctx->qc.n_panel_si <= 32 && si_side_panels(ctx->qc, std::max(2.0e4, 1.01 * ctx->layout.chi_max_table)) <= 63;
-        const size_t per_warp = mode == 1 ? sizeof(SIWarpState) + row_bytes + (si_warp_panels ? 0 : (size_t)2 * panel_cap * sizeof(double))
-                                          : sizeof(DIWarpState);
+        const size_t per_warp = mode == 1 ? row_bytes + (si_warp_panels ? 0 : (size_t)2 * panel_cap * sizeof(double)) : 0;
         /* as many warps per SM as the remaining shared memory carries (the kernels are latency-bound: more is faster) */
         int warps = mode == 1 ? kSIThreads / 32 : kDIThreads / 32;
-        if (mode == 2 && fixed < (size_t)ctx->smem_optin) warps = std::min<int>(warps, (int)(((size_t)ctx->smem_optin - fixed) / per_warp));
         const int threads = warps * 32;
         const size_t need = fixed + (size_t)warps * per_warp;
         if (warps >= 4 && need <= (size_t)ctx->smem_optin) {
             CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int), ctx->stream));
+            /* end-point values and amplitudes of every item, one thread each */
+            const size_t setup_bytes = (size_t)L.n * (mode == 1 ? sizeof(SIItemSetup) : sizeof(DIItemSetup));
+            if (L.setup.n != setup_bytes) CK(L.setup.alloc(setup_bytes));
+            item_setup_kernel<<<(L.n + 127) / 128, 128, 0, ctx->stream>>>(ctx->t, ctx->o, mode, b.pz.p, b.psep.p, L.point.p, L.mu.p, L.n,
+                                                                         reinterpret_cast<SIItemSetup *>(L.setup.p), reinterpret_cast<DIItemSetup *>(L.setup.p));
+            CK(cudaGetLastError());
+            ctx->last_launches += 1;
             int grid = std::min(ctx->n_sm, (L.n + warps - 1) / warps);
             if (grid < 1) grid = 1;
             if (mode == 1) {
@@ -651,14 +659,14 @@ int launch_integrated(coffe_b200_ctx *ctx, Batch &b, const int mode, unsigned in
                 CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
                 kernel<<<grid, threads, need, ctx->stream>>>(
                     ctx->t, ctx->o, make_rules(ctx), ch, reinterpret_cast<const uint4 *>(ctx->d_blob), stage_bytes, b.pz.p, b.psep.p,
-                    L.point.p, L.mu.p, L.n, stage_n, si_warp_panels ? 0 : panel_cap, L.val.p, evals, ctx->d_counter);
+                    L.point.p, L.mu.p, reinterpret_cast<const SIItemSetup *>(L.setup.p), L.n, stage_n, si_warp_panels ? 0 : panel_cap, L.val.p, evals, ctx->d_counter);
             }
             else {
                 auto kernel = di_items_smem_kernel;
                 CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
                 kernel<<<grid, threads, need, ctx->stream>>>(
                     ctx->t, ctx->o, make_rules(ctx), ch, reinterpret_cast<const uint4 *>(ctx->d_blob), stage_bytes, b.pz.p, b.psep.p,
-                    L.point.p, L.mu.p, L.n, stage_n, L.val.p, evals, ctx->d_counter);
+                    L.point.p, L.mu.p, reinterpret_cast<const DIItemSetup *>(L.setup.p), L.n, stage_n, L.val.p, evals, ctx->d_counter);
             }
             CK(cudaGetLastError());
             ctx->last_launches += 1;
@@ -730,12 +738,12 @@ int run_multipole_batch(coffe_b200_ctx *ctx, Batch &b, const LList &ls, const bo
    rule per distinct separation (`sep`, n_sep entries; point p uses rule point_rule[p]) and uploads those; the
    (point, mu, weight) items are expanded on the device. */
 int build_item_list(coffe_b200_ctx *ctx, const double *sep, const int n_sep, const std::vector<int> &point_rule, const DevBuf<int> &d_point_rule,
-                    const int n_per_panel, const double mu_panel_width, const bool half_only, const bool active, const int slot, ItemList &L)
+                    const int piece, const bool half_only, const bool active, const int slot, ItemList &L)
 {
     const int n = (int)point_rule.size();
     std::vector<int> point_begin(n + 1, 0);
     coffe_b200_ctx::MuRuleCache &mc = ctx->mu_cache[slot];
-    const bool hit = mc.valid && mc.n_per_panel == n_per_panel && mc.panel_width == mu_panel_width && mc.half_only == half_only &&
+    const bool hit = mc.valid && mc.piece == piece && mc.half_only == half_only &&
                      mc.active == active && (int)mc.sep.size() == n_sep && std::memcmp(&mc.qc, &ctx->qc, sizeof(QuadConfig)) == 0 &&
                      (n_sep == 0 || std::memcmp(mc.sep.data(), sep, sizeof(double) * n_sep) == 0);
     if (!hit) {
@@ -746,14 +754,14 @@ int build_item_list(coffe_b200_ctx *ctx, const double *sep, const int n_sep, con
         for (int r = 0; r < n_sep; ++r) {
             mc.rule_begin[r] = (int)mc.rule_mu.size();
             if (!active) continue;
-            build_mu_rule(ctx->qc, sep[r], mu, w, n_per_panel, mu_panel_width, half_only);
+            build_mu_rule(ctx->qc, sep[r], mu, w, piece, half_only);
             mc.rule_mu.insert(mc.rule_mu.end(), mu.begin(), mu.end());
             mc.rule_w.insert(mc.rule_w.end(), w.begin(), w.end());
         }
         mc.rule_begin[n_sep] = (int)mc.rule_mu.size();
         mc.sep.assign(sep, sep + n_sep);
         std::memcpy(&mc.qc, &ctx->qc, sizeof(QuadConfig));
-        mc.n_per_panel = n_per_panel; mc.panel_width = mu_panel_width; mc.half_only = half_only; mc.active = active;
+        mc.piece = piece; mc.half_only = half_only; mc.active = active;
         mc.valid = true;
     }
     const std::vector<int> &rule_begin = mc.rule_begin;
@@ -793,10 +801,10 @@ int build_multipole_batch(coffe_b200_ctx *ctx, const double *sep, const int n_se
     DevBuf<int> d_point_rule;
     CK(d_point_rule.upload(point_rule, ctx->stream));
     b.si_half = ctx->pops_identical && (ctx->mag_constant || !(ctx->o.d1 && ctx->o.len));
-    int rc = build_item_list(ctx, sep, n_sep, point_rule, d_point_rule, ctx->qc.n_mu_panel, ctx->qc.mu_panel_w, b.si_half, opt_has_si(ctx->o), 0, b.si);
+    int rc = build_item_list(ctx, sep, n_sep, point_rule, d_point_rule, 1, b.si_half, opt_has_si(ctx->o), 0, b.si);
     if (rc) return rc;
     b.di_half = ctx->di_mu_symmetric;
-    return build_item_list(ctx, sep, n_sep, point_rule, d_point_rule, ctx->qc.n_mu_panel_di, ctx->qc.mu_panel_w_di, b.di_half,
+    return build_item_list(ctx, sep, n_sep, point_rule, d_point_rule, 2, b.di_half,
                            opt_has_integrated(ctx->o), 1, b.di);
 }
 
@@ -1194,6 +1202,8 @@ int coffe_b200_get_quadrature(const coffe_b200_ctx *ctx, coffe_b200_quadrature *
     q->mu_panel_width_di = c.mu_panel_w_di; q->tail_ratio_di = c.tail_ratio_di; q->geometric_shift_di = c.geo_shift_di;
     q->geometric_growth = c.geo_growth; q->geometric_growth_di = c.geo_growth_di; q->n_renorm = c.n_ren;
     q->tail_map = c.tail_log ? 2 : 1; q->tail_map_di = c.tail_log_di ? 2 : 1;
+    q->mu_geometric_growth = c.mu_growth; q->mu_geometric_growth_di = c.mu_growth_di; q->mu_switch_break_di = c.mu_switch_di ? 1 : 2;
+    q->n_outer_min = c.n_outer_min; q->n_outer_step = c.n_outer_step;
     q->accuracy_target = ctx->target_in_force;
     return COFFE_B200_OK;
 }

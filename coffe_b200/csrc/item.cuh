@@ -16,6 +16,7 @@ struct Rules {
     const double *rpow;             /* tail_ratio^n, n < kMaxTail */
     int n_panel_si, n_panel_di;
     int n_outer;                    /* 0 = auto_n_outer(sep) */
+    int n_outer_min; double n_outer_step;    /* by separation: max(n_outer_min, 10 + sep / n_outer_step) */
     double panel_w_mpc, panel_du, eps_min, tail_ratio;
     double panel_w_di, panel_du_di;  /* panel plan of the inner integral of the integrated x integrated piece */
     const double *panel_x, *panel_w; /* nodes / weights of the n_panel_di rule when staged separately (else null: read from the bank) */
@@ -214,7 +215,7 @@ COFFE_HD double di_partial(const TA &t, const LosView &lv, const Rules &q, const
 {
     double acc = 0.0;
     const double sth = sqrt(g.s2);
-    const int n_outer = q.n_outer > 0 ? q.n_outer : auto_n_outer(g.sep);
+    const int n_outer = q.n_outer > 0 ? q.n_outer : auto_n_outer(g.sep, q.n_outer_min, q.n_outer_step);
     const double *outer_x = q.gl_x + rule_offset(n_outer), *outer_w = q.gl_w + rule_offset(n_outer);
     for (int io = group; io < n_outer; io += ngroups) {
         const double l1 = g.chi1 * outer_x[io];
@@ -227,7 +228,7 @@ COFFE_HD double di_partial(const TA &t, const LosView &lv, const Rules &q, const
 COFFE_HD unsigned int di_eval_count(const Rules &q, const Geometry &g)
 {
     const double sth = sqrt(g.s2);
-    const int n_outer = q.n_outer > 0 ? q.n_outer : auto_n_outer(g.sep);
+    const int n_outer = q.n_outer > 0 ? q.n_outer : auto_n_outer(g.sep, q.n_outer_min, q.n_outer_step);
     const double *outer_x = q.gl_x + rule_offset(n_outer);
     unsigned int n = 0;
     for (int io = 0; io < n_outer; ++io) {

@@ -167,6 +167,7 @@ struct QuadConfig {
     int n_mu_panel;         /* nodes per transverse-separation panel of the mu rule of the integrated pieces */
     double mu_rho0, mu_panel_w, mu_du;     /* panel plan in r_perp = r sqrt(1-mu^2) [Mpc] */
     int n_outer;            /* outer line-of-sight nodes of the integrated x integrated piece; 0 = by separation */
+    int n_outer_min; double n_outer_step;  /* by separation: max(n_outer_min, 10 + sep / n_outer_step) */
     int n_panel_si, n_panel_di;            /* nodes per inner panel */
     int n_z;                /* nodes of the redshift average */
     double panel_w;         /* W  [Mpc] */
@@ -183,6 +184,8 @@ struct QuadConfig {
     /* growth factor per geometric panel under the sinh map (panel_plan); <= 1: the doubling panels with Gauss-Legendre nodes in d */
     double geo_growth, geo_growth_di;
     int tail_log, tail_log_di;     /* tail panels with Gauss-Legendre nodes in log(d) instead of d */
+    double mu_growth, mu_growth_di; /* growth factor of the log-mapped geometric r_perp panels of the mu rules; <= 1: doubling panels in phi */
+    int mu_switch_di;       /* the integrated x integrated mu rule keeps the break at |mu| = 0.999 (only the local x integrated integrand switches there) */
     int n_ren;              /* nodes of the inner rule of renormalization(l1, l2) in the integrated x integrated piece (even) */
 };
 
@@ -196,12 +199,12 @@ COFFE_HD int rule_offset(const int n) { return n * (n - 1) / 2; }
    worst multipole): r <= 224 Mpc is converged to the 2e-6 floor of the other rules with 24 nodes; r = 299 Mpc
    needs 28 (1e-6; 24 gives 1e-5), r = 448 Mpc needs 44 (2e-6; 36 gives 1e-5, 24 gives 2e-4): independent of z.
    The floor of 30 keeps the l = 4 multipole at r = 60-150 Mpc below 3e-6 (26 nodes: 6e-6). */
-COFFE_HD int auto_n_outer(const double sep)
+COFFE_HD int auto_n_outer(const double sep, const int n_min = 30, const double step = 12.0)
 {
-    int n = 10 + (int)(sep / 12.0);
-    if (n < 30) n = 30;
+    int n = 10 + (int)(sep / step);
+    if (n < n_min) n = n_min;
     if (n > 96) n = 96;
-    return n & ~1;
+    return n;
 }
 
 }  // namespace coffe

@@ -18,13 +18,14 @@ inline QuadConfig default_quadrature()
     QuadConfig q;
     q.n_mu_ni = 32;
     q.n_mu_panel = 8; q.mu_rho0 = 4.0; q.mu_panel_w = 32.0; q.mu_du = 256.0;
-    q.n_outer = 0;
+    q.n_outer = 0; q.n_outer_min = 30; q.n_outer_step = 12.0;
     q.n_panel_si = 8; q.n_panel_di = 8;
     q.n_z = 8;
     q.panel_w = 64.0; q.panel_du = 128.0; q.eps_min = 1e-3; q.tail_ratio = 1.5;
     q.n_mu_panel_di = 5; q.panel_w_di = 64.0; q.panel_du_di = 192.0; q.mu_panel_w_di = 64.0; q.tail_ratio_di = 6.0; q.geo_shift_di = 1;
     q.geo_growth = 1.0; q.geo_growth_di = 8.0;
-    q.n_ren = 32;
+    q.n_ren = 24;
+    q.mu_growth = 3.0; q.mu_growth_di = 1.0; q.mu_switch_di = 1;
     q.tail_log = 0; q.tail_log_di = 1;
     return q;
 }
@@ -40,7 +41,9 @@ inline QuadConfig default_quadrature()
 inline QuadConfig total_target_quadrature()
 {
     QuadConfig q = default_quadrature();
-    q.n_panel_di = 6; q.n_mu_panel_di = 4;
+    q.n_panel_di = 6; q.n_mu_panel_di = 4; q.n_ren = 12;
+    q.n_outer_min = 25; q.n_outer_step = 15.0;
+    q.mu_growth = 8.0; q.mu_switch_di = 0;
     q.mu_panel_w = 64.0; q.n_mu_panel = 7; q.n_panel_si = 6;
     q.mu_rho0 = 8.0;
     return q;
@@ -56,6 +59,8 @@ inline QuadConfig merge_quadrature(const QuadConfig &base, const coffe_b200_quad
     if (u.mu_uniform_extent > 0) q.mu_du = u.mu_uniform_extent;
     if (u.n_outer > 0) q.n_outer = u.n_outer;
     if (u.n_outer < 0) q.n_outer = 0;
+    if (u.n_outer_min > 0) q.n_outer_min = u.n_outer_min;
+    if (u.n_outer_step > 0) q.n_outer_step = u.n_outer_step;
     if (u.n_panel_si > 0) q.n_panel_si = u.n_panel_si;
     if (u.n_panel_di > 0) q.n_panel_di = u.n_panel_di;
     if (u.n_z > 0) q.n_z = u.n_z;
@@ -74,6 +79,9 @@ inline QuadConfig merge_quadrature(const QuadConfig &base, const coffe_b200_quad
     if (u.n_renorm > 0) q.n_ren = u.n_renorm & ~1;
     if (u.tail_map > 0) q.tail_log = u.tail_map == 2;
     if (u.tail_map_di > 0) q.tail_log_di = u.tail_map_di == 2;
+    if (u.mu_geometric_growth > 0) q.mu_growth = u.mu_geometric_growth;
+    if (u.mu_geometric_growth_di > 0) q.mu_growth_di = u.mu_geometric_growth_di;
+    if (u.mu_switch_break_di > 0) q.mu_switch_di = u.mu_switch_break_di == 1;
     return q;
 }
 
@@ -154,29 +162,54 @@ inline std::vector<double> build_rpow(const double ratio)
 /* mu rule of the integrated pieces for one separation: the integrands are functions of the transverse
    separation r_perp = r sin(phi), mu = cos(phi), that peak sharply at r_perp -> 0 (|mu| -> 1) and carry
    BAO-scale structure in r_perp.  Panels in phi with break points at r_perp = B_k (the same geometric /
-   uniform / geometric plan as the line-of-sight integrals) plus one at |mu| = 0.999 where the reference
-   switches formulas; n-point Gauss-Legendre per panel; mirrored to mu < 0.  Weights are for the measure
-   dmu/2, i.e. xi_l = (2l+1) sum_j w_j P_l(mu_j) xi(mu_j)      (src/signal.c:97-110, 541). */
-inline void build_mu_rule(const QuadConfig &q, const double sep, std::vector<double> &mu, std::vector<double> &w, const int n_per_panel = 0,
-                          const double panel_width = 0.0, const bool half_only = false)
+   uniform / geometric plan as the line-of-sight integrals) plus, for the local x integrated piece, one at |mu| = 0.999
+   where the reference switches formulas; n-point Gauss-Legendre per panel; mirrored to mu < 0.  Weights are for the measure
+   dmu/2, i.e. xi_l = (2l+1) sum_j w_j P_l(mu_j) xi(mu_j)      (src/signal.c:97-110, 541).
+   piece: 1 = local x integrated, 2 = integrated x integrated (its own node count, panel width, growth and switch break).
+   With a growth factor > 1 the geometric region [rho0, panel width] is cut into equal panels in log(r_perp) with the nodes
+   Gauss-Legendre in log(r_perp): the small-r_perp behaviour of the integrated pieces is logarithmic. */
+inline void build_mu_rule(const QuadConfig &q, const double sep, std::vector<double> &mu, std::vector<double> &w, const int piece = 1,
+                          const bool half_only = false)
 {
-    const int n_mu_panel = n_per_panel > 0 ? n_per_panel : q.n_mu_panel;
-    const double mu_panel_w = panel_width > 0.0 ? panel_width : q.mu_panel_w;
+    const bool di = piece == 2;
+    const int n_mu_panel = di ? q.n_mu_panel_di : q.n_mu_panel;
+    const double mu_panel_w = di ? q.mu_panel_w_di : q.mu_panel_w;
+    const double growth = di ? q.mu_growth_di : q.mu_growth;
+    const bool switch_break = di ? q.mu_switch_di != 0 : true;
     mu.clear(); w.clear();
     std::vector<double> bp;
     bp.push_back(0.0);
     double b = q.mu_rho0;
+    double log_lo = 0.0, log_hi = 0.0;      /* region of the log-mapped panels */
+    const double w_log = std::min(mu_panel_w, 0.5 * sep);      /* in log(r_perp) only where phi is still far from pi/2 */
+    if (growth > 1.0 && b < w_log) {
+        const int J = std::max(1, (int)std::ceil(std::log(w_log / b) / std::log(growth) - 1e-12));
+        const double ratio = std::pow(w_log / b, 1.0 / J);
+        log_lo = b;
+        for (int k = 0; k < J; ++k) { bp.push_back(b); b = k + 1 == J ? w_log : b * ratio; }
+        log_hi = w_log;
+    }
     while (b < mu_panel_w && b < sep) { bp.push_back(b); b *= 2.0; }
     while (b < q.mu_du && b < sep) { bp.push_back(b); b += mu_panel_w; }
     while (b < sep) { bp.push_back(b); b *= q.tail_ratio; }
     bp.push_back(sep);
-    bp.push_back(sep * std::sqrt(1.0 - kMuSwitch * kMuSwitch));
+    if (switch_break) bp.push_back(sep * std::sqrt(1.0 - kMuSwitch * kMuSwitch));
     std::sort(bp.begin(), bp.end());
     std::vector<double> x, wt;
     build::gauss_legendre_01(n_mu_panel, x, wt);
     for (size_t k = 0; k + 1 < bp.size(); ++k) {
         const double a = std::asin(std::min(1.0, bp[k] / sep)), c = std::asin(std::min(1.0, bp[k + 1] / sep));
         if (!(c - a > 1e-14)) continue;
+        if (log_hi > log_lo && bp[k] >= log_lo && bp[k + 1] <= log_hi) {
+            /* nodes in u = log(r_perp): phi = asin(e^u / r), dphi/du = tan(phi) */
+            const double u0 = std::log(bp[k]), u1 = std::log(bp[k + 1]);
+            for (int j = 0; j < n_mu_panel; ++j) {
+                const double sphi = std::exp(u0 + (u1 - u0) * x[j]) / sep, cphi = std::sqrt(1.0 - sphi * sphi);
+                mu.push_back(cphi);
+                w.push_back((u1 - u0) * wt[j] * (sphi / cphi) * sphi / 2.0);
+            }
+            continue;
+        }
         for (int j = 0; j < n_mu_panel; ++j) {
             const double phi = a + (c - a) * x[j];
             mu.push_back(std::cos(phi));

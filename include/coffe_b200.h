@@ -142,6 +142,15 @@ typedef struct coffe_b200_quadrature {
     /* variable of the Gauss-Legendre nodes on the tail panels beyond the uniform extent: 0 = library default, 1 = d, 2 = log(d)
        (power-law tails are entire functions of log(d): wider panels at the same node count).  First: local x integrated. */
     int tail_map, tail_map_di;
+    /* mu rules of the integrated pieces: growth factor of the geometric r_perp panels between mu_rho0 and the panel width, with
+       the nodes Gauss-Legendre in log(r_perp) (0 = default, (0, 1] = doubling panels with nodes in phi); and whether the rule of
+       the integrated x integrated piece keeps the break at |mu| = 0.999 (0 = default, 1 = yes, 2 = no: only the local x integrated
+       integrand switches formulas there, src/functions.c:2199) */
+    double mu_geometric_growth, mu_geometric_growth_di;
+    int mu_switch_break_di;
+    /* outer nodes by separation (n_outer = -1 / default): max(n_outer_min, 10 + sep / n_outer_step [Mpc]) */
+    int n_outer_min;
+    double n_outer_step;
 } coffe_b200_quadrature;
 enum { COFFE_B200_TARGET_AUTO = 0, COFFE_B200_TARGET_PIECE = 1, COFFE_B200_TARGET_TOTAL = 2 };
 

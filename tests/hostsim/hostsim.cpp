@@ -41,7 +41,7 @@ static void set_rules(HostSim *s)
     Rules &q = s->q;
     s->rpow = build_rpow(s->qc.tail_ratio);
     q.gl_x = s->bx.data(); q.gl_w = s->bw.data(); q.rpow = s->rpow.data();
-    q.n_panel_si = s->qc.n_panel_si; q.n_panel_di = s->qc.n_panel_di; q.n_outer = s->qc.n_outer;
+    q.n_panel_si = s->qc.n_panel_si; q.n_panel_di = s->qc.n_panel_di; q.n_outer = s->qc.n_outer; q.n_outer_min = s->qc.n_outer_min; q.n_outer_step = s->qc.n_outer_step;
     q.panel_w_mpc = s->qc.panel_w; q.panel_du = s->qc.panel_du; q.eps_min = s->qc.eps_min; q.tail_ratio = s->qc.tail_ratio;
     q.panel_w_di = s->qc.panel_w_di; q.panel_du_di = s->qc.panel_du_di;
     q.panel_x = q.panel_w = q.panel_p = nullptr;
@@ -228,8 +228,7 @@ void hs_multipoles(void *h, double z, double sep, const int *ls, int n_l, double
     HostSim *s = (HostSim *)h;
     for (int p = 1; p < 3; ++p) {
         std::vector<double> mu, w;
-        build_mu_rule(s->qc, sep, mu, w, p == 1 ? s->qc.n_mu_panel : s->qc.n_mu_panel_di, p == 1 ? s->qc.mu_panel_w : s->qc.mu_panel_w_di,
-                      p == 2 ? s->di_half : s->si_half());
+        build_mu_rule(s->qc, sep, mu, w, p, p == 2 ? s->di_half : s->si_half());
         const int nm = (int)mu.size();
         std::vector<double> v((size_t)3 * nm);
 #pragma omp parallel for schedule(dynamic, 1)
@@ -258,14 +257,14 @@ void hs_eval_counts(void *h, double z, double sep, double *out)
     std::vector<double> mu, w;
     const double chi_mean = bg_chi(s->t.bg, z);
     out[0] = out[1] = 0.0;
-    build_mu_rule(s->qc, sep, mu, w, s->qc.n_mu_panel, 0.0, s->si_half());
+    build_mu_rule(s->qc, sep, mu, w, 1, s->si_half());
     for (size_t im = 0; im < mu.size(); ++im) {
         const Geometry g = geometry(chi_mean, sep, mu[im]);
         const EndVals e1 = end_eval(s->o, s->t, g.chi1, 1), e2 = end_eval(s->o, s->t, g.chi2, 2);
         const SIHalf ha = si_half_setup(s->o, g, e1, e2, true), hb = si_half_setup(s->o, g, e2, e1, false);
         out[0] += si_eval_count(s->q, g, ha) + si_eval_count(s->q, g, hb);
     }
-    build_mu_rule(s->qc, sep, mu, w, s->qc.n_mu_panel_di, s->qc.mu_panel_w_di, s->di_half);
+    build_mu_rule(s->qc, sep, mu, w, 2, s->di_half);
     for (size_t im = 0; im < mu.size(); ++im) {
         const Geometry g = geometry(chi_mean, sep, mu[im]);
         const EndVals e1 = end_eval(s->o, s->t, g.chi1, 1), e2 = end_eval(s->o, s->t, g.chi2, 2);
