@@ -51,7 +51,7 @@ COFFE_HD PanelPlan panel_plan(double eps, const double eps_min, const double W, 
         /* sinh map: f(sqrt(d^2 + eps^2)) = f(eps cosh t) under d = eps sinh t has its singularities at t = +- i pi/2 whatever the
            panel, so a Gauss-Legendre rule in t converges like rho^(-2n) with (rho - 1/rho) = 2 pi / L on a panel of length L in t:
            rho = 4.7 for L = ln 4.  The region [0, W] is cut into J equal panels in t, the fewest with L <= geo_L. */
-        const double T = asinh(W / eps);
+        const double x = W / eps, T = log(x + sqrt(fma(x, x, 1.0)));       /* asinh(x), x > 1 */
         J = (int)ceil(T / geo_L);
         if (J < 1) J = 1;
         p.L = T / J;
