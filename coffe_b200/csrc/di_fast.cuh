@@ -208,18 +208,34 @@ COFFE_HD double di_inner_group(const DISideCtx<TA> &cx, const Rules &q, const DI
     const PanelPlan plan = di_plan(q, o);
     const DISides p = di_sides(plan, f, o);
     double acc = 0.0;
-    const double pj = plan.lnr > 0.0 ? (q.panel_p ? q.panel_p[j] : exp(plan.lnr * xj)) : 0.0;         /* ratio^x_j */
-    /* ---- mirror pairs, k = 0 .. k_pair-1: never clipped ---- */
-    {
-        /* sinh-map state: (S, C) = (sinh, cosh)(k L), (sj, cj) = (sinh, cosh)(L x_j), (S1, C1) = (sinh, cosh)(L) */
-        double S = 0.0, C = 1.0, sj = 0.0, cj = 1.0, S1 = 0.0, C1 = 1.0;
-        if (plan.L > 0.0 && p.k_pair > 0) {
-            const double e = exp(plan.L * xj), ie = 1.0 / e, e1 = exp(plan.L), ie1 = 1.0 / e1;
-            sj = 0.5 * (e - ie); cj = 0.5 * (e + ie); S1 = 0.5 * (e1 - ie1); C1 = 0.5 * (e1 + ie1);
-        }
-        const int JM = plan.J + plan.M;
-        for (int k = 0; k < p.k_pair; ++k) {
-            double d, wgt;
+    const double pj = plan.lnr > 0.0 ? (q.panel_p ? q.panel_p[j] : exp(plan.lnr * xj)) : 0.0;
+    double S = 0.0, C = 1.0, sj = 0.0, cj = 1.0, S1 = 0.0, C1 = 1.0;
+    if (plan.L > 0.0 && p.k_pair > 0) {
+        const double e = exp(plan.L * xj), ie = 1.0 / e, e1 = exp(plan.L), ie1 = 1.0 / e1;
+        sj = 0.5 * (e - ie); cj = 0.5 * (e + ie); S1 = 0.5 * (e1 - ie1); C1 = 0.5 * (e1 + ie1);
+    }
+    const int JM = plan.J + plan.M;
+    const bool ordinary = p.a_neg == 0.0;
+    const bool neg_long = p.k_neg > p.k_pos;
+    const int k_long = neg_long ? p.k_neg : p.k_pos;
+    const int n_single = ordinary ? 2 + (k_long - 1 > p.k_pair ? k_long - 1 - p.k_pair : 0) : p.k_neg;
+    const int n_units = n_single + p.k_pair;
+    /* ONE loop over the units and ONE copy of the integrand (di_shared, and di_side in a loop over the two sides that is not unrolled):
+       the kernel is bound by its instruction footprint -- with separate loops for the pairs (two inlined sides) and the single panels
+       it measured 12 % slower, with a third copy for the last panels 25 %.
+       Order: the panels left over beside the pairs first -- negative side k_pair .. k_neg-1, positive side k_pair .. k_pos-1: the
+       shorter side has one panel left, its last; the longer side the panels from k_pair on; every last panel is clipped by the end
+       of its line of sight, and the two of them come first, while all groups of the warp are still in step, so that the clipped
+       tail panel with its two square roots holds nobody up.  (When the ridge lies beyond the end of the second line of sight,
+       c0 > chi2, only |d| in [a_neg, b_neg] of the negative side exists: its panels in order, clipped at both ends.)  Then the
+       mirror pairs k = 0 .. k_pair-1, never clipped; on the sinh-map panels (S, C) = (sinh, cosh)(k L) follow from a two-term
+       recurrence with (S1, C1) = (sinh, cosh)(L) and the node from the addition theorem with (sj, cj) = (sinh, cosh)(L x_j). */
+    for (int u = 0; u < n_units; ++u) {
+        double d = 0.0, wgt = 0.0;
+        int sides = 0;
+        if (u >= n_single) {
+            const int k = u - n_single;
+            sides = 3;
             if (k < plan.J) {
                 if (plan.L > 0.0) {
                     d = plan.eps * fma(S, cj, C * sj);
@@ -233,10 +249,7 @@ COFFE_HD double di_inner_group(const DISideCtx<TA> &cx, const Rules &q, const DI
                     d = fma(wd, xj, lo); wgt = wd * wj;
                 }
             }
-            else if (k < JM) {
-                d = fma(plan.W, xj, plan.BJ + (k - plan.J) * plan.W);
-                wgt = plan.W * wj;
-            }
+            else if (k < JM) { d = fma(plan.W, xj, plan.BJ + (k - plan.J) * plan.W); wgt = plan.W * wj; }
             else {
                 const int n = k - JM;
                 const double lo = plan.BJM * plan.rpow[n < kMaxTail ? n : kMaxTail - 1];
@@ -246,51 +259,45 @@ COFFE_HD double di_inner_group(const DISideCtx<TA> &cx, const Rules &q, const DI
                     d = fma(wd, xj, lo); wgt = wd * wj;
                 }
             }
+        }
+        else {
+            const int e = u;
+            const bool neg = ordinary ? (e == 0 || (e >= 2 && neg_long)) : true;
+            const int k = !ordinary ? e : e == 0 ? p.k_neg - 1 : e == 1 ? p.k_pos - 1 : p.k_pair + e - 2;
+            if (k >= 0) {
+                double lo = panel_break(plan, k), up = panel_break(plan, k + 1);
+                const double a = neg ? p.a_neg : 0.0, b = neg ? p.b_neg : p.b_pos;
+                const bool lo_cl = lo < a, up_cl = up > b;
+                if (lo_cl) lo = a;
+                if (up_cl) up = b;
+                if (up > lo) {
+                    sides = neg ? 1 : 2;
+                    const int map = panel_map(plan, k);
+                    if (map == 2) {
+                        if (lo_cl || up_cl) {
+                            /* clipped tail panel [lo, up]: d = lo (1 + a x)^4 reaches up at x = 1 with a = (up/lo)^(1/4) - 1.  Like
+                               log(d) it keeps d^-p far from its singularity (rho = 9 at up/lo = 6) at the price of two square roots */
+                            const double a4 = sqrt(sqrt(up / lo)) - 1.0, t = fma(a4, xj, 1.0), t2 = t * t;
+                            d = lo * (t2 * t2); wgt = (4.0 * a4 * lo * wj) * (t2 * t);
+                        }
+                        else { d = lo * pj; wgt = d * (plan.lnr * wj); }
+                    }
+                    else if (map == 1) panel_node(plan, k, lo, up, lo_cl, up_cl, xj, wj, d, wgt);
+                    else { const double wd = up - lo; d = fma(wd, xj, lo); wgt = wd * wj; }
+                }
+            }
+        }
+        if (sides) {
             const DIShared s = di_shared(*cx.ta, f, o, d);
-            const double v = di_side<ALL>(cx, f, o, s, o.c0 - d) + di_side<ALL>(cx, f, o, s, o.c0 + d);
+            double v = 0.0;
+#pragma unroll 1
+            for (int sd = 0; sd < 2; ++sd)
+                if (sides & (1 << sd)) v += di_side<ALL>(cx, f, o, s, sd == 0 ? o.c0 - d : o.c0 + d);
             acc = fma(wgt, v, acc);
         }
     }
-    /* ---- what is left of the two sides: negative side k_pair .. k_neg-1, positive side k_pair .. k_pos-1 ----
-       The shorter side has one panel left, its last; the longer side the panels from k_pair on.  Every last panel is clipped by the
-       end of its line of sight.  Order: the two last panels first -- there all groups of a warp are still in step, so the clipped
-       tail panel with its two square roots holds nobody up -- then the unclipped panels of the longer side.  (When the ridge lies
-       beyond the end of the second line of sight, c0 > chi2, only |d| in [a_neg, b_neg] of the negative side exists: its panels
-       in order, clipped at both ends.)  One loop, one copy of the integrand: the kernel is sensitive to its instruction footprint
-       (a variant with the last panels in a loop of their own measured 13 % slower). */
-    const bool ordinary = p.a_neg == 0.0;
-    const bool neg_long = p.k_neg > p.k_pos;
-    const int k_long = neg_long ? p.k_neg : p.k_pos;
-    const int n_single = ordinary ? 2 + (k_long - 1 > p.k_pair ? k_long - 1 - p.k_pair : 0) : p.k_neg;
-    for (int e = 0; e < n_single; ++e) {
-        const bool neg = ordinary ? (e == 0 || (e >= 2 && neg_long)) : true;
-        const int k = !ordinary ? e : e == 0 ? p.k_neg - 1 : e == 1 ? p.k_pos - 1 : p.k_pair + e - 2;
-        if (k < 0) continue;
-        double lo = panel_break(plan, k), up = panel_break(plan, k + 1);
-        const double a = neg ? p.a_neg : 0.0, b = neg ? p.b_neg : p.b_pos;
-        const bool lo_cl = lo < a, up_cl = up > b;
-        if (lo_cl) lo = a;
-        if (up_cl) up = b;
-        if (!(up > lo)) continue;
-        double d, wgt;
-        const int map = panel_map(plan, k);
-        if (map == 2) {
-            if (lo_cl || up_cl) {
-                /* clipped tail panel [lo, up]: d = lo (1 + a x)^4 reaches up at x = 1 with a = (up/lo)^(1/4) - 1.  Like log(d) it
-                   keeps d^-p far from its singularity (rho = 9 at up/lo = 6) and costs two square roots instead of log and exp */
-                const double a4 = sqrt(sqrt(up / lo)) - 1.0, t = fma(a4, xj, 1.0), t2 = t * t;
-                d = lo * (t2 * t2); wgt = (4.0 * a4 * lo * wj) * (t2 * t);
-            }
-            else { d = lo * pj; wgt = d * (plan.lnr * wj); }
-        }
-        else if (map == 1) panel_node(plan, k, lo, up, lo_cl, up_cl, xj, wj, d, wgt);
-        else { const double wd = up - lo; d = fma(wd, xj, lo); wgt = wd * wj; }
-        const DIShared s = di_shared(*cx.ta, f, o, d);
-        acc = fma(wgt, di_side<ALL>(cx, f, o, s, neg ? o.c0 - d : o.c0 + d), acc);
-    }
     return acc;
 }
-
 COFFE_HD unsigned int di_inner_eval_count(const Rules &q, const DIFast &f, const DIOuter &o)
 {
     const PanelPlan plan = di_plan(q, o);
