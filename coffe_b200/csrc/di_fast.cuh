@@ -323,7 +323,7 @@ COFFE_HD double di_fast_partial(const TA &ta, const Tables &t, const double2 *lo
                                 const int group, const int ngroups, const int j)
 {
     const DIFast f = di_fast_setup(k, g);
-    const int n_outer = q.n_outer > 0 ? q.n_outer : auto_n_outer(g.sep, q.n_outer_min, q.n_outer_step);
+    const int n_outer = q.n_outer > 0 ? q.n_outer : auto_n_outer(g.sep, q.n_outer_min, q.n_outer_step, q.n_panel_di);
     const double *outer_x = q.gl_x + rule_offset(n_outer), *outer_w = q.gl_w + rule_offset(n_outer);
     DISideCtx<TA> cx;
     cx.ta = &ta; cx.los = los; cx.los_n = t.los.n; cx.los_inv_h = t.los.inv_h;
@@ -350,7 +350,7 @@ COFFE_HD double di_fast_partial(const TA &ta, const Tables &t, const double2 *lo
 COFFE_HD unsigned int di_fast_eval_count(const Rules &q, const Geometry &g, const DIConst &k)
 {
     const DIFast f = di_fast_setup(k, g);
-    const int n_outer = q.n_outer > 0 ? q.n_outer : auto_n_outer(g.sep, q.n_outer_min, q.n_outer_step);
+    const int n_outer = q.n_outer > 0 ? q.n_outer : auto_n_outer(g.sep, q.n_outer_min, q.n_outer_step, q.n_panel_di);
     const double *outer_x = q.gl_x + rule_offset(n_outer);
     unsigned int n = 0;
     double4 unit; unit.x = unit.y = unit.z = unit.w = 1.0;

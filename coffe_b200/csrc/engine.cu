@@ -233,12 +233,14 @@ __global__ void __launch_bounds__(kSIThreads, 1) si_items_smem_kernel(
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int n_warps = kSIThreads / 32;
     const int n_col_max = t.has_divergent ? t.ren2d.n : 0;
-    /* layout: [compact blob prefix][line-of-sight table][tail powers, panel rule][per-warp columns][per-warp panel lists] */
+    /* layout: [compact blob prefix][line-of-sight table][tail powers, panel rule][per-warp columns][per-warp half][per-warp panel lists] */
     double2 *los_s = reinterpret_cast<double2 *>(smem + stage_bytes);
     double *small = reinterpret_cast<double *>(los_s + (size_t)kLosStride * los_stage_n);
     double2 *cols = reinterpret_cast<double2 *>(small + kDISmallDoubles);
     double2 *col = cols + (size_t)warp * n_col_max;
-    double *scratch = reinterpret_cast<double *>(cols + (size_t)n_warps * n_col_max) + (size_t)warp * 2 * panel_cap;
+    SIHalf *h_all = reinterpret_cast<SIHalf *>(cols + (size_t)n_warps * n_col_max);
+    SIHalf &h = h_all[warp];        /* amplitudes and polynomial coefficients of the half in work: read with uniform addresses (broadcast) */
+    double *scratch = reinterpret_cast<double *>(h_all + n_warps) + (size_t)warp * 2 * panel_cap;
     {
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
         for (int i = tid; i < stage_bytes / 16; i += kSIThreads) dst[i] = blob[i];
@@ -273,9 +275,15 @@ __global__ void __launch_bounds__(kSIThreads, 1) si_items_smem_kernel(
         double si = 0.0;
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
-            const SIHalf h = su->h[half];
+            __syncwarp();               /* the previous half's readers are done */
+            {
+                static_assert(sizeof(SIHalf) % 8 == 0, "SIHalf is copied in 8-byte words");
+                const double *src = reinterpret_cast<const double *>(&su->h[half]);
+                double *dst = reinterpret_cast<double *>(&h);
+                for (int i = lane; i < (int)(sizeof(SIHalf) / 8); i += 32) dst[i] = src[i];
+            }
+            __syncwarp();
             if (h.need_ren) {
-                __syncwarp();           /* the previous half's readers are done */
                 ta.n_col = ren_row_count(t.ren2d, h.co);
                 ren_col_fill(t.ren2d, h.cs, ta.n_col, col, lane, 32);
                 ta.col = col;
@@ -638,7 +646,7 @@ int launch_integrated(coffe_b200_ctx *ctx, Batch &b, const int mode, unsigned in
         /* the local x integrated kernel is compiled for a fixed warp count: the scalar path's panel lists are dropped when the
            warp-held bookkeeping is selected (they would not fit next to the renormalisation columns) */
         const bool si_warp_panels = ctx->qc.n_panel_si <= 32 && si_side_panels(ctx->qc, std::max(2.0e4, 1.01 * ctx->layout.chi_max_table)) <= 63;
-        const size_t per_warp = mode == 1 ? row_bytes + (si_warp_panels ? 0 : (size_t)2 * panel_cap * sizeof(double)) : 0;
+        const size_t per_warp = mode == 1 ? row_bytes + sizeof(SIHalf) + (si_warp_panels ? 0 : (size_t)2 * panel_cap * sizeof(double)) : 0;
         /* as many warps per SM as the remaining shared memory carries (the kernels are latency-bound: more is faster) */
         int warps = mode == 1 ? kSIThreads / 32 : kDIThreads / 32;
         const int threads = warps * 32;

@@ -257,6 +257,13 @@ struct SIHalf {
     int any_lens, any_g4, any_g5, need_ren;
     int mid;                                        /* midpoint approximation: den/rsd/d1 x len read the 2-D tables */
     double zs, D1s;                                 /* redshift and growth factor of the local end */
+    /* The lensing bracket of the half as polynomials in lambda with the amplitudes folded in (si_half_setup), so that a node
+       costs a few Horner steps instead of re-deriving every coefficient from (cs, cos theta):
+         br = I00 P00(l) + [I02 P02(l) + I13 P13(l)] / R^2 + I04 P04(l - cs) / R^4 + I11 P11(l) + I20 p20 + I31 p31 + I22 p22 l
+       (|mu| >= 0.999: I04 (p04a[0] + p04a[1] l) in place of the quintic, src/functions.c:2199).  The quintic is held in powers of
+       l - cs with coefficients in powers of w = 1 - cos(theta) -- the form in which the reference's O(chi^5) terms have already
+       cancelled down to O(chi r^4) (see the comment at its derivation in si_half_setup). */
+    double p00[2], p02[4], p13[5], p04[6], p04a[2], p11[3], p20, p31, p22;
 };
 
 /* src = local end, oth = the end whose line of sight is integrated.  `first` selects the quirks of the
@@ -303,6 +310,44 @@ COFFE_HD SIHalf si_half_setup(const Options &o, const Geometry &g, const EndVals
     h.any_g4 = o.g4 && opt_has_ni(o);
     h.any_g5 = o.g5 && opt_has_ni(o);
     h.need_ren = o.divergent && ((h.g4_ren != 0.0) || (h.g5_ren != 0.0));
+    {
+        const double cs = h.cs, cs2 = cs * cs, cs3 = cs2 * cs, c = g.c, c2 = c * c, tc = 2 * c2 - 1, s2 = g.s2, w = g.omc;
+        const double ad = h.a_denlen, ar = h.a_rsdlen, a1 = h.a_d1len, ap = h.a_pot;
+        /* den-len: 2 cs c I11 - cs^2 s2 l I02 / R^2                                                       src/functions.c:1592-1640 */
+        /* rsd-len: (l (1 + 3 tc) - 6 cs c) I00 / 15 - (6 cs^3 c - cs^2 (9 c^2 + 11) l + cs c (3 tc + 19) l^2 - 2 (3 tc + 1) l^3) I02 / (21 R^2)
+                    - p5 I04 / (35 R^4)                                                                     src/functions.c:2059-2390 */
+        /* d1-len:  2 (c (l^2 - 2 cs^2) + cs l (2 tc - 1)) I11 / 15 + 2 c I20 / 3
+                    - (4 cs^4 c - cs^3 (c^2 + 9) l + cs^2 c (c^2 + 5) l^2 - 2 cs (tc - 2) l^3 - 2 c l^4) I13 / (15 R^2)    :2490-2560 */
+        h.p00[0] = -ar * 6 * cs * c / 15.; h.p00[1] = ar * (1 + 3 * tc) / 15.;
+        h.p02[0] = -ar * 6 * cs3 * c / 21.;
+        h.p02[1] = ar * cs2 * (9 * c2 + 11) / 21. - ad * cs2 * s2;
+        h.p02[2] = -ar * cs * c * (3 * tc + 19) / 21.;
+        h.p02[3] = ar * 2 * (3 * tc + 1) / 21.;
+        h.p13[0] = -a1 * 4 * cs2 * cs2 * c / 15.;
+        h.p13[1] = a1 * cs3 * (c2 + 9) / 15.;
+        h.p13[2] = -a1 * cs2 * c * (c2 + 5) / 15.;
+        h.p13[3] = a1 * 2 * cs * (tc - 2) / 15.;
+        h.p13[4] = a1 * 2 * c / 15.;
+        /* the reference's quintic (functions.c:2205-2214) cancels from O(chi^5) to O(chi r^4); expanded in d = l - cs and
+           w = 1 - cos(theta) it reads
+             -4 d^4 (2 cs + d) + w (4 d^2 (12 cs^3 + 23 cs^2 d + 15 cs d^2 + 3 d^3)
+                + w (-6 l^2 (2 cs^3 + 6 cs^2 d + 6 cs d^2 + d^3) + w (2 cs l^2 (2 cs^2 + 4 cs d + 3 d^2) + w cs^2 l^3))),
+           which collected in powers of d gives the coefficients below (every bracket a polynomial in the small w) */
+        const double k35 = -ar / 35.;
+        h.p04[0] = k35 * cs3 * cs2 * w * w * (w - 2) * (w + 6);
+        h.p04[1] = k35 * cs2 * cs2 * w * w * (w * (3 * w + 16) - 60);
+        h.p04[2] = k35 * cs3 * w * (w * (w * (3 * w + 26) - 120) + 48);
+        h.p04[3] = k35 * cs2 * w * (w * (w * (w + 20) - 114) + 92);
+        h.p04[4] = k35 * 2 * cs * (w * (w * (3 * w - 24) + 30) - 4);
+        h.p04[5] = k35 * -2 * (w * (3 * w - 6) + 2);
+        h.p04a[0] = ar * 4 * cs / 35.; h.p04a[1] = ar * 4 / 35.;
+        h.p11[0] = ad * 2 * cs * c - a1 * 4 * c * cs2 / 15.;
+        h.p11[1] = a1 * 2 * cs * (2 * tc - 1) / 15.;
+        h.p11[2] = a1 * 2 * c / 15.;
+        h.p20 = a1 * 2 * c / 3.;
+        h.p31 = ap * 2 * cs * c;
+        h.p22 = -ap * cs2 * s2;
+    }
     return h;
 }
 
@@ -340,34 +385,17 @@ COFFE_HD double si_half_eval(const TA &t, const SIHalf &h, const Geometry &g, co
     if (h.any_lens) {
         double br = 0.0;
         if (rr != 0.0) {
+            /* the brackets as polynomials in l (coefficients and their derivation: si_half_setup) */
             const double irr = iR * iR;
-            const double tc = 2 * c2 - 1;
-            if (h.a_denlen != 0.0)                                                                  /* :1592-1640 */
-                br += h.a_denlen * (2 * cs * c * Is[I11] - cs * cs * l * s2 * Is[I02] * irr);
-            if (h.a_rsdlen != 0.0) {                                                                /* :2059-2390 */
-                double b = (l - 6 * cs * c + 3 * l * tc) * Is[I00] / 15.
-                         - (6 * cs * cs * cs * c - cs * cs * l * (9 * c2 + 11) + cs * l * l * c * (3 * tc + 19) - 2 * l * l * l * (3 * tc + 1)) * Is[I02] * irr / 21.;
-                if (!h.alt_i04) {
-                    /* the reference's quintic (functions.c:2205-2214) cancels from O(chi^5) to O(chi r^4); the same
-                       polynomial expanded in the small quantities d = l - cs and w = 1 - cos(theta): */
-                    const double w = g.omc, d2 = dl * dl, cs2 = cs * cs, l2 = l * l;
-                    const double p5 = -4 * d2 * d2 * (2 * cs + dl)
-                                    + w * (4 * d2 * (12 * cs2 * cs + 23 * cs2 * dl + 15 * cs * d2 + 3 * d2 * dl)
-                                    + w * (-6 * l2 * (2 * cs2 * cs + 6 * cs2 * dl + 6 * cs * d2 + d2 * dl)
-                                    + w * (2 * cs * l2 * (2 * cs2 + 4 * cs * dl + 3 * d2)
-                                    + w * cs2 * l2 * l)));
-                    b += -p5 * Is[I04] * irr * irr / 35.;
-                }
-                else b += 4. * (l + cs) * Is[I04] / 35.;
-                br += h.a_rsdlen * b;
-            }
-            if (h.a_d1len != 0.0) {                                                                 /* :2490-2560 */
-                const double cs2 = cs * cs, l2 = l * l;
-                br += h.a_d1len * (2 * (c * (l2 - 2 * cs2) + cs * l * (2 * tc - 1)) * Is[I11] / 15. + 2 * c * Is[I20] / 3.
-                                   - (4 * cs2 * cs2 * c - cs2 * cs * l * (c2 + 9) + cs2 * l2 * c * (c2 + 5) - 2 * cs * l2 * l * (tc - 2) - 2 * l2 * l2 * c) * Is[I13] * irr / 15.);
-            }
-            if (h.a_pot != 0.0)                                                                     /* :3000-3121 */
-                br += h.a_pot * (2 * cs * c * I[I31] - cs * cs * l * s2 * I[I22]);
+            br = Is[I00] * fma(h.p00[1], l, h.p00[0])
+               + Is[I11] * fma(fma(h.p11[2], l, h.p11[1]), l, h.p11[0])
+               + Is[I20] * h.p20
+               + irr * (Is[I02] * fma(fma(fma(h.p02[3], l, h.p02[2]), l, h.p02[1]), l, h.p02[0])
+                        + Is[I13] * fma(fma(fma(fma(h.p13[4], l, h.p13[3]), l, h.p13[2]), l, h.p13[1]), l, h.p13[0]))
+               + I[I31] * h.p31 + I[I22] * (h.p22 * l);
+            if (!h.alt_i04)
+                br += Is[I04] * (irr * irr) * fma(fma(fma(fma(fma(h.p04[5], dl, h.p04[4]), dl, h.p04[3]), dl, h.p04[2]), dl, h.p04[1]), dl, h.p04[0]);
+            else br += Is[I04] * fma(h.p04a[1], l, h.p04a[0]);
             res += (h.co - l) * W * br;
         }
         else {

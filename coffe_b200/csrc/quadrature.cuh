@@ -199,10 +199,13 @@ COFFE_HD int rule_offset(const int n) { return n * (n - 1) / 2; }
    worst multipole): r <= 224 Mpc is converged to the 2e-6 floor of the other rules with 24 nodes; r = 299 Mpc
    needs 28 (1e-6; 24 gives 1e-5), r = 448 Mpc needs 44 (2e-6; 36 gives 1e-5, 24 gives 2e-4): independent of z.
    The floor of 30 keeps the l = 4 multipole at r = 60-150 Mpc below 3e-6 (26 nodes: 6e-6). */
-COFFE_HD int auto_n_outer(const double sep, const int n_min = 30, const double step = 12.0)
+COFFE_HD int auto_n_outer(const double sep, const int n_min = 30, const double step = 12.0, const int n_panel = 0)
 {
     int n = 10 + (int)(sep / step);
     if (n < n_min) n = n_min;
+    /* the kernel runs 32 / n_panel outer nodes side by side (di_fast.cuh): a count that does not fill its last round costs the same
+       as the next multiple, so take the multiple */
+    if (n_panel > 0 && n_panel <= 32) { const int g = 32 / n_panel; n = (n + g - 1) / g * g; }
     if (n > 96) n = 96;
     return n;
 }
