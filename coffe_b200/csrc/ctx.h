@@ -27,6 +27,7 @@ struct coffe_b200_ctx {
     Arena arena;            /* host copy (set-up and range checks only) */
     Layout layout;
     double *d_arena = nullptr;
+    size_t d_arena_cap = 0, d_blob_cap = 0;      /* doubles allocated behind d_arena / d_blob */
     Tables t;               /* device view */
     Tables t_host;          /* host view */
     double omega_matter = 0, h = 0;

@@ -192,7 +192,7 @@ constexpr int kDISmallDoubles = kMaxTail + 3 * 32;
    dependent spline lookups through L2) folded into the amplitudes of the two halves / of the integrated x integrated terms.  Computed
    by item_setup_kernel, one THREAD per item, ahead of the integration kernels: inside them this chain ran on one or two lanes of a
    warp while the other thirty waited (a third of the local x integrated kernel's time). */
-struct SIItemSetup { SIHalf h[2]; };
+struct SIItemSetup { Geometry g; SIHalf h[2]; };
 struct DIItemSetup { DIConst k; };
 
 __global__ void item_setup_kernel(const __grid_constant__ Tables t, const __grid_constant__ Options o, const int mode,
@@ -208,6 +208,7 @@ __global__ void item_setup_kernel(const __grid_constant__ Tables t, const __grid
     const EndVals e1 = end_eval_at(o, t, g.chi1, los_z(t.los.v, t.los.n, t.los.inv_h, g.chi1), 1);
     const EndVals e2 = end_eval_at(o, t, g.chi2, los_z(t.los.v, t.los.n, t.los.inv_h, g.chi2), 2);
     if (mode == 1) {
+        si_out[i].g = g;
         si_out[i].h[0] = si_half_setup(o, g, e1, e2, true);
         si_out[i].h[1] = si_half_setup(o, g, e2, e1, false);
     }
@@ -238,9 +239,9 @@ __global__ void __launch_bounds__(kSIThreads, 1) si_items_smem_kernel(
     double *small = reinterpret_cast<double *>(los_s + (size_t)kLosStride * los_stage_n);
     double2 *cols = reinterpret_cast<double2 *>(small + kDISmallDoubles);
     double2 *col = cols + (size_t)warp * n_col_max;
-    SIHalf *h_all = reinterpret_cast<SIHalf *>(cols + (size_t)n_warps * n_col_max);
-    SIHalf &h = h_all[warp];        /* amplitudes and polynomial coefficients of the half in work: read with uniform addresses (broadcast) */
-    double *scratch = reinterpret_cast<double *>(h_all + n_warps) + (size_t)warp * 2 * panel_cap;
+    SIItemSetup *su_all = reinterpret_cast<SIItemSetup *>(cols + (size_t)n_warps * n_col_max);
+    SIItemSetup &su = su_all[warp]; /* geometry, amplitudes and polynomial coefficients of the item in work: read with uniform addresses (broadcast) */
+    double *scratch = reinterpret_cast<double *>(su_all + n_warps) + (size_t)warp * 2 * panel_cap;
     {
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
         for (int i = tid; i < stage_bytes / 16; i += kSIThreads) dst[i] = blob[i];
@@ -262,28 +263,45 @@ __global__ void __launch_bounds__(kSIThreads, 1) si_items_smem_kernel(
     q.rpow = small;
     if (q_in.n_panel_si <= 32) { q.panel_x_si = small + kMaxTail; q.panel_w_si = small + kMaxTail + 32; }
 
-    for (;;) {
-        unsigned int item = 0;
-        if (lane == 0) item = atomicAdd(counter, 1u);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= (unsigned int)n_items) break;
-        const int p = item_point[item];
-        const double z = pz[p], sep = psep[p], mu = item_mu[item];
-        const Geometry g = geometry(bg_chi(t.bg, z), sep, mu);
-        const SIItemSetup *su = item_setup + item;
-        if (out_evals && lane == 0) out_evals[item] = si_eval_count(q, g, su->h[0]) + si_eval_count(q, g, su->h[1]);
+    /* Items are drawn from a global counter two ahead, and the set-up record of the next item (768 bytes written by item_setup_kernel,
+       a DRAM round trip away) is loaded into registers while the current one is integrated: an item takes ~20 us, of which the
+       dependent chain counter -> record cost a third when it ran at the head of every item. */
+    constexpr int kWords = (int)(sizeof(SIItemSetup) / 8), kPre = (kWords + 31) / 32;
+    static_assert(sizeof(SIItemSetup) % 8 == 0, "the record is copied in 8-byte words");
+    const double *records = reinterpret_cast<const double *>(item_setup);
+    auto draw = [&]() {
+        unsigned int i = 0;
+        if (lane == 0) i = atomicAdd(counter, 1u);
+        return __shfl_sync(0xffffffffu, i, 0);
+    };
+    double pre[kPre];
+    auto prefetch = [&](const unsigned int i) {
+        if (i < (unsigned int)n_items)
+#pragma unroll
+            for (int w = 0; w < kPre; ++w)
+                if (lane + 32 * w < kWords) pre[w] = records[(size_t)i * kWords + lane + 32 * w];
+    };
+    unsigned int item = draw(), next = draw();
+    prefetch(item);
+    while (item < (unsigned int)n_items) {
+        __syncwarp();                   /* the previous item's readers are done */
+        {
+            double *dst = reinterpret_cast<double *>(&su);
+#pragma unroll
+            for (int w = 0; w < kPre; ++w)
+                if (lane + 32 * w < kWords) dst[lane + 32 * w] = pre[w];
+        }
+        __syncwarp();
+        prefetch(next);
+        const unsigned int after = draw();
+        const Geometry &g = su.g;
+        if (out_evals && lane == 0) out_evals[item] = si_eval_count(q, g, su.h[0]) + si_eval_count(q, g, su.h[1]);
         double si = 0.0;
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
-            __syncwarp();               /* the previous half's readers are done */
-            {
-                static_assert(sizeof(SIHalf) % 8 == 0, "SIHalf is copied in 8-byte words");
-                const double *src = reinterpret_cast<const double *>(&su->h[half]);
-                double *dst = reinterpret_cast<double *>(&h);
-                for (int i = lane; i < (int)(sizeof(SIHalf) / 8); i += 32) dst[i] = src[i];
-            }
-            __syncwarp();
+            const SIHalf &h = su.h[half];
             if (h.need_ren) {
+                __syncwarp();           /* the previous half's readers of the column are done */
                 ta.n_col = ren_row_count(t.ren2d, h.co);
                 ren_col_fill(t.ren2d, h.cs, ta.n_col, col, lane, 32);
                 ta.col = col;
@@ -297,7 +315,7 @@ __global__ void __launch_bounds__(kSIThreads, 1) si_items_smem_kernel(
         }
         si = warp_sum(si);
         if (lane == 0) out[item] = si;
-        __syncwarp();
+        item = next; next = after;
     }
 }
 
@@ -646,7 +664,7 @@ int launch_integrated(coffe_b200_ctx *ctx, Batch &b, const int mode, unsigned in
         /* the local x integrated kernel is compiled for a fixed warp count: the scalar path's panel lists are dropped when the
            warp-held bookkeeping is selected (they would not fit next to the renormalisation columns) */
         const bool si_warp_panels = ctx->qc.n_panel_si <= 32 && si_side_panels(ctx->qc, std::max(2.0e4, 1.01 * ctx->layout.chi_max_table)) <= 63;
-        const size_t per_warp = mode == 1 ? row_bytes + sizeof(SIHalf) + (si_warp_panels ? 0 : (size_t)2 * panel_cap * sizeof(double)) : 0;
+        const size_t per_warp = mode == 1 ? row_bytes + sizeof(SIItemSetup) + (si_warp_panels ? 0 : (size_t)2 * panel_cap * sizeof(double)) : 0;
         /* as many warps per SM as the remaining shared memory carries (the kernels are latency-bound: more is faster) */
         int warps = mode == 1 ? kSIThreads / 32 : kDIThreads / 32;
         const int threads = warps * 32;
@@ -1104,9 +1122,15 @@ int coffe_internal_prepare_tables(const coffe_b200_tables *T, PreparedTables &P,
 int coffe_internal_commit_tables(coffe_b200_ctx *ctx, PreparedTables &P, const bool own)
 {
     CK(cudaSetDevice(ctx->device));
-    if (ctx->d_arena) { cudaFree(ctx->d_arena); ctx->d_arena = nullptr; }
+    /* the device buffers are kept across uploads and only grow: a new cosmology per call is the MCMC inner loop, and cudaFree /
+       cudaMalloc beside a warm stream-ordered pool measured up to 100 ms there */
     ctx->have_tables = false;
-    CK(cudaMalloc(&ctx->d_arena, P.A.buf.size() * sizeof(double)));
+    if (ctx->d_arena_cap < P.A.buf.size()) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_arena) { cudaFree(ctx->d_arena); ctx->d_arena = nullptr; ctx->d_arena_cap = 0; }
+        CK(cudaMalloc(&ctx->d_arena, P.A.buf.size() * sizeof(double)));
+        ctx->d_arena_cap = P.A.buf.size();
+    }
     CK(cudaMemcpyAsync(ctx->d_arena, P.A.buf.data(), P.A.buf.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     const Layout &L = P.L;
     ctx->layout = L;
@@ -1114,9 +1138,13 @@ int coffe_internal_commit_tables(coffe_b200_ctx *ctx, PreparedTables &P, const b
     los_build_kernel<<<(L.los_n + 127) / 128, 128, 0, ctx->stream>>>(ctx->t, reinterpret_cast<double2 *>(ctx->d_arena + L.los), L.los_n, L.los_h,
                                                                      L.chi_max_table);
     CK(cudaGetLastError());
-    if (ctx->d_blob) { cudaFree(ctx->d_blob); ctx->d_blob = nullptr; }
     if (P.has_compact) {
-        CK(cudaMalloc(&ctx->d_blob, P.compact.blob.size() * sizeof(double)));
+        if (ctx->d_blob_cap < P.compact.blob.size()) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (ctx->d_blob) { cudaFree(ctx->d_blob); ctx->d_blob = nullptr; ctx->d_blob_cap = 0; }
+            CK(cudaMalloc(&ctx->d_blob, P.compact.blob.size() * sizeof(double)));
+            ctx->d_blob_cap = P.compact.blob.size();
+        }
         CK(cudaMemcpyAsync(ctx->d_blob, P.compact.blob.data(), P.compact.blob.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));

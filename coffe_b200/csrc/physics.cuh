@@ -356,7 +356,7 @@ COFFE_HD SIHalf si_half_setup(const Options &o, const Geometry &g, const EndVals
 template <bool MID = false, class TA>
 COFFE_HD double si_half_eval(const TA &t, const SIHalf &h, const Geometry &g, const double lambda, const double4 los)
 {
-    const double c = g.c, c2 = c * c, s2 = g.s2;
+    const double c = g.c, s2 = g.s2;
     const double cs = h.cs, l = lambda;
     /* r^2 = l^2 + cs^2 - 2 cs l cos(theta), written without the cancellation */
     const double dl = l - cs;
@@ -466,7 +466,7 @@ template <class TA>
 COFFE_HD double di_eval(const TA &t, const DIConst &k, const Geometry &g, const double l1, const double l2,
                         const double4 los1, const double4 los2)
 {
-    const double c = g.c, c2 = c * c;
+    const double c = g.c;
     const double d = l1 - l2;
     double r2 = d * d + 2.0 * l1 * l2 * g.omc;
     if (r2 < 0) r2 = 0;
