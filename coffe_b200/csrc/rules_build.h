@@ -22,7 +22,7 @@ inline QuadConfig default_quadrature()
     q.n_panel_si = 8; q.n_panel_di = 8;
     q.n_z = 8;
     q.panel_w = 64.0; q.panel_du = 128.0; q.eps_min = 1e-3; q.tail_ratio = 1.5;
-    q.n_mu_panel_di = 5; q.panel_w_di = 96.0; q.panel_du_di = 192.0; q.mu_panel_w_di = 64.0; q.tail_ratio_di = 6.0; q.geo_shift_di = 1;
+    q.n_mu_panel_di = 5; q.panel_w_di = 64.0; q.panel_du_di = 192.0; q.mu_panel_w_di = 64.0; q.tail_ratio_di = 6.0; q.geo_shift_di = 1;
     q.geo_growth = 1.0; q.geo_growth_di = 8.0;
     q.n_ren = 24;
     q.mu_growth = 3.0; q.mu_growth_di = 1.0; q.mu_switch_di = 1;
@@ -43,6 +43,7 @@ inline QuadConfig total_target_quadrature()
     QuadConfig q = default_quadrature();
     q.n_panel_di = 6; q.n_mu_panel_di = 4; q.n_ren = 12;
     q.n_outer_min = 25; q.n_outer_step = 15.0;
+    q.panel_w_di = 96.0;
     q.mu_growth = 8.0; q.mu_switch_di = 0;
     q.mu_panel_w = 64.0; q.n_mu_panel = 7; q.n_panel_si = 6;
     q.mu_rho0 = 8.0;
