@@ -264,7 +264,18 @@ COFFE_HD double di_inner_group(const DISideCtx<TA> &cx, const Rules &q, const DI
             const int e = u;
             const bool neg = ordinary ? (e == 0 || (e >= 2 && neg_long)) : true;
             const int k = !ordinary ? e : e == 0 ? p.k_neg - 1 : e == 1 ? p.k_pos - 1 : p.k_pair + e - 2;
-            if (k >= 0) {
+            const int map = k >= 0 ? panel_map(plan, k) : 0;
+            if (k >= 0 && ordinary && map == 1) {
+                /* sinh-map panel [k L, (k + 1) L] in t = asinh(d / eps); a last panel ends at the end of its line of sight */
+                const double b = neg ? p.b_neg : p.b_pos, xb = b / plan.eps;
+                const double s0 = k * plan.L, s1 = e < 2 ? fmin((k + 1) * plan.L, log(xb + sqrt(fma(xb, xb, 1.0)))) : (k + 1) * plan.L;
+                if (s1 > s0) {
+                    sides = neg ? 1 : 2;
+                    const double h = s1 - s0, ex = exp(fma(h, xj, s0)), ie = 1.0 / ex;
+                    d = (0.5 * plan.eps) * (ex - ie); wgt = (0.5 * plan.eps) * (ex + ie) * (h * wj);
+                }
+            }
+            else if (k >= 0) {
                 double lo = panel_break(plan, k), up = panel_break(plan, k + 1);
                 const double a = neg ? p.a_neg : 0.0, b = neg ? p.b_neg : p.b_pos;
                 const bool lo_cl = lo < a, up_cl = up > b;
@@ -272,7 +283,6 @@ COFFE_HD double di_inner_group(const DISideCtx<TA> &cx, const Rules &q, const DI
                 if (up_cl) up = b;
                 if (up > lo) {
                     sides = neg ? 1 : 2;
-                    const int map = panel_map(plan, k);
                     if (map == 2) {
                         if (lo_cl || up_cl) {
                             /* clipped tail panel [lo, up]: d = lo (1 + a x)^4 reaches up at x = 1 with a = (up/lo)^(1/4) - 1.  Like
@@ -282,7 +292,7 @@ COFFE_HD double di_inner_group(const DISideCtx<TA> &cx, const Rules &q, const DI
                         }
                         else { d = lo * pj; wgt = d * (plan.lnr * wj); }
                     }
-                    else if (map == 1) panel_node(plan, k, lo, up, lo_cl, up_cl, xj, wj, d, wgt);
+                    else if (map == 1) d = panel_node_sinh(plan.eps, plan.L, k, lo, up, lo_cl, up_cl, xj, wj, &wgt);
                     else { const double wd = up - lo; d = fma(wd, xj, lo); wgt = wd * wj; }
                 }
             }

@@ -6,6 +6,8 @@
 #if defined(__CUDACC__)
 #define COFFE_HD __host__ __device__ __forceinline__
 #define COFFE_D __device__ __forceinline__
+/* rarely executed helpers; kept inline: taken out of line (__noinline__) they measured 1.5 % slower (profiles/README.md) */
+#define COFFE_COLD __host__ __device__ __forceinline__
 #if defined(__CUDA_ARCH__)
 #define COFFE_SYNC_LANES() __syncwarp()
 #define COFFE_RSQRT(x) rsqrt(x)
@@ -18,6 +20,7 @@
 #define COFFE_RSQRT(x) (1.0 / std::sqrt(x))
 #define COFFE_HD inline
 #define COFFE_D inline
+#define COFFE_COLD inline
 #include <cmath>
 #include <cstring>
 struct alignas(8) int2 { int x, y; };

@@ -71,11 +71,17 @@ COFFE_HD PanelPlan panel_plan(double eps, const double eps_min, const double W, 
     return p;
 }
 
+/* break k < J of the geometric region (out of line: the kernels' hot loops ask for it a few times per line of sight) */
+COFFE_COLD double panel_break_geometric(const double eps, const double L, const int shift, const int k)
+{
+    return L > 0.0 ? eps * sinh(k * L) : ldexp(eps, shift * (k - 1));
+}
+
 COFFE_HD double panel_break(const PanelPlan &p, const int k)
 {
     if (k <= 0) return 0.0;
-    if (p.L > 0.0 && k <= p.J) return k == p.J ? p.BJ : p.eps * sinh(k * p.L);
-    if (k <= p.J) return ldexp(p.eps, p.shift * (k - 1));
+    if (k == p.J) return p.BJ;
+    if (k < p.J) return panel_break_geometric(p.eps, p.L, p.shift, k);
     if (k <= p.J + p.M) return p.BJ + (k - p.J) * p.W;
     const int n = k - p.J - p.M;
     return p.BJM * p.rpow[n < kMaxTail ? n : kMaxTail - 1];
@@ -159,6 +165,16 @@ COFFE_HD void panel_node(const PanelPlan &p, const int k, const double lo, const
     double s0, s1;
     panel_map_ends(p, map, k, lo, up, lo_clipped, up_clipped, s0, s1);
     panel_node_ends(p, map, s0, s1, x, w, d, wgt);
+}
+
+/* node of a sinh-map panel clipped to [lo, up], out of line (scalars only): returns d, *wgt = weight */
+COFFE_COLD double panel_node_sinh(const double eps, const double L, const int k, const double lo, const double up, const bool lo_clipped,
+                                  const bool up_clipped, const double x, const double w, double *wgt)
+{
+    const double s0 = lo_clipped ? asinh(lo / eps) : k * L, s1 = up_clipped ? asinh(up / eps) : (k + 1) * L;
+    const double h = s1 - s0, e = exp(fma(h, x, s0)), ie = 1.0 / e;
+    *wgt = (0.5 * eps) * (e + ie) * (h * w);
+    return (0.5 * eps) * (e - ie);
 }
 
 /* runtime quadrature configuration (mirrors coffe_b200_quadrature, include/coffe_b200.h) */

@@ -1,2 +1,3 @@
 python tools/quad_sweep.py 2>&1 | tail -1
-python -m pytest tests -m gpu -q -x -k "parity or capi" 2>&1 | tail -3
+python tools/piece_sweep.py 2>&1 | tail -4
+python -m pytest tests -m gpu -q -x -k "parity" 2>&1 | tail -3
