@@ -62,7 +62,7 @@ class Quadrature(C.Structure):
                 ("mu_panel_width_di", C.c_double), ("tail_ratio_di", C.c_double), ("geometric_shift_di", C.c_int),
                 ("accuracy_target", C.c_int), ("geometric_growth", C.c_double), ("geometric_growth_di", C.c_double), ("n_renorm", C.c_int), ("tail_map", C.c_int), ("tail_map_di", C.c_int),
                 ("mu_geometric_growth", C.c_double), ("mu_geometric_growth_di", C.c_double), ("mu_switch_break_di", C.c_int),
-                ("n_outer_min", C.c_int), ("n_outer_step", C.c_double)]
+                ("n_outer_min", C.c_int), ("n_outer_step", C.c_double), ("mu_tail_ratio", C.c_double)]
 
 
 class CovarianceParams(C.Structure):

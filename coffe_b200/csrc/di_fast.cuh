@@ -169,32 +169,12 @@ COFFE_HD double di_ren_smooth_partial(const Renorm2DView &r2d, const double2 *lo
 }
 
 /* The inner integral over lambda_2 in [0, chi2] at one outer node, on ONE GROUP of n_panel lanes: lane j owns node j of every panel
-   and walks through the panels in sequence -- first the K_pair mirror pairs (panels that neither side clips: the nodes at -d and +d
-   share R, hence one lookup of the nine I^n_l), then the remaining panels of the two sides singly.  A warp runs 32 / n_panel groups
-   side by side, each on its own outer node (engine.cu: di_items_smem_kernel), so the lanes stay busy whatever the panel counts are
-   and the set-up of an outer node is paid once per group, not once per warp.
-   Walking the panels in order makes the mapped nodes cheap: on the sinh-map panels (quadrature.cuh) sinh / cosh of t = L (k + x_j)
-   follow from the addition theorem and a two-term recurrence in k (one exp per lane and outer node), on the log-mapped tail panels
-   the node is the panel's start times ratio^x_j.  Returns this lane's partial sum. */
-struct DISides {
-    double a_neg, b_neg, b_pos;
-    int k_neg, k_pos, k_pair;
-};
-
-COFFE_HD DISides di_sides(const PanelPlan &plan, const DIFast &f, const DIOuter &o)
-{
-    DISides p;
-    p.b_neg = o.c0;
-    p.a_neg = o.c0 > f.chi2 ? o.c0 - f.chi2 : 0.0;
-    p.b_pos = f.chi2 - o.c0;
-    p.k_neg = panel_count(plan, p.b_neg);
-    p.k_pos = p.b_pos > 0.0 ? panel_count(plan, p.b_pos) : 0;
-    /* the last panel of the shorter side is clipped (or ends within rounding of the end of the line of sight): not paired */
-    const int kc = p.k_neg < p.k_pos ? p.k_neg : p.k_pos;
-    p.k_pair = (p.a_neg == 0.0 && kc > 0) ? kc - 1 : 0;
-    return p;
-}
-
+   and walks through the units of the integral in sequence (quadrature.cuh: RidgeUnits -- mirror pairs share one lookup of the nine
+   I^n_l).  A warp runs 32 / n_panel groups side by side, each on its own outer node (engine.cu: di_items_smem_kernel), so the
+   lanes stay busy whatever the panel counts are and the set-up of an outer node is paid once per group, not once per warp.
+   ONE loop over the units and ONE copy of the integrand (di_shared, and di_side in a loop over the two sides that is not unrolled):
+   the kernel is bound by its instruction footprint -- with separate loops for the pairs (two inlined sides) and the single panels
+   it measured 12 % slower, with a third copy for the last panels 25 %.  Returns this lane's partial sum. */
 COFFE_HD PanelPlan di_plan(const Rules &q, const DIOuter &o)
 {
     return panel_plan(sqrt(o.eps2), q.eps_min, q.panel_w_di, q.panel_du_di, q.tail_ratio_di, q.rpow_di, q.geo_shift_di, q.geo_L_di, q.tail_lnr_di);
@@ -206,97 +186,12 @@ COFFE_HD double di_inner_group(const DISideCtx<TA> &cx, const Rules &q, const DI
     const int np = q.n_panel_di;
     const double xj = q.panel_x ? q.panel_x[j] : q.gl_x[rule_offset(np) + j], wj = q.panel_w ? q.panel_w[j] : q.gl_w[rule_offset(np) + j];
     const PanelPlan plan = di_plan(q, o);
-    const DISides p = di_sides(plan, f, o);
+    RidgeUnits u;
+    ridge_units_init(u, plan, o.c0, f.chi2, xj, wj, plan.lnr > 0.0 ? (q.panel_p ? q.panel_p[j] : exp(plan.lnr * xj)) : 0.0);
     double acc = 0.0;
-    const double pj = plan.lnr > 0.0 ? (q.panel_p ? q.panel_p[j] : exp(plan.lnr * xj)) : 0.0;
-    double S = 0.0, C = 1.0, sj = 0.0, cj = 1.0, S1 = 0.0, C1 = 1.0;
-    if (plan.L > 0.0 && p.k_pair > 0) {
-        const double e = exp(plan.L * xj), ie = 1.0 / e, e1 = exp(plan.L), ie1 = 1.0 / e1;
-        sj = 0.5 * (e - ie); cj = 0.5 * (e + ie); S1 = 0.5 * (e1 - ie1); C1 = 0.5 * (e1 + ie1);
-    }
-    const int JM = plan.J + plan.M;
-    const bool ordinary = p.a_neg == 0.0;
-    const bool neg_long = p.k_neg > p.k_pos;
-    const int k_long = neg_long ? p.k_neg : p.k_pos;
-    const int n_single = ordinary ? 2 + (k_long - 1 > p.k_pair ? k_long - 1 - p.k_pair : 0) : p.k_neg;
-    const int n_units = n_single + p.k_pair;
-    /* ONE loop over the units and ONE copy of the integrand (di_shared, and di_side in a loop over the two sides that is not unrolled):
-       the kernel is bound by its instruction footprint -- with separate loops for the pairs (two inlined sides) and the single panels
-       it measured 12 % slower, with a third copy for the last panels 25 %.
-       Order: the panels left over beside the pairs first -- negative side k_pair .. k_neg-1, positive side k_pair .. k_pos-1: the
-       shorter side has one panel left, its last; the longer side the panels from k_pair on; every last panel is clipped by the end
-       of its line of sight, and the two of them come first, while all groups of the warp are still in step, so that the clipped
-       tail panel with its two square roots holds nobody up.  (When the ridge lies beyond the end of the second line of sight,
-       c0 > chi2, only |d| in [a_neg, b_neg] of the negative side exists: its panels in order, clipped at both ends.)  Then the
-       mirror pairs k = 0 .. k_pair-1, never clipped; on the sinh-map panels (S, C) = (sinh, cosh)(k L) follow from a two-term
-       recurrence with (S1, C1) = (sinh, cosh)(L) and the node from the addition theorem with (sj, cj) = (sinh, cosh)(L x_j). */
-    for (int u = 0; u < n_units; ++u) {
-        double d = 0.0, wgt = 0.0;
-        int sides = 0;
-        if (u >= n_single) {
-            const int k = u - n_single;
-            sides = 3;
-            if (k < plan.J) {
-                if (plan.L > 0.0) {
-                    d = plan.eps * fma(S, cj, C * sj);
-                    wgt = (plan.eps * plan.L * wj) * fma(C, cj, S * sj);
-                    const double Sn = fma(S, C1, C * S1);
-                    C = fma(C, C1, S * S1);
-                    S = Sn;
-                }
-                else {
-                    const double lo = panel_break(plan, k), wd = panel_break(plan, k + 1) - lo;
-                    d = fma(wd, xj, lo); wgt = wd * wj;
-                }
-            }
-            else if (k < JM) { d = fma(plan.W, xj, plan.BJ + (k - plan.J) * plan.W); wgt = plan.W * wj; }
-            else {
-                const int n = k - JM;
-                const double lo = plan.BJM * plan.rpow[n < kMaxTail ? n : kMaxTail - 1];
-                if (plan.lnr > 0.0) { d = lo * pj; wgt = d * (plan.lnr * wj); }
-                else {
-                    const double wd = plan.BJM * plan.rpow[n + 1 < kMaxTail ? n + 1 : kMaxTail - 1] - lo;
-                    d = fma(wd, xj, lo); wgt = wd * wj;
-                }
-            }
-        }
-        else {
-            const int e = u;
-            const bool neg = ordinary ? (e == 0 || (e >= 2 && neg_long)) : true;
-            const int k = !ordinary ? e : e == 0 ? p.k_neg - 1 : e == 1 ? p.k_pos - 1 : p.k_pair + e - 2;
-            const int map = k >= 0 ? panel_map(plan, k) : 0;
-            if (k >= 0 && ordinary && map == 1) {
-                /* sinh-map panel [k L, (k + 1) L] in t = asinh(d / eps); a last panel ends at the end of its line of sight */
-                const double b = neg ? p.b_neg : p.b_pos, xb = b / plan.eps;
-                const double s0 = k * plan.L, s1 = e < 2 ? fmin((k + 1) * plan.L, log(xb + sqrt(fma(xb, xb, 1.0)))) : (k + 1) * plan.L;
-                if (s1 > s0) {
-                    sides = neg ? 1 : 2;
-                    const double h = s1 - s0, ex = exp(fma(h, xj, s0)), ie = 1.0 / ex;
-                    d = (0.5 * plan.eps) * (ex - ie); wgt = (0.5 * plan.eps) * (ex + ie) * (h * wj);
-                }
-            }
-            else if (k >= 0) {
-                double lo = panel_break(plan, k), up = panel_break(plan, k + 1);
-                const double a = neg ? p.a_neg : 0.0, b = neg ? p.b_neg : p.b_pos;
-                const bool lo_cl = lo < a, up_cl = up > b;
-                if (lo_cl) lo = a;
-                if (up_cl) up = b;
-                if (up > lo) {
-                    sides = neg ? 1 : 2;
-                    if (map == 2) {
-                        if (lo_cl || up_cl) {
-                            /* clipped tail panel [lo, up]: d = lo (1 + a x)^4 reaches up at x = 1 with a = (up/lo)^(1/4) - 1.  Like
-                               log(d) it keeps d^-p far from its singularity (rho = 9 at up/lo = 6) at the price of two square roots */
-                            const double a4 = sqrt(sqrt(up / lo)) - 1.0, t = fma(a4, xj, 1.0), t2 = t * t;
-                            d = lo * (t2 * t2); wgt = (4.0 * a4 * lo * wj) * (t2 * t);
-                        }
-                        else { d = lo * pj; wgt = d * (plan.lnr * wj); }
-                    }
-                    else if (map == 1) d = panel_node_sinh(plan.eps, plan.L, k, lo, up, lo_cl, up_cl, xj, wj, &wgt);
-                    else { const double wd = up - lo; d = fma(wd, xj, lo); wgt = wd * wj; }
-                }
-            }
-        }
+    for (int iu = 0; iu < u.n_units; ++iu) {
+        double d, wgt;
+        const int sides = ridge_unit_node(u, iu, d, wgt);
         if (sides) {
             const DIShared s = di_shared(*cx.ta, f, o, d);
             double v = 0.0;
@@ -308,21 +203,10 @@ COFFE_HD double di_inner_group(const DISideCtx<TA> &cx, const Rules &q, const DI
     }
     return acc;
 }
+
 COFFE_HD unsigned int di_inner_eval_count(const Rules &q, const DIFast &f, const DIOuter &o)
 {
-    const PanelPlan plan = di_plan(q, o);
-    const DISides p = di_sides(plan, f, o);
-    unsigned int n = 2u * p.k_pair;
-    for (int side = 0; side < 2; ++side) {
-        const double a = side == 0 ? p.a_neg : 0.0, b = side == 0 ? p.b_neg : p.b_pos;
-        for (int k = p.k_pair; k < (side == 0 ? p.k_neg : p.k_pos); ++k) {
-            double lo = panel_break(plan, k), up = panel_break(plan, k + 1);
-            if (lo < a) lo = a;
-            if (up > b) up = b;
-            if (up > lo) ++n;
-        }
-    }
-    return n * q.n_panel_di;
+    return ridge_units_count(di_plan(q, o), o.c0, f.chi2) * q.n_panel_di;
 }
 
 /* integrated x integrated piece per unit (x1, x2): outer nodes strided over `ngroups` groups of n_panel lanes, `j` = this lane's node.

@@ -147,14 +147,17 @@ __global__ void __launch_bounds__(kItemThreads, COFFE_ITEM_MIN_BLOCKS) integrate
     __syncthreads();
 
     if (out_evals && tid == 0)
-        out_evals[item] = mode == 1 ? si_eval_count(q, sh.g, sh.ha) + si_eval_count(q, sh.g, sh.hb)
+        out_evals[item] = mode == 1 ? (o.midpoint ? si_eval_count(q, sh.g, sh.ha) + si_eval_count(q, sh.g, sh.hb)
+                                                  : si_group_eval_count(q, sh.g, sh.ha) + si_group_eval_count(q, sh.g, sh.hb))
                                     : (o.midpoint ? di_eval_count(q, sh.g) : di_fast_eval_count(q, sh.g, sh.k));
     const ExactAccess ta{&t};
     double v = 0.0;
     if (mode == 1) {
         if (warp < 2)
+            /* midpoint: the 2-D tables depend on z(lambda), no shared lookup for mirror nodes: the plain ridge rule.  Otherwise the
+               group walk of the shared-memory kernel, one group per half here (lanes beyond n_panel_si idle: this is the cross-check path) */
             v = o.midpoint ? si_half_partial<ExactAccess, true>(ta, t.los, q, sh.g, warp == 0 ? sh.ha : sh.hb, los, lane, 32, sh.panels[warp])
-                           : si_half_partial(ta, t.los, q, sh.g, warp == 0 ? sh.ha : sh.hb, los, lane, 32, sh.panels[warp]);
+                           : (lane < q.n_panel_si ? si_half_group(ta, t.ren2d, t.los, q, sh.g, warp == 0 ? sh.ha : sh.hb, los, lane) : 0.0);
     }
     /* midpoint approximation: the mirror nodes of di_fast share one table lookup, which the 2-D tables (z differs between the
        mirror nodes) do not allow: the plain ridge rule over di_eval, same panels and nodes */
@@ -217,40 +220,39 @@ __global__ void item_setup_kernel(const __grid_constant__ Tables t, const __grid
 
 constexpr int kSIThreads = 384;
 
-/* WARP_PANELS: panel bookkeeping of the two 1-D integrals held by the warp (item.cuh: si_half_partial_warp); the host selects it when
-   the configured plan never has more than 63 panels on a side (default: at most 36).  Per warp: one renormalisation column
-   (tables.cuh: ren_col_fill -- renormalisation(lambda, chi_source) collapsed onto lambda once per half, so a node costs one 1-D
-   Hermite lookup in shared memory instead of a 16-term bicubic patch through L2), then its state and the scalar path's panel list. */
-template <bool WARP_PANELS>
+/* Local x integrated piece, one HALF (item, source end) per group of n_panel_si lanes, 32 / n_panel_si halves side by side in a warp
+   (item.cuh: si_half_group).  A warp draws a batch of 32 / n_panel_si consecutive halves from a global counter; each group copies
+   the record of its half's item (geometry + both halves, written by item_setup_kernel) into its slot of shared memory -- read from
+   there with group-uniform addresses -- integrates, and adds its half to out[item] (two addends on a zeroed value: the order does
+   not matter).  The batches are drawn two ahead and the next record is in registers before the current half is done. */
+struct SIGroupSlot { Geometry g; SIHalf h; };
+
 __global__ void __launch_bounds__(kSIThreads, 1) si_items_smem_kernel(
     const __grid_constant__ Tables t, const __grid_constant__ Options o, const __grid_constant__ Rules q_in,
     const __grid_constant__ CompactHeader ch, const uint4 *__restrict__ blob, const int stage_bytes,
-    const double *__restrict__ pz, const double *__restrict__ psep,
-    const int *__restrict__ item_point, const double *__restrict__ item_mu, const SIItemSetup *__restrict__ item_setup, const int n_items,
-    const int los_stage_n, const int panel_cap, double *__restrict__ out,
+    const SIItemSetup *__restrict__ item_setup, const int n_items,
+    const int los_stage_n, double *__restrict__ out,
     unsigned int *__restrict__ out_evals, unsigned int *__restrict__ counter)
 {
     extern __shared__ __align__(16) unsigned char smem[];
+    const unsigned int full = 0xffffffffu;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int n_warps = kSIThreads / 32;
-    const int n_col_max = t.has_divergent ? t.ren2d.n : 0;
-    /* layout: [compact blob prefix][line-of-sight table][tail powers, panel rule][per-warp columns][per-warp half][per-warp panel lists] */
+    const int np = q_in.n_panel_si, ppi = 32 / np;          /* n_panel_si <= 32: the host checks */
+    const int grp = lane / np, j = lane - grp * np;
+    const bool lane_on = grp < ppi;
+    /* layout: [compact blob prefix][line-of-sight table][tail powers, panel rule][per-warp: ppi slots] */
     double2 *los_s = reinterpret_cast<double2 *>(smem + stage_bytes);
     double *small = reinterpret_cast<double *>(los_s + (size_t)kLosStride * los_stage_n);
-    double2 *cols = reinterpret_cast<double2 *>(small + kDISmallDoubles);
-    double2 *col = cols + (size_t)warp * n_col_max;
-    SIItemSetup *su_all = reinterpret_cast<SIItemSetup *>(cols + (size_t)n_warps * n_col_max);
-    SIItemSetup &su = su_all[warp]; /* geometry, amplitudes and polynomial coefficients of the item in work: read with uniform addresses (broadcast) */
-    double *scratch = reinterpret_cast<double *>(su_all + n_warps) + (size_t)warp * 2 * panel_cap;
+    SIGroupSlot *slots = reinterpret_cast<SIGroupSlot *>(small + kDISmallDoubles) + (size_t)warp * ppi;
     {
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
         for (int i = tid; i < stage_bytes / 16; i += kSIThreads) dst[i] = blob[i];
         for (int i = tid; i < kLosStride * los_stage_n; i += kSIThreads) los_s[i] = t.los.v[i];
         if (tid < kMaxTail) small[tid] = q_in.rpow[tid];
-        const int np = q_in.n_panel_si < 32 ? q_in.n_panel_si : 32;
         if (tid < np) {
-            small[kMaxTail + tid] = q_in.gl_x[rule_offset(q_in.n_panel_si) + tid];
-            small[kMaxTail + 32 + tid] = q_in.gl_w[rule_offset(q_in.n_panel_si) + tid];
+            small[kMaxTail + tid] = q_in.gl_x[rule_offset(np) + tid];
+            small[kMaxTail + 32 + tid] = q_in.gl_w[rule_offset(np) + tid];
+            small[kMaxTail + 64 + tid] = exp(q_in.tail_lnr * q_in.gl_x[rule_offset(np) + tid]);
         }
     }
     __syncthreads();
@@ -258,64 +260,64 @@ __global__ void __launch_bounds__(kSIThreads, 1) si_items_smem_kernel(
     ta.t = &t; ta.c.base = smem; ta.c.h = ch;
     LosView lv = t.los;
     lv.v = los_s;
-    /* the tail powers and the panel rule are read by every panel of every item: from shared memory, not through L1 */
     Rules q = q_in;
     q.rpow = small;
-    if (q_in.n_panel_si <= 32) { q.panel_x_si = small + kMaxTail; q.panel_w_si = small + kMaxTail + 32; }
+    q.panel_x_si = small + kMaxTail; q.panel_w_si = small + kMaxTail + 32; q.panel_p_si = small + kMaxTail + 64;
 
-    /* Items are drawn from a global counter two ahead, and the set-up record of the next item (768 bytes written by item_setup_kernel,
-       a DRAM round trip away) is loaded into registers while the current one is integrated: an item takes ~20 us, of which the
-       dependent chain counter -> record cost a third when it ran at the head of every item. */
-    constexpr int kWords = (int)(sizeof(SIItemSetup) / 8), kPre = (kWords + 31) / 32;
-    static_assert(sizeof(SIItemSetup) % 8 == 0, "the record is copied in 8-byte words");
+    /* words of a slot: the geometry of the item, then the half */
+    constexpr int kGeoWords = (int)(sizeof(Geometry) / 8), kHalfWords = (int)(sizeof(SIHalf) / 8), kWords = kGeoWords + kHalfWords;
+    constexpr int kRecWords = (int)(sizeof(SIItemSetup) / 8);
+    static_assert(sizeof(Geometry) % 8 == 0 && sizeof(SIHalf) % 8 == 0 && offsetof(SIItemSetup, h) == sizeof(Geometry), "records are copied in 8-byte words");
+    constexpr int kPre = 9;                                 /* words per lane held in registers: enough for n_panel_si >= 6 */
     const double *records = reinterpret_cast<const double *>(item_setup);
+    const unsigned int n_halves = 2u * (unsigned int)n_items;
     auto draw = [&]() {
         unsigned int i = 0;
-        if (lane == 0) i = atomicAdd(counter, 1u);
-        return __shfl_sync(0xffffffffu, i, 0);
+        if (lane == 0) i = atomicAdd(counter, (unsigned int)ppi);
+        return __shfl_sync(full, i, 0);
+    };
+    /* word i of the slot of half hh: the geometry of its item, then the half */
+    auto word_of = [&](const unsigned int hh, const int i) {
+        const int half_off = kGeoWords + (int)(hh & 1u) * kHalfWords;
+        return records + (size_t)(hh >> 1) * kRecWords + (i < kGeoWords ? i : half_off + (i - kGeoWords));
     };
     double pre[kPre];
-    auto prefetch = [&](const unsigned int i) {
-        if (i < (unsigned int)n_items)
+    auto prefetch = [&](const unsigned int batch) {
+        const unsigned int hh = batch + grp;
+        if (lane_on && hh < n_halves)
 #pragma unroll
             for (int w = 0; w < kPre; ++w)
-                if (lane + 32 * w < kWords) pre[w] = records[(size_t)i * kWords + lane + 32 * w];
+                if (j + np * w < kWords) pre[w] = *word_of(hh, j + np * w);
     };
-    unsigned int item = draw(), next = draw();
-    prefetch(item);
-    while (item < (unsigned int)n_items) {
-        __syncwarp();                   /* the previous item's readers are done */
-        {
-            double *dst = reinterpret_cast<double *>(&su);
+    unsigned int first = draw(), next = draw();
+    prefetch(first);
+    while (first < n_halves) {
+        const unsigned int hh = first + grp;
+        const bool valid = lane_on && hh < n_halves;
+        SIGroupSlot &slot = slots[lane_on ? grp : 0];
+        __syncwarp();                   /* the previous batch's readers are done */
+        if (valid) {
+            double *dst = reinterpret_cast<double *>(&slot);
 #pragma unroll
             for (int w = 0; w < kPre; ++w)
-                if (lane + 32 * w < kWords) dst[lane + 32 * w] = pre[w];
+                if (j + np * w < kWords) dst[j + np * w] = pre[w];
+            for (int i = j + np * kPre; i < kWords; i += np) dst[i] = *word_of(hh, i);      /* fewer than 6 lanes per group: the rest directly */
         }
         __syncwarp();
         prefetch(next);
         const unsigned int after = draw();
-        const Geometry &g = su.g;
-        if (out_evals && lane == 0) out_evals[item] = si_eval_count(q, g, su.h[0]) + si_eval_count(q, g, su.h[1]);
         double si = 0.0;
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-            const SIHalf &h = su.h[half];
-            if (h.need_ren) {
-                __syncwarp();           /* the previous half's readers of the column are done */
-                ta.n_col = ren_row_count(t.ren2d, h.co);
-                ren_col_fill(t.ren2d, h.cs, ta.n_col, col, lane, 32);
-                ta.col = col;
-                __syncwarp();
-            }
-            else ta.col = nullptr;
-#if defined(__CUDA_ARCH__)
-            if (WARP_PANELS) { si += si_half_partial_warp(ta, lv, q, g, h, los_s, lane); continue; }
-#endif
-            si += si_half_partial(ta, lv, q, g, h, los_s, lane, 32, scratch);
+        if (valid) {
+            si = si_half_group(ta, t.ren2d, lv, q, slot.g, slot.h, los_s, j);
+            if (out_evals && j == 0) atomicAdd(&out_evals[hh >> 1], si_group_eval_count(q, slot.g, slot.h));
         }
-        si = warp_sum(si);
-        if (lane == 0) out[item] = si;
-        item = next; next = after;
+        /* sum over the lanes of the group: np <= 32 consecutive lanes */
+        for (int off = 1; off < np; off <<= 1) {
+            const double other = __shfl_down_sync(full, si, off);
+            if (j + off < np) si += other;
+        }
+        if (valid && j == 0) atomicAdd(&out[hh >> 1], si);
+        first = next; next = after;
     }
 }
 
@@ -404,7 +406,8 @@ __global__ void item_cost_kernel(const __grid_constant__ Tables t, const __grid_
     const Geometry g = geometry(bg_chi(t.bg, pz[p]), psep[p], item_mu[i]);
     const EndVals e1 = end_eval(o, t, g.chi1, 1), e2 = end_eval(o, t, g.chi2, 2);
     unsigned int c;
-    if (mode == 1) c = si_eval_count(q, g, si_half_setup(o, g, e1, e2, true)) + si_eval_count(q, g, si_half_setup(o, g, e2, e1, false));
+    if (mode == 1) c = o.midpoint ? si_eval_count(q, g, si_half_setup(o, g, e1, e2, true)) + si_eval_count(q, g, si_half_setup(o, g, e2, e1, false))
+                                  : si_group_eval_count(q, g, si_half_setup(o, g, e1, e2, true)) + si_group_eval_count(q, g, si_half_setup(o, g, e2, e1, false));
     else c = di_fast_eval_count(q, g, di_setup(o, e1, e2));
     atomicAdd(&cost[p], (unsigned long long)c * weight);
 }
@@ -523,7 +526,7 @@ Rules make_rules(const coffe_b200_ctx *ctx)
     q.panel_w_mpc = ctx->qc.panel_w; q.panel_du = ctx->qc.panel_du; q.eps_min = ctx->qc.eps_min; q.tail_ratio = ctx->qc.tail_ratio;
     q.panel_w_di = ctx->qc.panel_w_di; q.panel_du_di = ctx->qc.panel_du_di;
     q.panel_x = q.panel_w = q.panel_p = nullptr;
-    q.panel_x_si = q.panel_w_si = nullptr;
+    q.panel_x_si = q.panel_w_si = q.panel_p_si = nullptr;
     q.rpow_di = ctx->d_rpow_di; q.tail_ratio_di = ctx->qc.tail_ratio_di; q.geo_shift_di = ctx->qc.geo_shift_di;
     q.n_ren = ctx->qc.n_ren;
     q.tail_lnr = ctx->qc.tail_log ? std::log(ctx->qc.tail_ratio) : 0.0;
@@ -653,19 +656,14 @@ int launch_integrated(coffe_b200_ctx *ctx, Batch &b, const int mode, unsigned in
     int stage_n = (int)std::ceil(b.chi_max / ctx->layout.los_h) + 3;
     if (stage_n > ctx->layout.los_n) stage_n = ctx->layout.los_n;
     const size_t los_bytes = (size_t)kLosStride * stage_n * sizeof(double2);
-    const size_t row_bytes = (size_t)(ctx->layout.has_divergent ? ctx->layout.ren2d_n : 0) * sizeof(double2);
-    if (ctx->variant == 1 && ctx->compact.h.valid && !ctx->o.midpoint && (mode == 1 || ctx->qc.n_panel_di <= 32)) {
+    if (ctx->variant == 1 && ctx->compact.h.valid && !ctx->o.midpoint && (mode == 1 ? ctx->qc.n_panel_si <= 32 : ctx->qc.n_panel_di <= 32)) {
         /* shared-memory tables: blob prefix covering R <= 2 chi_max, line-of-sight table, per-warp state */
         const int stage_bytes = compact_stage_bytes(ctx->compact, 2.0 * b.chi_max);
         CompactHeader ch = ctx->compact.h;
         ch.n_knots = (stage_bytes - ch.off_knots) / kKnotBytes;
-        const int panel_cap = max_panels(ctx->qc);
         const size_t fixed = (size_t)stage_bytes + los_bytes + kDISmallDoubles * sizeof(double);
-        /* the local x integrated kernel is compiled for a fixed warp count: the scalar path's panel lists are dropped when the
-           warp-held bookkeeping is selected (they would not fit next to the renormalisation columns) */
-        const bool si_warp_panels = ctx->qc.n_panel_si <= 32 && si_side_panels(ctx->qc, std::max(2.0e4, 1.01 * ctx->layout.chi_max_table)) <= 63;
-        const size_t per_warp = mode == 1 ? row_bytes + sizeof(SIItemSetup) + (si_warp_panels ? 0 : (size_t)2 * panel_cap * sizeof(double)) : 0;
-        /* as many warps per SM as the remaining shared memory carries (the kernels are latency-bound: more is faster) */
+        /* per warp: one slot (geometry + half) per group of the local x integrated kernel */
+        const size_t per_warp = mode == 1 ? (size_t)(32 / ctx->qc.n_panel_si) * sizeof(SIGroupSlot) : 0;
         int warps = mode == 1 ? kSIThreads / 32 : kDIThreads / 32;
         const int threads = warps * 32;
         const size_t need = fixed + (size_t)warps * per_warp;
@@ -681,11 +679,14 @@ int launch_integrated(coffe_b200_ctx *ctx, Batch &b, const int mode, unsigned in
             int grid = std::min(ctx->n_sm, (L.n + warps - 1) / warps);
             if (grid < 1) grid = 1;
             if (mode == 1) {
-                auto kernel = si_warp_panels ? si_items_smem_kernel<true> : si_items_smem_kernel<false>;
+                /* every half adds itself to its item's value (and count) */
+                CK(cudaMemsetAsync(L.val.p, 0, sizeof(double) * L.n, ctx->stream));
+                if (evals) CK(cudaMemsetAsync(evals, 0, sizeof(unsigned int) * L.n, ctx->stream));
+                auto kernel = si_items_smem_kernel;
                 CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
                 kernel<<<grid, threads, need, ctx->stream>>>(
-                    ctx->t, ctx->o, make_rules(ctx), ch, reinterpret_cast<const uint4 *>(ctx->d_blob), stage_bytes, b.pz.p, b.psep.p,
-                    L.point.p, L.mu.p, reinterpret_cast<const SIItemSetup *>(L.setup.p), L.n, stage_n, si_warp_panels ? 0 : panel_cap, L.val.p, evals, ctx->d_counter);
+                    ctx->t, ctx->o, make_rules(ctx), ch, reinterpret_cast<const uint4 *>(ctx->d_blob), stage_bytes,
+                    reinterpret_cast<const SIItemSetup *>(L.setup.p), L.n, stage_n, L.val.p, evals, ctx->d_counter);
             }
             else {
                 auto kernel = di_items_smem_kernel;
@@ -1239,7 +1240,7 @@ int coffe_b200_get_quadrature(const coffe_b200_ctx *ctx, coffe_b200_quadrature *
     q->geometric_growth = c.geo_growth; q->geometric_growth_di = c.geo_growth_di; q->n_renorm = c.n_ren;
     q->tail_map = c.tail_log ? 2 : 1; q->tail_map_di = c.tail_log_di ? 2 : 1;
     q->mu_geometric_growth = c.mu_growth; q->mu_geometric_growth_di = c.mu_growth_di; q->mu_switch_break_di = c.mu_switch_di ? 1 : 2;
-    q->n_outer_min = c.n_outer_min; q->n_outer_step = c.n_outer_step;
+    q->n_outer_min = c.n_outer_min; q->n_outer_step = c.n_outer_step; q->mu_tail_ratio = c.mu_tail;
     q->accuracy_target = ctx->target_in_force;
     return COFFE_B200_OK;
 }
@@ -1373,6 +1374,11 @@ static int corrfunc_core(coffe_b200_ctx *ctx, const double *z_mean, int n_z, con
 int coffe_internal_corrfunc_range(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double *mu, int n_mu,
                                   const double *sep, int n_sep, long begin, long end, double *out_sum)
 {
+    /* The 2-point function at a fixed mu always runs under the piece rules: the total target sizes the rules of the integrated
+       pieces against the l = 0..4 scale of a multipole, i.e. after the mu integral; at a single (mu, r) the local terms can be
+       close to a zero crossing and the caller compares the value with itself. */
+    PieceRules pr(ctx);
+    if (pr.rc) return pr.rc;
     std::vector<double> pc;
     const int rc = corrfunc_core(ctx, z_mean, n_z, mu, n_mu, sep, n_sep, begin, end, pc);
     if (rc) return rc;

@@ -22,6 +22,7 @@ struct Rules {
     const double *panel_x, *panel_w; /* nodes / weights of the n_panel_di rule when staged separately (else null: read from the bank) */
     const double *panel_p;           /* tail_ratio_di^x_j for the nodes of that rule, when staged (log-mapped tail panels) */
     const double *panel_x_si, *panel_w_si;   /* the same for the n_panel_si rule */
+    const double *panel_p_si;                /* tail_ratio^x_j for the nodes of that rule, when staged */
     const double *rpow_di;           /* tail_ratio_di^n, n < kMaxTail */
     double tail_ratio_di;
     int geo_shift_di;
@@ -147,55 +148,73 @@ COFFE_HD unsigned int si_eval_count(const Rules &q, const Geometry &g, const SIH
     return ridge_eval_count(h.co, h.cs * g.c, h.cs * sqrt(g.s2), q, q.n_panel_si);
 }
 
-#if defined(__CUDA_ARCH__)
-/* The same integral on a full warp with the panel bookkeeping held by the warp (the scheme of di_fast.cuh: di_inner_partial_warp):
-   lane k computes the break B_k once, the panel counts of the two sides are two ballots, a panel's ends two shuffles.  With ~3.5
-   sweeps per lane and half, the scalar bookkeeping of ridge_integrate (panel plan, two counting loops, panel list through shared
-   memory, two barriers) cost as many instructions as the evaluations themselves (ncu r2: 713 thread instructions per evaluation
-   against 342 in the integrated x integrated kernel).  Same breaks, nodes and weights; the panel count is the by-break definition
-   (quadrature.cuh: panel_count_by_break), so a break within rounding of the end of a side may add a panel a few ulp wide.
-   Valid when a side never has more than 63 panels and the rule is staged (q.panel_x_si): the host checks the configured plan. */
-template <class TA>
-__device__ __forceinline__ double si_half_partial_warp(const TA &t, const LosView &lv, const Rules &q, const Geometry &g, const SIHalf &h,
-                                                       const double2 *los, const int lane)
+/* ---- one half on ONE GROUP of n_panel_si lanes (the layout of di_fast.cuh: di_inner_group) ---------------------------------------
+   Lane j owns node j of every panel and walks through the units of the half's line-of-sight integral in sequence (quadrature.cuh:
+   RidgeUnits).  R^2 = d^2 + cs^2 sin^2(theta) depends on |d| = |lambda - cs cos(theta)| only, so the two nodes of a mirror pair
+   share one lookup of the nine I^n_l here too; the brackets, polynomials in lambda (physics.cuh: si_half_body), are evaluated per
+   side.  A warp runs 32 / n_panel_si halves side by side (engine.cu: si_items_smem_kernel).
+   renormalization(lambda, chi_source), the smooth half of the renormalised potential terms, is integrated apart on two
+   Gauss-Legendre panels split at lambda = chi_source (the reasoning of di_fast.cuh: di_ren_smooth_partial): no column of the
+   renormalisation grid per half in shared memory, which is what lets several halves share a warp. */
+COFFE_HD double si_ren_smooth_partial(const Renorm2DView &r2d, const double2 *los, const int los_n, const double los_inv_h, const Rules &q,
+                                      const SIHalf &h, const int j, const int nlanes)
 {
-    const unsigned int full = 0xffffffffu;
-    const int np = q.n_panel_si;            /* <= 32 (the caller checks) */
-    const int ppi = 32 / np;
-    const int lp = lane / np, j = lane - lp * np;
-    const bool on = lp < ppi;
-    const double center = h.cs * g.c, eps = h.cs * sqrt(g.s2), hi = h.co;
-    const PanelPlan plan = panel_plan(eps, q.eps_min, q.panel_w_mpc, q.panel_du, q.tail_ratio, q.rpow, 1, q.geo_L, q.tail_lnr);
-    /* breaks B_0 .. B_63 in two registers per lane (the default plan needs up to 36 per side: 18 geometric from the eps floor,
-       3 uniform, 15 tail panels at ratio 1.5) */
-    const double brk0 = panel_break(plan, lane), brk1 = panel_break(plan, lane + 32);
-    const double b_neg = center, a_neg = center > hi ? center - hi : 0.0, b_pos = hi - center;
-    const int k_neg = b_neg > 0.0 ? __popc(__ballot_sync(full, brk0 < b_neg)) + __popc(__ballot_sync(full, brk1 < b_neg)) : 0;
-    const int k_pos = b_pos > 0.0 ? __popc(__ballot_sync(full, brk0 < b_pos)) + __popc(__ballot_sync(full, brk1 < b_pos)) : 0;
-    const double xj = q.panel_x_si[j], wj = q.panel_w_si[j];
-    const int n_all = k_neg + k_pos;
+    const int half = q.n_ren / 2;
+    const double *x = q.gl_x + rule_offset(half), *w = q.gl_w + rule_offset(half);
+    const double split = h.cs < h.co ? h.cs : h.co;
     double acc = 0.0;
-    for (int e0 = 0; e0 < n_all; e0 += ppi) {
-        const int e = e0 + lp;
-        const bool neg = e < k_neg;
-        const int k = neg ? e : e - k_neg;
-        const double lo0 = __shfl_sync(full, brk0, k & 31), lo1 = __shfl_sync(full, brk1, k & 31);
-        const double up0 = __shfl_sync(full, brk0, (k + 1) & 31), up1 = __shfl_sync(full, brk1, (k + 1) & 31);
-        double lo = k < 32 ? lo0 : lo1, up = k + 1 < 32 ? up0 : up1;
-        const double a = neg ? a_neg : 0.0, b = neg ? b_neg : b_pos;
-        const bool lo_cl = lo < a, up_cl = up > b;
-        if (lo_cl) lo = a;
-        if (up_cl) up = b;
-        if (on && e < n_all && up > lo) {
-            double d, wgt;
-            panel_node(plan, k, lo, up, lo_cl, up_cl, xj, wj, d, wgt);
-            const double lambda = neg ? center - d : center + d;
-            acc = fma(wgt, si_half_eval(t, h, g, lambda, los_eval(los, lv.n, lv.inv_h, lambda)), acc);
+    for (int i = j; i < 2 * half; i += nlanes) {
+        const bool upper = i >= half;
+        const int jj = upper ? i - half : i;
+        const double lo = upper ? split : 0.0, wd = upper ? h.co - split : split;
+        const double l = fma(wd, x[jj], lo);
+        const double4 ls = los_eval(los, los_n, los_inv_h, l);
+        acc = fma(wd * w[jj], renorm2d_eval(r2d, l, h.cs) * ls.x * fma(h.g5_ren, ls.y, h.g4_ren), acc);
+    }
+    return -acc;
+}
+
+COFFE_HD PanelPlan si_plan(const Rules &q, const Geometry &g, const SIHalf &h)
+{
+    return panel_plan(h.cs * sqrt(g.s2), q.eps_min, q.panel_w_mpc, q.panel_du, q.tail_ratio, q.rpow, 1, q.geo_L, q.tail_lnr);
+}
+
+template <class TA>
+COFFE_HD double si_half_group(const TA &t, const Renorm2DView &r2d, const LosView &lv, const Rules &q, const Geometry &g, const SIHalf &h,
+                              const double2 *los, const int j)
+{
+    const int np = q.n_panel_si;
+    const double xj = q.panel_x_si ? q.panel_x_si[j] : q.gl_x[rule_offset(np) + j], wj = q.panel_w_si ? q.panel_w_si[j] : q.gl_w[rule_offset(np) + j];
+    const double center = h.cs * g.c, eps2 = h.cs * h.cs * g.s2;
+    const PanelPlan plan = si_plan(q, g, h);
+    RidgeUnits u;
+    ridge_units_init(u, plan, center, h.co, xj, wj, plan.lnr > 0.0 ? (q.panel_p_si ? q.panel_p_si[j] : exp(plan.lnr * xj)) : 0.0);
+    double acc = 0.0;
+    for (int iu = 0; iu < u.n_units; ++iu) {
+        double d, wgt;
+        const int sides = ridge_unit_node(u, iu, d, wgt);
+        if (sides) {
+            const double rr = fma(d, d, eps2), iR = rr > 0.0 ? COFFE_RSQRT(rr) : 0.0;
+            double I[N_ITAB9];
+            t.ifam9(rr * iR, I, h.need_ren != 0);
+            double v = 0.0;
+#pragma unroll 1
+            for (int sd = 0; sd < 2; ++sd)
+                if (sides & (1 << sd)) {
+                    const double l = sd == 0 ? center - d : center + d;
+                    v += si_half_body<false, true>(t, h, g, l, los_eval(los, lv.n, lv.inv_h, l), rr, iR, I);
+                }
+            acc = fma(wgt, v, acc);
         }
     }
+    if (h.need_ren) acc += si_ren_smooth_partial(r2d, los, lv.n, lv.inv_h, q, h, j, np);
     return acc / h.co;
 }
-#endif
+
+COFFE_HD unsigned int si_group_eval_count(const Rules &q, const Geometry &g, const SIHalf &h)
+{
+    return ridge_units_count(si_plan(q, g, h), h.cs * g.c, h.co) * q.n_panel_si;
+}
 
 template <class TA>
 struct DIFunctor {

@@ -351,21 +351,17 @@ COFFE_HD SIHalf si_half_setup(const Options &o, const Geometry &g, const EndVals
     return h;
 }
 
-/* integrand of one half at lambda (distance along the integrated line of sight), per unit x = lambda/co.
-   los = {W, V, U, Wa}(lambda). */
-template <bool MID = false, class TA>
-COFFE_HD double si_half_eval(const TA &t, const SIHalf &h, const Geometry &g, const double lambda, const double4 los)
+/* The part of the integrand behind the table lookup: rr = R^2, iR = 1/R and I = the nine table values at R are passed in, so that the
+   kernel can share one lookup between the two nodes at the same distance from the closest approach (item.cuh: si_half_group).
+   SPLIT_REN: renormalization(lambda, chi_source) is integrated apart (si_ren_smooth_partial), only I^4_0(R) is added here. */
+template <bool MID, bool SPLIT_REN, class TA>
+COFFE_HD double si_half_body(const TA &t, const SIHalf &h, const Geometry &g, const double lambda, const double4 los,
+                             const double rr, const double iR, const double *I)
 {
     const double c = g.c, s2 = g.s2;
     const double cs = h.cs, l = lambda;
-    /* r^2 = l^2 + cs^2 - 2 cs l cos(theta), written without the cancellation */
     const double dl = l - cs;
-    double rr = dl * dl + 2.0 * cs * l * g.omc;
-    if (rr < 0) rr = 0;
-    const double iR = rr > 0.0 ? COFFE_RSQRT(rr) : 0.0;
     const double R = rr * iR;
-    double I[N_ITAB9];
-    t.ifam9(R, I, h.need_ren != 0);          /* the eight I^n_l and, for the renormalised potential terms, I^4_0 in the same lookup */
     const double W = los.x, V = los.y, Wa = los.w;
     double res = 0.0;
     /* Midpoint approximation (src/functions.c:1626-1700, 2061-2326, 2492-2918): den-len, rsd-len and d1-len read
@@ -410,13 +406,29 @@ COFFE_HD double si_half_eval(const TA &t, const SIHalf &h, const Geometry &g, co
     if (h.any_g4 || h.any_g5) {
         double ren = 0.0;
         if (h.need_ren)                                                                             /* :1524-1556 */
-            ren = (rr == 0.0) ? t.ren0(l) : I[N_ITAB] - t.ren2d(l, cs);
+            ren = SPLIT_REN ? ((rr == 0.0) ? t.ren0(l) + t.ren2d(l, cs) : I[N_ITAB])
+                            : ((rr == 0.0) ? t.ren0(l) : I[N_ITAB] - t.ren2d(l, cs));
         const double b_rsd = (2 * rr / 3. - s2 * l * l) * I[I22] - I[I20] / 3.;
         const double b_d1 = (l * c - cs) * I[I31];
         if (h.any_g4) res += W * (h.g4_i20 * I[I20] + h.g4_rsd * b_rsd + h.g4_d1 * b_d1 + h.g4_ren * ren);
         if (h.any_g5) res += V * (h.g5_i20 * Wa * I[I20] + W * (h.g5_rsd * b_rsd + h.g5_d1 * b_d1 + h.g5_ren * ren));
     }
     return res;
+}
+
+/* integrand of one half at lambda (distance along the integrated line of sight), per unit x = lambda/co.
+   los = {W, V, U, Wa}(lambda). */
+template <bool MID = false, class TA>
+COFFE_HD double si_half_eval(const TA &t, const SIHalf &h, const Geometry &g, const double lambda, const double4 los)
+{
+    /* r^2 = l^2 + cs^2 - 2 cs l cos(theta), written without the cancellation */
+    const double dl = lambda - h.cs;
+    double rr = dl * dl + 2.0 * h.cs * lambda * g.omc;
+    if (rr < 0) rr = 0;
+    const double iR = rr > 0.0 ? COFFE_RSQRT(rr) : 0.0;
+    double I[N_ITAB9];
+    t.ifam9(rr * iR, I, h.need_ren != 0);    /* the eight I^n_l and, for the renormalised potential terms, I^4_0 in the same lookup */
+    return si_half_body<MID, false>(t, h, g, lambda, los, rr, iR, I);
 }
 
 /* ---- integrated x integrated ------------------------------------------------------------------- */

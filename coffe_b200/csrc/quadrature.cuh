@@ -177,6 +177,137 @@ COFFE_COLD double panel_node_sinh(const double eps, const double L, const int k,
     return (0.5 * eps) * (e - ie);
 }
 
+/* ---- the panels of one ridge integral as a sequence of UNITS, for one lane that owns node j of every panel -------------------
+   Integral over lambda in [0, hi] with the closest approach at `center` (>= 0): |d| = |lambda - center| runs over
+   [a_neg, b_neg] on the near side and [0, b_pos] on the far side.  Where neither side is clipped the panels of the two sides are
+   mirror images: such a MIRROR PAIR is one unit with two nodes, center - d and center + d, which share R = sqrt(d^2 + eps^2) and
+   therefore one table lookup.  Order of the units (ridge_unit_node):
+     1. the two last panels (near side k_neg-1, far side k_pos-1), each clipped by the end of its line of sight -- first, while
+        the groups of lanes that walk different integrals side by side in a warp are still in step, so that a clipped tail panel
+        with its two square roots holds nobody up;
+     2. the unclipped panels k_pair .. of the longer side that have no partner;
+     3. the mirror pairs k = 0 .. k_pair-1; on the sinh-map panels (S, C) = (sinh, cosh)(k L) follow from a two-term recurrence
+        with (S1, C1) = (sinh, cosh)(L) and the node from the addition theorem with (sj, cj) = (sinh, cosh)(L x_j): one exp per
+        lane and integral; on the log-mapped tail panels the node is the panel's start times ratio^x_j (pj).
+   When the closest approach lies beyond the end of the line of sight (center > hi) only [a_neg, b_neg] of the near side exists:
+   its panels in order, clipped at both ends. */
+struct RidgeUnits {
+    PanelPlan plan;
+    double a_neg, b_neg, b_pos;
+    int k_neg, k_pos, k_pair;
+    bool ordinary, neg_long;
+    int n_single, n_units;
+    double xj, wj, pj;
+    double S, C, sj, cj, S1, C1;
+};
+
+COFFE_HD void ridge_units_init(RidgeUnits &u, const PanelPlan &plan, const double center, const double hi, const double xj, const double wj,
+                               const double pj /* ratio^x_j of a log-tail plan, 0 otherwise */)
+{
+    u.plan = plan;
+    u.xj = xj; u.wj = wj; u.pj = pj;
+    u.b_neg = center;
+    u.a_neg = center > hi ? center - hi : 0.0;
+    u.b_pos = hi - center;
+    u.k_neg = panel_count(plan, u.b_neg);
+    u.k_pos = u.b_pos > 0.0 ? panel_count(plan, u.b_pos) : 0;
+    /* the last panel of the shorter side is clipped (or ends within rounding of the end of the line of sight): not paired */
+    const int kc = u.k_neg < u.k_pos ? u.k_neg : u.k_pos;
+    u.k_pair = (u.a_neg == 0.0 && kc > 0) ? kc - 1 : 0;
+    u.ordinary = u.a_neg == 0.0;
+    u.neg_long = u.k_neg > u.k_pos;
+    const int k_long = u.neg_long ? u.k_neg : u.k_pos;
+    u.n_single = u.ordinary ? 2 + (k_long - 1 > u.k_pair ? k_long - 1 - u.k_pair : 0) : u.k_neg;
+    u.n_units = u.n_single + u.k_pair;
+    u.S = 0.0; u.C = 1.0; u.sj = 0.0; u.cj = 1.0; u.S1 = 0.0; u.C1 = 1.0;
+    if (plan.L > 0.0 && u.k_pair > 0) {
+        const double e = exp(plan.L * xj), ie = 1.0 / e, e1 = exp(plan.L), ie1 = 1.0 / e1;
+        u.sj = 0.5 * (e - ie); u.cj = 0.5 * (e + ie); u.S1 = 0.5 * (e1 - ie1); u.C1 = 0.5 * (e1 + ie1);
+    }
+}
+
+/* unit iu = 0 .. n_units-1, to be asked for in order: |d| of this lane's node, its weight, and which sides carry it
+   (bit 0: center - d, bit 1: center + d; 0: empty) */
+COFFE_HD int ridge_unit_node(RidgeUnits &u, const int iu, double &d, double &wgt)
+{
+    const PanelPlan &plan = u.plan;
+    const double xj = u.xj, wj = u.wj;
+    d = 0.0; wgt = 0.0;
+    if (iu >= u.n_single) {
+        const int k = iu - u.n_single;
+        if (k < plan.J) {
+            if (plan.L > 0.0) {
+                d = plan.eps * fma(u.S, u.cj, u.C * u.sj);
+                wgt = (plan.eps * plan.L * wj) * fma(u.C, u.cj, u.S * u.sj);
+                const double Sn = fma(u.S, u.C1, u.C * u.S1);
+                u.C = fma(u.C, u.C1, u.S * u.S1);
+                u.S = Sn;
+            }
+            else {
+                const double lo = panel_break(plan, k), wd = panel_break(plan, k + 1) - lo;
+                d = fma(wd, xj, lo); wgt = wd * wj;
+            }
+        }
+        else if (k < plan.J + plan.M) { d = fma(plan.W, xj, plan.BJ + (k - plan.J) * plan.W); wgt = plan.W * wj; }
+        else {
+            const int n = k - plan.J - plan.M;
+            const double lo = plan.BJM * plan.rpow[n < kMaxTail ? n : kMaxTail - 1];
+            if (plan.lnr > 0.0) { d = lo * u.pj; wgt = d * (plan.lnr * wj); }
+            else {
+                const double wd = plan.BJM * plan.rpow[n + 1 < kMaxTail ? n + 1 : kMaxTail - 1] - lo;
+                d = fma(wd, xj, lo); wgt = wd * wj;
+            }
+        }
+        return 3;
+    }
+    const int e = iu;
+    const bool neg = u.ordinary ? (e == 0 || (e >= 2 && u.neg_long)) : true;
+    const int k = !u.ordinary ? e : e == 0 ? u.k_neg - 1 : e == 1 ? u.k_pos - 1 : u.k_pair + e - 2;
+    if (k < 0) return 0;
+    const int map = panel_map(plan, k);
+    if (u.ordinary && map == 1) {
+        /* sinh-map panel [k L, (k + 1) L] in t = asinh(d / eps); a last panel ends at the end of its line of sight */
+        const double b = neg ? u.b_neg : u.b_pos, xb = b / plan.eps;
+        const double s0 = k * plan.L, s1 = e < 2 ? fmin((k + 1) * plan.L, log(xb + sqrt(fma(xb, xb, 1.0)))) : (k + 1) * plan.L;
+        if (!(s1 > s0)) return 0;
+        const double h = s1 - s0, ex = exp(fma(h, xj, s0)), ie = 1.0 / ex;
+        d = (0.5 * plan.eps) * (ex - ie); wgt = (0.5 * plan.eps) * (ex + ie) * (h * wj);
+        return neg ? 1 : 2;
+    }
+    double lo = panel_break(plan, k), up = panel_break(plan, k + 1);
+    const double a = neg ? u.a_neg : 0.0, b = neg ? u.b_neg : u.b_pos;
+    const bool lo_cl = lo < a, up_cl = up > b;
+    if (lo_cl) lo = a;
+    if (up_cl) up = b;
+    if (!(up > lo)) return 0;
+    if (map == 2) {
+        if (lo_cl || up_cl) {
+            /* clipped tail panel [lo, up]: d = lo (1 + a x)^4 reaches up at x = 1 with a = (up/lo)^(1/4) - 1.  Like log(d) it keeps
+               d^-p far from its singularity (rho = 9 at up/lo = 6) at the price of two square roots instead of log and exp */
+            const double a4 = sqrt(sqrt(up / lo)) - 1.0, t = fma(a4, xj, 1.0), t2 = t * t;
+            d = lo * (t2 * t2); wgt = (4.0 * a4 * lo * wj) * (t2 * t);
+        }
+        else { d = lo * u.pj; wgt = d * (plan.lnr * wj); }
+    }
+    else if (map == 1) d = panel_node_sinh(plan.eps, plan.L, k, lo, up, lo_cl, up_cl, xj, wj, &wgt);
+    else { const double wd = up - lo; d = fma(wd, xj, lo); wgt = wd * wj; }
+    return neg ? 1 : 2;
+}
+
+/* integrand evaluations the units of one ridge integral ask for, per node of the panel rule */
+COFFE_HD unsigned int ridge_units_count(const PanelPlan &plan, const double center, const double hi)
+{
+    RidgeUnits u;
+    ridge_units_init(u, plan, center, hi, 0.5, 1.0, 1.0);
+    unsigned int n = 0;
+    for (int iu = 0; iu < u.n_units; ++iu) {
+        double d, w;
+        const int sides = ridge_unit_node(u, iu, d, w);
+        n += (sides & 1) + ((sides >> 1) & 1);
+    }
+    return n;
+}
+
 /* runtime quadrature configuration (mirrors coffe_b200_quadrature, include/coffe_b200.h) */
 struct QuadConfig {
     int n_mu_ni;            /* Gauss-Legendre nodes in mu for the local x local piece */
@@ -200,6 +331,7 @@ struct QuadConfig {
     /* growth factor per geometric panel under the sinh map (panel_plan); <= 1: the doubling panels with Gauss-Legendre nodes in d */
     double geo_growth, geo_growth_di;
     int tail_log, tail_log_di;     /* tail panels with Gauss-Legendre nodes in log(d) instead of d */
+    double mu_tail;         /* growth factor of the r_perp panels of the mu rules beyond mu_du */
     double mu_growth, mu_growth_di; /* growth factor of the log-mapped geometric r_perp panels of the mu rules; <= 1: doubling panels in phi */
     int mu_switch_di;       /* the integrated x integrated mu rule keeps the break at |mu| = 0.999 (only the local x integrated integrand switches there) */
     int n_ren;              /* nodes of the inner rule of renormalization(l1, l2) in the integrated x integrated piece (even) */

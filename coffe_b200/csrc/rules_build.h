@@ -23,9 +23,9 @@ inline QuadConfig default_quadrature()
     q.n_z = 8;
     q.panel_w = 64.0; q.panel_du = 128.0; q.eps_min = 1e-3; q.tail_ratio = 1.5;
     q.n_mu_panel_di = 5; q.panel_w_di = 64.0; q.panel_du_di = 192.0; q.mu_panel_w_di = 64.0; q.tail_ratio_di = 6.0; q.geo_shift_di = 1;
-    q.geo_growth = 1.0; q.geo_growth_di = 8.0;
+    q.geo_growth = 4.0; q.geo_growth_di = 8.0;
     q.n_ren = 24;
-    q.mu_growth = 3.0; q.mu_growth_di = 1.0; q.mu_switch_di = 1;
+    q.mu_growth = 3.0; q.mu_growth_di = 1.0; q.mu_switch_di = 1; q.mu_tail = 1.5;
     q.tail_log = 0; q.tail_log_di = 1;
     return q;
 }
@@ -45,6 +45,7 @@ inline QuadConfig total_target_quadrature()
     q.n_outer_min = 25; q.n_outer_step = 15.0;
     q.panel_w_di = 96.0;
     q.mu_growth = 8.0; q.mu_switch_di = 0;
+    q.tail_log = 1; q.tail_ratio = 3.0;
     q.mu_panel_w = 64.0; q.n_mu_panel = 7; q.n_panel_si = 6;
     q.mu_rho0 = 8.0;
     return q;
@@ -60,6 +61,7 @@ inline QuadConfig merge_quadrature(const QuadConfig &base, const coffe_b200_quad
     if (u.mu_uniform_extent > 0) q.mu_du = u.mu_uniform_extent;
     if (u.n_outer > 0) q.n_outer = u.n_outer;
     if (u.n_outer < 0) q.n_outer = 0;
+    if (u.mu_tail_ratio > 1.0) q.mu_tail = u.mu_tail_ratio;
     if (u.n_outer_min > 0) q.n_outer_min = u.n_outer_min;
     if (u.n_outer_step > 0) q.n_outer_step = u.n_outer_step;
     if (u.n_panel_si > 0) q.n_panel_si = u.n_panel_si;
@@ -137,7 +139,7 @@ inline bool quadrature_valid(const QuadConfig &q, const int panel_capacity)
            q.panel_w > 0 && q.panel_du >= 0 && q.eps_min > 0 && q.tail_ratio > 1.0 &&
            q.mu_rho0 > 0 && q.mu_panel_w > 0 && q.mu_du >= 0 &&
            q.n_mu_panel_di >= 2 && q.n_mu_panel_di <= kMaxRule && q.panel_w_di > 0 && q.panel_du_di >= 0 && q.mu_panel_w_di > 0 && q.tail_ratio_di > 1.0 &&
-           q.geo_shift_di >= 1 && q.geo_shift_di <= 3 && q.geo_growth >= 0 && q.geo_growth_di >= 0 && q.n_ren >= 2 && q.n_ren <= 2 * kMaxRule;
+           q.geo_shift_di >= 1 && q.geo_shift_di <= 3 && q.geo_growth >= 0 && q.geo_growth_di >= 0 && q.mu_tail > 1.0 && q.n_ren >= 2 && q.n_ren <= 2 * kMaxRule;
 }
 
 /* bank of Gauss-Legendre rules on [0,1], rule n at offset n(n-1)/2 */
@@ -192,7 +194,7 @@ inline void build_mu_rule(const QuadConfig &q, const double sep, std::vector<dou
     }
     while (b < mu_panel_w && b < sep) { bp.push_back(b); b *= 2.0; }
     while (b < q.mu_du && b < sep) { bp.push_back(b); b += mu_panel_w; }
-    while (b < sep) { bp.push_back(b); b *= q.tail_ratio; }
+    while (b < sep) { bp.push_back(b); b *= q.mu_tail; }
     bp.push_back(sep);
     if (switch_break) bp.push_back(sep * std::sqrt(1.0 - kMuSwitch * kMuSwitch));
     std::sort(bp.begin(), bp.end());

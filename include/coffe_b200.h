@@ -122,8 +122,8 @@ typedef struct coffe_b200_quadrature {
     double tail_ratio_di;
     int geometric_shift_di;      /* log2 of the growth factor of its geometric panels: 1 = doubling, 2 = x4 */
     /* What the 1e-5 gate is measured against, which picks the library defaults the zeros above stand for:
-       0 = automatic: COFFE_B200_TARGET_TOTAL when density or RSD is among the contributions and the call returns totals
-           (multipoles / corrfunc / average multipoles / their group and sharded forms), COFFE_B200_TARGET_PIECE otherwise and
+       0 = automatic: COFFE_B200_TARGET_TOTAL when density or RSD is among the contributions and the call returns mu-integrated totals
+           (multipoles / average multipoles / their group and sharded forms; the 2-point function at a fixed mu always gets the piece rules), COFFE_B200_TARGET_PIECE otherwise and
            always for the *_pieces entry points (a caller of coffe_integrate(flag_integral) gets each piece to 1e-5 of itself);
        1 = COFFE_B200_TARGET_PIECE: every piece (local x local, local x integrated, integrated x integrated) within 1e-5 of its own
            l = 0..4 scale -- what a lensing-only or cross-only configuration needs;
@@ -151,6 +151,7 @@ typedef struct coffe_b200_quadrature {
     /* outer nodes by separation (n_outer = -1 / default): max(n_outer_min, 10 + sep / n_outer_step [Mpc]) */
     int n_outer_min;
     double n_outer_step;
+    double mu_tail_ratio;        /* growth factor of the r_perp panels of the mu rules beyond mu_uniform_extent (default 1.5) */
 } coffe_b200_quadrature;
 enum { COFFE_B200_TARGET_AUTO = 0, COFFE_B200_TARGET_PIECE = 1, COFFE_B200_TARGET_TOTAL = 2 };
 

@@ -45,7 +45,7 @@ static void set_rules(HostSim *s)
     q.panel_w_mpc = s->qc.panel_w; q.panel_du = s->qc.panel_du; q.eps_min = s->qc.eps_min; q.tail_ratio = s->qc.tail_ratio;
     q.panel_w_di = s->qc.panel_w_di; q.panel_du_di = s->qc.panel_du_di;
     q.panel_x = q.panel_w = q.panel_p = nullptr;
-    q.panel_x_si = q.panel_w_si = nullptr;
+    q.panel_x_si = q.panel_w_si = q.panel_p_si = nullptr;
     s->rpow_di = build_rpow(s->qc.tail_ratio_di);
     q.rpow_di = s->rpow_di.data(); q.tail_ratio_di = s->qc.tail_ratio_di; q.geo_shift_di = s->qc.geo_shift_di;
     q.n_ren = s->qc.n_ren;
@@ -194,8 +194,18 @@ static void item_pieces(void *h, double z, double sep, double mu, int mask, doub
     if (opt_has_si(o) && (mask & 2)) {
         const SIHalf ha = si_half_setup(o, g, e1, e2, true), hb = si_half_setup(o, g, e2, e1, false);
         double scratch[2 * kMaxPanels];
-        if (s->variant) { const CompactAccess ca = s->compact(); out[1] = si_half_partial(ca, s->t.los, s->q, g, ha, s->t.los.v, 0, 1, scratch) + si_half_partial(ca, s->t.los, s->q, g, hb, s->t.los.v, 0, 1, scratch); }
-        else { const ExactAccess ea{&s->t}; out[1] = si_half_partial(ea, s->t.los, s->q, g, ha, s->t.los.v, 0, 1, scratch) + si_half_partial(ea, s->t.los, s->q, g, hb, s->t.los.v, 0, 1, scratch); }
+        /* the kernel's lane decomposition: the n_panel_si lanes of one group in turn; the midpoint mode keeps the plain ridge rule */
+        double acc = 0.0;
+        if (o.midpoint) {
+            const ExactAccess ea{&s->t};
+            acc = si_half_partial<ExactAccess, true>(ea, s->t.los, s->q, g, ha, s->t.los.v, 0, 1, scratch) + si_half_partial<ExactAccess, true>(ea, s->t.los, s->q, g, hb, s->t.los.v, 0, 1, scratch);
+        }
+        else
+            for (int j = 0; j < s->q.n_panel_si; ++j) {
+                if (s->variant) { const CompactAccess ca = s->compact(); acc += si_half_group(ca, s->t.ren2d, s->t.los, s->q, g, ha, s->t.los.v, j) + si_half_group(ca, s->t.ren2d, s->t.los, s->q, g, hb, s->t.los.v, j); }
+                else { const ExactAccess ea{&s->t}; acc += si_half_group(ea, s->t.ren2d, s->t.los, s->q, g, ha, s->t.los.v, j) + si_half_group(ea, s->t.ren2d, s->t.los, s->q, g, hb, s->t.los.v, j); }
+            }
+        out[1] = acc;
     }
     if (opt_has_integrated(o) && (mask & 4)) {
         const DIConst k = di_setup(o, e1, e2);
@@ -262,7 +272,7 @@ void hs_eval_counts(void *h, double z, double sep, double *out)
         const Geometry g = geometry(chi_mean, sep, mu[im]);
         const EndVals e1 = end_eval(s->o, s->t, g.chi1, 1), e2 = end_eval(s->o, s->t, g.chi2, 2);
         const SIHalf ha = si_half_setup(s->o, g, e1, e2, true), hb = si_half_setup(s->o, g, e2, e1, false);
-        out[0] += si_eval_count(s->q, g, ha) + si_eval_count(s->q, g, hb);
+        out[0] += si_group_eval_count(s->q, g, ha) + si_group_eval_count(s->q, g, hb);
     }
     build_mu_rule(s->qc, sep, mu, w, 2, s->di_half);
     for (size_t im = 0; im < mu.size(); ++im) {

@@ -498,7 +498,7 @@ def test_quadrature_self_convergence_on_a_wide_grid(engine):
     s = [15.0, 120.0, 448.0]
     base = engine.multipoles(z, s, [0, 2, 4])
     engine.set_quadrature(n_mu_panel=12, n_mu_panel_di=10, mu_panel_width=16.0, n_outer=96, n_panel_si=12, n_panel_di=12, panel_width=8.0,
-                          panel_uniform_extent=640.0, panel_width_di=16.0, panel_uniform_extent_di=640.0, mu_panel_width_di=16.0, tail_ratio=1.3, tail_ratio_di=1.3, geometric_shift_di=1, geometric_growth=1.0, geometric_growth_di=1.0, n_renorm=64, tail_map=1, tail_map_di=1, mu_geometric_growth=1.0, mu_geometric_growth_di=1.0, mu_switch_break_di=1, n_mu_ni=64)
+                          panel_uniform_extent=640.0, panel_width_di=16.0, panel_uniform_extent_di=640.0, mu_panel_width_di=16.0, tail_ratio=1.3, tail_ratio_di=1.3, geometric_shift_di=1, geometric_growth=1.0, geometric_growth_di=1.0, n_renorm=64, tail_map=1, tail_map_di=1, mu_geometric_growth=1.0, mu_geometric_growth_di=1.0, mu_switch_break_di=1, mu_tail_ratio=1.3, n_mu_ni=64)
     fine = engine.multipoles(z, s, [0, 2, 4])
     engine.set_quadrature()
     err = np.abs(base - fine) / np.max(np.abs(fine), axis=1, keepdims=True)
@@ -507,7 +507,7 @@ def test_quadrature_self_convergence_on_a_wide_grid(engine):
     engine.set_quadrature(accuracy_target=1)
     pb = engine.multipoles_pieces(z, s, [0, 2, 4])
     engine.set_quadrature(accuracy_target=1, n_mu_panel=12, n_mu_panel_di=10, mu_panel_width=16.0, n_outer=96, n_panel_si=12, n_panel_di=12, panel_width=8.0,
-                          panel_uniform_extent=640.0, panel_width_di=16.0, panel_uniform_extent_di=640.0, mu_panel_width_di=16.0, tail_ratio=1.3, tail_ratio_di=1.3, geometric_shift_di=1, geometric_growth=1.0, geometric_growth_di=1.0, n_renorm=64, tail_map=1, tail_map_di=1, mu_geometric_growth=1.0, mu_geometric_growth_di=1.0, mu_switch_break_di=1, n_mu_ni=64)
+                          panel_uniform_extent=640.0, panel_width_di=16.0, panel_uniform_extent_di=640.0, mu_panel_width_di=16.0, tail_ratio=1.3, tail_ratio_di=1.3, geometric_shift_di=1, geometric_growth=1.0, geometric_growth_di=1.0, n_renorm=64, tail_map=1, tail_map_di=1, mu_geometric_growth=1.0, mu_geometric_growth_di=1.0, mu_switch_break_di=1, mu_tail_ratio=1.3, n_mu_ni=64)
     pf = engine.multipoles_pieces(z, s, [0, 2, 4])
     engine.set_quadrature()
     perr = np.abs(pb - pf) / np.max(np.abs(pf), axis=2, keepdims=True)
@@ -636,7 +636,7 @@ def test_covariance_structure(engine):
 # ---- dense parity on the benchmarked grids (task 1) -------------------------------------------
 FINE_RULES = dict(n_mu_panel=12, n_mu_panel_di=10, mu_panel_width=16.0, n_outer=96, n_panel_si=12, n_panel_di=12, panel_width=8.0,
                   panel_uniform_extent=640.0, panel_width_di=16.0, panel_uniform_extent_di=640.0, mu_panel_width_di=16.0,
-                  tail_ratio=1.3, tail_ratio_di=1.3, geometric_shift_di=1, geometric_growth=1.0, geometric_growth_di=1.0, n_renorm=64, tail_map=1, tail_map_di=1, mu_geometric_growth=1.0, mu_geometric_growth_di=1.0, mu_switch_break_di=1, n_mu_ni=64)
+                  tail_ratio=1.3, tail_ratio_di=1.3, geometric_shift_di=1, geometric_growth=1.0, geometric_growth_di=1.0, n_renorm=64, tail_map=1, tail_map_di=1, mu_geometric_growth=1.0, mu_geometric_growth_di=1.0, mu_switch_break_di=1, mu_tail_ratio=1.3, n_mu_ni=64)
 
 
 def cfg5_grid():

@@ -1,3 +1,1 @@
-python tools/quad_sweep.py 2>&1 | tail -1
-python tools/piece_sweep.py 2>&1 | tail -4
-python -m pytest tests -m gpu -q -x -k "parity" 2>&1 | tail -3
+python -m pytest tests -m gpu -q -x -k "cfg2 or corrfunc or dropin or coffe_class" 2>&1 | tail -3

@@ -17,7 +17,7 @@ H = 0.67
 FINE = dict(n_mu_panel=12, n_mu_panel_di=10, mu_panel_width=16.0, n_outer=96, n_panel_si=12, n_panel_di=12, panel_width=8.0,
             panel_uniform_extent=640.0, panel_width_di=16.0, panel_uniform_extent_di=640.0, mu_panel_width_di=16.0,
             tail_ratio=1.3, tail_ratio_di=1.3, geometric_shift_di=1, geometric_growth=1.0, geometric_growth_di=1.0, n_renorm=64,
-            tail_map=1, tail_map_di=1, mu_geometric_growth=1.0, mu_geometric_growth_di=1.0, mu_switch_break_di=1, n_mu_ni=64)
+            tail_map=1, tail_map_di=1, mu_geometric_growth=1.0, mu_geometric_growth_di=1.0, mu_switch_break_di=1, mu_tail_ratio=1.3, n_mu_ni=64)
 z, sep, ls = np.array([0.5, 1.0, 1.5, 2.0]), np.geomspace(10.0, 300.0, 24) / H, [0, 2, 4]
 eng = coffe_b200.Engine(0)
 eng.upload_tables(load_default_tableset())

@@ -20,7 +20,7 @@ import os
 ALL = os.environ["COFFE_SWEEP_CONTRIB"].split(",") if os.environ.get("COFFE_SWEEP_CONTRIB") else list(coffe_b200.capi.CONTRIBUTIONS)
 FINE = dict(n_mu_panel=12, n_mu_panel_di=10, mu_panel_width=16.0, n_outer=96, n_panel_si=12, n_panel_di=12, panel_width=8.0,
             panel_uniform_extent=640.0, panel_width_di=16.0, panel_uniform_extent_di=640.0, mu_panel_width_di=16.0,
-            tail_ratio=1.3, tail_ratio_di=1.3, geometric_shift_di=1, geometric_growth=1.0, geometric_growth_di=1.0, n_renorm=64, tail_map=1, tail_map_di=1, mu_geometric_growth=1.0, mu_geometric_growth_di=1.0, mu_switch_break_di=1, n_mu_ni=64)
+            tail_ratio=1.3, tail_ratio_di=1.3, geometric_shift_di=1, geometric_growth=1.0, geometric_growth_di=1.0, n_renorm=64, tail_map=1, tail_map_di=1, mu_geometric_growth=1.0, mu_geometric_growth_di=1.0, mu_switch_break_di=1, mu_tail_ratio=1.3, n_mu_ni=64)
 z, sep, ls = np.linspace(0.5, 2.0, 32), np.linspace(10.0, 300.0, 1000) / H, [0, 2, 4]
 idx = np.arange(0, 1000, 8)
 zi = np.arange(0, 32, 2)                      # 16 z x 125 r = 2000 points
