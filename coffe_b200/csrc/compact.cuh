@@ -179,7 +179,7 @@ COFFE_HD void compact_ifam9(const CompactView &c, const double r, double out[N_I
 {
     const int hi = hi_word(r);
     int reg = (hi >> 18) - c.h.region0;
-    if (reg < 0) {
+    if (COFFE_UNLIKELY(reg < 0)) {
         compact_ifam_all(c, r, out);
         out[N_ITAB] = want_i40 ? compact_i40(c, r) : 0.0;
         return;

@@ -3,6 +3,9 @@
 // compile under plain g++ for the CPU-only debugging harness in tests/hostsim (test infrastructure:
 // the product library never executes these on the host).
 #pragma once
+/* branch hints: the persistent kernels stall on instruction fetch, rare paths should leave the main line */
+#define COFFE_LIKELY(x) __builtin_expect(!!(x), 1)
+#define COFFE_UNLIKELY(x) __builtin_expect(!!(x), 0)
 #if defined(__CUDACC__)
 #define COFFE_HD __host__ __device__ __forceinline__
 #define COFFE_D __device__ __forceinline__

@@ -81,7 +81,7 @@ COFFE_HD double panel_break(const PanelPlan &p, const int k)
 {
     if (k <= 0) return 0.0;
     if (k == p.J) return p.BJ;
-    if (k < p.J) return panel_break_geometric(p.eps, p.L, p.shift, k);
+    if (COFFE_UNLIKELY(k < p.J)) return panel_break_geometric(p.eps, p.L, p.shift, k);
     if (k <= p.J + p.M) return p.BJ + (k - p.J) * p.W;
     const int n = k - p.J - p.M;
     return p.BJM * p.rpow[n < kMaxTail ? n : kMaxTail - 1];
@@ -236,7 +236,7 @@ COFFE_HD int ridge_unit_node(RidgeUnits &u, const int iu, double &d, double &wgt
     if (iu >= u.n_single) {
         const int k = iu - u.n_single;
         if (k < plan.J) {
-            if (plan.L > 0.0) {
+            if (COFFE_LIKELY(plan.L > 0.0)) {
                 d = plan.eps * fma(u.S, u.cj, u.C * u.sj);
                 wgt = (plan.eps * plan.L * wj) * fma(u.C, u.cj, u.S * u.sj);
                 const double Sn = fma(u.S, u.C1, u.C * u.S1);
@@ -252,7 +252,7 @@ COFFE_HD int ridge_unit_node(RidgeUnits &u, const int iu, double &d, double &wgt
         else {
             const int n = k - plan.J - plan.M;
             const double lo = plan.BJM * plan.rpow[n < kMaxTail ? n : kMaxTail - 1];
-            if (plan.lnr > 0.0) { d = lo * u.pj; wgt = d * (plan.lnr * wj); }
+            if (COFFE_LIKELY(plan.lnr > 0.0)) { d = lo * u.pj; wgt = d * (plan.lnr * wj); }
             else {
                 const double wd = plan.BJM * plan.rpow[n + 1 < kMaxTail ? n + 1 : kMaxTail - 1] - lo;
                 d = fma(wd, xj, lo); wgt = wd * wj;
@@ -289,7 +289,7 @@ COFFE_HD int ridge_unit_node(RidgeUnits &u, const int iu, double &d, double &wgt
         }
         else { d = lo * u.pj; wgt = d * (plan.lnr * wj); }
     }
-    else if (map == 1) d = panel_node_sinh(plan.eps, plan.L, k, lo, up, lo_cl, up_cl, xj, wj, &wgt);
+    else if (COFFE_UNLIKELY(map == 1)) d = panel_node_sinh(plan.eps, plan.L, k, lo, up, lo_cl, up_cl, xj, wj, &wgt);
     else { const double wd = up - lo; d = fma(wd, xj, lo); wgt = wd * wj; }
     return neg ? 1 : 2;
 }
