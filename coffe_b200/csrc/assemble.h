@@ -43,7 +43,7 @@ struct Layout {
     int extra_n[kMaxExtra] = {0}, extra_l[kMaxExtra] = {0}, extra_half[kMaxExtra] = {0}, n_extra = 0;
     HintOff i40_hint;
     size_t ifam_x = 0, ifam_k = 0; int ifam_n = 0, ifam_n_small = 0; double ifam_r0 = 1, ifam_inv_dln = 0;
-    size_t ren2d_x = 0, ren2d_node = 0, ren2d_nodeT = 0; int ren2d_n = 0; double ren2d_x0 = 0, ren2d_inv_dx = 0, ren2d_dx = 0;
+    size_t ren2d_x = 0, ren2d_node = 0; int ren2d_n = 0; double ren2d_x0 = 0, ren2d_inv_dx = 0, ren2d_dx = 0;
     size_t los = 0; int los_n = 0; double los_h = 0;
     int has_divergent = 0, has_ifam = 0, interp_kind = 5;
     size_t mid_z = 0, mid_node[N_ITAB] = {0}; int mid_nz = 0, mid_nr = 0; double mid_z0 = 0, mid_inv_dz = 0;     /* 2-D I^n_l(z, r) tables */
@@ -86,7 +86,6 @@ inline Tables make_view(const Layout &L, const double *base)
     t.ren0 = view_of(L.ren0, base);
     t.ren2d.x = base + L.ren2d_x;
     t.ren2d.node = reinterpret_cast<const double4 *>(base + L.ren2d_node);
-    t.ren2d.nodeT = reinterpret_cast<const double4 *>(base + L.ren2d_nodeT);
     t.ren2d.n = L.ren2d_n; t.ren2d.x0 = L.ren2d_x0; t.ren2d.inv_dx = L.ren2d_inv_dx; t.ren2d.dx = L.ren2d_dx;
     t.los.v = reinterpret_cast<const double2 *>(base + L.los);
     t.los.n = L.los_n; t.los.h = L.los_h; t.los.inv_h = L.los_h > 0 ? 1.0 / L.los_h : 0.0;
@@ -359,12 +358,6 @@ inline bool assemble_serial(const coffe_b200_tables &T, Arena &A, Layout &L, std
         const std::vector<build::Coef> node = build::bicubic_nodes(T.renorm_chi, T.renorm_chi, T.renorm_z, nr, nr);
         L.ren2d_x = A.put(T.renorm_chi, nr);
         L.ren2d_node = A.put(node);
-        {
-            std::vector<build::Coef> nodeT(node.size());
-            for (int j = 0; j < nr; ++j)
-                for (int i = 0; i < nr; ++i) nodeT[(size_t)i * nr + j] = node[(size_t)j * nr + i];
-            L.ren2d_nodeT = A.put(nodeT);
-        }
         L.ren2d_n = nr;
         L.ren2d_x0 = T.renorm_chi[0];
         L.ren2d_inv_dx = (nr - 1) / (T.renorm_chi[nr - 1] - T.renorm_chi[0]);

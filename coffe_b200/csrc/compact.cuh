@@ -229,14 +229,10 @@ struct ExactAccess {
 struct CompactAccess {
     const Tables *t;           /* renormalisation grid and zero-separation spline stay in global memory (L2) */
     CompactView c;
-    /* optional: renormalisation(., y0) collapsed onto its first argument by ren_col_fill (the local x integrated kernel sets it per
-       half: y0 = chi of the source end); ren2d(a, b) then ignores b */
-    const double2 *col = nullptr;
-    int n_col = 0;
     COFFE_HD void ifam_all(const double r, double out[N_ITAB]) const { compact_ifam_all(c, r, out); }
     COFFE_HD void ifam9(const double r, double out[N_ITAB9], const bool want_i40) const { compact_ifam9(c, r, out, want_i40); }
     COFFE_HD double i40(const double r) const { return compact_i40(c, r); }
-    COFFE_HD double ren2d(const double a, const double b) const { return col ? ren_row_eval(t->ren2d, col, n_col, a) : renorm2d_eval(t->ren2d, a, b); }
+    COFFE_HD double ren2d(const double a, const double b) const { return renorm2d_eval(t->ren2d, a, b); }
     COFFE_HD double ren0(const double l) const { return spline_eval(t->ren0, l); }
     /* the 2-D tables are never resampled into shared memory: the host routes midpoint runs to the exact-table kernel */
     COFFE_HD void ifam_mid(const double r, const double z, double out[N_ITAB]) const { mid2d_eval_all(t->mid, t->ifam, z, r, out); }

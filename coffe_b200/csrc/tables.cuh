@@ -226,7 +226,6 @@ COFFE_HD void ifam_eval_all(const IntegralFamilyView &t, const double r, double 
 struct Renorm2DView {
     const double *x;        /* n knots (same on both axes) */
     const double4 *node;    /* n*n nodes {z, zx, zy, zxy}; index j*n + i with i <-> first argument */
-    const double4 *nodeT;   /* the same nodes transposed, index i*n + j: a sweep over the second argument is contiguous */
     int n;
     double x0, inv_dx, dx;
 };
@@ -252,94 +251,6 @@ COFFE_HD double renorm2d_eval(const Renorm2DView &t, const double x, const doubl
          + h01t * (h00u * n10.x + h01u * n11.x + h10u * n10.z + h11u * n11.z)
          + h10t * (h00u * n00.y + h01u * n01.y + h10u * n00.w + h11u * n01.w)
          + h11t * (h00u * n10.y + h01u * n11.y + h10u * n10.w + h11u * n11.w);
-}
-
-/* renormalisation(x, .) for a fixed first argument, collapsed onto the knots of the second: row[j] = {value,
-   dy d/dy} at y_j.  ren_row_eval(row, y) is then the same bicubic patch as renorm2d_eval(x, y) with the sums
-   reassociated: the integrated x integrated kernel fills one row per outer line-of-sight node (cooperatively,
-   `nlanes` lanes) and every inner node costs one 1-D Hermite lookup instead of a 16-term patch. */
-/* knots per lane in flight in ren_row_fill (3 measured slower: the extra registers spill) */
-static const int kRowInFlight = 2;
-COFFE_HD void ren_row_fill(const Renorm2DView &t, const double x, const int n_row, double2 *row, const int lane, const int nlanes)
-{
-    const double sx = (x - t.x0) * t.inv_dx;
-    int xi = (int)sx;
-    if (xi < 0) xi = 0;
-    if (xi > t.n - 2) xi = t.n - 2;
-    const double tt = sx - xi, t2 = tt * tt, t3 = t2 * tt;
-    const double h00 = 2 * t3 - 3 * t2 + 1, h10 = (t3 - 2 * t2 + tt) * t.dx, h01 = -2 * t3 + 3 * t2, h11 = (t3 - t2) * t.dx;
-    const double4 *a = t.nodeT + (size_t)xi * t.n, *b = a + t.n;
-    /* kRowInFlight knots per lane in flight: the loads come from L2 and nothing else can hide their latency here */
-    for (int j0 = lane; j0 < n_row; j0 += kRowInFlight * nlanes) {
-        double4 p[kRowInFlight], q[kRowInFlight];
-#pragma unroll
-        for (int u = 0; u < kRowInFlight; ++u) {
-            const int j = j0 + u * nlanes;
-            if (j < n_row) { p[u] = a[j]; q[u] = b[j]; }
-        }
-#pragma unroll
-        for (int u = 0; u < kRowInFlight; ++u) {
-            const int j = j0 + u * nlanes;
-            if (j < n_row) {
-                double2 o;
-                o.x = h00 * p[u].x + h01 * q[u].x + h10 * p[u].y + h11 * q[u].y;
-                o.y = (h00 * p[u].z + h01 * q[u].z + h10 * p[u].w + h11 * q[u].w) * t.dx;
-                row[j] = o;
-            }
-        }
-    }
-}
-
-/* rows needed to cover second arguments up to y_max */
-/* the same collapse along the other axis: renormalisation(., y) for a fixed SECOND argument, col[i] = {value, dx d/dx} at x_i (the local x
-   integrated piece evaluates renormalisation(lambda, chi_source) with the source end fixed per half).  Reads two contiguous rows
-   of the node table; ren_row_eval(col, x) is then the bicubic patch with the sums reassociated. */
-COFFE_HD void ren_col_fill(const Renorm2DView &t, const double y, const int n_col, double2 *col, const int lane, const int nlanes)
-{
-    const double sy = (y - t.x0) * t.inv_dx;
-    int yi = (int)sy;
-    if (yi < 0) yi = 0;
-    if (yi > t.n - 2) yi = t.n - 2;
-    const double u = sy - yi, u2 = u * u, u3 = u2 * u;
-    const double h00 = 2 * u3 - 3 * u2 + 1, h10 = (u3 - 2 * u2 + u) * t.dx, h01 = -2 * u3 + 3 * u2, h11 = (u3 - u2) * t.dx;
-    const double4 *a = t.node + (size_t)yi * t.n, *b = a + t.n;
-    for (int i0 = lane; i0 < n_col; i0 += kRowInFlight * nlanes) {
-        double4 p[kRowInFlight], q[kRowInFlight];
-#pragma unroll
-        for (int v = 0; v < kRowInFlight; ++v) {
-            const int i = i0 + v * nlanes;
-            if (i < n_col) { p[v] = a[i]; q[v] = b[i]; }
-        }
-#pragma unroll
-        for (int v = 0; v < kRowInFlight; ++v) {
-            const int i = i0 + v * nlanes;
-            if (i < n_col) {
-                double2 o;
-                o.x = h00 * p[v].x + h01 * q[v].x + h10 * p[v].z + h11 * q[v].z;
-                o.y = (h00 * p[v].y + h01 * q[v].y + h10 * p[v].w + h11 * q[v].w) * t.dx;
-                col[i] = o;
-            }
-        }
-    }
-}
-
-COFFE_HD int ren_row_count(const Renorm2DView &t, const double y_max)
-{
-    int n = (int)((y_max - t.x0) * t.inv_dx) + 3;
-    if (n > t.n) n = t.n;
-    if (n < 2) n = 2;
-    return n;
-}
-
-COFFE_HD double ren_row_eval(const Renorm2DView &t, const double2 *row, const int n_row, const double y)
-{
-    const double sy = (y - t.x0) * t.inv_dx;
-    int yi = (int)sy;
-    if (yi < 0) yi = 0;
-    if (yi > n_row - 2) yi = n_row - 2;
-    const HermiteBasis b = hermite_basis(sy - yi);
-    const double2 p = row[yi], q = row[yi + 1];
-    return hermite_eval(b, p.x, p.y, q.x, q.y);
 }
 
 /* ---- line-of-sight functions resampled on a uniform lambda grid --------------------------------

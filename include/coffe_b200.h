@@ -128,7 +128,7 @@ typedef struct coffe_b200_quadrature {
        1 = COFFE_B200_TARGET_PIECE: every piece (local x local, local x integrated, integrated x integrated) within 1e-5 of its own
            l = 0..4 scale -- what a lensing-only or cross-only configuration needs;
        2 = COFFE_B200_TARGET_TOTAL: the returned multipole within 1e-5 of the l = 0..4 scale of the point; the integrated pieces are
-           then at most a few per cent of the total and carry coarser rules (0.7 of the evaluations). */
+           then at most a few per cent of the total and carry coarser rules (a third of the evaluations). */
     int accuracy_target;
     /* Geometric panels of the line-of-sight plans under the sinh map d = eps sinh(t) (eps = impact parameter of the two lines of
        sight, d = distance from their closest approach): the region |d| < panel_width is cut into equal panels in t with a growth
