@@ -282,8 +282,15 @@ __global__ void __launch_bounds__(kSIThreads, 1) si_items_smem_kernel(
         return records + (size_t)(hh >> 1) * kRecWords + (i < kGeoWords ? i : half_off + (i - kGeoWords));
     };
     double pre[kPre];
+    /* batch q (drawn as first = q ppi): the halves of the SAME source end of ppi consecutive items -- neighbours in mu of one point,
+       whose integrals have nearly the same number of panels, so that the groups of a warp finish together (batches of consecutive
+       halves, which mix the two ends of an item, left 22 of 32 lanes busy) */
+    auto half_of = [&](const unsigned int batch) {
+        const unsigned int q = batch / (unsigned int)ppi;
+        return 2u * ((q >> 1) * (unsigned int)ppi + (unsigned int)grp) + (q & 1u);
+    };
     auto prefetch = [&](const unsigned int batch) {
-        const unsigned int hh = batch + grp;
+        const unsigned int hh = half_of(batch);
         if (lane_on && hh < n_halves)
 #pragma unroll
             for (int w = 0; w < kPre; ++w)
@@ -291,8 +298,10 @@ __global__ void __launch_bounds__(kSIThreads, 1) si_items_smem_kernel(
     };
     unsigned int first = draw(), next = draw();
     prefetch(first);
-    while (first < n_halves) {
-        const unsigned int hh = first + grp;
+    /* batches cover the items in pairs of (ppi items, end 0), (ppi items, end 1): the last pair may reach beyond the list */
+    const unsigned int n_batched = 2u * (unsigned int)ppi * (((unsigned int)n_items + ppi - 1) / ppi);
+    while (first < n_batched) {
+        const unsigned int hh = half_of(first);
         const bool valid = lane_on && hh < n_halves;
         SIGroupSlot &slot = slots[lane_on ? grp : 0];
         __syncwarp();                   /* the previous batch's readers are done */
