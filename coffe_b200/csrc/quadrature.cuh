@@ -57,7 +57,7 @@ COFFE_HD PanelPlan panel_plan(double eps, const double eps_min, const double W, 
         p.L = T / J;
         b = W;
     }
-    else if (eps < W) {          /* otherwise the cusp is wider than a uniform panel: uniform panels from d = 0 */
+    else if (COFFE_UNLIKELY(eps < W)) {          /* doubling panels (legacy plan); otherwise the cusp is wider than a uniform panel: uniform panels from d = 0 */
         /* J - 1 = smallest m >= 1 with eps 2^(shift m) >= W, from the exponents (exact: the same J and B_J as repeated doubling) */
         const int e0 = ilogb(W) - ilogb(eps);
         const int n = ldexp(eps, e0) >= W ? e0 : e0 + 1;         /* smallest n with eps 2^n >= W; n >= 1 here */
@@ -92,15 +92,16 @@ COFFE_HD int panel_count(const PanelPlan &p, const double b)
 {
     if (b <= 0.0) return 0;
     int k = 1;
-    if (b > p.BJM) {
+    if (COFFE_LIKELY(b > p.BJM)) {
         k = p.J + p.M;
         int n = 1;
         while (n < kMaxTail - 1 && p.BJM * p.rpow[n] < b) ++n;      /* smallest n with B_(k+n) >= b */
         return k + n;
     }
     if (b > p.BJ || p.J == 0) return p.J + (int)ceil((b - p.BJ) / p.W);
-    if (p.L > 0.0) {
-        k = (int)ceil(asinh(b / p.eps) / p.L);
+    if (COFFE_LIKELY(p.L > 0.0)) {
+        const double xb = b / p.eps;
+        k = (int)ceil(log(xb + sqrt(fma(xb, xb, 1.0))) / p.L);         /* asinh */
         return k < 1 ? 1 : k > p.J ? p.J : k;
     }
     double e = p.eps;
@@ -108,9 +109,8 @@ COFFE_HD int panel_count(const PanelPlan &p, const double b)
     return k;
 }
 
-/* the same count from the breaks themselves: smallest k >= 1 with B_k >= b.  This is the definition the integrated x integrated
-   kernel uses (its warp holds B_0..B_31 in its lanes and counts with one ballot, di_fast.cuh); it differs from panel_count only
-   when b sits within rounding of a uniform break, where the extra panel is a few ulp wide. */
+/* the same count from the breaks themselves: smallest k >= 1 with B_k >= b (CPU tests of the closed forms); it differs from
+   panel_count only when b sits within rounding of a break, where the extra panel is a few ulp wide. */
 COFFE_HD int panel_count_by_break(const PanelPlan &p, const double b)
 {
     if (b <= 0.0) return 0;
