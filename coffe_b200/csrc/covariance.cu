@@ -132,15 +132,36 @@ __global__ void cov_bessel_kernel(const double *__restrict__ k, const int n_node
     V[idx] = v;
 }
 
-/* partial Gram products over a k range: P[split][p][row][col] += sum_k W_p(k) V[k][row] V[k][col] */
+/* partial Gram products over a k range: P[split][p][row][col] += sum_k W_p(k) V[k][row] V[k][col].
+   The product is symmetric: every pair of tiles is computed in ONE orientation, (ta, tb) with ta <= tb -- rows from tile ta scaled
+   by the weight, columns from tile tb -- and written to both places.  sym = 1 (a call that owns every row): one block per pair
+   ta <= tb, 15 of the 25 tile pairs of cfg4.  sym = 0 (row ranges of the multi-GPU drivers): one block per tile (tr, tc) of the
+   owned rows, which computes the pair in the same orientation and writes the transpose when tc < tr -- so that a row range
+   reproduces the entries of the full call bit for bit. */
 __global__ void __launch_bounds__(256) cov_gram_kernel(const double *__restrict__ V, const double *__restrict__ W, const int n_nodes,
                                                        const int Mpad, const int n_splits, double *__restrict__ P, const int accumulate,
-                                                       const int tr0, const int n_tr /* tile rows [tr0, tr0 + n_tr): the rows this device owns */)
+                                                       const int tr0, const int n_tr /* tile rows [tr0, tr0 + n_tr): the rows this device owns */,
+                                                       const int sym)
 {
     __shared__ double As[kKc][kTile], Bs[kKc][kTile], Ws[kKc][2];
     const int tiles = Mpad / kTile;
-    const int tile = blockIdx.x % (n_tr * tiles), split = blockIdx.x / (n_tr * tiles);
-    const int tr = tr0 + tile / tiles, tc = tile % tiles;
+    const int per_split = sym ? tiles * (tiles + 1) / 2 : n_tr * tiles;
+    const int tile = blockIdx.x % per_split, split = blockIdx.x / per_split;
+    int ta, tb;
+    bool write_direct, write_mirror;
+    if (sym) {
+        /* pair index -> (ta, tb), ta <= tb: row ta of the upper triangle holds tiles - ta pairs */
+        int u = tile;
+        ta = 0;
+        while (u >= tiles - ta) { u -= tiles - ta; ++ta; }
+        tb = ta + u;
+        write_direct = true; write_mirror = ta != tb;
+    }
+    else {
+        const int tr = tr0 + tile / tiles, tc = tile % tiles;
+        ta = tr < tc ? tr : tc; tb = tr < tc ? tc : tr;
+        write_direct = tc >= tr; write_mirror = tc < tr;
+    }
     const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
     const int per = (n_nodes + n_splits - 1) / n_splits;
     const int k0 = split * per, k1 = min(n_nodes, k0 + per);
@@ -154,8 +175,8 @@ __global__ void __launch_bounds__(256) cov_gram_kernel(const double *__restrict_
         for (int e = threadIdx.x; e < kKc * kTile; e += 256) {
             const int kk = e / kTile, c = e % kTile;
             const bool ok = kb + kk < k1;
-            As[kk][c] = ok ? V[(size_t)(kb + kk) * Mpad + tr * kTile + c] : 0.0;
-            Bs[kk][c] = ok ? V[(size_t)(kb + kk) * Mpad + tc * kTile + c] : 0.0;
+            As[kk][c] = ok ? V[(size_t)(kb + kk) * Mpad + ta * kTile + c] : 0.0;
+            Bs[kk][c] = ok ? V[(size_t)(kb + kk) * Mpad + tb * kTile + c] : 0.0;
         }
         if (threadIdx.x < kKc * 2) {
             const int kk = threadIdx.x / 2, p = threadIdx.x % 2;
@@ -182,9 +203,17 @@ __global__ void __launch_bounds__(256) cov_gram_kernel(const double *__restrict_
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const size_t o = (size_t)(tr * kTile + ty * 4 + i) * Mpad + tc * kTile + tx * 4 + j;
-            if (accumulate) { P1[o] += acc1[i][j]; P2[o] += acc2[i][j]; }
-            else { P1[o] = acc1[i][j]; P2[o] = acc2[i][j]; }
+            const int r = ta * kTile + ty * 4 + i, c = tb * kTile + tx * 4 + j;
+            if (write_direct) {
+                const size_t o = (size_t)r * Mpad + c;
+                if (accumulate) { P1[o] += acc1[i][j]; P2[o] += acc2[i][j]; }
+                else { P1[o] = acc1[i][j]; P2[o] = acc2[i][j]; }
+            }
+            if (write_mirror) {
+                const size_t o = (size_t)c * Mpad + r;
+                if (accumulate) { P1[o] += acc1[i][j]; P2[o] += acc2[i][j]; }
+                else { P1[o] = acc1[i][j]; P2[o] = acc2[i][j]; }
+            }
         }
 }
 
@@ -575,7 +604,7 @@ static int covariance_core(coffe_b200_ctx *ctx, const coffe_b200_covariance_para
     const int tr0 = row_begin / kTile, n_tr = (row_end - 1) / kTile - tr0 + 1;
     /* the k split (and with it the order of the partial sums) is fixed by the FULL matrix, not by the rows this call computes: a row
        range must reproduce the entries of the full call bit for bit (multi-GPU sharding over rows) */
-    int n_splits = std::max(1, (4 * ctx->n_sm) / (tiles * tiles));
+    int n_splits = std::max(1, (4 * ctx->n_sm) / (tiles * (tiles + 1) / 2));       /* ~4 blocks per SM over the pairs of tiles ta <= tb */
     const int chunk = std::max(kKc, std::min(n_nodes, (int)std::min<size_t>((size_t)1 << 31, ((size_t)2 << 30) / ((size_t)Mpad * 8))));
     if (n_splits > (chunk + kKc - 1) / kKc) n_splits = (chunk + kKc - 1) / kKc;
     CK(d_W.alloc((size_t)2 * n_nodes));
@@ -604,7 +633,8 @@ static int covariance_core(coffe_b200_ctx *ctx, const coffe_b200_covariance_para
             const size_t tot = (size_t)nn * Mpad;
             cov_bessel_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(d_k.p + c0, nn, d_sep.p, n_sep, d_l.p, n_l, delta, Mpad, d_V.p);
             CK(cudaGetLastError());
-            cov_gram_kernel<<<n_tr * tiles * n_splits, 256, 0, ctx->stream>>>(d_V.p, d_W.p + 2 * (size_t)c0, nn, Mpad, n_splits, d_P.p, it > 0, tr0, n_tr);
+            const int sym = tr0 == 0 && n_tr == tiles;
+            cov_gram_kernel<<<(sym ? tiles * (tiles + 1) / 2 : n_tr * tiles) * n_splits, 256, 0, ctx->stream>>>(d_V.p, d_W.p + 2 * (size_t)c0, nn, Mpad, n_splits, d_P.p, it > 0, tr0, n_tr, sym);
             CK(cudaGetLastError());
             ctx->last_launches += 2;
         }
