@@ -389,25 +389,6 @@ __global__ void __launch_bounds__(1024) cov_fftlog_rows_kernel(const FftPlan pla
 
 /* ---- host helpers ----------------------------------------------------------------------------------- */
 /* bicubic patch on a (possibly non-uniform) grid from node data {z, z_x, z_y, z_xy}, node index j*nx + i (gsl_interp2d_bicubic) */
-double bicubic_eval_host(const std::vector<double> &xa, const std::vector<double> &ya, const std::vector<build::Coef> &node, const double x, const double y)
-{
-    const int nx = (int)xa.size(), ny = (int)ya.size();
-    int xi = (int)(std::upper_bound(xa.begin(), xa.end(), x) - xa.begin()) - 1, yi = (int)(std::upper_bound(ya.begin(), ya.end(), y) - ya.begin()) - 1;
-    xi = std::max(0, std::min(nx - 2, xi)); yi = std::max(0, std::min(ny - 2, yi));
-    const double dx = xa[xi + 1] - xa[xi], dy = ya[yi + 1] - ya[yi];
-    const double t = (x - xa[xi]) / dx, u = (y - ya[yi]) / dy;
-    const build::Coef &n00 = node[(size_t)yi * nx + xi], &n10 = node[(size_t)yi * nx + xi + 1];
-    const build::Coef &n01 = node[(size_t)(yi + 1) * nx + xi], &n11 = node[(size_t)(yi + 1) * nx + xi + 1];
-    const double t2 = t * t, t3 = t2 * t, u2 = u * u, u3 = u2 * u;
-    const double h00t = 2 * t3 - 3 * t2 + 1, h10t = (t3 - 2 * t2 + t) * dx, h01t = -2 * t3 + 3 * t2, h11t = (t3 - t2) * dx;
-    const double h00u = 2 * u3 - 3 * u2 + 1, h10u = (u3 - 2 * u2 + u) * dy, h01u = -2 * u3 + 3 * u2, h11u = (u3 - u2) * dy;
-    /* Coef members {y, b, c, d} hold {z, z_x, z_y, z_xy} */
-    return h00t * (h00u * n00.y + h01u * n01.y + h10u * n00.c + h11u * n01.c)
-         + h01t * (h00u * n10.y + h01u * n11.y + h10u * n10.c + h11u * n11.c)
-         + h10t * (h00u * n00.b + h01u * n01.b + h10u * n00.d + h11u * n01.d)
-         + h11t * (h00u * n10.b + h01u * n11.b + h10u * n10.d + h11u * n11.d);
-}
-
 double covariance_coefficient(const double b1, const double b2, const double f, const int ell)      /* src/covariance.c:40-57 */
 {
     switch (ell) {
@@ -445,12 +426,95 @@ double legendre_integral(const int n, const int m, const int a, const int b)
 }
 
 /* G^(p)[(i1, m), (i2, n)] of stage B from the 2-D FFTLog: h_G[p * Mpad^2 + row * Mpad + col] */
-int fill_G_fftlog(coffe_b200_ctx *ctx, const coffe_b200_covariance_params *p, const int Mpad, std::vector<double> &h_G)
+/* ---- bicubic resampling of a 2-D FFTLog block on the device -------------------------------------------------------------------
+   gsl_interp2d_bicubic (src/covariance.c:428-455): node derivatives from natural cubic splines along the grid lines, Hermite patch.
+   Until round 2 every block went to the host for this (8 MB down, ~55 ms of spline solves, 12 blocks: the 0.7 s of the method).
+   The tridiagonal system depends on the knots only: its elimination factors are computed once on the host (table_build.h:
+   natural_c, same arithmetic), a line then costs one forward and one backward sweep.  One thread per line. */
+struct SplineLines {
+    const double *x, *off, *diagp, *w;      /* knots; off-diagonal, eliminated diagonal and elimination factors of the n - 2 equations */
+    int n;
+};
+
+/* derivative at every knot of the natural cubic spline through the n values src[line * line_stride + i * elem_stride];
+   scratch: n doubles per line, laid out [i * n_lines + line] */
+__global__ void cov_spline_derivs_kernel(const SplineLines sp, const double *__restrict__ src, const long line_stride, const long elem_stride,
+                                         double *__restrict__ dst, double *__restrict__ scratch, const int n_lines)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_lines) return;
+    const int n = sp.n, m = n - 2;
+    const double *y = src + (size_t)t * line_stride;
+    double *o = dst + (size_t)t * line_stride;
+    double *c = scratch + t;                /* c[i] at scratch[i * n_lines + t] */
+    auto Y = [&](const int i) { return y[(size_t)i * elem_stride]; };
+    auto C = [&](const int i) -> double & { return c[(size_t)i * n_lines]; };
+    /* forward sweep: g[i] kept in C(i + 1) */
+    double g_prev = 0.0;
+    for (int i = 0; i < m; ++i) {
+        const double h0 = sp.x[i + 1] - sp.x[i], h1 = sp.x[i + 2] - sp.x[i + 1];
+        double g = 3.0 * ((Y(i + 2) - Y(i + 1)) / h1 - (Y(i + 1) - Y(i)) / h0);
+        if (i > 0) g -= sp.w[i] * g_prev;
+        C(i + 1) = g;
+        g_prev = g;
+    }
+    C(0) = 0.0; C(n - 1) = 0.0;
+    C(m) = C(m) / sp.diagp[m - 1];
+    for (int i = m - 2; i >= 0; --i) C(i + 1) = (C(i + 1) - sp.off[i] * C(i + 2)) / sp.diagp[i];
+    for (int i = 0; i + 1 < n; ++i) {
+        const double dx = sp.x[i + 1] - sp.x[i];
+        o[(size_t)i * elem_stride] = (Y(i + 1) - Y(i)) / dx - dx * (C(i + 1) + 2.0 * C(i)) / 3.0;
+    }
+    {
+        const int i = n - 2;
+        const double dx = sp.x[i + 1] - sp.x[i];
+        const double b = (Y(i + 1) - Y(i)) / dx - dx * (C(i + 1) + 2.0 * C(i)) / 3.0;
+        const double d = (C(i + 1) - C(i)) / (3.0 * dx);
+        o[(size_t)(n - 1) * elem_stride] = b + dx * (2.0 * C(i) + 3.0 * dx * d);
+    }
+}
+
+/* G[(row0 + m) * Mpad + col0 + n] = norm * patch(sep_m, sep_n) (and the mirrored entry) from the node data A = {z, zx, zy, zxy}[i * n + j],
+   i along the first argument */
+__global__ void cov_bicubic_eval_kernel(const double *__restrict__ xa, const int n, const double *__restrict__ z, const double *__restrict__ zx,
+                                        const double *__restrict__ zy, const double *__restrict__ zxy, const double *__restrict__ sep,
+                                        const int n_sep, const double norm, const int Mpad, const int row0, const int col0, const int mirror,
+                                        double *__restrict__ G)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_sep * n_sep) return;
+    const int m = e / n_sep, q = e % n_sep;
+    auto cell = [&](const double v) {
+        int lo = 0, hi = n - 1;             /* last knot <= v, clamped to [0, n - 2] */
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (xa[mid] > v) hi = mid; else lo = mid; }
+        return lo;
+    };
+    const double x = sep[m], y = sep[q];
+    const int xi = cell(x), yi = cell(y);
+    const double dx = xa[xi + 1] - xa[xi], dy = xa[yi + 1] - xa[yi];
+    const double t = (x - xa[xi]) / dx, u = (y - xa[yi]) / dy;
+    const double t2 = t * t, t3 = t2 * t, u2 = u * u, u3 = u2 * u;
+    const double h00t = 2 * t3 - 3 * t2 + 1, h10t = (t3 - 2 * t2 + t) * dx, h01t = -2 * t3 + 3 * t2, h11t = (t3 - t2) * dx;
+    const double h00u = 2 * u3 - 3 * u2 + 1, h10u = (u3 - 2 * u2 + u) * dy, h01u = -2 * u3 + 3 * u2, h11u = (u3 - u2) * dy;
+    const size_t a00 = (size_t)xi * n + yi, a10 = a00 + n, a01 = a00 + 1, a11 = a10 + 1;       /* a[x-knot][y-knot] */
+    const double v = h00t * (h00u * z[a00] + h01u * z[a01] + h10u * zy[a00] + h11u * zy[a01])
+                   + h01t * (h00u * z[a10] + h01u * z[a11] + h10u * zy[a10] + h11u * zy[a11])
+                   + h10t * (h00u * zx[a00] + h01u * zx[a01] + h10u * zxy[a00] + h11u * zxy[a01])
+                   + h11t * (h00u * zx[a10] + h01u * zx[a11] + h10u * zxy[a10] + h11u * zxy[a11]);
+    G[(size_t)(row0 + m) * Mpad + col0 + q] = norm * v;
+    if (mirror) G[(size_t)(col0 + q) * Mpad + row0 + m] = norm * v;
+}
+
+int fill_G_fftlog(coffe_b200_ctx *ctx, const coffe_b200_covariance_params *p, const int Mpad, double *d_G /* [2][Mpad][Mpad] on the device */)
 {
     const int n_l = p->n_l, n_sep = p->n_sep;
     const int N = p->integration_bins > 0 ? p->integration_bins : 8000;
     FftPlan plan;
     if (N < 64 || N % 2 || !make_fft_plan(N, plan)) { ctx->err = "covariance_integration_bins must be even with prime factors 2, 3, 5 only"; return COFFE_B200_EINVAL; }
+    DevBuf<double> d_tw;
+    CK(cudaSetDevice(ctx->device));
+    CK(d_tw.alloc((size_t)2 * N));
+    CK(fft_plan_twiddles(plan, d_tw.p, ctx->stream));
     FftlogGeom g;
     g.N = N; g.kmin = p->k_min; g.ratio = p->k_max / p->k_min; g.dlnk = std::log(g.ratio) / N; g.nu = 1.01;      /* src/covariance.c:375-377 */
     /* r_i = 1 / k[N-1-i], ascending; rows / columns needed: the cells of the requested separations +- the reach of the spline derivatives */
@@ -492,9 +556,24 @@ int fill_G_fftlog(coffe_b200_ctx *ctx, const coffe_b200_covariance_params *p, co
     CK(cudaGetLastError());
     ctx->last_launches += 3;
 
-    h_G.assign((size_t)2 * Mpad * Mpad, 0.0);
-    std::vector<double> h_R((size_t)n_sub * n_sub), z((size_t)n_sub * n_sub);
+    CK(cudaMemsetAsync(d_G, 0, sizeof(double) * 2 * Mpad * Mpad, ctx->stream));
+    /* the natural-spline system of the knots rs, eliminated once (table_build.h: natural_c) */
+    DevBuf<double> d_rs, d_off, d_diagp, d_w, d_zx, d_zy, d_zxy, d_scr, d_seps;
+    {
+        const int m = n_sub - 2;
+        std::vector<double> off(m), diagp(m), w(m, 0.0);
+        for (int i = 0; i < m; ++i) {
+            const double h0 = rs[i + 1] - rs[i], h1 = rs[i + 2] - rs[i + 1];
+            off[i] = h1; diagp[i] = 2.0 * (h1 + h0);
+        }
+        for (int i = 1; i < m; ++i) { w[i] = off[i - 1] / diagp[i - 1]; diagp[i] -= w[i] * off[i - 1]; }
+        CK(d_rs.upload(rs, ctx->stream)); CK(d_off.upload(off, ctx->stream)); CK(d_diagp.upload(diagp, ctx->stream)); CK(d_w.upload(w, ctx->stream));
+    }
+    CK(d_seps.upload(std::vector<double>(p->sep, p->sep + n_sep), ctx->stream));
+    CK(d_zx.alloc((size_t)n_sub * n_sub)); CK(d_zy.alloc((size_t)n_sub * n_sub)); CK(d_zxy.alloc((size_t)n_sub * n_sub)); CK(d_scr.alloc((size_t)n_sub * n_sub));
+    const SplineLines sp{d_rs.p, d_off.p, d_diagp.p, d_w.p, n_sub};
     const double pi = 3.14159265358979323846;
+    const int lb = (n_sub + 127) / 128;
     for (int i1 = 0; i1 < n_l; ++i1)
         for (int i2 = i1; i2 < n_l; ++i2)
             for (int pw = 0; pw < 2; ++pw) {
@@ -507,22 +586,19 @@ int fill_G_fftlog(coffe_b200_ctx *ctx, const coffe_b200_covariance_params *p, co
                 cov_fftlog_rows_kernel<<<std::min(n_cta, n_sub), 1024, 0, ctx->stream>>>(plan, g, reinterpret_cast<const cplx *>(d_Y.p), i_lo, n_sub,
                                                                                       reinterpret_cast<cplx *>(d_work.p), d_R.p);
                 CK(cudaGetLastError());
-                ctx->last_launches += 2;
-                CK(cudaMemcpyAsync(h_R.data(), d_R.p, h_R.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-                CK(cudaStreamSynchronize(ctx->stream));
-                /* bicubic resampling onto the separations (gsl_interp2d_bicubic on the (r1, r2) grid, z[j*nx + i] <-> (r1_i, r2_j),
-                   src/covariance.c:428-455); derivative estimates from natural cubic splines along the rows and columns of the block */
-                for (int i = 0; i < n_sub; ++i)
-                    for (int j = 0; j < n_sub; ++j) z[(size_t)j * n_sub + i] = h_R[(size_t)i * n_sub + j];
-                const std::vector<build::Coef> node = build::bicubic_nodes(rs.data(), rs.data(), z.data(), n_sub, n_sub);
+                /* bicubic resampling onto the separations, A[i][j] = R[i * n_sub + j] <-> (r1_i, r2_j): z_x along i (stride n_sub), z_y
+                   along j, z_xy = (z_y)_x, as gsl_interp2d_bicubic estimates them (src/covariance.c:428-455) */
+                cov_spline_derivs_kernel<<<lb, 128, 0, ctx->stream>>>(sp, d_R.p, 1, n_sub, d_zx.p, d_scr.p, n_sub);
+                cov_spline_derivs_kernel<<<lb, 128, 0, ctx->stream>>>(sp, d_R.p, n_sub, 1, d_zy.p, d_scr.p, n_sub);
+                cov_spline_derivs_kernel<<<lb, 128, 0, ctx->stream>>>(sp, d_zy.p, 1, n_sub, d_zxy.p, d_scr.p, n_sub);
                 const double norm = (pw == 0 ? 2.0 : 1.0) / pi / pi;               /* src/covariance.c:760-769 */
-                for (int m = 0; m < n_sep; ++m)
-                    for (int n = 0; n < n_sep; ++n) {
-                        const double v = norm * bicubic_eval_host(rs, rs, node, p->sep[m], p->sep[n]);
-                        h_G[(size_t)pw * Mpad * Mpad + (size_t)(i1 * n_sep + m) * Mpad + (i2 * n_sep + n)] = v;
-                        if (i2 != i1) h_G[(size_t)pw * Mpad * Mpad + (size_t)(i2 * n_sep + n) * Mpad + (i1 * n_sep + m)] = v;   /* :779-788 */
-                    }
+                cov_bicubic_eval_kernel<<<(n_sep * n_sep + 127) / 128, 128, 0, ctx->stream>>>(d_rs.p, n_sub, d_R.p, d_zx.p, d_zy.p, d_zxy.p, d_seps.p, n_sep, norm,
+                                                                                          Mpad, i1 * n_sep, i2 * n_sep, i2 != i1 /* :779-788 */,
+                                                                                          d_G + (size_t)pw * Mpad * Mpad);
+                CK(cudaGetLastError());
+                ctx->last_launches += 6;
             }
+    CK(cudaStreamSynchronize(ctx->stream));
     return COFFE_B200_OK;
 }
 
@@ -616,11 +692,8 @@ static int covariance_core(coffe_b200_ctx *ctx, const coffe_b200_covariance_para
     const bool fftlog = p->integration_method == 2;        /* COFFE_COVARIANCE_INTEGRATION_FFTLOG, src/common.h:301-302 */
     if (fftlog) {
         /* the reference has no binned variant of this path and falls back to the unbinned one with a warning (src/covariance.c:713-720) */
-        std::vector<double> h_G;
-        const int rc = fill_G_fftlog(ctx, p, Mpad, h_G);
+        const int rc = fill_G_fftlog(ctx, p, Mpad, d_G.p);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(d_G.p, h_G.data(), h_G.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
     }
     SplineView s1{d_pkx.p, reinterpret_cast<const double4 *>(d_c1.p), p->n_pk}, s2{d_pkx.p, reinterpret_cast<const double4 *>(d_c2.p), p->n_pk};
     if (!fftlog) {

@@ -1057,6 +1057,10 @@ int coffe_b200_create(int device, coffe_b200_ctx **out)
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
             unsigned long long keep = ~0ull;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            /* first use of the pool costs ~40 ms (measured inside the first call): pay it here, once per context */
+            void *warm = nullptr;
+            if (cudaMallocAsync(&warm, 1 << 20, ctx->stream) == cudaSuccess) { cudaFreeAsync(warm, ctx->stream); cudaStreamSynchronize(ctx->stream); }
+            else cudaGetLastError();
         }
     }
     std::memset(&ctx->o, 0, sizeof(ctx->o));

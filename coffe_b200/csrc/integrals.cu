@@ -262,6 +262,9 @@ int coffe_b200_integrals(coffe_b200_ctx *ctx, const coffe_b200_integrals_params 
     CK(cudaSetDevice(ctx->device));
     ctx->last_ms = 0; ctx->last_launches = 0;
     cudaStream_t st = ctx->stream;
+    DevBuf<double> d_tw;
+    CK(d_tw.alloc((size_t)2 * N));
+    CK(fft_plan_twiddles(plan, d_tw.p, st));
 
     /* P(k): natural cubic spline for 2-FAST (src/twofast.c:399), the configured interpolation for the direct integrals */
     std::vector<build::Coef> c_nat = build::cspline_coefs(p->pk_k, p->pk_p, p->n_pk), c_int;

@@ -1,3 +1,2 @@
-python -m pytest tests -m gpu -q -x -k "covariance or cov" 2>&1 | tail -3
-python -m pytest tests/test_multigpu.py tests/test_coffe_class.py tests/test_dropin.py -m gpu -q 2>&1 | tail -2
-python bench.py --no-cpu-baseline --no-extras 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); c=d['covariance']; print(d['value'], c['value'], c['wall_ms'], c['kernel_ms'])"
+python -m pytest tests -m gpu -q -x -k "fftlog or covariance or cov" 2>&1 | tail -3
+python bench.py --no-cpu-baseline --no-extras 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); c=d['covariance']; print(d['value'], c['value'], c['wall_ms'], c['kernel_ms'], c['fftlog'])"
