@@ -84,6 +84,35 @@ void *hs_create(const coffe_b200_tables *T, const coffe_b200_options *opt)
 
 void hs_destroy(void *h) { delete (HostSim *)h; }
 
+/* the ridge rule of quadrature.cuh (RidgeUnits: the unit walk both integration kernels use) on a closed-form test integrand, without a
+   context: integral over lambda in [0, hi] of (1 + lambda / hi) / (d^2 + eps^2)^p, d = lambda - center, with n_panel nodes per panel
+   and the given plan; p = 0 checks that the units tile [0, hi] exactly once */
+double hs_ridge_rule(double center, double hi, double eps, double eps_min, double W, double Du, double ratio, double growth, int tail_log,
+                     int n_panel, double p, double *n_evals)
+{
+    const std::vector<double> rp = build_rpow(ratio);
+    std::vector<double> x, w;
+    build::gauss_legendre_01(n_panel, x, w);
+    const PanelPlan plan = panel_plan(eps, eps_min, W, Du, ratio, rp.data(), 1, growth > 1.0 ? std::log(growth) : 0.0, tail_log ? std::log(ratio) : 0.0);
+    double acc = 0.0, n = 0.0;
+    for (int j = 0; j < n_panel; ++j) {
+        RidgeUnits u;
+        ridge_units_init(u, plan, center, hi, x[j], w[j], tail_log ? std::exp(std::log(ratio) * x[j]) : 0.0);
+        for (int iu = 0; iu < u.n_units; ++iu) {
+            double d, wgt;
+            const int sides = ridge_unit_node(u, iu, d, wgt);
+            for (int sd = 0; sd < 2; ++sd)
+                if (sides & (1 << sd)) {
+                    const double lam = sd == 0 ? center - d : center + d;
+                    acc += wgt * (1.0 + lam / hi) * std::pow(d * d + eps * eps, -p);
+                    n += 1.0;
+                }
+        }
+    }
+    if (n_evals) *n_evals = n;
+    return acc;
+}
+
 /* panel plan of quadrature.cuh without a context: out = {J, M, B_J, B_(J+M), panel_count(b), panel_count_by_break(b),
    J and B_J by repeated doubling (the definition the closed form must reproduce)} */
 void hs_panel_plan(double eps, double eps_min, double W, double Du, double ratio, int shift, double b, double *out)

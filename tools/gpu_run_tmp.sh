@@ -1,2 +1,2 @@
-python -m pytest tests -m gpu -q -x -k "fftlog or covariance or cov" 2>&1 | tail -3
-python bench.py --no-cpu-baseline --no-extras 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); c=d['covariance']; print(d['value'], c['value'], c['wall_ms'], c['kernel_ms'], c['fftlog'])"
+timeout 900 compute-sanitizer --tool memcheck python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/sanitizer_memcheck.log 2>&1; tail -4 gpurun_out/sanitizer_memcheck.log
+timeout 900 compute-sanitizer --tool racecheck python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/sanitizer_racecheck.log 2>&1; tail -4 gpurun_out/sanitizer_racecheck.log
