@@ -802,3 +802,32 @@ def test_cfg3_average_multipoles_match_converged_oracle_fixture(engine):
         ps = np.max(np.abs(want[:, :, piece]), axis=2, keepdims=True)
         assert np.max(np.abs(got[:, :, piece] - want[:, :, piece]) / ps) < 1e-5, (piece, np.abs(got[:, :, piece] - want[:, :, piece]) / ps)
     assert float(fx["oracle_self_error"].max()) < 1e-6 and float(fx["z_rule_error"]) < 1e-6
+
+
+def test_rules_follow_the_call_and_the_contributions(engine):
+    """which defaults the zeros of coffe_b200_quadrature stand for: total-target rules with the mapped panels for
+    mu-integrated totals when density / RSD are on; piece rules for pieces, for the 2-point function at a fixed mu (its value is
+    compared with itself) and whenever no local term sets the scale; six mu nodes for potential terms without lensing"""
+    engine.set_options(ALL)
+    engine.set_quadrature()
+    q = engine.get_quadrature()
+    assert q["accuracy_target"] == 2 and q["geometric_growth_di"] == 8.0 and q["tail_map_di"] == 2 and q["tail_ratio_di"] == 6.0
+    assert q["geometric_growth"] == 4.0 and q["tail_map"] == 2 and q["mu_switch_break_di"] == 2 and q["n_renorm"] == 12
+    assert q["n_outer_min"] == 25 and q["panel_width_di"] == 96.0 and q["n_panel_di"] == 6 and q["n_mu_panel_di"] == 4
+    sep, mu = np.array([30.0, 150.0, 400.0]), np.array([-0.7, 0.2, 0.98])
+    a = engine.corrfunc([1.0], mu, sep)
+    engine.set_quadrature(accuracy_target=1)
+    q1 = engine.get_quadrature()
+    assert q1["accuracy_target"] == 1 and q1["tail_map"] == 1 and q1["mu_switch_break_di"] == 1 and q1["n_renorm"] == 24 and q1["n_panel_di"] == 8
+    b = engine.corrfunc([1.0], mu, sep)
+    assert np.array_equal(a, b)                     # the 2-point function ran under the piece rules either way
+    pieces = engine.multipoles_pieces([1.0], sep, [0, 2, 4])
+    engine.set_quadrature()
+    assert np.array_equal(pieces, engine.multipoles_pieces([1.0], sep, [0, 2, 4]))      # and so do the *_pieces calls
+    assert not np.array_equal(pieces.sum(0), engine.multipoles([1.0], sep, [0, 2, 4]))  # while the totals take the coarser rules
+    engine.set_options(["g4", "g5"])
+    q2 = engine.get_quadrature()
+    assert q2["accuracy_target"] == 1 and q2["n_mu_panel_di"] == 6
+    engine.set_options(["len", "g4"])
+    assert engine.get_quadrature()["n_mu_panel_di"] == 5
+    engine.set_options(ALL)
