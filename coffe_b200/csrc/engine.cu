@@ -198,24 +198,41 @@ constexpr int kDISmallDoubles = kMaxTail + 3 * 32;
 struct SIItemSetup { Geometry g; SIHalf h[2]; };
 struct DIItemSetup { DIConst k; };
 
-__global__ void item_setup_kernel(const __grid_constant__ Tables t, const __grid_constant__ Options o, const int mode,
+constexpr int kSetupThreads = 32;
+/* words of a staged record: one more than the record so that the threads of a warp write different banks */
+constexpr int kSetupStride = (int)(sizeof(SIItemSetup) / 8) + 1;
+
+template <int mode>
+__global__ void item_setup_kernel(const __grid_constant__ Tables t, const __grid_constant__ Options o,
                                   const double *__restrict__ pz, const double *__restrict__ psep,
                                   const int *__restrict__ item_point, const double *__restrict__ item_mu, const int n_items,
                                   SIItemSetup *__restrict__ si_out, DIItemSetup *__restrict__ di_out)
 {
+    /* the 768-byte records of the local x integrated items go through shared memory so that the block writes them as one
+       contiguous run (a record per thread straight to global memory: 96 stores of a 768-byte stride per warp, 0.9 ms per cfg5 step) */
+    __shared__ double stage[mode == 1 ? kSetupThreads * kSetupStride : 1];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_items) return;
-    const int p = item_point[i];
-    const Geometry g = geometry(bg_chi(t.bg, pz[p]), psep[p], item_mu[i]);
-    /* redshift of the end points from the line-of-sight table (fifth slot), as the integration kernels read it along the way */
-    const EndVals e1 = end_eval_at(o, t, g.chi1, los_z(t.los.v, t.los.n, t.los.inv_h, g.chi1), 1);
-    const EndVals e2 = end_eval_at(o, t, g.chi2, los_z(t.los.v, t.los.n, t.los.inv_h, g.chi2), 2);
-    if (mode == 1) {
-        si_out[i].g = g;
-        si_out[i].h[0] = si_half_setup(o, g, e1, e2, true);
-        si_out[i].h[1] = si_half_setup(o, g, e2, e1, false);
+    const bool have = i < n_items;
+    if (have) {
+        const int p = item_point[i];
+        const Geometry g = geometry(bg_chi(t.bg, pz[p]), psep[p], item_mu[i]);
+        /* redshift of the end points from the line-of-sight table (fifth slot), as the integration kernels read it along the way */
+        const EndVals e1 = end_eval_at(o, t, g.chi1, los_z(t.los.v, t.los.n, t.los.inv_h, g.chi1), 1);
+        const EndVals e2 = end_eval_at(o, t, g.chi2, los_z(t.los.v, t.los.n, t.los.inv_h, g.chi2), 2);
+        if (mode == 1) {
+            SIItemSetup *rec = reinterpret_cast<SIItemSetup *>(stage + (size_t)threadIdx.x * kSetupStride);
+            rec->g = g;
+            rec->h[0] = si_half_setup(o, g, e1, e2, true);
+            rec->h[1] = si_half_setup(o, g, e2, e1, false);
+        }
+        else di_out[i].k = di_setup(o, e1, e2);
     }
-    else di_out[i].k = di_setup(o, e1, e2);
+    if (mode != 1) return;
+    __syncthreads();
+    constexpr int kWords = (int)(sizeof(SIItemSetup) / 8);
+    const int first = blockIdx.x * blockDim.x, n_here = min((int)blockDim.x, n_items - first);
+    double *dst = reinterpret_cast<double *>(si_out + first);
+    for (int e = threadIdx.x; e < n_here * kWords; e += blockDim.x) dst[e] = stage[(e / kWords) * kSetupStride + e % kWords];
 }
 
 constexpr int kSIThreads = 384;
@@ -681,8 +698,12 @@ int launch_integrated(coffe_b200_ctx *ctx, Batch &b, const int mode, unsigned in
             /* end-point values and amplitudes of every item, one thread each */
             const size_t setup_bytes = (size_t)L.n * (mode == 1 ? sizeof(SIItemSetup) : sizeof(DIItemSetup));
             if (L.setup.n != setup_bytes) CK(L.setup.alloc(setup_bytes));
-            item_setup_kernel<<<(L.n + 127) / 128, 128, 0, ctx->stream>>>(ctx->t, ctx->o, mode, b.pz.p, b.psep.p, L.point.p, L.mu.p, L.n,
-                                                                         reinterpret_cast<SIItemSetup *>(L.setup.p), reinterpret_cast<DIItemSetup *>(L.setup.p));
+            if (mode == 1)
+                item_setup_kernel<1><<<(L.n + kSetupThreads - 1) / kSetupThreads, kSetupThreads, 0, ctx->stream>>>(
+                    ctx->t, ctx->o, b.pz.p, b.psep.p, L.point.p, L.mu.p, L.n, reinterpret_cast<SIItemSetup *>(L.setup.p), nullptr);
+            else
+                item_setup_kernel<2><<<(L.n + 127) / 128, 128, 0, ctx->stream>>>(
+                    ctx->t, ctx->o, b.pz.p, b.psep.p, L.point.p, L.mu.p, L.n, nullptr, reinterpret_cast<DIItemSetup *>(L.setup.p));
             CK(cudaGetLastError());
             ctx->last_launches += 1;
             int grid = std::min(ctx->n_sm, (L.n + warps - 1) / warps);
