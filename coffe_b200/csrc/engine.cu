@@ -1078,9 +1078,25 @@ int coffe_b200_create(int device, coffe_b200_ctx **out)
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
             unsigned long long keep = ~0ull;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            /* lazy module loading would otherwise put the load of the two large kernels inside the first call */
+            {
+                cudaFuncAttributes fa;
+                cudaFuncGetAttributes(&fa, di_items_smem_kernel);
+                cudaFuncGetAttributes(&fa, si_items_smem_kernel);
+                cudaFuncGetAttributes(&fa, item_setup_kernel<1>);
+                cudaFuncGetAttributes(&fa, item_setup_kernel<2>);
+                cudaFuncGetAttributes(&fa, ni_multipoles_kernel);
+                cudaFuncGetAttributes(&fa, reduce_multipoles_kernel);
+                cudaFuncGetAttributes(&fa, expand_items_kernel);
+                cudaGetLastError();
+            }
             /* first use of the pool costs ~40 ms (measured inside the first call): pay it here, once per context */
+            /* ... and reserve what a full-grid call takes from it (~1 GB of item set-up records for 32 x 1000 points; growing the pool
+               by that much measured 100-250 ms inside the first call).  COFFE_B200_POOL_MB overrides the reservation (0 = none). */
+            size_t reserve_mb = 1024;
+            if (const char *e = std::getenv("COFFE_B200_POOL_MB")) reserve_mb = (size_t)std::max(0L, std::atol(e));
             void *warm = nullptr;
-            if (cudaMallocAsync(&warm, 1 << 20, ctx->stream) == cudaSuccess) { cudaFreeAsync(warm, ctx->stream); cudaStreamSynchronize(ctx->stream); }
+            if (cudaMallocAsync(&warm, std::max<size_t>(reserve_mb, 1) << 20, ctx->stream) == cudaSuccess) { cudaFreeAsync(warm, ctx->stream); cudaStreamSynchronize(ctx->stream); }
             else cudaGetLastError();
         }
     }
