@@ -4,10 +4,12 @@
 //   point  = one (z, separation) pair of the output grid (for redshift-averaged multipoles: one
 //            (bin, separation, z-node) triple);
 //   item   = one (point, mu-node) pair.  The integrated pieces (local x integrated, integrated x
-//            integrated) of the 2-point function at that (z, r, mu) are computed by ONE CTA:
-//            thread 0 folds the end-point amplitudes into shared memory, the line-of-sight table is
-//            staged in shared memory, warps stride over the outer line-of-sight nodes and lanes over
-//            the inner panel nodes, partial sums are combined with warp shuffles;
+//            integrated) of the 2-point function at that (z, r, mu) come from three kernels per piece:
+//            item_setup_kernel (one thread per item: end-point values folded into amplitudes / polynomial
+//            coefficients, one record per item in HBM), then a persistent kernel with the I^n_l and
+//            line-of-sight tables in shared memory, in which every GROUP of n_panel lanes walks one
+//            line-of-sight integral (di_items_smem_kernel: one warp per item, one outer node per group;
+//            si_items_smem_kernel: one half per group), partial sums combined with warp shuffles;
 //   the local x local piece is a 1-D Gauss-Legendre sum in mu, one warp per point;
 //   a last kernel forms (2l+1) sum_mu w P_l(mu) xi(mu) per point in a fixed order (deterministic).
 // This replaces the three OpenMP sweeps of coffe_multipoles_init / coffe_corrfunc_init /
@@ -179,14 +181,14 @@ __global__ void __launch_bounds__(kItemThreads, COFFE_ITEM_MIN_BLOCKS) integrate
 }
 
 
-/* ---- integrated pieces, shared-memory tables: persistent CTAs, one warp per item ------------------
+/* ---- integrated pieces, shared-memory tables: persistent CTAs ---------------------------------------
    Every CTA copies the compact tables (compact.cuh) and the line-of-sight table into shared memory once,
-   then its warps draw items from a global counter until none are left.  A warp owns its item: the lanes
-   stride over the (panel, node) pairs of the inner ridge rule while the outer line-of-sight nodes are visited
-   in order, so the result of an item does not depend on which warp computed it (bit-reproducible for any
-   grid size or GPU count).  Two kernels so that each gets its own register allocation:
-   si_items_smem_kernel (local x integrated: two 1-D integrals per item) and di_items_smem_kernel
-   (integrated x integrated: the 2-D integral, > 90 % of the device time of a step). */
+   then its warps draw work from a global counter until none is left.  A group of n_panel lanes owns one
+   line-of-sight integral and sums it in a fixed order, so a result does not depend on which warp computed it
+   (bit-reproducible for any grid size or GPU count).  Two kernels so that each gets its own register
+   allocation: si_items_smem_kernel (local x integrated: two 1-D integrals per item, one per group) and
+   di_items_smem_kernel (integrated x integrated: the 2-D integral, one warp per item and one outer node per
+   group; 86 % of the device time of a cfg5 step). */
 /* doubles of the small read-only block staged next to the tables: powers of the tail ratio, then the nodes and
    weights of the inner panel rule */
 constexpr int kDISmallDoubles = kMaxTail + 3 * 32;

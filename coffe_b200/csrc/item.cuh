@@ -2,9 +2,11 @@
 // dispatcher returns (coffe_integrate, src/signal.c:472-771): local x local (closed form),
 // local x integrated (1-D line-of-sight integral per half) and integrated x integrated (2-D).
 //
-// Written as lane-strided partial sums: a caller with `nlanes` cooperating lanes passes its lane id and
-// reduces the returned partials (warp shuffle on the device; nlanes = 1 in the CPU debugging harness),
-// so the device kernels and the harness execute the same arithmetic on the same nodes.
+// Written as per-lane partial sums: lane j of a group of n_panel lanes owns node j of every panel and the caller reduces the
+// partials (warp shuffle on the device; the CPU debugging harness calls the lanes of a group in turn), so the device kernels and
+// the harness execute the same arithmetic on the same nodes.  (ridge_integrate / si_half_partial / di_partial below are the plain
+// panel-list form of the same integrals: the midpoint-approximation mode, whose 2-D tables rule out the shared lookup of mirror
+// nodes, still runs on them.)
 #pragma once
 #include "physics.cuh"
 #include "quadrature.cuh"
