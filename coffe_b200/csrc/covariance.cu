@@ -138,7 +138,7 @@ __global__ void cov_bessel_kernel(const double *__restrict__ k, const int n_node
    ta <= tb, 15 of the 25 tile pairs of cfg4.  sym = 0 (row ranges of the multi-GPU drivers): one block per tile (tr, tc) of the
    owned rows, which computes the pair in the same orientation and writes the transpose when tc < tr -- so that a row range
    reproduces the entries of the full call bit for bit. */
-__global__ void __launch_bounds__(256) cov_gram_kernel(const double *__restrict__ V, const double *__restrict__ W, const int n_nodes,
+__global__ void __launch_bounds__(256, 2) cov_gram_kernel(const double *__restrict__ V, const double *__restrict__ W, const int n_nodes,
                                                        const int Mpad, const int n_splits, double *__restrict__ P, const int accumulate,
                                                        const int tr0, const int n_tr /* tile rows [tr0, tr0 + n_tr): the rows this device owns */,
                                                        const int sym)
@@ -170,19 +170,36 @@ __global__ void __launch_bounds__(256) cov_gram_kernel(const double *__restrict_
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) { acc1[i][j] = 0.0; acc2[i][j] = 0.0; }
-    for (int kb = k0; kb < k1; kb += kKc) {
-        /* 16 x 64 doubles per operand tile, 256 threads: 4 each */
-        for (int e = threadIdx.x; e < kKc * kTile; e += 256) {
-            const int kk = e / kTile, c = e % kTile;
+    /* 16 x 64 doubles per operand tile, 256 threads: 4 each; the next k tile is loaded into registers while the current one is
+       multiplied (the loads come from L2 / HBM: without the overlap the kernel waited on them, long scoreboard 3.3 per issue) */
+    double ra[4], rb[4], rw = 0.0;
+    auto fetch = [&](const int kb) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = threadIdx.x + 256 * u, kk = e / kTile, c = e % kTile;
             const bool ok = kb + kk < k1;
-            As[kk][c] = ok ? V[(size_t)(kb + kk) * Mpad + ta * kTile + c] : 0.0;
-            Bs[kk][c] = ok ? V[(size_t)(kb + kk) * Mpad + tb * kTile + c] : 0.0;
+            ra[u] = ok ? V[(size_t)(kb + kk) * Mpad + ta * kTile + c] : 0.0;
+            rb[u] = ok ? V[(size_t)(kb + kk) * Mpad + tb * kTile + c] : 0.0;
         }
         if (threadIdx.x < kKc * 2) {
             const int kk = threadIdx.x / 2, p = threadIdx.x % 2;
-            Ws[kk][p] = kb + kk < k1 ? W[2 * (size_t)(kb + kk) + p] : 0.0;
+            rw = kb + kk < k1 ? W[2 * (size_t)(kb + kk) + p] : 0.0;
         }
+    };
+    auto commit = [&]() {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = threadIdx.x + 256 * u, kk = e / kTile, c = e % kTile;
+            As[kk][c] = ra[u]; Bs[kk][c] = rb[u];
+        }
+        if (threadIdx.x < kKc * 2) Ws[threadIdx.x / 2][threadIdx.x % 2] = rw;
+    };
+    static_assert(kKc * kTile == 4 * 256, "four doubles of each operand tile per thread");
+    if (k0 < k1) fetch(k0);
+    for (int kb = k0; kb < k1; kb += kKc) {
+        commit();
         __syncthreads();
+        if (kb + kKc < k1) fetch(kb + kKc);
 #pragma unroll
         for (int kk = 0; kk < kKc; ++kk) {
             double a[4], b[4];
