@@ -645,8 +645,10 @@ def cfg5_grid():
 
 def test_cfg5_dense_self_convergence_default_vs_doubled_rules():
     """Every point of a dense subsample of the benchmarked cfg5 grid -- all 32 z_mean x (every 2nd separation + the separations
-    within +-2 grid knots of every rule switch: the mu-panel plan changes at r_perp = 16, 32, 64, 96 ... 256, 384 Mpc and the outer
-    rule max(30, 10 + r/12) has its kink at 240 Mpc and then steps every 12 Mpc) -- with the default fixed-node rules against the
+    within +-2 grid knots of every rule switch: the mu-panel plans change at r = 16, 32, 64, 96 ... 256, 384 Mpc, the log-mapped r_perp
+    panels of the local x integrated rule at r = 16 and 128 Mpc, and the outer rule max(25, 10 + r/15), rounded up to whole rounds of
+    five lane groups, steps at 225, 300 and 375 Mpc; the steps of the round-1 rule, 240 + 12 k, stay in the list) -- with the default
+    fixed-node rules against the
     same kernels with every node count doubled and every panel narrowed (FINE_RULES): each multipole within 1e-5 of the l = 0..4
     scale of the point.  ~16 700 (z, r) points, under the automatic accuracy target (the rules the benchmark times); a node count that
     fails here is raised, not the tolerance."""
@@ -657,7 +659,7 @@ def test_cfg5_dense_self_convergence_default_vs_doubled_rules():
     eng.set_options(ALL)
     z, sep, ls = cfg5_grid()
     pick = set(range(0, 1000, 2)) | {999}           # every second separation of the grid: ~16 700 (z, r) points, half of cfg5
-    switches = [16.0, 32.0, 64.0, 96.0, 128.0, 160.0, 192.0, 224.0, 240.0, 256.0, 384.0] + [240.0 + 12.0 * k for k in range(1, 18)]
+    switches = [16.0, 32.0, 64.0, 96.0, 128.0, 160.0, 192.0, 224.0, 225.0, 240.0, 256.0, 300.0, 375.0, 384.0] + [240.0 + 12.0 * k for k in range(1, 18)]
     for s in switches:
         j = int(np.searchsorted(sep, s))
         pick |= {k for k in range(j - 2, j + 2) if 0 <= k < 1000}
