@@ -566,11 +566,33 @@ Rules make_rules(const coffe_b200_ctx *ctx)
 
 /* (re)derive the rules in force: defaults of the accuracy target, then the caller's non-zero knobs.  want_pieces: the call returns
    the pieces themselves (coffe_integrate per flag_integral), which an automatic target always serves at piece accuracy. */
+/* How large the integrated terms are against the density term, up to geometry: max over the knots of the uploaded bias tables of
+   |2 - 5 s(z)| / b(z), worst of the two populations.  2 for the default biases (b = 1, s = 0), under which the two line-of-sight
+   pieces are at most a few per cent of every multipole of the benchmarked grid -- the premise of the total target. */
+double integrated_share_factor(const coffe_b200_ctx *ctx)
+{
+    if (!ctx->have_tables) return 2.0;
+    const Tables &t = ctx->t_host;
+    double worst = 0.0;
+    for (int pop = 0; pop < 2; ++pop) {
+        const SplineView b = t.bias[pop == 0 ? B_GAL1 : B_GAL2], s = t.bias[pop == 0 ? B_MAG1 : B_MAG2];
+        if (!b.x || !s.x || b.n < 2 || s.n < 2) continue;
+        for (int i = 0; i < b.n; ++i) {
+            const double z = b.x[i], bz = std::fabs(spline_eval(b, z)), sz = spline_eval(s, std::min(std::max(z, s.x[0]), s.x[s.n - 1]));
+            worst = std::max(worst, std::fabs(2.0 - 5.0 * sz) / std::max(bz, 1e-3));
+        }
+    }
+    return worst;
+}
+
 int apply_quadrature(coffe_b200_ctx *ctx, const bool want_pieces)
 {
     int target = ctx->user_q.accuracy_target;
+    /* automatic: the total target needs the density term to set the scale of the multipoles (RSD alone is an order of magnitude
+       smaller) and biases under which the integrated terms stay small against it: twice the default ratio at most */
     if (target != COFFE_B200_TARGET_PIECE && target != COFFE_B200_TARGET_TOTAL)
-        target = (!want_pieces && (ctx->o.den || ctx->o.rsd) && !ctx->o.midpoint) ? COFFE_B200_TARGET_TOTAL : COFFE_B200_TARGET_PIECE;
+        target = (!want_pieces && ctx->o.den && !ctx->o.midpoint && integrated_share_factor(ctx) <= 4.0) ? COFFE_B200_TARGET_TOTAL
+                                                                                                         : COFFE_B200_TARGET_PIECE;
     QuadConfig base = target == COFFE_B200_TARGET_TOTAL ? total_target_quadrature() : default_quadrature();
     /* potential terms without lensing: the integrated x integrated piece is then smooth in mu but its l = 4 moment sets the scale of
        what 5 nodes per r_perp panel leave (1.0e-5 of the piece at r = 30 Mpc; 6 nodes: 1.9e-6, profiles/r2_piece_sweep_b.log) */
@@ -1213,6 +1235,7 @@ int coffe_internal_commit_tables(coffe_b200_ctx *ctx, PreparedTables &P, const b
     ctx->pops_identical = P.pops_identical;
     ctx->mag_constant = P.mag_constant;
     ctx->have_tables = true;
+    if (const int rq = apply_quadrature(ctx, false)) return rq;       /* the automatic accuracy target looks at the bias tables */
     ctx->generation++;
     return COFFE_B200_OK;
 }

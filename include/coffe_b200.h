@@ -122,7 +122,8 @@ typedef struct coffe_b200_quadrature {
     double tail_ratio_di;
     int geometric_shift_di;      /* log2 of the growth factor of its geometric panels: 1 = doubling, 2 = x4 */
     /* What the 1e-5 gate is measured against, which picks the library defaults the zeros above stand for:
-       0 = automatic: COFFE_B200_TARGET_TOTAL when density or RSD is among the contributions and the call returns mu-integrated totals
+       0 = automatic: COFFE_B200_TARGET_TOTAL when density is among the contributions, the uploaded biases keep the integrated terms
+           small against it (max |2 - 5 s(z)| / b(z) at most twice its default of 2) and the call returns mu-integrated totals
            (multipoles / average multipoles / their group and sharded forms; the 2-point function at a fixed mu always gets the piece rules), COFFE_B200_TARGET_PIECE otherwise and
            always for the *_pieces entry points (a caller of coffe_integrate(flag_integral) gets each piece to 1e-5 of itself);
        1 = COFFE_B200_TARGET_PIECE: every piece (local x local, local x integrated, integrated x integrated) within 1e-5 of its own

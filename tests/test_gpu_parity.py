@@ -832,4 +832,16 @@ def test_rules_follow_the_call_and_the_contributions(engine):
     assert q2["accuracy_target"] == 1 and q2["n_mu_panel_di"] == 6
     engine.set_options(["len", "g4"])
     assert engine.get_quadrature()["n_mu_panel_di"] == 5
+    engine.set_options(["rsd", "len"])              # without the density term nothing keeps the integrated pieces small: piece rules
+    assert engine.get_quadrature()["accuracy_target"] == 1
     engine.set_options(ALL)
+    # biases that make the integrated terms large against the density term switch the automatic target off
+    import coffe_b200
+    from coffe_b200.default_tables import load_default_tableset, BIAS_Z
+    eng = coffe_b200.Engine(0)
+    eng.set_options(ALL)
+    eng.upload_tables(load_default_tableset(bias={"magnification_bias1": (BIAS_Z, np.full_like(BIAS_Z, -0.5)), "magnification_bias2": (BIAS_Z, np.full_like(BIAS_Z, -0.5))}))
+    assert eng.get_quadrature()["accuracy_target"] == 1        # |2 - 5 s| / b = 4.5
+    eng.upload_tables(load_default_tableset(bias={"galaxy_bias1": (BIAS_Z, np.full_like(BIAS_Z, 2.0)), "galaxy_bias2": (BIAS_Z, np.full_like(BIAS_Z, 2.0))}))
+    assert eng.get_quadrature()["accuracy_target"] == 2
+    eng.close()
