@@ -212,9 +212,16 @@ def own_tables(eng, z):
 
 def extras(eng, tables):
     """the other configurations of BASELINE.json through the same C ABI, host buffers in and out (wall clock around the call,
-    second call of two): cfg2 (full-sky 2PCF, 100 separations x 50 mu at z = 1), cfg3 (redshift-averaged multipoles, den + rsd + len,
+    second call of two): cfg1 (flat-sky density + RSD multipoles), cfg2 (full-sky 2PCF, 100 separations x 50 mu at z = 1), cfg3 (redshift-averaged multipoles, den + rsd + len,
     8 bins x 200 separations) and the set-up path (table upload = host assembly + shared-memory table build + H2D)"""
     out = {}
+    # cfg1: the reference's own CPU-runnable case (DEFAULT_SETTINGS): flat-sky density + RSD multipoles at z = 1 on its separations
+    sep1 = np.arange(10.0, 201.0, 5.0) / H
+    eng.set_options(("den", "rsd"), flatsky_local=True)
+    eng.multipoles([1.0], sep1, [0, 2, 4])
+    t0 = time.perf_counter(); r = eng.multipoles([1.0], sep1, [0, 2, 4]); dt = time.perf_counter() - t0
+    out["cfg1_flatsky_multipoles"] = {"value": r.size / dt, "unit": "points/s", "points": int(r.size), "wall_ms": dt * 1e3, "kernel_ms": eng.last_timing()[0],
+                                      "workload": "cfg1: flat-sky density + RSD multipoles l = 0,2,4 at z_mean = 1.0, separations 10-200 Mpc/h (local terms only)"}
     sep2, mu2 = np.linspace(10.0, 300.0, 100) / H, np.linspace(-0.98, 0.98, 50)
     eng.set_options(ALL)
     eng.corrfunc([1.0], mu2, sep2)
