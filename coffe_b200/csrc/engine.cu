@@ -599,7 +599,7 @@ int apply_quadrature(coffe_b200_ctx *ctx, const bool want_pieces)
     if (target != COFFE_B200_TARGET_TOTAL && !ctx->o.len && (ctx->o.g4 || ctx->o.g5)) base.n_mu_panel_di = 6;
     const QuadConfig merged = merge_quadrature(base, ctx->user_q);
     if (!quadrature_valid(merged, kMaxPanels)) {
-        ctx->err = "quadrature sizes out of range (node counts 2..128; the line-of-sight panel plan must fit " + std::to_string(kMaxPanels) + " panels)";
+        ctx->err = "quadrature sizes out of range (node counts 2..128, nodes per line-of-sight panel 2..32; the line-of-sight panel plan must fit " + std::to_string(kMaxPanels) + " panels)";
         return COFFE_B200_EINVAL;
     }
     if (std::memcmp(&merged, &ctx->qc, sizeof(QuadConfig)) == 0 && target == ctx->target_in_force) return COFFE_B200_OK;

@@ -134,8 +134,8 @@ inline bool quadrature_valid(const QuadConfig &q, const int panel_capacity)
     if (!(q.panel_w > 0 && q.eps_min > 0 && q.tail_ratio > 1.0 && q.panel_du >= 0)) return false;
     if (max_panels(q) > panel_capacity) return false;
     return q.n_mu_ni >= 2 && q.n_mu_ni <= kMaxRule && q.n_mu_panel >= 2 && q.n_mu_panel <= kMaxRule &&
-           q.n_outer >= 0 && q.n_outer <= kMaxRule && q.n_panel_si >= 2 && q.n_panel_si <= kMaxRule &&
-           q.n_panel_di >= 2 && q.n_panel_di <= kMaxRule && q.n_z >= 1 && q.n_z <= kMaxRule &&
+           q.n_outer >= 0 && q.n_outer <= kMaxRule && q.n_panel_si >= 2 && q.n_panel_si <= 32 &&
+           q.n_panel_di >= 2 && q.n_panel_di <= 32 &&        /* a panel's nodes are the lanes of one group of a warp */ q.n_z >= 1 && q.n_z <= kMaxRule &&
            q.panel_w > 0 && q.panel_du >= 0 && q.eps_min > 0 && q.tail_ratio > 1.0 &&
            q.mu_rho0 > 0 && q.mu_panel_w > 0 && q.mu_du >= 0 &&
            q.n_mu_panel_di >= 2 && q.n_mu_panel_di <= kMaxRule && q.panel_w_di > 0 && q.panel_du_di >= 0 && q.mu_panel_w_di > 0 && q.tail_ratio_di > 1.0 &&

@@ -112,7 +112,7 @@ typedef struct coffe_b200_quadrature {
     int n_mu_panel;              /* nodes per r_perp panel of the mu rule of the integrated pieces */
     double mu_rho0, mu_panel_width, mu_uniform_extent;   /* r_perp panel plan [Mpc] */
     int n_outer;                 /* outer line-of-sight nodes (integrated x integrated); -1 = by separation */
-    int n_panel_si, n_panel_di;  /* nodes per line-of-sight panel */
+    int n_panel_si, n_panel_di;  /* nodes per line-of-sight panel (at most 32: a panel is walked by one group of lanes of a warp) */
     int n_z;                     /* nodes of the redshift average */
     double panel_width, panel_uniform_extent, eps_min, tail_ratio;   /* line-of-sight panel plan [Mpc] */
     /* the integrated x integrated piece has its own mu rule and inner panel plan (it is smoother and dominates the cost) */

@@ -810,6 +810,7 @@ def test_rules_follow_the_call_and_the_contributions(engine):
     """which defaults the zeros of coffe_b200_quadrature stand for: total-target rules with the mapped panels for
     mu-integrated totals when density / RSD are on; piece rules for pieces, for the 2-point function at a fixed mu (its value is
     compared with itself) and whenever no local term sets the scale; six mu nodes for potential terms without lensing"""
+    import coffe_b200
     engine.set_options(ALL)
     engine.set_quadrature()
     q = engine.get_quadrature()
@@ -832,11 +833,15 @@ def test_rules_follow_the_call_and_the_contributions(engine):
     assert q2["accuracy_target"] == 1 and q2["n_mu_panel_di"] == 6
     engine.set_options(["len", "g4"])
     assert engine.get_quadrature()["n_mu_panel_di"] == 5
+    with pytest.raises(coffe_b200.CoffeB200Error):  # a panel's nodes are the lanes of one group of a warp
+        engine.set_quadrature(n_panel_di=40)
+    with pytest.raises(coffe_b200.CoffeB200Error):
+        engine.set_quadrature(n_panel_si=33)
+    engine.set_quadrature()
     engine.set_options(["rsd", "len"])              # without the density term nothing keeps the integrated pieces small: piece rules
     assert engine.get_quadrature()["accuracy_target"] == 1
     engine.set_options(ALL)
     # biases that make the integrated terms large against the density term switch the automatic target off
-    import coffe_b200
     from coffe_b200.default_tables import load_default_tableset, BIAS_Z
     eng = coffe_b200.Engine(0)
     eng.set_options(ALL)
