@@ -815,7 +815,7 @@ def test_rules_follow_the_call_and_the_contributions(engine):
     engine.set_quadrature()
     q = engine.get_quadrature()
     assert q["accuracy_target"] == 2 and q["geometric_growth_di"] == 8.0 and q["tail_map_di"] == 2 and q["tail_ratio_di"] == 6.0
-    assert q["geometric_growth"] == 4.0 and q["tail_map"] == 2 and q["mu_switch_break_di"] == 2 and q["n_renorm"] == 12
+    assert q["geometric_growth"] == 4.0 and q["tail_map"] == 2 and q["mu_switch_break_di"] == 2 and q["n_renorm"] == 6
     assert q["n_outer_min"] == 25 and q["panel_width_di"] == 96.0 and q["n_panel_di"] == 6 and q["n_mu_panel_di"] == 4
     sep, mu = np.array([30.0, 150.0, 400.0]), np.array([-0.7, 0.2, 0.98])
     a = engine.corrfunc([1.0], mu, sep)
