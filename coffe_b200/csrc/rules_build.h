@@ -42,7 +42,7 @@ inline QuadConfig total_target_quadrature()
 {
     QuadConfig q = default_quadrature();
     q.n_panel_di = 6; q.n_mu_panel_di = 4; q.n_ren = 6;
-    q.n_outer_min = 25; q.n_outer_step = 15.0;
+    q.n_outer_min = 15; q.n_outer_step = 15.0;
     q.panel_w_di = 96.0;
     q.mu_growth = 8.0; q.mu_switch_di = 0;
     q.tail_log = 1; q.tail_ratio = 3.0;

@@ -646,8 +646,8 @@ def cfg5_grid():
 def test_cfg5_dense_self_convergence_default_vs_doubled_rules():
     """Every point of a dense subsample of the benchmarked cfg5 grid -- all 32 z_mean x (every 2nd separation + the separations
     within +-2 grid knots of every rule switch: the mu-panel plans change at r = 16, 32, 64, 96 ... 256, 384 Mpc, the log-mapped r_perp
-    panels of the local x integrated rule at r = 16 and 128 Mpc, and the outer rule max(25, 10 + r/15), rounded up to whole rounds of
-    five lane groups, steps at 225, 300 and 375 Mpc; the steps of the round-1 rule, 240 + 12 k, stay in the list) -- with the default
+    panels of the local x integrated rule at r = 16 and 128 Mpc, and the outer rule max(15, 10 + r/15), rounded up to whole rounds of
+    five lane groups, steps at 75, 150, 225, 300 and 375 Mpc; the steps of the round-1 rule, 240 + 12 k, stay in the list) -- with the default
     fixed-node rules against the
     same kernels with every node count doubled and every panel narrowed (FINE_RULES): each multipole within 1e-5 of the l = 0..4
     scale of the point.  ~16 700 (z, r) points, under the automatic accuracy target (the rules the benchmark times); a node count that
@@ -659,7 +659,7 @@ def test_cfg5_dense_self_convergence_default_vs_doubled_rules():
     eng.set_options(ALL)
     z, sep, ls = cfg5_grid()
     pick = set(range(0, 1000, 2)) | {999}           # every second separation of the grid: ~16 700 (z, r) points, half of cfg5
-    switches = [16.0, 32.0, 64.0, 96.0, 128.0, 160.0, 192.0, 224.0, 225.0, 240.0, 256.0, 300.0, 375.0, 384.0] + [240.0 + 12.0 * k for k in range(1, 18)]
+    switches = [16.0, 32.0, 64.0, 75.0, 96.0, 128.0, 150.0, 160.0, 192.0, 224.0, 225.0, 240.0, 256.0, 300.0, 375.0, 384.0] + [240.0 + 12.0 * k for k in range(1, 18)]
     for s in switches:
         j = int(np.searchsorted(sep, s))
         pick |= {k for k in range(j - 2, j + 2) if 0 <= k < 1000}
@@ -816,7 +816,7 @@ def test_rules_follow_the_call_and_the_contributions(engine):
     q = engine.get_quadrature()
     assert q["accuracy_target"] == 2 and q["geometric_growth_di"] == 8.0 and q["tail_map_di"] == 2 and q["tail_ratio_di"] == 6.0
     assert q["geometric_growth"] == 4.0 and q["tail_map"] == 2 and q["mu_switch_break_di"] == 2 and q["n_renorm"] == 6
-    assert q["n_outer_min"] == 25 and q["panel_width_di"] == 96.0 and q["n_panel_di"] == 6 and q["n_mu_panel_di"] == 4
+    assert q["n_outer_min"] == 15 and q["panel_width_di"] == 96.0 and q["n_panel_di"] == 6 and q["n_mu_panel_di"] == 4
     sep, mu = np.array([30.0, 150.0, 400.0]), np.array([-0.7, 0.2, 0.98])
     a = engine.corrfunc([1.0], mu, sep)
     engine.set_quadrature(accuracy_target=1)

@@ -10,7 +10,7 @@ from coffe_b200.default_tables import load_default_tableset
 eng = coffe_b200.Engine(0); eng.upload_tables(load_default_tableset()); eng.set_options(T.ALL)
 z, sep, ls = T.cfg5_grid()
 pick = set(range(0, 1000, 2)) | {999}
-switches = [16.0, 32.0, 64.0, 96.0, 128.0, 160.0, 192.0, 224.0, 225.0, 240.0, 256.0, 300.0, 375.0, 384.0] + [240.0 + 12.0 * k for k in range(1, 18)]
+switches = [16.0, 32.0, 64.0, 75.0, 96.0, 128.0, 150.0, 160.0, 192.0, 224.0, 225.0, 240.0, 256.0, 300.0, 375.0, 384.0] + [240.0 + 12.0 * k for k in range(1, 18)]
 for s in switches:
     j = int(np.searchsorted(sep, s)); pick |= {k for k in range(j - 2, j + 2) if 0 <= k < 1000}
 idx = np.array(sorted(pick))
