@@ -311,6 +311,18 @@ void hs_eval_counts(void *h, double z, double sep, double *out)
     }
 }
 
+/* mu rule of one piece (1 = local x integrated, 2 = integrated x integrated) for one separation under the quadrature configuration in
+   force: returns the node count, fills mu / w (capacity cap) */
+int hs_mu_rule(void *h, double sep, int piece, int half_only, int cap, double *mu_out, double *w_out)
+{
+    HostSim *s = (HostSim *)h;
+    std::vector<double> mu, w;
+    build_mu_rule(s->qc, sep, mu, w, piece, half_only != 0);
+    const int n = (int)mu.size();
+    for (int i = 0; i < n && i < cap; ++i) { mu_out[i] = mu[i]; w_out[i] = w[i]; }
+    return n;
+}
+
 int hs_n_mu(void *h, double sep)
 {
     HostSim *s = (HostSim *)h;

@@ -84,6 +84,13 @@ class HostSim:
         self.lib.hs_n_mu.restype = C.c_int
         return self.lib.hs_n_mu(self.h, C.c_double(sep))
 
+    def mu_rule(self, sep, piece, half_only=False):
+        """(mu, w) of the mu rule of piece 1 (local x integrated) or 2 (integrated x integrated) at this separation"""
+        mu, w = np.zeros(4096), np.zeros(4096)
+        self.lib.hs_mu_rule.restype = C.c_int
+        n = self.lib.hs_mu_rule(self.h, C.c_double(sep), C.c_int(piece), C.c_int(int(half_only)), C.c_int(4096), capi.ptr(mu), capi.ptr(w))
+        return mu[:n].copy(), w[:n].copy()
+
     def eval_counts(self, z, sep):
         """(SI, DI) integrand evaluations of the fixed-node rules at one (z, sep), summed over the mu items"""
         out = np.zeros(2)

@@ -240,6 +240,34 @@ def test_ridge_units_tile_the_line_of_sight_and_integrate_a_cusp():
     assert all(v < 5e-8 for v in worst.values()), worst
 
 
+def test_mu_rules_are_normalised_and_integrate_smooth_functions(ref, tableset):
+    """rules_build.h build_mu_rule: panels in r_perp with the nodes in phi, or in ln(r_perp) on the log-mapped geometric panels (local x
+    integrated piece), for the measure dmu / 2: weights sum to 1, low Legendre moments vanish, a function with the logarithmic
+    small-r_perp behaviour of the integrated pieces is integrated to the accuracy the panel counts promise; the half rule (mu > 0 with
+    doubled weights) agrees with the full one on even functions"""
+    from scipy.special import eval_legendre
+    from scipy.integrate import quad
+    hs = hostsim_bridge.HostSim(ref, ["len"], tableset=tableset)
+    settings = {"piece rules": {}, "total-target rules": dict(mu_geometric_growth=8.0, mu_rho0=8.0, mu_panel_width=64.0, n_mu_panel=7, n_mu_panel_di=4,
+                                                            mu_switch_break_di=2),
+                "doubling panels": dict(mu_geometric_growth=1.0, mu_geometric_growth_di=1.0)}
+    for name, kw in settings.items():
+        hs.set_quadrature(**kw)
+        for sep in (12.0, 15.9, 16.1, 40.0, 127.0, 129.0, 200.0, 448.0):
+            for piece in (1, 2):
+                mu, w = hs.mu_rule(sep, piece)
+                assert abs(w.sum() - 1.0) < (2e-5 if piece == 2 else 2e-7), (name, sep, piece, w.sum() - 1.0)
+                for l in (1, 2, 3, 4):
+                    assert abs(np.sum(w * eval_legendre(l, mu))) < (2e-4 if piece == 2 else 2e-6), (name, sep, piece, l)
+                # logarithmic in r_perp = sep sqrt(1 - mu^2), smooth otherwise
+                f = lambda m: np.log(1.0 + sep * np.sqrt(1.0 - m * m)) * (1.0 + 0.3 * m * m)
+                want = quad(lambda m: 0.5 * f(m), -1.0, 1.0, epsabs=0, epsrel=1e-12, limit=400, points=[-0.999, 0.999])[0]
+                tol = 2e-4 if piece == 2 else 5e-6         # 4-5 nodes per panel (wide panels in phi just below a break) against 7-8
+                assert abs(np.sum(w * f(mu)) / want - 1) < tol, (name, sep, piece, np.sum(w * f(mu)) / want - 1)
+                mh, wh = hs.mu_rule(sep, piece, half_only=True)
+                assert abs(np.sum(wh * f(mh)) - np.sum(w * f(mu))) < 1e-14 * abs(want) * len(mu)
+
+
 def test_packed_knot_slopes_round_to_nearest():
     """compact.cuh: a scaled slope is stored as the upper 32 bits of its double, rounded to nearest: relative error <= 2^-21"""
     import ctypes as C
