@@ -493,7 +493,8 @@ def main():
                        "sharding": f"contiguous cost-balanced blocks of (z, r) items over {world} GPU(s), tables replicated, blocks gathered device to device "
                                    f"by the library's NCCL calls on the compute stream" + (" (inside every timed step)" if world > 1 else " (none at N = 1)"),
                        "block_items": [bounds[r + 1] - bounds[r] for r in range(world)],
-                       "l2_policy": "compute-bound FP64 kernel; working set (tables 2.6 MB) is L2-resident by design, no HBM streaming to flush",
+                       "l2_policy": "FP64 kernels bound by instruction issue; the spline tables (2.6 MB) are L2 / shared-memory resident by design, the per-item set-up "
+                                    "records (0.9 GB per step, larger than L2) are rewritten and streamed from HBM every step",
                        "quadrature": eng.get_quadrature(), "wall_ms_per_step": wall_ms_max / args.steps},
             "roofline": {"bound": "fp64", "kernel": "di_items_smem_kernel", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved / peak_tf if peak_tf and achieved else None,
