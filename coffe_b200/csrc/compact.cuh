@@ -27,11 +27,10 @@ namespace coffe {
 
 static const int kKnotStride = 18;      /* doubles per knot in the builder's working copy: 9 x {f, h f'}: the eight I^n_l of the family, then I^4_0
                                            (zero without the divergent tables) */
-/* A knot as it is staged in shared memory: the nine values as doubles, the nine scaled slopes h f' as the upper 32 bits of their
-   doubles (20-bit mantissa, rounded to nearest by the builder; the low word is zero when the value is rebuilt, which costs no
-   conversion instruction), 4 bytes of padding: 112 B instead of 144.  The integrated kernels run at 81 % of the shared-memory /
+/* A knot as it is staged in shared memory: the nine values as doubles, the nine scaled slopes h f' as floats
+   (24-bit mantissa, rounded to nearest by the builder; one conversion instruction to unpack), 4 bytes of padding: 112 B instead of 144.  The integrated kernels run at 81 % of the shared-memory /
    L1 data pipe (profiles/r1_di_kernel_cfg5_v40_ncu.txt), so bytes per lookup are what they pay for.  A slope enters the Hermite
-   form with weight |h10|, |h11| <= 4/27 and |h f'| is a fraction of the local envelope, so its 2.4e-7 relative rounding moves
+   form with weight |h10|, |h11| <= 4/27 and |h f'| is a fraction of the local envelope, so its 6e-8 relative rounding moves
    the interpolant by < 4e-8 of the envelope -- the builder's error check (region_fill) runs on the rounded slopes and
    reports it inside max_rel_error.  A 112-byte stride is 7 bank groups of 16 bytes: neighbouring knots fall on different ones. */
 static const int kKnotBytes = 112;
@@ -64,17 +63,26 @@ inline int hi_word(const double v) { long long b; memcpy(&b, &v, 8); return (int
 inline double from_hi_word(const int hi) { const long long b = (long long)(unsigned int)hi << 32; double v; memcpy(&v, &b, 8); return v; }
 #endif
 
-/* h f' as stored: the double rounded to its upper 32 bits */
+/* h f' as stored: a float (24-bit mantissa: 6e-8 relative, it enters the Hermite form with weight <= 4/27), one conversion
+   instruction to unpack.  (Until the end of round 2: the upper 32 bits of the double, 20 mantissa bits, unpacked by two moves.) */
 COFFE_HD int slope_word(const double v)
 {
+    const float f = (float)v;
 #if defined(__CUDA_ARCH__)
-    const long long b = __double_as_longlong(v);
+    return __float_as_int(f);
 #else
-    long long b; memcpy(&b, &v, 8);
+    int w; memcpy(&w, &f, 4); return w;
 #endif
-    return (int)((unsigned long long)(b + 0x80000000LL) >> 32);
 }
-COFFE_HD double slope_rounded(const double v) { return from_hi_word(slope_word(v)); }
+COFFE_HD double slope_unpack(const int w)
+{
+#if defined(__CUDA_ARCH__)
+    return (double)__int_as_float(w);
+#else
+    float f; memcpy(&f, &w, 4); return (double)f;
+#endif
+}
+COFFE_HD double slope_rounded(const double v) { return slope_unpack(slope_word(v)); }
 
 /* the 16-byte words of a packed knot */
 struct KnotWord { int x, y, z, w; };
@@ -113,10 +121,10 @@ COFFE_HD void knot_group_eval(const unsigned char *k0, const unsigned char *k1, 
     KnotWord s0, s1;
     knot_words(k0 + g * kKnotGroupBytes + 32, s0);
     knot_words(k1 + g * kKnotGroupBytes + 32, s1);
-    out[0] = hermite_eval(hb, a0.x, from_hi_word(s0.x), b0.x, from_hi_word(s1.x));
-    out[1] = hermite_eval(hb, a0.y, from_hi_word(s0.y), b0.y, from_hi_word(s1.y));
-    out[2] = hermite_eval(hb, a1.x, from_hi_word(s0.z), b1.x, from_hi_word(s1.z));
-    out[3] = hermite_eval(hb, a1.y, from_hi_word(s0.w), b1.y, from_hi_word(s1.w));
+    out[0] = hermite_eval(hb, a0.x, slope_unpack(s0.x), b0.x, slope_unpack(s1.x));
+    out[1] = hermite_eval(hb, a0.y, slope_unpack(s0.y), b0.y, slope_unpack(s1.y));
+    out[2] = hermite_eval(hb, a1.x, slope_unpack(s0.z), b1.x, slope_unpack(s1.z));
+    out[3] = hermite_eval(hb, a1.y, slope_unpack(s0.w), b1.y, slope_unpack(s1.w));
 }
 
 /* the ninth function (I^4_0) */
@@ -126,7 +134,7 @@ COFFE_HD double knot_tail_eval(const unsigned char *k0, const unsigned char *k1,
     KnotWord t0, t1;
     knot_words(k0 + 96, t0);
     knot_words(k1 + 96, t1);
-    return hermite_eval(hb, word_pair(t0.x, t0.y), from_hi_word(t0.z), word_pair(t1.x, t1.y), from_hi_word(t1.z));
+    return hermite_eval(hb, word_pair(t0.x, t0.y), slope_unpack(t0.z), word_pair(t1.x, t1.y), slope_unpack(t1.z));
 }
 
 /* view of a staged blob (shared memory on the device, host memory in the CPU harness) */

@@ -269,14 +269,14 @@ def test_mu_rules_are_normalised_and_integrate_smooth_functions(ref, tableset):
 
 
 def test_packed_knot_slopes_round_to_nearest():
-    """compact.cuh: a scaled slope is stored as the upper 32 bits of its double, rounded to nearest: relative error <= 2^-21"""
+    """compact.cuh: a scaled slope is stored as a float, rounded to nearest: relative error <= 2^-24"""
     import ctypes as C
     lib = C.CDLL(str(hostsim_bridge.LIB))
     lib.hs_slope_rounded.restype = C.c_double
     lib.hs_slope_rounded.argtypes = [C.c_double]
     rng = np.random.default_rng(3)
-    v = np.concatenate([rng.normal(size=2000) * 10.0 ** rng.uniform(-30, 30, 2000), [0.0, 1.0, -1.0, 1.0 + 2.0 ** -21, 1.0 + 2.0 ** -20]])
+    v = np.concatenate([rng.normal(size=2000) * 10.0 ** rng.uniform(-30, 30, 2000), [0.0, 1.0, -1.0, 1.0 + 2.0 ** -24, 1.0 + 2.0 ** -23]])
     got = np.array([lib.hs_slope_rounded(float(x)) for x in v])
     nz = v != 0
-    assert np.all(np.abs(got[nz] / v[nz] - 1) <= 2.0 ** -21) and got[~nz].tolist() == [0.0]
-    assert lib.hs_slope_rounded(1.0) == 1.0 and lib.hs_slope_rounded(1.0 + 2.0 ** -20) == 1.0 + 2.0 ** -20
+    assert np.all(np.abs(got[nz] / v[nz] - 1) <= 2.0 ** -24) and got[~nz].tolist() == [0.0]
+    assert lib.hs_slope_rounded(1.0) == 1.0 and lib.hs_slope_rounded(1.0 + 2.0 ** -23) == 1.0 + 2.0 ** -23
