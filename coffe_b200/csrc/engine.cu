@@ -561,6 +561,7 @@ Rules make_rules(const coffe_b200_ctx *ctx)
     q.tail_lnr_di = ctx->qc.tail_log_di ? std::log(ctx->qc.tail_ratio_di) : 0.0;
     q.geo_L = ctx->qc.geo_growth > 1.0 ? std::log(ctx->qc.geo_growth) : 0.0;
     q.geo_L_di = ctx->qc.geo_growth_di > 1.0 ? std::log(ctx->qc.geo_growth_di) : 0.0;
+    rules_reciprocals(q);
     return q;
 }
 

@@ -30,8 +30,15 @@ struct Rules {
     int geo_shift_di;
     int n_ren;                       /* nodes of the inner rule of renormalization(l1, l2) (di_fast.cuh: di_ren_smooth_partial), even */
     double tail_lnr, tail_lnr_di;    /* log of the tail ratio when the tail panels carry their nodes in log(d) (quadrature.cuh); 0 = in d */
+    double inv_w, inv_w_di, inv_geo_L, inv_geo_L_di;   /* reciprocals of the panel widths and of geo_L (0 where that is 0): rules_reciprocals */
     double geo_L, geo_L_di;          /* log of the growth factor of the sinh-map geometric panels (quadrature.cuh); 0 = doubling panels */
 };
+
+inline void rules_reciprocals(Rules &q)
+{
+    q.inv_w = 1.0 / q.panel_w_mpc; q.inv_w_di = 1.0 / q.panel_w_di;
+    q.inv_geo_L = q.geo_L > 0.0 ? 1.0 / q.geo_L : 0.0; q.inv_geo_L_di = q.geo_L_di > 0.0 ? 1.0 / q.geo_L_di : 0.0;
+}
 
 /* panels one ridge_integrate call can hold in its scratch area (engine.cu checks the configured plan) */
 static const int kMaxPanels = 256;
@@ -178,7 +185,7 @@ COFFE_HD double si_ren_smooth_partial(const Renorm2DView &r2d, const double2 *lo
 
 COFFE_HD PanelPlan si_plan(const Rules &q, const Geometry &g, const SIHalf &h)
 {
-    return panel_plan(h.cs * sqrt(g.s2), q.eps_min, q.panel_w_mpc, q.panel_du, q.tail_ratio, q.rpow, 1, q.geo_L, q.tail_lnr);
+    return panel_plan(h.cs * sqrt(g.s2), q.eps_min, q.panel_w_mpc, q.panel_du, q.tail_ratio, q.rpow, 1, q.geo_L, q.tail_lnr, 0.0, q.inv_w, q.inv_geo_L);
 }
 
 template <class TA>

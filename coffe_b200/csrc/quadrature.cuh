@@ -23,7 +23,7 @@ static const int kMaxTail = 48;
 
 struct PanelPlan {
     const double *rpow;
-    double eps, W, ratio;
+    double eps, inv_eps, W, inv_W, ratio;
     int shift;      /* log2 of the growth factor of the geometric panels (1: doubling, 2: x4) */
     int J;          /* B_k = eps 2^(shift (k-1)) for 1 <= k <= J */
     int M;          /* B_k = B_J + (k-J) W for J < k <= J+M */
@@ -35,15 +35,32 @@ struct PanelPlan {
                        the singularity of d^-p at the origin (rho = 3.7 for ratio 3, 2 for ratio 9) */
 };
 
+/* asinh(x), x >= 0, and (up / lo)^(1/4): written on the reciprocal square root, which costs the device a third of a square root
+   plus a division (the plan and the clipped last panels ask for them once or twice per line of sight) */
+COFFE_HD double asinh_pos(const double x)
+{
+    const double s = fma(x, x, 1.0);
+    return log(fma(s, COFFE_RSQRT(s), x));
+}
+COFFE_HD double fourth_root_ratio(const double up, const double lo)
+{
+    const double il = COFFE_RSQRT(lo), x = up * il * il;        /* up / lo */
+    const double s = x * COFFE_RSQRT(x);                        /* its square root */
+    return s * COFFE_RSQRT(s);
+}
+
 COFFE_HD PanelPlan panel_plan(double eps, const double eps_min, const double W, const double Du, const double ratio, const double *rpow,
-                              const int shift = 1, const double geo_L = 0.0, const double tail_lnr = 0.0)
+                              const int shift = 1, const double geo_L = 0.0, const double tail_lnr = 0.0, double inv_eps = 0.0,
+                              double inv_W = 0.0, double inv_geo_L = 0.0 /* reciprocals the caller holds already (0: computed here) */)
 {
     PanelPlan p;
     p.lnr = tail_lnr;
     p.rpow = rpow;
     p.shift = shift;
-    if (eps < eps_min) eps = eps_min;
-    p.eps = eps; p.W = W; p.ratio = ratio;
+    if (eps < eps_min) { eps = eps_min; inv_eps = 0.0; }
+    if (!(inv_eps > 0.0)) inv_eps = 1.0 / eps;
+    if (!(inv_W > 0.0)) inv_W = 1.0 / W;
+    p.eps = eps; p.inv_eps = inv_eps; p.W = W; p.inv_W = inv_W; p.ratio = ratio;
     p.L = 0.0;
     int J = 0;
     double b = 0.0;
@@ -51,8 +68,8 @@ COFFE_HD PanelPlan panel_plan(double eps, const double eps_min, const double W, 
         /* sinh map: f(sqrt(d^2 + eps^2)) = f(eps cosh t) under d = eps sinh t has its singularities at t = +- i pi/2 whatever the
            panel, so a Gauss-Legendre rule in t converges like rho^(-2n) with (rho - 1/rho) = 2 pi / L on a panel of length L in t:
            rho = 4.7 for L = ln 4.  The region [0, W] is cut into J equal panels in t, the fewest with L <= geo_L. */
-        const double x = W / eps, T = log(x + sqrt(fma(x, x, 1.0)));       /* asinh(x), x > 1 */
-        J = (int)ceil(T / geo_L);
+        const double T = asinh_pos(W * inv_eps);
+        J = (int)ceil(inv_geo_L > 0.0 ? T * inv_geo_L : T / geo_L);
         if (J < 1) J = 1;
         p.L = T / J;
         b = W;
@@ -66,7 +83,7 @@ COFFE_HD PanelPlan panel_plan(double eps, const double eps_min, const double W, 
     }
     p.J = J; p.BJ = b;
     int M = 0;
-    if (b < Du) M = (int)ceil((Du - b) / W);
+    if (b < Du) M = (int)ceil((Du - b) * inv_W);
     p.M = M; p.BJM = b + M * W;
     return p;
 }
@@ -98,10 +115,9 @@ COFFE_HD int panel_count(const PanelPlan &p, const double b)
         while (n < kMaxTail - 1 && p.BJM * p.rpow[n] < b) ++n;      /* smallest n with B_(k+n) >= b */
         return k + n;
     }
-    if (b > p.BJ || p.J == 0) return p.J + (int)ceil((b - p.BJ) / p.W);
+    if (b > p.BJ || p.J == 0) return p.J + (int)ceil((b - p.BJ) * p.inv_W);
     if (COFFE_LIKELY(p.L > 0.0)) {
-        const double xb = b / p.eps;
-        k = (int)ceil(log(xb + sqrt(fma(xb, xb, 1.0))) / p.L);         /* asinh */
+        k = (int)ceil(asinh_pos(b * p.inv_eps) / p.L);
         return k < 1 ? 1 : k > p.J ? p.J : k;
     }
     double e = p.eps;
@@ -267,8 +283,8 @@ COFFE_HD int ridge_unit_node(RidgeUnits &u, const int iu, double &d, double &wgt
     const int map = panel_map(plan, k);
     if (u.ordinary && map == 1) {
         /* sinh-map panel [k L, (k + 1) L] in t = asinh(d / eps); a last panel ends at the end of its line of sight */
-        const double b = neg ? u.b_neg : u.b_pos, xb = b / plan.eps;
-        const double s0 = k * plan.L, s1 = e < 2 ? fmin((k + 1) * plan.L, log(xb + sqrt(fma(xb, xb, 1.0)))) : (k + 1) * plan.L;
+        const double b = neg ? u.b_neg : u.b_pos;
+        const double s0 = k * plan.L, s1 = e < 2 ? fmin((k + 1) * plan.L, asinh_pos(b * plan.inv_eps)) : (k + 1) * plan.L;
         if (!(s1 > s0)) return 0;
         const double h = s1 - s0, ex = exp(fma(h, xj, s0)), ie = 1.0 / ex;
         d = (0.5 * plan.eps) * (ex - ie); wgt = (0.5 * plan.eps) * (ex + ie) * (h * wj);
@@ -283,8 +299,8 @@ COFFE_HD int ridge_unit_node(RidgeUnits &u, const int iu, double &d, double &wgt
     if (map == 2) {
         if (lo_cl || up_cl) {
             /* clipped tail panel [lo, up]: d = lo (1 + a x)^4 reaches up at x = 1 with a = (up/lo)^(1/4) - 1.  Like log(d) it keeps
-               d^-p far from its singularity (rho = 9 at up/lo = 6) at the price of two square roots instead of log and exp */
-            const double a4 = sqrt(sqrt(up / lo)) - 1.0, t = fma(a4, xj, 1.0), t2 = t * t;
+               d^-p far from its singularity (rho = 9 at up/lo = 6) at the price of a fourth root instead of log and exp */
+            const double a4 = fourth_root_ratio(up, lo) - 1.0, t = fma(a4, xj, 1.0), t2 = t * t;
             d = lo * (t2 * t2); wgt = (4.0 * a4 * lo * wj) * (t2 * t);
         }
         else { d = lo * u.pj; wgt = d * (plan.lnr * wj); }

@@ -53,6 +53,7 @@ static void set_rules(HostSim *s)
     q.tail_lnr_di = s->qc.tail_log_di ? std::log(s->qc.tail_ratio_di) : 0.0;
     q.geo_L = s->qc.geo_growth > 1.0 ? std::log(s->qc.geo_growth) : 0.0;
     q.geo_L_di = s->qc.geo_growth_di > 1.0 ? std::log(s->qc.geo_growth_di) : 0.0;
+    rules_reciprocals(q);
 }
 
 extern "C" {
