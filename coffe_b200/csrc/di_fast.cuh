@@ -37,17 +37,17 @@ COFFE_HD DIFast di_fast_setup(const DIConst &k, const Geometry &g)
 {
     DIFast f;
     const double c = g.c, cm = -g.s2, a = k.k_ll * k.h4;
-    f.k00 = a * 2 * cm / 5.;
-    f.k20 = a * 4 * c / 3.;
-    f.k11a = a * 4 * c / 15.;
-    f.k11b = a * 24 * c * c / 15.;
-    f.k02a = a * 4 * cm / 7.;
-    f.k02b = a * 6 * cm * c / 7.;
+    f.k00 = a * 2 * cm * (1.0 / 5.0);
+    f.k20 = a * 4 * c * (1.0 / 3.0);
+    f.k11a = a * 4 * c * (1.0 / 15.0);
+    f.k11b = a * 24 * c * c * (1.0 / 15.0);
+    f.k02a = a * 4 * cm * (1.0 / 7.0);
+    f.k02b = a * 6 * cm * c * (1.0 / 7.0);
     f.k13c = a * 2 * c * cm;
-    f.k04a = a * 6 * cm / 35.;
-    f.k04b = a * 30 * c * cm / 35.;
+    f.k04a = a * 6 * cm * (1.0 / 35.0);
+    f.k04b = a * 30 * c * cm * (1.0 / 35.0);
     f.k04c = a * cm * cm;
-    f.k_ll0 = a * 4.; f.k_ll1 = a * 24. / 15.;
+    f.k_ll0 = a * 4.; f.k_ll1 = a * 24. * (1.0 / 15.0);
     f.two_c = 2 * c; f.s2 = g.s2;
     f.k_4l = k.k_4l * k.h4; f.k_5la = k.k_5la * k.h4; f.k_5lb = k.k_5lb * k.h4;
     f.k_44 = k.k_44 * k.h4; f.k_55 = k.k_55 * k.h4; f.k_45a = k.k_45a * k.h4; f.k_45b = k.k_45b * k.h4;

@@ -185,7 +185,9 @@ COFFE_HD double si_ren_smooth_partial(const Renorm2DView &r2d, const double2 *lo
 
 COFFE_HD PanelPlan si_plan(const Rules &q, const Geometry &g, const SIHalf &h)
 {
-    return panel_plan(h.cs * sqrt(g.s2), q.eps_min, q.panel_w_mpc, q.panel_du, q.tail_ratio, q.rpow, 1, q.geo_L, q.tail_lnr, 0.0, q.inv_w, q.inv_geo_L);
+    /* impact parameter cs sin(theta) and its inverse from one reciprocal square root (as di_plan) */
+    const double e2 = fmax(h.cs * h.cs * g.s2, q.eps_min * q.eps_min), ie = COFFE_RSQRT(e2);
+    return panel_plan(e2 * ie, q.eps_min, q.panel_w_mpc, q.panel_du, q.tail_ratio, q.rpow, 1, q.geo_L, q.tail_lnr, ie, q.inv_w, q.inv_geo_L);
 }
 
 template <class TA>

@@ -318,33 +318,33 @@ COFFE_HD SIHalf si_half_setup(const Options &o, const Geometry &g, const EndVals
                     - p5 I04 / (35 R^4)                                                                     src/functions.c:2059-2390 */
         /* d1-len:  2 (c (l^2 - 2 cs^2) + cs l (2 tc - 1)) I11 / 15 + 2 c I20 / 3
                     - (4 cs^4 c - cs^3 (c^2 + 9) l + cs^2 c (c^2 + 5) l^2 - 2 cs (tc - 2) l^3 - 2 c l^4) I13 / (15 R^2)    :2490-2560 */
-        h.p00[0] = -ar * 6 * cs * c / 15.; h.p00[1] = ar * (1 + 3 * tc) / 15.;
-        h.p02[0] = -ar * 6 * cs3 * c / 21.;
-        h.p02[1] = ar * cs2 * (9 * c2 + 11) / 21. - ad * cs2 * s2;
-        h.p02[2] = -ar * cs * c * (3 * tc + 19) / 21.;
-        h.p02[3] = ar * 2 * (3 * tc + 1) / 21.;
-        h.p13[0] = -a1 * 4 * cs2 * cs2 * c / 15.;
-        h.p13[1] = a1 * cs3 * (c2 + 9) / 15.;
-        h.p13[2] = -a1 * cs2 * c * (c2 + 5) / 15.;
-        h.p13[3] = a1 * 2 * cs * (tc - 2) / 15.;
-        h.p13[4] = a1 * 2 * c / 15.;
+        h.p00[0] = -ar * 6 * cs * c * (1.0 / 15.0); h.p00[1] = ar * (1 + 3 * tc) * (1.0 / 15.0);
+        h.p02[0] = -ar * 6 * cs3 * c * (1.0 / 21.0);
+        h.p02[1] = ar * cs2 * (9 * c2 + 11) * (1.0 / 21.0) - ad * cs2 * s2;
+        h.p02[2] = -ar * cs * c * (3 * tc + 19) * (1.0 / 21.0);
+        h.p02[3] = ar * 2 * (3 * tc + 1) * (1.0 / 21.0);
+        h.p13[0] = -a1 * 4 * cs2 * cs2 * c * (1.0 / 15.0);
+        h.p13[1] = a1 * cs3 * (c2 + 9) * (1.0 / 15.0);
+        h.p13[2] = -a1 * cs2 * c * (c2 + 5) * (1.0 / 15.0);
+        h.p13[3] = a1 * 2 * cs * (tc - 2) * (1.0 / 15.0);
+        h.p13[4] = a1 * 2 * c * (1.0 / 15.0);
         /* the reference's quintic (functions.c:2205-2214) cancels from O(chi^5) to O(chi r^4); expanded in d = l - cs and
            w = 1 - cos(theta) it reads
              -4 d^4 (2 cs + d) + w (4 d^2 (12 cs^3 + 23 cs^2 d + 15 cs d^2 + 3 d^3)
                 + w (-6 l^2 (2 cs^3 + 6 cs^2 d + 6 cs d^2 + d^3) + w (2 cs l^2 (2 cs^2 + 4 cs d + 3 d^2) + w cs^2 l^3))),
            which collected in powers of d gives the coefficients below (every bracket a polynomial in the small w) */
-        const double k35 = -ar / 35.;
+        const double k35 = -ar * (1.0 / 35.0);
         h.p04[0] = k35 * cs3 * cs2 * w * w * (w - 2) * (w + 6);
         h.p04[1] = k35 * cs2 * cs2 * w * w * (w * (3 * w + 16) - 60);
         h.p04[2] = k35 * cs3 * w * (w * (w * (3 * w + 26) - 120) + 48);
         h.p04[3] = k35 * cs2 * w * (w * (w * (w + 20) - 114) + 92);
         h.p04[4] = k35 * 2 * cs * (w * (w * (3 * w - 24) + 30) - 4);
         h.p04[5] = k35 * -2 * (w * (3 * w - 6) + 2);
-        h.p04a[0] = ar * 4 * cs / 35.; h.p04a[1] = ar * 4 / 35.;
-        h.p11[0] = ad * 2 * cs * c - a1 * 4 * c * cs2 / 15.;
-        h.p11[1] = a1 * 2 * cs * (2 * tc - 1) / 15.;
-        h.p11[2] = a1 * 2 * c / 15.;
-        h.p20 = a1 * 2 * c / 3.;
+        h.p04a[0] = ar * 4 * cs * (1.0 / 35.0); h.p04a[1] = ar * 4 * (1.0 / 35.0);
+        h.p11[0] = ad * 2 * cs * c - a1 * 4 * c * cs2 * (1.0 / 15.0);
+        h.p11[1] = a1 * 2 * cs * (2 * tc - 1) * (1.0 / 15.0);
+        h.p11[2] = a1 * 2 * c * (1.0 / 15.0);
+        h.p20 = a1 * 2 * c * (1.0 / 3.0);
         h.p31 = ap * 2 * cs * c;
         h.p22 = -ap * cs2 * s2;
     }
@@ -408,7 +408,8 @@ COFFE_HD double si_half_body(const TA &t, const SIHalf &h, const Geometry &g, co
         if (h.need_ren)                                                                             /* :1524-1556 */
             ren = SPLIT_REN ? ((rr == 0.0) ? t.ren0(l) + t.ren2d(l, cs) : I[N_ITAB])
                             : ((rr == 0.0) ? t.ren0(l) : I[N_ITAB] - t.ren2d(l, cs));
-        const double b_rsd = (2 * rr / 3. - s2 * l * l) * I[I22] - I[I20] / 3.;
+        /* thirds as multiplications: a division by a constant stays a division (a 15-instruction serial chain) without fast-math */
+        const double b_rsd = fma(rr, 2.0 / 3.0, -(s2 * l * l)) * I[I22] - I[I20] * (1.0 / 3.0);
         const double b_d1 = (l * c - cs) * I[I31];
         if (h.any_g4) res += W * (h.g4_i20 * I[I20] + h.g4_rsd * b_rsd + h.g4_d1 * b_d1 + h.g4_ren * ren);
         if (h.any_g5) res += V * (h.g5_i20 * Wa * I[I20] + W * (h.g5_rsd * b_rsd + h.g5_d1 * b_d1 + h.g5_ren * ren));
