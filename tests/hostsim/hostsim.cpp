@@ -128,6 +128,10 @@ void hs_panel_plan(double eps, double eps_min, double W, double Du, double ratio
     out[6] = J; out[7] = bj;
 }
 
+/* the two closed forms the panel plan evaluates on the reciprocal square root (quadrature.cuh) */
+double hs_asinh_pos(double x) { return asinh_pos(x); }
+double hs_fourth_root_ratio(double up, double lo) { return fourth_root_ratio(up, lo); }
+
 /* a slope as the packed knots store it (compact.cuh) */
 double hs_slope_rounded(double v) { return slope_rounded(v); }
 

@@ -204,6 +204,26 @@ def test_panel_plan_closed_form_and_break_counts():
     assert n_diff <= 4
 
 
+def test_plan_closed_forms_on_the_reciprocal_square_root():
+    """quadrature.cuh: asinh(x) = log(x + s rsqrt(s)), s = x^2 + 1, and (up/lo)^(1/4) from three reciprocal square roots (what the
+    panel plan and the clipped tail panels evaluate instead of square roots and divisions) agree with the library functions to
+    rounding over the range the plans see (W / eps from 1 to 1e5, panel ratios up to 6)"""
+    import ctypes as C
+    lib = C.CDLL(str(hostsim_bridge.LIB))
+    lib.hs_asinh_pos.restype = C.c_double
+    lib.hs_asinh_pos.argtypes = [C.c_double]
+    lib.hs_fourth_root_ratio.restype = C.c_double
+    lib.hs_fourth_root_ratio.argtypes = [C.c_double, C.c_double]
+    rng = np.random.default_rng(17)
+    x = 10.0 ** rng.uniform(-0.3, 6, 3000)            # the plan asks for x = W / eps > 1 (below 1 the log form loses digits like log1p)
+    got = np.array([lib.hs_asinh_pos(float(v)) for v in x])
+    assert np.max(np.abs(got / np.arcsinh(x) - 1)) < 2e-15
+    lo = 10.0 ** rng.uniform(-2, 4, 3000)
+    up = lo * 10.0 ** rng.uniform(0, 1, 3000)
+    got = np.array([lib.hs_fourth_root_ratio(float(u), float(l)) for u, l in zip(up, lo)])
+    assert np.max(np.abs(got / (up / lo) ** 0.25 - 1)) < 4e-16 * 4
+
+
 def test_ridge_units_tile_the_line_of_sight_and_integrate_a_cusp():
     """quadrature.cuh RidgeUnits (the unit walk of both integration kernels): with every panel layout -- doubling panels in d, sinh-map
     panels, tails in d or in ln d, closest approach inside, at the edge of and beyond the line of sight -- the units cover [0, hi]
