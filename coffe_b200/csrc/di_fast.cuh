@@ -102,17 +102,17 @@ COFFE_HD DIShared di_shared(const TA &ta, const DIFast &f, const DIOuter &o, con
 }
 
 /* what the inner loop needs to read the tables of the second line of sight */
-template <class TA>
+template <class TA, class LP = const double2 *>
 struct DISideCtx {
     const TA *ta;
-    const double2 *los; int los_n; double los_inv_h;
+    LP los; int los_n; double los_inv_h;        /* Hermite knots (const double2 *) or the staged records (const LosRec *) */
     const Renorm2DView *r2d;
 };
 
 /* integrand at lambda_2 = l2 (per unit lambda_2, H0^4 and all amplitudes included).  ALL: every group of terms is
    on and R^2 > 1e-12 is guaranteed by the caller (squared impact parameter above it), so the body is branch-free. */
-template <bool ALL, class TA>
-COFFE_HD double di_side(const DISideCtx<TA> &cx, const DIFast &f, const DIOuter &o, const DIShared &s, const double l2)
+template <bool ALL, class TA, class LP>
+COFFE_HD double di_side(const DISideCtx<TA, LP> &cx, const DIFast &f, const DIOuter &o, const DIShared &s, const double l2)
 {
     const double4 los2 = los_eval(cx.los, cx.los_n, cx.los_inv_h, l2);
     const double ll = o.l1 * l2, e2 = f.chi2 - l2;
@@ -150,7 +150,8 @@ COFFE_HD double di_side(const DISideCtx<TA> &cx, const DIFast &f, const DIOuter 
    rule -- two Gauss-Legendre panels split at the diagonal, n_ren nodes together (one per lane on the device) -- instead of riding on
    the ridge panels: against a composite rule on the cells of the grid 2 x 16 nodes leave 4e-8 of this half (CPU experiment, three
    distances), i.e. < 1e-6 of the difference.  Returns this lane's share of - integral dl2 W2 (B0 + B1 V2) renormalization(l1, l2). */
-COFFE_HD double di_ren_smooth_partial(const Renorm2DView &r2d, const double2 *los, const int los_n, const double los_inv_h, const Rules &q,
+template <class LP>
+COFFE_HD double di_ren_smooth_partial(const Renorm2DView &r2d, const LP los, const int los_n, const double los_inv_h, const Rules &q,
                                       const DIFast &f, const DIOuter &o, const int lane, const int nlanes)
 {
     const int half = q.n_ren / 2;
@@ -182,8 +183,8 @@ COFFE_HD PanelPlan di_plan(const Rules &q, const DIOuter &o)
     return panel_plan(e2 * ie, q.eps_min, q.panel_w_di, q.panel_du_di, q.tail_ratio_di, q.rpow_di, q.geo_shift_di, q.geo_L_di, q.tail_lnr_di, ie, q.inv_w_di, q.inv_geo_L_di);
 }
 
-template <bool ALL, class TA>
-COFFE_HD double di_inner_group(const DISideCtx<TA> &cx, const Rules &q, const DIFast &f, const DIOuter &o, const int j)
+template <bool ALL, class TA, class LP>
+COFFE_HD double di_inner_group(const DISideCtx<TA, LP> &cx, const Rules &q, const DIFast &f, const DIOuter &o, const int j)
 {
     const int np = q.n_panel_di;
     const double xj = q.panel_x ? q.panel_x[j] : q.gl_x[rule_offset(np) + j], wj = q.panel_w ? q.panel_w[j] : q.gl_w[rule_offset(np) + j];
@@ -214,14 +215,14 @@ COFFE_HD unsigned int di_inner_eval_count(const Rules &q, const DIFast &f, const
 /* integrated x integrated piece per unit (x1, x2): outer nodes strided over `ngroups` groups of n_panel lanes, `j` = this lane's node.
    The loop is uniform over the groups (a group without an outer node in the last round idles): no lane leaves early, so the device
    kernels may use warp-wide votes inside. */
-template <class TA>
-COFFE_HD double di_fast_partial(const TA &ta, const Tables &t, const double2 *los, const Rules &q, const Geometry &g, const DIConst &k,
+template <class TA, class LP>
+COFFE_HD double di_fast_partial(const TA &ta, const Tables &t, const LP los, const Rules &q, const Geometry &g, const DIConst &k,
                                 const int group, const int ngroups, const int j)
 {
     const DIFast f = di_fast_setup(k, g);
     const int n_outer = q.n_outer > 0 ? q.n_outer : auto_n_outer(g.sep, q.n_outer_min, q.n_outer_step, q.n_panel_di);
     const double *outer_x = q.gl_x + rule_offset(n_outer), *outer_w = q.gl_w + rule_offset(n_outer);
-    DISideCtx<TA> cx;
+    DISideCtx<TA, LP> cx;
     cx.ta = &ta; cx.los = los; cx.los_n = t.los.n; cx.los_inv_h = t.los.inv_h;
     cx.r2d = &t.ren2d;
     double acc = 0.0;

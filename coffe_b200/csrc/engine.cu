@@ -260,13 +260,13 @@ __global__ void __launch_bounds__(kSIThreads, 1) si_items_smem_kernel(
     const int grp = lane / np, j = lane - grp * np;
     const bool lane_on = grp < ppi;
     /* layout: [compact blob prefix][line-of-sight table][tail powers, panel rule][per-warp: ppi slots] */
-    double2 *los_s = reinterpret_cast<double2 *>(smem + stage_bytes);
-    double *small = reinterpret_cast<double *>(los_s + (size_t)kLosStride * los_stage_n);
+    LosRec *los_s = reinterpret_cast<LosRec *>(smem + stage_bytes);          /* one record per interval (tables.cuh) in the room of the knots */
+    double *small = reinterpret_cast<double *>(los_s + los_stage_n);
     SIGroupSlot *slots = reinterpret_cast<SIGroupSlot *>(small + kDISmallDoubles) + (size_t)warp * ppi;
     {
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
         for (int i = tid; i < stage_bytes / 16; i += kSIThreads) dst[i] = blob[i];
-        for (int i = tid; i < kLosStride * los_stage_n; i += kSIThreads) los_s[i] = t.los.v[i];
+        for (int i = tid; i + 1 < los_stage_n; i += kSIThreads) los_rec_pack(t.los.v + (size_t)kLosStride * i, t.los.v + (size_t)kLosStride * (i + 1), los_s[i]);
         if (tid < kMaxTail) small[tid] = q_in.rpow[tid];
         if (tid < np) {
             small[kMaxTail + tid] = q_in.gl_x[rule_offset(np) + tid];
@@ -277,8 +277,7 @@ __global__ void __launch_bounds__(kSIThreads, 1) si_items_smem_kernel(
     __syncthreads();
     CompactAccess ta;
     ta.t = &t; ta.c.base = smem; ta.c.h = ch;
-    LosView lv = t.los;
-    lv.v = los_s;
+    const LosView lv = t.los;           /* n and 1/h; the values are read from the staged records */
     Rules q = q_in;
     q.rpow = small;
     q.panel_x_si = small + kMaxTail; q.panel_w_si = small + kMaxTail + 32; q.panel_p_si = small + kMaxTail + 64;
@@ -336,7 +335,7 @@ __global__ void __launch_bounds__(kSIThreads, 1) si_items_smem_kernel(
         const unsigned int after = draw();
         double si = 0.0;
         if (valid) {
-            si = si_half_group(ta, t.ren2d, lv, q, slot.g, slot.h, los_s, j);
+            si = si_half_group(ta, t.ren2d, lv, q, slot.g, slot.h, (const LosRec *)los_s, j);
             if (out_evals && j == 0) atomicAdd(&out_evals[hh >> 1], si_group_eval_count(q, slot.g, slot.h));
         }
         /* sum over the lanes of the group: np <= 32 consecutive lanes */
@@ -373,12 +372,12 @@ __global__ void __launch_bounds__(kDIThreads, 1) di_items_smem_kernel(
     const int np = q.n_panel_di, ppi = 32 / np;             /* n_panel_di <= 32: the host checks */
     const int grp = lane / np, j = lane - grp * np;
     /* layout: [compact blob prefix][line-of-sight table][tail powers, panel rule] */
-    double2 *los_s = reinterpret_cast<double2 *>(smem + stage_bytes);
-    double *small = reinterpret_cast<double *>(los_s + (size_t)kLosStride * los_stage_n);
+    LosRec *los_s = reinterpret_cast<LosRec *>(smem + stage_bytes);
+    double *small = reinterpret_cast<double *>(los_s + los_stage_n);
     {
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
         for (int i = tid; i < stage_bytes / 16; i += n_threads) dst[i] = blob[i];
-        for (int i = tid; i < kLosStride * los_stage_n; i += n_threads) los_s[i] = t.los.v[i];
+        for (int i = tid; i + 1 < los_stage_n; i += n_threads) los_rec_pack(t.los.v + (size_t)kLosStride * i, t.los.v + (size_t)kLosStride * (i + 1), los_s[i]);
         if (tid < kMaxTail) small[tid] = q.rpow_di[tid];
         if (tid < np) {
             small[kMaxTail + tid] = q.gl_x[rule_offset(np) + tid];
@@ -403,7 +402,7 @@ __global__ void __launch_bounds__(kDIThreads, 1) di_items_smem_kernel(
         const Geometry g = geometry(bg_chi(t.bg, z), sep, mu);
         const DIConst k = item_setup[item].k;
         if (out_evals && lane == 0) out_evals[item] = di_fast_eval_count(ql, g, k);
-        double di = di_fast_partial(ta, t, los_s, ql, g, k, grp < ppi ? grp : ppi, ppi, j);
+        double di = di_fast_partial(ta, t, (const LosRec *)los_s, ql, g, k, grp < ppi ? grp : ppi, ppi, j);
         di = warp_sum(di);
         if (lane == 0) out[item] = di;
         __syncwarp();

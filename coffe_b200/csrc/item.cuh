@@ -165,7 +165,8 @@ COFFE_HD unsigned int si_eval_count(const Rules &q, const Geometry &g, const SIH
    renormalization(lambda, chi_source), the smooth half of the renormalised potential terms, is integrated apart on two
    Gauss-Legendre panels split at lambda = chi_source (the reasoning of di_fast.cuh: di_ren_smooth_partial): no column of the
    renormalisation grid per half in shared memory, which is what lets several halves share a warp. */
-COFFE_HD double si_ren_smooth_partial(const Renorm2DView &r2d, const double2 *los, const int los_n, const double los_inv_h, const Rules &q,
+template <class LP>
+COFFE_HD double si_ren_smooth_partial(const Renorm2DView &r2d, const LP los, const int los_n, const double los_inv_h, const Rules &q,
                                       const SIHalf &h, const int j, const int nlanes)
 {
     const int half = q.n_ren / 2;
@@ -190,9 +191,9 @@ COFFE_HD PanelPlan si_plan(const Rules &q, const Geometry &g, const SIHalf &h)
     return panel_plan(e2 * ie, q.eps_min, q.panel_w_mpc, q.panel_du, q.tail_ratio, q.rpow, 1, q.geo_L, q.tail_lnr, ie, q.inv_w, q.inv_geo_L);
 }
 
-template <class TA>
+template <class TA, class LP>
 COFFE_HD double si_half_group(const TA &t, const Renorm2DView &r2d, const LosView &lv, const Rules &q, const Geometry &g, const SIHalf &h,
-                              const double2 *los, const int j)
+                              const LP los, const int j)
 {
     const int np = q.n_panel_si;
     const double xj = q.panel_x_si ? q.panel_x_si[j] : q.gl_x[rule_offset(np) + j], wj = q.panel_w_si ? q.panel_w_si[j] : q.gl_w[rule_offset(np) + j];

@@ -283,6 +283,64 @@ COFFE_HD double4 los_eval(const double2 *v, const int n, const double inv_h, con
     return o;
 }
 
+/* The same table as the integration kernels stage it in shared memory: one 80-byte record per INTERVAL holding the cubic of each of the
+   four functions in t = lambda / h - j, constant term as a double, the three higher coefficients as floats (they describe the change
+   across one ~18 Mpc interval, a per cent of the value: 6e-8 of that).  A lookup reads one record instead of two knots, and the fields
+   are laid out so that the integrated x integrated piece (W, V, U) reads 16-byte words 0..3 and the local x integrated piece
+   (W, V, Wa) words 1..4: four loads per lookup instead of six.  Built from the Hermite knots by los_rec_pack. */
+struct alignas(16) LosRec {
+    double c0z; float c1z, c2z;             /* word 0 */
+    float c3z, c3x; double c0x;             /* word 1 */
+    double c0y; float c1x, c2x;             /* word 2 */
+    float c1y, c2y, c3y, c3w;               /* word 3 */
+    double c0w; float c1w, c2w;             /* word 4 */
+};
+static_assert(sizeof(LosRec) == 16 * kLosStride, "a record takes the room of a knot");
+
+COFFE_HD void los_rec_pack(const double2 *k0, const double2 *k1, LosRec &r)
+{
+    double c0[4], c1[4], c2[4], c3[4];
+    for (int f = 0; f < 4; ++f) {
+        const double f0 = k0[f].x, m0 = k0[f].y, f1 = k1[f].x, m1 = k1[f].y, df = f1 - f0;
+        c0[f] = f0; c1[f] = m0; c2[f] = 3.0 * df - 2.0 * m0 - m1; c3[f] = m0 + m1 - 2.0 * df;
+    }
+    r.c0x = c0[0]; r.c1x = (float)c1[0]; r.c2x = (float)c2[0]; r.c3x = (float)c3[0];
+    r.c0y = c0[1]; r.c1y = (float)c1[1]; r.c2y = (float)c2[1]; r.c3y = (float)c3[1];
+    r.c0z = c0[2]; r.c1z = (float)c1[2]; r.c2z = (float)c2[2]; r.c3z = (float)c3[2];
+    r.c0w = c0[3]; r.c1w = (float)c1[3]; r.c2w = (float)c2[3]; r.c3w = (float)c3[3];
+}
+
+COFFE_HD double los_cubic(const double c0, const float c1, const float c2, const float c3, const double t)
+{
+    return fma(fma(fma((double)c3, t, (double)c2), t, (double)c1), t, c0);
+}
+
+/* n = number of knots of the table the records were built from (n - 1 records) */
+COFFE_HD double4 los_eval(const LosRec *v, const int n, const double inv_h, const double lambda)
+{
+    const double s = lambda * inv_h;
+    int j = (int)s;
+    if (j < 0) j = 0;
+    if (j > n - 2) j = n - 2;
+    const double t = s - j;
+    double4 o;
+#if defined(__CUDA_ARCH__)
+    const int4 *p = reinterpret_cast<const int4 *>(v + j);
+    const int4 w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3], w4 = p[4];        /* the unused ones are dropped by the compiler */
+    o.x = los_cubic(__hiloint2double(w1.w, w1.z), __int_as_float(w2.z), __int_as_float(w2.w), __int_as_float(w1.y), t);
+    o.y = los_cubic(__hiloint2double(w2.y, w2.x), __int_as_float(w3.x), __int_as_float(w3.y), __int_as_float(w3.z), t);
+    o.z = los_cubic(__hiloint2double(w0.y, w0.x), __int_as_float(w0.z), __int_as_float(w0.w), __int_as_float(w1.x), t);
+    o.w = los_cubic(__hiloint2double(w4.y, w4.x), __int_as_float(w4.z), __int_as_float(w4.w), __int_as_float(w3.w), t);
+#else
+    const LosRec &r = v[j];
+    o.x = los_cubic(r.c0x, r.c1x, r.c2x, r.c3x, t);
+    o.y = los_cubic(r.c0y, r.c1y, r.c2y, r.c3y, t);
+    o.z = los_cubic(r.c0z, r.c1z, r.c2z, r.c3z, t);
+    o.w = los_cubic(r.c0w, r.c1w, r.c2w, r.c3w, t);
+#endif
+    return o;
+}
+
 /* ---- I^n_l(z, r) tables of the midpoint approximation (coffe_integral_t.result2d, src/integrals.c:663-767) ------------------
    GSL's bicubic interpolant on the (z, r) grid: per node {f, f_z, f_r, f_zr} (table_build.h: bicubic_nodes restates how GSL
    estimates the derivatives), evaluated with the Hermite patch of the cell; z knots uniform, r knots = the family's own.

@@ -23,6 +23,7 @@ struct HostSim {
     Options o;
     QuadConfig qc;
     std::vector<double> bx, bw, rpow, rpow_di;
+    std::vector<LosRec> los_rec;    /* the line-of-sight table as the shared-memory kernels stage it (tables.cuh) */
     Rules q;
     std::string err;
     CompactBuild cb;
@@ -69,6 +70,8 @@ void *hs_create(const coffe_b200_tables *T, const coffe_b200_options *opt)
     /* line-of-sight table */
     double2 *los = reinterpret_cast<double2 *>(s->arena.buf.data() + s->layout.los);
     for (int i = 0; i < s->layout.los_n; ++i) los_knot(s->t, i, s->layout.los_h, s->layout.chi_max_table, los + (size_t)kLosStride * i);
+    s->los_rec.resize(s->layout.los_n);
+    for (int i = 0; i + 1 < s->layout.los_n; ++i) los_rec_pack(los + (size_t)kLosStride * i, los + (size_t)kLosStride * (i + 1), s->los_rec[i]);
     Options &o = s->o;
     o.den = opt->den; o.rsd = opt->rsd; o.len = opt->len; o.d1 = opt->d1; o.d2 = opt->d2;
     o.g1 = opt->g1; o.g2 = opt->g2; o.g3 = opt->g3; o.g4 = opt->g4; o.g5 = opt->g5;
@@ -131,6 +134,15 @@ void hs_panel_plan(double eps, double eps_min, double W, double Du, double ratio
 /* the two closed forms the panel plan evaluates on the reciprocal square root (quadrature.cuh) */
 double hs_asinh_pos(double x) { return asinh_pos(x); }
 double hs_fourth_root_ratio(double up, double lo) { return fourth_root_ratio(up, lo); }
+
+/* the line-of-sight table at lambda through the Hermite knots (out[0..3]) and through the staged per-interval records (out[4..7]) */
+void hs_los_both(void *h, double lambda, double *out)
+{
+    HostSim *s = (HostSim *)h;
+    const double4 a = los_eval(s->t.los.v, s->t.los.n, s->t.los.inv_h, lambda);
+    const double4 b = los_eval((const LosRec *)s->los_rec.data(), s->t.los.n, s->t.los.inv_h, lambda);
+    out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w; out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w;
+}
 
 /* a slope as the packed knots store it (compact.cuh) */
 double hs_slope_rounded(double v) { return slope_rounded(v); }
@@ -236,7 +248,7 @@ static void item_pieces(void *h, double z, double sep, double mu, int mask, doub
         }
         else
             for (int j = 0; j < s->q.n_panel_si; ++j) {
-                if (s->variant) { const CompactAccess ca = s->compact(); acc += si_half_group(ca, s->t.ren2d, s->t.los, s->q, g, ha, s->t.los.v, j) + si_half_group(ca, s->t.ren2d, s->t.los, s->q, g, hb, s->t.los.v, j); }
+                if (s->variant) { const CompactAccess ca = s->compact(); const LosRec *lr = s->los_rec.data(); acc += si_half_group(ca, s->t.ren2d, s->t.los, s->q, g, ha, lr, j) + si_half_group(ca, s->t.ren2d, s->t.los, s->q, g, hb, lr, j); }
                 else { const ExactAccess ea{&s->t}; acc += si_half_group(ea, s->t.ren2d, s->t.los, s->q, g, ha, s->t.los.v, j) + si_half_group(ea, s->t.ren2d, s->t.los, s->q, g, hb, s->t.los.v, j); }
             }
         out[1] = acc;
@@ -255,7 +267,7 @@ static void item_pieces(void *h, double z, double sep, double mu, int mask, doub
             /* the kernel's lane decomposition: the n_panel lanes of one group in turn */
             double acc = 0.0;
             for (int j = 0; j < s->q.n_panel_di; ++j) {
-                if (s->variant) acc += di_fast_partial(s->compact(), s->t, s->t.los.v, s->q, g, k, 0, 1, j);
+                if (s->variant) acc += di_fast_partial(s->compact(), s->t, (const LosRec *)s->los_rec.data(), s->q, g, k, 0, 1, j);
                 else acc += di_fast_partial(ExactAccess{&s->t}, s->t, s->t.los.v, s->q, g, k, 0, 1, j);
             }
             out[2] = acc;

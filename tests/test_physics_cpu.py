@@ -78,6 +78,29 @@ def test_line_of_sight_resampling_error(ref, tableset):
             assert _rel(a, b) < 1e-6
 
 
+def test_line_of_sight_records_reproduce_the_hermite_knots(ref, tableset):
+    """tables.cuh LosRec: the per-interval cubic records the shared-memory kernels stage (constant term double, higher coefficients
+    float) against the Hermite knots they are built from: the same polynomial up to the float rounding of coefficients that describe
+    the change across one interval -- < 1e-8 of the largest value of each function, at the knots themselves exact"""
+    import ctypes as C
+    ref.set_contributions(list(ALL))
+    hs = hostsim_bridge.HostSim(ref, list(ALL), tableset=tableset)
+    hs.lib.hs_los_both.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double)]
+    out = np.zeros(8)
+    rng = np.random.default_rng(23)
+    chi_max = float(ref.comoving_distance(2.0)) if hasattr(ref, "comoving_distance") else 3500.0
+    lam = np.concatenate([rng.uniform(0.0, chi_max, 4000), [0.0, 1e-9, chi_max]])
+    vals = []
+    for l in lam:
+        hs.lib.hs_los_both(hs.h, float(l), out.ctypes.data_as(C.POINTER(C.c_double)))
+        vals.append(out.copy())
+    vals = np.array(vals)
+    scale = np.max(np.abs(vals[:, :4]), axis=0)
+    err = np.max(np.abs(vals[:, 4:] - vals[:, :4]), axis=0) / scale
+    assert np.all(err < 1e-8), err
+    assert np.all(vals[-3, 4:] == vals[-3, :4])           # lambda = 0: the constant terms are the knot values
+
+
 def test_fixed_node_rules_vs_converged_oracle_pointwise(ref, tableset):
     """2PCF pieces at fixed mu: default rules (hot-path arithmetic) vs high-order rule over reference integrands"""
     from oracle.converged import ConvergedOracle
