@@ -54,6 +54,10 @@ struct coffe_b200_ctx {
     int variant = 1;        /* 1 = shared-memory tables (default), 0 = exact tables through L1/L2 */
     int last_variant = -1;
     int n_sm = 0, smem_optin = 0;
+    /* pinned host buffer the results of a call land in (grown on demand): a device-to-host copy into pageable memory goes through the
+       driver's own staging buffer in chunks */
+    double *h_stage = nullptr;
+    size_t h_stage_cap = 0;
     /* timing of the last call */
     double last_ms = 0;
     int last_launches = 0;

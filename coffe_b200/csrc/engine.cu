@@ -622,12 +622,13 @@ int apply_quadrature(coffe_b200_ctx *ctx, const bool want_pieces)
 }
 
 /* host-side range check of one point: the reference aborts (non-finite integrand) outside the tables */
-int check_point(coffe_b200_ctx *ctx, const double z, const double sep, const bool need_renorm)
+/* chi = comoving distance to z when the caller has it (a grid call asks for the same redshift n_sep times), else < 0 */
+int check_point(coffe_b200_ctx *ctx, const double z, const double sep, const bool need_renorm, double chi = -1.0)
 {
     const Tables &t = ctx->t_host;
     const double zmax = t.bg.z[t.bg.n - 1];
     if (!(z > 0.0) || !(z < zmax) || !(sep > 0.0)) { ctx->err = "redshift or separation outside the background table"; return COFFE_B200_ERANGE; }
-    const double chi = bg_chi(t.bg, z);
+    if (chi < 0.0) chi = bg_chi(t.bg, z);
     if (!(chi - sep / 2. > 0.0)) { ctx->err = "separation larger than twice the comoving distance to z_mean"; return COFFE_B200_ERANGE; }
     if (!(chi + sep / 2. < ctx->layout.chi_max_table)) { ctx->err = "chi_mean + sep/2 outside the background table"; return COFFE_B200_ERANGE; }
     if (!(sep <= ctx->layout.r_max_table)) { ctx->err = "separation outside the I^n_l tables"; return COFFE_B200_ERANGE; }
@@ -964,12 +965,18 @@ int plan_build(coffe_b200_ctx *ctx, const double *z_mean, int n_z, const double 
     static const bool trace = std::getenv("COFFE_B200_TRACE") != nullptr;
     const auto t0 = std::chrono::steady_clock::now();
     auto ms_since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+    const bool ren_range = ren && renorm_range_needed(ctx->o);
+    const double z_table_max = ctx->t_host.bg.z[ctx->t_host.bg.n - 1];
+    long iz_at = -1;
+    double chi_at = -1.0;           /* comoving distance to the redshift of row iz_at: one lookup per row, not per point */
     for (long it = begin; it < end; ++it) {
-        const double z = z_mean[it / n_sep], s = sep[it % n_sep];
-        rc = check_point(ctx, z, s, ren && renorm_range_needed(ctx->o));
+        const long iz = it / n_sep;
+        const double z = z_mean[iz], s = sep[it - iz * n_sep];
+        if (iz != iz_at) { iz_at = iz; chi_at = (z > 0.0 && z < z_table_max) ? bg_chi(ctx->t_host.bg, z) : -1.0; }
+        rc = check_point(ctx, z, s, ren_range, chi_at);
         if (rc) return rc;
-        pz.push_back(z); psep.push_back(s); point_rule.push_back((int)(it % n_sep));
-        const double chi2 = bg_chi(ctx->t_host.bg, z) + s / 2.;
+        pz.push_back(z); psep.push_back(s); point_rule.push_back((int)(it - iz * n_sep));
+        const double chi2 = chi_at + s / 2.;
         if (chi2 > pl.b.chi_max) pl.b.chi_max = chi2;
     }
     const double t_check = ms_since();
@@ -1014,10 +1021,25 @@ int plan_sync(coffe_b200_plan &pl)
 int plan_fetch(coffe_b200_plan &pl, std::vector<double> &hm)
 {
     coffe_b200_ctx *ctx = pl.ctx;
-    hm.assign((size_t)pl.n * 3 * pl.ls.n, 0.0);
-    if (pl.n == 0) return COFFE_B200_OK;
-    CK(cudaMemcpyAsync(hm.data(), pl.b.pm.p, hm.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    const size_t n = (size_t)pl.n * 3 * pl.ls.n;
+    if (pl.n == 0) { hm.clear(); return COFFE_B200_OK; }
+    if (ctx->h_stage_cap < n) {
+        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+        ctx->h_stage = nullptr; ctx->h_stage_cap = 0;
+        const size_t cap = n + n / 4;
+        if (cudaMallocHost(reinterpret_cast<void **>(&ctx->h_stage), cap * sizeof(double)) == cudaSuccess) ctx->h_stage_cap = cap;
+        else { ctx->h_stage = nullptr; (void)cudaGetLastError(); }          /* no pinned memory to be had: copy into the vector itself */
+    }
+    if (ctx->h_stage) {
+        CK(cudaMemcpyAsync(ctx->h_stage, pl.b.pm.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        hm.assign(ctx->h_stage, ctx->h_stage + n);
+    }
+    else {
+        hm.assign(n, 0.0);
+        CK(cudaMemcpyAsync(hm.data(), pl.b.pm.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     return check_finite(ctx, hm.data(), hm.size());
 }
 
@@ -1151,6 +1173,7 @@ void coffe_b200_destroy(coffe_b200_ctx *ctx)
     if (ctx->d_rpow) cudaFree(ctx->d_rpow);
     if (ctx->d_rpow_di) cudaFree(ctx->d_rpow_di);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->d_blob) cudaFree(ctx->d_blob);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
